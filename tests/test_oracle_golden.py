@@ -1,0 +1,143 @@
+"""CPU: the oracle restatement (oracle/vsl_oracle.py) against the golden vectors that were produced by
+executing the reference's own source over the TF1 shim (tests/golden/make_golden.py).
+
+Same op order on the same torch-CPU kernels => the fp32 comparisons are bit-exact except where libm-level
+sin/cos enter (none here: both sides call torch.sin/cos)."""
+import torch
+
+from oracle import vsl_oracle as O
+from tests.conftest import rel_err
+
+WARP_CASES = ['warp_eular', 'warp_angleaxis', 'warp_v1_eular', 'warp_matrix_far', 'warp_identity',
+              'warp_eular_wild']
+
+
+def _functional(c, outs):
+    Rs = [c.R_img, c.R_coords, c.R_wmask, c.R_z]
+    n = 3 if 'z' not in c else 4
+    return sum((o * r.to(o.dtype)).sum() for o, r in zip(outs[:n], Rs))
+
+
+def test_warp_forward_bit_exact(golden):
+    for name in WARP_CASES:
+        c = golden[name]
+        outs = O.projective_inverse_warp(c.img, c.depth, c.pose, c.K, c.format)
+        assert torch.equal(outs[0], c.out), name
+        assert torch.equal(outs[1], c.coords), name
+        assert torch.equal(outs[2], c.wmask), name
+        if 'z' in c:
+            assert torch.equal(outs[3], c.z), name
+            assert torch.equal(outs[4], c.pose_mat), name
+
+
+def test_warp_gradients(golden):
+    for name in WARP_CASES:
+        c = golden[name]
+        for dt, tag, tol in ((torch.float32, 'f32', 1e-6), (torch.float64, 'f64', 1e-12)):
+            a = [c.img.to(dt).requires_grad_(), c.depth.to(dt).requires_grad_(), c.pose.to(dt).requires_grad_()]
+            outs = O.projective_inverse_warp(a[0], a[1], a[2], c.K.to(dt), c.format)
+            g = torch.autograd.grad(_functional(c, outs), a)
+            for got, key in zip(g, ('g_img_', 'g_depth_', 'g_pose_')):
+                assert rel_err(got, c[key + tag]) <= tol, (name, key, tag)
+
+
+def test_identity_pose_kat(golden):
+    c = golden['warp_identity']
+    out, coords, wmask, z, _ = O.projective_inverse_warp(c.img, c.depth, c.pose, c.K, 'matrix')
+    B, H, W, _ = c.img.shape
+    grid = O.meshgrid(B, H, W, is_homogeneous=False).permute(0, 2, 3, 1)
+    # K K^-1 p reproduces the fp32 grid to a few ulp; the warp reproduces the source to 1e-5
+    assert (coords - grid).abs().max() < 2e-4
+    assert (out - c.img).abs().max() < 2e-5 * 40
+    assert (wmask[:, :-1, :-1] - 1).abs().max() < 1e-4
+    assert torch.allclose(z.squeeze(3), c.depth)
+
+
+def test_pose(golden):
+    c = golden['pose']
+    for fmt in ('eular', 'angleaxis'):
+        assert torch.equal(O.pose_vec2mat(c.vec, fmt), c['mat_' + fmt])
+        for dt, tag, tol in ((torch.float32, 'f32', 1e-6), (torch.float64, 'f64', 1e-12)):
+            v = c.vec.to(dt).requires_grad_()
+            g, = torch.autograd.grad((O.pose_vec2mat(v, fmt) * c.R.to(dt)).sum(), v)
+            assert rel_err(g, c['g_%s_%s' % (fmt, tag)]) <= tol
+    assert float(c['g_eular_f64'][0, 3]) == 0.0 and float(c['g_eular_f64'][0, 4]) == 0.0  # clipped at +-pi
+    m0 = O.pose_vec2mat(torch.zeros(2, 6), 'angleaxis')
+    assert torch.isnan(m0[:, :3, :3]).all() and torch.isnan(c.mat_angleaxis_zero[:, :3, :3]).all()
+
+
+def test_sampler(golden):
+    for name in ('sampler_c3', 'sampler_c1'):
+        c = golden[name]
+        out, wm = O.bilinear_sampler(c.imgs, c.coords)
+        assert torch.equal(out, c.out) and torch.equal(wm, c.wmask)
+        assert float(wm.min()) >= 0.0 and float(wm.max()) <= 1.0 + 1e-6
+        for dt, tag, tol in ((torch.float32, 'f32', 1e-6), (torch.float64, 'f64', 1e-12)):
+            a, co = c.imgs.to(dt).requires_grad_(), c.coords.to(dt).requires_grad_()
+            o, w = O.bilinear_sampler(a, co)
+            gi, gc = torch.autograd.grad((o * c.R.to(dt)).sum() + (w * c.Rm.to(dt)).sum(), [a, co])
+            assert rel_err(gi, c['g_imgs_' + tag]) <= tol and rel_err(gc, c['g_coords_' + tag]) <= tol
+
+
+def test_sampler_border_semantics(golden):
+    """Zero padding, not clamping (utils.py:266-270): x = -1 and x = W give 0, x = -0.5 gives half."""
+    img = torch.arange(1.0, 7.0).reshape(1, 1, 6, 1)
+
+    def at(x):
+        return float(O.bilinear_sampler(img, torch.tensor([[[[x, 0.0]]]]))[0])
+    assert at(-1.0) == 0.0 and at(6.0) == 0.0 and at(-0.5) == 0.5 and at(5.5) == 3.0 and at(5.0) == 6.0
+
+
+def test_flow_and_consistency(golden):
+    c = golden['optflow']
+    assert torch.equal(O.optflow_warp(c.img, c.flowx, c.flowy), c.out)
+    c = golden['consist']
+    fx, fy = O.depth_optflow(c.coords)
+    assert torch.equal(fx, c.flowx) and torch.equal(fy, c.flowy)
+    assert torch.equal(O.consistent_depth_loss(c.src_depth, c.z, c.coords), c.err)
+
+
+def test_loss_terms(golden):
+    c = golden['terms']
+    for dt, tag, tol in ((torch.float32, 'f32', 1e-6), (torch.float64, 'f64', 1e-12)):
+        p, l = c.disp.to(dt).requires_grad_(), c.logits.to(dt).requires_grad_()
+        sm, smi = O.compute_smooth_loss(p), O.compute_smooth_loss(1.0 / p)
+        ex = O.compute_exp_reg_loss(l, O.get_reference_explain_mask(0, 2, 10, 14, dt))
+        assert rel_err(sm, c['smooth_' + tag]) <= tol and rel_err(smi, c['smooth_inv_' + tag]) <= tol
+        assert rel_err(ex, c['exp_' + tag]) <= tol
+        assert rel_err(torch.autograd.grad(sm, p)[0], c['g_smooth_' + tag]) <= tol
+        assert rel_err(torch.autograd.grad(smi, p)[0], c['g_smooth_inv_' + tag]) <= tol
+        assert rel_err(torch.autograd.grad(ex, l)[0], c['g_exp_' + tag]) <= tol
+    assert float(c.smooth_quad) == 8.0 and float(O.compute_smooth_loss(c.quad)) == 8.0
+    lin = torch.arange(20.0).reshape(1, 4, 5, 1) * 0.5 + 3
+    assert float(O.compute_smooth_loss(lin)) == 0.0 and float(O.compute_smooth_loss(torch.ones(1, 5, 5, 1))) == 0.0
+
+
+def test_pyramid_and_intrinsics(golden):
+    c = golden['pyramid']
+    for s in (1, 2, 3):
+        assert torch.equal(O.resize_area(c.img, 16 >> s, 24 >> s), c['l%d' % s])
+    assert torch.equal(O.multi_scale_intrinsics(c.K, 4), c.K_pyr)
+
+
+def test_composite_loss(golden):
+    for name in ('loss_sfm', 'loss_lr', 'loss_nomask'):
+        c = golden[name]
+        fl = c.flags
+        S, V = fl['num_scales'], fl['V']
+        flags = O.LossFlags(**{k: v for k, v in fl.items() if k not in ('mask', 'V')})
+        for dt, tag, tol in ((torch.float32, 'f32', 2e-6), (torch.float64, 'f64', 1e-12)):
+            xs = [c['x%d' % s].to(dt).requires_grad_() for s in range(S)]
+            ps = c.poses.to(dt).requires_grad_()
+            lgs = [c['logits%d' % s].to(dt).requires_grad_() for s in range(S)] if fl['mask'] else None
+            pixel, smooth, exp = O.view_synthesis_loss(
+                c.tgt.to(dt), [c['src%d' % v].to(dt) for v in range(V)], xs, ps, c.K_pyr.to(dt), lgs, None, flags)
+            assert rel_err(pixel, c['pixel_' + tag]) <= tol and rel_err(smooth, c['smooth_' + tag]) <= tol
+            if fl['mask']:
+                assert rel_err(exp, c['exp_' + tag]) <= tol
+            grads = torch.autograd.grad(pixel + smooth + exp, xs + [ps] + (lgs or []))
+            for s in range(S):
+                assert rel_err(grads[s], c['g_x%d_%s' % (s, tag)]) <= tol, (name, s, tag)
+                if fl['mask']:
+                    assert rel_err(grads[S + 1 + s], c['g_logits%d_%s' % (s, tag)]) <= tol
+            assert rel_err(grads[S], c['g_poses_' + tag]) <= tol
