@@ -1,0 +1,146 @@
+/* vsl.h -- C ABI of the B200-native view-synthesis-loss library (libvsl.so).
+ *
+ * The reference (wrlife/tf_depth_estimation) has no FFI: its "operator interface" for this path is a set
+ * of Python functions over framework tensors.  Each entry point below is what a binding for one of those
+ * functions would call; the citation gives the reference function it replaces (paths relative to the
+ * reference checkout).  INTEGRATION.md shows the reference-side stub for each.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to contiguous float32, layouts as in the reference (NHWC images,
+ *     [B,H,W] depth, [B,H,W,2] coords with x first, row-major 3x3 / 4x4 matrices);
+ *   - the caller owns every buffer, including the workspace (`ws`, size from the matching *_ws_bytes());
+ *     the library allocates nothing, frees nothing and keeps no global state;
+ *   - all work is enqueued on `stream` (a cudaStream_t); no call synchronises;
+ *   - return value: 0 = OK, < 0 = VSL_E_* argument error (nothing enqueued), > 0 = a raw cudaError_t;
+ *     no C++ exception crosses the boundary;
+ *   - nullable outputs are skipped when NULL;
+ *   - gather indices are exact integers for any size (the reference computes them in float32 and breaks
+ *     beyond 2^24 elements, utils.py:273-294).
+ */
+#ifndef VSL_H_
+#define VSL_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* vsl_stream_t; /* cudaStream_t */
+
+#define VSL_VERSION 100
+
+enum { VSL_POSE_EULER = 0, VSL_POSE_ANGLEAXIS = 1, VSL_POSE_MATRIX = 2 };
+
+enum {
+  VSL_OK = 0,
+  VSL_E_NULL = -1,      /* a required pointer is NULL            */
+  VSL_E_SHAPE = -2,     /* non-positive or unsupported dimension */
+  VSL_E_FORMAT = -3,    /* unknown pose format / mask mode       */
+  VSL_E_ALIGN = -4,     /* pointer not 4-byte (or required 16-byte) aligned */
+  VSL_E_UNSUPPORTED = -5
+};
+
+enum { VSL_MASK_NONE = 0, VSL_MASK_EXP = 1, VSL_MASK_CONST = 2 };
+
+#define VSL_MAX_SCALES 6
+#define VSL_MAX_VIEWS 4
+
+int vsl_version(void);
+const char* vsl_strerror(int code);
+
+/* ---- pose_vec2mat(vec[, format])  utils.py:79-98, utils_lr.py:106-149 (euler2mat utils.py:26-75,
+ *      axis_angle_to_rotation_matrix utils_lr.py:77-103).  format: EULER or ANGLEAXIS. */
+int vsl_pose_vec2mat_fwd(const float* vec /*[B,6]*/, int B, int format, float* mat /*[B,4,4]*/,
+                         vsl_stream_t stream);
+int vsl_pose_vec2mat_bwd(const float* vec, const float* g_mat /*[B,4,4]*/, int B, int format,
+                         float* g_vec /*[B,6]*/, vsl_stream_t stream);
+
+/* ---- projective_inverse_warp(img, depth, pose, intrinsics[, format])  utils.py:168-199,
+ *      utils_lr.py:222-256 (meshgrid :142-166, pixel2cam :100-119, cam2pixel :121-140, bilinear_sampler
+ *      :219-308 fused).  pose: [B,6] for EULER/ANGLEAXIS, [B,4,4] for MATRIX. */
+size_t vsl_warp_ws_bytes(int B, int H, int W);
+int vsl_warp_fwd(const float* img /*[B,H,W,C]*/, const float* depth /*[B,H,W]*/, const float* pose,
+                 const float* K /*[B,3,3]*/, int B, int H, int W, int C, int format,
+                 float* out_img /*[B,H,W,C] nullable*/, float* coords /*[B,H,W,2] nullable*/,
+                 float* wmask /*[B,H,W,1] nullable*/, float* src_depth /*[B,H,W,1] nullable*/,
+                 float* pose_mat /*[B,4,4] nullable*/, void* ws, vsl_stream_t stream);
+/* Backward of the above for upstream gradients of (out_img, coords, wmask, src_depth, pose_mat), each
+ * nullable.  g_img is accumulated with atomics (summation order not deterministic) and zeroed here first;
+ * g_depth and g_pose are deterministic.  g_pose has the shape of `pose`. */
+int vsl_warp_bwd(const float* img, const float* depth, const float* pose, const float* K, int B, int H,
+                 int W, int C, int format, const float* g_out_img, const float* g_coords,
+                 const float* g_wmask, const float* g_src_depth, const float* g_pose_mat,
+                 float* g_img /*nullable*/, float* g_depth /*[B,H,W] nullable*/, float* g_pose /*nullable*/,
+                 void* ws, vsl_stream_t stream);
+
+/* ---- bilinear_sampler(imgs, coords)  utils.py:219-308; also the core of optflow_warp (utils.py:201-217)
+ *      and consistent_depth_loss (utils_lr.py:369-458).  With flow != NULL the sampled coordinates are
+ *      meshgrid + flow (flowx, flowy as two [B,Ht,Wt,1] planes) instead of `coords`. */
+int vsl_bilinear_fwd(const float* imgs /*[B,Hs,Ws,C]*/, const float* coords /*[B,Ht,Wt,2] or NULL*/,
+                     const float* flowx, const float* flowy, int B, int Hs, int Ws, int C, int Ht, int Wt,
+                     float* out /*[B,Ht,Wt,C]*/, float* wmask /*[B,Ht,Wt,1] nullable*/,
+                     float* coords_out /*[B,Ht,Wt,2] nullable*/, vsl_stream_t stream);
+int vsl_bilinear_bwd(const float* imgs, const float* coords, const float* flowx, const float* flowy, int B,
+                     int Hs, int Ws, int C, int Ht, int Wt, const float* g_out, const float* g_wmask,
+                     float* g_imgs /*nullable, atomics*/, float* g_coords /*[B,Ht,Wt,2] nullable*/,
+                     vsl_stream_t stream);
+
+/* ---- depth_optflow(coords)  utils.py:321-338: flow = coords - meshgrid. */
+int vsl_depth_optflow(const float* coords /*[B,H,W,2]*/, int B, int H, int W, float* flowx, float* flowy,
+                      vsl_stream_t stream);
+
+/* ---- compute_smooth_loss(pred_disp)  my_losses.py:27-36.  x: [B,H,W,C].  With inverse != 0 the loss is
+ *      taken on 1/x (train_depth_then_cam_lr.py:217) and g_x is chained through the reciprocal.
+ *      loss: one device float.  g_loss: device float (upstream), NULL means 1. */
+size_t vsl_smooth_ws_bytes(int B, int H, int W, int C);
+int vsl_smooth_fwd(const float* x, int B, int H, int W, int C, int inverse, float* loss, void* ws,
+                   vsl_stream_t stream);
+int vsl_smooth_bwd(const float* x, int B, int H, int W, int C, int inverse, const float* g_loss, float* g_x,
+                   vsl_stream_t stream);
+
+/* ---- compute_exp_reg_loss(pred, ref=[0,1])  my_losses.py:14-23,39-43: mean softmax cross-entropy of
+ *      2-channel logits [N,2] against the constant label [0,1]. */
+size_t vsl_expreg_ws_bytes(long long N);
+int vsl_expreg_fwd(const float* logits, long long N, float* loss, void* ws, vsl_stream_t stream);
+int vsl_expreg_bwd(const float* logits, long long N, const float* g_loss, float* g_logits,
+                   vsl_stream_t stream);
+
+/* ---- tf.image.resize_area pyramid (integer factors), e.g. train_depth_then_cam_lr.py:227-232.
+ *      Writes levels 1..S-1 (H>>s x W>>s block means of level 0) of an NHWC image in one pass.
+ *      H and W must be divisible by 2^(S-1). */
+int vsl_pyramid(const float* img /*[B,H,W,C]*/, int B, int H, int W, int C, int S,
+                float* const* levels /*host array of S-1 device pointers*/, vsl_stream_t stream);
+
+/* ---- the fused multi-scale view-synthesis loss: the per-scale loop of train.py:107-135 with the
+ *      explainability mask of train_depth_then_cam_lr.py:297-328 (or a constant validity mask,
+ *      train_optflow_combine.py:176,187-188), forward AND backward in one pass over the data.
+ *
+ *      losses[3] = (pixel, smooth, exp); gradients are those of (pixel + smooth + exp) * loss_scale.  */
+typedef struct {
+  int B, H, W;           /* level-0 size; level s is (H>>s) x (W>>s) */
+  int S, V;              /* scales (<= VSL_MAX_SCALES), source views (<= VSL_MAX_VIEWS) */
+  int pose_format;       /* VSL_POSE_*: poses are [B,V,6] or [B,V,4,4] */
+  int mask_mode;         /* VSL_MASK_* */
+  int pixel_scale_norm;  /* data_weight / 2^s (train.py:135) or data_weight (train_depth_then_cam_lr.py:310) */
+  int depth_is_inverse;  /* warp depth = 1/x (train.py:128) or x */
+  int smooth_on_inverse; /* smoothness on 1/x (train_depth_then_cam_lr.py:217) or on x (train.py:108) */
+  float data_weight, smooth_weight, explain_reg_weight;
+  float loss_scale;      /* upstream gradient of the summed loss, folded into every gradient */
+} VslLossDesc;
+
+size_t vsl_loss_ws_bytes(const VslLossDesc* d);
+int vsl_loss_fwd_bwd(const VslLossDesc* d,
+                     const float* tgt /*[B,H,W,3]*/, const float* const* srcs /*host array V x [B,H,W,3]*/,
+                     const float* const* x_pyr /*host array S x [B,Hs,Ws,1]*/,
+                     const float* poses, const float* K_pyr /*[B,S,3,3]*/,
+                     const float* const* logits_pyr /*S x [B,Hs,Ws,2V], MASK_EXP*/,
+                     const float* const* mask_pyr /*S x [B,Hs,Ws,1], MASK_CONST*/,
+                     float* losses /*device [3]*/, float* const* g_x_pyr /*S x [B,Hs,Ws,1]*/,
+                     float* g_poses /*same shape as poses*/, float* const* g_logits_pyr /*S, MASK_EXP*/,
+                     void* ws, vsl_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VSL_H_ */

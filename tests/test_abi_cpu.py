@@ -1,0 +1,83 @@
+"""CPU: the C-ABI library loads, exports every symbol include/vsl.h declares, and validates arguments
+before touching a device (no compute calls here -- there is no GPU)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import __graft_entry__ as graft
+from tf_depth_estimation_b200 import _lib, ops
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='module')
+def lib():
+    graft.build()
+    return _lib.load()
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, 'include', 'vsl.h')).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    return sorted(set(re.findall(r'\b(vsl_[a-z0-9_]+)\s*\(', src)))
+
+
+def test_every_declared_symbol_is_exported_and_bound(lib):
+    syms = header_symbols()
+    assert len(syms) >= 19
+    for s in syms:
+        assert hasattr(lib, s), 'libvsl.so does not export %s' % s
+        assert s in _lib.SIGNATURES, 'binding lacks a prototype for %s' % s
+    assert sorted(_lib.SIGNATURES) == syms
+    assert lib.vsl_version() == 100
+
+
+def test_error_codes_without_a_device(lib):
+    assert lib.vsl_strerror(0) == b'ok'
+    assert lib.vsl_pose_vec2mat_fwd(None, 4, 0, None, None) == -1          # VSL_E_NULL
+    assert lib.vsl_pose_vec2mat_fwd(8, 0, 0, 8, None) == -2                # VSL_E_SHAPE
+    assert lib.vsl_pose_vec2mat_fwd(8, 4, 2, 8, None) == -3                # VSL_E_FORMAT (matrix is not a vector)
+    assert lib.vsl_warp_fwd(16, 16, 16, 16, 2, 8, 8, 5, 0, None, None, None, None, None, 16, None) == -2  # C = 5
+    assert lib.vsl_warp_fwd(16, 16, 16, 16, 2, 8, 8, 3, 7, None, None, None, None, None, 16, None) == -3
+    assert lib.vsl_warp_fwd(16, 16, 16, 16, 2, 8, 8, 3, 0, None, None, None, None, None, 20, None) == -4  # ws align
+    assert lib.vsl_smooth_fwd(16, 1, 2, 8, 1, 0, 16, 16, None) == -2       # H <= 2: no second difference
+    assert b'NULL' in lib.vsl_strerror(-1)
+    with pytest.raises(_lib.VslError):
+        _lib.check(-2)
+
+
+def test_loss_descriptor_validation_and_workspace(lib):
+    d = _lib.VslLossDesc(32, 128, 416, 4, 2, 0, 1, 1, 1, 0, 1.0, 0.5, 0.2, 1.0)
+    n = lib.vsl_loss_ws_bytes(ctypes.byref(d))
+    # pyramid levels 1..3 of (V+1) images dominate: 3 * 32*128*416*3*4 B * (1/4+1/16+1/64)
+    pyr = 3 * 32 * 128 * 416 * 3 * 4 * (1 / 4 + 1 / 16 + 1 / 64)
+    assert pyr < n < pyr * 1.1
+    bad = _lib.VslLossDesc(32, 100, 416, 4, 2, 0, 1, 1, 1, 0, 1.0, 0.5, 0.2, 1.0)   # 100 % 8 != 0
+    assert lib.vsl_loss_ws_bytes(ctypes.byref(bad)) == 0
+    bad = _lib.VslLossDesc(32, 128, 416, 4, 5, 0, 1, 1, 1, 0, 1.0, 0.5, 0.2, 1.0)   # V > VSL_MAX_VIEWS
+    assert lib.vsl_loss_ws_bytes(ctypes.byref(bad)) == 0
+    assert ctypes.sizeof(_lib.VslLossDesc) == 14 * 4
+
+
+def test_host_side_rejects_cpu_tensors_and_bad_shapes(lib):
+    img = torch.zeros(2, 8, 8, 3)
+    with pytest.raises(TypeError, match='no CPU fallback'):
+        ops.projective_inverse_warp(img, torch.ones(2, 8, 8), torch.zeros(2, 6), torch.eye(3).repeat(2, 1, 1))
+    with pytest.raises(ValueError):
+        ops.projective_inverse_warp(img, torch.ones(2, 8, 9), torch.zeros(2, 6), torch.eye(3).repeat(2, 1, 1))
+    with pytest.raises(ValueError):
+        ops.projective_inverse_warp(img, torch.ones(2, 8, 8), torch.zeros(2, 6), torch.eye(3).repeat(2, 1, 1), 'quat')
+    with pytest.raises(ValueError):
+        ops.pose_vec2mat(torch.zeros(2, 7))
+    with pytest.raises(ValueError):
+        ops.compute_exp_reg_loss(torch.zeros(2, 4, 4, 3))
+
+
+def test_missing_library_fails_loudly(monkeypatch, lib):
+    monkeypatch.setattr(_lib, '_lib', None)
+    monkeypatch.setattr(_lib, 'LIB_PATH', '/nonexistent/libvsl.so')
+    with pytest.raises(ImportError, match='no CPU or eager fallback'):
+        _lib.load()

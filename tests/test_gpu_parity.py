@@ -1,0 +1,312 @@
+"""GPU parity: the CUDA path, called through the C ABI (ctypes binding in tf_depth_estimation_b200/_lib.py),
+against (a) the committed golden vectors produced by executing the reference's source and (b) the CPU oracle
+on freshly seeded inputs.
+
+Tolerances are BASELINE.json's: warped images 1e-5 abs, forward losses 1e-5 rel, gradients 1e-4 rel
+(max-norm: max|a-b| / max|b|).  Where the pose is given as a matrix no transcendental enters and the sampled
+coordinates are required to be BIT-EXACT.  d(img) is accumulated with float atomics: its summation order is
+not deterministic, the tolerance covers it.
+"""
+import pytest
+import torch
+
+from oracle import vsl_oracle as O
+from tests.conftest import rel_err
+from tf_depth_estimation_b200 import ops, synth
+
+pytestmark = pytest.mark.gpu
+
+DEV = 'cuda:0'
+WARP_CASES = ['warp_eular', 'warp_angleaxis', 'warp_v1_eular', 'warp_matrix_far', 'warp_identity']
+
+
+def cu(t, grad=False):
+    return t.to(DEV).float().contiguous().requires_grad_(grad)
+
+
+def test_warp_forward_golden(golden):
+    for name in WARP_CASES:
+        c = golden[name]
+        out, coords, wmask, z, pose_mat = ops.projective_inverse_warp(cu(c.img), cu(c.depth), cu(c.pose), cu(c.K), c.format)
+        if c.format == 'matrix':
+            assert torch.equal(coords.cpu(), c.coords), name + ': coords must be bit-exact'
+            assert torch.equal(z.cpu(), c.z), name
+            assert torch.equal(wmask.cpu(), c.wmask), name
+            assert torch.equal(out.cpu(), c.out), name
+        else:
+            assert (coords.cpu() - c.coords).abs().max() < 2e-4, name
+        assert (out.cpu() - c.out).abs().max() <= 1e-5, (name, float((out.cpu() - c.out).abs().max()))
+        assert (wmask.cpu() - c.wmask).abs().max() <= 2e-4, name
+        if 'pose_mat' in c:
+            assert (pose_mat.cpu() - c.pose_mat).abs().max() <= 1e-6, name
+
+
+def test_warp_wild_pose_golden(golden):
+    """Near-90-degree rotation and a clipped Euler angle: points behind the camera / z ~ 0 are not special-cased
+    (utils.py:136).  Compare where the projection is well conditioned; everything must stay finite or NaN/Inf in
+    the same places."""
+    c = golden['warp_eular_wild']
+    out, coords, wmask, z, _ = ops.projective_inverse_warp(cu(c.img), cu(c.depth), cu(c.pose), cu(c.K), 'eular')
+    ok = (z.cpu().abs() > 1e-2).squeeze(3) & (c.coords.abs().amax(3) < 1e4)
+    assert ok.float().mean() > 0.9
+    assert ((coords.cpu() - c.coords).abs().amax(3)[ok] / c.coords.abs().amax(3)[ok].clamp_min(1.0)).max() < 1e-5
+    assert (out.cpu() - c.out).abs().amax(3)[ok].max() <= 1e-4
+
+
+def _warp_grads(c, wrt_img=True):
+    a = [cu(c.img, wrt_img), cu(c.depth, True), cu(c.pose, True)]
+    outs = ops.projective_inverse_warp(a[0], a[1], a[2], cu(c.K), c.format)
+    Rs = [c.R_img, c.R_coords, c.R_wmask, c.R_z]
+    n = 4 if 'z' in c else 3
+    L = sum((o * cu(r)).sum() for o, r in zip(outs[:n], Rs))
+    L.backward()
+    return a
+
+
+def test_warp_backward_golden(golden):
+    for name in WARP_CASES:
+        c = golden[name]
+        a = _warp_grads(c)
+        for t, key in zip(a, ('g_img_', 'g_depth_', 'g_pose_')):
+            e32, e64 = rel_err(t.grad, c[key + 'f32']), rel_err(t.grad, c[key + 'f64'])
+            assert min(e32, e64) <= 1e-4, (name, key, e32, e64)
+
+
+def test_pose_vec2mat_golden(golden):
+    c = golden['pose']
+    for fmt in ('eular', 'angleaxis'):
+        v = cu(c.vec, True)
+        m = ops.pose_vec2mat(v, fmt)
+        assert (m.cpu() - c['mat_' + fmt]).abs().max() <= 1e-6
+        (m * cu(c.R)).sum().backward()
+        assert rel_err(v.grad, c['g_%s_f64' % fmt]) <= 1e-5
+    assert float(v.grad[0, 3]) != 0  # angle-axis has no clip
+    v = cu(c.vec, True)
+    (ops.pose_vec2mat(v, 'eular') * cu(c.R)).sum().backward()
+    assert float(v.grad[0, 3]) == 0.0 and float(v.grad[0, 4]) == 0.0  # clipped at +-pi (utils.py:40-42)
+    m0 = ops.pose_vec2mat(torch.zeros(2, 6, device=DEV), 'angleaxis')
+    assert torch.isnan(m0[:, :3, :3]).all()  # reference behaviour: axis / 0 (utils_lr.py:133)
+
+
+def test_sampler_golden(golden):
+    for name in ('sampler_c3', 'sampler_c1'):
+        c = golden[name]
+        imgs, coords = cu(c.imgs, True), cu(c.coords, True)
+        out, wm = ops.bilinear_sampler(imgs, coords)
+        assert torch.equal(out.detach().cpu(), c.out) and torch.equal(wm.detach().cpu(), c.wmask), name
+        ((out * cu(c.R)).sum() + (wm * cu(c.Rm)).sum()).backward()
+        assert rel_err(imgs.grad, c.g_imgs_f64) <= 1e-5 and rel_err(coords.grad, c.g_coords_f64) <= 1e-5
+
+
+def test_flow_and_consistency_golden(golden):
+    c = golden['optflow']
+    assert torch.equal(ops.optflow_warp(cu(c.img), cu(c.flowx), cu(c.flowy)).cpu(), c.out)
+    c = golden['consist']
+    fx, fy = ops.depth_optflow(cu(c.coords))
+    assert torch.equal(fx.cpu(), c.flowx) and torch.equal(fy.cpu(), c.flowy)
+    err = ops.consistent_depth_loss(cu(c.src_depth), cu(c.z), cu(c.coords))
+    assert torch.equal(err.cpu(), c.err)
+
+
+def test_optflow_warp_gradients():
+    g = torch.Generator().manual_seed(5)
+    d = synth.make_snippets(2, 24, 32, S=1, V=1, seed=3)
+    fx, fy = 2 * torch.randn(2, 24, 32, 1, generator=g), 2 * torch.randn(2, 24, 32, 1, generator=g)
+    R = torch.randn(2, 24, 32, 3, generator=g)
+    a = [d['srcs'][0].double().requires_grad_(), fx.double().requires_grad_(), fy.double().requires_grad_()]
+    (O.optflow_warp(*a) * R.double()).sum().backward()
+    b = [cu(d['srcs'][0], True), cu(fx, True), cu(fy, True)]
+    (ops.optflow_warp(*b) * cu(R)).sum().backward()
+    for x, y in zip(a, b):
+        assert rel_err(y.grad, x.grad) <= 1e-4
+
+
+def test_loss_terms_golden(golden):
+    c = golden['terms']
+    for inverse, key in ((False, 'smooth'), (True, 'smooth_inv')):
+        p = cu(c.disp, True)
+        sm = ops.compute_smooth_loss(p, inverse=inverse)
+        assert rel_err(sm, c[key + '_f64']) <= 1e-5
+        sm.backward()
+        assert rel_err(p.grad, c['g_' + key + '_f64']) <= 1e-4
+    l = cu(c.logits, True)
+    ex = ops.compute_exp_reg_loss(l)
+    assert rel_err(ex, c.exp_f64) <= 1e-5
+    (3.0 * ex).backward()
+    assert rel_err(l.grad, 3.0 * c.g_exp_f64) <= 1e-4
+    assert float(ops.compute_smooth_loss(cu(c.quad))) == 8.0  # quadratic ramp KAT
+    lin = torch.arange(20.0).reshape(1, 4, 5, 1) * 0.5 + 3
+    assert float(ops.compute_smooth_loss(cu(lin))) == 0.0
+
+
+def test_pyramid_golden_bit_exact(golden):
+    c = golden['pyramid']
+    lv = ops.image_pyramid(cu(c.img), 4)
+    for s in (1, 2, 3):
+        assert torch.equal(lv[s].cpu(), c['l%d' % s])
+
+
+def _run_fused(c, fl, S, V):
+    flags = ops.LossFlags(**{k: v for k, v in fl.items() if k not in ('mask', 'V')})
+    xs = [cu(c['x%d' % s], True) for s in range(S)]
+    ps = cu(c.poses, True)
+    lgs = [cu(c['logits%d' % s], True) for s in range(S)] if fl['mask'] else None
+    total, losses = ops.view_synthesis_loss(cu(c.tgt), [cu(c['src%d' % v]) for v in range(V)], xs, ps, cu(c.K_pyr),
+                                            logits_pyr=lgs, flags=flags)
+    total.backward()
+    return losses, xs, ps, lgs
+
+
+def test_fused_loss_golden(golden):
+    for name in ('loss_sfm', 'loss_lr', 'loss_nomask'):
+        c = golden[name]
+        fl = c.flags
+        S, V = fl['num_scales'], fl['V']
+        losses, xs, ps, lgs = _run_fused(c, fl, S, V)
+        for i, key in enumerate(('pixel', 'smooth', 'exp')):
+            want = float(c[key + '_f64'])
+            assert abs(float(losses[i]) - want) <= 1e-5 * abs(want) + 1e-9, (name, key, float(losses[i]), want)
+        for s in range(S):
+            e = min(rel_err(xs[s].grad, c['g_x%d_f32' % s]), rel_err(xs[s].grad, c['g_x%d_f64' % s]))
+            assert e <= 1e-4, (name, 'g_x', s, e)
+            if fl['mask']:
+                assert rel_err(lgs[s].grad, c['g_logits%d_f64' % s]) <= 1e-4, (name, 'g_logits', s)
+        e = min(rel_err(ps.grad, c.g_poses_f32), rel_err(ps.grad, c.g_poses_f64))
+        assert e <= 1e-4, (name, 'g_poses', e)
+
+
+def test_fused_matches_unfused_composition():
+    """Fused kernel == the same loop assembled from the stand-alone ops (reference call signatures), at a
+    shape with ragged tiles (W not a multiple of 32, H not a multiple of 8 at the coarse scales)."""
+    B, H, W, S, V = 3, 40, 104, 3, 2
+    d = synth.make_snippets(B, H, W, S=S, V=V, seed=21, motion=2.0)
+    flags = ops.LossFlags(num_scales=S, pose_format='angleaxis', smooth_weight=0.7, data_weight=2.0,
+                          explain_reg_weight=0.3, pixel_scale_norm=False, smooth_on_inverse=True)
+    xs = [cu(x, True) for x in d['disp_pyr']]
+    ps = cu(d['poses'], True)
+    lgs = [cu(l, True) for l in d['logits_pyr']]
+    tgt, srcs, Kp = cu(d['tgt']), [cu(s) for s in d['srcs']], cu(d['K_pyr'])
+    total, losses = ops.view_synthesis_loss(tgt, srcs, xs, ps, Kp, logits_pyr=lgs, flags=flags)
+    total.backward()
+
+    xs2 = [cu(x, True) for x in d['disp_pyr']]
+    ps2 = cu(d['poses'], True)
+    lgs2 = [cu(l, True) for l in d['logits_pyr']]
+    tp, sp = ops.image_pyramid(tgt, S), [ops.image_pyramid(s, S) for s in srcs]
+    pixel = smooth = exp = 0
+    for s in range(S):
+        smooth = smooth + flags.smooth_weight / 2 ** s * ops.compute_smooth_loss(xs2[s], inverse=True)
+        for v in range(V):
+            warped = ops.projective_inverse_warp(sp[v][s], (1.0 / xs2[s]).squeeze(3), ps2[:, v].contiguous(),
+                                                 Kp[:, s].contiguous(), 'angleaxis')[0]
+            lg = lgs2[s][..., 2 * v:2 * v + 2].contiguous()
+            exp = exp + flags.explain_reg_weight * ops.compute_exp_reg_loss(lg)
+            m = torch.softmax(lg, -1)[..., 1:2]
+            pixel = pixel + ((warped - tp[s]).abs() * m).mean() * flags.data_weight
+    (pixel + smooth + exp).backward()
+    for got, want in zip(losses.tolist(), (float(pixel), float(smooth), float(exp))):
+        assert abs(got - want) <= 1e-5 * abs(want)
+    for s in range(S):
+        assert rel_err(xs[s].grad, xs2[s].grad) <= 1e-4
+        assert rel_err(lgs[s].grad, lgs2[s].grad) <= 1e-4
+    assert rel_err(ps.grad, ps2.grad) <= 1e-4
+
+
+def test_fused_against_oracle_fresh_inputs():
+    """Oracle (float64 autograd) on a freshly seeded cfg-shaped crop, both mask modes."""
+    B, H, W, S, V = 2, 32, 104, 4, 2
+    d = synth.make_snippets(B, H, W, S=S, V=V, seed=33)
+    for mode in ('exp', 'const', 'none'):
+        flags = ops.LossFlags(num_scales=S)
+        of = O.LossFlags(num_scales=S)
+        g = torch.Generator().manual_seed(3)
+        masks = [torch.rand(B, H >> s, W >> s, 1, generator=g) for s in range(S)]
+        xs = [cu(x, True) for x in d['disp_pyr']]
+        ps = cu(d['poses'], True)
+        lgs = [cu(l, True) for l in d['logits_pyr']] if mode == 'exp' else None
+        total, losses = ops.view_synthesis_loss(cu(d['tgt']), [cu(s) for s in d['srcs']], xs, ps, cu(d['K_pyr']),
+                                                logits_pyr=lgs, mask_pyr=[cu(m) for m in masks] if mode == 'const' else None,
+                                                flags=flags)
+        total.backward()
+        oxs = [x.double().requires_grad_() for x in d['disp_pyr']]
+        ops_ = d['poses'].double().requires_grad_()
+        ol = [l.double().requires_grad_() for l in d['logits_pyr']] if mode == 'exp' else None
+        ref = O.view_synthesis_loss(d['tgt'].double(), [s.double() for s in d['srcs']], oxs, ops_, d['K_pyr'].double(),
+                                    ol, [m.double() for m in masks] if mode == 'const' else None, of)
+        sum(ref).backward()
+        for got, want in zip(losses.tolist(), ref):
+            assert abs(got - float(want)) <= 1e-5 * abs(float(want)) + 1e-9, (mode, got, float(want))
+        assert rel_err(ps.grad, ops_.grad) <= 1e-4, mode
+        for s in range(S):
+            assert rel_err(xs[s].grad, oxs[s].grad) <= 1e-4, (mode, s)
+            if mode == 'exp':
+                assert rel_err(lgs[s].grad, ol[s].grad) <= 1e-4
+
+
+# ---------------------------------------------------------------------------------------- full size
+def _cfg2_inputs(seed=1234, B=32):
+    d = synth.make_snippets(B, 128, 416, S=4, V=2, seed=seed)
+    return d
+
+
+def test_full_size_properties_cfg2():
+    """BASELINE.json config 2 (B=32, 128x416, 4 scales, 2 views): size-independent properties."""
+    d = _cfg2_inputs()
+    img, depth = cu(d['srcs'][0]), cu((1.0 / d['disp_pyr'][0]).squeeze(3))
+    pose, K = cu(d['poses'][:, 0]), cu(d['K'])
+    # identity pose: coords == the reference's fp32 grid up to K K^-1 rounding, warp == src, wmask == 1
+    eye = torch.eye(4, device=DEV).repeat(32, 1, 1)
+    out, coords, wmask, z, _ = ops.projective_inverse_warp(img, depth, eye, K, 'matrix')
+    grid = O.meshgrid(1, 128, 416, is_homogeneous=False).permute(0, 2, 3, 1).to(DEV)
+    assert (coords - grid).abs().max() < 5e-4
+    assert (out - img).abs().max() <= 1e-4 and (wmask[:, :-1, :-1] - 1).abs().max() < 1e-3
+    assert torch.equal(z.squeeze(3), depth)
+    # linearity in the source image and wmask in [0, 1]
+    img2 = cu(d['srcs'][1])
+    o1 = ops.projective_inverse_warp(img, depth, pose, K)[0]
+    o2 = ops.projective_inverse_warp(img2, depth, pose, K)[0]
+    o12, _, wm, _, _ = ops.projective_inverse_warp(0.25 * img + 2.0 * img2, depth, pose, K)
+    assert (o12 - (0.25 * o1 + 2.0 * o2)).abs().max() <= 1e-5
+    assert float(wm.min()) >= 0.0 and float(wm.max()) <= 1.0 + 1e-6
+    # pure x translation with constant depth: uniform shift of fx * tx / d pixels
+    tx, dconst = 0.05, 2.0
+    T = torch.eye(4, device=DEV).repeat(32, 1, 1)
+    T[:, 0, 3] = tx
+    c2 = ops.projective_inverse_warp(img, torch.full_like(depth, dconst), T, K, 'matrix')[1]
+    shift = float(K[0, 0, 0]) * tx / dconst
+    assert (c2[..., 0] - (grid[..., 0] + shift)).abs().max() < 1e-3 and (c2[..., 1] - grid[..., 1]).abs().max() < 1e-3
+
+
+def test_full_size_fused_batch_shards_and_determinism():
+    """The path shards over the batch: the fused loss of the whole batch equals the sum over two
+    half-batch ranks of (loss * 1/2), per-sample gradients agree, and two runs are bit-identical."""
+    d = _cfg2_inputs(seed=99)
+    flags = ops.LossFlags()
+    dev_in = dict(tgt=cu(d['tgt']), srcs=[cu(s) for s in d['srcs']], xs=[cu(x) for x in d['disp_pyr']],
+                  poses=cu(d['poses']), Kp=cu(d['K_pyr']), lgs=[cu(l) for l in d['logits_pyr']])
+
+    def run(lo, hi):
+        plan = ops.ViewSynthesisPlan(hi - lo, 128, 416, 2, flags, 1, torch.device(DEV))
+        sl = lambda t: t[lo:hi].contiguous()
+        plan.run(sl(dev_in['tgt']), [sl(s) for s in dev_in['srcs']], [sl(x) for x in dev_in['xs']],
+                 sl(dev_in['poses']), sl(dev_in['Kp']), [sl(l) for l in dev_in['lgs']])
+        torch.cuda.synchronize()
+        return plan
+
+    whole, again = run(0, 32), run(0, 32)
+    assert torch.equal(whole.losses, again.losses) and torch.equal(whole.g_poses, again.g_poses)
+    assert all(torch.equal(a, b) for a, b in zip(whole.g_x, again.g_x))
+    h0, h1 = run(0, 16), run(16, 32)
+    assert rel_err(0.5 * (h0.losses + h1.losses), whole.losses) <= 1e-6
+    # means are over the local batch, so a rank's gradients are 2x the global ones
+    assert rel_err(torch.cat([h0.g_poses, h1.g_poses]) * 0.5, whole.g_poses) <= 1e-5
+    assert rel_err(torch.cat([h0.g_x[0], h1.g_x[0]]) * 0.5, whole.g_x[0]) <= 1e-5
+    assert rel_err(torch.cat([h0.g_logits[1], h1.g_logits[1]]) * 0.5, whole.g_logits[1]) <= 1e-5
+
+
+def test_no_cpu_fallback():
+    d = synth.make_snippets(1, 16, 32, S=1, V=1, seed=1)
+    with pytest.raises(TypeError):
+        ops.bilinear_sampler(d['srcs'][0], torch.zeros(1, 16, 32, 2))
+    with pytest.raises(TypeError):
+        ops.compute_smooth_loss(d['disp_pyr'][0].double().to(DEV))

@@ -1,0 +1,684 @@
+// libvsl: the reference's geometry / sampler / loss-term functions as stand-alone sm_100a kernels
+// (one launch per reference function; the multi-scale fused path lives in vsl_loss.cu).
+#include "vsl_common.cuh"
+
+namespace vsl {
+
+// =====================================================================================================
+// pose_vec2mat  (utils.py:79-98, utils_lr.py:106-149)
+// =====================================================================================================
+__global__ void pose_fwd_kernel(const float* __restrict__ vec, int B, int format, float* __restrict__ mat) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float T[16];
+  pose_to_mat(vec + b * 6, format, T);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) mat[b * 16 + i] = T[i];
+}
+
+__global__ void pose_bwd_kernel(const float* __restrict__ vec, const float* __restrict__ g_mat, int B,
+                                int format, float* __restrict__ g_vec) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  double gT[16];
+  for (int i = 0; i < 16; ++i) gT[i] = g_mat[b * 16 + i];
+  float g[6];
+  pose_vec_grad(vec + b * 6, format, gT, g);
+  for (int i = 0; i < 6; ++i) g_vec[b * 6 + i] = g[i];
+}
+
+// Per (scale, view, batch) transform table: K_s^-1 and rows 0..2 of K4_s . T_v.
+// xf[(s*V + v)*B + b];  K_pyr is [B,S,3,3];  poses is [B,V,6] or [B,V,4,4].
+__global__ void prep_xforms_kernel(const float* __restrict__ poses, const float* __restrict__ K_pyr, int B,
+                                   int S, int V, int format, Xform* __restrict__ xf,
+                                   float* __restrict__ pose_mat /*[B,V,4,4] nullable*/) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= S * V * B) return;
+  int b = idx % B, v = (idx / B) % V, s = idx / (B * V);
+  const int psz = (format == VSL_POSE_MATRIX) ? 16 : 6;
+  float T[16], K[9];
+  pose_to_mat(poses + (size_t)(b * V + v) * psz, format, T);
+#pragma unroll
+  for (int i = 0; i < 9; ++i) K[i] = K_pyr[(size_t)(b * S + s) * 9 + i];
+  Xform o;
+  inv3_lu(K, o.kinv);
+  proj_rows(K, T, o.p);
+  xf[idx] = o;
+  if (pose_mat != nullptr && s == 0)
+    for (int i = 0; i < 16; ++i) pose_mat[(size_t)(b * V + v) * 16 + i] = T[i];
+}
+
+// =====================================================================================================
+// projective_inverse_warp  (utils.py:168-199, utils_lr.py:222-256)
+// grid = (ceil(H*W / 256), B); one thread per target pixel.
+// =====================================================================================================
+template <int C>
+__global__ void __launch_bounds__(256)
+warp_fwd_kernel(const float* __restrict__ img, const float* __restrict__ depth, const Xform* __restrict__ xf,
+                int H, int W, float* __restrict__ out, float* __restrict__ coords, float* __restrict__ wmask,
+                float* __restrict__ zout) {
+  __shared__ Xform sx;
+  const int b = blockIdx.y;
+  if (threadIdx.x < 21) reinterpret_cast<float*>(&sx)[threadIdx.x] = reinterpret_cast<const float*>(xf + b)[threadIdx.x];
+  __syncthreads();
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= H * W) return;
+  const int i = pix / W, j = pix - i * W;
+  const size_t gp = (size_t)b * H * W + pix;
+  const float gx = grid_coord(j, W, grid_step(W)), gy = grid_coord(i, H, grid_step(H));
+  const float d = depth[gp];
+  Ray r = back_project(sx.kinv, gx, gy);
+  Proj q = project(sx.p, __fmul_rn(r.r0, d), __fmul_rn(r.r1, d), __fmul_rn(r.r2, d));
+  Foot f = footprint(q.x, q.y, W, H);
+  const float w00 = __fmul_rn(f.wx0, f.wy0), w01 = __fmul_rn(f.wx0, f.wy1), w10 = __fmul_rn(f.wx1, f.wy0),
+              w11 = __fmul_rn(f.wx1, f.wy1);
+  if (out != nullptr) {
+    const float* base = img + (size_t)b * H * W * C;
+    const float* p00 = base + ((size_t)f.y0 * W + f.x0) * C;
+    const float* p01 = base + ((size_t)f.y1 * W + f.x0) * C;
+    const float* p10 = base + ((size_t)f.y0 * W + f.x1) * C;
+    const float* p11 = base + ((size_t)f.y1 * W + f.x1) * C;
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+      out[gp * C + c] = blend(w00, w01, w10, w11, __ldg(p00 + c), __ldg(p01 + c), __ldg(p10 + c), __ldg(p11 + c));
+  }
+  if (coords != nullptr) reinterpret_cast<float2*>(coords)[gp] = make_float2(q.x, q.y);
+  if (wmask != nullptr) wmask[gp] = __fadd_rn(__fadd_rn(__fadd_rn(w00, w01), w10), w11);
+  if (zout != nullptr) zout[gp] = q.z;
+}
+
+// Backward.  Per pixel: d(coords) from the four upstream gradients, then du, d(depth), and a block
+// partial of dP = sum du (x) [cam;1] written to partial[(b*nblk + blk)*12 ..].
+template <int C>
+__global__ void __launch_bounds__(256)
+warp_bwd_kernel(const float* __restrict__ img, const float* __restrict__ depth, const Xform* __restrict__ xf,
+                int H, int W, const float* __restrict__ g_out, const float* __restrict__ g_coords,
+                const float* __restrict__ g_wmask, const float* __restrict__ g_z, float* __restrict__ g_img,
+                float* __restrict__ g_depth, float* __restrict__ partial) {
+  __shared__ Xform sx;
+  __shared__ float scratch[12 * 8];
+  const int b = blockIdx.y;
+  if (threadIdx.x < 21) reinterpret_cast<float*>(&sx)[threadIdx.x] = reinterpret_cast<const float*>(xf + b)[threadIdx.x];
+  __syncthreads();
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  float acc[12];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) acc[k] = 0.f;
+  if (pix < H * W) {
+    const int i = pix / W, j = pix - i * W;
+    const size_t gp = (size_t)b * H * W + pix;
+    const float gx = grid_coord(j, W, grid_step(W)), gy = grid_coord(i, H, grid_step(H));
+    const float d = depth[gp];
+    Ray r = back_project(sx.kinv, gx, gy);
+    const float c0 = __fmul_rn(r.r0, d), c1 = __fmul_rn(r.r1, d), c2 = __fmul_rn(r.r2, d);
+    Proj q = project(sx.p, c0, c1, c2);
+    Foot f = footprint(q.x, q.y, W, H);
+    float dx = 0.f, dy = 0.f;
+    if (g_out != nullptr) {
+      const size_t ib = (size_t)b * H * W * C;
+      const size_t o00 = ib + ((size_t)f.y0 * W + f.x0) * C, o01 = ib + ((size_t)f.y1 * W + f.x0) * C;
+      const size_t o10 = ib + ((size_t)f.y0 * W + f.x1) * C, o11 = ib + ((size_t)f.y1 * W + f.x1) * C;
+      const float w00 = f.wx0 * f.wy0, w01 = f.wx0 * f.wy1, w10 = f.wx1 * f.wy0, w11 = f.wx1 * f.wy1;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const float g = g_out[gp * C + c];
+        const float i00 = __ldg(img + o00 + c), i01 = __ldg(img + o01 + c), i10 = __ldg(img + o10 + c),
+                    i11 = __ldg(img + o11 + c);
+        dx += g * (f.wy0 * (f.mx1 * i10 - f.mx0 * i00) + f.wy1 * (f.mx1 * i11 - f.mx0 * i01));
+        dy += g * (f.wx0 * (f.my1 * i01 - f.my0 * i00) + f.wx1 * (f.my1 * i11 - f.my0 * i10));
+        if (g_img != nullptr) {
+          if (w00 != 0.f) atomicAdd(g_img + o00 + c, w00 * g);
+          if (w01 != 0.f) atomicAdd(g_img + o01 + c, w01 * g);
+          if (w10 != 0.f) atomicAdd(g_img + o10 + c, w10 * g);
+          if (w11 != 0.f) atomicAdd(g_img + o11 + c, w11 * g);
+        }
+      }
+    }
+    if (g_wmask != nullptr) {
+      const float g = g_wmask[gp];
+      dx += g * (f.wy0 + f.wy1) * (f.mx1 - f.mx0);
+      dy += g * (f.wx0 + f.wx1) * (f.my1 - f.my0);
+    }
+    if (g_coords != nullptr) {
+      float2 gc = reinterpret_cast<const float2*>(g_coords)[gp];
+      dx += gc.x;
+      dy += gc.y;
+    }
+    const float du0 = dx / q.zp, du1 = dy / q.zp;
+    float du2 = -(q.x * du0 + q.y * du1);
+    if (g_z != nullptr) du2 += g_z[gp];
+    if (g_depth != nullptr) {
+      const float gc0 = du0 * sx.p[0] + du1 * sx.p[4] + du2 * sx.p[8];
+      const float gc1 = du0 * sx.p[1] + du1 * sx.p[5] + du2 * sx.p[9];
+      const float gc2 = du0 * sx.p[2] + du1 * sx.p[6] + du2 * sx.p[10];
+      g_depth[gp] = gc0 * r.r0 + gc1 * r.r1 + gc2 * r.r2;
+    }
+    acc[0] = du0 * c0; acc[1] = du0 * c1; acc[2] = du0 * c2; acc[3] = du0;
+    acc[4] = du1 * c0; acc[5] = du1 * c1; acc[6] = du1 * c2; acc[7] = du1;
+    acc[8] = du2 * c0; acc[9] = du2 * c1; acc[10] = du2 * c2; acc[11] = du2;
+  }
+  if (partial != nullptr) block_sum<12>(acc, scratch, partial + ((size_t)b * gridDim.x + blockIdx.x) * 12);
+}
+
+// One warp per batch element: fixed-order sum of the block partials, dT = K4^T dP (+ upstream dT), then the
+// pose parameterisation's chain rule.
+__global__ void warp_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, const float* __restrict__ pose,
+                                         const float* __restrict__ K, const float* __restrict__ g_pose_mat,
+                                         int B, int format, float* __restrict__ g_pose) {
+  const int b = blockIdx.x, lane = threadIdx.x;
+  double s[12];
+  for (int k = 0; k < 12; ++k) s[k] = 0.0;
+  for (int i = lane; i < nblk; i += 32)
+    for (int k = 0; k < 12; ++k) s[k] += (double)partial[((size_t)b * nblk + i) * 12 + k];
+  for (int k = 0; k < 12; ++k)
+    for (int o = 16; o > 0; o >>= 1) s[k] += __shfl_xor_sync(0xffffffffu, s[k], o);
+  if (lane != 0) return;
+  double gT[16];
+  const float* Kb = K + (size_t)b * 9;
+  for (int k = 0; k < 3; ++k)
+    for (int j = 0; j < 4; ++j)
+      gT[k * 4 + j] = (double)Kb[k] * s[j] + (double)Kb[3 + k] * s[4 + j] + (double)Kb[6 + k] * s[8 + j];
+  for (int j = 0; j < 4; ++j) gT[12 + j] = 0.0;
+  if (g_pose_mat != nullptr)
+    for (int i = 0; i < 16; ++i) gT[i] += (double)g_pose_mat[(size_t)b * 16 + i];
+  if (format == VSL_POSE_MATRIX) {
+    for (int i = 0; i < 16; ++i) g_pose[(size_t)b * 16 + i] = (float)gT[i];
+  } else {
+    float g[6];
+    pose_vec_grad(pose + (size_t)b * 6, format, gT, g);
+    for (int i = 0; i < 6; ++i) g_pose[(size_t)b * 6 + i] = g[i];
+  }
+}
+
+// =====================================================================================================
+// bilinear_sampler  (utils.py:219-308); coordinates either given or meshgrid + flow (utils.py:201-217)
+// =====================================================================================================
+VSL_DEV float2 sample_coords(const float* coords, const float* flowx, const float* flowy, size_t gp, int i,
+                             int j, int Ht, int Wt) {
+  if (flowx != nullptr)
+    return make_float2(__fadd_rn(grid_coord(j, Wt, grid_step(Wt)), flowx[gp]),
+                       __fadd_rn(grid_coord(i, Ht, grid_step(Ht)), flowy[gp]));
+  return reinterpret_cast<const float2*>(coords)[gp];
+}
+
+template <int C>
+__global__ void __launch_bounds__(256)
+bilinear_fwd_kernel(const float* __restrict__ imgs, const float* __restrict__ coords,
+                    const float* __restrict__ flowx, const float* __restrict__ flowy, int Hs, int Ws, int Ht,
+                    int Wt, float* __restrict__ out, float* __restrict__ wmask, float* __restrict__ coords_out) {
+  const int b = blockIdx.y, pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= Ht * Wt) return;
+  const int i = pix / Wt, j = pix - i * Wt;
+  const size_t gp = (size_t)b * Ht * Wt + pix;
+  const float2 xy = sample_coords(coords, flowx, flowy, gp, i, j, Ht, Wt);
+  Foot f = footprint(xy.x, xy.y, Ws, Hs);
+  const float w00 = __fmul_rn(f.wx0, f.wy0), w01 = __fmul_rn(f.wx0, f.wy1), w10 = __fmul_rn(f.wx1, f.wy0),
+              w11 = __fmul_rn(f.wx1, f.wy1);
+  const float* base = imgs + (size_t)b * Hs * Ws * C;
+  const float* p00 = base + ((size_t)f.y0 * Ws + f.x0) * C;
+  const float* p01 = base + ((size_t)f.y1 * Ws + f.x0) * C;
+  const float* p10 = base + ((size_t)f.y0 * Ws + f.x1) * C;
+  const float* p11 = base + ((size_t)f.y1 * Ws + f.x1) * C;
+#pragma unroll
+  for (int c = 0; c < C; ++c)
+    out[gp * C + c] = blend(w00, w01, w10, w11, __ldg(p00 + c), __ldg(p01 + c), __ldg(p10 + c), __ldg(p11 + c));
+  if (wmask != nullptr) wmask[gp] = __fadd_rn(__fadd_rn(__fadd_rn(w00, w01), w10), w11);
+  if (coords_out != nullptr) reinterpret_cast<float2*>(coords_out)[gp] = xy;
+}
+
+template <int C>
+__global__ void __launch_bounds__(256)
+bilinear_bwd_kernel(const float* __restrict__ imgs, const float* __restrict__ coords,
+                    const float* __restrict__ flowx, const float* __restrict__ flowy, int Hs, int Ws, int Ht,
+                    int Wt, const float* __restrict__ g_out, const float* __restrict__ g_wmask,
+                    float* __restrict__ g_imgs, float* __restrict__ g_coords) {
+  const int b = blockIdx.y, pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= Ht * Wt) return;
+  const int i = pix / Wt, j = pix - i * Wt;
+  const size_t gp = (size_t)b * Ht * Wt + pix;
+  const float2 xy = sample_coords(coords, flowx, flowy, gp, i, j, Ht, Wt);
+  Foot f = footprint(xy.x, xy.y, Ws, Hs);
+  const size_t ib = (size_t)b * Hs * Ws * C;
+  const size_t o00 = ib + ((size_t)f.y0 * Ws + f.x0) * C, o01 = ib + ((size_t)f.y1 * Ws + f.x0) * C;
+  const size_t o10 = ib + ((size_t)f.y0 * Ws + f.x1) * C, o11 = ib + ((size_t)f.y1 * Ws + f.x1) * C;
+  const float w00 = f.wx0 * f.wy0, w01 = f.wx0 * f.wy1, w10 = f.wx1 * f.wy0, w11 = f.wx1 * f.wy1;
+  float dx = 0.f, dy = 0.f;
+  if (g_out != nullptr) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float g = g_out[gp * C + c];
+      const float i00 = __ldg(imgs + o00 + c), i01 = __ldg(imgs + o01 + c), i10 = __ldg(imgs + o10 + c),
+                  i11 = __ldg(imgs + o11 + c);
+      dx += g * (f.wy0 * (f.mx1 * i10 - f.mx0 * i00) + f.wy1 * (f.mx1 * i11 - f.mx0 * i01));
+      dy += g * (f.wx0 * (f.my1 * i01 - f.my0 * i00) + f.wx1 * (f.my1 * i11 - f.my0 * i10));
+      if (g_imgs != nullptr) {
+        if (w00 != 0.f) atomicAdd(g_imgs + o00 + c, w00 * g);
+        if (w01 != 0.f) atomicAdd(g_imgs + o01 + c, w01 * g);
+        if (w10 != 0.f) atomicAdd(g_imgs + o10 + c, w10 * g);
+        if (w11 != 0.f) atomicAdd(g_imgs + o11 + c, w11 * g);
+      }
+    }
+  }
+  if (g_wmask != nullptr) {
+    const float g = g_wmask[gp];
+    dx += g * (f.wy0 + f.wy1) * (f.mx1 - f.mx0);
+    dy += g * (f.wx0 + f.wx1) * (f.my1 - f.my0);
+  }
+  if (g_coords != nullptr) reinterpret_cast<float2*>(g_coords)[gp] = make_float2(dx, dy);
+}
+
+__global__ void depth_optflow_kernel(const float* __restrict__ coords, int H, int W, size_t n,
+                                     float* __restrict__ flowx, float* __restrict__ flowy) {
+  size_t gp = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gp >= n) return;
+  const int pix = (int)(gp % ((size_t)H * W)), i = pix / W, j = pix - i * W;
+  float2 c = reinterpret_cast<const float2*>(coords)[gp];
+  flowx[gp] = __fsub_rn(c.x, grid_coord(j, W, grid_step(W)));
+  flowy[gp] = __fsub_rn(c.y, grid_coord(i, H, grid_step(H)));
+}
+
+// =====================================================================================================
+// compute_smooth_loss  (my_losses.py:27-36).  x is [B,H,W,C]; the stencil runs over (H,W) per channel.
+// Each second difference is owned by its top-left element, so it is counted exactly once.
+// =====================================================================================================
+struct SmoothDims {
+  int B, H, W, C, inverse;
+  float c_xx, c_xy, c_yx, c_yy;  // weight / element count of each of the four means
+};
+
+VSL_DEV float smooth_q(const float* x, int inverse, size_t idx) {
+  float v = x[idx];
+  return inverse ? __fdiv_rn(1.0f, v) : v;
+}
+
+__global__ void __launch_bounds__(256)
+smooth_fwd_kernel(const float* __restrict__ x, SmoothDims d, float* __restrict__ partial) {
+  __shared__ float scratch[8];
+  const size_t n = (size_t)d.B * d.H * d.W * d.C;
+  float acc[1] = {0.f};
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(e % d.C);
+    const size_t p = e / d.C;
+    const int j = (int)(p % d.W), i = (int)((p / d.W) % d.H);
+    const size_t sx = d.C, sy = (size_t)d.W * d.C;
+    (void)c;
+    const float q00 = smooth_q(x, d.inverse, e);
+    float s = 0.f;
+    if (j + 2 < d.W) {
+      const float q01 = smooth_q(x, d.inverse, e + sx), q02 = smooth_q(x, d.inverse, e + 2 * sx);
+      s += d.c_xx * fabsf(__fsub_rn(__fsub_rn(q02, q01), __fsub_rn(q01, q00)));
+    }
+    if (i + 2 < d.H) {
+      const float q10 = smooth_q(x, d.inverse, e + sy), q20 = smooth_q(x, d.inverse, e + 2 * sy);
+      s += d.c_yy * fabsf(__fsub_rn(__fsub_rn(q20, q10), __fsub_rn(q10, q00)));
+    }
+    if (i + 1 < d.H && j + 1 < d.W) {
+      const float q01 = smooth_q(x, d.inverse, e + sx), q10 = smooth_q(x, d.inverse, e + sy),
+                  q11 = smooth_q(x, d.inverse, e + sy + sx);
+      s += d.c_xy * fabsf(__fsub_rn(__fsub_rn(q11, q10), __fsub_rn(q01, q00)));  // d/dy of dx
+      s += d.c_yx * fabsf(__fsub_rn(__fsub_rn(q11, q01), __fsub_rn(q10, q00)));  // d/dx of dy
+    }
+    acc[0] += s;
+  }
+  block_sum<1>(acc, scratch, partial + blockIdx.x);
+}
+
+// Sums `n` partials in double in a fixed order; out[0] = result.  One block.
+__global__ void sum_partials_kernel(const float* __restrict__ partial, int n, float* __restrict__ out) {
+  __shared__ double sh[256];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += (double)partial[i];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = (float)sh[0];
+}
+
+// Gradient as a gather stencil (deterministic): every element collects the signs of the second
+// differences it takes part in.
+__global__ void __launch_bounds__(256)
+smooth_bwd_kernel(const float* __restrict__ x, SmoothDims d, const float* __restrict__ g_loss,
+                  float* __restrict__ g_x) {
+  const size_t n = (size_t)d.B * d.H * d.W * d.C;
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const size_t p = e / d.C;
+  const int j = (int)(p % d.W), i = (int)((p / d.W) % d.H);
+  const long long sx = d.C, sy = (long long)d.W * d.C;
+  auto Q = [&](int di, int dj) { return smooth_q(x, d.inverse, (size_t)((long long)e + di * sy + dj * sx)); };
+  auto sxx = [&](int di, int dj) -> float {  // sign of dx2 owned by (i+di, j+dj)
+    const int jj = j + dj;
+    if (jj < 0 || jj + 2 >= d.W) return 0.f;
+    const float a = Q(di, dj), b = Q(di, dj + 1), c = Q(di, dj + 2);
+    return sgn(__fsub_rn(__fsub_rn(c, b), __fsub_rn(b, a)));
+  };
+  auto syy = [&](int di, int dj) -> float {
+    const int ii = i + di;
+    if (ii < 0 || ii + 2 >= d.H) return 0.f;
+    const float a = Q(di, dj), b = Q(di + 1, dj), c = Q(di + 2, dj);
+    return sgn(__fsub_rn(__fsub_rn(c, b), __fsub_rn(b, a)));
+  };
+  auto sxy = [&](int di, int dj, int order) -> float {
+    const int ii = i + di, jj = j + dj;
+    if (ii < 0 || jj < 0 || ii + 1 >= d.H || jj + 1 >= d.W) return 0.f;
+    const float q00 = Q(di, dj), q01 = Q(di, dj + 1), q10 = Q(di + 1, dj), q11 = Q(di + 1, dj + 1);
+    return order == 0 ? sgn(__fsub_rn(__fsub_rn(q11, q10), __fsub_rn(q01, q00)))
+                      : sgn(__fsub_rn(__fsub_rn(q11, q01), __fsub_rn(q10, q00)));
+  };
+  float g = d.c_xx * (sxx(0, 0) - 2.f * sxx(0, -1) + sxx(0, -2)) + d.c_yy * (syy(0, 0) - 2.f * syy(-1, 0) + syy(-2, 0));
+  g += d.c_xy * (sxy(0, 0, 0) - sxy(0, -1, 0) - sxy(-1, 0, 0) + sxy(-1, -1, 0));
+  g += d.c_yx * (sxy(0, 0, 1) - sxy(0, -1, 1) - sxy(-1, 0, 1) + sxy(-1, -1, 1));
+  if (d.inverse) { const float q = Q(0, 0); g = -g * q * q; }
+  if (g_loss != nullptr) g *= g_loss[0];
+  g_x[e] = g;
+}
+
+// =====================================================================================================
+// compute_exp_reg_loss  (my_losses.py:39-43) against the constant label [0,1] (my_losses.py:14-23)
+// =====================================================================================================
+__global__ void __launch_bounds__(256)
+expreg_fwd_kernel(const float* __restrict__ logits, long long N, float inv_n, float* __restrict__ partial) {
+  __shared__ float scratch[8];
+  float acc[1] = {0.f};
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < N; r += (long long)gridDim.x * blockDim.x) {
+    const float2 l = reinterpret_cast<const float2*>(logits)[r];
+    const float m = fmaxf(l.x, l.y);
+    acc[0] += (m + logf(expf(l.x - m) + expf(l.y - m))) - l.y;
+  }
+  acc[0] *= inv_n;
+  block_sum<1>(acc, scratch, partial + blockIdx.x);
+}
+
+__global__ void __launch_bounds__(256)
+expreg_bwd_kernel(const float* __restrict__ logits, long long N, float inv_n, const float* __restrict__ g_loss,
+                  float* __restrict__ g_logits) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= N) return;
+  const float2 l = reinterpret_cast<const float2*>(logits)[r];
+  const float m = fmaxf(l.x, l.y);
+  const float e0 = expf(l.x - m), e1 = expf(l.y - m);
+  float g0 = e0 / (e0 + e1) * inv_n;  // softmax - [0,1]: (p0, p1 - 1) = (p0, -p0)
+  if (g_loss != nullptr) g0 *= g_loss[0];
+  reinterpret_cast<float2*>(g_logits)[r] = make_float2(g0, -g0);
+}
+
+// =====================================================================================================
+// resize_area pyramid: one pass over level 0 writes every coarser level.  A block stages an F x TC tile
+// (F = 2^(S-1)) in shared memory; each coarser element is the y-outer / x-inner sequential sum of its
+// block of LEVEL-0 values times 1/4^s -- the summation order of TF's ResizeArea, hence bit-exact.
+// =====================================================================================================
+struct PyrLevels { float* p[VSL_MAX_SCALES]; };
+
+__global__ void __launch_bounds__(256)
+pyramid_kernel(const float* __restrict__ img, int H, int W, int C, int S, int F, int TC, PyrLevels lv) {
+  extern __shared__ float tile[];  // [F][TC*C]
+  const int b = blockIdx.z, y0 = blockIdx.y * F, x0 = blockIdx.x * TC;
+  const int cols = min(TC, W - x0);  // multiple of F
+  const int rowf = cols * C;
+  const float* src = img + ((size_t)b * H + y0) * W * C + (size_t)x0 * C;
+  for (int e = threadIdx.x; e < F * rowf; e += blockDim.x) {
+    const int r = e / rowf, k = e - r * rowf;
+    tile[r * (TC * C) + k] = src[(size_t)r * W * C + k];
+  }
+  __syncthreads();
+  for (int s = 1; s < S; ++s) {
+    const int f = 1 << s, oh = F >> s, ow = cols >> s;
+    const float scale = 1.0f / (float)(f * f);
+    const int Ws = W >> s, Hs = H >> s;
+    float* dst = lv.p[s] + (((size_t)b * Hs + (y0 >> s)) * Ws + (x0 >> s)) * C;
+    for (int e = threadIdx.x; e < oh * ow * C; e += blockDim.x) {
+      const int c = e % C, ox = (e / C) % ow, oy = e / (C * ow);
+      const float* t = tile + (oy * f) * (TC * C) + (ox * f) * C + c;
+      float acc = t[0];
+      for (int dy = 0; dy < f; ++dy)
+        for (int dx = (dy == 0 ? 1 : 0); dx < f; ++dx) acc = __fadd_rn(acc, t[dy * (TC * C) + dx * C]);
+      dst[((size_t)oy * Ws + ox) * C + c] = __fmul_rn(acc, scale);
+    }
+  }
+}
+
+}  // namespace vsl
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+using namespace vsl;
+
+extern "C" {
+
+int vsl_version(void) { return VSL_VERSION; }
+
+const char* vsl_strerror(int code) {
+  switch (code) {
+    case VSL_OK: return "ok";
+    case VSL_E_NULL: return "vsl: a required pointer is NULL";
+    case VSL_E_SHAPE: return "vsl: non-positive or unsupported dimension";
+    case VSL_E_FORMAT: return "vsl: unknown pose format or mask mode";
+    case VSL_E_ALIGN: return "vsl: misaligned pointer";
+    case VSL_E_UNSUPPORTED: return "vsl: unsupported configuration";
+    default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "vsl: unknown error";
+  }
+}
+
+int vsl_pose_vec2mat_fwd(const float* vec, int B, int format, float* mat, vsl_stream_t stream) {
+  VSL_REQUIRE(vec && mat, VSL_E_NULL);
+  VSL_REQUIRE(B > 0, VSL_E_SHAPE);
+  VSL_REQUIRE(format == VSL_POSE_EULER || format == VSL_POSE_ANGLEAXIS, VSL_E_FORMAT);
+  pose_fwd_kernel<<<(B + 63) / 64, 64, 0, (cudaStream_t)stream>>>(vec, B, format, mat);
+  return launch_status();
+}
+
+int vsl_pose_vec2mat_bwd(const float* vec, const float* g_mat, int B, int format, float* g_vec,
+                         vsl_stream_t stream) {
+  VSL_REQUIRE(vec && g_mat && g_vec, VSL_E_NULL);
+  VSL_REQUIRE(B > 0, VSL_E_SHAPE);
+  VSL_REQUIRE(format == VSL_POSE_EULER || format == VSL_POSE_ANGLEAXIS, VSL_E_FORMAT);
+  pose_bwd_kernel<<<(B + 63) / 64, 64, 0, (cudaStream_t)stream>>>(vec, g_mat, B, format, g_vec);
+  return launch_status();
+}
+
+static int warp_nblk(int H, int W) { return (H * W + 255) / 256; }
+
+size_t vsl_warp_ws_bytes(int B, int H, int W) {
+  if (B <= 0 || H <= 0 || W <= 0) return 0;
+  return round_up(sizeof(Xform) * (size_t)B, 256) + sizeof(float) * 12 * (size_t)B * warp_nblk(H, W);
+}
+
+static int check_warp_args(const void* img, const void* depth, const void* pose, const void* K, int B, int H,
+                           int W, int C, int format, const void* ws) {
+  VSL_REQUIRE(img && depth && pose && K && ws, VSL_E_NULL);
+  VSL_REQUIRE(B > 0 && H > 1 && W > 1 && C >= 1 && C <= 4, VSL_E_SHAPE);
+  VSL_REQUIRE((long long)H * W < (1ll << 31) / 4 && B <= 65535, VSL_E_SHAPE);
+  VSL_REQUIRE(format >= VSL_POSE_EULER && format <= VSL_POSE_MATRIX, VSL_E_FORMAT);
+  VSL_REQUIRE(aligned(ws, 16), VSL_E_ALIGN);
+  return VSL_OK;
+}
+
+int vsl_warp_fwd(const float* img, const float* depth, const float* pose, const float* K, int B, int H, int W,
+                 int C, int format, float* out_img, float* coords, float* wmask, float* src_depth,
+                 float* pose_mat, void* ws, vsl_stream_t stream) {
+  int rc = check_warp_args(img, depth, pose, K, B, H, W, C, format, ws);
+  if (rc != VSL_OK) return rc;
+  VSL_REQUIRE(coords == nullptr || aligned(coords, 8), VSL_E_ALIGN);
+  cudaStream_t st = (cudaStream_t)stream;
+  Xform* xf = reinterpret_cast<Xform*>(ws);
+  prep_xforms_kernel<<<(B + 63) / 64, 64, 0, st>>>(pose, K, B, 1, 1, format, xf, pose_mat);
+  dim3 grid(warp_nblk(H, W), B);
+  switch (C) {
+    case 1: warp_fwd_kernel<1><<<grid, 256, 0, st>>>(img, depth, xf, H, W, out_img, coords, wmask, src_depth); break;
+    case 2: warp_fwd_kernel<2><<<grid, 256, 0, st>>>(img, depth, xf, H, W, out_img, coords, wmask, src_depth); break;
+    case 3: warp_fwd_kernel<3><<<grid, 256, 0, st>>>(img, depth, xf, H, W, out_img, coords, wmask, src_depth); break;
+    default: warp_fwd_kernel<4><<<grid, 256, 0, st>>>(img, depth, xf, H, W, out_img, coords, wmask, src_depth); break;
+  }
+  return launch_status();
+}
+
+int vsl_warp_bwd(const float* img, const float* depth, const float* pose, const float* K, int B, int H, int W,
+                 int C, int format, const float* g_out_img, const float* g_coords, const float* g_wmask,
+                 const float* g_src_depth, const float* g_pose_mat, float* g_img, float* g_depth, float* g_pose,
+                 void* ws, vsl_stream_t stream) {
+  int rc = check_warp_args(img, depth, pose, K, B, H, W, C, format, ws);
+  if (rc != VSL_OK) return rc;
+  VSL_REQUIRE(g_coords == nullptr || aligned(g_coords, 8), VSL_E_ALIGN);
+  cudaStream_t st = (cudaStream_t)stream;
+  Xform* xf = reinterpret_cast<Xform*>(ws);
+  float* partial = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + round_up(sizeof(Xform) * (size_t)B, 256));
+  prep_xforms_kernel<<<(B + 63) / 64, 64, 0, st>>>(pose, K, B, 1, 1, format, xf, nullptr);
+  if (g_img != nullptr) {
+    cudaError_t e = cudaMemsetAsync(g_img, 0, sizeof(float) * (size_t)B * H * W * C, st);
+    if (e != cudaSuccess) return (int)e;
+  }
+  const int nblk = warp_nblk(H, W);
+  dim3 grid(nblk, B);
+  float* part = g_pose ? partial : nullptr;
+  switch (C) {
+    case 1: warp_bwd_kernel<1><<<grid, 256, 0, st>>>(img, depth, xf, H, W, g_out_img, g_coords, g_wmask, g_src_depth, g_img, g_depth, part); break;
+    case 2: warp_bwd_kernel<2><<<grid, 256, 0, st>>>(img, depth, xf, H, W, g_out_img, g_coords, g_wmask, g_src_depth, g_img, g_depth, part); break;
+    case 3: warp_bwd_kernel<3><<<grid, 256, 0, st>>>(img, depth, xf, H, W, g_out_img, g_coords, g_wmask, g_src_depth, g_img, g_depth, part); break;
+    default: warp_bwd_kernel<4><<<grid, 256, 0, st>>>(img, depth, xf, H, W, g_out_img, g_coords, g_wmask, g_src_depth, g_img, g_depth, part); break;
+  }
+  if (g_pose != nullptr)
+    warp_bwd_finalize_kernel<<<B, 32, 0, st>>>(partial, nblk, pose, K, g_pose_mat, B, format, g_pose);
+  return launch_status();
+}
+
+static int check_bilinear_args(const void* imgs, const void* coords, const void* fx, const void* fy, int B,
+                               int Hs, int Ws, int C, int Ht, int Wt) {
+  VSL_REQUIRE(imgs, VSL_E_NULL);
+  VSL_REQUIRE((coords != nullptr) != (fx != nullptr), VSL_E_NULL);
+  VSL_REQUIRE((fx != nullptr) == (fy != nullptr), VSL_E_NULL);
+  VSL_REQUIRE(B > 0 && B <= 65535 && Hs > 0 && Ws > 0 && Ht > 0 && Wt > 0 && C >= 1 && C <= 4, VSL_E_SHAPE);
+  VSL_REQUIRE(coords == nullptr || aligned(coords, 8), VSL_E_ALIGN);
+  return VSL_OK;
+}
+
+int vsl_bilinear_fwd(const float* imgs, const float* coords, const float* flowx, const float* flowy, int B,
+                     int Hs, int Ws, int C, int Ht, int Wt, float* out, float* wmask, float* coords_out,
+                     vsl_stream_t stream) {
+  int rc = check_bilinear_args(imgs, coords, flowx, flowy, B, Hs, Ws, C, Ht, Wt);
+  if (rc != VSL_OK) return rc;
+  VSL_REQUIRE(out, VSL_E_NULL);
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid((Ht * Wt + 255) / 256, B);
+  switch (C) {
+    case 1: bilinear_fwd_kernel<1><<<grid, 256, 0, st>>>(imgs, coords, flowx, flowy, Hs, Ws, Ht, Wt, out, wmask, coords_out); break;
+    case 2: bilinear_fwd_kernel<2><<<grid, 256, 0, st>>>(imgs, coords, flowx, flowy, Hs, Ws, Ht, Wt, out, wmask, coords_out); break;
+    case 3: bilinear_fwd_kernel<3><<<grid, 256, 0, st>>>(imgs, coords, flowx, flowy, Hs, Ws, Ht, Wt, out, wmask, coords_out); break;
+    default: bilinear_fwd_kernel<4><<<grid, 256, 0, st>>>(imgs, coords, flowx, flowy, Hs, Ws, Ht, Wt, out, wmask, coords_out); break;
+  }
+  return launch_status();
+}
+
+int vsl_bilinear_bwd(const float* imgs, const float* coords, const float* flowx, const float* flowy, int B,
+                     int Hs, int Ws, int C, int Ht, int Wt, const float* g_out, const float* g_wmask,
+                     float* g_imgs, float* g_coords, vsl_stream_t stream) {
+  int rc = check_bilinear_args(imgs, coords, flowx, flowy, B, Hs, Ws, C, Ht, Wt);
+  if (rc != VSL_OK) return rc;
+  VSL_REQUIRE(g_coords == nullptr || aligned(g_coords, 8), VSL_E_ALIGN);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (g_imgs != nullptr) {
+    cudaError_t e = cudaMemsetAsync(g_imgs, 0, sizeof(float) * (size_t)B * Hs * Ws * C, st);
+    if (e != cudaSuccess) return (int)e;
+  }
+  dim3 grid((Ht * Wt + 255) / 256, B);
+  switch (C) {
+    case 1: bilinear_bwd_kernel<1><<<grid, 256, 0, st>>>(imgs, coords, flowx, flowy, Hs, Ws, Ht, Wt, g_out, g_wmask, g_imgs, g_coords); break;
+    case 2: bilinear_bwd_kernel<2><<<grid, 256, 0, st>>>(imgs, coords, flowx, flowy, Hs, Ws, Ht, Wt, g_out, g_wmask, g_imgs, g_coords); break;
+    case 3: bilinear_bwd_kernel<3><<<grid, 256, 0, st>>>(imgs, coords, flowx, flowy, Hs, Ws, Ht, Wt, g_out, g_wmask, g_imgs, g_coords); break;
+    default: bilinear_bwd_kernel<4><<<grid, 256, 0, st>>>(imgs, coords, flowx, flowy, Hs, Ws, Ht, Wt, g_out, g_wmask, g_imgs, g_coords); break;
+  }
+  return launch_status();
+}
+
+int vsl_depth_optflow(const float* coords, int B, int H, int W, float* flowx, float* flowy, vsl_stream_t stream) {
+  VSL_REQUIRE(coords && flowx && flowy, VSL_E_NULL);
+  VSL_REQUIRE(B > 0 && H > 1 && W > 1, VSL_E_SHAPE);
+  VSL_REQUIRE(aligned(coords, 8), VSL_E_ALIGN);
+  const size_t n = (size_t)B * H * W;
+  depth_optflow_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(coords, H, W, n, flowx, flowy);
+  return launch_status();
+}
+
+static const int kReduceBlocks = 148 * 8;
+
+static SmoothDims smooth_dims(int B, int H, int W, int C, int inverse) {
+  SmoothDims d;
+  d.B = B; d.H = H; d.W = W; d.C = C; d.inverse = inverse;
+  const double bc = (double)B * C;
+  d.c_xx = (float)(1.0 / (bc * H * (W - 2)));
+  d.c_xy = (float)(1.0 / (bc * (H - 1) * (W - 1)));
+  d.c_yx = d.c_xy;
+  d.c_yy = (float)(1.0 / (bc * (H - 2) * W));
+  return d;
+}
+
+size_t vsl_smooth_ws_bytes(int, int, int, int) { return sizeof(float) * kReduceBlocks; }
+
+int vsl_smooth_fwd(const float* x, int B, int H, int W, int C, int inverse, float* loss, void* ws,
+                   vsl_stream_t stream) {
+  VSL_REQUIRE(x && loss && ws, VSL_E_NULL);
+  VSL_REQUIRE(B > 0 && H > 2 && W > 2 && C > 0, VSL_E_SHAPE);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n = (size_t)B * H * W * C;
+  const int blocks = (int)((n + 255) / 256 < (size_t)kReduceBlocks ? (n + 255) / 256 : kReduceBlocks);
+  smooth_fwd_kernel<<<blocks, 256, 0, st>>>(x, smooth_dims(B, H, W, C, inverse), (float*)ws);
+  sum_partials_kernel<<<1, 256, 0, st>>>((const float*)ws, blocks, loss);
+  return launch_status();
+}
+
+int vsl_smooth_bwd(const float* x, int B, int H, int W, int C, int inverse, const float* g_loss, float* g_x,
+                   vsl_stream_t stream) {
+  VSL_REQUIRE(x && g_x, VSL_E_NULL);
+  VSL_REQUIRE(B > 0 && H > 2 && W > 2 && C > 0, VSL_E_SHAPE);
+  const size_t n = (size_t)B * H * W * C;
+  smooth_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      x, smooth_dims(B, H, W, C, inverse), g_loss, g_x);
+  return launch_status();
+}
+
+size_t vsl_expreg_ws_bytes(long long) { return sizeof(float) * kReduceBlocks; }
+
+int vsl_expreg_fwd(const float* logits, long long N, float* loss, void* ws, vsl_stream_t stream) {
+  VSL_REQUIRE(logits && loss && ws, VSL_E_NULL);
+  VSL_REQUIRE(N > 0, VSL_E_SHAPE);
+  VSL_REQUIRE(aligned(logits, 8), VSL_E_ALIGN);
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long nb = (N + 255) / 256;
+  const int blocks = (int)(nb < kReduceBlocks ? nb : kReduceBlocks);
+  expreg_fwd_kernel<<<blocks, 256, 0, st>>>(logits, N, (float)(1.0 / (double)N), (float*)ws);
+  sum_partials_kernel<<<1, 256, 0, st>>>((const float*)ws, blocks, loss);
+  return launch_status();
+}
+
+int vsl_expreg_bwd(const float* logits, long long N, const float* g_loss, float* g_logits, vsl_stream_t stream) {
+  VSL_REQUIRE(logits && g_logits, VSL_E_NULL);
+  VSL_REQUIRE(N > 0, VSL_E_SHAPE);
+  VSL_REQUIRE(aligned(logits, 8) && aligned(g_logits, 8), VSL_E_ALIGN);
+  expreg_bwd_kernel<<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      logits, N, (float)(1.0 / (double)N), g_loss, g_logits);
+  return launch_status();
+}
+
+int vsl_pyramid(const float* img, int B, int H, int W, int C, int S, float* const* levels, vsl_stream_t stream) {
+  VSL_REQUIRE(img && levels, VSL_E_NULL);
+  VSL_REQUIRE(S >= 1 && S <= VSL_MAX_SCALES && B > 0 && B <= 65535 && C >= 1 && C <= 4, VSL_E_SHAPE);
+  if (S == 1) return VSL_OK;
+  const int F = 1 << (S - 1);
+  VSL_REQUIRE(H > 0 && W > 0 && H % F == 0 && W % F == 0, VSL_E_SHAPE);
+  PyrLevels lv;
+  for (int s = 0; s < VSL_MAX_SCALES; ++s) lv.p[s] = nullptr;
+  for (int s = 1; s < S; ++s) {
+    VSL_REQUIRE(levels[s - 1], VSL_E_NULL);
+    lv.p[s] = levels[s - 1];
+  }
+  const int TC = 1024 / F > 128 ? 128 : 1024 / F;  // multiple of F for F <= 32
+  dim3 grid((W + TC - 1) / TC, H / F, B);
+  const size_t smem = sizeof(float) * (size_t)F * TC * C;
+  pyramid_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(img, H, W, C, S, F, TC, lv);
+  return launch_status();
+}
+
+}  // extern "C"

@@ -1,0 +1,386 @@
+"""Host side of the view-synthesis-loss path: torch tensors in, libvsl (C ABI) calls out.
+
+torch is used for device memory, streams and autograd bookkeeping only; every number is produced by the
+hand-written sm_100a kernels in csrc/.  All tensors must be CUDA float32; anything else raises.
+"""
+import torch
+
+from . import _lib
+from ._lib import POSE_FORMATS, VslLossDesc, check, ptr_array
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32(t, name):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise TypeError('%s must be a CUDA tensor (this path has no CPU fallback)' % name)
+    if t.dtype != torch.float32:
+        raise TypeError('%s must be float32, got %s' % (name, t.dtype))
+    return t.contiguous()
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+def _fmt(format):
+    try:
+        return POSE_FORMATS[format]
+    except KeyError:
+        raise ValueError("format must be 'eular', 'angleaxis' or 'matrix', got %r" % (format,))
+
+
+# ----------------------------------------------------------------------------------------------------
+class _PoseVec2Mat(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, vec, fmt):
+        lib = _lib.load()
+        vec = _f32(vec, 'vec')
+        B = vec.shape[0]
+        mat = torch.empty(B, 4, 4, device=vec.device, dtype=torch.float32)
+        check(lib.vsl_pose_vec2mat_fwd(vec.data_ptr(), B, fmt, mat.data_ptr(), _stream()))
+        ctx.save_for_backward(vec)
+        ctx.fmt = fmt
+        return mat
+
+    @staticmethod
+    def backward(ctx, g_mat):
+        vec, = ctx.saved_tensors
+        g_vec = torch.empty_like(vec)
+        check(_lib.load().vsl_pose_vec2mat_bwd(vec.data_ptr(), _f32(g_mat, 'g_mat').data_ptr(), vec.shape[0],
+                                               ctx.fmt, g_vec.data_ptr(), _stream()))
+        return g_vec, None
+
+
+def pose_vec2mat(vec, format='eular'):
+    if vec.dim() != 2 or vec.shape[1] != 6:
+        raise ValueError('vec must be [B, 6], got %s' % (tuple(vec.shape),))
+    fmt = _fmt(format)
+    if fmt == 2:
+        raise ValueError("pose_vec2mat takes 'eular' or 'angleaxis'")
+    return _PoseVec2Mat.apply(vec, fmt)
+
+
+# ----------------------------------------------------------------------------------------------------
+class _ProjectiveInverseWarp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img, depth, pose, K, fmt):
+        lib = _lib.load()
+        img, depth, pose, K = _f32(img, 'img'), _f32(depth, 'depth'), _f32(pose, 'pose'), _f32(K, 'intrinsics')
+        B, H, W, C = img.shape
+        dev = img.device
+        out = torch.empty(B, H, W, C, device=dev)
+        coords = torch.empty(B, H, W, 2, device=dev)
+        wmask = torch.empty(B, H, W, 1, device=dev)
+        z = torch.empty(B, H, W, 1, device=dev)
+        pose_mat = torch.empty(B, 4, 4, device=dev)
+        ws = _ws(lib.vsl_warp_ws_bytes(B, H, W), dev)
+        check(lib.vsl_warp_fwd(img.data_ptr(), depth.data_ptr(), pose.data_ptr(), K.data_ptr(), B, H, W, C, fmt,
+                               out.data_ptr(), coords.data_ptr(), wmask.data_ptr(), z.data_ptr(),
+                               pose_mat.data_ptr(), ws.data_ptr(), _stream()))
+        ctx.save_for_backward(img, depth, pose, K)
+        ctx.fmt = fmt
+        return out, coords, wmask, z, pose_mat
+
+    @staticmethod
+    def backward(ctx, g_out, g_coords, g_wmask, g_z, g_pose_mat):
+        lib = _lib.load()
+        img, depth, pose, K = ctx.saved_tensors
+        B, H, W, C = img.shape
+        need_img, need_depth, need_pose = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        gs = [None if g is None else _f32(g, 'grad') for g in (g_out, g_coords, g_wmask, g_z, g_pose_mat)]
+        g_img = torch.empty_like(img) if need_img else None
+        g_depth = torch.empty_like(depth) if need_depth else None
+        g_pose = torch.empty_like(pose) if need_pose else None
+        ws = _ws(lib.vsl_warp_ws_bytes(B, H, W), img.device)
+        check(lib.vsl_warp_bwd(img.data_ptr(), depth.data_ptr(), pose.data_ptr(), K.data_ptr(), B, H, W, C, ctx.fmt,
+                               _p(gs[0]), _p(gs[1]), _p(gs[2]), _p(gs[3]), _p(gs[4]),
+                               _p(g_img), _p(g_depth), _p(g_pose), ws.data_ptr(), _stream()))
+        return g_img, g_depth, g_pose, None, None
+
+
+def projective_inverse_warp(img, depth, pose, intrinsics, format='eular'):
+    """utils_lr.py:222-256 -> (out_img, src_pixel_coords, wmask, src_depth, pose_mat)."""
+    fmt = _fmt(format)
+    if img.dim() != 4 or depth.dim() != 3 or tuple(depth.shape) != tuple(img.shape[:3]):
+        raise ValueError('img [B,H,W,C] and depth [B,H,W] disagree: %s vs %s' % (tuple(img.shape), tuple(depth.shape)))
+    B = img.shape[0]
+    want = (B, 4, 4) if fmt == 2 else (B, 6)
+    if tuple(pose.shape) != want or tuple(intrinsics.shape) != (B, 3, 3):
+        raise ValueError('pose must be %s and intrinsics %s' % (want, (B, 3, 3)))
+    return _ProjectiveInverseWarp.apply(img, depth, pose, intrinsics, fmt)
+
+
+# ----------------------------------------------------------------------------------------------------
+class _Bilinear(torch.autograd.Function):
+    """coords given (flow is None) or meshgrid + flow."""
+
+    @staticmethod
+    def forward(ctx, imgs, coords, flowx, flowy):
+        lib = _lib.load()
+        imgs = _f32(imgs, 'imgs')
+        B, Hs, Ws, C = imgs.shape
+        if coords is not None:
+            coords = _f32(coords, 'coords')
+            Ht, Wt = coords.shape[1], coords.shape[2]
+        else:
+            flowx, flowy = _f32(flowx, 'flowx'), _f32(flowy, 'flowy')
+            Ht, Wt = flowx.shape[1], flowx.shape[2]
+        out = torch.empty(B, Ht, Wt, C, device=imgs.device)
+        wmask = torch.empty(B, Ht, Wt, 1, device=imgs.device)
+        check(lib.vsl_bilinear_fwd(imgs.data_ptr(), _p(coords), _p(flowx), _p(flowy), B, Hs, Ws, C, Ht, Wt,
+                                   out.data_ptr(), wmask.data_ptr(), None, _stream()))
+        ctx.save_for_backward(imgs, coords, flowx, flowy)
+        return out, wmask
+
+    @staticmethod
+    def backward(ctx, g_out, g_wmask):
+        lib = _lib.load()
+        imgs, coords, flowx, flowy = ctx.saved_tensors
+        B, Hs, Ws, C = imgs.shape
+        ref = coords if coords is not None else flowx
+        Ht, Wt = ref.shape[1], ref.shape[2]
+        g_out = None if g_out is None else _f32(g_out, 'g_out')
+        g_wmask = None if g_wmask is None else _f32(g_wmask, 'g_wmask')
+        need_c = any(ctx.needs_input_grad[1:])
+        g_imgs = torch.empty_like(imgs) if ctx.needs_input_grad[0] else None
+        g_coords = torch.empty(B, Ht, Wt, 2, device=imgs.device) if need_c else None
+        check(lib.vsl_bilinear_bwd(imgs.data_ptr(), _p(coords), _p(flowx), _p(flowy), B, Hs, Ws, C, Ht, Wt,
+                                   _p(g_out), _p(g_wmask), _p(g_imgs), _p(g_coords), _stream()))
+        if coords is not None:
+            return g_imgs, g_coords, None, None
+        gfx = g_coords[..., 0:1].contiguous() if ctx.needs_input_grad[2] else None
+        gfy = g_coords[..., 1:2].contiguous() if ctx.needs_input_grad[3] else None
+        return g_imgs, None, gfx, gfy
+
+
+def bilinear_sampler(imgs, coords):
+    """utils.py:219-308 -> (output, wmask)."""
+    if imgs.dim() != 4 or coords.dim() != 4 or coords.shape[3] != 2 or coords.shape[0] != imgs.shape[0]:
+        raise ValueError('imgs [B,Hs,Ws,C] / coords [B,Ht,Wt,2] expected')
+    return _Bilinear.apply(imgs, coords, None, None)
+
+
+def optflow_warp(img, flowx, flowy):
+    """utils.py:201-217 -> output_img."""
+    B, H, W, _ = img.shape
+    if tuple(flowx.shape) != (B, H, W, 1) or tuple(flowy.shape) != (B, H, W, 1):
+        raise ValueError('flowx / flowy must be [B,H,W,1]')
+    return _Bilinear.apply(img, None, flowx, flowy)[0]
+
+
+class _DepthOptflow(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, coords):
+        coords = _f32(coords, 'coords')
+        B, H, W, _ = coords.shape
+        fx = torch.empty(B, H, W, 1, device=coords.device)
+        fy = torch.empty(B, H, W, 1, device=coords.device)
+        check(_lib.load().vsl_depth_optflow(coords.data_ptr(), B, H, W, fx.data_ptr(), fy.data_ptr(), _stream()))
+        return fx, fy
+
+    @staticmethod
+    def backward(ctx, gfx, gfy):
+        return torch.cat([gfx, gfy], dim=3)
+
+
+def depth_optflow(src_pixel_coords):
+    """utils.py:321-338 -> (flowx, flowy)."""
+    return _DepthOptflow.apply(src_pixel_coords)
+
+
+def consistent_depth_loss(src_depth, pred_src_depth, coords):
+    """utils_lr.py:369-458: |pred_src_depth - bilinear(src_depth, coords)| (no reduction)."""
+    sampled, _ = _Bilinear.apply(src_depth, coords, None, None)
+    return torch.abs(pred_src_depth - sampled)
+
+
+# ----------------------------------------------------------------------------------------------------
+class _SmoothLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, inverse):
+        lib = _lib.load()
+        x = _f32(x, 'pred_disp')
+        B, H, W, C = x.shape
+        loss = torch.empty((), device=x.device)
+        ws = _ws(lib.vsl_smooth_ws_bytes(B, H, W, C), x.device)
+        check(lib.vsl_smooth_fwd(x.data_ptr(), B, H, W, C, int(inverse), loss.data_ptr(), ws.data_ptr(), _stream()))
+        ctx.save_for_backward(x)
+        ctx.inverse = int(inverse)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        x, = ctx.saved_tensors
+        B, H, W, C = x.shape
+        g_x = torch.empty_like(x)
+        check(_lib.load().vsl_smooth_bwd(x.data_ptr(), B, H, W, C, ctx.inverse, _f32(g, 'g').data_ptr(),
+                                         g_x.data_ptr(), _stream()))
+        return g_x, None
+
+
+def compute_smooth_loss(pred_disp, inverse=False):
+    """my_losses.py:27-36.  inverse=True evaluates the loss on 1/pred_disp inside the kernel."""
+    if pred_disp.dim() != 4:
+        raise ValueError('pred_disp must be [B,H,W,C]')
+    return _SmoothLoss.apply(pred_disp, inverse)
+
+
+class _ExpReg(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits):
+        lib = _lib.load()
+        logits = _f32(logits, 'pred')
+        N = logits.numel() // 2
+        loss = torch.empty((), device=logits.device)
+        ws = _ws(lib.vsl_expreg_ws_bytes(N), logits.device)
+        check(lib.vsl_expreg_fwd(logits.data_ptr(), N, loss.data_ptr(), ws.data_ptr(), _stream()))
+        ctx.save_for_backward(logits)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        logits, = ctx.saved_tensors
+        g_l = torch.empty_like(logits)
+        check(_lib.load().vsl_expreg_bwd(logits.data_ptr(), logits.numel() // 2, _f32(g, 'g').data_ptr(),
+                                         g_l.data_ptr(), _stream()))
+        return g_l
+
+
+def compute_exp_reg_loss(pred, ref=None):
+    """my_losses.py:39-43 with ref = the constant [0,1] mask of my_losses.py:14-23 (the only one used)."""
+    if pred.shape[-1] != 2:
+        raise ValueError('pred must have 2 channels')
+    return _ExpReg.apply(pred)
+
+
+def image_pyramid(img, num_scales):
+    """tf.image.resize_area(img, [H/2^s, W/2^s]) for s = 0..S-1 (level 0 is `img` itself). No gradient."""
+    lib = _lib.load()
+    img = _f32(img.detach(), 'img')
+    B, H, W, C = img.shape
+    levels = [torch.empty(B, H >> s, W >> s, C, device=img.device) for s in range(1, num_scales)]
+    check(lib.vsl_pyramid(img.data_ptr(), B, H, W, C, num_scales, ptr_array([l.data_ptr() for l in levels]), _stream()))
+    return [img] + levels
+
+
+# ----------------------------------------------------------------------------------------------------
+class LossFlags(object):
+    """Loss configuration with the reference's FLAGS attribute names (train_depth_then_cam_lr.py:44-54)."""
+
+    def __init__(self, **kw):
+        self.num_scales = 4
+        self.smooth_weight = 0.5
+        self.data_weight = 1.0
+        self.explain_reg_weight = 0.2
+        self.pose_format = 'eular'
+        self.pixel_scale_norm = True     # data_weight / 2^s (train.py:135)
+        self.depth_is_inverse = True     # warp depth = 1/x (train.py:128)
+        self.smooth_on_inverse = False   # smooth(1/x) (train_depth_then_cam_lr.py:217)
+        self.__dict__.update(kw)
+
+
+class ViewSynthesisPlan(object):
+    """Pre-allocated state for repeated fused-loss steps at one shape: workspace, gradient buffers and the
+    pointer tables of the C call.  One instance per (shape, flags); not thread-safe."""
+
+    def __init__(self, B, H, W, V, flags, mask_mode, device, loss_scale=1.0):
+        lib = _lib.load()
+        S = flags.num_scales
+        self.B, self.H, self.W, self.S, self.V = B, H, W, S, V
+        self.mask_mode = mask_mode
+        self.fmt = _fmt(flags.pose_format)
+        self.desc = VslLossDesc(B, H, W, S, V, self.fmt, mask_mode, int(flags.pixel_scale_norm),
+                                int(flags.depth_is_inverse), int(flags.smooth_on_inverse),
+                                float(flags.data_weight), float(flags.smooth_weight),
+                                float(flags.explain_reg_weight), float(loss_scale))
+        nbytes = lib.vsl_loss_ws_bytes(self.desc)
+        if nbytes == 0:
+            raise ValueError('unsupported loss shape B=%d H=%d W=%d S=%d V=%d' % (B, H, W, S, V))
+        self.ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        self.losses = torch.zeros(3, device=device)
+        self.g_x = [torch.empty(B, H >> s, W >> s, 1, device=device) for s in range(S)]
+        self.g_poses = torch.empty((B, V, 4, 4) if self.fmt == 2 else (B, V, 6), device=device)
+        self.g_logits = ([torch.empty(B, H >> s, W >> s, 2 * V, device=device) for s in range(S)]
+                         if mask_mode == _lib.MASK_EXP else None)
+        self.version = 0  # bumped by every run(); lets autograd detect a stale backward
+        self._gx_ptrs = ptr_array([t.data_ptr() for t in self.g_x])
+        self._gl_ptrs = ptr_array([t.data_ptr() for t in self.g_logits]) if self.g_logits else None
+
+    def run(self, tgt, srcs, x_pyr, poses, K_pyr, logits_pyr=None, mask_pyr=None):
+        """Enqueue one fused forward+backward.  Inputs must already be contiguous CUDA float32 of the plan's
+        shapes.  Results land in self.losses / self.g_x / self.g_poses / self.g_logits."""
+        lib = _lib.load()
+        self.version += 1
+        check(lib.vsl_loss_fwd_bwd(
+            self.desc, tgt.data_ptr(), ptr_array([s.data_ptr() for s in srcs]),
+            ptr_array([x.data_ptr() for x in x_pyr]), poses.data_ptr(), K_pyr.data_ptr(),
+            ptr_array([l.data_ptr() for l in logits_pyr]) if logits_pyr is not None else None,
+            ptr_array([m.data_ptr() for m in mask_pyr]) if mask_pyr is not None else None,
+            self.losses.data_ptr(), self._gx_ptrs, self.g_poses.data_ptr(), self._gl_ptrs,
+            self.ws.data_ptr(), _stream()))
+        return self.losses
+
+
+class _ViewSynthesisLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, plan, tgt, srcs, K_pyr, poses, n_x, *pyr):
+        x_pyr = [_f32(t, 'x_pyr') for t in pyr[:n_x]]
+        rest = [_f32(t, 'pyr') for t in pyr[n_x:]]
+        logits = rest if plan.mask_mode == _lib.MASK_EXP else None
+        mask = rest if plan.mask_mode == _lib.MASK_CONST else None
+        plan.run(_f32(tgt, 'tgt'), [_f32(s, 'src') for s in srcs], x_pyr, _f32(poses, 'poses'), _f32(K_pyr, 'K_pyr'),
+                 logits, mask)
+        ctx.plan = plan
+        ctx.version = plan.version
+        ctx.n_x = n_x
+        ctx.n_rest = len(rest)
+        losses = plan.losses.clone()
+        total = losses.sum()
+        ctx.mark_non_differentiable(losses)
+        return total, losses
+
+    @staticmethod
+    def backward(ctx, g_total, _g_losses):
+        plan = ctx.plan
+        if plan.version != ctx.version:
+            raise RuntimeError('view_synthesis_loss: the plan ran again before this backward; the gradients of '
+                               'the earlier forward were overwritten (call backward before the next forward)')
+        g_x = [g * g_total for g in plan.g_x]
+        g_rest = ([g * g_total for g in plan.g_logits] if plan.mask_mode == _lib.MASK_EXP
+                  else [None] * ctx.n_rest)
+        return (None, None, None, None, plan.g_poses * g_total, None) + tuple(g_x) + tuple(g_rest)
+
+
+_PLANS = {}
+
+
+def view_synthesis_loss(tgt, srcs, x_pyr, poses, K_pyr, logits_pyr=None, mask_pyr=None, flags=None):
+    """The reference's per-scale loss loop (train.py:107-135 + train_depth_then_cam_lr.py:297-328) as ONE fused
+    forward+backward call.
+
+    tgt [B,H,W,3]; srcs: list of V [B,H,W,3]; x_pyr: list of S network outputs [B,Hs,Ws,1]; poses [B,V,6] or
+    [B,V,4,4]; K_pyr [B,S,3,3]; logits_pyr: list of S [B,Hs,Ws,2V] (explainability) or mask_pyr: list of S
+    constant weights [B,Hs,Ws,1].  -> (total, losses[3] = pixel, smooth, exp).  `total` is differentiable wrt
+    x_pyr, poses and logits_pyr; the gradients were produced in the same kernel pass as the loss.
+    """
+    flags = flags or LossFlags()
+    if logits_pyr is not None and mask_pyr is not None:
+        raise ValueError('give logits_pyr or mask_pyr, not both')
+    B, H, W, C = tgt.shape
+    V, S = len(srcs), flags.num_scales
+    if C != 3 or len(x_pyr) != S:
+        raise ValueError('tgt must be [B,H,W,3] and x_pyr must hold num_scales=%d levels' % S)
+    mode = _lib.MASK_EXP if logits_pyr is not None else (_lib.MASK_CONST if mask_pyr is not None else _lib.MASK_NONE)
+    key = (B, H, W, V, mode, tgt.device, tuple(sorted(flags.__dict__.items())))
+    plan = _PLANS.get(key)
+    if plan is None:
+        plan = _PLANS[key] = ViewSynthesisPlan(B, H, W, V, flags, mode, tgt.device)
+    rest = list(logits_pyr if logits_pyr is not None else (mask_pyr or []))
+    return _ViewSynthesisLoss.apply(plan, tgt, list(srcs), K_pyr, poses, S, *x_pyr, *rest)
