@@ -24,7 +24,8 @@ class VslLossDesc(ctypes.Structure):
                 ('pixel_scale_norm', ctypes.c_int), ('depth_is_inverse', ctypes.c_int),
                 ('smooth_on_inverse', ctypes.c_int),
                 ('data_weight', ctypes.c_float), ('smooth_weight', ctypes.c_float),
-                ('explain_reg_weight', ctypes.c_float), ('loss_scale', ctypes.c_float)]
+                ('explain_reg_weight', ctypes.c_float), ('loss_scale', ctypes.c_float),
+                ('ev_main_begin', ctypes.c_void_p), ('ev_main_end', ctypes.c_void_p)]
 
 
 # name -> (restype, argtypes); every symbol include/vsl.h declares

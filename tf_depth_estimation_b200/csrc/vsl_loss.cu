@@ -354,7 +354,9 @@ void layout(const VslLossDesc* d, WsLayout* L) {
 template <int V>
 int run_loss(const VslLossDesc* d, const WsLayout& L, LossParams& P, const float* poses, const float* K_pyr,
              float* losses, float* g_poses, cudaStream_t st) {
+  if (d->ev_main_begin != nullptr) cudaEventRecord((cudaEvent_t)d->ev_main_begin, st);
   loss_fused_kernel<V><<<L.n_items, 256, 0, st>>>(P);
+  if (d->ev_main_end != nullptr) cudaEventRecord((cudaEvent_t)d->ev_main_end, st);
   loss_finalize_kernel<V><<<d->B + 1, 128, 0, st>>>(P, poses, K_pyr, d->pose_format, 1.0f / d->loss_scale,
                                                       losses, g_poses);
   return launch_status();

@@ -299,7 +299,7 @@ class ViewSynthesisPlan(object):
         self.desc = VslLossDesc(B, H, W, S, V, self.fmt, mask_mode, int(flags.pixel_scale_norm),
                                 int(flags.depth_is_inverse), int(flags.smooth_on_inverse),
                                 float(flags.data_weight), float(flags.smooth_weight),
-                                float(flags.explain_reg_weight), float(loss_scale))
+                                float(flags.explain_reg_weight), float(loss_scale), None, None)
         nbytes = lib.vsl_loss_ws_bytes(self.desc)
         if nbytes == 0:
             raise ValueError('unsupported loss shape B=%d H=%d W=%d S=%d V=%d' % (B, H, W, S, V))
@@ -313,19 +313,29 @@ class ViewSynthesisPlan(object):
         self._gx_ptrs = ptr_array([t.data_ptr() for t in self.g_x])
         self._gl_ptrs = ptr_array([t.data_ptr() for t in self.g_logits]) if self.g_logits else None
 
+    def bind(self, tgt, srcs, x_pyr, poses, K_pyr, logits_pyr=None, mask_pyr=None):
+        """Pre-marshal the C arguments for one set of input buffers; run_bound(args) then costs one ctypes
+        call.  The caller keeps the tensors alive."""
+        return (self.desc, tgt.data_ptr(), ptr_array([s.data_ptr() for s in srcs]),
+                ptr_array([x.data_ptr() for x in x_pyr]), poses.data_ptr(), K_pyr.data_ptr(),
+                ptr_array([l.data_ptr() for l in logits_pyr]) if logits_pyr is not None else None,
+                ptr_array([m.data_ptr() for m in mask_pyr]) if mask_pyr is not None else None,
+                self.losses.data_ptr(), self._gx_ptrs, self.g_poses.data_ptr(), self._gl_ptrs,
+                self.ws.data_ptr())
+
+    def run_bound(self, args, stream=None):
+        self.version += 1
+        check(_lib.load().vsl_loss_fwd_bwd(*args, _stream() if stream is None else stream))
+        return self.losses
+
+    def set_profile_events(self, begin=None, end=None):
+        """cudaEvent_t handles (ints) recorded immediately around the fused loss kernel; None switches off."""
+        self.desc.ev_main_begin, self.desc.ev_main_end = begin, end
+
     def run(self, tgt, srcs, x_pyr, poses, K_pyr, logits_pyr=None, mask_pyr=None):
         """Enqueue one fused forward+backward.  Inputs must already be contiguous CUDA float32 of the plan's
         shapes.  Results land in self.losses / self.g_x / self.g_poses / self.g_logits."""
-        lib = _lib.load()
-        self.version += 1
-        check(lib.vsl_loss_fwd_bwd(
-            self.desc, tgt.data_ptr(), ptr_array([s.data_ptr() for s in srcs]),
-            ptr_array([x.data_ptr() for x in x_pyr]), poses.data_ptr(), K_pyr.data_ptr(),
-            ptr_array([l.data_ptr() for l in logits_pyr]) if logits_pyr is not None else None,
-            ptr_array([m.data_ptr() for m in mask_pyr]) if mask_pyr is not None else None,
-            self.losses.data_ptr(), self._gx_ptrs, self.g_poses.data_ptr(), self._gl_ptrs,
-            self.ws.data_ptr(), _stream()))
-        return self.losses
+        return self.run_bound(self.bind(tgt, srcs, x_pyr, poses, K_pyr, logits_pyr, mask_pyr))
 
 
 class _ViewSynthesisLoss(torch.autograd.Function):
