@@ -4,7 +4,7 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 A *step* is one pass of the hot path over one batch of synthetic frame snippets: K_s^-1 / P tables, the
-resize_area pyramids of target + source images, and the fused multi-scale loss forward+backward (6 launches).
+resize_area pyramids of target + source images, and the fused multi-scale loss forward+backward (3 launches).
 Workload at every N: BASELINE.json configs[1] per GPU -- B=32, 128x416, 4 scales, 2 source views, fp32,
 explainability mask on (weak scaling: the path shards over the batch, no data-path collective).
 
@@ -314,7 +314,7 @@ def run_ours(args):
                          'kernel_ms_min': min(kern_ms), 'kernel_share_of_step': kmean / (ms_max / K), 'peak_source': peak_src},
             'e2e': {'value': pixel_views(B) * world / (e2e_ms * 1e-3) / 1e6, 'unit': UNIT, 'ms_per_step': e2e_ms,
                     'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'steps': Ke},
-            'gpu_launches': 6 * K, 'launches_per_step': 6, 'clocks': clocks,
+            'gpu_launches': 3 * K, 'launches_per_step': 3, 'clocks': clocks,
             'losses': {'pixel': losses[0], 'smooth': losses[1], 'exp': losses[2]},
         }
         if world == 1 and not args.no_cpu_baseline:

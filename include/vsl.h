@@ -127,6 +127,9 @@ typedef struct {
   int smooth_on_inverse; /* smoothness on 1/x (train_depth_then_cam_lr.py:217) or on x (train.py:108) */
   float data_weight, smooth_weight, explain_reg_weight;
   float loss_scale;      /* upstream gradient of the summed loss, folded into every gradient */
+  int exact_coords;      /* 1: reference rounding sequence for coordinates / softmax / blend (bit-identical
+                            sample positions to the oracle for matrix poses); 0: FMA + MUFU fast path */
+  int reserved_;
   void* ev_main_begin;   /* optional cudaEvent_t pair recorded on `stream` immediately around the fused  */
   void* ev_main_end;     /* loss kernel (launch 3 of the step) so a caller can time it in situ; NULL = off */
 } VslLossDesc;

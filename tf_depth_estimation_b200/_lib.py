@@ -25,6 +25,7 @@ class VslLossDesc(ctypes.Structure):
                 ('smooth_on_inverse', ctypes.c_int),
                 ('data_weight', ctypes.c_float), ('smooth_weight', ctypes.c_float),
                 ('explain_reg_weight', ctypes.c_float), ('loss_scale', ctypes.c_float),
+                ('exact_coords', ctypes.c_int), ('reserved_', ctypes.c_int),
                 ('ev_main_begin', ctypes.c_void_p), ('ev_main_end', ctypes.c_void_p)]
 
 

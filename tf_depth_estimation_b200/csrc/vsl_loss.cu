@@ -4,16 +4,16 @@
 // Python loop over S scales x V source views of ~150 TF ops each, then autodiff of all of it.  Here the
 // whole thing is three launches:
 //
-//   1. prep_xforms_kernel   (vsl_ops.cu)  K_s^-1 and P = K4_s . T_v per (scale, view, batch element)
-//   2. pyramid_kernel       (vsl_ops.cu)  resize_area levels 1..S-1 of the target and source images
-//   3. loss_fused_kernel    (this file)   every scale and view in ONE grid:
+//   1. pyramid_kernel       (vsl_ops.cu)  resize_area levels 1..S-1 of the target and source images, and
+//                                         (riding along) K_s^-1 and P = K4_s . T_v per (scale, view, batch)
+//   2. loss_fused_kernel    (this file)   every scale and view in ONE grid:
 //        per target pixel: smoothness stencil (forward sum + gradient) on a shared-memory tile of x,
 //        then per view: back-project, pose, project, bilinear gather of the source, L1 against the
 //        target, explainability / validity mask, softmax cross-entropy regulariser -- and, because the
 //        loss is a weighted sum of means whose upstream gradient is known (loss_scale), the gradients
 //        d/dx, d/dlogits are written in the same pass and dP = sum du (x) [cam;1] is accumulated in
 //        registers and reduced once per block.  No full-resolution intermediate is ever written.
-//   4. loss_finalize_kernel (this file)   fixed-order reduction of the block partials (deterministic),
+//   3. loss_finalize_kernel (this file)   fixed-order reduction of the block partials (deterministic),
 //        dT = K4^T dP summed over scales, pose chain rule, the three loss scalars.
 //
 // Work decomposition: an "item" is an 8-row x (32*R)-column tile of one image at one scale; block = 8
@@ -27,8 +27,12 @@ namespace vsl {
 constexpr int kTH = 8;      // tile rows = warps per block
 constexpr int kMaxR = 4;    // pixels per thread
 constexpr int kHalo = 2;
-constexpr int kTileW = 32 * kMaxR + 2 * kHalo;
-constexpr int kTileH = kTH + 2 * kHalo;
+constexpr int kTileW = 32 * kMaxR + 2 * kHalo;  // 132 columns of x
+constexpr int kTileH = kTH + 2 * kHalo;         // 12 rows of x
+constexpr int kQStride = kTileW + 4;
+constexpr int kOwnW = 32 * kMaxR + kHalo;       // owners: tile + 2 columns to the left
+constexpr int kOwnH = kTH + kHalo;              //         tile + 2 rows above
+constexpr int kOStride = kOwnW + 2;
 
 struct LossParams {
   int B, H, W, S, V;
@@ -51,10 +55,21 @@ struct LossParams {
 
 template <int V> struct NT { static constexpr int value = 3 + 12 * V; };
 
-template <int V>
-__global__ void __launch_bounds__(256, 2)
+VSL_DEV float signed_by(float c, float v) {  // c * sign(v), sign(0) = 0
+  return (v == 0.f) ? 0.f : copysignf(c, v);
+}
+
+// EXACT = true : coordinates, softmax and the warped value follow the reference's rounding sequence
+//                (bit-identical sample positions to the oracle for matrix poses).
+// EXACT = false: the same algebra with FMA contraction, MUFU reciprocal / exp / log and the closed form
+//                d(depth) = -<du, t> / depth; differs from EXACT by a few ulp per quantity.
+template <int V, bool EXACT>
+__global__ void __launch_bounds__(256, 3)
 loss_fused_kernel(const LossParams P) {
-  __shared__ float qt[kTileH][kTileW];          // smoothness operand (x or 1/x) with a 2-pixel halo
+  __shared__ float qt[kTileH][kQStride];     // smoothness operand (x or 1/x) with a 2-pixel halo
+  __shared__ float sA[kOwnH][kOStride];      // cxx * sign(dx2)  of the stencil owned by each element
+  __shared__ float sB[kOwnH][kOStride];      // cyy * sign(dy2)
+  __shared__ float sC[kOwnH][kOStride];      // cxy * sign(dxdy) + cyx * sign(dydx)
   __shared__ Xform sxf[V];
   __shared__ float scratch[NT<V>::value * kTH];
 
@@ -68,33 +83,68 @@ loss_fused_kernel(const LossParams P) {
   const int H = P.H >> s, W = P.W >> s, R = P.R[s];
   const int y_base = band * kTH, x_base = tx * 32 * R;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tw = 32 * R;
 
   // ---- stage the x tile (+halo) and this image's V transforms
   const float* __restrict__ xs = P.x[s] + (size_t)b * H * W;
-  const int tw = 32 * R + 2 * kHalo;
-  for (int e = threadIdx.x; e < kTileH * tw; e += blockDim.x) {
-    const int ty = e / tw, txx = e - ty * tw;
-    const int gy = y_base + ty - kHalo, gx = x_base + txx - kHalo;
-    float v = 0.f;
-    if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
-      v = xs[(size_t)gy * W + gx];
-      if (P.smooth_on_inverse) v = __fdiv_rn(1.0f, v);
+  for (int ty = warp; ty < kTileH; ty += kTH) {
+    const int gy = y_base + ty - kHalo;
+    const bool rin = gy >= 0 && gy < H;
+    const float* __restrict__ row = xs + (size_t)(rin ? gy : 0) * W;
+    for (int tc = lane; tc < tw + 2 * kHalo; tc += 32) {
+      const int gx = x_base + tc - kHalo;
+      float v = 0.f;
+      if (rin && gx >= 0 && gx < W) {
+        v = row[gx];
+        if (P.smooth_on_inverse) v = __fdiv_rn(1.0f, v);
+      }
+      qt[ty][tc] = v;
     }
-    qt[ty][txx] = v;
   }
-  for (int e = threadIdx.x; e < V * 21; e += blockDim.x)
-    reinterpret_cast<float*>(sxf)[e] =
-        reinterpret_cast<const float*>(P.xf + ((size_t)s * V + e / 21) * P.B + b)[e % 21];
+  if (threadIdx.x < V * 21)
+    reinterpret_cast<float*>(sxf)[threadIdx.x] =
+        reinterpret_cast<const float*>(P.xf + ((size_t)s * V + threadIdx.x / 21) * P.B + b)[threadIdx.x % 21];
+  __syncthreads();
+
+  const float cpix = P.cpix[s], cexp = P.cexp[s];
+  float pix_sum = 0.f, exp_sum = 0.f, sm_sum = 0.f;
+
+  // ---- smoothness, pass 1: every element of (tile + 2 rows above + 2 columns left) evaluates the four
+  // second differences it owns (it is their top-left corner) ONCE and publishes their weighted signs.
+  {
+    const float cxx = P.csm[s][0], cxy = P.csm[s][1], cyx = P.csm[s][2], cyy = P.csm[s][3];
+    for (int oy = warp; oy < kOwnH; oy += kTH) {
+      const int gy = y_base - kHalo + oy;
+      const bool rin = gy >= 0 && gy < H;
+      for (int ox = lane; ox < tw + kHalo; ox += 32) {
+        const int gx = x_base - kHalo + ox;
+        const bool in = rin && gx >= 0 && gx < W;
+        const float q00 = qt[oy][ox], q01 = qt[oy][ox + 1], q02 = qt[oy][ox + 2];
+        const float q10 = qt[oy + 1][ox], q11 = qt[oy + 1][ox + 1], q20 = qt[oy + 2][ox];
+        const float dx0 = __fsub_rn(q01, q00), dy0 = __fsub_rn(q10, q00);
+        float dxx = __fsub_rn(__fsub_rn(q02, q01), dx0);
+        float dyy = __fsub_rn(__fsub_rn(q20, q10), dy0);
+        float dxy = __fsub_rn(__fsub_rn(q11, q10), dx0);  // d/dy of dx
+        float dyx = __fsub_rn(__fsub_rn(q11, q01), dy0);  // d/dx of dy
+        if (!(in && gx + 2 < W)) dxx = 0.f;
+        if (!(in && gy + 2 < H)) dyy = 0.f;
+        if (!(in && gx + 1 < W && gy + 1 < H)) { dxy = 0.f; dyx = 0.f; }
+        sA[oy][ox] = signed_by(cxx, dxx);
+        sB[oy][ox] = signed_by(cyy, dyy);
+        sC[oy][ox] = signed_by(cxy, dxy) + signed_by(cyx, dyx);
+        if (oy >= kHalo && ox >= kHalo)
+          sm_sum += cxx * fabsf(dxx) + cyy * fabsf(dyy) + cxy * fabsf(dxy) + cyx * fabsf(dyx);
+      }
+    }
+  }
   __syncthreads();
 
   const int y = y_base + warp;
   const bool row_ok = y < H;
   const float gy = grid_coord(y, H, grid_step(H));
   const float wstep = grid_step(W);
-  const float cpix = P.cpix[s], cexp = P.cexp[s];
-  const float cxx = P.csm[s][0], cxy = P.csm[s][1], cyx = P.csm[s][2], cyy = P.csm[s][3];
+  const size_t img_off = (size_t)b * H * W;
 
-  float pix_sum = 0.f, exp_sum = 0.f, sm_sum = 0.f;
   float S1[V][3], S2[V][3], S3[V][3];  // sum du*d*gx, sum du*d, sum du
 #pragma unroll
   for (int v = 0; v < V; ++v)
@@ -104,46 +154,22 @@ loss_fused_kernel(const LossParams P) {
   for (int r = 0; r < R; ++r) {
     const int x = x_base + r * 32 + lane;
     if (!(row_ok && x < W)) continue;
-    const size_t pix = ((size_t)b * H + y) * W + x;
-    const int ty = warp + kHalo, txx = r * 32 + lane + kHalo;
+    const int pofs = y * W + x;              // pixel offset inside this image
+    const size_t pix = img_off + pofs;
+    const int oy = warp + kHalo, ox = r * 32 + lane + kHalo;
 
-    // ---- smoothness: forward terms owned by (y,x), gradient gathered from the 14 stencils touching it
-    float g_q;
-    {
-      auto Q = [&](int dy, int dx) { return qt[ty + dy][txx + dx]; };
-      auto d2 = [&](float a, float bb, float c) { return __fsub_rn(__fsub_rn(c, bb), __fsub_rn(bb, a)); };
-      auto mixed = [&](int dy, int dx, float& vxy, float& vyx) {
-        const float q00 = Q(dy, dx), q01 = Q(dy, dx + 1), q10 = Q(dy + 1, dx), q11 = Q(dy + 1, dx + 1);
-        vxy = __fsub_rn(__fsub_rn(q11, q10), __fsub_rn(q01, q00));
-        vyx = __fsub_rn(__fsub_rn(q11, q01), __fsub_rn(q10, q00));
-      };
-      const bool xm2 = x >= 2 && x < W, xm1 = x >= 1 && x + 1 < W, x0 = x + 2 < W;
-      const bool ym2 = y >= 2, ym1 = y >= 1 && y + 1 < H, y0 = y + 2 < H;
-      const float qc = Q(0, 0);
-      const float vx0 = x0 ? d2(qc, Q(0, 1), Q(0, 2)) : 0.f;
-      const float vx1 = xm1 ? d2(Q(0, -1), qc, Q(0, 1)) : 0.f;
-      const float vx2 = xm2 ? d2(Q(0, -2), Q(0, -1), qc) : 0.f;
-      const float vy0 = y0 ? d2(qc, Q(1, 0), Q(2, 0)) : 0.f;
-      const float vy1 = ym1 ? d2(Q(-1, 0), qc, Q(1, 0)) : 0.f;
-      const float vy2 = ym2 ? d2(Q(-2, 0), Q(-1, 0), qc) : 0.f;
-      float a00 = 0.f, b00 = 0.f, a01 = 0.f, b01 = 0.f, a10 = 0.f, b10 = 0.f, a11 = 0.f, b11 = 0.f;
-      const bool cx0 = x + 1 < W, cx1 = x >= 1, cy0 = y + 1 < H, cy1 = y >= 1;
-      if (cy0 && cx0) mixed(0, 0, a00, b00);
-      if (cy0 && cx1) mixed(0, -1, a01, b01);
-      if (cy1 && cx0) mixed(-1, 0, a10, b10);
-      if (cy1 && cx1) mixed(-1, -1, a11, b11);
-      sm_sum += cxx * fabsf(vx0) + cyy * fabsf(vy0) + cxy * fabsf(a00) + cyx * fabsf(b00);
-      g_q = cxx * (sgn(vx0) - 2.f * sgn(vx1) + sgn(vx2)) + cyy * (sgn(vy0) - 2.f * sgn(vy1) + sgn(vy2)) +
-            cxy * (sgn(a00) - sgn(a01) - sgn(a10) + sgn(a11)) + cyx * (sgn(b00) - sgn(b01) - sgn(b10) + sgn(b11));
-    }
+    // ---- smoothness, pass 2: gradient = the published signs of the 10 stencils this element is part of
+    const float g_q = (sA[oy][ox] - 2.f * sA[oy][ox - 1] + sA[oy][ox - 2]) +
+                      (sB[oy][ox] - 2.f * sB[oy - 1][ox] + sB[oy - 2][ox]) +
+                      (sC[oy][ox] - sC[oy][ox - 1] - sC[oy - 1][ox] + sC[oy - 1][ox - 1]);
 
     // ---- depth of this pixel and d(depth)/dx, d(q)/dx
-    const float qc = qt[ty][txx];
+    const float qc = qt[oy][ox];
     float d, dd_dx, dq_dx;
     if (P.smooth_on_inverse) {
       dq_dx = -qc * qc;
       if (P.depth_is_inverse) { d = qc; dd_dx = dq_dx; }
-      else { d = xs[(size_t)y * W + x]; dd_dx = 1.f; }
+      else { d = xs[pofs]; dd_dx = 1.f; }
     } else {
       dq_dx = 1.f;
       if (P.depth_is_inverse) { d = __fdiv_rn(1.0f, qc); dd_dx = -d * d; }
@@ -152,66 +178,104 @@ loss_fused_kernel(const LossParams P) {
 
     const float gx = grid_coord(x, W, wstep);
     const float* __restrict__ tp = P.tgt[s] + pix * 3;
-    const float t0 = tp[0], t1 = tp[1], t2 = tp[2];
+    const float tt[3] = {tp[0], tp[1], tp[2]};
     const float dgx = d * gx;
+    // K^-1 is the same for every view of a scale
+    float r0, r1, r2;
+    if (EXACT) {
+      Ray ray = back_project(sxf[0].kinv, gx, gy);
+      r0 = ray.r0; r1 = ray.r1; r2 = ray.r2;
+    } else {
+      const float* k = sxf[0].kinv;
+      r0 = fmaf(k[0], gx, fmaf(k[1], gy, k[2]));
+      r1 = fmaf(k[3], gx, fmaf(k[4], gy, k[5]));
+      r2 = fmaf(k[6], gx, fmaf(k[7], gy, k[8]));
+    }
+    const float c0 = __fmul_rn(r0, d), c1 = __fmul_rn(r1, d), c2 = __fmul_rn(r2, d);
     float g_d = 0.f;
 
 #pragma unroll
     for (int v = 0; v < V; ++v) {
-      const Xform& xf = sxf[v];
-      Ray ray = back_project(xf.kinv, gx, gy);
-      Proj q = project(xf.p, __fmul_rn(ray.r0, d), __fmul_rn(ray.r1, d), __fmul_rn(ray.r2, d));
-      Foot f = footprint(q.x, q.y, W, H);
-      const float* __restrict__ sb = P.src[v][s] + (size_t)b * H * W * 3;
-      const float* __restrict__ p00 = sb + ((size_t)f.y0 * W + f.x0) * 3;
-      const float* __restrict__ p01 = sb + ((size_t)f.y1 * W + f.x0) * 3;
-      const float* __restrict__ p10 = sb + ((size_t)f.y0 * W + f.x1) * 3;
-      const float* __restrict__ p11 = sb + ((size_t)f.y1 * W + f.x1) * 3;
+      const float* __restrict__ pp = sxf[v].p;
+      float qx, qy, rz;
+      if (EXACT) {
+        Proj q = project(pp, c0, c1, c2);
+        qx = q.x; qy = q.y; rz = 1.0f / q.zp;
+      } else {
+        const float u0 = fmaf(pp[0], c0, fmaf(pp[1], c1, fmaf(pp[2], c2, pp[3])));
+        const float u1 = fmaf(pp[4], c0, fmaf(pp[5], c1, fmaf(pp[6], c2, pp[7])));
+        const float u2 = fmaf(pp[8], c0, fmaf(pp[9], c1, fmaf(pp[10], c2, pp[11])));
+        rz = __fdividef(1.0f, u2 + kEpsZ);
+        qx = u0 * rz; qy = u1 * rz;
+      }
+      const Foot f = footprint(qx, qy, W, H);
+      const float* __restrict__ p00 = P.src[v][s] + (img_off + (size_t)(f.y0 * W + f.x0)) * 3;
+      const int dxo = (f.x1 - f.x0) * 3, dyo = (f.y1 - f.y0) * W * 3;
+      const float* __restrict__ p10 = p00 + dxo;
+      const float* __restrict__ p01 = p00 + dyo;
+      const float* __restrict__ p11 = p01 + dxo;
       float i00[3], i01[3], i10[3], i11[3];
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        i00[c] = __ldg(p00 + c); i01[c] = __ldg(p01 + c); i10[c] = __ldg(p10 + c); i11[c] = __ldg(p11 + c);
+        i00[c] = __ldg(p00 + c); i10[c] = __ldg(p10 + c); i01[c] = __ldg(p01 + c); i11[c] = __ldg(p11 + c);
       }
-      // mask value m and its logits
+      // mask value m (explainability softmax or constant) and the regulariser
       float m = 1.f, p0 = 0.f, p1 = 0.f;
-      float2 lg = make_float2(0.f, 0.f);
       if (P.mask_mode == VSL_MASK_EXP) {
-        lg = *reinterpret_cast<const float2*>(P.logits[s] + pix * (2 * V) + 2 * v);
-        const float mx = fmaxf(lg.x, lg.y);
-        const float e0 = expf(lg.x - mx), e1 = expf(lg.y - mx), se = e0 + e1;
-        p0 = e0 / se; p1 = e1 / se;
+        const float2 lg = *reinterpret_cast<const float2*>(P.logits[s] + pix * (2 * V) + 2 * v);
+        if (EXACT) {
+          const float mx = fmaxf(lg.x, lg.y);
+          const float e0 = expf(lg.x - mx), e1 = expf(lg.y - mx), se = e0 + e1;
+          p0 = e0 / se; p1 = e1 / se;
+          exp_sum += (mx + logf(se)) - lg.y;
+        } else {
+          const float z = lg.x - lg.y;
+          const float t = __expf(-fabsf(z)), se = 1.f + t, big = __fdividef(1.f, se), small = t * big;
+          p0 = z >= 0.f ? big : small;
+          p1 = z >= 0.f ? small : big;
+          exp_sum += __logf(se) + fmaxf(z, 0.f);
+        }
         m = p1;
-        exp_sum += (mx + logf(se)) - lg.y;
       } else if (P.mask_mode == VSL_MASK_CONST) {
         m = P.mask[s][pix];
       }
       const float w00 = __fmul_rn(f.wx0, f.wy0), w01 = __fmul_rn(f.wx0, f.wy1), w10 = __fmul_rn(f.wx1, f.wy0),
                   w11 = __fmul_rn(f.wx1, f.wy1);
-      const float tt[3] = {t0, t1, t2};
+      const float ax0 = f.wy0 * f.mx1, bx0 = f.wy0 * f.mx0, ax1 = f.wy1 * f.mx1, bx1 = f.wy1 * f.mx0;
+      const float ay0 = f.wx0 * f.my1, by0 = f.wx0 * f.my0, ay1 = f.wx1 * f.my1, by1 = f.wx1 * f.my0;
       float E = 0.f, dx = 0.f, dy = 0.f;
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        const float e = blend(w00, w01, w10, w11, i00[c], i01[c], i10[c], i11[c]) - tt[c];
+        const float wv = EXACT ? blend(w00, w01, w10, w11, i00[c], i01[c], i10[c], i11[c])
+                               : fmaf(w11, i11[c], fmaf(w10, i10[c], fmaf(w01, i01[c], w00 * i00[c])));
+        const float e = wv - tt[c];
         E += fabsf(e);
-        const float g = sgn(e);
-        dx += g * (f.wy0 * (f.mx1 * i10[c] - f.mx0 * i00[c]) + f.wy1 * (f.mx1 * i11[c] - f.mx0 * i01[c]));
-        dy += g * (f.wx0 * (f.my1 * i01[c] - f.my0 * i00[c]) + f.wx1 * (f.my1 * i11[c] - f.my0 * i10[c]));
+        const float tx_ = ax0 * i10[c] - bx0 * i00[c] + ax1 * i11[c] - bx1 * i01[c];
+        const float ty_ = ay0 * i01[c] - by0 * i00[c] + ay1 * i11[c] - by1 * i10[c];
+        const float sg = signed_by(1.f, e);
+        dx = fmaf(sg, tx_, dx);
+        dy = fmaf(sg, ty_, dy);
       }
-      pix_sum += m * E;
+      pix_sum = fmaf(m, E, pix_sum);
       if (P.mask_mode == VSL_MASK_EXP) {
         const float g0 = p0 * (cexp - cpix * E * p1);
         *reinterpret_cast<float2*>(P.g_logits[s] + pix * (2 * V) + 2 * v) = make_float2(g0, -g0);
       }
-      const float k = cpix * m / q.zp;
-      const float du0 = dx * k, du1 = dy * k, du2 = -(q.x * du0 + q.y * du1);
-      const float gc0 = du0 * xf.p[0] + du1 * xf.p[4] + du2 * xf.p[8];
-      const float gc1 = du0 * xf.p[1] + du1 * xf.p[5] + du2 * xf.p[9];
-      const float gc2 = du0 * xf.p[2] + du1 * xf.p[6] + du2 * xf.p[10];
-      g_d += gc0 * ray.r0 + gc1 * ray.r1 + gc2 * ray.r2;
-      S1[v][0] += du0 * dgx; S1[v][1] += du1 * dgx; S1[v][2] += du2 * dgx;
-      S2[v][0] += du0 * d;   S2[v][1] += du1 * d;   S2[v][2] += du2 * d;
-      S3[v][0] += du0;       S3[v][1] += du1;       S3[v][2] += du2;
+      const float k = cpix * m * rz;
+      const float du0 = dx * k, du1 = dy * k, du2 = -(qx * du0 + qy * du1);
+      if (EXACT) {
+        const float gc0 = du0 * pp[0] + du1 * pp[4] + du2 * pp[8];
+        const float gc1 = du0 * pp[1] + du1 * pp[5] + du2 * pp[9];
+        const float gc2 = du0 * pp[2] + du1 * pp[6] + du2 * pp[10];
+        g_d += gc0 * r0 + gc1 * r1 + gc2 * r2;
+      } else {
+        g_d -= du0 * pp[3] + du1 * pp[7] + du2 * pp[11];  // <du, M ray> = <du, u - t> / d and <du, u> = 0
+      }
+      S1[v][0] = fmaf(du0, dgx, S1[v][0]); S1[v][1] = fmaf(du1, dgx, S1[v][1]); S1[v][2] = fmaf(du2, dgx, S1[v][2]);
+      S2[v][0] = fmaf(du0, d, S2[v][0]);   S2[v][1] = fmaf(du1, d, S2[v][1]);   S2[v][2] = fmaf(du2, d, S2[v][2]);
+      S3[v][0] += du0;                     S3[v][1] += du1;                     S3[v][2] += du2;
     }
+    if (!EXACT) g_d = __fdividef(g_d, d);
     P.g_x[s][pix] = g_d * dd_dx + g_q * dq_dx;
   }
 
@@ -231,74 +295,69 @@ loss_fused_kernel(const LossParams P) {
 }
 
 // grid = B + 1 blocks of 128 threads.  Block b < B: pose gradients of batch element b (all views).
-// Block B: the three loss scalars.  Everything is summed in a fixed order in double.
+// Block B: the three loss scalars.  Every sum runs in a fixed order in double => deterministic.
 template <int V>
 __global__ void __launch_bounds__(128)
 loss_finalize_kernel(const LossParams P, const float* __restrict__ poses, const float* __restrict__ K_pyr,
                      int pose_format, float inv_loss_scale, float* __restrict__ losses, float* __restrict__ g_poses) {
   constexpr int N = NT<V>::value;
-  __shared__ double sh[128];
-  auto block_dsum = [&](double v) -> double {
-    sh[threadIdx.x] = v;
-    __syncthreads();
-    for (int o = 64; o > 0; o >>= 1) {
-      if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
-      __syncthreads();
-    }
-    double r = sh[0];
-    __syncthreads();
-    return r;
-  };
+  __shared__ double sh[128 * 3];
+  __shared__ double tsum[VSL_MAX_SCALES * V * 12];
   const int n_items = P.item_begin[P.S];
   if ((int)blockIdx.x == P.B) {
-    for (int t = 0; t < 3; ++t) {
-      double s = 0.0;
-      for (int i = threadIdx.x; i < n_items; i += blockDim.x) s += (double)P.partials[(size_t)i * N + t];
-      s = block_dsum(s);
-      if (threadIdx.x == 0) losses[t] = (float)(s * (double)inv_loss_scale);
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    for (int i = threadIdx.x; i < n_items; i += blockDim.x) {
+      const float* p = P.partials + (size_t)i * N;
+      a0 += (double)p[0]; a1 += (double)p[1]; a2 += (double)p[2];
     }
+    sh[threadIdx.x * 3] = a0; sh[threadIdx.x * 3 + 1] = a1; sh[threadIdx.x * 3 + 2] = a2;
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) {
+      if ((int)threadIdx.x < o)
+        for (int t = 0; t < 3; ++t) sh[threadIdx.x * 3 + t] += sh[(threadIdx.x + o) * 3 + t];
+      __syncthreads();
+    }
+    if (threadIdx.x < 3) losses[threadIdx.x] = (float)(sh[threadIdx.x] * (double)inv_loss_scale);
     return;
   }
   const int b = blockIdx.x;
+  // one thread per (scale, view, component): a serial, fixed-order sum over that image's items
+  for (int e = threadIdx.x; e < P.S * V * 12; e += blockDim.x) {
+    const int k = e % 12, v = (e / 12) % V, s = e / (12 * V);
+    const int per_b = P.bands[s] * P.tiles_x[s];
+    const float* p = P.partials + (size_t)(P.item_begin[s] + b * per_b) * N + 3 + v * 12 + k;
+    double a = 0.0;
+    for (int i = 0; i < per_b; ++i) a += (double)p[(size_t)i * N];
+    tsum[e] = a;
+  }
+  __syncthreads();
+  if ((int)threadIdx.x >= V) return;
+  const int v = threadIdx.x;
   const int psz = (pose_format == VSL_POSE_MATRIX) ? 16 : 6;
-  for (int v = 0; v < V; ++v) {
-    double gT[16];
-    for (int i = 0; i < 16; ++i) gT[i] = 0.0;
-    for (int s = 0; s < P.S; ++s) {
-      const int per_b = P.bands[s] * P.tiles_x[s];
-      const int first = P.item_begin[s] + b * per_b;
-      double t[12];
-      for (int k = 0; k < 12; ++k) {
-        double a = 0.0;
-        for (int i = threadIdx.x; i < per_b; i += blockDim.x)
-          a += (double)P.partials[(size_t)(first + i) * N + 3 + v * 12 + k];
-        t[k] = block_dsum(a);
-      }
-      if (threadIdx.x == 0) {
-        const Xform& xf = P.xf[((size_t)s * V + v) * P.B + b];
-        const float* Ks = K_pyr + ((size_t)b * P.S + s) * 9;
-        double dP[12];
-        for (int i = 0; i < 3; ++i) {
-          for (int j = 0; j < 3; ++j)
-            dP[i * 4 + j] = (double)xf.kinv[j * 3] * t[i] + (double)xf.kinv[j * 3 + 1] * t[3 + i] +
-                            (double)xf.kinv[j * 3 + 2] * t[6 + i];
-          dP[i * 4 + 3] = t[9 + i];
-        }
-        for (int k = 0; k < 3; ++k)
-          for (int j = 0; j < 4; ++j)
-            gT[k * 4 + j] += (double)Ks[k] * dP[j] + (double)Ks[3 + k] * dP[4 + j] + (double)Ks[6 + k] * dP[8 + j];
-      }
+  double gT[16];
+  for (int i = 0; i < 16; ++i) gT[i] = 0.0;
+  for (int s = 0; s < P.S; ++s) {
+    const double* t = tsum + (s * V + v) * 12;
+    const Xform& xf = P.xf[((size_t)s * V + v) * P.B + b];
+    const float* Ks = K_pyr + ((size_t)b * P.S + s) * 9;
+    double dP[12];
+    for (int i = 0; i < 3; ++i) {
+      for (int j = 0; j < 3; ++j)
+        dP[i * 4 + j] = (double)xf.kinv[j * 3] * t[i] + (double)xf.kinv[j * 3 + 1] * t[3 + i] +
+                        (double)xf.kinv[j * 3 + 2] * t[6 + i];
+      dP[i * 4 + 3] = t[9 + i];
     }
-    if (threadIdx.x == 0) {
-      float* out = g_poses + ((size_t)b * V + v) * psz;
-      if (pose_format == VSL_POSE_MATRIX) {
-        for (int i = 0; i < 16; ++i) out[i] = (float)gT[i];
-      } else {
-        float g[6];
-        pose_vec_grad(poses + ((size_t)b * V + v) * 6, pose_format, gT, g);
-        for (int i = 0; i < 6; ++i) out[i] = g[i];
-      }
-    }
+    for (int k = 0; k < 3; ++k)
+      for (int j = 0; j < 4; ++j)
+        gT[k * 4 + j] += (double)Ks[k] * dP[j] + (double)Ks[3 + k] * dP[4 + j] + (double)Ks[6 + k] * dP[8 + j];
+  }
+  float* out = g_poses + ((size_t)b * V + v) * psz;
+  if (pose_format == VSL_POSE_MATRIX) {
+    for (int i = 0; i < 16; ++i) out[i] = (float)gT[i];
+  } else {
+    float g[6];
+    pose_vec_grad(poses + ((size_t)b * V + v) * 6, pose_format, gT, g);
+    for (int i = 0; i < 6; ++i) out[i] = g[i];
   }
 }
 
@@ -318,7 +377,7 @@ struct WsLayout {
 int check_desc(const VslLossDesc* d) {
   VSL_REQUIRE(d, VSL_E_NULL);
   VSL_REQUIRE(d->S >= 1 && d->S <= VSL_MAX_SCALES && d->V >= 1 && d->V <= VSL_MAX_VIEWS, VSL_E_SHAPE);
-  VSL_REQUIRE(d->B > 0 && d->B <= 65535 && d->H > 0 && d->W > 0, VSL_E_SHAPE);
+  VSL_REQUIRE(d->B > 0 && d->B <= 65535 / (VSL_MAX_VIEWS + 1) && d->H > 0 && d->W > 0, VSL_E_SHAPE);
   const int F = 1 << (d->S - 1);
   VSL_REQUIRE(d->H % F == 0 && d->W % F == 0 && (d->H >> (d->S - 1)) >= 3 && (d->W >> (d->S - 1)) >= 3, VSL_E_SHAPE);
   VSL_REQUIRE(d->pose_format >= VSL_POSE_EULER && d->pose_format <= VSL_POSE_MATRIX, VSL_E_FORMAT);
@@ -355,7 +414,8 @@ template <int V>
 int run_loss(const VslLossDesc* d, const WsLayout& L, LossParams& P, const float* poses, const float* K_pyr,
              float* losses, float* g_poses, cudaStream_t st) {
   if (d->ev_main_begin != nullptr) cudaEventRecord((cudaEvent_t)d->ev_main_begin, st);
-  loss_fused_kernel<V><<<L.n_items, 256, 0, st>>>(P);
+  if (d->exact_coords) loss_fused_kernel<V, true><<<L.n_items, 256, 0, st>>>(P);
+  else loss_fused_kernel<V, false><<<L.n_items, 256, 0, st>>>(P);
   if (d->ev_main_end != nullptr) cudaEventRecord((cudaEvent_t)d->ev_main_end, st);
   loss_finalize_kernel<V><<<d->B + 1, 128, 0, st>>>(P, poses, K_pyr, d->pose_format, 1.0f / d->loss_scale,
                                                       losses, g_poses);
@@ -432,21 +492,20 @@ int vsl_loss_fwd_bwd(const VslLossDesc* d, const float* tgt, const float* const*
     P.csm[s][3] = (float)(sw / ((double)d->B * (H - 2) * W));
   }
 
-  // 1. transforms
-  const int nx = d->S * d->V * d->B;
-  prep_xforms_kernel<<<(nx + 63) / 64, 64, 0, st>>>(poses, K_pyr, d->B, d->S, d->V, d->pose_format, xf, nullptr);
-  // 2. image pyramids (target + V sources)
+  // 1 + 2. transforms and the image pyramids (target + V sources) in one launch
+  const PrepJob prep = make_prep(poses, K_pyr, d->B, d->S, d->V, d->pose_format, xf, nullptr);
   if (d->S > 1) {
-    const int F = 1 << (d->S - 1);
-    const int TC = 1024 / F > 128 ? 128 : 1024 / F;
-    dim3 grid((d->W + TC - 1) / TC, d->H / F, d->B);
-    const size_t smem = sizeof(float) * (size_t)F * TC * 3;
+    PyrJob job;
+    job.nimg = d->V + 1;
     for (int i = 0; i <= d->V; ++i) {
-      PyrLevels lv;
-      for (int s = 0; s < VSL_MAX_SCALES; ++s) lv.p[s] = nullptr;
-      for (int s = 1; s < d->S; ++s) lv.p[s] = pyr + L.pyr_img * (size_t)i + L.level_off[s];
-      pyramid_kernel<<<grid, 256, smem, st>>>(i == 0 ? tgt : srcs[i - 1], d->H, d->W, 3, d->S, F, TC, lv);
+      job.img[i] = (i == 0) ? tgt : srcs[i - 1];
+      for (int s = 0; s < VSL_MAX_SCALES; ++s)
+        job.lvl[i][s] = (s >= 1 && s < d->S) ? pyr + L.pyr_img * (size_t)i + L.level_off[s] : nullptr;
     }
+    rc = launch_pyramid(job, prep, d->B, d->H, d->W, 3, d->S, st);
+    if (rc != VSL_OK) return rc;
+  } else {
+    prep_xforms_kernel<<<(prep.n + 63) / 64, 64, 0, st>>>(prep);
   }
   // 3 + 4. fused loss and finalize
   switch (d->V) {

@@ -29,23 +29,40 @@ __global__ void pose_bwd_kernel(const float* __restrict__ vec, const float* __re
 
 // Per (scale, view, batch) transform table: K_s^-1 and rows 0..2 of K4_s . T_v.
 // xf[(s*V + v)*B + b];  K_pyr is [B,S,3,3];  poses is [B,V,6] or [B,V,4,4].
-__global__ void prep_xforms_kernel(const float* __restrict__ poses, const float* __restrict__ K_pyr, int B,
-                                   int S, int V, int format, Xform* __restrict__ xf,
-                                   float* __restrict__ pose_mat /*[B,V,4,4] nullable*/) {
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= S * V * B) return;
-  int b = idx % B, v = (idx / B) % V, s = idx / (B * V);
-  const int psz = (format == VSL_POSE_MATRIX) ? 16 : 6;
+struct PrepJob {
+  const float* poses;
+  const float* K_pyr;
+  Xform* xf;
+  float* pose_mat;  // [B,V,4,4], nullable
+  int B, S, V, format, n;
+};
+
+VSL_DEV void prep_one(const PrepJob& j, int idx) {
+  const int b = idx % j.B, v = (idx / j.B) % j.V, s = idx / (j.B * j.V);
+  const int psz = (j.format == VSL_POSE_MATRIX) ? 16 : 6;
   float T[16], K[9];
-  pose_to_mat(poses + (size_t)(b * V + v) * psz, format, T);
+  pose_to_mat(j.poses + (size_t)(b * j.V + v) * psz, j.format, T);
 #pragma unroll
-  for (int i = 0; i < 9; ++i) K[i] = K_pyr[(size_t)(b * S + s) * 9 + i];
+  for (int i = 0; i < 9; ++i) K[i] = j.K_pyr[(size_t)(b * j.S + s) * 9 + i];
   Xform o;
   inv3_lu(K, o.kinv);
   proj_rows(K, T, o.p);
-  xf[idx] = o;
-  if (pose_mat != nullptr && s == 0)
-    for (int i = 0; i < 16; ++i) pose_mat[(size_t)(b * V + v) * 16 + i] = T[i];
+  j.xf[idx] = o;
+  if (j.pose_mat != nullptr && s == 0)
+    for (int i = 0; i < 16; ++i) j.pose_mat[(size_t)(b * j.V + v) * 16 + i] = T[i];
+}
+
+__global__ void prep_xforms_kernel(const PrepJob j) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < j.n) prep_one(j, idx);
+}
+
+static inline PrepJob make_prep(const float* poses, const float* K_pyr, int B, int S, int V, int format, Xform* xf,
+                                float* pose_mat) {
+  PrepJob j;
+  j.poses = poses; j.K_pyr = K_pyr; j.xf = xf; j.pose_mat = pose_mat;
+  j.B = B; j.S = S; j.V = V; j.format = format; j.n = B * S * V;
+  return j;
 }
 
 // =====================================================================================================
@@ -406,38 +423,80 @@ expreg_bwd_kernel(const float* __restrict__ logits, long long N, float inv_n, co
 }
 
 // =====================================================================================================
-// resize_area pyramid: one pass over level 0 writes every coarser level.  A block stages an F x TC tile
-// (F = 2^(S-1)) in shared memory; each coarser element is the y-outer / x-inner sequential sum of its
-// block of LEVEL-0 values times 1/4^s -- the summation order of TF's ResizeArea, hence bit-exact.
+// resize_area pyramid: ONE launch reads level 0 of up to VSL_MAX_VIEWS+1 images once and writes every
+// coarser level.  A block stages an F x TC tile (F = 2^(S-1)) in shared memory with 16-byte loads; each
+// coarser element is the y-outer / x-inner sequential sum of its block of LEVEL-0 values times 1/4^s -- the
+// summation order of TF's ResizeArea with unit weights, hence bit-exact against the oracle.  The first few
+// blocks also fill the per-(scale, view, batch) transform table when a PrepJob rides along.
 // =====================================================================================================
-struct PyrLevels { float* p[VSL_MAX_SCALES]; };
+struct PyrJob {
+  const float* img[VSL_MAX_VIEWS + 1];
+  float* lvl[VSL_MAX_VIEWS + 1][VSL_MAX_SCALES];  // [image][scale], scale 0 unused
+  int nimg;
+};
 
+template <int C>
 __global__ void __launch_bounds__(256)
-pyramid_kernel(const float* __restrict__ img, int H, int W, int C, int S, int F, int TC, PyrLevels lv) {
-  extern __shared__ float tile[];  // [F][TC*C]
-  const int b = blockIdx.z, y0 = blockIdx.y * F, x0 = blockIdx.x * TC;
+pyramid_kernel(const PyrJob job, const PrepJob prep, int B, int H, int W, int S, int F, int TC) {
+  extern __shared__ float4 tile4[];
+  float* tile = reinterpret_cast<float*>(tile4);  // [F][TC*C]
+  if (prep.n > 0) {
+    const int lb = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    const int idx = lb * blockDim.x + threadIdx.x;
+    if (idx < prep.n) prep_one(prep, idx);
+  }
+  const int im = blockIdx.z / B, b = blockIdx.z - im * B;
+  const int y0 = blockIdx.y * F, x0 = blockIdx.x * TC;
   const int cols = min(TC, W - x0);  // multiple of F
-  const int rowf = cols * C;
-  const float* src = img + ((size_t)b * H + y0) * W * C + (size_t)x0 * C;
-  for (int e = threadIdx.x; e < F * rowf; e += blockDim.x) {
-    const int r = e / rowf, k = e - r * rowf;
-    tile[r * (TC * C) + k] = src[(size_t)r * W * C + k];
+  const int rowf = cols * C, stride = TC * C;
+  const float* __restrict__ src = job.img[im] + ((size_t)b * H + y0) * W * C + (size_t)x0 * C;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool vec = ((W * C) % 4 == 0) && ((x0 * C) % 4 == 0) && (rowf % 4 == 0) &&
+                   ((reinterpret_cast<uintptr_t>(job.img[im]) & 15) == 0);
+  if (vec) {
+    for (int r = warp; r < F; r += 8) {
+      const float4* __restrict__ g = reinterpret_cast<const float4*>(src + (size_t)r * W * C);
+      float4* t = reinterpret_cast<float4*>(tile + r * stride);
+      for (int k = lane; k < rowf / 4; k += 32) t[k] = __ldg(g + k);
+    }
+  } else {
+    for (int r = warp; r < F; r += 8)
+      for (int k = lane; k < rowf; k += 32) tile[r * stride + k] = __ldg(src + (size_t)r * W * C + k);
   }
   __syncthreads();
-  for (int s = 1; s < S; ++s) {
-    const int f = 1 << s, oh = F >> s, ow = cols >> s;
+  // coarsest level first: its elements carry the longest dependent chains
+  int first = 0;
+  for (int s = S - 1; s >= 1; --s) {
+    const int f = 1 << s, oh = F >> s, ow = cols >> s, n = oh * ow * C;
     const float scale = 1.0f / (float)(f * f);
     const int Ws = W >> s, Hs = H >> s;
-    float* dst = lv.p[s] + (((size_t)b * Hs + (y0 >> s)) * Ws + (x0 >> s)) * C;
-    for (int e = threadIdx.x; e < oh * ow * C; e += blockDim.x) {
+    float* __restrict__ dst = job.lvl[im][s] + (((size_t)b * Hs + (y0 >> s)) * Ws + (x0 >> s)) * C;
+    // rotate the thread -> element map so that the short levels land on threads the long ones left idle
+    for (int e = (int)threadIdx.x - first; e < n; e += blockDim.x) {
+      if (e < 0) continue;
       const int c = e % C, ox = (e / C) % ow, oy = e / (C * ow);
-      const float* t = tile + (oy * f) * (TC * C) + (ox * f) * C + c;
+      const float* t = tile + (oy * f) * stride + (ox * f) * C + c;
       float acc = t[0];
       for (int dy = 0; dy < f; ++dy)
-        for (int dx = (dy == 0 ? 1 : 0); dx < f; ++dx) acc = __fadd_rn(acc, t[dy * (TC * C) + dx * C]);
+        for (int dx = (dy == 0 ? 1 : 0); dx < f; ++dx) acc = __fadd_rn(acc, t[dy * stride + dx * C]);
       dst[((size_t)oy * Ws + ox) * C + c] = __fmul_rn(acc, scale);
     }
+    first = (first + n) % (int)blockDim.x;
   }
+}
+
+static int launch_pyramid(const PyrJob& job, const PrepJob& prep, int B, int H, int W, int C, int S, cudaStream_t st) {
+  const int F = 1 << (S - 1);
+  const int TC = 1024 / F > 128 ? 128 : 1024 / F;  // multiple of F for F <= 32
+  dim3 grid((W + TC - 1) / TC, H / F, B * job.nimg);
+  const size_t smem = sizeof(float) * (size_t)F * TC * C;
+  switch (C) {
+    case 1: pyramid_kernel<1><<<grid, 256, smem, st>>>(job, prep, B, H, W, S, F, TC); break;
+    case 2: pyramid_kernel<2><<<grid, 256, smem, st>>>(job, prep, B, H, W, S, F, TC); break;
+    case 3: pyramid_kernel<3><<<grid, 256, smem, st>>>(job, prep, B, H, W, S, F, TC); break;
+    default: pyramid_kernel<4><<<grid, 256, smem, st>>>(job, prep, B, H, W, S, F, TC); break;
+  }
+  return launch_status();
 }
 
 }  // namespace vsl
@@ -505,7 +564,7 @@ int vsl_warp_fwd(const float* img, const float* depth, const float* pose, const 
   VSL_REQUIRE(coords == nullptr || aligned(coords, 8), VSL_E_ALIGN);
   cudaStream_t st = (cudaStream_t)stream;
   Xform* xf = reinterpret_cast<Xform*>(ws);
-  prep_xforms_kernel<<<(B + 63) / 64, 64, 0, st>>>(pose, K, B, 1, 1, format, xf, pose_mat);
+  prep_xforms_kernel<<<(B + 63) / 64, 64, 0, st>>>(make_prep(pose, K, B, 1, 1, format, xf, pose_mat));
   dim3 grid(warp_nblk(H, W), B);
   switch (C) {
     case 1: warp_fwd_kernel<1><<<grid, 256, 0, st>>>(img, depth, xf, H, W, out_img, coords, wmask, src_depth); break;
@@ -526,7 +585,7 @@ int vsl_warp_bwd(const float* img, const float* depth, const float* pose, const 
   cudaStream_t st = (cudaStream_t)stream;
   Xform* xf = reinterpret_cast<Xform*>(ws);
   float* partial = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + round_up(sizeof(Xform) * (size_t)B, 256));
-  prep_xforms_kernel<<<(B + 63) / 64, 64, 0, st>>>(pose, K, B, 1, 1, format, xf, nullptr);
+  prep_xforms_kernel<<<(B + 63) / 64, 64, 0, st>>>(make_prep(pose, K, B, 1, 1, format, xf, nullptr));
   if (g_img != nullptr) {
     cudaError_t e = cudaMemsetAsync(g_img, 0, sizeof(float) * (size_t)B * H * W * C, st);
     if (e != cudaSuccess) return (int)e;
@@ -664,21 +723,21 @@ int vsl_expreg_bwd(const float* logits, long long N, const float* g_loss, float*
 
 int vsl_pyramid(const float* img, int B, int H, int W, int C, int S, float* const* levels, vsl_stream_t stream) {
   VSL_REQUIRE(img && levels, VSL_E_NULL);
-  VSL_REQUIRE(S >= 1 && S <= VSL_MAX_SCALES && B > 0 && B <= 65535 && C >= 1 && C <= 4, VSL_E_SHAPE);
+  VSL_REQUIRE(S >= 1 && S <= VSL_MAX_SCALES && B > 0 && B <= 65535 / (VSL_MAX_VIEWS + 1) && C >= 1 && C <= 4, VSL_E_SHAPE);
   if (S == 1) return VSL_OK;
   const int F = 1 << (S - 1);
   VSL_REQUIRE(H > 0 && W > 0 && H % F == 0 && W % F == 0, VSL_E_SHAPE);
-  PyrLevels lv;
-  for (int s = 0; s < VSL_MAX_SCALES; ++s) lv.p[s] = nullptr;
+  PyrJob job;
+  job.nimg = 1;
+  job.img[0] = img;
+  for (int s = 0; s < VSL_MAX_SCALES; ++s) job.lvl[0][s] = nullptr;
   for (int s = 1; s < S; ++s) {
     VSL_REQUIRE(levels[s - 1], VSL_E_NULL);
-    lv.p[s] = levels[s - 1];
+    job.lvl[0][s] = levels[s - 1];
   }
-  const int TC = 1024 / F > 128 ? 128 : 1024 / F;  // multiple of F for F <= 32
-  dim3 grid((W + TC - 1) / TC, H / F, B);
-  const size_t smem = sizeof(float) * (size_t)F * TC * C;
-  pyramid_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(img, H, W, C, S, F, TC, lv);
-  return launch_status();
+  PrepJob none;
+  none.n = 0;
+  return launch_pyramid(job, none, B, H, W, C, S, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -283,6 +283,7 @@ class LossFlags(object):
         self.pixel_scale_norm = True     # data_weight / 2^s (train.py:135)
         self.depth_is_inverse = True     # warp depth = 1/x (train.py:128)
         self.smooth_on_inverse = False   # smooth(1/x) (train_depth_then_cam_lr.py:217)
+        self.exact_coords = False        # True: reference rounding sequence in the fused kernel (slower)
         self.__dict__.update(kw)
 
 
@@ -299,7 +300,8 @@ class ViewSynthesisPlan(object):
         self.desc = VslLossDesc(B, H, W, S, V, self.fmt, mask_mode, int(flags.pixel_scale_norm),
                                 int(flags.depth_is_inverse), int(flags.smooth_on_inverse),
                                 float(flags.data_weight), float(flags.smooth_weight),
-                                float(flags.explain_reg_weight), float(loss_scale), None, None)
+                                float(flags.explain_reg_weight), float(loss_scale),
+                                int(getattr(flags, 'exact_coords', False)), 0, None, None)
         nbytes = lib.vsl_loss_ws_bytes(self.desc)
         if nbytes == 0:
             raise ValueError('unsupported loss shape B=%d H=%d W=%d S=%d V=%d' % (B, H, W, S, V))
