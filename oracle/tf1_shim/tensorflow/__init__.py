@@ -21,8 +21,9 @@ Where a TF kernel's arithmetic order matters the shim states the convention:
   forward/back substitution.
 * tf.add_n sums left to right.
 * tf.image.resize_area supports integer shrink factors only (all the reference
-  uses); each output is the y-outer/x-inner sequential sum of the block times
-  1/(fy*fx), which is what ResizeArea computes when every overlap weight is 1.
+  uses).  Order of TF's ResizeArea kernel (ComputePatchSum) when every overlap
+  weight is 1: per contributing row the fx values are summed left to right, the
+  fy row sums are accumulated top to bottom, the total is scaled by 1/(fy*fx).
 * tf.gather raises on out-of-range indices like the TF CPU kernel.
 
 `set_float(torch.float64)` makes 'float32' mean float64 so the same reference
@@ -421,9 +422,10 @@ class _Image(object):
         blocks = x.reshape(B, oh, fy, ow, fx, C)
         acc = None
         for dy in np.arange(fy):
-            for dx in np.arange(fx):
-                v = blocks[:, :, dy, :, dx, :]
-                acc = v if acc is None else acc + v
+            row = blocks[:, :, dy, :, 0, :]
+            for dx in np.arange(1, fx):
+                row = row + blocks[:, :, dy, :, dx, :]
+            acc = row if acc is None else acc + row
         scale = torch.tensor(1.0, dtype=_FLOAT) / torch.tensor(float(fy * fx), dtype=_FLOAT)
         return _T(acc * scale)
 

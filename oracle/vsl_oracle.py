@@ -291,17 +291,21 @@ def get_reference_explain_mask(downscaling, batch, height, width, dtype=torch.fl
 
 
 def resize_area(x, oh, ow):
-    """tf.image.resize_area for integer shrink factors (e.g. train_depth_then_cam_lr.py:227-232)."""
+    """tf.image.resize_area for integer shrink factors (e.g. train_depth_then_cam_lr.py:227-232).
+
+    Order of TF's ResizeArea kernel (ComputePatchSum) when every overlap weight is 1: per contributing row the
+    fx values are summed left to right, the fy row sums are accumulated top to bottom, then * 1/(fy*fx)."""
     B, H, W, C = x.shape
     assert H % oh == 0 and W % ow == 0
     fy, fx = H // oh, W // ow
     blk = x.reshape(B, oh, fy, ow, fx, C)
-    acc = None
+    total = None
     for dy in range(fy):
-        for dx in range(fx):
-            v = blk[:, :, dy, :, dx, :]
-            acc = v if acc is None else acc + v
-    return acc * (torch.tensor(1.0, dtype=x.dtype) / torch.tensor(float(fy * fx), dtype=x.dtype))
+        row = blk[:, :, dy, :, 0, :]
+        for dx in range(1, fx):
+            row = row + blk[:, :, dy, :, dx, :]
+        total = row if total is None else total + row
+    return total * (torch.tensor(1.0, dtype=x.dtype) / torch.tensor(float(fy * fx), dtype=x.dtype))
 
 
 # ----------------------------------------------------------------------------

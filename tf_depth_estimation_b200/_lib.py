@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libvsl.so')
+LIB_PATH = os.environ.get('VSL_LIB_PATH') or os.path.join(_HERE, 'libvsl.so')  # override: kernel experiments
 
 POSE_FORMATS = {'eular': 0, 'euler': 0, 'angleaxis': 1, 'matrix': 2}
 MASK_NONE, MASK_EXP, MASK_CONST = 0, 1, 2

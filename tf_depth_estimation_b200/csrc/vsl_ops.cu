@@ -424,10 +424,13 @@ expreg_bwd_kernel(const float* __restrict__ logits, long long N, float inv_n, co
 
 // =====================================================================================================
 // resize_area pyramid: ONE launch reads level 0 of up to VSL_MAX_VIEWS+1 images once and writes every
-// coarser level.  A block stages an F x TC tile (F = 2^(S-1)) in shared memory with 16-byte loads; each
-// coarser element is the y-outer / x-inner sequential sum of its block of LEVEL-0 values times 1/4^s -- the
-// summation order of TF's ResizeArea with unit weights, hence bit-exact against the oracle.  The first few
-// blocks also fill the per-(scale, view, batch) transform table when a PrepJob rides along.
+// coarser level.  A block stages an F x TC tile (F = 2^(S-1)) in shared memory with 16-byte loads.
+// Summation order = TF's ResizeArea (ComputePatchSum) with unit overlap weights: for every output element
+// the f level-0 values of each contributing row are summed left to right, the f row sums are then
+// accumulated top to bottom, and the total is multiplied by 1/f^2 -- always from LEVEL-0 values, never from
+// a coarser level, hence bit-exact against the oracle.  Phase 1 forms the row sums of every level for one
+// F-pixel row segment per thread; phase 2 adds them down the rows, one output element per thread.
+// The first few blocks also fill the per-(scale, view, batch) transform table when a PrepJob rides along.
 // =====================================================================================================
 struct PyrJob {
   const float* img[VSL_MAX_VIEWS + 1];
@@ -435,20 +438,13 @@ struct PyrJob {
   int nimg;
 };
 
-template <int C>
-__global__ void __launch_bounds__(256)
-pyramid_kernel(const PyrJob job, const PrepJob prep, int B, int H, int W, int S, int F, int TC) {
-  extern __shared__ float4 tile4[];
-  float* tile = reinterpret_cast<float*>(tile4);  // [F][TC*C]
-  if (prep.n > 0) {
-    const int lb = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
-    const int idx = lb * blockDim.x + threadIdx.x;
-    if (idx < prep.n) prep_one(prep, idx);
-  }
-  const int im = blockIdx.z / B, b = blockIdx.z - im * B;
-  const int y0 = blockIdx.y * F, x0 = blockIdx.x * TC;
-  const int cols = min(TC, W - x0);  // multiple of F
-  const int rowf = cols * C, stride = TC * C;
+// Tile body.  FULL = the tile is TC columns wide, so every extent below is a compile-time constant.
+template <int C, int LOG2F, int TC, bool FULL>
+VSL_DEV void pyramid_tile(const PyrJob& job, float* tile, int im, int b, int y0, int x0, int cols_rt, int H, int W) {
+  constexpr int F = 1 << LOG2F, S = LOG2F + 1, stride = TC * C;
+  constexpr int tstride = stride + 4;  // level-0 tile rows are skewed by 4 banks (phase 1 walks rows fastest)
+  const int cols = FULL ? TC : cols_rt;  // multiple of F
+  const int rowf = cols * C;
   const float* __restrict__ src = job.img[im] + ((size_t)b * H + y0) * W * C + (size_t)x0 * C;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool vec = ((W * C) % 4 == 0) && ((x0 * C) % 4 == 0) && (rowf % 4 == 0) &&
@@ -456,47 +452,102 @@ pyramid_kernel(const PyrJob job, const PrepJob prep, int B, int H, int W, int S,
   if (vec) {
     for (int r = warp; r < F; r += 8) {
       const float4* __restrict__ g = reinterpret_cast<const float4*>(src + (size_t)r * W * C);
-      float4* t = reinterpret_cast<float4*>(tile + r * stride);
+      float4* t = reinterpret_cast<float4*>(tile + r * tstride);
+#pragma unroll
       for (int k = lane; k < rowf / 4; k += 32) t[k] = __ldg(g + k);
     }
   } else {
     for (int r = warp; r < F; r += 8)
-      for (int k = lane; k < rowf; k += 32) tile[r * stride + k] = __ldg(src + (size_t)r * W * C + k);
+      for (int k = lane; k < rowf; k += 32) tile[r * tstride + k] = __ldg(src + (size_t)r * W * C + k);
   }
   __syncthreads();
-  // coarsest level first: its elements carry the longest dependent chains
-  int first = 0;
+  // row sums of level s live at rs + rs_off(s) as [F][(TC >> s) * C]
+  float* rs = tile + F * tstride;
+  auto rs_off = [](int s) { return F * stride - ((F * stride) >> (s - 1)); };
+  // ---- phase 1: one thread per (row, F-pixel segment, channel); rows fastest so that the threads of a
+  // warp read different rows of the tile (row stride = 1536 B + bank skew from the channel/segment index)
+  const int nseg = cols >> LOG2F;
+  for (int it = threadIdx.x; it < F * nseg * C; it += blockDim.x) {
+    const int r = it & (F - 1), gc = it >> LOG2F;  // gc = g * C + c
+    const int g = gc / C, c = gc - g * C;
+    float a[F];
+#pragma unroll
+    for (int k = 0; k < F; ++k) a[k] = tile[r * tstride + (g * F + k) * C + c];
+#pragma unroll
+    for (int s = 1; s < S; ++s) {
+      const int f = 1 << s;
+      float* out = rs + rs_off(s) + r * (stride >> s) + (g * (F >> s)) * C + c;
+#pragma unroll
+      for (int j = 0; j < (F >> s); ++j) {
+        float acc = a[j * f];
+#pragma unroll
+        for (int k = 1; k < f; ++k) acc = __fadd_rn(acc, a[j * f + k]);
+        out[j * C] = acc;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- phase 2: one thread per output element; consecutive threads write consecutive floats
+#pragma unroll
   for (int s = S - 1; s >= 1; --s) {
-    const int f = 1 << s, oh = F >> s, ow = cols >> s, n = oh * ow * C;
+    const int f = 1 << s, oh = F >> s, rowlen = (cols >> s) * C, rstride = stride >> s;
     const float scale = 1.0f / (float)(f * f);
     const int Ws = W >> s, Hs = H >> s;
     float* __restrict__ dst = job.lvl[im][s] + (((size_t)b * Hs + (y0 >> s)) * Ws + (x0 >> s)) * C;
-    // rotate the thread -> element map so that the short levels land on threads the long ones left idle
-    for (int e = (int)threadIdx.x - first; e < n; e += blockDim.x) {
-      if (e < 0) continue;
-      const int c = e % C, ox = (e / C) % ow, oy = e / (C * ow);
-      const float* t = tile + (oy * f) * stride + (ox * f) * C + c;
+    const float* base = rs + rs_off(s);
+    for (int e = threadIdx.x; e < oh * rowlen; e += blockDim.x) {
+      const int oy = e / rowlen, k = e - oy * rowlen;
+      const float* t = base + (oy * f) * rstride + k;
       float acc = t[0];
-      for (int dy = 0; dy < f; ++dy)
-        for (int dx = (dy == 0 ? 1 : 0); dx < f; ++dx) acc = __fadd_rn(acc, t[dy * stride + dx * C]);
-      dst[((size_t)oy * Ws + ox) * C + c] = __fmul_rn(acc, scale);
+#pragma unroll
+      for (int dy = 1; dy < f; ++dy) acc = __fadd_rn(acc, t[dy * rstride]);
+      dst[(size_t)oy * Ws * C + k] = __fmul_rn(acc, scale);
     }
-    first = (first + n) % (int)blockDim.x;
   }
 }
 
-static int launch_pyramid(const PyrJob& job, const PrepJob& prep, int B, int H, int W, int C, int S, cudaStream_t st) {
+template <int C, int LOG2F>
+__global__ void __launch_bounds__(256)
+pyramid_kernel(const PyrJob job, const PrepJob prep, int B, int H, int W) {
+  constexpr int F = 1 << LOG2F;
+  constexpr int TC = (1024 / F > 128) ? 128 : 1024 / F;  // multiple of F for F <= 32
+  extern __shared__ float4 tile4[];
+  float* tile = reinterpret_cast<float*>(tile4);  // [F][TC*C] level-0 values, then the row sums per level
+  if (prep.n > 0) {
+    const int lb = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    const int idx = lb * blockDim.x + threadIdx.x;
+    if (idx < prep.n) prep_one(prep, idx);
+  }
+  const int im = blockIdx.z / B, b = blockIdx.z - im * B;
+  const int y0 = blockIdx.y * F, x0 = blockIdx.x * TC;
+  const int cols = min(TC, W - x0);
+  if (cols == TC) pyramid_tile<C, LOG2F, TC, true>(job, tile, im, b, y0, x0, cols, H, W);
+  else pyramid_tile<C, LOG2F, TC, false>(job, tile, im, b, y0, x0, cols, H, W);
+}
+
+template <int C>
+static int launch_pyramid_c(const PyrJob& job, const PrepJob& prep, int B, int H, int W, int S, cudaStream_t st) {
   const int F = 1 << (S - 1);
   const int TC = 1024 / F > 128 ? 128 : 1024 / F;  // multiple of F for F <= 32
   dim3 grid((W + TC - 1) / TC, H / F, B * job.nimg);
-  const size_t smem = sizeof(float) * (size_t)F * TC * C;
-  switch (C) {
-    case 1: pyramid_kernel<1><<<grid, 256, smem, st>>>(job, prep, B, H, W, S, F, TC); break;
-    case 2: pyramid_kernel<2><<<grid, 256, smem, st>>>(job, prep, B, H, W, S, F, TC); break;
-    case 3: pyramid_kernel<3><<<grid, 256, smem, st>>>(job, prep, B, H, W, S, F, TC); break;
-    default: pyramid_kernel<4><<<grid, 256, smem, st>>>(job, prep, B, H, W, S, F, TC); break;
+  const size_t smem = sizeof(float) * ((size_t)F * TC * C * 2 + 4 * F);  // skewed tile + row sums
+  switch (S) {
+    case 2: pyramid_kernel<C, 1><<<grid, 256, smem, st>>>(job, prep, B, H, W); break;
+    case 3: pyramid_kernel<C, 2><<<grid, 256, smem, st>>>(job, prep, B, H, W); break;
+    case 4: pyramid_kernel<C, 3><<<grid, 256, smem, st>>>(job, prep, B, H, W); break;
+    case 5: pyramid_kernel<C, 4><<<grid, 256, smem, st>>>(job, prep, B, H, W); break;
+    default: pyramid_kernel<C, 5><<<grid, 256, smem, st>>>(job, prep, B, H, W); break;
   }
   return launch_status();
+}
+
+static int launch_pyramid(const PyrJob& job, const PrepJob& prep, int B, int H, int W, int C, int S, cudaStream_t st) {
+  switch (C) {
+    case 1: return launch_pyramid_c<1>(job, prep, B, H, W, S, st);
+    case 2: return launch_pyramid_c<2>(job, prep, B, H, W, S, st);
+    case 3: return launch_pyramid_c<3>(job, prep, B, H, W, S, st);
+    default: return launch_pyramid_c<4>(job, prep, B, H, W, S, st);
+  }
 }
 
 }  // namespace vsl
