@@ -90,6 +90,29 @@ int vsl_bilinear_bwd(const float* imgs, const float* coords, const float* flowx,
 int vsl_depth_optflow(const float* coords /*[B,H,W,2]*/, int B, int H, int W, float* flowx, float* flowy,
                       vsl_stream_t stream);
 
+/* ---- the geometry building blocks as ops of their own (the warp entry points inline them).  Planar [B,C,H,W]
+ *      layouts as in the reference.
+ *      meshgrid(batch, h, w, is_homogeneous)               utils.py:142-166  -> [B, 3|2, H, W]
+ *      pixel2cam(depth, pixel_coords, K, is_homogeneous)   utils.py:100-119  -> [B, 4|3, H, W]
+ *      cam2pixel(cam_coords, proj)                         utils.py:121-140, utils_lr.py:172-194
+ *                                                          -> coords [B,H,W,2], z_u [B,H,W,1] (nullable)
+ *      axis_angle_to_rotation_matrix(axis, angle)          utils_lr.py:77-103 -> [B,3,3]  */
+int vsl_meshgrid(int B, int H, int W, int homogeneous, float* out, vsl_stream_t stream);
+int vsl_pixel2cam_fwd(const float* depth /*[B,H,W]*/, const float* pixel_coords /*[B,3,H,W]*/,
+                      const float* K /*[B,3,3]*/, int B, int H, int W, int homogeneous, float* cam,
+                      vsl_stream_t stream);
+int vsl_pixel2cam_bwd(const float* pixel_coords, const float* K, const float* g_cam, int B, int H, int W,
+                      int homogeneous, float* g_depth /*[B,H,W]*/, vsl_stream_t stream);
+int vsl_cam2pixel_fwd(const float* cam /*[B,4,H,W]*/, const float* proj /*[B,4,4]*/, int B, int H, int W,
+                      float* coords, float* z, vsl_stream_t stream);
+int vsl_cam2pixel_bwd(const float* cam, const float* proj, const float* g_coords /*nullable*/,
+                      const float* g_z /*nullable*/, int B, int H, int W, float* g_cam /*[B,4,H,W] nullable*/,
+                      float* g_proj /*[B,4,4] nullable*/, vsl_stream_t stream);
+int vsl_axis_angle_fwd(const float* axis /*[B,3]*/, const float* angle /*[B]*/, int B, float* R /*[B,3,3]*/,
+                       vsl_stream_t stream);
+int vsl_axis_angle_bwd(const float* axis, const float* angle, const float* g_R, int B, float* g_axis,
+                       float* g_angle, vsl_stream_t stream);
+
 /* ---- compute_smooth_loss(pred_disp)  my_losses.py:27-36.  x: [B,H,W,C].  With inverse != 0 the loss is
  *      taken on 1/x (train_depth_then_cam_lr.py:217) and g_x is chained through the reciprocal.
  *      loss: one device float.  g_loss: device float (upstream), NULL means 1. */

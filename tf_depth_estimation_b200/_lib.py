@@ -41,6 +41,13 @@ SIGNATURES = {
     'vsl_bilinear_fwd': (ctypes.c_int, [_c_float_p] * 4 + [ctypes.c_int] * 6 + [_c_float_p] * 3 + [_c_stream]),
     'vsl_bilinear_bwd': (ctypes.c_int, [_c_float_p] * 4 + [ctypes.c_int] * 6 + [_c_float_p] * 4 + [_c_stream]),
     'vsl_depth_optflow': (ctypes.c_int, [_c_float_p] + [ctypes.c_int] * 3 + [_c_float_p] * 2 + [_c_stream]),
+    'vsl_meshgrid': (ctypes.c_int, [ctypes.c_int] * 4 + [_c_float_p, _c_stream]),
+    'vsl_pixel2cam_fwd': (ctypes.c_int, [_c_float_p] * 3 + [ctypes.c_int] * 4 + [_c_float_p, _c_stream]),
+    'vsl_pixel2cam_bwd': (ctypes.c_int, [_c_float_p] * 3 + [ctypes.c_int] * 4 + [_c_float_p, _c_stream]),
+    'vsl_cam2pixel_fwd': (ctypes.c_int, [_c_float_p] * 2 + [ctypes.c_int] * 3 + [_c_float_p] * 2 + [_c_stream]),
+    'vsl_cam2pixel_bwd': (ctypes.c_int, [_c_float_p] * 4 + [ctypes.c_int] * 3 + [_c_float_p] * 2 + [_c_stream]),
+    'vsl_axis_angle_fwd': (ctypes.c_int, [_c_float_p] * 2 + [ctypes.c_int, _c_float_p, _c_stream]),
+    'vsl_axis_angle_bwd': (ctypes.c_int, [_c_float_p] * 3 + [ctypes.c_int] + [_c_float_p] * 2 + [_c_stream]),
     'vsl_smooth_ws_bytes': (ctypes.c_size_t, [ctypes.c_int] * 4),
     'vsl_smooth_fwd': (ctypes.c_int, [_c_float_p] + [ctypes.c_int] * 5 + [_c_float_p, ctypes.c_void_p, _c_stream]),
     'vsl_smooth_bwd': (ctypes.c_int, [_c_float_p] + [ctypes.c_int] * 5 + [_c_float_p, _c_float_p, _c_stream]),

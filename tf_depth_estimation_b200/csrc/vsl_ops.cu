@@ -295,6 +295,157 @@ __global__ void depth_optflow_kernel(const float* __restrict__ coords, int H, in
 }
 
 // =====================================================================================================
+// The reference's geometry building blocks as callable ops of their own (the fused warp above inlines them):
+// meshgrid (utils.py:142-166), pixel2cam (utils.py:100-119), cam2pixel (utils.py:121-140, utils_lr.py:172-194),
+// axis_angle_to_rotation_matrix (utils_lr.py:77-103).  Layouts are the reference's planar [B,C,H,W].
+// =====================================================================================================
+__global__ void meshgrid_kernel(int H, int W, int planes, size_t n, float* __restrict__ out) {
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const int j = (int)(e % W), i = (int)((e / W) % H), p = (int)((e / ((size_t)W * H)) % planes);
+  out[e] = p == 0 ? grid_coord(j, W, grid_step(W)) : (p == 1 ? grid_coord(i, H, grid_step(H)) : 1.0f);
+}
+
+// cam[k] = (K^-1 p)[k] * depth (+ a plane of ones).  One thread per pixel; grid.y = batch.
+__global__ void __launch_bounds__(256)
+pixel2cam_fwd_kernel(const float* __restrict__ depth, const float* __restrict__ pc, const float* __restrict__ K,
+                     int HW, int planes, float* __restrict__ cam) {
+  __shared__ float kinv[9];
+  const int b = blockIdx.y;
+  if (threadIdx.x == 0) inv3_lu(K + (size_t)b * 9, kinv);
+  __syncthreads();
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= HW) return;
+  const float* p = pc + (size_t)b * 3 * HW + pix;
+  const float p0 = p[0], p1 = p[HW], p2 = p[2 * (size_t)HW], d = depth[(size_t)b * HW + pix];
+  float* o = cam + (size_t)b * planes * HW + pix;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float r = __fadd_rn(__fadd_rn(__fmul_rn(kinv[k * 3], p0), __fmul_rn(kinv[k * 3 + 1], p1)),
+                              __fmul_rn(kinv[k * 3 + 2], p2));
+    o[(size_t)k * HW] = __fmul_rn(r, d);
+  }
+  if (planes == 4) o[3 * (size_t)HW] = 1.0f;
+}
+
+__global__ void __launch_bounds__(256)
+pixel2cam_bwd_kernel(const float* __restrict__ pc, const float* __restrict__ K, const float* __restrict__ g_cam,
+                     int HW, int planes, float* __restrict__ g_depth) {
+  __shared__ float kinv[9];
+  const int b = blockIdx.y;
+  if (threadIdx.x == 0) inv3_lu(K + (size_t)b * 9, kinv);
+  __syncthreads();
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= HW) return;
+  const float* p = pc + (size_t)b * 3 * HW + pix;
+  const float p0 = p[0], p1 = p[HW], p2 = p[2 * (size_t)HW];
+  const float* g = g_cam + (size_t)b * planes * HW + pix;
+  float acc = 0.f;
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+    acc += g[(size_t)k * HW] * (kinv[k * 3] * p0 + kinv[k * 3 + 1] * p1 + kinv[k * 3 + 2] * p2);
+  g_depth[(size_t)b * HW + pix] = acc;
+}
+
+// u = proj . cam; coords = (u0, u1) / (u2 + eps); z = u2.
+__global__ void __launch_bounds__(256)
+cam2pixel_fwd_kernel(const float* __restrict__ cam, const float* __restrict__ proj, int HW,
+                     float* __restrict__ coords, float* __restrict__ z) {
+  __shared__ float P[12];
+  const int b = blockIdx.y;
+  if (threadIdx.x < 12) P[threadIdx.x] = proj[(size_t)b * 16 + threadIdx.x];
+  __syncthreads();
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= HW) return;
+  const float* c = cam + (size_t)b * 4 * HW + pix;
+  const float c0 = c[0], c1 = c[HW], c2 = c[2 * (size_t)HW], c3 = c[3 * (size_t)HW];
+  float u[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+    u[k] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(P[k * 4], c0), __fmul_rn(P[k * 4 + 1], c1)),
+                               __fmul_rn(P[k * 4 + 2], c2)), __fmul_rn(P[k * 4 + 3], c3));
+  const float zp = __fadd_rn(u[2], kEpsZ);
+  reinterpret_cast<float2*>(coords)[(size_t)b * HW + pix] = make_float2(__fdiv_rn(u[0], zp), __fdiv_rn(u[1], zp));
+  if (z != nullptr) z[(size_t)b * HW + pix] = u[2];
+}
+
+// One block per batch element (deterministic): g_cam per pixel, g_proj rows 0..2 by a block reduction.
+__global__ void __launch_bounds__(256)
+cam2pixel_bwd_kernel(const float* __restrict__ cam, const float* __restrict__ proj, const float* __restrict__ g_coords,
+                     const float* __restrict__ g_z, int HW, float* __restrict__ g_cam, float* __restrict__ g_proj) {
+  __shared__ float P[12];
+  __shared__ float scratch[12 * 8];
+  const int b = blockIdx.x;
+  if (threadIdx.x < 12) P[threadIdx.x] = proj[(size_t)b * 16 + threadIdx.x];
+  __syncthreads();
+  float acc[12];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) acc[k] = 0.f;
+  for (int pix = threadIdx.x; pix < HW; pix += blockDim.x) {
+    const float* c = cam + (size_t)b * 4 * HW + pix;
+    const float cc[4] = {c[0], c[HW], c[2 * (size_t)HW], c[3 * (size_t)HW]};
+    float u[3];
+    for (int k = 0; k < 3; ++k) u[k] = P[k * 4] * cc[0] + P[k * 4 + 1] * cc[1] + P[k * 4 + 2] * cc[2] + P[k * 4 + 3] * cc[3];
+    const float zp = u[2] + kEpsZ;
+    float2 g = make_float2(0.f, 0.f);
+    if (g_coords != nullptr) g = reinterpret_cast<const float2*>(g_coords)[(size_t)b * HW + pix];
+    float du[3];
+    du[0] = g.x / zp; du[1] = g.y / zp;
+    du[2] = -((u[0] / zp) * du[0] + (u[1] / zp) * du[1]);
+    if (g_z != nullptr) du[2] += g_z[(size_t)b * HW + pix];
+    if (g_cam != nullptr)
+      for (int j = 0; j < 4; ++j)
+        g_cam[((size_t)b * 4 + j) * HW + pix] = du[0] * P[j] + du[1] * P[4 + j] + du[2] * P[8 + j];
+    for (int k = 0; k < 3; ++k)
+      for (int j = 0; j < 4; ++j) acc[k * 4 + j] += du[k] * cc[j];
+  }
+  float tot[12];
+  __shared__ float res[12];
+  block_sum<12>(acc, scratch, res);
+  __syncthreads();
+  (void)tot;
+  if (g_proj != nullptr && threadIdx.x < 16) g_proj[(size_t)b * 16 + threadIdx.x] = threadIdx.x < 12 ? res[threadIdx.x] : 0.f;
+}
+
+// R = I + sin(angle) A + (1 - cos(angle)) A.A with A = [axis]x, for an arbitrary (not necessarily unit) axis.
+__global__ void axis_angle_fwd_kernel(const float* __restrict__ axis, const float* __restrict__ angle, int B,
+                                      float* __restrict__ R) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float a0 = axis[b * 3], a1 = axis[b * 3 + 1], a2 = axis[b * 3 + 2], th = angle[b];
+  float A[9] = {0.f, -a2, a1, a2, 0.f, -a0, -a1, a0, 0.f}, AA[9];
+  mm3(A, A, AA);
+  const float s = sinf(th), omc = __fsub_rn(1.0f, cosf(th));
+  for (int i = 0; i < 9; ++i)
+    R[b * 9 + i] = __fadd_rn(__fadd_rn((i % 4 == 0) ? 1.0f : 0.0f, __fmul_rn(s, A[i])), __fmul_rn(omc, AA[i]));
+}
+
+__global__ void axis_angle_bwd_kernel(const float* __restrict__ axis, const float* __restrict__ angle,
+                                      const float* __restrict__ g_R, int B, float* __restrict__ g_axis,
+                                      float* __restrict__ g_angle) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const double a[3] = {axis[b * 3], axis[b * 3 + 1], axis[b * 3 + 2]}, th = angle[b];
+  double A[9] = {0, -a[2], a[1], a[2], 0, -a[0], -a[1], a[0], 0}, AA[9], G[9];
+  for (int i = 0; i < 9; ++i) G[i] = g_R[b * 9 + i];
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
+    double t = 0; for (int k = 0; k < 3; ++k) t += A[i * 3 + k] * A[k * 3 + j]; AA[i * 3 + j] = t; }
+  const double s = sin(th), c = cos(th);
+  double gs = 0, gomc = 0;
+  for (int i = 0; i < 9; ++i) { gs += G[i] * A[i]; gomc += G[i] * AA[i]; }
+  g_angle[b] = (float)(gs * c + gomc * s);
+  double dA[9];
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
+    double t = 0;
+    for (int k = 0; k < 3; ++k) t += G[i * 3 + k] * A[j * 3 + k] + A[k * 3 + i] * G[k * 3 + j];
+    dA[i * 3 + j] = s * G[i * 3 + j] + (1 - c) * t;
+  }
+  g_axis[b * 3] = (float)(-(dA[5] - dA[7]));
+  g_axis[b * 3 + 1] = (float)(dA[2] - dA[6]);
+  g_axis[b * 3 + 2] = (float)(-(dA[1] - dA[3]));
+}
+
+// =====================================================================================================
 // compute_smooth_loss  (my_losses.py:27-36).  x is [B,H,W,C]; the stencil runs over (H,W) per channel.
 // Each second difference is owned by its top-left element, so it is counted exactly once.
 // =====================================================================================================
@@ -709,6 +860,67 @@ int vsl_depth_optflow(const float* coords, int B, int H, int W, float* flowx, fl
   VSL_REQUIRE(aligned(coords, 8), VSL_E_ALIGN);
   const size_t n = (size_t)B * H * W;
   depth_optflow_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(coords, H, W, n, flowx, flowy);
+  return launch_status();
+}
+
+int vsl_meshgrid(int B, int H, int W, int homogeneous, float* out, vsl_stream_t stream) {
+  VSL_REQUIRE(out, VSL_E_NULL);
+  VSL_REQUIRE(B > 0 && H > 1 && W > 1, VSL_E_SHAPE);
+  const int planes = homogeneous ? 3 : 2;
+  const size_t n = (size_t)B * planes * H * W;
+  meshgrid_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(H, W, planes, n, out);
+  return launch_status();
+}
+
+int vsl_pixel2cam_fwd(const float* depth, const float* pixel_coords, const float* K, int B, int H, int W,
+                      int homogeneous, float* cam, vsl_stream_t stream) {
+  VSL_REQUIRE(depth && pixel_coords && K && cam, VSL_E_NULL);
+  VSL_REQUIRE(B > 0 && B <= 65535 && H > 0 && W > 0, VSL_E_SHAPE);
+  dim3 grid((H * W + 255) / 256, B);
+  pixel2cam_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(depth, pixel_coords, K, H * W, homogeneous ? 4 : 3, cam);
+  return launch_status();
+}
+
+int vsl_pixel2cam_bwd(const float* pixel_coords, const float* K, const float* g_cam, int B, int H, int W,
+                      int homogeneous, float* g_depth, vsl_stream_t stream) {
+  VSL_REQUIRE(pixel_coords && K && g_cam && g_depth, VSL_E_NULL);
+  VSL_REQUIRE(B > 0 && B <= 65535 && H > 0 && W > 0, VSL_E_SHAPE);
+  dim3 grid((H * W + 255) / 256, B);
+  pixel2cam_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(pixel_coords, K, g_cam, H * W, homogeneous ? 4 : 3, g_depth);
+  return launch_status();
+}
+
+int vsl_cam2pixel_fwd(const float* cam, const float* proj, int B, int H, int W, float* coords, float* z,
+                      vsl_stream_t stream) {
+  VSL_REQUIRE(cam && proj && coords, VSL_E_NULL);
+  VSL_REQUIRE(B > 0 && B <= 65535 && H > 0 && W > 0, VSL_E_SHAPE);
+  VSL_REQUIRE(aligned(coords, 8), VSL_E_ALIGN);
+  dim3 grid((H * W + 255) / 256, B);
+  cam2pixel_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(cam, proj, H * W, coords, z);
+  return launch_status();
+}
+
+int vsl_cam2pixel_bwd(const float* cam, const float* proj, const float* g_coords, const float* g_z, int B, int H,
+                      int W, float* g_cam, float* g_proj, vsl_stream_t stream) {
+  VSL_REQUIRE(cam && proj, VSL_E_NULL);
+  VSL_REQUIRE(B > 0 && H > 0 && W > 0, VSL_E_SHAPE);
+  VSL_REQUIRE(g_coords == nullptr || aligned(g_coords, 8), VSL_E_ALIGN);
+  cam2pixel_bwd_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(cam, proj, g_coords, g_z, H * W, g_cam, g_proj);
+  return launch_status();
+}
+
+int vsl_axis_angle_fwd(const float* axis, const float* angle, int B, float* R, vsl_stream_t stream) {
+  VSL_REQUIRE(axis && angle && R, VSL_E_NULL);
+  VSL_REQUIRE(B > 0, VSL_E_SHAPE);
+  axis_angle_fwd_kernel<<<(B + 63) / 64, 64, 0, (cudaStream_t)stream>>>(axis, angle, B, R);
+  return launch_status();
+}
+
+int vsl_axis_angle_bwd(const float* axis, const float* angle, const float* g_R, int B, float* g_axis,
+                       float* g_angle, vsl_stream_t stream) {
+  VSL_REQUIRE(axis && angle && g_R && g_axis && g_angle, VSL_E_NULL);
+  VSL_REQUIRE(B > 0, VSL_E_SHAPE);
+  axis_angle_bwd_kernel<<<(B + 63) / 64, 64, 0, (cudaStream_t)stream>>>(axis, angle, g_R, B, g_axis, g_angle);
   return launch_status();
 }
 

@@ -202,6 +202,107 @@ def consistent_depth_loss(src_depth, pred_src_depth, coords):
 
 
 # ----------------------------------------------------------------------------------------------------
+def meshgrid(batch, height, width, is_homogeneous=True, device='cuda'):
+    """utils.py:142-166 -> [B, 3|2, H, W] (the reference's float32 linspace grid, not exact integers)."""
+    out = torch.empty(batch, 3 if is_homogeneous else 2, height, width, device=device)
+    check(_lib.load().vsl_meshgrid(batch, height, width, int(is_homogeneous), out.data_ptr(), _stream()))
+    return out
+
+
+class _Pixel2Cam(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, depth, pc, K, homog):
+        depth, pc, K = _f32(depth, 'depth'), _f32(pc, 'pixel_coords'), _f32(K, 'intrinsics')
+        B, H, W = depth.shape
+        cam = torch.empty(B, 4 if homog else 3, H, W, device=depth.device)
+        check(_lib.load().vsl_pixel2cam_fwd(depth.data_ptr(), pc.data_ptr(), K.data_ptr(), B, H, W, int(homog),
+                                            cam.data_ptr(), _stream()))
+        ctx.save_for_backward(pc, K)
+        ctx.homog = homog
+        return cam
+
+    @staticmethod
+    def backward(ctx, g_cam):
+        pc, K = ctx.saved_tensors
+        B, _, H, W = pc.shape
+        g_depth = torch.empty(B, H, W, device=pc.device)
+        check(_lib.load().vsl_pixel2cam_bwd(pc.data_ptr(), K.data_ptr(), _f32(g_cam, 'g_cam').data_ptr(), B, H, W,
+                                            int(ctx.homog), g_depth.data_ptr(), _stream()))
+        return g_depth, None, None, None
+
+
+def pixel2cam(depth, pixel_coords, intrinsics, is_homogeneous=True):
+    """utils.py:100-119 -> [B, 4|3, H, W].  Differentiable wrt depth."""
+    if depth.dim() != 3 or pixel_coords.dim() != 4 or pixel_coords.shape[1] != 3:
+        raise ValueError('depth [B,H,W] and pixel_coords [B,3,H,W] expected')
+    return _Pixel2Cam.apply(depth, pixel_coords, intrinsics, bool(is_homogeneous))
+
+
+class _Cam2Pixel(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cam, proj):
+        cam, proj = _f32(cam, 'cam_coords'), _f32(proj, 'proj')
+        B, _, H, W = cam.shape
+        coords = torch.empty(B, H, W, 2, device=cam.device)
+        z = torch.empty(B, H, W, 1, device=cam.device)
+        check(_lib.load().vsl_cam2pixel_fwd(cam.data_ptr(), proj.data_ptr(), B, H, W, coords.data_ptr(), z.data_ptr(),
+                                            _stream()))
+        ctx.save_for_backward(cam, proj)
+        return coords, z
+
+    @staticmethod
+    def backward(ctx, g_coords, g_z):
+        cam, proj = ctx.saved_tensors
+        B, _, H, W = cam.shape
+        g_cam = torch.empty_like(cam) if ctx.needs_input_grad[0] else None
+        g_proj = torch.empty_like(proj) if ctx.needs_input_grad[1] else None
+        gc = None if g_coords is None else _f32(g_coords, 'g_coords')
+        gz = None if g_z is None else _f32(g_z, 'g_z')
+        check(_lib.load().vsl_cam2pixel_bwd(cam.data_ptr(), proj.data_ptr(), _p(gc), _p(gz), B, H, W, _p(g_cam),
+                                            _p(g_proj), _stream()))
+        return g_cam, g_proj
+
+
+def cam2pixel(cam_coords, proj):
+    """utils_lr.py:172-194 -> (pixel_coords [B,H,W,2], z_u [B,H,W,1])."""
+    if cam_coords.dim() != 4 or cam_coords.shape[1] != 4 or tuple(proj.shape) != (cam_coords.shape[0], 4, 4):
+        raise ValueError('cam_coords [B,4,H,W] and proj [B,4,4] expected')
+    return _Cam2Pixel.apply(cam_coords, proj)
+
+
+class _AxisAngle(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, axis, angle):
+        axis, angle = _f32(axis, 'axis'), _f32(angle, 'angle')
+        B = axis.shape[0]
+        R = torch.empty(B, 3, 3, device=axis.device)
+        check(_lib.load().vsl_axis_angle_fwd(axis.data_ptr(), angle.data_ptr(), B, R.data_ptr(), _stream()))
+        ctx.save_for_backward(axis, angle)
+        return R
+
+    @staticmethod
+    def backward(ctx, g_R):
+        axis, angle = ctx.saved_tensors
+        g_axis, g_angle = torch.empty_like(axis), torch.empty_like(angle)
+        check(_lib.load().vsl_axis_angle_bwd(axis.data_ptr(), angle.data_ptr(), _f32(g_R, 'g_R').data_ptr(),
+                                             axis.shape[0], g_axis.data_ptr(), g_angle.data_ptr(), _stream()))
+        return g_axis, g_angle
+
+
+def axis_angle_to_rotation_matrix(axis, angle):
+    """utils_lr.py:77-103: axis [B,3], angle [B,1,1] -> I + sin(angle) [axis]x + (1-cos(angle)) [axis]x^2."""
+    if axis.dim() != 2 or axis.shape[1] != 3 or angle.numel() != axis.shape[0]:
+        raise ValueError('axis [B,3] and angle [B,1,1] expected')
+    return _AxisAngle.apply(axis, angle.reshape(-1)).reshape(-1, 3, 3)
+
+
+def euler2mat(z, y, x):
+    """utils.py:26-75: z, y, x [B,1] -> R = Rx.Ry.Rz [B,1,3,3] (angles clipped to +-pi)."""
+    vec = torch.cat([torch.zeros(z.shape[0], 3, device=z.device), x.reshape(-1, 1), y.reshape(-1, 1), z.reshape(-1, 1)], 1)
+    return pose_vec2mat(vec, 'eular')[:, :3, :3].unsqueeze(1)
+
+
+# ----------------------------------------------------------------------------------------------------
 class _SmoothLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, inverse):
