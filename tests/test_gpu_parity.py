@@ -204,7 +204,7 @@ def test_fused_exact_mode_matches_standalone_warp_bitwise(golden):
                                              cu(c.K_pyr[:, 0]), 'eular')[0]
         pixel = pixel + (warped - cu(c.tgt)).abs().mean()
     pixel.backward()
-    assert abs(float(losses[0]) - float(pixel)) <= 2e-7 * float(pixel)
+    assert abs(float(losses[0]) - float(pixel.detach())) <= 2e-7 * float(pixel.detach())
     assert rel_err(x.grad, x2.grad) <= 1e-6 and rel_err(ps.grad, ps2.grad) <= 1e-5
 
 
@@ -347,3 +347,59 @@ def test_no_cpu_fallback():
         ops.bilinear_sampler(d['srcs'][0], torch.zeros(1, 16, 32, 2))
     with pytest.raises(TypeError):
         ops.compute_smooth_loss(d['disp_pyr'][0].double().to(DEV))
+
+
+@pytest.mark.parametrize('B,H,W,S,V,fmt,mode', [
+    (2, 24, 36, 3, 1, 'eular', 'exp'),        # one view; 36 -> 18 -> 9: W % 4 != 0 at the coarse scales (unstaged path)
+    (1, 32, 72, 4, 3, 'angleaxis', 'exp'),    # three views (butterfly reduction with N = 39)
+    (2, 16, 48, 2, 4, 'matrix', 'none'),      # four views, matrix poses, no mask
+    (1, 64, 96, 5, 2, 'eular', 'const'),      # five scales (F = 16), constant validity mask
+    (3, 40, 44, 3, 2, 'eular', 'exp'),        # W = 44: ragged tiles, odd coarse widths (11)
+])
+def test_fused_shape_sweep_against_oracle(B, H, W, S, V, fmt, mode):
+    """Views 1..4, scales 2..5, widths that are not multiples of 32 / 4, every pose format and mask mode."""
+    d = synth.make_snippets(B, H, W, S=S, V=V, seed=100 + V + S, motion=1.5)
+    g = torch.Generator().manual_seed(7)
+    poses = d['poses']
+    if fmt == 'matrix':
+        poses = torch.stack([O.pose_vec2mat(d['poses'][:, v], 'eular') for v in range(V)], 1)
+    masks = [torch.rand(B, H >> s, W >> s, 1, generator=g) for s in range(S)]
+    for exact in (False, True):
+        flags = ops.LossFlags(num_scales=S, pose_format=fmt, exact_coords=exact, smooth_weight=0.3)
+        of = O.LossFlags(num_scales=S, pose_format=fmt, smooth_weight=0.3)
+        xs = [cu(x, True) for x in d['disp_pyr']]
+        ps = cu(poses, True)
+        lgs = [cu(l, True) for l in d['logits_pyr']] if mode == 'exp' else None
+        total, losses = ops.view_synthesis_loss(cu(d['tgt']), [cu(s) for s in d['srcs']], xs, ps, cu(d['K_pyr']),
+                                                logits_pyr=lgs, mask_pyr=[cu(m) for m in masks] if mode == 'const' else None,
+                                                flags=flags)
+        total.backward()
+        oxs = [x.double().requires_grad_() for x in d['disp_pyr']]
+        op_ = poses.double().requires_grad_()
+        ol = [l.double().requires_grad_() for l in d['logits_pyr']] if mode == 'exp' else None
+        ref = O.view_synthesis_loss(d['tgt'].double(), [s.double() for s in d['srcs']], oxs, op_, d['K_pyr'].double(),
+                                    ol, [m.double() for m in masks] if mode == 'const' else None, of)
+        sum(ref).backward()
+        for got, want in zip(losses.tolist(), ref):
+            assert abs(got - float(want)) <= 1e-5 * abs(float(want)) + 1e-9, (exact, got, float(want))
+        if fmt == 'matrix':
+            assert rel_err(ps.grad[:, :, :3], op_.grad[:, :, :3]) <= 1e-4   # row 3 of T never reaches the coordinates
+        else:
+            assert rel_err(ps.grad, op_.grad) <= 1e-4
+        ok = smooth_pixels(d['tgt'], d['srcs'], d['disp_pyr'], poses, d['K_pyr'], flags)
+        for s in range(S):
+            all_views = torch.stack(ok[s]).all(0)
+            assert masked_rel_err(xs[s].grad, oxs[s].grad, all_views.unsqueeze(3)) <= 1e-4, (exact, s)
+            if mode == 'exp':
+                m = torch.stack([o for o in ok[s] for _ in (0, 1)], dim=3)
+                assert masked_rel_err(lgs[s].grad, ol[s].grad, m) <= 1e-4, (exact, s)
+
+
+def test_pyramid_shapes_bit_exact():
+    """resize_area levels for 1..4 channels and 2..6 scales against the oracle's summation order."""
+    g = torch.Generator().manual_seed(11)
+    for C, S, H, W in ((3, 4, 16, 40), (1, 3, 8, 12), (4, 2, 6, 10), (2, 5, 32, 48), (3, 6, 64, 96), (3, 2, 10, 14)):
+        img = torch.rand(2, H, W, C, generator=g)
+        lv = ops.image_pyramid(cu(img), S)
+        for s in range(1, S):
+            assert torch.equal(lv[s].cpu(), O.resize_area(img, H >> s, W >> s)), (C, S, s)

@@ -46,6 +46,60 @@ VSL_DEV void block_sum(float (&v)[N], float* scratch, float* out) {
   }
 }
 
+// Butterfly ("transpose") reduction of N per-thread values: every step halves the number of values a lane
+// carries by trading one half for the partner's other half, so the warp needs ~N shuffles instead of 5 N.
+// After the five steps lane l holds BflySizes<N>::h5 slots; bfly_index<N>(l, j) names the value in slot j.
+template <int SZ, int OFF>
+VSL_DEV void bfly_step(float* v, int lane) {
+  constexpr int H = (SZ + 1) / 2;
+  const bool up = (lane & OFF) != 0;  // upper lanes keep [H, SZ), lower lanes keep [0, H)
+#pragma unroll
+  for (int i = 0; i < H; ++i) {
+    const float lo = v[i], hi = (i + H < SZ) ? v[i + H] : 0.f;
+    const float keep = up ? hi : lo, send = up ? lo : hi;
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
+  }
+}
+template <int N> struct BflySizes {
+  static constexpr int h1 = (N + 1) / 2, h2 = (h1 + 1) / 2, h3 = (h2 + 1) / 2, h4 = (h3 + 1) / 2, h5 = (h4 + 1) / 2;
+};
+// Value index of slot j of this lane after the five steps, or -1 if the slot is padding (a level of odd
+// size gives its upper half one slot less).
+template <int N>
+VSL_DEV int bfly_index(int lane, int j) {
+  using Z = BflySizes<N>;
+  int li = j + ((lane & 1) ? Z::h5 : 0);
+  bool ok = li < Z::h4;
+  li += (lane & 2) ? Z::h4 : 0; ok = ok && li < Z::h3;
+  li += (lane & 4) ? Z::h3 : 0; ok = ok && li < Z::h2;
+  li += (lane & 8) ? Z::h2 : 0; ok = ok && li < Z::h1;
+  li += (lane & 16) ? Z::h1 : 0; ok = ok && li < N;
+  return ok ? li : -1;
+}
+// Block sum with the butterfly inside each warp; totals land in out[0..N) (written by threads < N).
+// `scratch` holds N * (blockDim.x / 32) floats.  Fixed order => deterministic.
+template <int N>
+VSL_DEV void block_sum_bfly(float (&v)[N], float* scratch, float* out) {
+  using Z = BflySizes<N>;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  bfly_step<N, 16>(v, lane);
+  bfly_step<Z::h1, 8>(v, lane);
+  bfly_step<Z::h2, 4>(v, lane);
+  bfly_step<Z::h3, 2>(v, lane);
+  bfly_step<Z::h4, 1>(v, lane);
+#pragma unroll
+  for (int j = 0; j < Z::h5; ++j) {
+    const int idx = bfly_index<N>(lane, j);
+    if (idx >= 0) scratch[warp * N + idx] = v[j];
+  }
+  __syncthreads();
+  if (threadIdx.x < N) {
+    float s = 0.f;
+    for (int w = 0; w < nwarp; ++w) s += scratch[w * N + threadIdx.x];
+    out[threadIdx.x] = s;
+  }
+}
+
 VSL_DEV float sgn(float v) { return (v > 0.f) ? 1.f : ((v < 0.f) ? -1.f : 0.f); }  // tf.abs' gradient
 
 }  // namespace vsl

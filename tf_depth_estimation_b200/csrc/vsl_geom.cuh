@@ -206,7 +206,9 @@ __device__ inline void pose_vec_grad(const float* pose, int format, const double
     double a[3] = {pose[3], pose[4], pose[5]};  // x, y, z
     bool in[3];
     for (int i = 0; i < 3; ++i) { in[i] = (a[i] >= -pi && a[i] <= pi); a[i] = fmin(fmax(a[i], -pi), pi); }
-    double cx = cos(a[0]), sx = sin(a[0]), cy = cos(a[1]), sy = sin(a[1]), cz = cos(a[2]), sz = sin(a[2]);
+    // fp32 sin/cos (FP64 transcendentals are slow on this part and the forward pass is fp32 anyway)
+    double cx = cosf((float)a[0]), sx = sinf((float)a[0]), cy = cosf((float)a[1]), sy = sinf((float)a[1]),
+           cz = cosf((float)a[2]), sz = sinf((float)a[2]);
     double X[9] = {1, 0, 0, 0, cx, -sx, 0, sx, cx}, Y[9] = {cy, 0, sy, 0, 1, 0, -sy, 0, cy},
            Z[9] = {cz, -sz, 0, sz, cz, 0, 0, 0, 1};
     double dX[9] = {0, 0, 0, 0, -sx, -cx, 0, cx, -sx}, dY[9] = {-sy, 0, cy, 0, 0, 0, -cy, 0, -sy},
@@ -227,7 +229,7 @@ __device__ inline void pose_vec_grad(const float* pose, int format, const double
     double A[9] = {0, -a[2], a[1], a[2], 0, -a[0], -a[1], a[0], 0}, AA[9];
     for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
       double s = 0; for (int k = 0; k < 3; ++k) s += A[i * 3 + k] * A[k * 3 + j]; AA[i * 3 + j] = s; }
-    double s = sin(th), c = cos(th), gs = 0, gomc = 0;
+    double s = sinf((float)th), c = cosf((float)th), gs = 0, gomc = 0;
     for (int i = 0; i < 9; ++i) { gs += G[i] * A[i]; gomc += G[i] * AA[i]; }
     double gth = gs * c + gomc * s;
     // dA = s G + (1-c) (G A^T + A^T G)

@@ -6,7 +6,7 @@
 //
 //   1. pyramid_kernel       (vsl_ops.cu)  resize_area levels 1..S-1 of the target and source images, and
 //                                         (riding along) K_s^-1 and P = K4_s . T_v per (scale, view, batch)
-//   2. loss_fused_kernel    (this file)   every scale and view in ONE grid:
+//   2. loss_fused_kernel    (this file)   every scale and view in ONE grid, one block per tile:
 //        per target pixel: smoothness stencil (forward sum + gradient) on a shared-memory tile of x,
 //        then per view: back-project, pose, project, bilinear gather of the source, L1 against the
 //        target, explainability / validity mask, softmax cross-entropy regulariser -- and, because the
@@ -16,9 +16,14 @@
 //   3. loss_finalize_kernel (this file)   fixed-order reduction of the block partials (deterministic),
 //        dT = K4^T dP summed over scales, pose chain rule, the three loss scalars.
 //
-// Work decomposition: an "item" is an 8-row x (32*R)-column tile of one image at one scale; block = 8
-// warps, warp w owns row w, a thread visits R pixels 32 columns apart, so every global access of a warp
-// is a run of 32 consecutive pixels.  Items of all scales live in one 1-D grid, largest scale first.
+// Work decomposition: a tile is 8 rows x (32*R) columns of one image at one scale; block = 8 warps, warp w
+// owns row w, a thread visits R pixels 32 columns apart, so every global access of a warp is a run of 32
+// consecutive pixels.  Tiles of all scales live in one 1-D grid, largest scale first, and the hardware block
+// scheduler balances them (a persistent variant with static cost-balanced ranges measured 10 % slower).
+//
+// Streaming operands (target tile, logits tile) enter shared memory with 16-byte cp.async issued before the
+// smoothness pass, so their latency is covered by it; d/dlogits is assembled in the logits tile in place and
+// leaves with 16-byte stores.  Only the data-dependent bilinear gathers go through L1 as scalar loads.
 #include <algorithm>
 
 #include "vsl_common.cuh"
@@ -26,15 +31,16 @@
 
 namespace vsl {
 
-constexpr int kTH = 8;      // tile rows = warps per block
-constexpr int kMaxR = 4;    // pixels per thread
+constexpr int kTH = 8;                          // tile rows = warps per block
+constexpr int kThreads = 32 * kTH;
+constexpr int kMaxR = 4;                        // pixels per thread
+constexpr int kTW = 32 * kMaxR;                 // tile columns
 constexpr int kHalo = 2;
-constexpr int kTileW = 32 * kMaxR + 2 * kHalo;  // 132 columns of x
 constexpr int kTileH = kTH + 2 * kHalo;         // 12 rows of x
-constexpr int kQStride = kTileW + 4;
-constexpr int kOwnW = 32 * kMaxR + kHalo;       // owners: tile + 2 columns to the left
+constexpr int kQStride = kTW + 2 * kHalo + 4;   // 136
+constexpr int kOwnW = kTW + kHalo;              // owners: tile + 2 columns to the left
 constexpr int kOwnH = kTH + kHalo;              //         tile + 2 rows above
-constexpr int kOStride = kOwnW + 2;
+constexpr int kOStride = kOwnW + 2;             // 132
 
 struct LossParams {
   int B, H, W, S, V;
@@ -53,333 +59,336 @@ struct LossParams {
   float csm[VSL_MAX_SCALES][4];    // loss_scale * smooth_weight / 2^s / count_k   (xx, xy, yx, yy)
   int item_begin[VSL_MAX_SCALES + 1];
   int tiles_x[VSL_MAX_SCALES], bands[VSL_MAX_SCALES], R[VSL_MAX_SCALES];
+  int staged[VSL_MAX_SCALES];      // 1: rows of this scale are 16-byte aligned -> cp.async / vector path
 };
 
 template <int V> struct NT { static constexpr int value = 3 + 12 * V; };
 
-#ifndef VSL_PREFETCH
-#define VSL_PREFETCH 1
-#endif
-VSL_DEV void prefetch_l1(const void* p) {
-#if VSL_PREFETCH == 1
-  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-#elif VSL_PREFETCH == 2
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-#endif
-}
+// dynamic shared memory carve-up (floats)
+template <int V> struct Smem {
+  static constexpr int qt = 0;                                   // [kTileH][kQStride]
+  static constexpr int sA = qt + kTileH * kQStride;              // [kOwnH][kOStride] x 3
+  static constexpr int sB = sA + kOwnH * kOStride;
+  static constexpr int sC = sB + kOwnH * kOStride;
+  static constexpr int xf = sC + kOwnH * kOStride;               // V * 21 (padded to 24)
+  static constexpr int scratch = xf + V * 24;                    // NT * kTH
+  static constexpr int tgt = (scratch + NT<V>::value * kTH + 3) / 4 * 4;   // [kTH][kTW*3], 16-byte aligned
+  static constexpr int lg = tgt + kTH * kTW * 3;                 // [kTH][kTW*2V]
+  static constexpr int total = lg + kTH * kTW * 2 * V;
+  static constexpr size_t bytes = sizeof(float) * total;
+};
 
 VSL_DEV float signed_by(float c, float v) {  // c * sign(v), sign(0) = 0
   return (v == 0.f) ? 0.f : copysignf(c, v);
 }
 
-// First tile whose cumulative cost (in 32-column warp iterations) is >= x.  Tiles are ordered scale-major,
-// then image, band, column tile; a row of tiles at scale s costs ceil(W_s / 32) iterations in total.
-VSL_DEV int tile_at_cost(const LossParams& P, long long x) {
-  long long acc = 0;
-  for (int s = 0; s < P.S; ++s) {
-    const int rw = ((P.W >> s) + 31) >> 5;
-    const long long rows = (long long)P.B * P.bands[s];
-    const long long seg = rows * rw;
-    if (x < acc + seg) {
-      const long long q = (x - acc) / rw;
-      const int rem = (int)((x - acc) - q * rw);
-      return P.item_begin[s] + (int)q * P.tiles_x[s] + (rem + P.R[s] - 1) / P.R[s];
-    }
-    acc += seg;
-  }
-  return P.item_begin[P.S];
+VSL_DEV void cp_async16(float* smem_dst, const float* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+VSL_DEV void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
 // EXACT = true : coordinates, softmax and the warped value follow the reference's rounding sequence
 //                (bit-identical sample positions to the oracle for matrix poses).
 // EXACT = false: the same algebra with FMA contraction, MUFU reciprocal / exp / log and the closed form
 //                d(depth) = -<du, t> / depth; differs from EXACT by a few ulp per quantity.
-//
-// Persistent: the grid is a fixed number of blocks per SM; block c walks a contiguous, cost-balanced range of
-// the tile list, keeps its dP / loss accumulators in registers while the tiles belong to the same (scale,
-// image) and reduces them once per such run into the partial slot of the run's last tile (every other slot
-// it passes is zeroed), so the finalize kernel can add up slots in a fixed order.
 #ifndef VSL_FUSED_MIN_BLOCKS
 #define VSL_FUSED_MIN_BLOCKS 3
 #endif
 template <int V, bool EXACT>
-__global__ void __launch_bounds__(256, VSL_FUSED_MIN_BLOCKS)
-loss_fused_kernel(const LossParams P, long long total_cost) {
+__global__ void __launch_bounds__(kThreads, VSL_FUSED_MIN_BLOCKS)
+loss_fused_kernel(const LossParams P) {
   constexpr int N = NT<V>::value;
-  __shared__ float qt[kTileH][kQStride];     // smoothness operand (x or 1/x) with a 2-pixel halo
-  __shared__ float sA[kOwnH][kOStride];      // cxx * sign(dx2)  of the stencil owned by each element
-  __shared__ float sB[kOwnH][kOStride];      // cyy * sign(dy2)
-  __shared__ float sC[kOwnH][kOStride];      // cxy * sign(dxdy) + cyx * sign(dydx)
-  __shared__ Xform sxf[V];
-  __shared__ float scratch[N * kTH];
+  using L = Smem<V>;
+  extern __shared__ float4 smem4[];
+  float* sm = reinterpret_cast<float*>(smem4);
+  float (*qt)[kQStride] = reinterpret_cast<float (*)[kQStride]>(sm + L::qt);   // x or 1/x with a 2-pixel halo
+  float (*sA)[kOStride] = reinterpret_cast<float (*)[kOStride]>(sm + L::sA);   // cxx * sign(dx2) per owner
+  float (*sB)[kOStride] = reinterpret_cast<float (*)[kOStride]>(sm + L::sB);   // cyy * sign(dy2)
+  float (*sC)[kOStride] = reinterpret_cast<float (*)[kOStride]>(sm + L::sC);   // cxy*sign(dxdy) + cyx*sign(dydx)
+  float* sxf = sm + L::xf;                                                     // per view: kinv[9], p[12]
+  float* scratch = sm + L::scratch;
+  float* s_tgt = sm + L::tgt;
+  float* s_lg = sm + L::lg;
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int t_lo = tile_at_cost(P, total_cost * blockIdx.x / gridDim.x);
-  const int t_hi = tile_at_cost(P, total_cost * (blockIdx.x + 1) / gridDim.x);
+  // ---- which tile
+  const int tile = blockIdx.x;
+  int s = 0;
+  while (s + 1 < P.S && tile >= P.item_begin[s + 1]) ++s;
+  const int local = tile - P.item_begin[s];
+  const int per_b = P.bands[s] * P.tiles_x[s];
+  const int b = local / per_b, rem = local - b * per_b;
+  const int band = rem / P.tiles_x[s], tx = rem - band * P.tiles_x[s];
+  const int H = P.H >> s, W = P.W >> s, R = P.R[s];
+  const int y_base = band * kTH, x_base = tx * 32 * R;
+  const int cols = min(32 * R, W - x_base);            // valid columns of this tile
+  const int tw = ((cols + 31) >> 5) << 5;               // rounded up to whole warp iterations
+  const size_t img_off = (size_t)b * H * W;
+  const int y = y_base + warp;                          // this warp's row
+  const bool staged = P.staged[s] != 0;
+  const bool use_lg = P.mask_mode == VSL_MASK_EXP;
 
-  float pix_sum = 0.f, exp_sum = 0.f, sm_sum = 0.f;
-  float S1[V][3], S2[V][3], S3[V][3], S4[V][3];  // sum du*d*gx, du*d*gy, du*d, du
-  auto reset = [&]() {
-    pix_sum = 0.f; exp_sum = 0.f; sm_sum = 0.f;
-#pragma unroll
-    for (int v = 0; v < V; ++v)
-#pragma unroll
-      for (int i = 0; i < 3; ++i) { S1[v][i] = 0.f; S2[v][i] = 0.f; S3[v][i] = 0.f; S4[v][i] = 0.f; }
-  };
-  reset();
-
-  int s = 0, cur_b = -1, cur_s = -1;
-  float cpix = 0.f, cexp = 0.f;
-  for (int tile = t_lo; tile < t_hi; ++tile) {
-    while (s + 1 < P.S && tile >= P.item_begin[s + 1]) ++s;
-    const int local = tile - P.item_begin[s];
-    const int per_b = P.bands[s] * P.tiles_x[s];
-    const int b = local / per_b, rem = local - b * per_b;
-    const int band = rem / P.tiles_x[s], tx = rem - band * P.tiles_x[s];
-    const int H = P.H >> s, W = P.W >> s, R = P.R[s];
-    const int y_base = band * kTH, x_base = tx * 32 * R;
-    const int tw = min(32 * R, ((W - x_base + 31) >> 5) << 5);  // columns of this tile, rounded up to 32
-    const bool new_run = (b != cur_b) || (s != cur_s);
-
-    __syncthreads();  // the previous tile's readers of shared memory are done
-    // ---- stage the x tile (+halo), and on a new (scale, image) run its V transforms
-    const float* __restrict__ xs = P.x[s] + (size_t)b * H * W;
-    for (int ty = warp; ty < kTileH; ty += kTH) {
-      const int gy = y_base + ty - kHalo;
-      const bool rin = gy >= 0 && gy < H;
-      const float* __restrict__ row = xs + (size_t)(rin ? gy : 0) * W;
-      for (int tc = lane; tc < tw + 2 * kHalo; tc += 32) {
-        const int gx = x_base + tc - kHalo;
-        float v = 0.f;
-        if (rin && gx >= 0 && gx < W) {
-          v = row[gx];
-          if (P.smooth_on_inverse) v = __fdiv_rn(1.0f, v);
-        }
-        qt[ty][tc] = v;
-      }
-    }
-    if (new_run) {
-      if (threadIdx.x < V * 21)
-        reinterpret_cast<float*>(sxf)[threadIdx.x] =
-            reinterpret_cast<const float*>(P.xf + ((size_t)s * V + threadIdx.x / 21) * P.B + b)[threadIdx.x % 21];
-      cur_b = b; cur_s = s;
-      cpix = P.cpix[s]; cexp = P.cexp[s];
-    }
-    __syncthreads();
-
-    // ---- smoothness, pass 1: every element of (tile + 2 rows above + 2 columns left) evaluates the four
-    // second differences it owns (it is their top-left corner) ONCE and publishes their weighted signs.
-    {
-      const float cxx = P.csm[s][0], cxy = P.csm[s][1], cyx = P.csm[s][2], cyy = P.csm[s][3];
-      for (int oy = warp; oy < kOwnH; oy += kTH) {
-        const int gy = y_base - kHalo + oy;
-        const bool rin = gy >= 0 && gy < H;
-        for (int ox = lane; ox < tw + kHalo; ox += 32) {
-          const int gx = x_base - kHalo + ox;
-          const bool in = rin && gx >= 0 && gx < W;
-          const float q00 = qt[oy][ox], q01 = qt[oy][ox + 1], q02 = qt[oy][ox + 2];
-          const float q10 = qt[oy + 1][ox], q11 = qt[oy + 1][ox + 1], q20 = qt[oy + 2][ox];
-          const float dx0 = __fsub_rn(q01, q00), dy0 = __fsub_rn(q10, q00);
-          float dxx = __fsub_rn(__fsub_rn(q02, q01), dx0);
-          float dyy = __fsub_rn(__fsub_rn(q20, q10), dy0);
-          float dxy = __fsub_rn(__fsub_rn(q11, q10), dx0);  // d/dy of dx
-          float dyx = __fsub_rn(__fsub_rn(q11, q01), dy0);  // d/dx of dy
-          if (!(in && gx + 2 < W)) dxx = 0.f;
-          if (!(in && gy + 2 < H)) dyy = 0.f;
-          if (!(in && gx + 1 < W && gy + 1 < H)) { dxy = 0.f; dyx = 0.f; }
-          sA[oy][ox] = signed_by(cxx, dxx);
-          sB[oy][ox] = signed_by(cyy, dyy);
-          sC[oy][ox] = signed_by(cxy, dxy) + signed_by(cyx, dyx);
-          if (oy >= kHalo && ox >= kHalo)
-            sm_sum += cxx * fabsf(dxx) + cyy * fabsf(dyy) + cxy * fabsf(dxy) + cyx * fabsf(dyx);
-        }
-      }
-    }
-    __syncthreads();
-
-    const int y = y_base + warp;
-    const float gy = grid_coord(y, H, grid_step(H));
-    const float wstep = grid_step(W);
-    const size_t img_off = (size_t)b * H * W;
-
-    if (y < H) {
-      for (int r = 0; r * 32 < tw; ++r) {
-        const int x = x_base + r * 32 + lane;
-        if (x >= W) continue;
-        const int pofs = y * W + x;              // pixel offset inside this image
-        const size_t pix = img_off + pofs;
-        const int oy = warp + kHalo, ox = r * 32 + lane + kHalo;
-
-        // ---- smoothness, pass 2: gradient = the published signs of the 10 stencils this element is part of
-        const float g_q = (sA[oy][ox] - 2.f * sA[oy][ox - 1] + sA[oy][ox - 2]) +
-                          (sB[oy][ox] - 2.f * sB[oy - 1][ox] + sB[oy - 2][ox]) +
-                          (sC[oy][ox] - sC[oy][ox - 1] - sC[oy - 1][ox] + sC[oy - 1][ox - 1]);
-
-        // ---- depth of this pixel and d(depth)/dx, d(q)/dx
-        const float qc = qt[oy][ox];
-        float d, dd_dx, dq_dx;
-        if (P.smooth_on_inverse) {
-          dq_dx = -qc * qc;
-          if (P.depth_is_inverse) { d = qc; dd_dx = dq_dx; }
-          else { d = xs[pofs]; dd_dx = 1.f; }
-        } else {
-          dq_dx = 1.f;
-          if (P.depth_is_inverse) { d = __fdiv_rn(1.0f, qc); dd_dx = -d * d; }
-          else { d = qc; dd_dx = 1.f; }
-        }
-
-        const float gx = grid_coord(x, W, wstep);
-        const float* __restrict__ tp = P.tgt[s] + pix * 3;
-        const float tt[3] = {tp[0], tp[1], tp[2]};
-        // the thread's next pixel is 32 columns to the right (next iteration or next tile of this band)
-        const bool more = x + 32 < W;
-        if (more) {
-          prefetch_l1(tp + 96);
-          if (P.mask_mode == VSL_MASK_EXP) prefetch_l1(P.logits[s] + (pix + 32) * (2 * V));
-        }
-        const float dgx = d * gx, dgy = d * gy;
-        // K^-1 is the same for every view of a scale
-        float r0, r1, r2;
-        if (EXACT) {
-          Ray ray = back_project(sxf[0].kinv, gx, gy);
-          r0 = ray.r0; r1 = ray.r1; r2 = ray.r2;
-        } else {
-          const float* k = sxf[0].kinv;
-          r0 = fmaf(k[0], gx, fmaf(k[1], gy, k[2]));
-          r1 = fmaf(k[3], gx, fmaf(k[4], gy, k[5]));
-          r2 = fmaf(k[6], gx, fmaf(k[7], gy, k[8]));
-        }
-        const float c0 = __fmul_rn(r0, d), c1 = __fmul_rn(r1, d), c2 = __fmul_rn(r2, d);
-        float g_d = 0.f;
-
-#pragma unroll
-        for (int v = 0; v < V; ++v) {
-          const float* __restrict__ pp = sxf[v].p;
-          float qx, qy, rz;
-          if (EXACT) {
-            Proj q = project(pp, c0, c1, c2);
-            qx = q.x; qy = q.y; rz = 1.0f / q.zp;
-          } else {
-            const float u0 = fmaf(pp[0], c0, fmaf(pp[1], c1, fmaf(pp[2], c2, pp[3])));
-            const float u1 = fmaf(pp[4], c0, fmaf(pp[5], c1, fmaf(pp[6], c2, pp[7])));
-            const float u2 = fmaf(pp[8], c0, fmaf(pp[9], c1, fmaf(pp[10], c2, pp[11])));
-            rz = __fdividef(1.0f, u2 + kEpsZ);
-            qx = u0 * rz; qy = u1 * rz;
-          }
-          const Foot f = footprint(qx, qy, W, H);
-          const float* __restrict__ p00 = P.src[v][s] + (img_off + (size_t)(f.y0 * W + f.x0)) * 3;
-          const int dxo = (f.x1 - f.x0) * 3, dyo = (f.y1 - f.y0) * W * 3;
-          const float* __restrict__ p10 = p00 + dxo;
-          const float* __restrict__ p01 = p00 + dyo;
-          const float* __restrict__ p11 = p01 + dxo;
-          // guess: the next pixel samples ~32 source columns further on the same two rows (smooth flow)
-          if (more && f.x0 + 34 < W) { prefetch_l1(p00 + 96); prefetch_l1(p01 + 96); }
-          float i00[3], i01[3], i10[3], i11[3];
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            i00[c] = __ldg(p00 + c); i10[c] = __ldg(p10 + c); i01[c] = __ldg(p01 + c); i11[c] = __ldg(p11 + c);
-          }
-          // mask value m (explainability softmax or constant) and the regulariser
-          float m = 1.f, p0 = 0.f, p1 = 0.f;
-          if (P.mask_mode == VSL_MASK_EXP) {
-            const float2 lg = *reinterpret_cast<const float2*>(P.logits[s] + pix * (2 * V) + 2 * v);
-            if (EXACT) {
-              const float mx = fmaxf(lg.x, lg.y);
-              const float e0 = expf(lg.x - mx), e1 = expf(lg.y - mx), se = e0 + e1;
-              p0 = e0 / se; p1 = e1 / se;
-              exp_sum += (mx + logf(se)) - lg.y;
-            } else {
-              const float z = lg.x - lg.y;
-              const float t = __expf(-fabsf(z)), se = 1.f + t, big = __fdividef(1.f, se), small = t * big;
-              p0 = z >= 0.f ? big : small;
-              p1 = z >= 0.f ? small : big;
-              exp_sum += __logf(se) + fmaxf(z, 0.f);
-            }
-            m = p1;
-          } else if (P.mask_mode == VSL_MASK_CONST) {
-            m = P.mask[s][pix];
-          }
-          const float w00 = __fmul_rn(f.wx0, f.wy0), w01 = __fmul_rn(f.wx0, f.wy1),
-                      w10 = __fmul_rn(f.wx1, f.wy0), w11 = __fmul_rn(f.wx1, f.wy1);
-          // E = sum_c |e_c|; J_k = sum_c sign(e_c) * corner_k[c]  (the channel sum commutes with d/dx, d/dy)
-          float E = 0.f, J00 = 0.f, J01 = 0.f, J10 = 0.f, J11 = 0.f;
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            const float wv = EXACT ? blend(w00, w01, w10, w11, i00[c], i01[c], i10[c], i11[c])
-                                   : fmaf(w11, i11[c], fmaf(w10, i10[c], fmaf(w01, i01[c], w00 * i00[c])));
-            const float e = wv - tt[c];
-            E += fabsf(e);
-            const float sg = signed_by(1.f, e);
-            J00 = fmaf(sg, i00[c], J00); J01 = fmaf(sg, i01[c], J01);
-            J10 = fmaf(sg, i10[c], J10); J11 = fmaf(sg, i11[c], J11);
-          }
-          const float ex0 = f.mx1 * J10 - f.mx0 * J00, ex1 = f.mx1 * J11 - f.mx0 * J01;  // d/dx per row
-          const float ey0 = f.my1 * J01 - f.my0 * J00, ey1 = f.my1 * J11 - f.my0 * J10;  // d/dy per column
-          const float dx = f.wy0 * ex0 + f.wy1 * ex1;
-          const float dy = f.wx0 * ey0 + f.wx1 * ey1;
-          pix_sum = fmaf(m, E, pix_sum);
-          if (P.mask_mode == VSL_MASK_EXP) {
-            const float g0 = p0 * (cexp - cpix * E * p1);
-            *reinterpret_cast<float2*>(P.g_logits[s] + pix * (2 * V) + 2 * v) = make_float2(g0, -g0);
-          }
-          const float k = cpix * m * rz;
-          const float du0 = dx * k, du1 = dy * k, du2 = -(qx * du0 + qy * du1);
-          if (EXACT) {
-            const float gc0 = du0 * pp[0] + du1 * pp[4] + du2 * pp[8];
-            const float gc1 = du0 * pp[1] + du1 * pp[5] + du2 * pp[9];
-            const float gc2 = du0 * pp[2] + du1 * pp[6] + du2 * pp[10];
-            g_d += gc0 * r0 + gc1 * r1 + gc2 * r2;
-          } else {
-            g_d -= du0 * pp[3] + du1 * pp[7] + du2 * pp[11];  // <du, M ray> = <du, u - t> / d and <du, u> = 0
-          }
-          S1[v][0] = fmaf(du0, dgx, S1[v][0]); S1[v][1] = fmaf(du1, dgx, S1[v][1]); S1[v][2] = fmaf(du2, dgx, S1[v][2]);
-          S2[v][0] = fmaf(du0, dgy, S2[v][0]); S2[v][1] = fmaf(du1, dgy, S2[v][1]); S2[v][2] = fmaf(du2, dgy, S2[v][2]);
-          S3[v][0] = fmaf(du0, d, S3[v][0]);   S3[v][1] = fmaf(du1, d, S3[v][1]);   S3[v][2] = fmaf(du2, d, S3[v][2]);
-          S4[v][0] += du0;                     S4[v][1] += du1;                     S4[v][2] += du2;
-        }
-        if (!EXACT) g_d = __fdividef(g_d, d);
-        P.g_x[s][pix] = g_d * dd_dx + g_q * dq_dx;
-      }
-    }
-
-    // ---- end of a run of tiles of one (scale, image)?  reduce once; otherwise leave a zero slot behind
-    bool last_of_run = (tile + 1 == t_hi);
-    if (!last_of_run) {
-      int s2 = s;
-      while (s2 + 1 < P.S && tile + 1 >= P.item_begin[s2 + 1]) ++s2;
-      const int b2 = (tile + 1 - P.item_begin[s2]) / (P.bands[s2] * P.tiles_x[s2]);
-      last_of_run = (s2 != s) || (b2 != b);
-    }
-    float* slot = P.partials + (size_t)tile * N;
-    if (last_of_run) {
-      float vals[N];
-      vals[0] = pix_sum * cpix; vals[1] = sm_sum; vals[2] = exp_sum * cexp;
-#pragma unroll
-      for (int v = 0; v < V; ++v)
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          vals[3 + v * 12 + i] = S1[v][i];
-          vals[3 + v * 12 + 3 + i] = S2[v][i];
-          vals[3 + v * 12 + 6 + i] = S3[v][i];
-          vals[3 + v * 12 + 9 + i] = S4[v][i];
-        }
-      block_sum<N>(vals, scratch, slot);
-      reset();
-    } else if (threadIdx.x < N) {
-      slot[threadIdx.x] = 0.f;
+  // ---- 1. streaming operands: target and logits rows of the tile -> shared memory, asynchronously
+  if (staged && y < H) {
+    const size_t row = img_off + (size_t)y * W + x_base;
+    const float* __restrict__ gt = P.tgt[s] + row * 3;
+    float* dt = s_tgt + warp * (kTW * 3);
+    for (int k = lane; k < (cols * 3) >> 2; k += 32) cp_async16(dt + 4 * k, gt + 4 * k);
+    if (use_lg) {
+      const float* __restrict__ gl = P.logits[s] + row * (2 * V);
+      float* dl = s_lg + warp * (kTW * 2 * V);
+      for (int k = lane; k < (cols * 2 * V) >> 2; k += 32) cp_async16(dl + 4 * k, gl + 4 * k);
     }
   }
+
+  // ---- 2. the x tile (+halo) and this image's V transforms
+  const float* __restrict__ xs = P.x[s] + img_off;
+  for (int ty = warp; ty < kTileH; ty += kTH) {
+    const int gy = y_base + ty - kHalo;
+    const bool rin = gy >= 0 && gy < H;
+    const float* __restrict__ row = xs + (size_t)(rin ? gy : 0) * W;
+    for (int tc = lane; tc < tw + 2 * kHalo; tc += 32) {
+      const int gx = x_base + tc - kHalo;
+      float v = 0.f;
+      if (rin && gx >= 0 && gx < W) {
+        v = row[gx];
+        if (P.smooth_on_inverse) v = __fdiv_rn(1.0f, v);
+      }
+      qt[ty][tc] = v;
+    }
+  }
+  if (threadIdx.x < V * 21) {
+    const int v = threadIdx.x / 21, k = threadIdx.x - v * 21;
+    sxf[v * 24 + k] = reinterpret_cast<const float*>(P.xf + ((size_t)s * V + v) * P.B + b)[k];
+  }
+  __syncthreads();
+
+  const float cpix = P.cpix[s], cexp = P.cexp[s];
+  float pix_sum = 0.f, exp_sum = 0.f, sm_sum = 0.f;
+
+  // ---- 3. smoothness, pass 1: every element of (tile + 2 rows above + 2 columns left) evaluates the four
+  // second differences it owns (it is their top-left corner) ONCE and publishes their weighted signs.
+  {
+    const float cxx = P.csm[s][0], cxy = P.csm[s][1], cyx = P.csm[s][2], cyy = P.csm[s][3];
+    for (int oy = warp; oy < kOwnH; oy += kTH) {
+      const int gy = y_base - kHalo + oy;
+      const bool rin = gy >= 0 && gy < H;
+      for (int ox = lane; ox < tw + kHalo; ox += 32) {
+        const int gx = x_base - kHalo + ox;
+        const bool in = rin && gx >= 0 && gx < W;
+        const float q00 = qt[oy][ox], q01 = qt[oy][ox + 1], q02 = qt[oy][ox + 2];
+        const float q10 = qt[oy + 1][ox], q11 = qt[oy + 1][ox + 1], q20 = qt[oy + 2][ox];
+        const float dx0 = __fsub_rn(q01, q00), dy0 = __fsub_rn(q10, q00);
+        float dxx = __fsub_rn(__fsub_rn(q02, q01), dx0);
+        float dyy = __fsub_rn(__fsub_rn(q20, q10), dy0);
+        float dxy = __fsub_rn(__fsub_rn(q11, q10), dx0);  // d/dy of dx
+        float dyx = __fsub_rn(__fsub_rn(q11, q01), dy0);  // d/dx of dy
+        if (!(in && gx + 2 < W)) dxx = 0.f;
+        if (!(in && gy + 2 < H)) dyy = 0.f;
+        if (!(in && gx + 1 < W && gy + 1 < H)) { dxy = 0.f; dyx = 0.f; }
+        sA[oy][ox] = signed_by(cxx, dxx);
+        sB[oy][ox] = signed_by(cyy, dyy);
+        sC[oy][ox] = signed_by(cxy, dxy) + signed_by(cyx, dyx);
+        if (oy >= kHalo && ox >= kHalo)
+          sm_sum += cxx * fabsf(dxx) + cyy * fabsf(dyy) + cxy * fabsf(dxy) + cyx * fabsf(dyx);
+      }
+    }
+  }
+  cp_async_wait_all();
+  __syncthreads();
+
+  // ---- 4. the pixels
+  const float gy = grid_coord(y, H, grid_step(H));
+  const float wstep = grid_step(W);
+  float S1[V][3], S3[V][3], S4[V][3];  // sum du*d*gx, du*d, du   (sum du*d*gy = gy * S3: the row is fixed)
+#pragma unroll
+  for (int v = 0; v < V; ++v)
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { S1[v][i] = 0.f; S3[v][i] = 0.f; S4[v][i] = 0.f; }
+
+  if (y < H) {
+    for (int r = 0; r * 32 < tw; ++r) {
+      const int xl = r * 32 + lane;                // column inside the tile
+      const int x = x_base + xl;
+      if (x >= W) continue;
+      const int pofs = y * W + x;                  // pixel offset inside this image
+      const size_t pix = img_off + pofs;
+      const int oy = warp + kHalo, ox = xl + kHalo;
+
+      // smoothness, pass 2: gradient = the published signs of the 10 stencils this element is part of
+      const float g_q = (sA[oy][ox] - 2.f * sA[oy][ox - 1] + sA[oy][ox - 2]) +
+                        (sB[oy][ox] - 2.f * sB[oy - 1][ox] + sB[oy - 2][ox]) +
+                        (sC[oy][ox] - sC[oy][ox - 1] - sC[oy - 1][ox] + sC[oy - 1][ox - 1]);
+
+      // depth of this pixel and d(depth)/dx, d(q)/dx
+      const float qc = qt[oy][ox];
+      float d, dd_dx, dq_dx;
+      if (P.smooth_on_inverse) {
+        dq_dx = -qc * qc;
+        if (P.depth_is_inverse) { d = qc; dd_dx = dq_dx; }
+        else { d = xs[pofs]; dd_dx = 1.f; }
+      } else {
+        dq_dx = 1.f;
+        if (P.depth_is_inverse) { d = __fdiv_rn(1.0f, qc); dd_dx = -d * d; }
+        else { d = qc; dd_dx = 1.f; }
+      }
+
+      const float gx = grid_coord(x, W, wstep);
+      float tt[3];
+      if (staged) {
+        const float* t = s_tgt + (warp * kTW + xl) * 3;
+        tt[0] = t[0]; tt[1] = t[1]; tt[2] = t[2];
+      } else {
+        const float* __restrict__ t = P.tgt[s] + pix * 3;
+        tt[0] = t[0]; tt[1] = t[1]; tt[2] = t[2];
+      }
+      const float dgx = d * gx;
+      // K^-1 is the same for every view of a scale
+      float r0, r1, r2;
+      if (EXACT) {
+        Ray ray = back_project(sxf, gx, gy);
+        r0 = ray.r0; r1 = ray.r1; r2 = ray.r2;
+      } else {
+        r0 = fmaf(sxf[0], gx, fmaf(sxf[1], gy, sxf[2]));
+        r1 = fmaf(sxf[3], gx, fmaf(sxf[4], gy, sxf[5]));
+        r2 = fmaf(sxf[6], gx, fmaf(sxf[7], gy, sxf[8]));
+      }
+      const float c0 = __fmul_rn(r0, d), c1 = __fmul_rn(r1, d), c2 = __fmul_rn(r2, d);
+      float g_d = 0.f;
+
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const float* __restrict__ pp = sxf + v * 24 + 9;
+        float qx, qy, rz;
+        if (EXACT) {
+          Proj q = project(pp, c0, c1, c2);
+          qx = q.x; qy = q.y; rz = 1.0f / q.zp;
+        } else {
+          const float u0 = fmaf(pp[0], c0, fmaf(pp[1], c1, fmaf(pp[2], c2, pp[3])));
+          const float u1 = fmaf(pp[4], c0, fmaf(pp[5], c1, fmaf(pp[6], c2, pp[7])));
+          const float u2 = fmaf(pp[8], c0, fmaf(pp[9], c1, fmaf(pp[10], c2, pp[11])));
+          rz = __fdividef(1.0f, u2 + kEpsZ);
+          qx = u0 * rz; qy = u1 * rz;
+        }
+        const Foot f = footprint(qx, qy, W, H);
+        const float* __restrict__ p00 = P.src[v][s] + (img_off + (size_t)(f.y0 * W + f.x0)) * 3;
+        const int dxo = (f.x1 - f.x0) * 3, dyo = (f.y1 - f.y0) * W * 3;
+        const float* __restrict__ p10 = p00 + dxo;
+        const float* __restrict__ p01 = p00 + dyo;
+        const float* __restrict__ p11 = p01 + dxo;
+        float i00[3], i01[3], i10[3], i11[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          i00[c] = __ldg(p00 + c); i10[c] = __ldg(p10 + c); i01[c] = __ldg(p01 + c); i11[c] = __ldg(p11 + c);
+        }
+        // mask value m (explainability softmax or constant) and the regulariser
+        float m = 1.f, p0 = 0.f, p1 = 0.f;
+        float* lgp = s_lg + (warp * kTW + xl) * (2 * V) + 2 * v;   // staged logits slot, reused for d/dlogits
+        if (use_lg) {
+          const float2 lg = staged ? *reinterpret_cast<const float2*>(lgp)
+                                   : *reinterpret_cast<const float2*>(P.logits[s] + pix * (2 * V) + 2 * v);
+          if (EXACT) {
+            const float mx = fmaxf(lg.x, lg.y);
+            const float e0 = expf(lg.x - mx), e1 = expf(lg.y - mx), se = e0 + e1;
+            p0 = e0 / se; p1 = e1 / se;
+            exp_sum += (mx + logf(se)) - lg.y;
+          } else {
+            const float z = lg.x - lg.y;
+            const float t = __expf(-fabsf(z)), se = 1.f + t, big = __fdividef(1.f, se), small = t * big;
+            p0 = z >= 0.f ? big : small;
+            p1 = z >= 0.f ? small : big;
+            exp_sum += __logf(se) + fmaxf(z, 0.f);
+          }
+          m = p1;
+        } else if (P.mask_mode == VSL_MASK_CONST) {
+          m = P.mask[s][pix];
+        }
+        const float w00 = __fmul_rn(f.wx0, f.wy0), w01 = __fmul_rn(f.wx0, f.wy1),
+                    w10 = __fmul_rn(f.wx1, f.wy0), w11 = __fmul_rn(f.wx1, f.wy1);
+        // E = sum_c |e_c|; J_k = sum_c sign(e_c) * corner_k[c]  (the channel sum commutes with d/dx, d/dy)
+        float E = 0.f, J00 = 0.f, J01 = 0.f, J10 = 0.f, J11 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float wv = EXACT ? blend(w00, w01, w10, w11, i00[c], i01[c], i10[c], i11[c])
+                                 : fmaf(w11, i11[c], fmaf(w10, i10[c], fmaf(w01, i01[c], w00 * i00[c])));
+          const float e = wv - tt[c];
+          E += fabsf(e);
+          const float sg = signed_by(1.f, e);
+          J00 = fmaf(sg, i00[c], J00); J01 = fmaf(sg, i01[c], J01);
+          J10 = fmaf(sg, i10[c], J10); J11 = fmaf(sg, i11[c], J11);
+        }
+        const float ex0 = f.mx1 * J10 - f.mx0 * J00, ex1 = f.mx1 * J11 - f.mx0 * J01;  // d/dx per row
+        const float ey0 = f.my1 * J01 - f.my0 * J00, ey1 = f.my1 * J11 - f.my0 * J10;  // d/dy per column
+        const float dx = f.wy0 * ex0 + f.wy1 * ex1;
+        const float dy = f.wx0 * ey0 + f.wx1 * ey1;
+        pix_sum = fmaf(m, E, pix_sum);
+        if (use_lg) {
+          const float g0 = p0 * (cexp - cpix * E * p1);
+          if (staged) *reinterpret_cast<float2*>(lgp) = make_float2(g0, -g0);
+          else *reinterpret_cast<float2*>(P.g_logits[s] + pix * (2 * V) + 2 * v) = make_float2(g0, -g0);
+        }
+        const float k = cpix * m * rz;
+        const float du0 = dx * k, du1 = dy * k, du2 = -(qx * du0 + qy * du1);
+        if (EXACT) {
+          const float gc0 = du0 * pp[0] + du1 * pp[4] + du2 * pp[8];
+          const float gc1 = du0 * pp[1] + du1 * pp[5] + du2 * pp[9];
+          const float gc2 = du0 * pp[2] + du1 * pp[6] + du2 * pp[10];
+          g_d += gc0 * r0 + gc1 * r1 + gc2 * r2;
+        } else {
+          g_d -= du0 * pp[3] + du1 * pp[7] + du2 * pp[11];  // <du, M ray> = <du, u - t> / d and <du, u> = 0
+        }
+        S1[v][0] = fmaf(du0, dgx, S1[v][0]); S1[v][1] = fmaf(du1, dgx, S1[v][1]); S1[v][2] = fmaf(du2, dgx, S1[v][2]);
+        S3[v][0] = fmaf(du0, d, S3[v][0]);   S3[v][1] = fmaf(du1, d, S3[v][1]);   S3[v][2] = fmaf(du2, d, S3[v][2]);
+        S4[v][0] += du0;                     S4[v][1] += du1;                     S4[v][2] += du2;
+      }
+      if (!EXACT) g_d = __fdividef(g_d, d);
+      P.g_x[s][pix] = g_d * dd_dx + g_q * dq_dx;
+    }
+  }
+
+  // ---- 5. d/dlogits leaves the tile with 16-byte stores (each warp wrote its own row: no block barrier)
+  if (staged && use_lg && y < H) {
+    __syncwarp();
+    float* __restrict__ gl = P.g_logits[s] + (img_off + (size_t)y * W + x_base) * (2 * V);
+    const float* sl = s_lg + warp * (kTW * 2 * V);
+    for (int k = lane; k < (cols * 2 * V) >> 2; k += 32)
+      *reinterpret_cast<float4*>(gl + 4 * k) = *reinterpret_cast<const float4*>(sl + 4 * k);
+  }
+
+  // ---- 6. one block reduction per tile: 3 loss sums + per view (sum du d gx, gy sum du d, sum du d, sum du)
+  float vals[N];
+  vals[0] = pix_sum * cpix; vals[1] = sm_sum; vals[2] = exp_sum * cexp;
+#pragma unroll
+  for (int v = 0; v < V; ++v)
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      vals[3 + v * 12 + i] = S1[v][i];
+      vals[3 + v * 12 + 3 + i] = gy * S3[v][i];
+      vals[3 + v * 12 + 6 + i] = S3[v][i];
+      vals[3 + v * 12 + 9 + i] = S4[v][i];
+    }
+  block_sum_bfly<N>(vals, scratch, P.partials + (size_t)tile * N);
 }
 
-// grid = B + 1 blocks of 128 threads.  Block b < B: pose gradients of batch element b (all views).
+// grid = B + 1 blocks of 256 threads.  Block b < B: pose gradients of batch element b (all views); one WARP per
+// (scale, view, component) sums that image's partial slots (lane-strided, then a fixed shuffle tree).
 // Block B: the three loss scalars.  Every sum runs in a fixed order in double => deterministic.
 template <int V>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 loss_finalize_kernel(const LossParams P, const float* __restrict__ poses, const float* __restrict__ K_pyr,
                      int pose_format, float inv_loss_scale, float* __restrict__ losses, float* __restrict__ g_poses) {
   constexpr int N = NT<V>::value;
-  __shared__ double sh[128 * 3];
+  __shared__ double sh[32 * 3];
   __shared__ double tsum[VSL_MAX_SCALES * V * 12];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  auto warp_dsum = [](double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+  };
   const int n_items = P.item_begin[P.S];
   if ((int)blockIdx.x == P.B) {
     double a0 = 0.0, a1 = 0.0, a2 = 0.0;
@@ -387,53 +396,63 @@ loss_finalize_kernel(const LossParams P, const float* __restrict__ poses, const 
       const float* p = P.partials + (size_t)i * N;
       a0 += (double)p[0]; a1 += (double)p[1]; a2 += (double)p[2];
     }
-    sh[threadIdx.x * 3] = a0; sh[threadIdx.x * 3 + 1] = a1; sh[threadIdx.x * 3 + 2] = a2;
+    a0 = warp_dsum(a0); a1 = warp_dsum(a1); a2 = warp_dsum(a2);
+    if (lane == 0) { sh[warp * 3] = a0; sh[warp * 3 + 1] = a1; sh[warp * 3 + 2] = a2; }
     __syncthreads();
-    for (int o = 64; o > 0; o >>= 1) {
-      if ((int)threadIdx.x < o)
-        for (int t = 0; t < 3; ++t) sh[threadIdx.x * 3 + t] += sh[(threadIdx.x + o) * 3 + t];
-      __syncthreads();
+    if (threadIdx.x < 3) {
+      double t = 0.0;
+      for (int w = 0; w < nwarp; ++w) t += sh[w * 3 + threadIdx.x];
+      losses[threadIdx.x] = (float)(t * (double)inv_loss_scale);
     }
-    if (threadIdx.x < 3) losses[threadIdx.x] = (float)(sh[threadIdx.x] * (double)inv_loss_scale);
     return;
   }
   const int b = blockIdx.x;
-  // one thread per (scale, view, component): a serial, fixed-order sum over that image's items
-  for (int e = threadIdx.x; e < P.S * V * 12; e += blockDim.x) {
+  for (int e = warp; e < P.S * V * 12; e += nwarp) {
     const int k = e % 12, v = (e / 12) % V, s = e / (12 * V);
     const int per_b = P.bands[s] * P.tiles_x[s];
     const float* p = P.partials + (size_t)(P.item_begin[s] + b * per_b) * N + 3 + v * 12 + k;
     double a = 0.0;
-    for (int i = 0; i < per_b; ++i) a += (double)p[(size_t)i * N];
-    tsum[e] = a;
+    for (int i = lane; i < per_b; i += 32) a += (double)p[(size_t)i * N];
+    a = warp_dsum(a);
+    if (lane == 0) tsum[e] = a;
+  }
+  __syncthreads();
+  // dT[v][k][j] = sum_s sum_i K_s[i][k] * dP_s[i][j]: one thread per matrix element, short chains
+  __shared__ double sgT[VSL_MAX_VIEWS][16];
+  if ((int)threadIdx.x < V * 16) {
+    const int v = threadIdx.x >> 4, k = (threadIdx.x >> 2) & 3, j = threadIdx.x & 3;
+    double acc = 0.0;
+    if (k < 3) {
+      for (int s = 0; s < P.S; ++s) {
+        const double* t = tsum + (s * V + v) * 12;
+        const Xform& xf = P.xf[((size_t)s * V + v) * P.B + b];
+        const float* Ks = K_pyr + ((size_t)b * P.S + s) * 9;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const double dPij = (j < 3) ? (double)xf.kinv[j * 3] * t[i] + (double)xf.kinv[j * 3 + 1] * t[3 + i] +
+                                            (double)xf.kinv[j * 3 + 2] * t[6 + i]
+                                      : t[9 + i];
+          acc += (double)Ks[i * 3 + k] * dPij;
+        }
+      }
+    }
+    sgT[v][k * 4 + j] = acc;
   }
   __syncthreads();
   if ((int)threadIdx.x >= V) return;
   const int v = threadIdx.x;
   const int psz = (pose_format == VSL_POSE_MATRIX) ? 16 : 6;
   double gT[16];
-  for (int i = 0; i < 16; ++i) gT[i] = 0.0;
-  for (int s = 0; s < P.S; ++s) {
-    const double* t = tsum + (s * V + v) * 12;
-    const Xform& xf = P.xf[((size_t)s * V + v) * P.B + b];
-    const float* Ks = K_pyr + ((size_t)b * P.S + s) * 9;
-    double dP[12];
-    for (int i = 0; i < 3; ++i) {
-      for (int j = 0; j < 3; ++j)
-        dP[i * 4 + j] = (double)xf.kinv[j * 3] * t[i] + (double)xf.kinv[j * 3 + 1] * t[3 + i] +
-                        (double)xf.kinv[j * 3 + 2] * t[6 + i];
-      dP[i * 4 + 3] = t[9 + i];
-    }
-    for (int k = 0; k < 3; ++k)
-      for (int j = 0; j < 4; ++j)
-        gT[k * 4 + j] += (double)Ks[k] * dP[j] + (double)Ks[3 + k] * dP[4 + j] + (double)Ks[6 + k] * dP[8 + j];
-  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) gT[i] = sgT[v][i];
   float* out = g_poses + ((size_t)b * V + v) * psz;
   if (pose_format == VSL_POSE_MATRIX) {
+#pragma unroll
     for (int i = 0; i < 16; ++i) out[i] = (float)gT[i];
   } else {
     float g[6];
     pose_vec_grad(poses + ((size_t)b * V + v) * 6, pose_format, gT, g);
+#pragma unroll
     for (int i = 0; i < 6; ++i) out[i] = g[i];
   }
 }
@@ -476,7 +495,7 @@ void layout(const VslLossDesc* d, WsLayout* L) {
     L->item_begin[s] = n;
     n += d->B * L->bands[s] * L->tiles_x[s];
     L->level_off[s] = lv;
-    if (s >= 1) lv += (size_t)d->B * H * W * 3;
+    if (s >= 1) lv += round_up((size_t)d->B * H * W * 3, 4);  // keep every level 16-byte aligned
   }
   L->item_begin[d->S] = n;
   L->n_items = n;
@@ -487,28 +506,25 @@ void layout(const VslLossDesc* d, WsLayout* L) {
   L->total = L->pyr + sizeof(float) * lv * (size_t)(d->V + 1);
 }
 
+template <int V, bool EXACT>
+int launch_fused(const WsLayout& L, const LossParams& P, cudaStream_t st) {
+  // > 48 KB of dynamic shared memory needs the opt-in; idempotent and cheap, so set on every call (no state)
+  cudaError_t e = cudaFuncSetAttribute(loss_fused_kernel<V, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)Smem<V>::bytes);
+  if (e != cudaSuccess) return (int)e;
+  loss_fused_kernel<V, EXACT><<<L.n_items, kThreads, Smem<V>::bytes, st>>>(P);
+  return VSL_OK;
+}
+
 template <int V>
 int run_loss(const VslLossDesc* d, const WsLayout& L, LossParams& P, const float* poses, const float* K_pyr,
              float* losses, float* g_poses, cudaStream_t st) {
   if (d->ev_main_begin != nullptr) cudaEventRecord((cudaEvent_t)d->ev_main_begin, st);
-  // persistent grid: a fixed number of co-resident blocks per SM, never more blocks than tiles
-  int dev = 0, sms = 148, per_sm = 3;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  long long total_cost = 0;
-  for (int s = 0; s < d->S; ++s) total_cost += (long long)d->B * L.bands[s] * (((d->W >> s) + 31) >> 5);
-  if (d->exact_coords) {
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, loss_fused_kernel<V, true>, 256, 0);
-    const int grid = (int)std::min<long long>((long long)sms * std::max(per_sm, 1), (long long)L.n_items);
-    loss_fused_kernel<V, true><<<grid, 256, 0, st>>>(P, total_cost);
-  } else {
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, loss_fused_kernel<V, false>, 256, 0);
-    const int grid = (int)std::min<long long>((long long)sms * std::max(per_sm, 1), (long long)L.n_items);
-    loss_fused_kernel<V, false><<<grid, 256, 0, st>>>(P, total_cost);
-  }
+  const int rc = d->exact_coords ? launch_fused<V, true>(L, P, st) : launch_fused<V, false>(L, P, st);
+  if (rc != VSL_OK) return rc;
   if (d->ev_main_end != nullptr) cudaEventRecord((cudaEvent_t)d->ev_main_end, st);
-  loss_finalize_kernel<V><<<d->B + 1, 128, 0, st>>>(P, poses, K_pyr, d->pose_format, 1.0f / d->loss_scale,
-                                                      losses, g_poses);
+  loss_finalize_kernel<V><<<d->B + 1, 256, 0, st>>>(P, poses, K_pyr, d->pose_format, 1.0f / d->loss_scale,
+                                                       losses, g_poses);
   return launch_status();
 }
 
@@ -550,7 +566,7 @@ int vsl_loss_fwd_bwd(const VslLossDesc* d, const float* tgt, const float* const*
   for (int v = 0; v < d->V; ++v) VSL_REQUIRE(srcs[v], VSL_E_NULL);
   for (int s = 0; s < VSL_MAX_SCALES; ++s) {
     P.tgt[s] = nullptr; P.x[s] = nullptr; P.logits[s] = nullptr; P.mask[s] = nullptr;
-    P.g_x[s] = nullptr; P.g_logits[s] = nullptr;
+    P.g_x[s] = nullptr; P.g_logits[s] = nullptr; P.staged[s] = 0;
     for (int v = 0; v < VSL_MAX_VIEWS; ++v) P.src[v][s] = nullptr;
   }
   for (int s = 0; s < d->S; ++s) {
@@ -571,6 +587,10 @@ int vsl_loss_fwd_bwd(const VslLossDesc* d, const float* tgt, const float* const*
     P.tgt[s] = (s == 0) ? tgt : pyr + L.level_off[s];
     for (int v = 0; v < d->V; ++v) P.src[v][s] = (s == 0) ? srcs[v] : pyr + L.pyr_img * (size_t)(v + 1) + L.level_off[s];
     P.tiles_x[s] = L.tiles_x[s]; P.bands[s] = L.bands[s]; P.R[s] = L.R[s];
+    // 16-byte row alignment of the streamed operands: W % 4 == 0 makes every row start (and the tile's
+    // x_base, a multiple of 32) a multiple of 4 pixels = 48 B of target / 8V*4 B of logits
+    P.staged[s] = (W % 4 == 0) && aligned(P.tgt[s], 16) &&
+                  (d->mask_mode != VSL_MASK_EXP || (aligned(P.logits[s], 16) && aligned(P.g_logits[s], 16)));
     const double npx = (double)d->B * H * W;
     const double dw = d->pixel_scale_norm ? (double)d->data_weight / (double)(1 << s) : (double)d->data_weight;
     P.cpix[s] = (float)((double)d->loss_scale * dw / (npx * 3.0));
@@ -582,7 +602,7 @@ int vsl_loss_fwd_bwd(const VslLossDesc* d, const float* tgt, const float* const*
     P.csm[s][3] = (float)(sw / ((double)d->B * (H - 2) * W));
   }
 
-  // 1 + 2. transforms and the image pyramids (target + V sources) in one launch
+  // 1. transforms and the image pyramids (target + V sources) in one launch
   const PrepJob prep = make_prep(poses, K_pyr, d->B, d->S, d->V, d->pose_format, xf, nullptr);
   if (d->S > 1) {
     PyrJob job;
@@ -597,7 +617,7 @@ int vsl_loss_fwd_bwd(const VslLossDesc* d, const float* tgt, const float* const*
   } else {
     prep_xforms_kernel<<<(prep.n + 63) / 64, 64, 0, st>>>(prep);
   }
-  // 3 + 4. fused loss and finalize
+  // 2 + 3. fused loss and finalize
   switch (d->V) {
     case 1: return run_loss<1>(d, L, P, poses, K_pyr, losses, g_poses, st);
     case 2: return run_loss<2>(d, L, P, poses, K_pyr, losses, g_poses, st);
