@@ -1,0 +1,44 @@
+"""GPU: ops.HostPipeline (host buffers in / out, three overlapped streams) returns exactly what the plain plan
+computes, for every step of a run in which consecutive steps carry DIFFERENT inputs (buffer reuse hazards)."""
+import pytest
+import torch
+
+from tf_depth_estimation_b200 import _lib, ops, synth
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device('cuda:0')
+
+
+def _host_inputs(d):
+    pin = lambda t: t.contiguous().pin_memory()
+    return dict(tgt=pin(d['tgt']), srcs=[pin(s) for s in d['srcs']], xs=[pin(x) for x in d['disp_pyr']],
+                poses=pin(d['poses']), Kp=pin(d['K_pyr']), lgs=[pin(l) for l in d['logits_pyr']])
+
+
+def test_pipeline_matches_plan_over_many_steps():
+    B, H, W, S, V = 4, 32, 64, 3, 2
+    flags = ops.LossFlags(num_scales=S)
+    pipe = ops.HostPipeline(B, H, W, V, flags, _lib.MASK_EXP, DEV)
+    plan = ops.ViewSynthesisPlan(B, H, W, V, flags, _lib.MASK_EXP, DEV)
+    datasets = [synth.make_snippets(B, H, W, S=S, V=V, seed=200 + i) for i in range(5)]
+    hosts = [_host_inputs(d) for d in datasets]
+    slots, got = [], []
+    for i in range(7):                       # more steps than buffer sets: every slot is reused
+        slots.append(pipe.submit(hosts[i % 5]))
+        if i >= 1:                           # collect step i-1 while step i is in flight
+            l, gx, gp, gl = pipe.result(slots[i - 1])
+            got.append((l.clone(), [g.clone() for g in gx], gp.clone(), [g.clone() for g in gl]))
+    l, gx, gp, gl = pipe.result(slots[-1])
+    got.append((l.clone(), [g.clone() for g in gx], gp.clone(), [g.clone() for g in gl]))
+    for i, (l, gx, gp, gl) in enumerate(got):
+        d = datasets[i % 5]
+        cu = lambda t: t.to(DEV).contiguous()
+        plan.run(cu(d['tgt']), [cu(s) for s in d['srcs']], [cu(x) for x in d['disp_pyr']], cu(d['poses']),
+                 cu(d['K_pyr']), [cu(t) for t in d['logits_pyr']])
+        torch.cuda.synchronize()
+        assert torch.equal(l, plan.losses.cpu()), i
+        assert torch.equal(gp, plan.g_poses.cpu()), i
+        assert all(torch.equal(a, b.cpu()) for a, b in zip(gx, plan.g_x)), i
+        assert all(torch.equal(a, b.cpu()) for a, b in zip(gl, plan.g_logits)), i
+    h2d, d2h = pipe.bytes_per_step()
+    assert h2d == 4 * sum(t.numel() for t in pipe._flat(hosts[0])) and d2h > 0

@@ -195,54 +195,74 @@ VSL_DEV void pose_to_mat(const float* pose, int format, float* T) {
   T[12] = 0.f; T[13] = 0.f; T[14] = 0.f; T[15] = 1.f;
 }
 
-// ---- pose backward (double precision internally; B threads, negligible cost).
-// gT: upstream gradient of the 4x4 matrix.  g: gradient of the 6-vector.
-__device__ inline void pose_vec_grad(const float* pose, int format, const double* gT, float* g) {
+// ---- pose backward.  gT: upstream gradient of the 4x4 matrix (row-major); g: gradient of the 6-vector.
+// T = float keeps the serial chain short (FP64 issue latency dominates otherwise); the sums that feed gT are
+// accumulated in double by the callers.
+template <typename T>
+__device__ inline void pose_vec_grad(const float* pose, int format, const T* gT, float* g) {
   g[0] = (float)gT[3]; g[1] = (float)gT[7]; g[2] = (float)gT[11];
-  double G[9];
-  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) G[i * 3 + j] = gT[i * 4 + j];
+  T G[9];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) G[i * 3 + j] = gT[i * 4 + j];
+  auto mm = [](const T* p, const T* q, T* o) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        T s = 0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) s += p[i * 3 + k] * q[k * 3 + j];
+        o[i * 3 + j] = s;
+      }
+  };
+  auto dot = [](const T* p, const T* q) {
+    T s = 0;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) s += p[i] * q[i];
+    return s;
+  };
   if (format == 0) {
-    const double pi = (double)kPi;  // the clip bounds are fp32(pi) (utils.py:40-42)
-    double a[3] = {pose[3], pose[4], pose[5]};  // x, y, z
+    const float pi = kPi;  // the clip bounds are fp32(pi) (utils.py:40-42)
+    float a[3] = {pose[3], pose[4], pose[5]};  // x, y, z
     bool in[3];
-    for (int i = 0; i < 3; ++i) { in[i] = (a[i] >= -pi && a[i] <= pi); a[i] = fmin(fmax(a[i], -pi), pi); }
-    // fp32 sin/cos (FP64 transcendentals are slow on this part and the forward pass is fp32 anyway)
-    double cx = cosf((float)a[0]), sx = sinf((float)a[0]), cy = cosf((float)a[1]), sy = sinf((float)a[1]),
-           cz = cosf((float)a[2]), sz = sinf((float)a[2]);
-    double X[9] = {1, 0, 0, 0, cx, -sx, 0, sx, cx}, Y[9] = {cy, 0, sy, 0, 1, 0, -sy, 0, cy},
-           Z[9] = {cz, -sz, 0, sz, cz, 0, 0, 0, 1};
-    double dX[9] = {0, 0, 0, 0, -sx, -cx, 0, cx, -sx}, dY[9] = {-sy, 0, cy, 0, 0, 0, -cy, 0, -sy},
-           dZ[9] = {-sz, -cz, 0, cz, -sz, 0, 0, 0, 0};
-    auto mm = [](const double* p, const double* q, double* o) {
-      for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
-        double s = 0; for (int k = 0; k < 3; ++k) s += p[i * 3 + k] * q[k * 3 + j]; o[i * 3 + j] = s; }
-    };
-    auto dot = [](const double* p, const double* q) { double s = 0; for (int i = 0; i < 9; ++i) s += p[i] * q[i]; return s; };
-    double t1[9], t2[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { in[i] = (a[i] >= -pi && a[i] <= pi); a[i] = fminf(fmaxf(a[i], -pi), pi); }
+    const T cx = cosf(a[0]), sx = sinf(a[0]), cy = cosf(a[1]), sy = sinf(a[1]), cz = cosf(a[2]), sz = sinf(a[2]);
+    const T X[9] = {1, 0, 0, 0, cx, -sx, 0, sx, cx}, Y[9] = {cy, 0, sy, 0, 1, 0, -sy, 0, cy},
+            Z[9] = {cz, -sz, 0, sz, cz, 0, 0, 0, 1};
+    const T dX[9] = {0, 0, 0, 0, -sx, -cx, 0, cx, -sx}, dY[9] = {-sy, 0, cy, 0, 0, 0, -cy, 0, -sy},
+            dZ[9] = {-sz, -cz, 0, cz, -sz, 0, 0, 0, 0};
+    T t1[9], t2[9];
     mm(dX, Y, t1); mm(t1, Z, t2); g[3] = in[0] ? (float)dot(G, t2) : 0.f;
     mm(X, dY, t1); mm(t1, Z, t2); g[4] = in[1] ? (float)dot(G, t2) : 0.f;
     mm(X, Y, t1); mm(t1, dZ, t2); g[5] = in[2] ? (float)dot(G, t2) : 0.f;
   } else {
-    double r[3] = {pose[3], pose[4], pose[5]};
-    double th = sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
-    double a[3] = {r[0] / th, r[1] / th, r[2] / th};
-    double A[9] = {0, -a[2], a[1], a[2], 0, -a[0], -a[1], a[0], 0}, AA[9];
-    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
-      double s = 0; for (int k = 0; k < 3; ++k) s += A[i * 3 + k] * A[k * 3 + j]; AA[i * 3 + j] = s; }
-    double s = sinf((float)th), c = cosf((float)th), gs = 0, gomc = 0;
-    for (int i = 0; i < 9; ++i) { gs += G[i] * A[i]; gomc += G[i] * AA[i]; }
-    double gth = gs * c + gomc * s;
+    const T r[3] = {pose[3], pose[4], pose[5]};
+    const T th = sqrtf((float)(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]));
+    const T a[3] = {r[0] / th, r[1] / th, r[2] / th};
+    const T A[9] = {0, -a[2], a[1], a[2], 0, -a[0], -a[1], a[0], 0};
+    T AA[9];
+    mm(A, A, AA);
+    const T s = sinf((float)th), c = cosf((float)th);
+    T gth = dot(G, A) * c + dot(G, AA) * s;
     // dA = s G + (1-c) (G A^T + A^T G)
-    double dA[9];
-    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
-      double t = 0;
-      for (int k = 0; k < 3; ++k) t += G[i * 3 + k] * A[j * 3 + k] + A[k * 3 + i] * G[k * 3 + j];
-      dA[i * 3 + j] = s * G[i * 3 + j] + (1 - c) * t;
-    }
+    T dA[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        T t = 0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) t += G[i * 3 + k] * A[j * 3 + k] + A[k * 3 + i] * G[k * 3 + j];
+        dA[i * 3 + j] = s * G[i * 3 + j] + (1 - c) * t;
+      }
     // A = M - M^T with M01 = -a2, M02 = a1, M12 = -a0
-    double da[3] = {-(dA[5] - dA[7]), (dA[2] - dA[6]), -(dA[1] - dA[3])};
-    double dotar = da[0] * r[0] + da[1] * r[1] + da[2] * r[2];
+    const T da[3] = {-(dA[5] - dA[7]), (dA[2] - dA[6]), -(dA[1] - dA[3])};
+    const T dotar = da[0] * r[0] + da[1] * r[1] + da[2] * r[2];
     gth -= dotar / (th * th);
+#pragma unroll
     for (int i = 0; i < 3; ++i) g[3 + i] = (float)(da[i] / th + gth * r[i] / th);
   }
 }

@@ -60,6 +60,9 @@ struct LossParams {
   int item_begin[VSL_MAX_SCALES + 1];
   int tiles_x[VSL_MAX_SCALES], bands[VSL_MAX_SCALES], R[VSL_MAX_SCALES];
   int staged[VSL_MAX_SCALES];      // 1: rows of this scale are 16-byte aligned -> cp.async / vector path
+  int img_begin[VSL_MAX_SCALES + 1];  // prefix sums of tiles per image over the scales (grid.x index -> scale)
+  float inv_tx[VSL_MAX_SCALES];    // 1 / tiles_x
+  float wstep[VSL_MAX_SCALES], hstep[VSL_MAX_SCALES];  // meshgrid linspace steps 2/(W-1), 2/(H-1) in fp32
 };
 
 template <int V> struct NT { static constexpr int value = 3 + 12 * V; };
@@ -114,14 +117,13 @@ loss_fused_kernel(const LossParams P) {
   float* s_lg = sm + L::lg;
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // ---- which tile
-  const int tile = blockIdx.x;
+  // ---- which tile: grid = (tiles per image over all scales, B); no integer division on the way
+  const int t_img = blockIdx.x, b = blockIdx.y;
   int s = 0;
-  while (s + 1 < P.S && tile >= P.item_begin[s + 1]) ++s;
-  const int local = tile - P.item_begin[s];
-  const int per_b = P.bands[s] * P.tiles_x[s];
-  const int b = local / per_b, rem = local - b * per_b;
-  const int band = rem / P.tiles_x[s], tx = rem - band * P.tiles_x[s];
+  while (s + 1 < P.S && t_img >= P.img_begin[s + 1]) ++s;
+  const int rem = t_img - P.img_begin[s];
+  const int band = __float2int_rz(((float)rem + 0.5f) * P.inv_tx[s]), tx = rem - band * P.tiles_x[s];
+  const int tile = P.item_begin[s] + b * (P.img_begin[s + 1] - P.img_begin[s]) + rem;  // partial slot
   const int H = P.H >> s, W = P.W >> s, R = P.R[s];
   const int y_base = band * kTH, x_base = tx * 32 * R;
   const int cols = min(32 * R, W - x_base);            // valid columns of this tile
@@ -152,17 +154,22 @@ loss_fused_kernel(const LossParams P) {
     const float* __restrict__ row = xs + (size_t)(rin ? gy : 0) * W;
     for (int tc = lane; tc < tw + 2 * kHalo; tc += 32) {
       const int gx = x_base + tc - kHalo;
-      float v = 0.f;
-      if (rin && gx >= 0 && gx < W) {
-        v = row[gx];
-        if (P.smooth_on_inverse) v = __fdiv_rn(1.0f, v);
-      }
-      qt[ty][tc] = v;
+      qt[ty][tc] = (rin && gx >= 0 && gx < W) ? row[gx] : 0.f;
     }
   }
-  if (threadIdx.x < V * 21) {
+  if (P.smooth_on_inverse) {  // each thread revisits exactly the elements it wrote
+    for (int ty = warp; ty < kTileH; ty += kTH) {
+      const int gy = y_base + ty - kHalo;
+      for (int tc = lane; tc < tw + 2 * kHalo; tc += 32) {
+        const int gx = x_base + tc - kHalo;
+        if (gy >= 0 && gy < H && gx >= 0 && gx < W) qt[ty][tc] = __fdiv_rn(1.0f, qt[ty][tc]);
+      }
+    }
+  }
+  if (threadIdx.x < V * 21) {  // per view: K^-1 rows padded to float4 (12 floats), then the 3 rows of P (12 floats)
     const int v = threadIdx.x / 21, k = threadIdx.x - v * 21;
-    sxf[v * 24 + k] = reinterpret_cast<const float*>(P.xf + ((size_t)s * V + v) * P.B + b)[k];
+    const int dst = k < 9 ? (k / 3) * 4 + k % 3 : 12 + (k - 9);
+    sxf[v * 24 + dst] = reinterpret_cast<const float*>(P.xf + ((size_t)s * V + v) * P.B + b)[k];
   }
   __syncthreads();
 
@@ -201,8 +208,8 @@ loss_fused_kernel(const LossParams P) {
   __syncthreads();
 
   // ---- 4. the pixels
-  const float gy = grid_coord(y, H, grid_step(H));
-  const float wstep = grid_step(W);
+  const float gy = grid_coord(y, H, P.hstep[s]);
+  const float wstep = P.wstep[s];
   float S1[V][3], S3[V][3], S4[V][3];  // sum du*d*gx, du*d, du   (sum du*d*gy = gy * S3: the row is fixed)
 #pragma unroll
   for (int v = 0; v < V; ++v)
@@ -232,7 +239,7 @@ loss_fused_kernel(const LossParams P) {
         else { d = xs[pofs]; dd_dx = 1.f; }
       } else {
         dq_dx = 1.f;
-        if (P.depth_is_inverse) { d = __fdiv_rn(1.0f, qc); dd_dx = -d * d; }
+        if (P.depth_is_inverse) { d = EXACT ? __fdiv_rn(1.0f, qc) : __fdividef(1.0f, qc); dd_dx = -d * d; }
         else { d = qc; dd_dx = 1.f; }
       }
 
@@ -248,20 +255,32 @@ loss_fused_kernel(const LossParams P) {
       const float dgx = d * gx;
       // K^-1 is the same for every view of a scale
       float r0, r1, r2;
-      if (EXACT) {
-        Ray ray = back_project(sxf, gx, gy);
-        r0 = ray.r0; r1 = ray.r1; r2 = ray.r2;
-      } else {
-        r0 = fmaf(sxf[0], gx, fmaf(sxf[1], gy, sxf[2]));
-        r1 = fmaf(sxf[3], gx, fmaf(sxf[4], gy, sxf[5]));
-        r2 = fmaf(sxf[6], gx, fmaf(sxf[7], gy, sxf[8]));
+      {
+        const float4 k0 = *reinterpret_cast<const float4*>(sxf), k1 = *reinterpret_cast<const float4*>(sxf + 4),
+                     k2 = *reinterpret_cast<const float4*>(sxf + 8);
+        if (EXACT) {
+          const float kk[9] = {k0.x, k0.y, k0.z, k1.x, k1.y, k1.z, k2.x, k2.y, k2.z};
+          Ray ray = back_project(kk, gx, gy);
+          r0 = ray.r0; r1 = ray.r1; r2 = ray.r2;
+        } else {
+          r0 = fmaf(k0.x, gx, fmaf(k0.y, gy, k0.z));
+          r1 = fmaf(k1.x, gx, fmaf(k1.y, gy, k1.z));
+          r2 = fmaf(k2.x, gx, fmaf(k2.y, gy, k2.z));
+        }
       }
       const float c0 = __fmul_rn(r0, d), c1 = __fmul_rn(r1, d), c2 = __fmul_rn(r2, d);
       float g_d = 0.f;
 
 #pragma unroll
       for (int v = 0; v < V; ++v) {
-        const float* __restrict__ pp = sxf + v * 24 + 9;
+#ifdef VSL_XF_VEC
+        const float4 P0 = *reinterpret_cast<const float4*>(sxf + v * 24 + 12),
+                     P1 = *reinterpret_cast<const float4*>(sxf + v * 24 + 16),
+                     P2 = *reinterpret_cast<const float4*>(sxf + v * 24 + 20);
+        const float pp[12] = {P0.x, P0.y, P0.z, P0.w, P1.x, P1.y, P1.z, P1.w, P2.x, P2.y, P2.z, P2.w};
+#else
+        const float* __restrict__ pp = sxf + v * 24 + 12;
+#endif
         float qx, qy, rz;
         if (EXACT) {
           Proj q = project(pp, c0, c1, c2);
@@ -370,14 +389,40 @@ loss_fused_kernel(const LossParams P) {
       vals[3 + v * 12 + 6 + i] = S3[v][i];
       vals[3 + v * 12 + 9 + i] = S4[v][i];
     }
-  block_sum_bfly<N>(vals, scratch, P.partials + (size_t)tile * N);
+  // transposed reduction through shared memory (the tile buffers are dead by now): thread j sums the 32 lanes of
+  // one (value, warp) pair with a per-thread rotation that keeps every access bank-conflict free, then N
+  // threads add the 8 warp totals in a fixed order.  ~3x fewer instructions than shuffles for N >= 15.
+  static_assert(L::total >= N * kThreads + N * kTH, "reduction buffers must fit in the tile buffers");
+  __syncthreads();
+  float* red = sm;
+  float* wsum = sm + N * kThreads;  // [N][kTH] warp totals
+#pragma unroll
+  for (int k = 0; k < N; ++k) red[k * kThreads + threadIdx.x] = vals[k];
+  __syncthreads();
+  for (int j = threadIdx.x; j < N * kTH; j += kThreads) {
+    const float4* src = reinterpret_cast<const float4*>(red + j * 32);   // row (value j >> 3, warp j & 7)
+    float a = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 q = src[(i + j) & 7];   // rotation: the 8 threads of a quarter-warp hit 8 different banks
+      a += (q.x + q.y) + (q.z + q.w);
+    }
+    wsum[j] = a;
+  }
+  __syncthreads();
+  if (threadIdx.x < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < kTH; ++w) t += wsum[threadIdx.x * kTH + w];
+    P.partials[(size_t)tile * N + threadIdx.x] = t;
+  }
 }
 
-// grid = B + 1 blocks of 256 threads.  Block b < B: pose gradients of batch element b (all views); one WARP per
+// grid = B + 1 blocks of 1024 threads.  Block b < B: pose gradients of batch element b (all views); one WARP per
 // (scale, view, component) sums that image's partial slots (lane-strided, then a fixed shuffle tree).
 // Block B: the three loss scalars.  Every sum runs in a fixed order in double => deterministic.
 template <int V>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 loss_finalize_kernel(const LossParams P, const float* __restrict__ poses, const float* __restrict__ K_pyr,
                      int pose_format, float inv_loss_scale, float* __restrict__ losses, float* __restrict__ g_poses) {
   constexpr int N = NT<V>::value;
@@ -407,14 +452,25 @@ loss_finalize_kernel(const LossParams P, const float* __restrict__ poses, const 
     return;
   }
   const int b = blockIdx.x;
-  for (int e = warp; e < P.S * V * 12; e += nwarp) {
-    const int k = e % 12, v = (e / 12) % V, s = e / (12 * V);
-    const int per_b = P.bands[s] * P.tiles_x[s];
-    const float* p = P.partials + (size_t)(P.item_begin[s] + b * per_b) * N + 3 + v * 12 + k;
-    double a = 0.0;
-    for (int i = lane; i < per_b; i += 32) a += (double)p[(size_t)i * N];
-    a = warp_dsum(a);
-    if (lane == 0) tsum[e] = a;
+  // loads of every round first (independent, all in flight), shuffle trees afterwards
+  constexpr int kRounds = (VSL_MAX_SCALES * V * 12 + 31) / 32;
+  double acc[kRounds];
+#pragma unroll
+  for (int r = 0; r < kRounds; ++r) {
+    const int e = warp + r * nwarp;
+    acc[r] = 0.0;
+    if (e < P.S * V * 12) {
+      const int k = e % 12, v = (e / 12) % V, s = e / (12 * V);
+      const int per_b = P.bands[s] * P.tiles_x[s];
+      const float* p = P.partials + (size_t)(P.item_begin[s] + b * per_b) * N + 3 + v * 12 + k;
+      for (int i = lane; i < per_b; i += 32) acc[r] += (double)p[(size_t)i * N];
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < kRounds; ++r) {
+    const int e = warp + r * nwarp;
+    const double a = warp_dsum(acc[r]);
+    if (lane == 0 && e < P.S * V * 12) tsum[e] = a;
   }
   __syncthreads();
   // dT[v][k][j] = sum_s sum_i K_s[i][k] * dP_s[i][j]: one thread per matrix element, short chains
@@ -442,16 +498,16 @@ loss_finalize_kernel(const LossParams P, const float* __restrict__ poses, const 
   if ((int)threadIdx.x >= V) return;
   const int v = threadIdx.x;
   const int psz = (pose_format == VSL_POSE_MATRIX) ? 16 : 6;
-  double gT[16];
+  float gT[16];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) gT[i] = sgT[v][i];
+  for (int i = 0; i < 16; ++i) gT[i] = (float)sgT[v][i];
   float* out = g_poses + ((size_t)b * V + v) * psz;
   if (pose_format == VSL_POSE_MATRIX) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) out[i] = (float)gT[i];
+    for (int i = 0; i < 16; ++i) out[i] = gT[i];
   } else {
     float g[6];
-    pose_vec_grad(poses + ((size_t)b * V + v) * 6, pose_format, gT, g);
+    pose_vec_grad<float>(poses + ((size_t)b * V + v) * 6, pose_format, gT, g);
 #pragma unroll
     for (int i = 0; i < 6; ++i) out[i] = g[i];
   }
@@ -512,7 +568,7 @@ int launch_fused(const WsLayout& L, const LossParams& P, cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute(loss_fused_kernel<V, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)Smem<V>::bytes);
   if (e != cudaSuccess) return (int)e;
-  loss_fused_kernel<V, EXACT><<<L.n_items, kThreads, Smem<V>::bytes, st>>>(P);
+  loss_fused_kernel<V, EXACT><<<dim3(P.img_begin[P.S], P.B), kThreads, Smem<V>::bytes, st>>>(P);
   return VSL_OK;
 }
 
@@ -523,7 +579,7 @@ int run_loss(const VslLossDesc* d, const WsLayout& L, LossParams& P, const float
   const int rc = d->exact_coords ? launch_fused<V, true>(L, P, st) : launch_fused<V, false>(L, P, st);
   if (rc != VSL_OK) return rc;
   if (d->ev_main_end != nullptr) cudaEventRecord((cudaEvent_t)d->ev_main_end, st);
-  loss_finalize_kernel<V><<<d->B + 1, 256, 0, st>>>(P, poses, K_pyr, d->pose_format, 1.0f / d->loss_scale,
+  loss_finalize_kernel<V><<<d->B + 1, 1024, 0, st>>>(P, poses, K_pyr, d->pose_format, 1.0f / d->loss_scale,
                                                        losses, g_poses);
   return launch_status();
 }
@@ -563,6 +619,8 @@ int vsl_loss_fwd_bwd(const VslLossDesc* d, const float* tgt, const float* const*
   P.xf = xf;
   P.partials = reinterpret_cast<float*>(base + L.partials);
   for (int s = 0; s <= d->S; ++s) P.item_begin[s] = L.item_begin[s];
+  P.img_begin[0] = 0;
+  for (int s = 0; s < d->S; ++s) P.img_begin[s + 1] = P.img_begin[s] + L.bands[s] * L.tiles_x[s];
   for (int v = 0; v < d->V; ++v) VSL_REQUIRE(srcs[v], VSL_E_NULL);
   for (int s = 0; s < VSL_MAX_SCALES; ++s) {
     P.tgt[s] = nullptr; P.x[s] = nullptr; P.logits[s] = nullptr; P.mask[s] = nullptr;
@@ -587,6 +645,9 @@ int vsl_loss_fwd_bwd(const VslLossDesc* d, const float* tgt, const float* const*
     P.tgt[s] = (s == 0) ? tgt : pyr + L.level_off[s];
     for (int v = 0; v < d->V; ++v) P.src[v][s] = (s == 0) ? srcs[v] : pyr + L.pyr_img * (size_t)(v + 1) + L.level_off[s];
     P.tiles_x[s] = L.tiles_x[s]; P.bands[s] = L.bands[s]; P.R[s] = L.R[s];
+    P.inv_tx[s] = 1.0f / (float)L.tiles_x[s];
+    P.wstep[s] = 2.0f / (float)(W - 1);  // fp32 division, as grid_step() does on the device
+    P.hstep[s] = 2.0f / (float)(H - 1);
     // 16-byte row alignment of the streamed operands: W % 4 == 0 makes every row start (and the tile's
     // x_base, a multiple of 32) a multiple of 4 pixels = 48 B of target / 8V*4 B of logits
     P.staged[s] = (W % 4 == 0) && aligned(P.tgt[s], 16) &&

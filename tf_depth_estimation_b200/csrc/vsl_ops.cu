@@ -22,10 +22,10 @@ __global__ void pose_bwd_kernel(const float* __restrict__ vec, const float* __re
                                 int format, float* __restrict__ g_vec) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
-  double gT[16];
+  float gT[16];
   for (int i = 0; i < 16; ++i) gT[i] = g_mat[b * 16 + i];
   float g[6];
-  pose_vec_grad(vec + b * 6, format, gT, g);
+  pose_vec_grad<float>(vec + b * 6, format, gT, g);
   for (int i = 0; i < 6; ++i) g_vec[b * 6 + i] = g[i];
 }
 
@@ -204,7 +204,7 @@ __global__ void warp_bwd_finalize_kernel(const float* __restrict__ partial, int 
     for (int i = 0; i < 16; ++i) g_pose[(size_t)b * 16 + i] = (float)gT[i];
   } else {
     float g[6];
-    pose_vec_grad(pose + (size_t)b * 6, format, gT, g);
+    pose_vec_grad<double>(pose + (size_t)b * 6, format, gT, g);
     for (int i = 0; i < 6; ++i) g_pose[(size_t)b * 6 + i] = g[i];
   }
 }

@@ -497,3 +497,82 @@ def view_synthesis_loss(tgt, srcs, x_pyr, poses, K_pyr, logits_pyr=None, mask_py
         plan = _PLANS[key] = ViewSynthesisPlan(B, H, W, V, flags, mode, tgt.device)
     rest = list(logits_pyr if logits_pyr is not None else (mask_pyr or []))
     return _ViewSynthesisLoss.apply(plan, tgt, list(srcs), K_pyr, poses, S, *x_pyr, *rest)
+
+
+class HostPipeline(object):
+    """Fused loss steps fed from HOST memory: inputs arrive in pinned host buffers, losses and gradients are
+    returned in pinned host buffers.  Three streams (H2D, compute, D2H) and two buffer sets overlap the copies of
+    neighbouring steps with the kernels, so steady-state throughput is max(H2D, compute, D2H), not their sum.
+
+    submit(host_inputs) enqueues one step and returns its slot; result(slot) waits for that step's D2H and returns
+    (losses[3], g_x list, g_poses, g_logits list) as pinned host tensors (valid until the slot is reused, i.e.
+    until two more submits).  host_inputs: dict(tgt, srcs, xs, poses, Kp, lgs) of pinned CPU tensors."""
+
+    DEPTH = 2
+
+    def __init__(self, B, H, W, V, flags, mask_mode, device, loss_scale=1.0):
+        self.device = device
+        self.plans = [ViewSynthesisPlan(B, H, W, V, flags, mask_mode, device, loss_scale) for _ in range(self.DEPTH)]
+        S = flags.num_scales
+        pose_shape = (B, V, 4, 4) if self.plans[0].fmt == 2 else (B, V, 6)
+        mk = lambda *shape: torch.empty(*shape, device=device)
+        self.dev_in = [dict(tgt=mk(B, H, W, 3), srcs=[mk(B, H, W, 3) for _ in range(V)],
+                            xs=[mk(B, H >> s, W >> s, 1) for s in range(S)], poses=mk(*pose_shape), Kp=mk(B, S, 3, 3),
+                            lgs=([mk(B, H >> s, W >> s, 2 * V) for s in range(S)] if mask_mode == _lib.MASK_EXP else None))
+                       for _ in range(self.DEPTH)]
+        self.bound = [p.bind(d['tgt'], d['srcs'], d['xs'], d['poses'], d['Kp'], d['lgs'])
+                      for p, d in zip(self.plans, self.dev_in)]
+        pin = lambda t: torch.empty(t.shape, dtype=t.dtype).pin_memory()
+        self.host_out = [dict(losses=pin(p.losses), g_x=[pin(g) for g in p.g_x], g_poses=pin(p.g_poses),
+                              g_lgs=[pin(g) for g in (p.g_logits or [])]) for p in self.plans]
+        self.s_in, self.s_comp, self.s_out = (torch.cuda.Stream(device=device) for _ in range(3))
+        ev = lambda: [torch.cuda.Event() for _ in range(self.DEPTH)]
+        self.ev_in, self.ev_comp, self.ev_out = ev(), ev(), ev()
+        self.step = 0
+
+    @staticmethod
+    def _flat(d):
+        out = []
+        for k in ('tgt', 'srcs', 'xs', 'poses', 'Kp', 'lgs'):
+            v = d.get(k)
+            if v is None:
+                continue
+            out.extend(v if isinstance(v, (list, tuple)) else [v])
+        return out
+
+    def bytes_per_step(self):
+        h2d = sum(t.numel() * 4 for t in self._flat(self.dev_in[0]))
+        o = self.host_out[0]
+        d2h = sum(t.numel() * 4 for t in [o['losses'], o['g_poses']] + o['g_x'] + o['g_lgs'])
+        return h2d, d2h
+
+    def submit(self, host_inputs):
+        k = self.step % self.DEPTH
+        plan, dev, out = self.plans[k], self.dev_in[k], self.host_out[k]
+        first_use = self.step < self.DEPTH
+        with torch.cuda.stream(self.s_in):
+            if not first_use:
+                self.s_in.wait_event(self.ev_comp[k])          # step-2's kernels have consumed these inputs
+            for src, dst in zip(self._flat(host_inputs), self._flat(dev)):
+                dst.copy_(src, non_blocking=True)
+            self.ev_in[k].record(self.s_in)
+        with torch.cuda.stream(self.s_comp):
+            self.s_comp.wait_event(self.ev_in[k])
+            if not first_use:
+                self.s_comp.wait_event(self.ev_out[k])          # step-2's gradients have left the device
+            plan.run_bound(self.bound[k], self.s_comp.cuda_stream)
+            self.ev_comp[k].record(self.s_comp)
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(self.ev_comp[k])
+            out['losses'].copy_(plan.losses, non_blocking=True)
+            for src, dst in zip(plan.g_x + [plan.g_poses] + (plan.g_logits or []),
+                                out['g_x'] + [out['g_poses']] + out['g_lgs']):
+                dst.copy_(src, non_blocking=True)
+            self.ev_out[k].record(self.s_out)
+        self.step += 1
+        return k
+
+    def result(self, slot):
+        self.ev_out[slot].synchronize()
+        o = self.host_out[slot]
+        return o['losses'], o['g_x'], o['g_poses'], o['g_lgs']
