@@ -44,5 +44,5 @@ for ln, (_, c) in zip(lines, body):
 print('total executed warp-instr', tot)
 acc = 0
 for ln, c in sorted(per.items(), key=lambda kv: (kv[0] or ('', 0))):
-    if c * 200 >= tot:
+    if c * 200 >= tot or os.environ.get("LP_ALL"):
         print('%6.2f%%  %9d  %s:%s' % (100.0 * c / tot, c, ln[0] if ln else '?', ln[1] if ln else '?'))

@@ -4,49 +4,65 @@
 // Python loop over S scales x V source views of ~150 TF ops each, then autodiff of all of it.  Here the
 // whole thing is three launches:
 //
-//   1. pyramid_kernel       (vsl_ops.cu)  resize_area levels 1..S-1 of the target and source images, and
-//                                         (riding along) K_s^-1 and P = K4_s . T_v per (scale, view, batch)
-//   2. loss_fused_kernel    (this file)   every scale and view in ONE grid, one block per tile:
-//        per target pixel: smoothness stencil (forward sum + gradient) on a shared-memory tile of x,
-//        then per view: back-project, pose, project, bilinear gather of the source, L1 against the
-//        target, explainability / validity mask, softmax cross-entropy regulariser -- and, because the
-//        loss is a weighted sum of means whose upstream gradient is known (loss_scale), the gradients
-//        d/dx, d/dlogits are written in the same pass and dP = sum du (x) [cam;1] is accumulated in
-//        registers and reduced once per block.  No full-resolution intermediate is ever written.
-//   3. loss_finalize_kernel (this file)   fixed-order reduction of the block partials (deterministic),
-//        dT = K4^T dP summed over scales, pose chain rule, the three loss scalars.
+//   1. loss_prep_kernel     resize_area levels 1..S-1 of the target (RGB) and, for every source view, ALL
+//                           levels 0..S-1 re-laid as zero-bordered RGBA (16 bytes per pixel, 2 pixels of
+//                           zeros all round); K_s^-1 and P = K4_s . T_v per (scale, view, batch) ride along.
+//   2. loss_fused_kernel    every scale and view in ONE grid.  A WARP owns a tile of 32 columns x kRH rows
+//                           of one image at one scale and never talks to another warp (no block barrier):
+//        smoothness: the warp stages x (+2 halo) in its slice of shared memory, evaluates the four second
+//        differences each element owns ONCE and publishes their weighted signs; then it walks down the
+//        rows, lane = column: smoothness gradient gathered from the published signs (vertical neighbours
+//        carried in registers), back-projection, and per view projection, bilinear gather, L1 against the
+//        target, explainability / validity mask, softmax cross-entropy regulariser -- and, because the loss
+//        is a weighted sum of means whose upstream gradient is known (loss_scale), d/dx and d/dlogits are
+//        written in the same pass and dP = sum du (x) [cam;1] is accumulated in registers and reduced once
+//        per tile with a shuffle butterfly.  No full-resolution intermediate is ever written.
+//   3. loss_finalize_kernel fixed-order reduction of the tile partials (deterministic), dT = K4^T dP summed
+//                           over scales, pose chain rule, the three loss scalars.
 //
-// Work decomposition: a tile is 8 rows x (32*R) columns of one image at one scale; block = 8 warps, warp w
-// owns row w, a thread visits R pixels 32 columns apart, so every global access of a warp is a run of 32
-// consecutive pixels.  Tiles of all scales live in one 1-D grid, largest scale first, and the hardware block
-// scheduler balances them (a persistent variant with static cost-balanced ranges measured 10 % slower).
+// Why the zero-bordered RGBA copy of the sources: the gather is the L1-throughput hot spot.  With packed
+// RGB a corner is three scalar loads whose 32 lanes straddle four cache lines each (12 loads, ~54 L1
+// wavefronts per pixel-view); with one pixel = one aligned float4 it is 4 loads / ~18 wavefronts.  The
+// border implements the sampler's zero padding (utils.py:266-270) in the DATA: a corner outside the image
+// reads zeros, so neither the value nor d/dx, d/dy needs the four "corner == clipped corner" masks, and
+// coordinates are simply clamped to [-2, size] (where everything in reach is zero) before the floor.
 //
-// Streaming operands (target tile, logits tile) enter shared memory with 16-byte cp.async issued before the
-// smoothness pass, so their latency is covered by it; d/dlogits is assembled in the logits tile in place and
-// leaves with 16-byte stores.  Only the data-dependent bilinear gathers go through L1 as scalar loads.
+// floor + float->int without the quarter-rate conversion pipe: t = x (+, round-down) 1.5*2^23 has
+// floor(x) in its low mantissa bits, so floor(x) = t - 1.5*2^23 and the integer is a bit-cast away.
 #include <algorithm>
 
 #include "vsl_common.cuh"
-// Part of the single translation unit vsl_lib.cu (prep_xforms_kernel / pyramid_kernel come from vsl_ops.cu).
+// Part of the single translation unit vsl_lib.cu (prep_one / PrepJob / row_sums / PyrLevel come from vsl_ops.cu).
 
 namespace vsl {
 
-constexpr int kTH = 8;                          // tile rows = warps per block
-constexpr int kThreads = 32 * kTH;
-constexpr int kMaxR = 4;                        // pixels per thread
-constexpr int kTW = 32 * kMaxR;                 // tile columns
+#ifndef VSL_RH
+#define VSL_RH 16
+#endif
+#ifndef VSL_FUSED_WARPS
+#define VSL_FUSED_WARPS 8
+#endif
+#ifndef VSL_FUSED_MIN_BLOCKS
+#define VSL_FUSED_MIN_BLOCKS 2
+#endif
+
+constexpr int kRH = VSL_RH;                     // tile rows per warp
+constexpr int kWarps = VSL_FUSED_WARPS;         // independent warps per block
+constexpr int kThreads = 32 * kWarps;
 constexpr int kHalo = 2;
-constexpr int kTileH = kTH + 2 * kHalo;         // 12 rows of x
-constexpr int kQStride = kTW + 2 * kHalo + 4;   // 136
-constexpr int kOwnW = kTW + kHalo;              // owners: tile + 2 columns to the left
-constexpr int kOwnH = kTH + kHalo;              //         tile + 2 rows above
-constexpr int kOStride = kOwnW + 2;             // 132
+constexpr int kQH = kRH + 2 * kHalo;            // rows of x held per tile
+constexpr int kQS = 32 + 2 * kHalo;             // 36 columns of x
+constexpr int kOH = kRH + kHalo;                // owner rows: tile + 2 above
+constexpr int kOW = 32 + kHalo;                 // owner columns: tile + 2 to the left
+constexpr int kPad = 2;                         // zero border (pixels) of the RGBA source levels
+constexpr float kMagic = 12582912.0f;           // 1.5 * 2^23
+constexpr unsigned kMagicBits = 0x4B400000u;
 
 struct LossParams {
   int B, H, W, S, V;
   int mask_mode, depth_is_inverse, smooth_on_inverse;
-  const float* tgt[VSL_MAX_SCALES];
-  const float* src[VSL_MAX_VIEWS][VSL_MAX_SCALES];
+  const float* tgt[VSL_MAX_SCALES];                    // RGB
+  const float4* src[VSL_MAX_VIEWS][VSL_MAX_SCALES];    // zero-bordered RGBA [B][Hs+4][Ws+4]
   const float* x[VSL_MAX_SCALES];
   const float* logits[VSL_MAX_SCALES];
   const float* mask[VSL_MAX_SCALES];
@@ -58,299 +74,326 @@ struct LossParams {
   float cexp[VSL_MAX_SCALES];      // loss_scale * explain_reg_weight / (B Hs Ws)
   float csm[VSL_MAX_SCALES][4];    // loss_scale * smooth_weight / 2^s / count_k   (xx, xy, yx, yy)
   int item_begin[VSL_MAX_SCALES + 1];
-  int tiles_x[VSL_MAX_SCALES], bands[VSL_MAX_SCALES], R[VSL_MAX_SCALES];
-  int staged[VSL_MAX_SCALES];      // 1: rows of this scale are 16-byte aligned -> cp.async / vector path
-  int img_begin[VSL_MAX_SCALES + 1];  // prefix sums of tiles per image over the scales (grid.x index -> scale)
-  float inv_tx[VSL_MAX_SCALES];    // 1 / tiles_x
+  int strips[VSL_MAX_SCALES], bands[VSL_MAX_SCALES];
+  int lg_vec4[VSL_MAX_SCALES];     // logits / g_logits of this scale are 16-byte aligned (and V is even)
   float wstep[VSL_MAX_SCALES], hstep[VSL_MAX_SCALES];  // meshgrid linspace steps 2/(W-1), 2/(H-1) in fp32
 };
 
 template <int V> struct NT { static constexpr int value = 3 + 12 * V; };
 
-// dynamic shared memory carve-up (floats)
-template <int V> struct Smem {
-  static constexpr int qt = 0;                                   // [kTileH][kQStride]
-  static constexpr int sA = qt + kTileH * kQStride;              // [kOwnH][kOStride] x 3
-  static constexpr int sB = sA + kOwnH * kOStride;
-  static constexpr int sC = sB + kOwnH * kOStride;
-  static constexpr int xf = sC + kOwnH * kOStride;               // V * 21 (padded to 24)
-  static constexpr int scratch = xf + V * 24;                    // NT * kTH
-  static constexpr int tgt = (scratch + NT<V>::value * kTH + 3) / 4 * 4;   // [kTH][kTW*3], 16-byte aligned
-  static constexpr int lg = tgt + kTH * kTW * 3;                 // [kTH][kTW*2V]
-  static constexpr int total = lg + kTH * kTW * 2 * V;
-  static constexpr size_t bytes = sizeof(float) * total;
+// one warp's slice of dynamic shared memory (floats)
+template <int V> struct WarpSmem {
+  static constexpr int qt = 0;                          // [kQH][kQS]  x or 1/x with a 2-pixel halo
+  static constexpr int sA = qt + kQH * kQS;             // [kOH][kOW]  cxx * sign(dx2) per owner
+  static constexpr int sB = sA + kOH * kOW;             //             cyy * sign(dy2)
+  static constexpr int sC = sB + kOH * kOW;             //             cxy*sign(dxdy) + cyx*sign(dydx)
+  static constexpr int xf = (sC + kOH * kOW + 3) / 4 * 4;   // K^-1 rows padded to float4 (12), then V x P (12)
+  static constexpr int total = (xf + 12 + 12 * V + 3) / 4 * 4;
+  static constexpr size_t block_bytes = sizeof(float) * total * kWarps;
 };
 
 VSL_DEV float signed_by(float c, float v) {  // c * sign(v), sign(0) = 0
   return (v == 0.f) ? 0.f : copysignf(c, v);
 }
-
-VSL_DEV void cp_async16(float* smem_dst, const float* gmem_src) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+VSL_DEV float rcp_fast(float a) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+  return r;
 }
-VSL_DEV void cp_async_wait_all() {
-  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+// sign(e) in {-1, 0, 1} with two FMA-pipe instructions: sat(e * 2^100 + 0.5) is 0, 0.5 or 1
+VSL_DEV float sign_fast(float e) {
+  return fmaf(__saturatef(fmaf(e, 1.2676506e30f, 0.5f)), 2.0f, -1.0f);
+}
+
+// What one (pixel, view) has in flight between issuing its gathers and consuming them.
+struct Tap {
+  float4 A, B, C, D;             // corners (x0,y0) (x1,y0) (x0,y1) (x1,y1)
+  float wx0, wx1, wy0, wy1;      // (x1 - x), (x - x0), (y1 - y), (y - y0)
+  float qx, qy, rz;              // projected coordinates (unclamped) and 1 / (z + eps)
+};
+
+// Projection, footprint and the four 16-byte gathers of one view.  pp: the 12 floats of P in shared memory.
+template <bool EXACT>
+VSL_DEV void tap_issue(Tap& t, const float* pp, float c0, float c1, float c2, const float4* __restrict__ src,
+                       int stride4, int coff, float Wf, float Hf) {
+  const float4 P0 = *reinterpret_cast<const float4*>(pp), P1 = *reinterpret_cast<const float4*>(pp + 4),
+               P2 = *reinterpret_cast<const float4*>(pp + 8);
+  if (EXACT) {
+    const float p[12] = {P0.x, P0.y, P0.z, P0.w, P1.x, P1.y, P1.z, P1.w, P2.x, P2.y, P2.z, P2.w};
+    const Proj q = project(p, c0, c1, c2);
+    t.qx = q.x; t.qy = q.y; t.rz = 1.0f / q.zp;
+  } else {
+    const float u0 = fmaf(P0.x, c0, fmaf(P0.y, c1, fmaf(P0.z, c2, P0.w)));
+    const float u1 = fmaf(P1.x, c0, fmaf(P1.y, c1, fmaf(P1.z, c2, P1.w)));
+    const float u2 = fmaf(P2.x, c0, fmaf(P2.y, c1, fmaf(P2.z, c2, P2.w)));
+    t.rz = rcp_fast(u2 + kEpsZ);
+    t.qx = u0 * t.rz; t.qy = u1 * t.rz;
+  }
+  // beyond [-2, size] all four corners are border zeros; clamping there changes neither value nor gradient
+  const float xc = fminf(fmaxf(t.qx, -2.0f), Wf), yc = fminf(fmaxf(t.qy, -2.0f), Hf);
+  const float tx = __fadd_rd(xc, kMagic), ty = __fadd_rd(yc, kMagic);
+  const float fx = __fsub_rn(tx, kMagic), fy = __fsub_rn(ty, kMagic);   // floor, exactly
+  t.wx1 = __fsub_rn(xc, fx); t.wy1 = __fsub_rn(yc, fy);
+  if (EXACT) {
+    t.wx0 = __fsub_rn(__fadd_rn(fx, 1.0f), xc); t.wy0 = __fsub_rn(__fadd_rn(fy, 1.0f), yc);
+  } else {
+    t.wx0 = 1.0f - t.wx1; t.wy0 = 1.0f - t.wy1;
+  }
+  const int off = (int)(__float_as_uint(ty) * (unsigned)stride4 + __float_as_uint(tx) + (unsigned)coff);  // wraps to the true offset
+  const float4* __restrict__ p = src + off;
+  t.A = __ldg(p); t.B = __ldg(p + 1);
+  t.C = __ldg(p + stride4); t.D = __ldg(p + stride4 + 1);
 }
 
 // EXACT = true : coordinates, softmax and the warped value follow the reference's rounding sequence
 //                (bit-identical sample positions to the oracle for matrix poses).
 // EXACT = false: the same algebra with FMA contraction, MUFU reciprocal / exp / log and the closed form
 //                d(depth) = -<du, t> / depth; differs from EXACT by a few ulp per quantity.
-#ifndef VSL_FUSED_MIN_BLOCKS
-#define VSL_FUSED_MIN_BLOCKS 3
-#endif
 template <int V, bool EXACT>
 __global__ void __launch_bounds__(kThreads, VSL_FUSED_MIN_BLOCKS)
 loss_fused_kernel(const LossParams P) {
   constexpr int N = NT<V>::value;
-  using L = Smem<V>;
+  using L = WarpSmem<V>;
   extern __shared__ float4 smem4[];
-  float* sm = reinterpret_cast<float*>(smem4);
-  float (*qt)[kQStride] = reinterpret_cast<float (*)[kQStride]>(sm + L::qt);   // x or 1/x with a 2-pixel halo
-  float (*sA)[kOStride] = reinterpret_cast<float (*)[kOStride]>(sm + L::sA);   // cxx * sign(dx2) per owner
-  float (*sB)[kOStride] = reinterpret_cast<float (*)[kOStride]>(sm + L::sB);   // cyy * sign(dy2)
-  float (*sC)[kOStride] = reinterpret_cast<float (*)[kOStride]>(sm + L::sC);   // cxy*sign(dxdy) + cyx*sign(dydx)
-  float* sxf = sm + L::xf;                                                     // per view: kinv[9], p[12]
-  float* scratch = sm + L::scratch;
-  float* s_tgt = sm + L::tgt;
-  float* s_lg = sm + L::lg;
-
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // ---- which tile: grid = (tiles per image over all scales, B); no integer division on the way
-  const int t_img = blockIdx.x, b = blockIdx.y;
+  const int tile = blockIdx.x * kWarps + warp;
+  if (tile >= P.item_begin[P.S]) return;   // warps are independent: no block barrier anywhere below
+  float* wsm = reinterpret_cast<float*>(smem4) + warp * L::total;
+  float* qt = wsm + L::qt;
+  float* sA = wsm + L::sA;
+  float* sB = wsm + L::sB;
+  float* sC = wsm + L::sC;
+  float* sxf = wsm + L::xf;
+
+  // ---- which tile
   int s = 0;
-  while (s + 1 < P.S && t_img >= P.img_begin[s + 1]) ++s;
-  const int rem = t_img - P.img_begin[s];
-  const int band = __float2int_rz(((float)rem + 0.5f) * P.inv_tx[s]), tx = rem - band * P.tiles_x[s];
-  const int tile = P.item_begin[s] + b * (P.img_begin[s + 1] - P.img_begin[s]) + rem;  // partial slot
-  const int H = P.H >> s, W = P.W >> s, R = P.R[s];
-  const int y_base = band * kTH, x_base = tx * 32 * R;
-  const int cols = min(32 * R, W - x_base);            // valid columns of this tile
-  const int tw = ((cols + 31) >> 5) << 5;               // rounded up to whole warp iterations
+  while (s + 1 < P.S && tile >= P.item_begin[s + 1]) ++s;
+  const int strips = P.strips[s], per_b = strips * P.bands[s];
+  const int rem = tile - P.item_begin[s];
+  const int b = rem / per_b, r2 = rem - b * per_b;
+  const int band = r2 / strips, strip = r2 - band * strips;
+  const int H = P.H >> s, W = P.W >> s;
+  const int y_base = band * kRH, x_base = strip * 32;
+  const int rows = min(kRH, H - y_base);
+  const int x = x_base + lane;
+  const bool act = x < W;
   const size_t img_off = (size_t)b * H * W;
-  const int y = y_base + warp;                          // this warp's row
-  const bool staged = P.staged[s] != 0;
   const bool use_lg = P.mask_mode == VSL_MASK_EXP;
 
-  // ---- 1. streaming operands: target and logits rows of the tile -> shared memory, asynchronously
-  if (staged && y < H) {
-    const size_t row = img_off + (size_t)y * W + x_base;
-    const float* __restrict__ gt = P.tgt[s] + row * 3;
-    float* dt = s_tgt + warp * (kTW * 3);
-    for (int k = lane; k < (cols * 3) >> 2; k += 32) cp_async16(dt + 4 * k, gt + 4 * k);
-    if (use_lg) {
-      const float* __restrict__ gl = P.logits[s] + row * (2 * V);
-      float* dl = s_lg + warp * (kTW * 2 * V);
-      for (int k = lane; k < (cols * 2 * V) >> 2; k += 32) cp_async16(dl + 4 * k, gl + 4 * k);
-    }
-  }
-
-  // ---- 2. the x tile (+halo) and this image's V transforms
+  // ---- 1. the x tile (+halo), zero outside the image, and this image's transforms
   const float* __restrict__ xs = P.x[s] + img_off;
-  for (int ty = warp; ty < kTileH; ty += kTH) {
-    const int gy = y_base + ty - kHalo;
-    const bool rin = gy >= 0 && gy < H;
-    const float* __restrict__ row = xs + (size_t)(rin ? gy : 0) * W;
-    for (int tc = lane; tc < tw + 2 * kHalo; tc += 32) {
-      const int gx = x_base + tc - kHalo;
-      qt[ty][tc] = (rin && gx >= 0 && gx < W) ? row[gx] : 0.f;
-    }
-  }
-  if (P.smooth_on_inverse) {  // each thread revisits exactly the elements it wrote
-    for (int ty = warp; ty < kTileH; ty += kTH) {
-      const int gy = y_base + ty - kHalo;
-      for (int tc = lane; tc < tw + 2 * kHalo; tc += 32) {
-        const int gx = x_base + tc - kHalo;
-        if (gy >= 0 && gy < H && gx >= 0 && gx < W) qt[ty][tc] = __fdiv_rn(1.0f, qt[ty][tc]);
+  {
+    const bool inv_q = P.smooth_on_inverse != 0;
+#pragma unroll 4
+    for (int i = lane; i < kQH * kQS; i += 32) {
+      const int ty = i / kQS, tc = i - ty * kQS;
+      const int gy = y_base - kHalo + ty, gx = x_base - kHalo + tc;
+      float v = 0.f;
+      if ((unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W) {
+        v = __ldg(xs + gy * W + gx);
+        if (inv_q) v = __fdiv_rn(1.0f, v);
       }
+      qt[i] = v;
+    }
+    if (lane < 12) {
+      const int row = lane >> 2, col = lane & 3;
+      const Xform* xf0 = P.xf + ((size_t)s * V) * P.B + b;
+      sxf[lane] = col < 3 ? xf0->kinv[row * 3 + col] : 0.f;
+#pragma unroll
+      for (int v = 0; v < V; ++v) sxf[12 + v * 12 + lane] = P.xf[((size_t)s * V + v) * P.B + b].p[lane];
     }
   }
-  if (threadIdx.x < V * 21) {  // per view: K^-1 rows padded to float4 (12 floats), then the 3 rows of P (12 floats)
-    const int v = threadIdx.x / 21, k = threadIdx.x - v * 21;
-    const int dst = k < 9 ? (k / 3) * 4 + k % 3 : 12 + (k - 9);
-    sxf[v * 24 + dst] = reinterpret_cast<const float*>(P.xf + ((size_t)s * V + v) * P.B + b)[k];
-  }
-  __syncthreads();
+  __syncwarp();
 
   const float cpix = P.cpix[s], cexp = P.cexp[s];
   float pix_sum = 0.f, exp_sum = 0.f, sm_sum = 0.f;
 
-  // ---- 3. smoothness, pass 1: every element of (tile + 2 rows above + 2 columns left) evaluates the four
+  // ---- 2. smoothness, pass 1: every element of (tile + 2 rows above + 2 columns left) evaluates the four
   // second differences it owns (it is their top-left corner) ONCE and publishes their weighted signs.
   {
     const float cxx = P.csm[s][0], cxy = P.csm[s][1], cyx = P.csm[s][2], cyy = P.csm[s][3];
-    for (int oy = warp; oy < kOwnH; oy += kTH) {
-      const int gy = y_base - kHalo + oy;
-      const bool rin = gy >= 0 && gy < H;
-      for (int ox = lane; ox < tw + kHalo; ox += 32) {
-        const int gx = x_base - kHalo + ox;
-        const bool in = rin && gx >= 0 && gx < W;
-        const float q00 = qt[oy][ox], q01 = qt[oy][ox + 1], q02 = qt[oy][ox + 2];
-        const float q10 = qt[oy + 1][ox], q11 = qt[oy + 1][ox + 1], q20 = qt[oy + 2][ox];
-        const float dx0 = __fsub_rn(q01, q00), dy0 = __fsub_rn(q10, q00);
-        float dxx = __fsub_rn(__fsub_rn(q02, q01), dx0);
-        float dyy = __fsub_rn(__fsub_rn(q20, q10), dy0);
-        float dxy = __fsub_rn(__fsub_rn(q11, q10), dx0);  // d/dy of dx
-        float dyx = __fsub_rn(__fsub_rn(q11, q01), dy0);  // d/dx of dy
-        if (!(in && gx + 2 < W)) dxx = 0.f;
-        if (!(in && gy + 2 < H)) dyy = 0.f;
-        if (!(in && gx + 1 < W && gy + 1 < H)) { dxy = 0.f; dyx = 0.f; }
-        sA[oy][ox] = signed_by(cxx, dxx);
-        sB[oy][ox] = signed_by(cyy, dyy);
-        sC[oy][ox] = signed_by(cxy, dxy) + signed_by(cyx, dyx);
-        if (oy >= kHalo && ox >= kHalo)
-          sm_sum += cxx * fabsf(dxx) + cyy * fabsf(dyy) + cxy * fabsf(dxy) + cyx * fabsf(dyx);
-      }
+#pragma unroll 2
+    for (int i = lane; i < kOH * kOW; i += 32) {
+      const int oy = i / kOW, ox = i - oy * kOW;
+      const float* q = qt + oy * kQS + ox;
+      const float q00 = q[0], q01 = q[1], q02 = q[2], q10 = q[kQS], q11 = q[kQS + 1], q20 = q[2 * kQS];
+      const int gx = x_base - kHalo + ox, gy = y_base - kHalo + oy;
+      const float dx0 = __fsub_rn(q01, q00), dy0 = __fsub_rn(q10, q00);
+      float dxx = __fsub_rn(__fsub_rn(q02, q01), dx0);
+      float dyy = __fsub_rn(__fsub_rn(q20, q10), dy0);
+      float dxy = __fsub_rn(__fsub_rn(q11, q10), dx0);  // d/dy of dx
+      float dyx = __fsub_rn(__fsub_rn(q11, q01), dy0);  // d/dx of dy
+      // a difference exists iff its whole support lies inside the image
+      const bool xin = (unsigned)gx < (unsigned)W, yin = (unsigned)gy < (unsigned)H;
+      const bool x1in = gx >= 0 && gx + 1 < W, y1in = gy >= 0 && gy + 1 < H;
+      if (!(yin && gx >= 0 && gx + 2 < W)) dxx = 0.f;
+      if (!(xin && gy >= 0 && gy + 2 < H)) dyy = 0.f;
+      if (!(x1in && y1in)) { dxy = 0.f; dyx = 0.f; }
+      sA[i] = signed_by(cxx, dxx);
+      sB[i] = signed_by(cyy, dyy);
+      sC[i] = signed_by(cxy, dxy) + signed_by(cyx, dyx);
+      if (oy >= kHalo && ox >= kHalo)
+        sm_sum += cxx * fabsf(dxx) + cyy * fabsf(dyy) + cxy * fabsf(dxy) + cyx * fabsf(dyx);
     }
   }
-  cp_async_wait_all();
-  __syncthreads();
+  __syncwarp();
 
-  // ---- 4. the pixels
-  const float gy = grid_coord(y, H, P.hstep[s]);
-  const float wstep = P.wstep[s];
-  float S1[V][3], S3[V][3], S4[V][3];  // sum du*d*gx, du*d, du   (sum du*d*gy = gy * S3: the row is fixed)
+  // ---- 3. the pixels: lane = column, walking down the rows of the tile
+  const float gx = grid_coord(x, W, P.wstep[s]);
+  const float hstep = P.hstep[s];
+  const float Wf = (float)W, Hf = (float)H;
+  const int stride4 = W + 2 * kPad;
+  // corner offset = (iy + kPad) * stride4 + (ix + kPad) with iy, ix still carrying the magic bias
+  const int coff = (int)((unsigned)(kPad * stride4 + kPad) - kMagicBits * (unsigned)(stride4 + 1));
+  const size_t src_off = (size_t)b * (H + 2 * kPad) * stride4;
+
+  // K^-1: the column that multiplies gx is folded per thread, the other two stay as warp-uniform values
+  const float4 k0 = *reinterpret_cast<const float4*>(sxf), k1 = *reinterpret_cast<const float4*>(sxf + 4),
+               k2 = *reinterpret_cast<const float4*>(sxf + 8);
+  float kx0, kx1, kx2;
+  if (EXACT) {
+    kx0 = __fmul_rn(k0.x, gx); kx1 = __fmul_rn(k1.x, gx); kx2 = __fmul_rn(k2.x, gx);
+  } else {
+    kx0 = fmaf(k0.x, gx, k0.z); kx1 = fmaf(k1.x, gx, k1.z); kx2 = fmaf(k2.x, gx, k2.z);
+  }
+
+  float S2[V][3], S3[V][3], S4[V][3];  // sum du*d*gy, du*d, du   (sum du*d*gx = gx * S3: the column is fixed)
 #pragma unroll
   for (int v = 0; v < V; ++v)
 #pragma unroll
-    for (int i = 0; i < 3; ++i) { S1[v][i] = 0.f; S3[v][i] = 0.f; S4[v][i] = 0.f; }
+    for (int i = 0; i < 3; ++i) { S2[v][i] = 0.f; S3[v][i] = 0.f; S4[v][i] = 0.f; }
 
-  if (y < H) {
-    for (int r = 0; r * 32 < tw; ++r) {
-      const int xl = r * 32 + lane;                // column inside the tile
-      const int x = x_base + xl;
-      if (x >= W) continue;
-      const int pofs = y * W + x;                  // pixel offset inside this image
-      const size_t pix = img_off + pofs;
-      const int oy = warp + kHalo, ox = xl + kHalo;
+  // vertical neighbours of the smoothness gradient travel down in registers
+  const int o0 = kHalo * kOW + lane + kHalo;          // owner slot of (row 0, this column)
+  float b2 = sB[o0 - 2 * kOW], b1 = sB[o0 - kOW];
+  float c10 = sC[o0 - kOW], c11 = sC[o0 - kOW - 1];
 
-      // smoothness, pass 2: gradient = the published signs of the 10 stencils this element is part of
-      const float g_q = (sA[oy][ox] - 2.f * sA[oy][ox - 1] + sA[oy][ox - 2]) +
-                        (sB[oy][ox] - 2.f * sB[oy - 1][ox] + sB[oy - 2][ox]) +
-                        (sC[oy][ox] - sC[oy][ox - 1] - sC[oy - 1][ox] + sC[oy - 1][ox - 1]);
+  const float* __restrict__ tgt_img = P.tgt[s] + img_off * 3;
+  const float* __restrict__ lg_img = use_lg ? P.logits[s] + img_off * (2 * V) : nullptr;
+  float* __restrict__ glg_img = use_lg ? P.g_logits[s] + img_off * (2 * V) : nullptr;
+  const float* __restrict__ mk_img = P.mask_mode == VSL_MASK_CONST ? P.mask[s] + img_off : nullptr;
+  float* __restrict__ gx_img = P.g_x[s] + img_off;
+  const bool lg4 = (V % 2 == 0) && P.lg_vec4[s] != 0;
+  const int smooth_inv = P.smooth_on_inverse, depth_inv = P.depth_is_inverse;
 
-      // depth of this pixel and d(depth)/dx, d(q)/dx
-      const float qc = qt[oy][ox];
-      float d, dd_dx, dq_dx;
-      if (P.smooth_on_inverse) {
-        dq_dx = -qc * qc;
-        if (P.depth_is_inverse) { d = qc; dd_dx = dq_dx; }
-        else { d = xs[pofs]; dd_dx = 1.f; }
-      } else {
-        dq_dx = 1.f;
-        if (P.depth_is_inverse) { d = EXACT ? __fdiv_rn(1.0f, qc) : __fdividef(1.0f, qc); dd_dx = -d * d; }
-        else { d = qc; dd_dx = 1.f; }
-      }
+  for (int r = 0; r < rows; ++r) {
+    const int y = y_base + r;
+    const int o = o0 + r * kOW;
+    // smoothness, pass 2: gradient = the published signs of the 10 stencils this element is part of
+    const float a0 = sA[o], a1 = sA[o - 1], a2 = sA[o - 2];
+    const float b0 = sB[o], c00 = sC[o], c01 = sC[o - 1];
+    const float g_q = (a0 - 2.f * a1 + a2) + (b0 - 2.f * b1 + b2) + (c00 - c01 - c10 + c11);
+    b2 = b1; b1 = b0; c10 = c00; c11 = c01;
+    if (!act) continue;
 
-      const float gx = grid_coord(x, W, wstep);
-      float tt[3];
-      if (staged) {
-        const float* t = s_tgt + (warp * kTW + xl) * 3;
-        tt[0] = t[0]; tt[1] = t[1]; tt[2] = t[2];
-      } else {
-        const float* __restrict__ t = P.tgt[s] + pix * 3;
-        tt[0] = t[0]; tt[1] = t[1]; tt[2] = t[2];
-      }
-      const float dgx = d * gx;
-      // K^-1 is the same for every view of a scale
-      float r0, r1, r2;
-      {
-        const float4 k0 = *reinterpret_cast<const float4*>(sxf), k1 = *reinterpret_cast<const float4*>(sxf + 4),
-                     k2 = *reinterpret_cast<const float4*>(sxf + 8);
-        if (EXACT) {
-          const float kk[9] = {k0.x, k0.y, k0.z, k1.x, k1.y, k1.z, k2.x, k2.y, k2.z};
-          Ray ray = back_project(kk, gx, gy);
-          r0 = ray.r0; r1 = ray.r1; r2 = ray.r2;
-        } else {
-          r0 = fmaf(k0.x, gx, fmaf(k0.y, gy, k0.z));
-          r1 = fmaf(k1.x, gx, fmaf(k1.y, gy, k1.z));
-          r2 = fmaf(k2.x, gx, fmaf(k2.y, gy, k2.z));
-        }
-      }
-      const float c0 = __fmul_rn(r0, d), c1 = __fmul_rn(r1, d), c2 = __fmul_rn(r2, d);
-      float g_d = 0.f;
-
+    const int pofs = y * W + x;                  // pixel offset inside this image
+    const float qc = qt[(r + kHalo) * kQS + lane + kHalo];
+    float d, dd_dx, dq_dx;
+    if (smooth_inv) {
+      dq_dx = -qc * qc;
+      if (depth_inv) { d = qc; dd_dx = dq_dx; }
+      else { d = __ldg(xs + pofs); dd_dx = 1.f; }
+    } else {
+      dq_dx = 1.f;
+      if (depth_inv) { d = EXACT ? __fdiv_rn(1.0f, qc) : rcp_fast(qc); dd_dx = -d * d; }
+      else { d = qc; dd_dx = 1.f; }
+    }
+    float tt[3];
 #pragma unroll
-      for (int v = 0; v < V; ++v) {
-#ifdef VSL_XF_VEC
-        const float4 P0 = *reinterpret_cast<const float4*>(sxf + v * 24 + 12),
-                     P1 = *reinterpret_cast<const float4*>(sxf + v * 24 + 16),
-                     P2 = *reinterpret_cast<const float4*>(sxf + v * 24 + 20);
-        const float pp[12] = {P0.x, P0.y, P0.z, P0.w, P1.x, P1.y, P1.z, P1.w, P2.x, P2.y, P2.z, P2.w};
-#else
-        const float* __restrict__ pp = sxf + v * 24 + 12;
-#endif
-        float qx, qy, rz;
-        if (EXACT) {
-          Proj q = project(pp, c0, c1, c2);
-          qx = q.x; qy = q.y; rz = 1.0f / q.zp;
-        } else {
-          const float u0 = fmaf(pp[0], c0, fmaf(pp[1], c1, fmaf(pp[2], c2, pp[3])));
-          const float u1 = fmaf(pp[4], c0, fmaf(pp[5], c1, fmaf(pp[6], c2, pp[7])));
-          const float u2 = fmaf(pp[8], c0, fmaf(pp[9], c1, fmaf(pp[10], c2, pp[11])));
-          rz = __fdividef(1.0f, u2 + kEpsZ);
-          qx = u0 * rz; qy = u1 * rz;
-        }
-        const Foot f = footprint(qx, qy, W, H);
-        const float* __restrict__ p00 = P.src[v][s] + (img_off + (size_t)(f.y0 * W + f.x0)) * 3;
-        const int dxo = (f.x1 - f.x0) * 3, dyo = (f.y1 - f.y0) * W * 3;
-        const float* __restrict__ p10 = p00 + dxo;
-        const float* __restrict__ p01 = p00 + dyo;
-        const float* __restrict__ p11 = p01 + dxo;
-        float i00[3], i01[3], i10[3], i11[3];
+    for (int c = 0; c < 3; ++c) tt[c] = __ldg(tgt_img + pofs * 3 + c);
+    float lg[2 * V];
+    if (use_lg) {
+      if (lg4) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          i00[c] = __ldg(p00 + c); i10[c] = __ldg(p10 + c); i01[c] = __ldg(p01 + c); i11[c] = __ldg(p11 + c);
+        for (int k = 0; k < V / 2; ++k) {
+          const float4 q = __ldg(reinterpret_cast<const float4*>(lg_img + (size_t)pofs * (2 * V)) + k);
+          lg[4 * k] = q.x; lg[4 * k + 1] = q.y; lg[4 * k + 2] = q.z; lg[4 * k + 3] = q.w;
         }
+      } else {
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          const float2 q = __ldg(reinterpret_cast<const float2*>(lg_img + (size_t)pofs * (2 * V)) + k);
+          lg[2 * k] = q.x; lg[2 * k + 1] = q.y;
+        }
+      }
+    }
+    float mconst = 1.f;
+    if (mk_img != nullptr) mconst = __ldg(mk_img + pofs);
+
+    const float gy = grid_coord(y, H, hstep);
+    float r0, r1, r2;
+    if (EXACT) {  // pixel2cam's matmul (utils.py:114): sequential k, no contraction
+      r0 = __fadd_rn(__fadd_rn(kx0, __fmul_rn(k0.y, gy)), k0.z);
+      r1 = __fadd_rn(__fadd_rn(kx1, __fmul_rn(k1.y, gy)), k1.z);
+      r2 = __fadd_rn(__fadd_rn(kx2, __fmul_rn(k2.y, gy)), k2.z);
+    } else {
+      r0 = fmaf(k0.y, gy, kx0); r1 = fmaf(k1.y, gy, kx1); r2 = fmaf(k2.y, gy, kx2);
+    }
+    const float c0 = __fmul_rn(r0, d), c1 = __fmul_rn(r1, d), c2 = __fmul_rn(r2, d);
+    const float dgy = d * gy;
+    float g_d = 0.f;
+
+    // views two at a time: both sets of gathers are in flight before either is consumed
+#pragma unroll
+    for (int v0 = 0; v0 < V; v0 += 2) {
+      constexpr int kPair = 2;
+      Tap tap[kPair];
+#pragma unroll
+      for (int j = 0; j < kPair; ++j) {
+        const int v = v0 + j;
+        if (v < V)
+          tap_issue<EXACT>(tap[j], sxf + 12 + v * 12, c0, c1, c2, P.src[v][s] + src_off, stride4, coff, Wf, Hf);
+      }
+#pragma unroll
+      for (int j = 0; j < kPair; ++j) {
+        const int v = v0 + j;
+        if (v >= V) continue;
+        const Tap& t = tap[j];
         // mask value m (explainability softmax or constant) and the regulariser
-        float m = 1.f, p0 = 0.f, p1 = 0.f;
-        float* lgp = s_lg + (warp * kTW + xl) * (2 * V) + 2 * v;   // staged logits slot, reused for d/dlogits
+        float m = mconst, p0 = 0.f, p1 = 0.f;
         if (use_lg) {
-          const float2 lg = staged ? *reinterpret_cast<const float2*>(lgp)
-                                   : *reinterpret_cast<const float2*>(P.logits[s] + pix * (2 * V) + 2 * v);
+          const float l0 = lg[2 * v], l1 = lg[2 * v + 1];
           if (EXACT) {
-            const float mx = fmaxf(lg.x, lg.y);
-            const float e0 = expf(lg.x - mx), e1 = expf(lg.y - mx), se = e0 + e1;
+            const float mx = fmaxf(l0, l1);
+            const float e0 = expf(l0 - mx), e1 = expf(l1 - mx), se = e0 + e1;
             p0 = e0 / se; p1 = e1 / se;
-            exp_sum += (mx + logf(se)) - lg.y;
+            exp_sum += (mx + logf(se)) - l1;
           } else {
-            const float z = lg.x - lg.y;
-            const float t = __expf(-fabsf(z)), se = 1.f + t, big = __fdividef(1.f, se), small = t * big;
+            const float z = l0 - l1;
+            const float e = __expf(-fabsf(z)), se = 1.f + e, big = rcp_fast(se), small = e * big;
             p0 = z >= 0.f ? big : small;
             p1 = z >= 0.f ? small : big;
             exp_sum += __logf(se) + fmaxf(z, 0.f);
           }
           m = p1;
-        } else if (P.mask_mode == VSL_MASK_CONST) {
-          m = P.mask[s][pix];
         }
-        const float w00 = __fmul_rn(f.wx0, f.wy0), w01 = __fmul_rn(f.wx0, f.wy1),
-                    w10 = __fmul_rn(f.wx1, f.wy0), w11 = __fmul_rn(f.wx1, f.wy1);
+        const float w00 = __fmul_rn(t.wx0, t.wy0), w01 = __fmul_rn(t.wx0, t.wy1),
+                    w10 = __fmul_rn(t.wx1, t.wy0), w11 = __fmul_rn(t.wx1, t.wy1);
+        const float cA[3] = {t.A.x, t.A.y, t.A.z}, cB[3] = {t.B.x, t.B.y, t.B.z},
+                    cC[3] = {t.C.x, t.C.y, t.C.z}, cD[3] = {t.D.x, t.D.y, t.D.z};
         // E = sum_c |e_c|; J_k = sum_c sign(e_c) * corner_k[c]  (the channel sum commutes with d/dx, d/dy)
-        float E = 0.f, J00 = 0.f, J01 = 0.f, J10 = 0.f, J11 = 0.f;
+        float E = 0.f, JA = 0.f, JB = 0.f, JC = 0.f, JD = 0.f;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          const float wv = EXACT ? blend(w00, w01, w10, w11, i00[c], i01[c], i10[c], i11[c])
-                                 : fmaf(w11, i11[c], fmaf(w10, i10[c], fmaf(w01, i01[c], w00 * i00[c])));
+          const float wv = EXACT ? blend(w00, w01, w10, w11, cA[c], cC[c], cB[c], cD[c])
+                                 : fmaf(w11, cD[c], fmaf(w10, cB[c], fmaf(w01, cC[c], w00 * cA[c])));
           const float e = wv - tt[c];
           E += fabsf(e);
-          const float sg = signed_by(1.f, e);
-          J00 = fmaf(sg, i00[c], J00); J01 = fmaf(sg, i01[c], J01);
-          J10 = fmaf(sg, i10[c], J10); J11 = fmaf(sg, i11[c], J11);
+          const float sg = EXACT ? signed_by(1.f, e) : sign_fast(e);
+          JA = fmaf(sg, cA[c], JA); JB = fmaf(sg, cB[c], JB);
+          JC = fmaf(sg, cC[c], JC); JD = fmaf(sg, cD[c], JD);
         }
-        const float ex0 = f.mx1 * J10 - f.mx0 * J00, ex1 = f.mx1 * J11 - f.mx0 * J01;  // d/dx per row
-        const float ey0 = f.my1 * J01 - f.my0 * J00, ey1 = f.my1 * J11 - f.my0 * J10;  // d/dy per column
-        const float dx = f.wy0 * ex0 + f.wy1 * ex1;
-        const float dy = f.wx0 * ey0 + f.wx1 * ey1;
+        // the border zeros make the sampler's corner masks implicit: an outside corner contributes 0
+        const float dx = t.wy0 * (JB - JA) + t.wy1 * (JD - JC);
+        const float dy = t.wx0 * (JC - JA) + t.wx1 * (JD - JB);
         pix_sum = fmaf(m, E, pix_sum);
         if (use_lg) {
           const float g0 = p0 * (cexp - cpix * E * p1);
-          if (staged) *reinterpret_cast<float2*>(lgp) = make_float2(g0, -g0);
-          else *reinterpret_cast<float2*>(P.g_logits[s] + pix * (2 * V) + 2 * v) = make_float2(g0, -g0);
+          lg[2 * v] = g0; lg[2 * v + 1] = -g0;
         }
-        const float k = cpix * m * rz;
-        const float du0 = dx * k, du1 = dy * k, du2 = -(qx * du0 + qy * du1);
+        const float k = cpix * m * t.rz;
+        const float du0 = dx * k, du1 = dy * k, du2 = -(t.qx * du0 + t.qy * du1);
+        const float* pp = sxf + 12 + v * 12;
         if (EXACT) {
           const float gc0 = du0 * pp[0] + du1 * pp[4] + du2 * pp[8];
           const float gc1 = du0 * pp[1] + du1 * pp[5] + du2 * pp[9];
@@ -359,62 +402,50 @@ loss_fused_kernel(const LossParams P) {
         } else {
           g_d -= du0 * pp[3] + du1 * pp[7] + du2 * pp[11];  // <du, M ray> = <du, u - t> / d and <du, u> = 0
         }
-        S1[v][0] = fmaf(du0, dgx, S1[v][0]); S1[v][1] = fmaf(du1, dgx, S1[v][1]); S1[v][2] = fmaf(du2, dgx, S1[v][2]);
+        S2[v][0] = fmaf(du0, dgy, S2[v][0]); S2[v][1] = fmaf(du1, dgy, S2[v][1]); S2[v][2] = fmaf(du2, dgy, S2[v][2]);
         S3[v][0] = fmaf(du0, d, S3[v][0]);   S3[v][1] = fmaf(du1, d, S3[v][1]);   S3[v][2] = fmaf(du2, d, S3[v][2]);
         S4[v][0] += du0;                     S4[v][1] += du1;                     S4[v][2] += du2;
       }
-      if (!EXACT) g_d = __fdividef(g_d, d);
-      P.g_x[s][pix] = g_d * dd_dx + g_q * dq_dx;
+    }
+    if (!EXACT) g_d *= rcp_fast(d);
+    gx_img[pofs] = g_d * dd_dx + g_q * dq_dx;
+    if (use_lg) {
+      if (lg4) {
+#pragma unroll
+        for (int k = 0; k < V / 2; ++k)
+          reinterpret_cast<float4*>(glg_img + (size_t)pofs * (2 * V))[k] =
+              make_float4(lg[4 * k], lg[4 * k + 1], lg[4 * k + 2], lg[4 * k + 3]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < V; ++k)
+          reinterpret_cast<float2*>(glg_img + (size_t)pofs * (2 * V))[k] = make_float2(lg[2 * k], lg[2 * k + 1]);
+      }
     }
   }
 
-  // ---- 5. d/dlogits leaves the tile with 16-byte stores (each warp wrote its own row: no block barrier)
-  if (staged && use_lg && y < H) {
-    __syncwarp();
-    float* __restrict__ gl = P.g_logits[s] + (img_off + (size_t)y * W + x_base) * (2 * V);
-    const float* sl = s_lg + warp * (kTW * 2 * V);
-    for (int k = lane; k < (cols * 2 * V) >> 2; k += 32)
-      *reinterpret_cast<float4*>(gl + 4 * k) = *reinterpret_cast<const float4*>(sl + 4 * k);
-  }
-
-  // ---- 6. one block reduction per tile: 3 loss sums + per view (sum du d gx, gy sum du d, sum du d, sum du)
+  // ---- 4. one warp reduction per tile: 3 loss sums + per view (gx sum du d, sum du d gy, sum du d, sum du)
   float vals[N];
   vals[0] = pix_sum * cpix; vals[1] = sm_sum; vals[2] = exp_sum * cexp;
 #pragma unroll
   for (int v = 0; v < V; ++v)
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-      vals[3 + v * 12 + i] = S1[v][i];
-      vals[3 + v * 12 + 3 + i] = gy * S3[v][i];
+      vals[3 + v * 12 + i] = gx * S3[v][i];
+      vals[3 + v * 12 + 3 + i] = S2[v][i];
       vals[3 + v * 12 + 6 + i] = S3[v][i];
       vals[3 + v * 12 + 9 + i] = S4[v][i];
     }
-  // transposed reduction through shared memory (the tile buffers are dead by now): thread j sums the 32 lanes of
-  // one (value, warp) pair with a per-thread rotation that keeps every access bank-conflict free, then N
-  // threads add the 8 warp totals in a fixed order.  ~3x fewer instructions than shuffles for N >= 15.
-  static_assert(L::total >= N * kThreads + N * kTH, "reduction buffers must fit in the tile buffers");
-  __syncthreads();
-  float* red = sm;
-  float* wsum = sm + N * kThreads;  // [N][kTH] warp totals
+  using Z = BflySizes<N>;
+  bfly_step<N, 16>(vals, lane);
+  bfly_step<Z::h1, 8>(vals, lane);
+  bfly_step<Z::h2, 4>(vals, lane);
+  bfly_step<Z::h3, 2>(vals, lane);
+  bfly_step<Z::h4, 1>(vals, lane);
+  float* __restrict__ out = P.partials + (size_t)tile * N;
 #pragma unroll
-  for (int k = 0; k < N; ++k) red[k * kThreads + threadIdx.x] = vals[k];
-  __syncthreads();
-  for (int j = threadIdx.x; j < N * kTH; j += kThreads) {
-    const float4* src = reinterpret_cast<const float4*>(red + j * 32);   // row (value j >> 3, warp j & 7)
-    float a = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float4 q = src[(i + j) & 7];   // rotation: the 8 threads of a quarter-warp hit 8 different banks
-      a += (q.x + q.y) + (q.z + q.w);
-    }
-    wsum[j] = a;
-  }
-  __syncthreads();
-  if (threadIdx.x < N) {
-    float t = 0.f;
-#pragma unroll
-    for (int w = 0; w < kTH; ++w) t += wsum[threadIdx.x * kTH + w];
-    P.partials[(size_t)tile * N + threadIdx.x] = t;
+  for (int j = 0; j < Z::h5; ++j) {
+    const int idx = bfly_index<N>(lane, j);
+    if (idx >= 0) out[idx] = vals[j];
   }
 }
 
@@ -461,7 +492,7 @@ loss_finalize_kernel(const LossParams P, const float* __restrict__ poses, const 
     acc[r] = 0.0;
     if (e < P.S * V * 12) {
       const int k = e % 12, v = (e / 12) % V, s = e / (12 * V);
-      const int per_b = P.bands[s] * P.tiles_x[s];
+      const int per_b = P.bands[s] * P.strips[s];
       const float* p = P.partials + (size_t)(P.item_begin[s] + b * per_b) * N + 3 + v * 12 + k;
       for (int i = lane; i < per_b; i += 32) acc[r] += (double)p[(size_t)i * N];
     }
@@ -513,6 +544,171 @@ loss_finalize_kernel(const LossParams P, const float* __restrict__ poses, const 
   }
 }
 
+// =====================================================================================================
+// Launch 1: pyramids, RGBA re-layout of the sources, transforms.
+// One THREAD owns one F x F block of level-0 pixels (F = 2^(S-1)) of one image, as in pyramid_kernel
+// (vsl_ops.cu): it streams the block row by row with 16-byte loads, keeps the running sums of every level
+// in registers (ResizeArea order, always from level-0 values => bit-exact against the oracle) and stores
+// each coarser element the moment its last row has been added.  Target: RGB levels 1..S-1.  Sources: every
+// level INCLUDING 0 as zero-bordered RGBA.  Extra threads zero the borders and fill the transform table.
+// =====================================================================================================
+struct PrepImgJob {
+  const float* tgt;
+  const float* src[VSL_MAX_VIEWS];
+  float* tgt_lvl[VSL_MAX_SCALES];                   // RGB levels, [0] unused
+  float4* src_lvl[VSL_MAX_VIEWS][VSL_MAX_SCALES];   // zero-bordered RGBA levels
+  int V, B, H, W, S;
+  int n_blocks;                                     // (V + 1) * B * (H / F) * (W / F) pyramid threads
+  int border_begin[VSL_MAX_SCALES + 1];             // prefix sums of border float4 per image over the scales
+};
+
+// RGBA level `SHIFT` of a source: same accumulation as PyrLevel, float4 stores into the bordered layout
+template <int LOG2F, int SHIFT>
+struct PadLevel {
+  static constexpr int F = 1 << LOG2F, f = 1 << SHIFT, npx = F / f, n = npx * 3;
+  float acc[n];
+  VSL_DEV void add_row(const float* a, int r, float4* __restrict__ dst_row0, int stride4) {
+    float rs[n];
+    row_sums<3, F, SHIFT>(a, rs);
+    if ((r & (f - 1)) == 0) {
+#pragma unroll
+      for (int i = 0; i < n; ++i) acc[i] = rs[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < n; ++i) acc[i] = __fadd_rn(acc[i], rs[i]);
+    }
+    if ((r & (f - 1)) == f - 1) {
+      const float scale = 1.0f / (float)(f * f);
+      float4* __restrict__ d = dst_row0 + (size_t)(r >> SHIFT) * stride4;
+#pragma unroll
+      for (int j = 0; j < npx; ++j)
+        d[j] = make_float4(__fmul_rn(acc[3 * j], scale), __fmul_rn(acc[3 * j + 1], scale),
+                           __fmul_rn(acc[3 * j + 2], scale), 0.f);
+    }
+  }
+};
+
+template <int LOG2F>
+__global__ void __launch_bounds__(128)
+loss_prep_kernel(const PrepImgJob job, const PrepJob prep) {
+  constexpr int F = 1 << LOG2F, NF = F * 3;
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int B = job.B, H = job.H, W = job.W;
+  if (gid >= job.n_blocks) {
+    // ---- border zeros of the RGBA levels, then the transform table
+    int k = gid - job.n_blocks;
+    const int per_img = job.border_begin[job.S];
+    const int n_border = job.V * B * per_img;
+    if (k < n_border) {
+      const int vb = k / per_img;
+      k -= vb * per_img;
+      int s = 0;
+      while (s + 1 < job.S && k >= job.border_begin[s + 1]) ++s;
+      k -= job.border_begin[s];
+      const int v = vb / B, b = vb - v * B;
+      const int Hs = H >> s, Ws = W >> s, st = Ws + 2 * kPad;
+      int row, col;
+      if (k < 2 * kPad * st) {             // kPad full rows on top, kPad at the bottom
+        row = k / st; col = k - row * st;
+        if (row >= kPad) row += Hs;
+      } else {                             // 2 * kPad columns beside each image row
+        k -= 2 * kPad * st;
+        row = kPad + k / (2 * kPad);
+        const int c = k % (2 * kPad);
+        col = c < kPad ? c : Ws + c;
+      }
+      job.src_lvl[v][s][((size_t)b * (Hs + 2 * kPad) + row) * st + col] = make_float4(0.f, 0.f, 0.f, 0.f);
+      return;
+    }
+    k -= n_border;
+    if (k < prep.n) prep_one(prep, k);
+    return;
+  }
+  const int nbx = W >> LOG2F, nby = H >> LOG2F;
+  const int per_img = nbx * nby;
+  const int ib = gid / per_img, rem = gid - ib * per_img;   // ib = image * B + b
+  const int by = rem / nbx, bx = rem - by * nbx;
+  const int im = ib / B, b = ib - im * B;
+  const float* __restrict__ img = im == 0 ? job.tgt : job.src[im - 1];
+  const float* __restrict__ src = img + (((size_t)b * H + (size_t)by * F) * W + (size_t)bx * F) * 3;
+  const bool vec = (NF % 4 == 0) && ((W * 3) % 4 == 0) && ((reinterpret_cast<uintptr_t>(img) & 15) == 0);
+
+  auto load_row = [&](int r, float* a) {
+    const float* __restrict__ row = src + (size_t)r * W * 3;
+    if (vec) {
+#pragma unroll
+      for (int k = 0; k < NF / 4; ++k) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(row) + k);
+        a[4 * k] = v.x; a[4 * k + 1] = v.y; a[4 * k + 2] = v.z; a[4 * k + 3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < NF; ++k) a[k] = __ldg(row + k);
+    }
+  };
+
+  if (im == 0) {
+   if constexpr (LOG2F >= 1) {
+    PyrLevel<3, LOG2F, 1> l1;
+    PyrLevel<3, LOG2F, (LOG2F >= 2 ? 2 : 1)> l2;
+    PyrLevel<3, LOG2F, (LOG2F >= 3 ? 3 : 1)> l3;
+    PyrLevel<3, LOG2F, (LOG2F >= 4 ? 4 : 1)> l4;
+    PyrLevel<3, LOG2F, (LOG2F >= 5 ? 5 : 1)> l5;
+    auto dst0 = [&](int s) -> float* {
+      const int Hs = H >> s, Ws = W >> s;
+      return job.tgt_lvl[s] + (((size_t)b * Hs + (size_t)by * (F >> s)) * Ws + (size_t)bx * (F >> s)) * 3;
+    };
+    float* d1 = dst0(1);
+    float* d2 = LOG2F >= 2 ? dst0(2) : nullptr;
+    float* d3 = LOG2F >= 3 ? dst0(3) : nullptr;
+    float* d4 = LOG2F >= 4 ? dst0(4) : nullptr;
+    float* d5 = LOG2F >= 5 ? dst0(5) : nullptr;
+#pragma unroll
+    for (int r = 0; r < F; ++r) {
+      float a[NF];
+      load_row(r, a);
+      l1.add_row(a, r, d1, W >> 1);
+      if (LOG2F >= 2) l2.add_row(a, r, d2, W >> 2);
+      if (LOG2F >= 3) l3.add_row(a, r, d3, W >> 3);
+      if (LOG2F >= 4) l4.add_row(a, r, d4, W >> 4);
+      if (LOG2F >= 5) l5.add_row(a, r, d5, W >> 5);
+    }
+   }
+    return;
+  }
+
+  const int v = im - 1;
+  PadLevel<LOG2F, (LOG2F >= 1 ? 1 : 0)> l1;
+  PadLevel<LOG2F, (LOG2F >= 2 ? 2 : 0)> l2;
+  PadLevel<LOG2F, (LOG2F >= 3 ? 3 : 0)> l3;
+  PadLevel<LOG2F, (LOG2F >= 4 ? 4 : 0)> l4;
+  PadLevel<LOG2F, (LOG2F >= 5 ? 5 : 0)> l5;
+  auto dst0 = [&](int s) -> float4* {
+    const int Hs = H >> s, Ws = W >> s;
+    return job.src_lvl[v][s] + ((size_t)b * (Hs + 2 * kPad) + (size_t)by * (F >> s) + kPad) * (Ws + 2 * kPad) +
+           (size_t)bx * (F >> s) + kPad;
+  };
+  float4* d0 = dst0(0);
+  float4* d1 = LOG2F >= 1 ? dst0(1) : nullptr;
+  float4* d2 = LOG2F >= 2 ? dst0(2) : nullptr;
+  float4* d3 = LOG2F >= 3 ? dst0(3) : nullptr;
+  float4* d4 = LOG2F >= 4 ? dst0(4) : nullptr;
+  float4* d5 = LOG2F >= 5 ? dst0(5) : nullptr;
+#pragma unroll
+  for (int r = 0; r < F; ++r) {
+    float a[NF];
+    load_row(r, a);
+    float4* __restrict__ d = d0 + (size_t)r * (W + 2 * kPad);
+#pragma unroll
+    for (int j = 0; j < F; ++j) d[j] = make_float4(a[3 * j], a[3 * j + 1], a[3 * j + 2], 0.f);
+    if (LOG2F >= 1) l1.add_row(a, r, d1, (W >> 1) + 2 * kPad);
+    if (LOG2F >= 2) l2.add_row(a, r, d2, (W >> 2) + 2 * kPad);
+    if (LOG2F >= 3) l3.add_row(a, r, d3, (W >> 3) + 2 * kPad);
+    if (LOG2F >= 4) l4.add_row(a, r, d4, (W >> 4) + 2 * kPad);
+    if (LOG2F >= 5) l5.add_row(a, r, d5, (W >> 5) + 2 * kPad);
+  }
+}
+
 }  // namespace vsl
 
 using namespace vsl;
@@ -520,10 +716,11 @@ using namespace vsl;
 namespace {
 
 struct WsLayout {
-  size_t xf, partials, pyr, total;
-  size_t level_off[VSL_MAX_SCALES];  // offset (in floats) of level s inside one image's pyramid block
-  size_t pyr_img;                    // floats per image pyramid (levels 1..S-1)
-  int n_items, item_begin[VSL_MAX_SCALES + 1], tiles_x[VSL_MAX_SCALES], bands[VSL_MAX_SCALES], R[VSL_MAX_SCALES];
+  size_t xf, partials, tgt_pyr, src_pyr, total;      // byte offsets
+  size_t tgt_off[VSL_MAX_SCALES];                    // floats, level s of the target pyramid (s >= 1)
+  size_t src_off[VSL_MAX_SCALES];                    // float4, level s inside one view's RGBA block
+  size_t src_view;                                   // float4 per view
+  int n_items, item_begin[VSL_MAX_SCALES + 1], strips[VSL_MAX_SCALES], bands[VSL_MAX_SCALES];
 };
 
 int check_desc(const VslLossDesc* d) {
@@ -532,6 +729,9 @@ int check_desc(const VslLossDesc* d) {
   VSL_REQUIRE(d->B > 0 && d->B <= 65535 / (VSL_MAX_VIEWS + 1) && d->H > 0 && d->W > 0, VSL_E_SHAPE);
   const int F = 1 << (d->S - 1);
   VSL_REQUIRE(d->H % F == 0 && d->W % F == 0 && (d->H >> (d->S - 1)) >= 3 && (d->W >> (d->S - 1)) >= 3, VSL_E_SHAPE);
+  // 32-bit pixel offsets inside one image and thread indices of the prep launch
+  VSL_REQUIRE((long long)(d->H + 4) * (d->W + 4) < (1ll << 26), VSL_E_SHAPE);
+  VSL_REQUIRE((long long)(d->V + 1) * d->B * (d->H + 4) * (d->W + 4) < (1ll << 31), VSL_E_SHAPE);
   VSL_REQUIRE(d->pose_format >= VSL_POSE_EULER && d->pose_format <= VSL_POSE_MATRIX, VSL_E_FORMAT);
   VSL_REQUIRE(d->mask_mode >= VSL_MASK_NONE && d->mask_mode <= VSL_MASK_CONST, VSL_E_FORMAT);
   return VSL_OK;
@@ -540,47 +740,62 @@ int check_desc(const VslLossDesc* d) {
 void layout(const VslLossDesc* d, WsLayout* L) {
   const int nt = 3 + 12 * d->V;
   int n = 0;
-  size_t lv = 0;
+  size_t tl = 0, sl = 0;
   for (int s = 0; s < d->S; ++s) {
     const int H = d->H >> s, W = d->W >> s;
-    int R = (W + 31) / 32;
-    R = R > kMaxR ? kMaxR : R;
-    L->R[s] = R;
-    L->tiles_x[s] = (W + 32 * R - 1) / (32 * R);
-    L->bands[s] = (H + kTH - 1) / kTH;
+    L->strips[s] = (W + 31) / 32;
+    L->bands[s] = (H + kRH - 1) / kRH;
     L->item_begin[s] = n;
-    n += d->B * L->bands[s] * L->tiles_x[s];
-    L->level_off[s] = lv;
-    if (s >= 1) lv += round_up((size_t)d->B * H * W * 3, 4);  // keep every level 16-byte aligned
+    n += d->B * L->bands[s] * L->strips[s];
+    L->tgt_off[s] = tl;
+    if (s >= 1) tl += round_up((size_t)d->B * H * W * 3, 4);  // keep every level 16-byte aligned
+    L->src_off[s] = sl;
+    sl += (size_t)d->B * (H + 2 * kPad) * (W + 2 * kPad);
   }
   L->item_begin[d->S] = n;
   L->n_items = n;
-  L->pyr_img = lv;
+  L->src_view = sl;
   L->xf = 0;
   L->partials = round_up(sizeof(Xform) * (size_t)d->S * d->V * d->B, 256);
-  L->pyr = L->partials + round_up(sizeof(float) * (size_t)n * nt, 256);
-  L->total = L->pyr + sizeof(float) * lv * (size_t)(d->V + 1);
+  L->tgt_pyr = L->partials + round_up(sizeof(float) * (size_t)n * nt, 256);
+  L->src_pyr = L->tgt_pyr + round_up(sizeof(float) * tl, 256);
+  L->total = L->src_pyr + sizeof(float4) * sl * (size_t)d->V;
 }
 
 template <int V, bool EXACT>
-int launch_fused(const WsLayout& L, const LossParams& P, cudaStream_t st) {
+int launch_fused(const LossParams& P, cudaStream_t st) {
   // > 48 KB of dynamic shared memory needs the opt-in; idempotent and cheap, so set on every call (no state)
   cudaError_t e = cudaFuncSetAttribute(loss_fused_kernel<V, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)Smem<V>::bytes);
+                                       (int)WarpSmem<V>::block_bytes);
   if (e != cudaSuccess) return (int)e;
-  loss_fused_kernel<V, EXACT><<<dim3(P.img_begin[P.S], P.B), kThreads, Smem<V>::bytes, st>>>(P);
+  const int n = P.item_begin[P.S];
+  loss_fused_kernel<V, EXACT><<<(n + kWarps - 1) / kWarps, kThreads, WarpSmem<V>::block_bytes, st>>>(P);
   return VSL_OK;
 }
 
 template <int V>
-int run_loss(const VslLossDesc* d, const WsLayout& L, LossParams& P, const float* poses, const float* K_pyr,
-             float* losses, float* g_poses, cudaStream_t st) {
+int run_loss(const VslLossDesc* d, LossParams& P, const float* poses, const float* K_pyr, float* losses,
+             float* g_poses, cudaStream_t st) {
   if (d->ev_main_begin != nullptr) cudaEventRecord((cudaEvent_t)d->ev_main_begin, st);
-  const int rc = d->exact_coords ? launch_fused<V, true>(L, P, st) : launch_fused<V, false>(L, P, st);
+  const int rc = d->exact_coords ? launch_fused<V, true>(P, st) : launch_fused<V, false>(P, st);
   if (rc != VSL_OK) return rc;
   if (d->ev_main_end != nullptr) cudaEventRecord((cudaEvent_t)d->ev_main_end, st);
   loss_finalize_kernel<V><<<d->B + 1, 1024, 0, st>>>(P, poses, K_pyr, d->pose_format, 1.0f / d->loss_scale,
                                                        losses, g_poses);
+  return launch_status();
+}
+
+int launch_prep(const PrepImgJob& job, const PrepJob& prep, cudaStream_t st) {
+  const long long threads = (long long)job.n_blocks + (long long)job.V * job.B * job.border_begin[job.S] + prep.n;
+  const unsigned grid = (unsigned)((threads + 127) / 128);
+  switch (job.S) {
+    case 1: loss_prep_kernel<0><<<grid, 128, 0, st>>>(job, prep); break;
+    case 2: loss_prep_kernel<1><<<grid, 128, 0, st>>>(job, prep); break;
+    case 3: loss_prep_kernel<2><<<grid, 128, 0, st>>>(job, prep); break;
+    case 4: loss_prep_kernel<3><<<grid, 128, 0, st>>>(job, prep); break;
+    case 5: loss_prep_kernel<4><<<grid, 128, 0, st>>>(job, prep); break;
+    default: loss_prep_kernel<5><<<grid, 128, 0, st>>>(job, prep); break;
+  }
   return launch_status();
 }
 
@@ -611,7 +826,8 @@ int vsl_loss_fwd_bwd(const VslLossDesc* d, const float* tgt, const float* const*
   layout(d, &L);
   char* base = reinterpret_cast<char*>(ws);
   Xform* xf = reinterpret_cast<Xform*>(base + L.xf);
-  float* pyr = reinterpret_cast<float*>(base + L.pyr);
+  float* tgt_pyr = reinterpret_cast<float*>(base + L.tgt_pyr);
+  float4* src_pyr = reinterpret_cast<float4*>(base + L.src_pyr);
 
   LossParams P;
   P.B = d->B; P.H = d->H; P.W = d->W; P.S = d->S; P.V = d->V;
@@ -619,12 +835,10 @@ int vsl_loss_fwd_bwd(const VslLossDesc* d, const float* tgt, const float* const*
   P.xf = xf;
   P.partials = reinterpret_cast<float*>(base + L.partials);
   for (int s = 0; s <= d->S; ++s) P.item_begin[s] = L.item_begin[s];
-  P.img_begin[0] = 0;
-  for (int s = 0; s < d->S; ++s) P.img_begin[s + 1] = P.img_begin[s] + L.bands[s] * L.tiles_x[s];
   for (int v = 0; v < d->V; ++v) VSL_REQUIRE(srcs[v], VSL_E_NULL);
   for (int s = 0; s < VSL_MAX_SCALES; ++s) {
     P.tgt[s] = nullptr; P.x[s] = nullptr; P.logits[s] = nullptr; P.mask[s] = nullptr;
-    P.g_x[s] = nullptr; P.g_logits[s] = nullptr; P.staged[s] = 0;
+    P.g_x[s] = nullptr; P.g_logits[s] = nullptr; P.lg_vec4[s] = 0; P.strips[s] = 0; P.bands[s] = 0;
     for (int v = 0; v < VSL_MAX_VIEWS; ++v) P.src[v][s] = nullptr;
   }
   for (int s = 0; s < d->S; ++s) {
@@ -637,21 +851,17 @@ int vsl_loss_fwd_bwd(const VslLossDesc* d, const float* tgt, const float* const*
       VSL_REQUIRE(aligned(logits_pyr[s], 8) && aligned(g_logits_pyr[s], 8), VSL_E_ALIGN);
       P.logits[s] = logits_pyr[s];
       P.g_logits[s] = g_logits_pyr[s];
+      P.lg_vec4[s] = (d->V % 2 == 0) && aligned(logits_pyr[s], 16) && aligned(g_logits_pyr[s], 16);
     }
     if (d->mask_mode == VSL_MASK_CONST) {
       VSL_REQUIRE(mask_pyr[s], VSL_E_NULL);
       P.mask[s] = mask_pyr[s];
     }
-    P.tgt[s] = (s == 0) ? tgt : pyr + L.level_off[s];
-    for (int v = 0; v < d->V; ++v) P.src[v][s] = (s == 0) ? srcs[v] : pyr + L.pyr_img * (size_t)(v + 1) + L.level_off[s];
-    P.tiles_x[s] = L.tiles_x[s]; P.bands[s] = L.bands[s]; P.R[s] = L.R[s];
-    P.inv_tx[s] = 1.0f / (float)L.tiles_x[s];
+    P.tgt[s] = (s == 0) ? tgt : tgt_pyr + L.tgt_off[s];
+    for (int v = 0; v < d->V; ++v) P.src[v][s] = src_pyr + L.src_view * (size_t)v + L.src_off[s];
+    P.strips[s] = L.strips[s]; P.bands[s] = L.bands[s];
     P.wstep[s] = 2.0f / (float)(W - 1);  // fp32 division, as grid_step() does on the device
     P.hstep[s] = 2.0f / (float)(H - 1);
-    // 16-byte row alignment of the streamed operands: W % 4 == 0 makes every row start (and the tile's
-    // x_base, a multiple of 32) a multiple of 4 pixels = 48 B of target / 8V*4 B of logits
-    P.staged[s] = (W % 4 == 0) && aligned(P.tgt[s], 16) &&
-                  (d->mask_mode != VSL_MASK_EXP || (aligned(P.logits[s], 16) && aligned(P.g_logits[s], 16)));
     const double npx = (double)d->B * H * W;
     const double dw = d->pixel_scale_norm ? (double)d->data_weight / (double)(1 << s) : (double)d->data_weight;
     P.cpix[s] = (float)((double)d->loss_scale * dw / (npx * 3.0));
@@ -663,27 +873,35 @@ int vsl_loss_fwd_bwd(const VslLossDesc* d, const float* tgt, const float* const*
     P.csm[s][3] = (float)(sw / ((double)d->B * (H - 2) * W));
   }
 
-  // 1. transforms and the image pyramids (target + V sources) in one launch
+  // 1. pyramids, RGBA source levels, transforms
   const PrepJob prep = make_prep(poses, K_pyr, d->B, d->S, d->V, d->pose_format, xf, nullptr);
-  if (d->S > 1) {
-    PyrJob job;
-    job.nimg = d->V + 1;
-    for (int i = 0; i <= d->V; ++i) {
-      job.img[i] = (i == 0) ? tgt : srcs[i - 1];
-      for (int s = 0; s < VSL_MAX_SCALES; ++s)
-        job.lvl[i][s] = (s >= 1 && s < d->S) ? pyr + L.pyr_img * (size_t)i + L.level_off[s] : nullptr;
+  PrepImgJob job;
+  job.tgt = tgt;
+  job.V = d->V; job.B = d->B; job.H = d->H; job.W = d->W; job.S = d->S;
+  const int F = 1 << (d->S - 1);
+  job.n_blocks = (d->V + 1) * d->B * (d->H / F) * (d->W / F);
+  job.border_begin[0] = 0;
+  for (int s = 0; s < VSL_MAX_SCALES; ++s) {
+    job.tgt_lvl[s] = (s >= 1 && s < d->S) ? tgt_pyr + L.tgt_off[s] : nullptr;
+    for (int v = 0; v < VSL_MAX_VIEWS; ++v) {
+      job.src[v] = v < d->V ? srcs[v] : nullptr;
+      job.src_lvl[v][s] = (v < d->V && s < d->S) ? src_pyr + L.src_view * (size_t)v + L.src_off[s] : nullptr;
     }
-    rc = launch_pyramid(job, prep, d->B, d->H, d->W, 3, d->S, st);
-    if (rc != VSL_OK) return rc;
-  } else {
-    prep_xforms_kernel<<<(prep.n + 63) / 64, 64, 0, st>>>(prep);
+    if (s < d->S) {
+      const int H = d->H >> s, W = d->W >> s;
+      job.border_begin[s + 1] = job.border_begin[s] + (H + 2 * kPad) * (W + 2 * kPad) - H * W;
+    } else {
+      job.border_begin[s + 1] = job.border_begin[s];
+    }
   }
+  rc = launch_prep(job, prep, st);
+  if (rc != VSL_OK) return rc;
   // 2 + 3. fused loss and finalize
   switch (d->V) {
-    case 1: return run_loss<1>(d, L, P, poses, K_pyr, losses, g_poses, st);
-    case 2: return run_loss<2>(d, L, P, poses, K_pyr, losses, g_poses, st);
-    case 3: return run_loss<3>(d, L, P, poses, K_pyr, losses, g_poses, st);
-    default: return run_loss<4>(d, L, P, poses, K_pyr, losses, g_poses, st);
+    case 1: return run_loss<1>(d, P, poses, K_pyr, losses, g_poses, st);
+    case 2: return run_loss<2>(d, P, poses, K_pyr, losses, g_poses, st);
+    case 3: return run_loss<3>(d, P, poses, K_pyr, losses, g_poses, st);
+    default: return run_loss<4>(d, P, poses, K_pyr, losses, g_poses, st);
   }
 }
 
