@@ -184,9 +184,9 @@ loss_fused_kernel(const LossParams P) {
   const float* __restrict__ xs = P.x[s] + img_off;
   {
     const bool inv_q = P.smooth_on_inverse != 0;
+    int ty = 0, tc = lane;                       // (row, column) of flat element i, advanced without division
 #pragma unroll 4
     for (int i = lane; i < kQH * kQS; i += 32) {
-      const int ty = i / kQS, tc = i - ty * kQS;
       const int gy = y_base - kHalo + ty, gx = x_base - kHalo + tc;
       float v = 0.f;
       if ((unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W) {
@@ -194,6 +194,8 @@ loss_fused_kernel(const LossParams P) {
         if (inv_q) v = __fdiv_rn(1.0f, v);
       }
       qt[i] = v;
+      tc += 32;
+      if (tc >= kQS) { tc -= kQS; ++ty; }
     }
     if (lane < 12) {
       const int row = lane >> 2, col = lane & 3;
@@ -205,47 +207,59 @@ loss_fused_kernel(const LossParams P) {
   }
   __syncwarp();
 
-  const float cpix = P.cpix[s], cexp = P.cexp[s];
   float pix_sum = 0.f, exp_sum = 0.f, sm_sum = 0.f;
 
   // ---- 2. smoothness, pass 1: every element of (tile + 2 rows above + 2 columns left) evaluates the four
   // second differences it owns (it is their top-left corner) ONCE and publishes their weighted signs.
   {
     const float cxx = P.csm[s][0], cxy = P.csm[s][1], cyx = P.csm[s][2], cyy = P.csm[s][3];
+    int oy = 0, ox = lane;
 #pragma unroll 2
     for (int i = lane; i < kOH * kOW; i += 32) {
-      const int oy = i / kOW, ox = i - oy * kOW;
       const float* q = qt + oy * kQS + ox;
       const float q00 = q[0], q01 = q[1], q02 = q[2], q10 = q[kQS], q11 = q[kQS + 1], q20 = q[2 * kQS];
-      const int gx = x_base - kHalo + ox, gy = y_base - kHalo + oy;
+      const unsigned gx = (unsigned)(x_base - kHalo + ox), gy = (unsigned)(y_base - kHalo + oy);
       const float dx0 = __fsub_rn(q01, q00), dy0 = __fsub_rn(q10, q00);
       float dxx = __fsub_rn(__fsub_rn(q02, q01), dx0);
       float dyy = __fsub_rn(__fsub_rn(q20, q10), dy0);
       float dxy = __fsub_rn(__fsub_rn(q11, q10), dx0);  // d/dy of dx
       float dyx = __fsub_rn(__fsub_rn(q11, q01), dy0);  // d/dx of dy
-      // a difference exists iff its whole support lies inside the image
-      const bool xin = (unsigned)gx < (unsigned)W, yin = (unsigned)gy < (unsigned)H;
-      const bool x1in = gx >= 0 && gx + 1 < W, y1in = gy >= 0 && gy + 1 < H;
-      if (!(yin && gx >= 0 && gx + 2 < W)) dxx = 0.f;
-      if (!(xin && gy >= 0 && gy + 2 < H)) dyy = 0.f;
-      if (!(x1in && y1in)) { dxy = 0.f; dyx = 0.f; }
-      sA[i] = signed_by(cxx, dxx);
-      sB[i] = signed_by(cyy, dyy);
-      sC[i] = signed_by(cxy, dxy) + signed_by(cyx, dyx);
+      // a difference exists iff its whole support lies inside the image (unsigned compares fold the >= 0 tests;
+      // H, W >= 3 is guaranteed by check_desc)
+      if (!(gy < (unsigned)H && gx < (unsigned)(W - 2))) dxx = 0.f;
+      if (!(gx < (unsigned)W && gy < (unsigned)(H - 2))) dyy = 0.f;
+      if (!(gx < (unsigned)(W - 1) && gy < (unsigned)(H - 1))) { dxy = 0.f; dyx = 0.f; }
+      if (EXACT) {
+        sA[i] = signed_by(cxx, dxx);
+        sB[i] = signed_by(cyy, dyy);
+        sC[i] = signed_by(cxy, dxy) + signed_by(cyx, dyx);
+      } else {
+        sA[i] = cxx * sign_fast(dxx);
+        sB[i] = cyy * sign_fast(dyy);
+        sC[i] = fmaf(cxy, sign_fast(dxy), cyx * sign_fast(dyx));
+      }
       if (oy >= kHalo && ox >= kHalo)
         sm_sum += cxx * fabsf(dxx) + cyy * fabsf(dyy) + cxy * fabsf(dxy) + cyx * fabsf(dyx);
+      ox += 32;
+      if (ox >= kOW) { ox -= kOW; ++oy; }
     }
   }
   __syncwarp();
 
-  // ---- 3. the pixels: lane = column, walking down the rows of the tile
-  const float gx = grid_coord(x, W, P.wstep[s]);
+  // ---- 3. the pixels: lane = column, walking down the rows of the tile.
+  // Software pipeline: the streamed operands (target, logits, mask) of row r+1 are requested at the top of
+  // row r, and the gathers of a view are re-issued for the NEXT row (or the view two ahead) as soon as the
+  // current ones have been consumed, so every global load has about half a row of arithmetic to land.
+  // Lanes beyond the image edge (ragged last strip) compute on the last column and contribute nothing.
+  const int xl = min(x, W - 1);
+  const float gx = grid_coord(xl, W, P.wstep[s]);
   const float hstep = P.hstep[s];
   const float Wf = (float)W, Hf = (float)H;
   const int stride4 = W + 2 * kPad;
   // corner offset = (iy + kPad) * stride4 + (ix + kPad) with iy, ix still carrying the magic bias
   const int coff = (int)((unsigned)(kPad * stride4 + kPad) - kMagicBits * (unsigned)(stride4 + 1));
   const size_t src_off = (size_t)b * (H + 2 * kPad) * stride4;
+  const float cpix = act ? P.cpix[s] : 0.f, cexp = act ? P.cexp[s] : 0.f;
 
   // K^-1: the column that multiplies gx is folded per thread, the other two stay as warp-uniform values
   const float4 k0 = *reinterpret_cast<const float4*>(sxf), k1 = *reinterpret_cast<const float4*>(sxf + 4),
@@ -276,151 +290,167 @@ loss_fused_kernel(const LossParams P) {
   const bool lg4 = (V % 2 == 0) && P.lg_vec4[s] != 0;
   const int smooth_inv = P.smooth_on_inverse, depth_inv = P.depth_is_inverse;
 
-  for (int r = 0; r < rows; ++r) {
-    const int y = y_base + r;
-    const int o = o0 + r * kOW;
-    // smoothness, pass 2: gradient = the published signs of the 10 stencils this element is part of
-    const float a0 = sA[o], a1 = sA[o - 1], a2 = sA[o - 2];
-    const float b0 = sB[o], c00 = sC[o], c01 = sC[o - 1];
-    const float g_q = (a0 - 2.f * a1 + a2) + (b0 - 2.f * b1 + b2) + (c00 - c01 - c10 + c11);
-    b2 = b1; b1 = b0; c10 = c00; c11 = c01;
-    if (!act) continue;
+  struct Stream { float tt[3]; float lg[2 * V]; float mc; };               // streamed operands of one row
+  struct Geo { float d, dd_dx, dq_dx, dgy, r0, r1, r2, c0, c1, c2; };       // per-pixel geometry of one row
 
-    const int pofs = y * W + x;                  // pixel offset inside this image
-    const float qc = qt[(r + kHalo) * kQS + lane + kHalo];
-    float d, dd_dx, dq_dx;
-    if (smooth_inv) {
-      dq_dx = -qc * qc;
-      if (depth_inv) { d = qc; dd_dx = dq_dx; }
-      else { d = __ldg(xs + pofs); dd_dx = 1.f; }
-    } else {
-      dq_dx = 1.f;
-      if (depth_inv) { d = EXACT ? __fdiv_rn(1.0f, qc) : rcp_fast(qc); dd_dx = -d * d; }
-      else { d = qc; dd_dx = 1.f; }
-    }
-    float tt[3];
+  auto load_stream = [&](Stream& st, int pofs) {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) tt[c] = __ldg(tgt_img + pofs * 3 + c);
-    float lg[2 * V];
+    for (int c = 0; c < 3; ++c) st.tt[c] = __ldg(tgt_img + pofs * 3 + c);
     if (use_lg) {
       if (lg4) {
 #pragma unroll
         for (int k = 0; k < V / 2; ++k) {
           const float4 q = __ldg(reinterpret_cast<const float4*>(lg_img + (size_t)pofs * (2 * V)) + k);
-          lg[4 * k] = q.x; lg[4 * k + 1] = q.y; lg[4 * k + 2] = q.z; lg[4 * k + 3] = q.w;
+          st.lg[4 * k] = q.x; st.lg[4 * k + 1] = q.y; st.lg[4 * k + 2] = q.z; st.lg[4 * k + 3] = q.w;
         }
       } else {
 #pragma unroll
         for (int k = 0; k < V; ++k) {
           const float2 q = __ldg(reinterpret_cast<const float2*>(lg_img + (size_t)pofs * (2 * V)) + k);
-          lg[2 * k] = q.x; lg[2 * k + 1] = q.y;
+          st.lg[2 * k] = q.x; st.lg[2 * k + 1] = q.y;
         }
       }
     }
-    float mconst = 1.f;
-    if (mk_img != nullptr) mconst = __ldg(mk_img + pofs);
-
-    const float gy = grid_coord(y, H, hstep);
-    float r0, r1, r2;
-    if (EXACT) {  // pixel2cam's matmul (utils.py:114): sequential k, no contraction
-      r0 = __fadd_rn(__fadd_rn(kx0, __fmul_rn(k0.y, gy)), k0.z);
-      r1 = __fadd_rn(__fadd_rn(kx1, __fmul_rn(k1.y, gy)), k1.z);
-      r2 = __fadd_rn(__fadd_rn(kx2, __fmul_rn(k2.y, gy)), k2.z);
+    st.mc = 1.f;
+    if (mk_img != nullptr) st.mc = __ldg(mk_img + pofs);
+  };
+  auto make_geo = [&](Geo& g, int r, int pofs) {
+    const float qc = qt[(r + kHalo) * kQS + (xl - x_base) + kHalo];
+    if (smooth_inv) {
+      g.dq_dx = -qc * qc;
+      if (depth_inv) { g.d = qc; g.dd_dx = g.dq_dx; }
+      else { g.d = __ldg(xs + pofs); g.dd_dx = 1.f; }
     } else {
-      r0 = fmaf(k0.y, gy, kx0); r1 = fmaf(k1.y, gy, kx1); r2 = fmaf(k2.y, gy, kx2);
+      g.dq_dx = 1.f;
+      if (depth_inv) { g.d = EXACT ? __fdiv_rn(1.0f, qc) : rcp_fast(qc); g.dd_dx = -g.d * g.d; }
+      else { g.d = qc; g.dd_dx = 1.f; }
     }
-    const float c0 = __fmul_rn(r0, d), c1 = __fmul_rn(r1, d), c2 = __fmul_rn(r2, d);
-    const float dgy = d * gy;
-    float g_d = 0.f;
+    const float gy = grid_coord(y_base + r, H, hstep);
+    if (EXACT) {  // pixel2cam's matmul (utils.py:114): sequential k, no contraction
+      g.r0 = __fadd_rn(__fadd_rn(kx0, __fmul_rn(k0.y, gy)), k0.z);
+      g.r1 = __fadd_rn(__fadd_rn(kx1, __fmul_rn(k1.y, gy)), k1.z);
+      g.r2 = __fadd_rn(__fadd_rn(kx2, __fmul_rn(k2.y, gy)), k2.z);
+    } else {
+      g.r0 = fmaf(k0.y, gy, kx0); g.r1 = fmaf(k1.y, gy, kx1); g.r2 = fmaf(k2.y, gy, kx2);
+    }
+    g.c0 = __fmul_rn(g.r0, g.d); g.c1 = __fmul_rn(g.r1, g.d); g.c2 = __fmul_rn(g.r2, g.d);
+    g.dgy = g.d * gy;
+  };
 
-    // views two at a time: both sets of gathers are in flight before either is consumed
+  constexpr int NS = (V == 4) ? 2 : V;         // gather slots in flight
+  Tap tap[NS];
+  Stream cur, nxt;
+  Geo gc, gn;
+  int pofs = y_base * W + xl;                  // pixel offset inside this image
+  load_stream(cur, pofs);
+  make_geo(gc, 0, pofs);
 #pragma unroll
-    for (int v0 = 0; v0 < V; v0 += 2) {
-      constexpr int kPair = 2;
-      Tap tap[kPair];
+  for (int v = 0; v < NS; ++v)
+    tap_issue<EXACT>(tap[v], sxf + 12 + v * 12, gc.c0, gc.c1, gc.c2, P.src[v][s] + src_off, stride4, coff, Wf, Hf);
+
+  for (int r = 0; r < rows; ++r) {
+    const bool has_next = r + 1 < rows;
+    if (has_next) {
+      load_stream(nxt, pofs + W);
+      make_geo(gn, r + 1, pofs + W);
+    }
+    // smoothness, pass 2: gradient = the published signs of the 10 stencils this element is part of
+    const int o = o0 + r * kOW;
+    const float a0 = sA[o], a1 = sA[o - 1], a2 = sA[o - 2];
+    const float b0 = sB[o], c00 = sC[o], c01 = sC[o - 1];
+    const float g_q = (a0 - 2.f * a1 + a2) + (b0 - 2.f * b1 + b2) + (c00 - c01 - c10 + c11);
+    b2 = b1; b1 = b0; c10 = c00; c11 = c01;
+
+    float g_d = 0.f;
 #pragma unroll
-      for (int j = 0; j < kPair; ++j) {
-        const int v = v0 + j;
-        if (v < V)
-          tap_issue<EXACT>(tap[j], sxf + 12 + v * 12, c0, c1, c2, P.src[v][s] + src_off, stride4, coff, Wf, Hf);
-      }
-#pragma unroll
-      for (int j = 0; j < kPair; ++j) {
-        const int v = v0 + j;
-        if (v >= V) continue;
-        const Tap& t = tap[j];
-        // mask value m (explainability softmax or constant) and the regulariser
-        float m = mconst, p0 = 0.f, p1 = 0.f;
-        if (use_lg) {
-          const float l0 = lg[2 * v], l1 = lg[2 * v + 1];
-          if (EXACT) {
-            const float mx = fmaxf(l0, l1);
-            const float e0 = expf(l0 - mx), e1 = expf(l1 - mx), se = e0 + e1;
-            p0 = e0 / se; p1 = e1 / se;
-            exp_sum += (mx + logf(se)) - l1;
-          } else {
-            const float z = l0 - l1;
-            const float e = __expf(-fabsf(z)), se = 1.f + e, big = rcp_fast(se), small = e * big;
-            p0 = z >= 0.f ? big : small;
-            p1 = z >= 0.f ? small : big;
-            exp_sum += __logf(se) + fmaxf(z, 0.f);
-          }
-          m = p1;
-        }
-        const float w00 = __fmul_rn(t.wx0, t.wy0), w01 = __fmul_rn(t.wx0, t.wy1),
-                    w10 = __fmul_rn(t.wx1, t.wy0), w11 = __fmul_rn(t.wx1, t.wy1);
-        const float cA[3] = {t.A.x, t.A.y, t.A.z}, cB[3] = {t.B.x, t.B.y, t.B.z},
-                    cC[3] = {t.C.x, t.C.y, t.C.z}, cD[3] = {t.D.x, t.D.y, t.D.z};
-        // E = sum_c |e_c|; J_k = sum_c sign(e_c) * corner_k[c]  (the channel sum commutes with d/dx, d/dy)
-        float E = 0.f, JA = 0.f, JB = 0.f, JC = 0.f, JD = 0.f;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const float wv = EXACT ? blend(w00, w01, w10, w11, cA[c], cC[c], cB[c], cD[c])
-                                 : fmaf(w11, cD[c], fmaf(w10, cB[c], fmaf(w01, cC[c], w00 * cA[c])));
-          const float e = wv - tt[c];
-          E += fabsf(e);
-          const float sg = EXACT ? signed_by(1.f, e) : sign_fast(e);
-          JA = fmaf(sg, cA[c], JA); JB = fmaf(sg, cB[c], JB);
-          JC = fmaf(sg, cC[c], JC); JD = fmaf(sg, cD[c], JD);
-        }
-        // the border zeros make the sampler's corner masks implicit: an outside corner contributes 0
-        const float dx = t.wy0 * (JB - JA) + t.wy1 * (JD - JC);
-        const float dy = t.wx0 * (JC - JA) + t.wx1 * (JD - JB);
-        pix_sum = fmaf(m, E, pix_sum);
-        if (use_lg) {
-          const float g0 = p0 * (cexp - cpix * E * p1);
-          lg[2 * v] = g0; lg[2 * v + 1] = -g0;
-        }
-        const float k = cpix * m * t.rz;
-        const float du0 = dx * k, du1 = dy * k, du2 = -(t.qx * du0 + t.qy * du1);
-        const float* pp = sxf + 12 + v * 12;
+    for (int v = 0; v < V; ++v) {
+      Tap& t = tap[v % NS];
+      // mask value m (explainability softmax or constant) and the regulariser
+      float m = cur.mc, p0 = 0.f, p1 = 0.f;
+      if (use_lg) {
+        const float l0 = cur.lg[2 * v], l1 = cur.lg[2 * v + 1];
         if (EXACT) {
-          const float gc0 = du0 * pp[0] + du1 * pp[4] + du2 * pp[8];
-          const float gc1 = du0 * pp[1] + du1 * pp[5] + du2 * pp[9];
-          const float gc2 = du0 * pp[2] + du1 * pp[6] + du2 * pp[10];
-          g_d += gc0 * r0 + gc1 * r1 + gc2 * r2;
+          const float mx = fmaxf(l0, l1);
+          const float e0 = expf(l0 - mx), e1 = expf(l1 - mx), se = e0 + e1;
+          p0 = e0 / se; p1 = e1 / se;
+          exp_sum += (mx + logf(se)) - l1;
         } else {
-          g_d -= du0 * pp[3] + du1 * pp[7] + du2 * pp[11];  // <du, M ray> = <du, u - t> / d and <du, u> = 0
+          const float z = l0 - l1;
+          const float e = __expf(-fabsf(z)), se = 1.f + e, big = rcp_fast(se), small = e * big;
+          p0 = z >= 0.f ? big : small;
+          p1 = z >= 0.f ? small : big;
+          exp_sum += __logf(se) + fmaxf(z, 0.f);
         }
-        S2[v][0] = fmaf(du0, dgy, S2[v][0]); S2[v][1] = fmaf(du1, dgy, S2[v][1]); S2[v][2] = fmaf(du2, dgy, S2[v][2]);
-        S3[v][0] = fmaf(du0, d, S3[v][0]);   S3[v][1] = fmaf(du1, d, S3[v][1]);   S3[v][2] = fmaf(du2, d, S3[v][2]);
-        S4[v][0] += du0;                     S4[v][1] += du1;                     S4[v][2] += du2;
+        m = p1;
       }
-    }
-    if (!EXACT) g_d *= rcp_fast(d);
-    gx_img[pofs] = g_d * dd_dx + g_q * dq_dx;
-    if (use_lg) {
-      if (lg4) {
+      const float w00 = __fmul_rn(t.wx0, t.wy0), w01 = __fmul_rn(t.wx0, t.wy1),
+                  w10 = __fmul_rn(t.wx1, t.wy0), w11 = __fmul_rn(t.wx1, t.wy1);
+      const float cA[3] = {t.A.x, t.A.y, t.A.z}, cB[3] = {t.B.x, t.B.y, t.B.z},
+                  cC[3] = {t.C.x, t.C.y, t.C.z}, cD[3] = {t.D.x, t.D.y, t.D.z};
+      // E = sum_c |e_c|; J_k = sum_c sign(e_c) * corner_k[c]  (the channel sum commutes with d/dx, d/dy)
+      float E = 0.f, JA = 0.f, JB = 0.f, JC = 0.f, JD = 0.f;
 #pragma unroll
-        for (int k = 0; k < V / 2; ++k)
-          reinterpret_cast<float4*>(glg_img + (size_t)pofs * (2 * V))[k] =
-              make_float4(lg[4 * k], lg[4 * k + 1], lg[4 * k + 2], lg[4 * k + 3]);
+      for (int c = 0; c < 3; ++c) {
+        const float wv = EXACT ? blend(w00, w01, w10, w11, cA[c], cC[c], cB[c], cD[c])
+                               : fmaf(w11, cD[c], fmaf(w10, cB[c], fmaf(w01, cC[c], w00 * cA[c])));
+        const float e = wv - cur.tt[c];
+        E += fabsf(e);
+        const float sg = EXACT ? signed_by(1.f, e) : sign_fast(e);
+        JA = fmaf(sg, cA[c], JA); JB = fmaf(sg, cB[c], JB);
+        JC = fmaf(sg, cC[c], JC); JD = fmaf(sg, cD[c], JD);
+      }
+      // the border zeros make the sampler's corner masks implicit: an outside corner contributes 0
+      const float dx = t.wy0 * (JB - JA) + t.wy1 * (JD - JC);
+      const float dy = t.wx0 * (JC - JA) + t.wx1 * (JD - JB);
+      pix_sum = fmaf(m, E, pix_sum);
+      if (use_lg) {
+        const float g0 = p0 * (cexp - cpix * E * p1);
+        cur.lg[2 * v] = g0; cur.lg[2 * v + 1] = -g0;
+      }
+      const float k = cpix * m * t.rz;
+      const float du0 = dx * k, du1 = dy * k, du2 = -(t.qx * du0 + t.qy * du1);
+      const float* pp = sxf + 12 + v * 12;
+      if (EXACT) {
+        const float gc0 = du0 * pp[0] + du1 * pp[4] + du2 * pp[8];
+        const float gc1 = du0 * pp[1] + du1 * pp[5] + du2 * pp[9];
+        const float gc2 = du0 * pp[2] + du1 * pp[6] + du2 * pp[10];
+        g_d += gc0 * gc.r0 + gc1 * gc.r1 + gc2 * gc.r2;
       } else {
-#pragma unroll
-        for (int k = 0; k < V; ++k)
-          reinterpret_cast<float2*>(glg_img + (size_t)pofs * (2 * V))[k] = make_float2(lg[2 * k], lg[2 * k + 1]);
+        g_d -= du0 * pp[3] + du1 * pp[7] + du2 * pp[11];  // <du, M ray> = <du, u - t> / d and <du, u> = 0
+      }
+      S2[v][0] = fmaf(du0, gc.dgy, S2[v][0]); S2[v][1] = fmaf(du1, gc.dgy, S2[v][1]); S2[v][2] = fmaf(du2, gc.dgy, S2[v][2]);
+      S3[v][0] = fmaf(du0, gc.d, S3[v][0]);   S3[v][1] = fmaf(du1, gc.d, S3[v][1]);   S3[v][2] = fmaf(du2, gc.d, S3[v][2]);
+      S4[v][0] += du0;                        S4[v][1] += du1;                        S4[v][2] += du2;
+
+      // this slot is free: request the gathers it serves next
+      if (v + NS < V) {
+        const int vn = v + NS;
+        tap_issue<EXACT>(t, sxf + 12 + vn * 12, gc.c0, gc.c1, gc.c2, P.src[vn < V ? vn : 0][s] + src_off, stride4,
+                         coff, Wf, Hf);
+      } else if (has_next) {
+        const int vn = v + NS - V;
+        tap_issue<EXACT>(t, sxf + 12 + vn * 12, gn.c0, gn.c1, gn.c2, P.src[vn][s] + src_off, stride4, coff, Wf, Hf);
       }
     }
+    if (!EXACT) g_d *= rcp_fast(gc.d);
+    if (act) {
+      gx_img[pofs] = g_d * gc.dd_dx + g_q * gc.dq_dx;
+      if (use_lg) {
+        if (lg4) {
+#pragma unroll
+          for (int k = 0; k < V / 2; ++k)
+            reinterpret_cast<float4*>(glg_img + (size_t)pofs * (2 * V))[k] =
+                make_float4(cur.lg[4 * k], cur.lg[4 * k + 1], cur.lg[4 * k + 2], cur.lg[4 * k + 3]);
+        } else {
+#pragma unroll
+          for (int k = 0; k < V; ++k)
+            reinterpret_cast<float2*>(glg_img + (size_t)pofs * (2 * V))[k] =
+                make_float2(cur.lg[2 * k], cur.lg[2 * k + 1]);
+        }
+      }
+    }
+    cur = nxt; gc = gn;
+    pofs += W;
   }
 
   // ---- 4. one warp reduction per tile: 3 loss sums + per view (gx sum du d, sum du d gy, sum du d, sum du)
