@@ -155,7 +155,9 @@ loss_fused_kernel(const LossParams P) {
   constexpr int N = NT<V>::value;
   using L = WarpSmem<V>;
   extern __shared__ float4 smem4[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // the shuffle tells the compiler `warp` (and everything derived from it: tile, scale, sizes, base pointers) is
+  // warp-uniform, so those values live in uniform registers instead of 128-per-thread vector registers
+  const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int tile = blockIdx.x * kWarps + warp;
   if (tile >= P.item_begin[P.S]) return;   // warps are independent: no block barrier anywhere below
   float* wsm = reinterpret_cast<float*>(smem4) + warp * L::total;
@@ -383,12 +385,18 @@ loss_fused_kernel(const LossParams P) {
         }
         m = p1;
       }
+      // The padding channel of the four gathers carries zeros nobody needs.  Left to itself the register
+      // allocator hands those registers to the very next instructions after the loads are issued, and the
+      // write-after-write hazard then stalls the warp for the full memory latency.  OR-ing them into the
+      // running |e| sum (a no-op on the value) keeps them reserved until the data is consumed: 2 LOP3 per view.
+      const unsigned pad = __float_as_uint(t.A.w) | __float_as_uint(t.B.w) | __float_as_uint(t.C.w) |
+                           __float_as_uint(t.D.w);
       const float w00 = __fmul_rn(t.wx0, t.wy0), w01 = __fmul_rn(t.wx0, t.wy1),
                   w10 = __fmul_rn(t.wx1, t.wy0), w11 = __fmul_rn(t.wx1, t.wy1);
       const float cA[3] = {t.A.x, t.A.y, t.A.z}, cB[3] = {t.B.x, t.B.y, t.B.z},
                   cC[3] = {t.C.x, t.C.y, t.C.z}, cD[3] = {t.D.x, t.D.y, t.D.z};
       // E = sum_c |e_c|; J_k = sum_c sign(e_c) * corner_k[c]  (the channel sum commutes with d/dx, d/dy)
-      float E = 0.f, JA = 0.f, JB = 0.f, JC = 0.f, JD = 0.f;
+      float E = __uint_as_float(pad), JA = 0.f, JB = 0.f, JC = 0.f, JD = 0.f;
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         const float wv = EXACT ? blend(w00, w01, w10, w11, cA[c], cC[c], cB[c], cD[c])
