@@ -185,17 +185,17 @@ loss_fused_kernel(const LossParams P) {
   // ---- 1. the x tile (+halo), zero outside the image, and this image's transforms
   const float* __restrict__ xs = P.x[s] + img_off;
   {
-    const bool inv_q = P.smooth_on_inverse != 0;
+    // 4-byte cp.async with a zero source size outside the image: every element of the tile is in flight at
+    // once and no register holds it on the way
     int ty = 0, tc = lane;                       // (row, column) of flat element i, advanced without division
+    const unsigned qt_s = (unsigned)__cvta_generic_to_shared(qt);
 #pragma unroll 4
     for (int i = lane; i < kQH * kQS; i += 32) {
       const int gy = y_base - kHalo + ty, gx = x_base - kHalo + tc;
-      float v = 0.f;
-      if ((unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W) {
-        v = __ldg(xs + gy * W + gx);
-        if (inv_q) v = __fdiv_rn(1.0f, v);
-      }
-      qt[i] = v;
+      const bool in = (unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W;
+      const float* src = xs + (in ? gy * W + gx : 0);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(qt_s + 4u * i), "l"(src), "r"(in ? 4 : 0)
+                   : "memory");
       tc += 32;
       if (tc >= kQS) { tc -= kQS; ++ty; }
     }
@@ -205,6 +205,14 @@ loss_fused_kernel(const LossParams P) {
       sxf[lane] = col < 3 ? xf0->kinv[row * 3 + col] : 0.f;
 #pragma unroll
       for (int v = 0; v < V; ++v) sxf[12 + v * 12 + lane] = P.xf[((size_t)s * V + v) * P.B + b].p[lane];
+    }
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    if (P.smooth_on_inverse != 0) {   // the smoothness term lives on 1/x (train_depth_then_cam_lr.py:217)
+      for (int i = lane; i < kQH * kQS; i += 32) {
+        const float v = qt[i];
+        qt[i] = v != 0.f ? __fdiv_rn(1.0f, v) : 0.f;   // outside the image the tile stays 0
+      }
     }
   }
   __syncwarp();
@@ -316,12 +324,12 @@ loss_fused_kernel(const LossParams P) {
     st.mc = 1.f;
     if (mk_img != nullptr) st.mc = __ldg(mk_img + pofs);
   };
-  auto make_geo = [&](Geo& g, int r, int pofs) {
+  auto make_geo = [&](Geo& g, int r, float xv) {
     const float qc = qt[(r + kHalo) * kQS + (xl - x_base) + kHalo];
     if (smooth_inv) {
       g.dq_dx = -qc * qc;
       if (depth_inv) { g.d = qc; g.dd_dx = g.dq_dx; }
-      else { g.d = __ldg(xs + pofs); g.dd_dx = 1.f; }
+      else { g.d = xv; g.dd_dx = 1.f; }
     } else {
       g.dq_dx = 1.f;
       if (depth_inv) { g.d = EXACT ? __fdiv_rn(1.0f, qc) : rcp_fast(qc); g.dd_dx = -g.d * g.d; }
@@ -344,8 +352,16 @@ loss_fused_kernel(const LossParams P) {
   Stream cur, nxt;
   Geo gc, gn;
   int pofs = y_base * W + xl;                  // pixel offset inside this image
-  load_stream(cur, pofs);
-  make_geo(gc, 0, pofs);
+  // (smoothness on 1/x, warp with x): the tile holds 1/x, so x itself is streamed -- two rows ahead, because
+  // the geometry of row r+1 is built during row r
+  const bool need_x = smooth_inv && !depth_inv;
+  float xv1 = 0.f;
+  {
+    float xv0 = 0.f;
+    if (need_x) { xv0 = __ldg(xs + pofs); if (rows > 1) xv1 = __ldg(xs + pofs + W); }
+    load_stream(cur, pofs);
+    make_geo(gc, 0, xv0);
+  }
 #pragma unroll
   for (int v = 0; v < NS; ++v)
     tap_issue<EXACT>(tap[v], sxf + 12 + v * 12, gc.c0, gc.c1, gc.c2, P.src[v][s] + src_off, stride4, coff, Wf, Hf);
@@ -353,8 +369,11 @@ loss_fused_kernel(const LossParams P) {
   for (int r = 0; r < rows; ++r) {
     const bool has_next = r + 1 < rows;
     if (has_next) {
+      float xv2 = 0.f;
+      if (need_x && r + 2 < rows) xv2 = __ldg(xs + pofs + 2 * W);
       load_stream(nxt, pofs + W);
-      make_geo(gn, r + 1, pofs + W);
+      make_geo(gn, r + 1, xv1);
+      xv1 = xv2;
     }
     // smoothness, pass 2: gradient = the published signs of the 10 stencils this element is part of
     const int o = o0 + r * kOW;
