@@ -87,7 +87,8 @@ template <int V> struct WarpSmem {
   static constexpr int sA = qt + kQH * kQS;             // [kOH][kOW]  cxx * sign(dx2) per owner
   static constexpr int sB = sA + kOH * kOW;             //             cyy * sign(dy2)
   static constexpr int sC = sB + kOH * kOW;             //             cxy*sign(dxdy) + cyx*sign(dydx)
-  static constexpr int xf = (sC + kOH * kOW + 3) / 4 * 4;   // K^-1 rows padded to float4 (12), then V x P (12)
+  static constexpr int xc = sC + kOH * kOW;             // [kRH][32]  x itself where the tile holds 1/x
+  static constexpr int xf = (xc + kRH * 32 + 3) / 4 * 4;    // K^-1 rows padded to float4 (12), then V x P (12)
   static constexpr int total = (xf + 12 + 12 * V + 3) / 4 * 4;
   static constexpr size_t block_bytes = sizeof(float) * total * kWarps;
 };
@@ -165,6 +166,7 @@ loss_fused_kernel(const LossParams P) {
   float* sA = wsm + L::sA;
   float* sB = wsm + L::sB;
   float* sC = wsm + L::sC;
+  float* sxc = wsm + L::xc;
   float* sxf = wsm + L::xf;
 
   // ---- which tile
@@ -209,6 +211,9 @@ loss_fused_kernel(const LossParams P) {
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
     __syncwarp();
     if (P.smooth_on_inverse != 0) {   // the smoothness term lives on 1/x (train_depth_then_cam_lr.py:217)
+      if (!P.depth_is_inverse) {      // ... while the warp wants x itself: keep the tile's centre rows
+        for (int r = 0; r < kRH; ++r) sxc[r * 32 + lane] = qt[(r + kHalo) * kQS + lane + kHalo];
+      }
       for (int i = lane; i < kQH * kQS; i += 32) {
         const float v = qt[i];
         qt[i] = v != 0.f ? __fdiv_rn(1.0f, v) : 0.f;   // outside the image the tile stays 0
@@ -324,12 +329,12 @@ loss_fused_kernel(const LossParams P) {
     st.mc = 1.f;
     if (mk_img != nullptr) st.mc = __ldg(mk_img + pofs);
   };
-  auto make_geo = [&](Geo& g, int r, float xv) {
+  auto make_geo = [&](Geo& g, int r) {
     const float qc = qt[(r + kHalo) * kQS + (xl - x_base) + kHalo];
     if (smooth_inv) {
       g.dq_dx = -qc * qc;
       if (depth_inv) { g.d = qc; g.dd_dx = g.dq_dx; }
-      else { g.d = xv; g.dd_dx = 1.f; }
+      else { g.d = sxc[r * 32 + (xl - x_base)]; g.dd_dx = 1.f; }
     } else {
       g.dq_dx = 1.f;
       if (depth_inv) { g.d = EXACT ? __fdiv_rn(1.0f, qc) : rcp_fast(qc); g.dd_dx = -g.d * g.d; }
@@ -352,16 +357,8 @@ loss_fused_kernel(const LossParams P) {
   Stream cur, nxt;
   Geo gc, gn;
   int pofs = y_base * W + xl;                  // pixel offset inside this image
-  // (smoothness on 1/x, warp with x): the tile holds 1/x, so x itself is streamed -- two rows ahead, because
-  // the geometry of row r+1 is built during row r
-  const bool need_x = smooth_inv && !depth_inv;
-  float xv1 = 0.f;
-  {
-    float xv0 = 0.f;
-    if (need_x) { xv0 = __ldg(xs + pofs); if (rows > 1) xv1 = __ldg(xs + pofs + W); }
-    load_stream(cur, pofs);
-    make_geo(gc, 0, xv0);
-  }
+  load_stream(cur, pofs);
+  make_geo(gc, 0);
 #pragma unroll
   for (int v = 0; v < NS; ++v)
     tap_issue<EXACT>(tap[v], sxf + 12 + v * 12, gc.c0, gc.c1, gc.c2, P.src[v][s] + src_off, stride4, coff, Wf, Hf);
@@ -369,11 +366,8 @@ loss_fused_kernel(const LossParams P) {
   for (int r = 0; r < rows; ++r) {
     const bool has_next = r + 1 < rows;
     if (has_next) {
-      float xv2 = 0.f;
-      if (need_x && r + 2 < rows) xv2 = __ldg(xs + pofs + 2 * W);
       load_stream(nxt, pofs + W);
-      make_geo(gn, r + 1, xv1);
-      xv1 = xv2;
+      make_geo(gn, r + 1);
     }
     // smoothness, pass 2: gradient = the published signs of the 10 stencils this element is part of
     const int o = o0 + r * kOW;
