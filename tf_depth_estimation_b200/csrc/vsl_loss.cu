@@ -88,8 +88,7 @@ template <int V> struct WarpSmem {
   static constexpr int sB = sA + kOH * kOW;             //             cyy * sign(dy2)
   static constexpr int sC = sB + kOH * kOW;             //             cxy*sign(dxdy) + cyx*sign(dydx)
   static constexpr int xc = sC + kOH * kOW;             // [kRH][32]  x itself where the tile holds 1/x
-  static constexpr int xf = (xc + kRH * 32 + 3) / 4 * 4;    // K^-1 rows padded to float4 (12), then V x P (12)
-  static constexpr int total = (xf + 12 + 12 * V + 3) / 4 * 4;
+  static constexpr int total = (xc + kRH * 32 + 3) / 4 * 4;
   static constexpr size_t block_bytes = sizeof(float) * total * kWarps;
 };
 
@@ -99,6 +98,16 @@ VSL_DEV float signed_by(float c, float v) {  // c * sign(v), sign(0) = 0
 VSL_DEV float rcp_fast(float a) {
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+  return r;
+}
+VSL_DEV float ex2_fast(float a) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+  return r;
+}
+VSL_DEV float lg2_fast(float a) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
   return r;
 }
 // sign(e) in {-1, 0, 1} with two FMA-pipe instructions: sat(e * 2^100 + 0.5) is 0, 0.5 or 1
@@ -113,20 +122,17 @@ struct Tap {
   float qx, qy, rz;              // projected coordinates (unclamped) and 1 / (z + eps)
 };
 
-// Projection, footprint and the four 16-byte gathers of one view.  pp: the 12 floats of P in shared memory.
+// Projection, footprint and the four 16-byte gathers of one view.  p: the 12 floats of P (warp-uniform).
 template <bool EXACT>
-VSL_DEV void tap_issue(Tap& t, const float* pp, float c0, float c1, float c2, const float4* __restrict__ src,
+VSL_DEV void tap_issue(Tap& t, const float (&p)[12], float c0, float c1, float c2, const float4* __restrict__ src,
                        int stride4, int coff, float Wf, float Hf) {
-  const float4 P0 = *reinterpret_cast<const float4*>(pp), P1 = *reinterpret_cast<const float4*>(pp + 4),
-               P2 = *reinterpret_cast<const float4*>(pp + 8);
   if (EXACT) {
-    const float p[12] = {P0.x, P0.y, P0.z, P0.w, P1.x, P1.y, P1.z, P1.w, P2.x, P2.y, P2.z, P2.w};
     const Proj q = project(p, c0, c1, c2);
     t.qx = q.x; t.qy = q.y; t.rz = 1.0f / q.zp;
   } else {
-    const float u0 = fmaf(P0.x, c0, fmaf(P0.y, c1, fmaf(P0.z, c2, P0.w)));
-    const float u1 = fmaf(P1.x, c0, fmaf(P1.y, c1, fmaf(P1.z, c2, P1.w)));
-    const float u2 = fmaf(P2.x, c0, fmaf(P2.y, c1, fmaf(P2.z, c2, P2.w)));
+    const float u0 = fmaf(p[0], c0, fmaf(p[1], c1, fmaf(p[2], c2, p[3])));
+    const float u1 = fmaf(p[4], c0, fmaf(p[5], c1, fmaf(p[6], c2, p[7])));
+    const float u2 = fmaf(p[8], c0, fmaf(p[9], c1, fmaf(p[10], c2, p[11])));
     t.rz = rcp_fast(u2 + kEpsZ);
     t.qx = u0 * t.rz; t.qy = u1 * t.rz;
   }
@@ -135,15 +141,13 @@ VSL_DEV void tap_issue(Tap& t, const float* pp, float c0, float c1, float c2, co
   const float tx = __fadd_rd(xc, kMagic), ty = __fadd_rd(yc, kMagic);
   const float fx = __fsub_rn(tx, kMagic), fy = __fsub_rn(ty, kMagic);   // floor, exactly
   t.wx1 = __fsub_rn(xc, fx); t.wy1 = __fsub_rn(yc, fy);
-  if (EXACT) {
+  if (EXACT) {   // the fast path forms 1 - w at the point of use instead of carrying two more registers
     t.wx0 = __fsub_rn(__fadd_rn(fx, 1.0f), xc); t.wy0 = __fsub_rn(__fadd_rn(fy, 1.0f), yc);
-  } else {
-    t.wx0 = 1.0f - t.wx1; t.wy0 = 1.0f - t.wy1;
   }
   const int off = (int)(__float_as_uint(ty) * (unsigned)stride4 + __float_as_uint(tx) + (unsigned)coff);  // wraps to the true offset
-  const float4* __restrict__ p = src + off;
-  t.A = __ldg(p); t.B = __ldg(p + 1);
-  t.C = __ldg(p + stride4); t.D = __ldg(p + stride4 + 1);
+  const float4* __restrict__ g = src + off;
+  t.A = __ldg(g); t.B = __ldg(g + 1);
+  t.C = __ldg(g + stride4); t.D = __ldg(g + stride4 + 1);
 }
 
 // EXACT = true : coordinates, softmax and the warped value follow the reference's rounding sequence
@@ -151,7 +155,7 @@ VSL_DEV void tap_issue(Tap& t, const float* pp, float c0, float c1, float c2, co
 // EXACT = false: the same algebra with FMA contraction, MUFU reciprocal / exp / log and the closed form
 //                d(depth) = -<du, t> / depth; differs from EXACT by a few ulp per quantity.
 template <int V, bool EXACT>
-__global__ void __launch_bounds__(kThreads, VSL_FUSED_MIN_BLOCKS)
+__global__ void __launch_bounds__(kThreads, (V <= 2 ? VSL_FUSED_MIN_BLOCKS : 1))
 loss_fused_kernel(const LossParams P) {
   constexpr int N = NT<V>::value;
   using L = WarpSmem<V>;
@@ -167,7 +171,6 @@ loss_fused_kernel(const LossParams P) {
   float* sB = wsm + L::sB;
   float* sC = wsm + L::sC;
   float* sxc = wsm + L::xc;
-  float* sxf = wsm + L::xf;
 
   // ---- which tile
   int s = 0;
@@ -200,13 +203,6 @@ loss_fused_kernel(const LossParams P) {
                    : "memory");
       tc += 32;
       if (tc >= kQS) { tc -= kQS; ++ty; }
-    }
-    if (lane < 12) {
-      const int row = lane >> 2, col = lane & 3;
-      const Xform* xf0 = P.xf + ((size_t)s * V) * P.B + b;
-      sxf[lane] = col < 3 ? xf0->kinv[row * 3 + col] : 0.f;
-#pragma unroll
-      for (int v = 0; v < V; ++v) sxf[12 + v * 12 + lane] = P.xf[((size_t)s * V + v) * P.B + b].p[lane];
     }
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
     __syncwarp();
@@ -274,11 +270,26 @@ loss_fused_kernel(const LossParams P) {
   // corner offset = (iy + kPad) * stride4 + (ix + kPad) with iy, ix still carrying the magic bias
   const int coff = (int)((unsigned)(kPad * stride4 + kPad) - kMagicBits * (unsigned)(stride4 + 1));
   const size_t src_off = (size_t)b * (H + 2 * kPad) * stride4;
-  const float cpix = act ? P.cpix[s] : 0.f, cexp = act ? P.cexp[s] : 0.f;
+  const float cpix = P.cpix[s], cexp = P.cexp[s];
 
-  // K^-1: the column that multiplies gx is folded per thread, the other two stay as warp-uniform values
-  const float4 k0 = *reinterpret_cast<const float4*>(sxf), k1 = *reinterpret_cast<const float4*>(sxf + 4),
-               k2 = *reinterpret_cast<const float4*>(sxf + 8);
+  // This image's transforms.  Every lane reads the same words; the shuffle marks them warp-uniform, so K^-1 and
+  // the V projection matrices sit in uniform registers and enter the FMAs as operands -- no shared memory, no
+  // per-row reloads, no per-thread copies.
+  float kinv[9], Pm[V][12];
+  {
+    const float* xf0 = reinterpret_cast<const float*>(P.xf + ((size_t)s * V) * P.B + b);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) kinv[i] = __shfl_sync(0xffffffffu, __ldg(xf0 + i), 0);
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const float* xfv = reinterpret_cast<const float*>(P.xf + ((size_t)s * V + v) * P.B + b) + 9;
+#pragma unroll
+      for (int i = 0; i < 12; ++i) Pm[v][i] = __shfl_sync(0xffffffffu, __ldg(xfv + i), 0);
+    }
+  }
+  // K^-1: the column that multiplies gx is folded per thread
+  const float3 k0 = make_float3(kinv[0], kinv[1], kinv[2]), k1 = make_float3(kinv[3], kinv[4], kinv[5]),
+               k2 = make_float3(kinv[6], kinv[7], kinv[8]);
   float kx0, kx1, kx2;
   if (EXACT) {
     kx0 = __fmul_rn(k0.x, gx); kx1 = __fmul_rn(k1.x, gx); kx2 = __fmul_rn(k2.x, gx);
@@ -306,7 +317,7 @@ loss_fused_kernel(const LossParams P) {
   const int smooth_inv = P.smooth_on_inverse, depth_inv = P.depth_is_inverse;
 
   struct Stream { float tt[3]; float lg[2 * V]; float mc; };               // streamed operands of one row
-  struct Geo { float d, dd_dx, dq_dx, dgy, r0, r1, r2, c0, c1, c2; };       // per-pixel geometry of one row
+  struct Geo { float d, dgy, r0, r1, r2, c0, c1, c2; };                     // per-pixel geometry of one row
 
   auto load_stream = [&](Stream& st, int pofs) {
 #pragma unroll
@@ -331,15 +342,8 @@ loss_fused_kernel(const LossParams P) {
   };
   auto make_geo = [&](Geo& g, int r) {
     const float qc = qt[(r + kHalo) * kQS + (xl - x_base) + kHalo];
-    if (smooth_inv) {
-      g.dq_dx = -qc * qc;
-      if (depth_inv) { g.d = qc; g.dd_dx = g.dq_dx; }
-      else { g.d = sxc[r * 32 + (xl - x_base)]; g.dd_dx = 1.f; }
-    } else {
-      g.dq_dx = 1.f;
-      if (depth_inv) { g.d = EXACT ? __fdiv_rn(1.0f, qc) : rcp_fast(qc); g.dd_dx = -g.d * g.d; }
-      else { g.d = qc; g.dd_dx = 1.f; }
-    }
+    if (smooth_inv) g.d = depth_inv ? qc : sxc[r * 32 + (xl - x_base)];
+    else g.d = !depth_inv ? qc : (EXACT ? __fdiv_rn(1.0f, qc) : rcp_fast(qc));
     const float gy = grid_coord(y_base + r, H, hstep);
     if (EXACT) {  // pixel2cam's matmul (utils.py:114): sequential k, no contraction
       g.r0 = __fadd_rn(__fadd_rn(kx0, __fmul_rn(k0.y, gy)), k0.z);
@@ -352,60 +356,31 @@ loss_fused_kernel(const LossParams P) {
     g.dgy = g.d * gy;
   };
 
-  constexpr int NS = (V == 4) ? 2 : V;         // gather slots in flight
-  Tap tap[NS];
-  Stream cur, nxt;
-  Geo gc, gn;
-  int pofs = y_base * W + xl;                  // pixel offset inside this image
-  load_stream(cur, pofs);
-  make_geo(gc, 0);
-#pragma unroll
-  for (int v = 0; v < NS; ++v)
-    tap_issue<EXACT>(tap[v], sxf + 12 + v * 12, gc.c0, gc.c1, gc.c2, P.src[v][s] + src_off, stride4, coff, Wf, Hf);
+  // One row = two phases.  Phase 1 holds every long-latency wait and issue: blend view v from its landed
+  // gathers (reducing the 16 gathered floats to 5), re-issue that slot's gathers for the NEXT row at once, then
+  // request the next row's streamed operands.  Phase 2 (softmax, gradients, accumulation, stores: over half
+  // of the row's arithmetic) touches nothing in flight -- so whichever hardware scoreboards the compiler lets
+  // these load groups share, no wait ever lands on a load that was only just issued.
+  struct Keep { float E, u0, u1, u2; };         // what phase 2 needs of a view: sum|e| and dL/du up to the factor cpix * m
+  Tap tap[V];
+  int pofs = y_base * W + xl;                   // pixel offset inside this image
 
-  for (int r = 0; r < rows; ++r) {
+  auto row = [&](Stream& cur, Stream& nxt, Geo& gc, Geo& gn, int r) {
     const bool has_next = r + 1 < rows;
-    if (has_next) {
-      load_stream(nxt, pofs + W);
-      make_geo(gn, r + 1);
-    }
-    // smoothness, pass 2: gradient = the published signs of the 10 stencils this element is part of
-    const int o = o0 + r * kOW;
-    const float a0 = sA[o], a1 = sA[o - 1], a2 = sA[o - 2];
-    const float b0 = sB[o], c00 = sC[o], c01 = sC[o - 1];
-    const float g_q = (a0 - 2.f * a1 + a2) + (b0 - 2.f * b1 + b2) + (c00 - c01 - c10 + c11);
-    b2 = b1; b1 = b0; c10 = c00; c11 = c01;
-
-    float g_d = 0.f;
+    if (has_next) make_geo(gn, r + 1);
+    Keep keep[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) {
-      Tap& t = tap[v % NS];
-      // mask value m (explainability softmax or constant) and the regulariser
-      float m = cur.mc, p0 = 0.f, p1 = 0.f;
-      if (use_lg) {
-        const float l0 = cur.lg[2 * v], l1 = cur.lg[2 * v + 1];
-        if (EXACT) {
-          const float mx = fmaxf(l0, l1);
-          const float e0 = expf(l0 - mx), e1 = expf(l1 - mx), se = e0 + e1;
-          p0 = e0 / se; p1 = e1 / se;
-          exp_sum += (mx + logf(se)) - l1;
-        } else {
-          const float z = l0 - l1;
-          const float e = __expf(-fabsf(z)), se = 1.f + e, big = rcp_fast(se), small = e * big;
-          p0 = z >= 0.f ? big : small;
-          p1 = z >= 0.f ? small : big;
-          exp_sum += __logf(se) + fmaxf(z, 0.f);
-        }
-        m = p1;
-      }
+      Tap& t = tap[v];
       // The padding channel of the four gathers carries zeros nobody needs.  Left to itself the register
       // allocator hands those registers to the very next instructions after the loads are issued, and the
       // write-after-write hazard then stalls the warp for the full memory latency.  OR-ing them into the
       // running |e| sum (a no-op on the value) keeps them reserved until the data is consumed: 2 LOP3 per view.
       const unsigned pad = __float_as_uint(t.A.w) | __float_as_uint(t.B.w) | __float_as_uint(t.C.w) |
                            __float_as_uint(t.D.w);
-      const float w00 = __fmul_rn(t.wx0, t.wy0), w01 = __fmul_rn(t.wx0, t.wy1),
-                  w10 = __fmul_rn(t.wx1, t.wy0), w11 = __fmul_rn(t.wx1, t.wy1);
+      const float wx0 = EXACT ? t.wx0 : 1.0f - t.wx1, wy0 = EXACT ? t.wy0 : 1.0f - t.wy1;
+      const float w00 = __fmul_rn(wx0, wy0), w01 = __fmul_rn(wx0, t.wy1),
+                  w10 = __fmul_rn(t.wx1, wy0), w11 = __fmul_rn(t.wx1, t.wy1);
       const float cA[3] = {t.A.x, t.A.y, t.A.z}, cB[3] = {t.B.x, t.B.y, t.B.z},
                   cC[3] = {t.C.x, t.C.y, t.C.z}, cD[3] = {t.D.x, t.D.y, t.D.z};
       // E = sum_c |e_c|; J_k = sum_c sign(e_c) * corner_k[c]  (the channel sum commutes with d/dx, d/dy)
@@ -421,16 +396,53 @@ loss_fused_kernel(const LossParams P) {
         JC = fmaf(sg, cC[c], JC); JD = fmaf(sg, cD[c], JD);
       }
       // the border zeros make the sampler's corner masks implicit: an outside corner contributes 0
-      const float dx = t.wy0 * (JB - JA) + t.wy1 * (JD - JC);
-      const float dy = t.wx0 * (JC - JA) + t.wx1 * (JD - JB);
+      const float dx = wy0 * (JB - JA) + t.wy1 * (JD - JC);
+      const float dy = wx0 * (JC - JA) + t.wx1 * (JD - JB);
+      keep[v].E = E; keep[v].u0 = dx * t.rz; keep[v].u1 = dy * t.rz;
+      keep[v].u2 = -(t.qx * keep[v].u0 + t.qy * keep[v].u1);
+      if (has_next)
+        tap_issue<EXACT>(t, Pm[v], gn.c0, gn.c1, gn.c2, P.src[v][s] + src_off, stride4, coff, Wf, Hf);
+    }
+    if (has_next) load_stream(nxt, pofs + W);
+
+    // ---- phase 2
+    // smoothness, pass 2: gradient = the published signs of the 10 stencils this element is part of
+    const int o = o0 + r * kOW;
+    const float a0 = sA[o], a1 = sA[o - 1], a2 = sA[o - 2];
+    const float b0 = sB[o], c00 = sC[o], c01 = sC[o - 1];
+    const float g_q = (a0 - 2.f * a1 + a2) + (b0 - 2.f * b1 + b2) + (c00 - c01 - c10 + c11);
+    b2 = b1; b1 = b0; c10 = c00; c11 = c01;
+
+    float g_d = 0.f;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      // mask value m (explainability softmax or constant) and the regulariser
+      float m = cur.mc, p0 = 0.f, p1 = 0.f;
+      if (use_lg) {
+        const float l0 = cur.lg[2 * v], l1 = cur.lg[2 * v + 1];
+        if (EXACT) {
+          const float mx = fmaxf(l0, l1);
+          const float e0 = expf(l0 - mx), e1 = expf(l1 - mx), se = e0 + e1;
+          p0 = e0 / se; p1 = e1 / se;
+          exp_sum += (mx + logf(se)) - l1;
+        } else {
+          const float z = l0 - l1;
+          const float e = ex2_fast(-1.4426950408889634f * fabsf(z)), se = 1.f + e, big = rcp_fast(se), small = e * big;
+          p0 = z >= 0.f ? big : small;
+          p1 = z >= 0.f ? small : big;
+          exp_sum += fmaf(lg2_fast(se), 0.6931471805599453f, fmaxf(z, 0.f));
+        }
+        m = p1;
+      }
+      const float E = keep[v].E;
       pix_sum = fmaf(m, E, pix_sum);
       if (use_lg) {
         const float g0 = p0 * (cexp - cpix * E * p1);
         cur.lg[2 * v] = g0; cur.lg[2 * v + 1] = -g0;
       }
-      const float k = cpix * m * t.rz;
-      const float du0 = dx * k, du1 = dy * k, du2 = -(t.qx * du0 + t.qy * du1);
-      const float* pp = sxf + 12 + v * 12;
+      const float k = cpix * m;
+      const float du0 = keep[v].u0 * k, du1 = keep[v].u1 * k, du2 = keep[v].u2 * k;
+      const float* pp = Pm[v];
       if (EXACT) {
         const float gc0 = du0 * pp[0] + du1 * pp[4] + du2 * pp[8];
         const float gc1 = du0 * pp[1] + du1 * pp[5] + du2 * pp[9];
@@ -442,20 +454,19 @@ loss_fused_kernel(const LossParams P) {
       S2[v][0] = fmaf(du0, gc.dgy, S2[v][0]); S2[v][1] = fmaf(du1, gc.dgy, S2[v][1]); S2[v][2] = fmaf(du2, gc.dgy, S2[v][2]);
       S3[v][0] = fmaf(du0, gc.d, S3[v][0]);   S3[v][1] = fmaf(du1, gc.d, S3[v][1]);   S3[v][2] = fmaf(du2, gc.d, S3[v][2]);
       S4[v][0] += du0;                        S4[v][1] += du1;                        S4[v][2] += du2;
-
-      // this slot is free: request the gathers it serves next
-      if (v + NS < V) {
-        const int vn = v + NS;
-        tap_issue<EXACT>(t, sxf + 12 + vn * 12, gc.c0, gc.c1, gc.c2, P.src[vn < V ? vn : 0][s] + src_off, stride4,
-                         coff, Wf, Hf);
-      } else if (has_next) {
-        const int vn = v + NS - V;
-        tap_issue<EXACT>(t, sxf + 12 + vn * 12, gn.c0, gn.c1, gn.c2, P.src[vn][s] + src_off, stride4, coff, Wf, Hf);
-      }
     }
     if (!EXACT) g_d *= rcp_fast(gc.d);
     if (act) {
-      gx_img[pofs] = g_d * gc.dd_dx + g_q * gc.dq_dx;
+      // chain rules of depth = x or 1/x and of the smoothed quantity q = x or 1/x
+      float dd_dx = 1.f, dq_dx = 1.f;
+      if (smooth_inv) {
+        const float qc = qt[(r + kHalo) * kQS + (xl - x_base) + kHalo];
+        dq_dx = -qc * qc;
+        if (depth_inv) dd_dx = dq_dx;
+      } else if (depth_inv) {
+        dd_dx = -gc.d * gc.d;
+      }
+      gx_img[pofs] = g_d * dd_dx + g_q * dq_dx;
       if (use_lg) {
         if (lg4) {
 #pragma unroll
@@ -470,13 +481,27 @@ loss_fused_kernel(const LossParams P) {
         }
       }
     }
-    cur = nxt; gc = gn;
     pofs += W;
+  };
+
+  {
+    Stream st0, st1;                            // ping-pong: no register copies between rows
+    Geo g0, g1;
+    load_stream(st0, pofs);
+    make_geo(g0, 0);
+#pragma unroll
+    for (int v = 0; v < V; ++v)
+      tap_issue<EXACT>(tap[v], Pm[v], g0.c0, g0.c1, g0.c2, P.src[v][s] + src_off, stride4, coff, Wf, Hf);
+    for (int r = 0; r < rows; r += 2) {
+      row(st0, st1, g0, g1, r);
+      if (r + 1 < rows) row(st1, st0, g1, g0, r + 1);
+    }
   }
 
   // ---- 4. one warp reduction per tile: 3 loss sums + per view (gx sum du d, sum du d gy, sum du d, sum du)
   float vals[N];
   vals[0] = pix_sum * cpix; vals[1] = sm_sum; vals[2] = exp_sum * cexp;
+  if (!act) { vals[0] = 0.f; vals[2] = 0.f; }   // lanes past the image edge recomputed the last column
 #pragma unroll
   for (int v = 0; v < V; ++v)
 #pragma unroll
@@ -485,6 +510,7 @@ loss_fused_kernel(const LossParams P) {
       vals[3 + v * 12 + 3 + i] = S2[v][i];
       vals[3 + v * 12 + 6 + i] = S3[v][i];
       vals[3 + v * 12 + 9 + i] = S4[v][i];
+      if (!act) { vals[3 + v * 12 + i] = 0.f; vals[3 + v * 12 + 3 + i] = 0.f; vals[3 + v * 12 + 6 + i] = 0.f; vals[3 + v * 12 + 9 + i] = 0.f; }
     }
   using Z = BflySizes<N>;
   bfly_step<N, 16>(vals, lane);
