@@ -30,6 +30,7 @@
 // floor + float->int without the quarter-rate conversion pipe: t = x (+, round-down) 1.5*2^23 has
 // floor(x) in its low mantissa bits, so floor(x) = t - 1.5*2^23 and the integer is a bit-cast away.
 #include <algorithm>
+#include <type_traits>
 
 #include "vsl_common.cuh"
 // Part of the single translation unit vsl_lib.cu (prep_one / PrepJob / row_sums / PyrLevel come from vsl_ops.cu).
@@ -623,57 +624,150 @@ loss_finalize_kernel(const LossParams P, const float* __restrict__ poses, const 
 
 // =====================================================================================================
 // Launch 1: pyramids, RGBA re-layout of the sources, transforms.
-// One THREAD owns one F x F block of level-0 pixels (F = 2^(S-1)) of one image, as in pyramid_kernel
-// (vsl_ops.cu): it streams the block row by row with 16-byte loads, keeps the running sums of every level
-// in registers (ResizeArea order, always from level-0 values => bit-exact against the oracle) and stores
-// each coarser element the moment its last row has been added.  Target: RGB levels 1..S-1.  Sources: every
-// level INCLUDING 0 as zero-bordered RGBA.  Extra threads zero the borders and fill the transform table.
+// A block stages a tile of kPrepPx level-0 pixels (RB rows x TW columns, RB = max(F, 8), F = 2^(S-1)) of one
+// image in shared memory with 16-byte cp.async (rows are contiguous: every global access of the launch is a
+// full-line stream), then every thread produces output ELEMENTS from the tile:
+//   sources: level 0 as RGBA (float 4 of a pixel = 0) and every coarser level as RGBA,
+//   target : coarser levels as RGB,
+// one float per thread per step, consecutive threads -> consecutive floats, so the stores are full lines too.
+// An element of level s is summed in the order of TF's ResizeArea (ComputePatchSum): the f = 2^s level-0
+// values of a contributing row left to right, the f row sums top to bottom, times 1/f^2 -- always from
+// LEVEL-0 values, hence bit-exact against the oracle, like pyramid_kernel (vsl_ops.cu).
+// Blocks past the tiles zero the borders of the RGBA levels and fill the transform table.
 // =====================================================================================================
+constexpr int kPrepPx = 1024;       // level-0 pixels per tile
+constexpr int kPrepThreads = 256;
+
 struct PrepImgJob {
   const float* tgt;
   const float* src[VSL_MAX_VIEWS];
   float* tgt_lvl[VSL_MAX_SCALES];                   // RGB levels, [0] unused
   float4* src_lvl[VSL_MAX_VIEWS][VSL_MAX_SCALES];   // zero-bordered RGBA levels
   int V, B, H, W, S;
-  int n_blocks;                                     // (V + 1) * B * (H / F) * (W / F) pyramid threads
+  int tiles_x, tiles_y, n_tiles;                    // per image; n_tiles = (V + 1) * B * tiles_y * tiles_x
+  int n_extra_blocks;                               // border / transform blocks, FIRST in the grid
   int border_begin[VSL_MAX_SCALES + 1];             // prefix sums of border float4 per image over the scales
 };
 
-// RGBA level `SHIFT` of a source: same accumulation as PyrLevel, float4 stores into the bordered layout
-template <int LOG2F, int SHIFT>
-struct PadLevel {
-  static constexpr int F = 1 << LOG2F, f = 1 << SHIFT, npx = F / f, n = npx * 3;
-  float acc[n];
-  VSL_DEV void add_row(const float* a, int r, float4* __restrict__ dst_row0, int stride4) {
-    float rs[n];
-    row_sums<3, F, SHIFT>(a, rs);
-    if ((r & (f - 1)) == 0) {
+__host__ __device__ constexpr int ilog2(int v) { return v <= 1 ? 0 : 1 + ilog2(v >> 1); }
+
+// All elements of level SHIFT >= 3 that this tile covers: one float per (virtual) thread per step over a
+// (pixel, 4) grid whose sides are powers of two (shifts only); RGB output leaves the 4th lane of a pixel idle.
+// The caller hands this to the threads that are not busy with levels 1 and 2 (t = their index, nt = how many).
+template <int SHIFT, int TW, int RB, bool C4>
+VSL_DEV void prep_level(const float* tile, int rows, int cols, float* __restrict__ dst, int dst_row_stride, int t,
+                        int nt) {
+  constexpr int f = 1 << SHIFT, C = C4 ? 4 : 3;
+  constexpr int OW = TW >> SHIFT, OH = RB >> SHIFT;    // output pixels of a full tile
+  constexpr int LOG2OW = ilog2(OW);
+  const int ow = cols >> SHIFT, oh = rows >> SHIFT;
+  const float scale = 1.0f / (float)(f * f);
+  for (int o = t; o < OH * OW * 4; o += nt) {
+    const int c = o & 3, px = o >> 2;
+    const int oy = px >> LOG2OW, ox = px & (OW - 1);
+    if (oy >= oh || ox >= ow || (!C4 && c == 3)) continue;
+    float out = 0.f;
+    if (c < 3) {
+      const float* p = tile + (oy << SHIFT) * (TW * 3) + (ox << SHIFT) * 3 + c;
+      float acc = 0.f;
 #pragma unroll
-      for (int i = 0; i < n; ++i) acc[i] = rs[i];
+      for (int ry = 0; ry < f; ++ry) {
+        float rs = p[ry * (TW * 3)];
+#pragma unroll
+        for (int k = 1; k < f; ++k) rs = __fadd_rn(rs, p[ry * (TW * 3) + k * 3]);
+        acc = ry == 0 ? rs : __fadd_rn(acc, rs);
+      }
+      out = __fmul_rn(acc, scale);
+    }
+    dst[oy * dst_row_stride + ox * C + c] = out;
+  }
+}
+
+// Levels 1 and 2, one output PIXEL per thread with 8- / 16-byte shared-memory loads (the 2 x 3 or 4 x 3 floats of
+// a contributing row are contiguous).  Level 1 has exactly kPrepThreads pixels per full tile, level 2 a quarter.
+template <int SHIFT, int TW, int RB, bool C4>
+VSL_DEV void prep_level12(const float* tile, int rows, int cols, float* __restrict__ dst, int dst_row_stride, int t) {
+  static_assert(SHIFT == 1 || SHIFT == 2, "vector path covers levels 1 and 2");
+  constexpr int f = 1 << SHIFT, OW = TW >> SHIFT, OH = RB >> SHIFT, LOG2OW = ilog2(OW);
+  if (t >= OW * OH) return;
+  const int oy = t >> LOG2OW, ox = t & (OW - 1);
+  if (oy >= (rows >> SHIFT) || ox >= (cols >> SHIFT)) return;
+  const float* p = tile + (oy << SHIFT) * (TW * 3) + (ox << SHIFT) * 3;
+  float acc[3];
+#pragma unroll
+  for (int ry = 0; ry < f; ++ry) {
+    float a[f * 3];
+    if (SHIFT == 1) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const float2 q = reinterpret_cast<const float2*>(p + ry * (TW * 3))[k];
+        a[2 * k] = q.x; a[2 * k + 1] = q.y;
+      }
     } else {
 #pragma unroll
-      for (int i = 0; i < n; ++i) acc[i] = __fadd_rn(acc[i], rs[i]);
+      for (int k = 0; k < 3; ++k) {
+        const float4 q = reinterpret_cast<const float4*>(p + ry * (TW * 3))[k];
+        a[4 * k] = q.x; a[4 * k + 1] = q.y; a[4 * k + 2] = q.z; a[4 * k + 3] = q.w;
+      }
     }
-    if ((r & (f - 1)) == f - 1) {
-      const float scale = 1.0f / (float)(f * f);
-      float4* __restrict__ d = dst_row0 + (size_t)(r >> SHIFT) * stride4;
 #pragma unroll
-      for (int j = 0; j < npx; ++j)
-        d[j] = make_float4(__fmul_rn(acc[3 * j], scale), __fmul_rn(acc[3 * j + 1], scale),
-                           __fmul_rn(acc[3 * j + 2], scale), 0.f);
+    for (int c = 0; c < 3; ++c) {
+      float rs = a[c];
+#pragma unroll
+      for (int k = 1; k < f; ++k) rs = __fadd_rn(rs, a[k * 3 + c]);
+      acc[c] = ry == 0 ? rs : __fadd_rn(acc[c], rs);
     }
   }
-};
+  const float scale = 1.0f / (float)(f * f);
+  float* d = dst + oy * dst_row_stride + ox * (C4 ? 4 : 3);
+  if (C4) {
+    *reinterpret_cast<float4*>(d) = make_float4(__fmul_rn(acc[0], scale), __fmul_rn(acc[1], scale), __fmul_rn(acc[2], scale), 0.f);
+  } else {
+    d[0] = __fmul_rn(acc[0], scale); d[1] = __fmul_rn(acc[1], scale); d[2] = __fmul_rn(acc[2], scale);
+  }
+}
+
+// Every level of one staged tile.  Level 1: all threads.  Level 2: the first quarter.  Levels >= 3: the rest.
+template <int LOG2F, int TW, int RB, bool C4, typename DstOf>
+VSL_DEV void prep_levels(const float* tile, int rows, int cols, DstOf dst_of) {
+  const int t = threadIdx.x;
+  constexpr int n2 = (TW >> 2) * (RB >> 2);
+  if constexpr (LOG2F >= 1) { int st; float* d = dst_of(1, st); prep_level12<1, TW, RB, C4>(tile, rows, cols, d, st, t); }
+  if constexpr (LOG2F >= 2) { int st; float* d = dst_of(2, st); prep_level12<2, TW, RB, C4>(tile, rows, cols, d, st, t); }
+  if (t >= n2) {
+    if constexpr (LOG2F >= 3) { int st; float* d = dst_of(3, st); prep_level<3, TW, RB, C4>(tile, rows, cols, d, st, t - n2, kPrepThreads - n2); }
+    if constexpr (LOG2F >= 4) { int st; float* d = dst_of(4, st); prep_level<4, TW, RB, C4>(tile, rows, cols, d, st, t - n2, kPrepThreads - n2); }
+    if constexpr (LOG2F >= 5) { int st; float* d = dst_of(5, st); prep_level<5, TW, RB, C4>(tile, rows, cols, d, st, t - n2, kPrepThreads - n2); }
+  }
+}
+
+// Level 0 of a source as RGBA: one pixel per thread per step, a 16-byte store per pixel.
+template <int TW, int RB>
+VSL_DEV void prep_rgba0(const float* tile, int rows, int cols, float4* __restrict__ dst, int dst_row_stride4) {
+  constexpr int LOG2TW = TW == 32 ? 5 : TW == 64 ? 6 : 7;
+  static_assert((1 << LOG2TW) == TW, "tile width must be 32, 64 or 128");
+#pragma unroll
+  for (int j = 0; j < (TW * RB) / kPrepThreads; ++j) {
+    const int px = threadIdx.x + j * kPrepThreads;
+    const int y = px >> LOG2TW, x = px & (TW - 1);
+    if (y < rows && x < cols) {
+      const float* p = tile + y * (TW * 3) + x * 3;
+      dst[(size_t)y * dst_row_stride4 + x] = make_float4(p[0], p[1], p[2], 0.f);
+    }
+  }
+}
 
 template <int LOG2F>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kPrepThreads)
 loss_prep_kernel(const PrepImgJob job, const PrepJob prep) {
-  constexpr int F = 1 << LOG2F, NF = F * 3;
-  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  constexpr int F = 1 << LOG2F, RB = F > 8 ? F : 8, TW = kPrepPx / RB;
+  __shared__ float4 tile4[kPrepPx * 3 / 4];
+  float* tile = reinterpret_cast<float*>(tile4);
   const int B = job.B, H = job.H, W = job.W;
-  if (gid >= job.n_blocks) {
-    // ---- border zeros of the RGBA levels, then the transform table
-    int k = gid - job.n_blocks;
+  if ((int)blockIdx.x < job.n_extra_blocks) {
+    // ---- border zeros of the RGBA levels and the transform table: scheduled first, so their serial
+    // chains (sin / cos, LU inverse) run under the tiles instead of as a tail
+    int k = (int)blockIdx.x * kPrepThreads + threadIdx.x;
     const int per_img = job.border_begin[job.S];
     const int n_border = job.V * B * per_img;
     if (k < n_border) {
@@ -701,88 +795,54 @@ loss_prep_kernel(const PrepImgJob job, const PrepJob prep) {
     if (k < prep.n) prep_one(prep, k);
     return;
   }
-  const int nbx = W >> LOG2F, nby = H >> LOG2F;
-  const int per_img = nbx * nby;
-  const int ib = gid / per_img, rem = gid - ib * per_img;   // ib = image * B + b
-  const int by = rem / nbx, bx = rem - by * nbx;
+  // ---- which tile
+  const int per_img = job.tiles_x * job.tiles_y;
+  const int tile_id = (int)blockIdx.x - job.n_extra_blocks;
+  const int ib = tile_id / per_img, rem = tile_id - ib * per_img;   // ib = image * B + b
+  const int tyi = rem / job.tiles_x, txi = rem - tyi * job.tiles_x;
   const int im = ib / B, b = ib - im * B;
-  const float* __restrict__ img = im == 0 ? job.tgt : job.src[im - 1];
-  const float* __restrict__ src = img + (((size_t)b * H + (size_t)by * F) * W + (size_t)bx * F) * 3;
-  const bool vec = (NF % 4 == 0) && ((W * 3) % 4 == 0) && ((reinterpret_cast<uintptr_t>(img) & 15) == 0);
+  const int y0 = tyi * RB, x0 = txi * TW;
+  const int rows = min(RB, H - y0), cols = min(TW, W - x0);   // multiples of F
+  const float* __restrict__ img = im == 0 ? job.tgt : job.src[im > 0 ? im - 1 : 0];
+  const float* __restrict__ g0 = img + (((size_t)b * H + y0) * W + x0) * 3;
 
-  auto load_row = [&](int r, float* a) {
-    const float* __restrict__ row = src + (size_t)r * W * 3;
-    if (vec) {
-#pragma unroll
-      for (int k = 0; k < NF / 4; ++k) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(row) + k);
-        a[4 * k] = v.x; a[4 * k + 1] = v.y; a[4 * k + 2] = v.z; a[4 * k + 3] = v.w;
-      }
-    } else {
-#pragma unroll
-      for (int k = 0; k < NF; ++k) a[k] = __ldg(row + k);
+  // ---- stage: row r of the tile = cols * 3 contiguous floats
+  if ((W % 4 == 0) && (cols % 4 == 0) && ((reinterpret_cast<uintptr_t>(img) & 15) == 0)) {
+    const int q_row = cols * 3 / 4;                 // float4 per row
+    const unsigned ts = (unsigned)__cvta_generic_to_shared(tile);
+    for (int r = threadIdx.x >> 5; r < rows; r += kPrepThreads / 32)
+      for (int q = threadIdx.x & 31; q < q_row; q += 32)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ts + (unsigned)(r * TW * 3 + q * 4) * 4u),
+                     "l"(g0 + (size_t)r * W * 3 + q * 4)
+                     : "memory");
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+  } else {
+    const int n_row = cols * 3;
+    for (int i = threadIdx.x; i < rows * n_row; i += kPrepThreads) {
+      const int r = i / n_row, q = i - r * n_row;
+      tile[r * TW * 3 + q] = __ldg(g0 + (size_t)r * W * 3 + q);
     }
-  };
+  }
+  __syncthreads();
 
   if (im == 0) {
-   if constexpr (LOG2F >= 1) {
-    PyrLevel<3, LOG2F, 1> l1;
-    PyrLevel<3, LOG2F, (LOG2F >= 2 ? 2 : 1)> l2;
-    PyrLevel<3, LOG2F, (LOG2F >= 3 ? 3 : 1)> l3;
-    PyrLevel<3, LOG2F, (LOG2F >= 4 ? 4 : 1)> l4;
-    PyrLevel<3, LOG2F, (LOG2F >= 5 ? 5 : 1)> l5;
-    auto dst0 = [&](int s) -> float* {
-      const int Hs = H >> s, Ws = W >> s;
-      return job.tgt_lvl[s] + (((size_t)b * Hs + (size_t)by * (F >> s)) * Ws + (size_t)bx * (F >> s)) * 3;
+    prep_levels<LOG2F, TW, RB, false>(tile, rows, cols, [&](int sh, int& stride) {
+      const int Hs = H >> sh, Ws = W >> sh;
+      stride = Ws * 3;
+      return job.tgt_lvl[sh] + (((size_t)b * Hs + (y0 >> sh)) * Ws + (x0 >> sh)) * 3;
+    });
+  } else {
+    const int v = im - 1;
+    auto dst_of = [&](int sh, int& stride) {
+      const int Hs = H >> sh, Ws = W >> sh, st = Ws + 2 * kPad;
+      stride = st * 4;
+      return reinterpret_cast<float*>(job.src_lvl[v][sh] + ((size_t)b * (Hs + 2 * kPad) + (y0 >> sh) + kPad) * st +
+                                      (x0 >> sh) + kPad);
     };
-    float* d1 = dst0(1);
-    float* d2 = LOG2F >= 2 ? dst0(2) : nullptr;
-    float* d3 = LOG2F >= 3 ? dst0(3) : nullptr;
-    float* d4 = LOG2F >= 4 ? dst0(4) : nullptr;
-    float* d5 = LOG2F >= 5 ? dst0(5) : nullptr;
-#pragma unroll
-    for (int r = 0; r < F; ++r) {
-      float a[NF];
-      load_row(r, a);
-      l1.add_row(a, r, d1, W >> 1);
-      if (LOG2F >= 2) l2.add_row(a, r, d2, W >> 2);
-      if (LOG2F >= 3) l3.add_row(a, r, d3, W >> 3);
-      if (LOG2F >= 4) l4.add_row(a, r, d4, W >> 4);
-      if (LOG2F >= 5) l5.add_row(a, r, d5, W >> 5);
-    }
-   }
-    return;
-  }
-
-  const int v = im - 1;
-  PadLevel<LOG2F, (LOG2F >= 1 ? 1 : 0)> l1;
-  PadLevel<LOG2F, (LOG2F >= 2 ? 2 : 0)> l2;
-  PadLevel<LOG2F, (LOG2F >= 3 ? 3 : 0)> l3;
-  PadLevel<LOG2F, (LOG2F >= 4 ? 4 : 0)> l4;
-  PadLevel<LOG2F, (LOG2F >= 5 ? 5 : 0)> l5;
-  auto dst0 = [&](int s) -> float4* {
-    const int Hs = H >> s, Ws = W >> s;
-    return job.src_lvl[v][s] + ((size_t)b * (Hs + 2 * kPad) + (size_t)by * (F >> s) + kPad) * (Ws + 2 * kPad) +
-           (size_t)bx * (F >> s) + kPad;
-  };
-  float4* d0 = dst0(0);
-  float4* d1 = LOG2F >= 1 ? dst0(1) : nullptr;
-  float4* d2 = LOG2F >= 2 ? dst0(2) : nullptr;
-  float4* d3 = LOG2F >= 3 ? dst0(3) : nullptr;
-  float4* d4 = LOG2F >= 4 ? dst0(4) : nullptr;
-  float4* d5 = LOG2F >= 5 ? dst0(5) : nullptr;
-#pragma unroll
-  for (int r = 0; r < F; ++r) {
-    float a[NF];
-    load_row(r, a);
-    float4* __restrict__ d = d0 + (size_t)r * (W + 2 * kPad);
-#pragma unroll
-    for (int j = 0; j < F; ++j) d[j] = make_float4(a[3 * j], a[3 * j + 1], a[3 * j + 2], 0.f);
-    if (LOG2F >= 1) l1.add_row(a, r, d1, (W >> 1) + 2 * kPad);
-    if (LOG2F >= 2) l2.add_row(a, r, d2, (W >> 2) + 2 * kPad);
-    if (LOG2F >= 3) l3.add_row(a, r, d3, (W >> 3) + 2 * kPad);
-    if (LOG2F >= 4) l4.add_row(a, r, d4, (W >> 4) + 2 * kPad);
-    if (LOG2F >= 5) l5.add_row(a, r, d5, (W >> 5) + 2 * kPad);
+    int st0;
+    float* d0 = dst_of(0, st0);
+    prep_rgba0<TW, RB>(tile, rows, cols, reinterpret_cast<float4*>(d0), st0 / 4);
+    prep_levels<LOG2F, TW, RB, true>(tile, rows, cols, dst_of);
   }
 }
 
@@ -863,15 +923,14 @@ int run_loss(const VslLossDesc* d, LossParams& P, const float* poses, const floa
 }
 
 int launch_prep(const PrepImgJob& job, const PrepJob& prep, cudaStream_t st) {
-  const long long threads = (long long)job.n_blocks + (long long)job.V * job.B * job.border_begin[job.S] + prep.n;
-  const unsigned grid = (unsigned)((threads + 127) / 128);
+  const unsigned grid = (unsigned)(job.n_tiles + job.n_extra_blocks);
   switch (job.S) {
-    case 1: loss_prep_kernel<0><<<grid, 128, 0, st>>>(job, prep); break;
-    case 2: loss_prep_kernel<1><<<grid, 128, 0, st>>>(job, prep); break;
-    case 3: loss_prep_kernel<2><<<grid, 128, 0, st>>>(job, prep); break;
-    case 4: loss_prep_kernel<3><<<grid, 128, 0, st>>>(job, prep); break;
-    case 5: loss_prep_kernel<4><<<grid, 128, 0, st>>>(job, prep); break;
-    default: loss_prep_kernel<5><<<grid, 128, 0, st>>>(job, prep); break;
+    case 1: loss_prep_kernel<0><<<grid, kPrepThreads, 0, st>>>(job, prep); break;
+    case 2: loss_prep_kernel<1><<<grid, kPrepThreads, 0, st>>>(job, prep); break;
+    case 3: loss_prep_kernel<2><<<grid, kPrepThreads, 0, st>>>(job, prep); break;
+    case 4: loss_prep_kernel<3><<<grid, kPrepThreads, 0, st>>>(job, prep); break;
+    case 5: loss_prep_kernel<4><<<grid, kPrepThreads, 0, st>>>(job, prep); break;
+    default: loss_prep_kernel<5><<<grid, kPrepThreads, 0, st>>>(job, prep); break;
   }
   return launch_status();
 }
@@ -956,7 +1015,12 @@ int vsl_loss_fwd_bwd(const VslLossDesc* d, const float* tgt, const float* const*
   job.tgt = tgt;
   job.V = d->V; job.B = d->B; job.H = d->H; job.W = d->W; job.S = d->S;
   const int F = 1 << (d->S - 1);
-  job.n_blocks = (d->V + 1) * d->B * (d->H / F) * (d->W / F);
+  {
+    const int RB = F > 8 ? F : 8, TW = kPrepPx / RB;
+    job.tiles_x = (d->W + TW - 1) / TW;
+    job.tiles_y = (d->H + RB - 1) / RB;
+    job.n_tiles = (d->V + 1) * d->B * job.tiles_x * job.tiles_y;
+  }
   job.border_begin[0] = 0;
   for (int s = 0; s < VSL_MAX_SCALES; ++s) {
     job.tgt_lvl[s] = (s >= 1 && s < d->S) ? tgt_pyr + L.tgt_off[s] : nullptr;
@@ -971,6 +1035,7 @@ int vsl_loss_fwd_bwd(const VslLossDesc* d, const float* tgt, const float* const*
       job.border_begin[s + 1] = job.border_begin[s];
     }
   }
+  job.n_extra_blocks = (int)(((long long)job.V * job.B * job.border_begin[job.S] + prep.n + kPrepThreads - 1) / kPrepThreads);
   rc = launch_prep(job, prep, st);
   if (rc != VSL_OK) return rc;
   // 2 + 3. fused loss and finalize
