@@ -645,7 +645,7 @@ struct PrepImgJob {
   float4* src_lvl[VSL_MAX_VIEWS][VSL_MAX_SCALES];   // zero-bordered RGBA levels
   int V, B, H, W, S;
   int tiles_x, tiles_y, n_tiles;                    // per image; n_tiles = (V + 1) * B * tiles_y * tiles_x
-  int n_extra_blocks;                               // border / transform blocks, FIRST in the grid
+  int n_extra_blocks, extra_z;                      // border / transform blocks: the first extra_z grid slices
   int border_begin[VSL_MAX_SCALES + 1];             // prefix sums of border float4 per image over the scales
 };
 
@@ -764,10 +764,11 @@ loss_prep_kernel(const PrepImgJob job, const PrepJob prep) {
   __shared__ float4 tile4[kPrepPx * 3 / 4];
   float* tile = reinterpret_cast<float*>(tile4);
   const int B = job.B, H = job.H, W = job.W;
-  if ((int)blockIdx.x < job.n_extra_blocks) {
+  // grid = (tiles_x, tiles_y, extra_z + (V + 1) * B): no integer division on the way to a tile
+  if ((int)blockIdx.z < job.extra_z) {
     // ---- border zeros of the RGBA levels and the transform table: scheduled first, so their serial
     // chains (sin / cos, LU inverse) run under the tiles instead of as a tail
-    int k = (int)blockIdx.x * kPrepThreads + threadIdx.x;
+    int k = (((int)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * kPrepThreads + threadIdx.x;
     const int per_img = job.border_begin[job.S];
     const int n_border = job.V * B * per_img;
     if (k < n_border) {
@@ -796,10 +797,8 @@ loss_prep_kernel(const PrepImgJob job, const PrepJob prep) {
     return;
   }
   // ---- which tile
-  const int per_img = job.tiles_x * job.tiles_y;
-  const int tile_id = (int)blockIdx.x - job.n_extra_blocks;
-  const int ib = tile_id / per_img, rem = tile_id - ib * per_img;   // ib = image * B + b
-  const int tyi = rem / job.tiles_x, txi = rem - tyi * job.tiles_x;
+  const int tyi = blockIdx.y, txi = blockIdx.x;
+  const int ib = (int)blockIdx.z - job.extra_z;           // image * B + b
   const int im = ib / B, b = ib - im * B;
   const int y0 = tyi * RB, x0 = txi * TW;
   const int rows = min(RB, H - y0), cols = min(TW, W - x0);   // multiples of F
@@ -810,11 +809,23 @@ loss_prep_kernel(const PrepImgJob job, const PrepJob prep) {
   if ((W % 4 == 0) && (cols % 4 == 0) && ((reinterpret_cast<uintptr_t>(img) & 15) == 0)) {
     const int q_row = cols * 3 / 4;                 // float4 per row
     const unsigned ts = (unsigned)__cvta_generic_to_shared(tile);
-    for (int r = threadIdx.x >> 5; r < rows; r += kPrepThreads / 32)
-      for (int q = threadIdx.x & 31; q < q_row; q += 32)
+    if (rows == RB && cols == TW) {                 // full tile: compile-time trip counts
+      constexpr int QR = TW * 3 / 4;
+#pragma unroll
+      for (int i = 0; i < (RB * QR) / kPrepThreads; ++i) {
+        const int e = threadIdx.x + i * kPrepThreads;
+        const int r = e / QR, q = e - r * QR;
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ts + (unsigned)(r * TW * 3 + q * 4) * 4u),
                      "l"(g0 + (size_t)r * W * 3 + q * 4)
                      : "memory");
+      }
+    } else {
+      for (int r = threadIdx.x >> 5; r < rows; r += kPrepThreads / 32)
+        for (int q = threadIdx.x & 31; q < q_row; q += 32)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ts + (unsigned)(r * TW * 3 + q * 4) * 4u),
+                       "l"(g0 + (size_t)r * W * 3 + q * 4)
+                       : "memory");
+    }
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
   } else {
     const int n_row = cols * 3;
@@ -923,7 +934,7 @@ int run_loss(const VslLossDesc* d, LossParams& P, const float* poses, const floa
 }
 
 int launch_prep(const PrepImgJob& job, const PrepJob& prep, cudaStream_t st) {
-  const unsigned grid = (unsigned)(job.n_tiles + job.n_extra_blocks);
+  const dim3 grid(job.tiles_x, job.tiles_y, job.extra_z + (job.V + 1) * job.B);
   switch (job.S) {
     case 1: loss_prep_kernel<0><<<grid, kPrepThreads, 0, st>>>(job, prep); break;
     case 2: loss_prep_kernel<1><<<grid, kPrepThreads, 0, st>>>(job, prep); break;
@@ -1036,6 +1047,7 @@ int vsl_loss_fwd_bwd(const VslLossDesc* d, const float* tgt, const float* const*
     }
   }
   job.n_extra_blocks = (int)(((long long)job.V * job.B * job.border_begin[job.S] + prep.n + kPrepThreads - 1) / kPrepThreads);
+  job.extra_z = (job.n_extra_blocks + job.tiles_x * job.tiles_y - 1) / (job.tiles_x * job.tiles_y);
   rc = launch_prep(job, prep, st);
   if (rc != VSL_OK) return rc;
   // 2 + 3. fused loss and finalize
