@@ -273,6 +273,10 @@ loss_fused_kernel(const LossParams P) {
   const size_t src_off = (size_t)b * (H + 2 * kPad) * stride4;
   const float cpix = P.cpix[s], cexp = P.cexp[s];
 
+  // Everything above read only the caller's inputs.  The launch is programmatically dependent on the prep launch
+  // (it may start while that one drains): wait here, before the first read of what prep wrote.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+
   // This image's transforms.  Every lane reads the same words; the shuffle marks them warp-uniform, so K^-1 and
   // the V projection matrices sit in uniform registers and enter the FMAs as operands -- no shared memory, no
   // per-row reloads, no per-thread copies.
@@ -535,6 +539,7 @@ __global__ void __launch_bounds__(1024)
 loss_finalize_kernel(const LossParams P, const float* __restrict__ poses, const float* __restrict__ K_pyr,
                      int pose_format, float inv_loss_scale, float* __restrict__ losses, float* __restrict__ g_poses) {
   constexpr int N = NT<V>::value;
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // programmatic dependent launch: the fused launch must be done
   __shared__ double sh[32 * 3];
   __shared__ double tsum[VSL_MAX_SCALES * V * 12];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
@@ -917,7 +922,20 @@ int launch_fused(const LossParams& P, cudaStream_t st) {
                                        (int)WarpSmem<V>::block_bytes);
   if (e != cudaSuccess) return (int)e;
   const int n = P.item_begin[P.S];
-  loss_fused_kernel<V, EXACT><<<(n + kWarps - 1) / kWarps, kThreads, WarpSmem<V>::block_bytes, st>>>(P);
+  // programmatic dependent launch: blocks may be scheduled while the prep launch drains; the kernel itself
+  // waits (griddepcontrol.wait) before touching anything prep produced
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((n + kWarps - 1) / kWarps);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = WarpSmem<V>::block_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, loss_fused_kernel<V, EXACT>, P);
+  if (e != cudaSuccess) return (int)e;
   return VSL_OK;
 }
 
@@ -928,8 +946,20 @@ int run_loss(const VslLossDesc* d, LossParams& P, const float* poses, const floa
   const int rc = d->exact_coords ? launch_fused<V, true>(P, st) : launch_fused<V, false>(P, st);
   if (rc != VSL_OK) return rc;
   if (d->ev_main_end != nullptr) cudaEventRecord((cudaEvent_t)d->ev_main_end, st);
-  loss_finalize_kernel<V><<<d->B + 1, 1024, 0, st>>>(P, poses, K_pyr, d->pose_format, 1.0f / d->loss_scale,
-                                                       losses, g_poses);
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(d->B + 1);
+    cfg.blockDim = dim3(1024);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, loss_finalize_kernel<V>, P, poses, K_pyr, d->pose_format,
+                                             1.0f / d->loss_scale, losses, g_poses);
+    if (e != cudaSuccess) return (int)e;
+  }
   return launch_status();
 }
 
