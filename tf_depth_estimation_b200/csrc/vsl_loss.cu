@@ -326,24 +326,24 @@ loss_fused_kernel(const LossParams P) {
 
   auto load_stream = [&](Stream& st, int pofs) {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) st.tt[c] = __ldg(tgt_img + pofs * 3 + c);
+    for (int c = 0; c < 3; ++c) st.tt[c] = __ldcs(tgt_img + pofs * 3 + c);
     if (use_lg) {
       if (lg4) {
 #pragma unroll
         for (int k = 0; k < V / 2; ++k) {
-          const float4 q = __ldg(reinterpret_cast<const float4*>(lg_img + (size_t)pofs * (2 * V)) + k);
+          const float4 q = __ldcs(reinterpret_cast<const float4*>(lg_img + (size_t)pofs * (2 * V)) + k);
           st.lg[4 * k] = q.x; st.lg[4 * k + 1] = q.y; st.lg[4 * k + 2] = q.z; st.lg[4 * k + 3] = q.w;
         }
       } else {
 #pragma unroll
         for (int k = 0; k < V; ++k) {
-          const float2 q = __ldg(reinterpret_cast<const float2*>(lg_img + (size_t)pofs * (2 * V)) + k);
+          const float2 q = __ldcs(reinterpret_cast<const float2*>(lg_img + (size_t)pofs * (2 * V)) + k);
           st.lg[2 * k] = q.x; st.lg[2 * k + 1] = q.y;
         }
       }
     }
     st.mc = 1.f;
-    if (mk_img != nullptr) st.mc = __ldg(mk_img + pofs);
+    if (mk_img != nullptr) st.mc = __ldcs(mk_img + pofs);
   };
   auto make_geo = [&](Geo& g, int r) {
     const float qc = qt[(r + kHalo) * kQS + (xl - x_base) + kHalo];
@@ -471,18 +471,18 @@ loss_fused_kernel(const LossParams P) {
       } else if (depth_inv) {
         dd_dx = -gc.d * gc.d;
       }
-      gx_img[pofs] = g_d * dd_dx + g_q * dq_dx;
+      __stcs(gx_img + pofs, g_d * dd_dx + g_q * dq_dx);
       if (use_lg) {
         if (lg4) {
 #pragma unroll
           for (int k = 0; k < V / 2; ++k)
-            reinterpret_cast<float4*>(glg_img + (size_t)pofs * (2 * V))[k] =
-                make_float4(cur.lg[4 * k], cur.lg[4 * k + 1], cur.lg[4 * k + 2], cur.lg[4 * k + 3]);
+            __stcs(reinterpret_cast<float4*>(glg_img + (size_t)pofs * (2 * V)) + k,
+                   make_float4(cur.lg[4 * k], cur.lg[4 * k + 1], cur.lg[4 * k + 2], cur.lg[4 * k + 3]));
         } else {
 #pragma unroll
           for (int k = 0; k < V; ++k)
-            reinterpret_cast<float2*>(glg_img + (size_t)pofs * (2 * V))[k] =
-                make_float2(cur.lg[2 * k], cur.lg[2 * k + 1]);
+            __stcs(reinterpret_cast<float2*>(glg_img + (size_t)pofs * (2 * V)) + k,
+                   make_float2(cur.lg[2 * k], cur.lg[2 * k + 1]));
         }
       }
     }
@@ -814,21 +814,25 @@ loss_prep_kernel(const PrepImgJob job, const PrepJob prep) {
   if ((W % 4 == 0) && (cols % 4 == 0) && ((reinterpret_cast<uintptr_t>(img) & 15) == 0)) {
     const int q_row = cols * 3 / 4;                 // float4 per row
     const unsigned ts = (unsigned)__cvta_generic_to_shared(tile);
+    // the level-0 images are read exactly once: evict-first in L2, so that what this launch WRITES (the RGBA
+    // levels the fused launch gathers from next) is what stays resident
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
     if (rows == RB && cols == TW) {                 // full tile: compile-time trip counts
       constexpr int QR = TW * 3 / 4;
 #pragma unroll
       for (int i = 0; i < (RB * QR) / kPrepThreads; ++i) {
         const int e = threadIdx.x + i * kPrepThreads;
         const int r = e / QR, q = e - r * QR;
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ts + (unsigned)(r * TW * 3 + q * 4) * 4u),
-                     "l"(g0 + (size_t)r * W * 3 + q * 4)
+        asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(ts + (unsigned)(r * TW * 3 + q * 4) * 4u),
+                     "l"(g0 + (size_t)r * W * 3 + q * 4), "l"(pol)
                      : "memory");
       }
     } else {
       for (int r = threadIdx.x >> 5; r < rows; r += kPrepThreads / 32)
         for (int q = threadIdx.x & 31; q < q_row; q += 32)
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ts + (unsigned)(r * TW * 3 + q * 4) * 4u),
-                       "l"(g0 + (size_t)r * W * 3 + q * 4)
+          asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(ts + (unsigned)(r * TW * 3 + q * 4) * 4u),
+                       "l"(g0 + (size_t)r * W * 3 + q * 4), "l"(pol)
                        : "memory");
     }
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
