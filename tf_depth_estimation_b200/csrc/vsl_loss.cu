@@ -235,7 +235,7 @@ loss_fused_kernel(const LossParams P) {
       float dxx = __fsub_rn(__fsub_rn(q02, q01), dx0);
       float dyy = __fsub_rn(__fsub_rn(q20, q10), dy0);
       float dxy = __fsub_rn(__fsub_rn(q11, q10), dx0);  // d/dy of dx
-      float dyx = __fsub_rn(__fsub_rn(q11, q01), dy0);  // d/dx of dy
+      float dyx = EXACT ? __fsub_rn(__fsub_rn(q11, q01), dy0) : 0.f;  // d/dx of dy
       // a difference exists iff its whole support lies inside the image (unsigned compares fold the >= 0 tests;
       // H, W >= 3 is guaranteed by check_desc)
       if (!(gy < (unsigned)H && gx < (unsigned)(W - 2))) dxx = 0.f;
@@ -245,13 +245,16 @@ loss_fused_kernel(const LossParams P) {
         sA[i] = signed_by(cxx, dxx);
         sB[i] = signed_by(cyy, dyy);
         sC[i] = signed_by(cxy, dxy) + signed_by(cyx, dyx);
+        if (oy >= kHalo && ox >= kHalo)
+          sm_sum += cxx * fabsf(dxx) + cyy * fabsf(dyy) + cxy * fabsf(dxy) + cyx * fabsf(dyx);
       } else {
+        // d/dy of dx and d/dx of dy are the same number up to rounding: the fast path evaluates it once
+        const float cm = cxy + cyx;
         sA[i] = cxx * sign_fast(dxx);
         sB[i] = cyy * sign_fast(dyy);
-        sC[i] = fmaf(cxy, sign_fast(dxy), cyx * sign_fast(dyx));
+        sC[i] = cm * sign_fast(dxy);
+        if (oy >= kHalo && ox >= kHalo) sm_sum += cxx * fabsf(dxx) + cyy * fabsf(dyy) + cm * fabsf(dxy);
       }
-      if (oy >= kHalo && ox >= kHalo)
-        sm_sum += cxx * fabsf(dxx) + cyy * fabsf(dyy) + cxy * fabsf(dxy) + cyx * fabsf(dyx);
       ox += 32;
       if (ox >= kOW) { ox -= kOW; ++oy; }
     }
@@ -383,12 +386,12 @@ loss_fused_kernel(const LossParams P) {
       // running |e| sum (a no-op on the value) keeps them reserved until the data is consumed: 2 LOP3 per view.
       const unsigned pad = __float_as_uint(t.A.w) | __float_as_uint(t.B.w) | __float_as_uint(t.C.w) |
                            __float_as_uint(t.D.w);
-      const float wx0 = EXACT ? t.wx0 : 1.0f - t.wx1, wy0 = EXACT ? t.wy0 : 1.0f - t.wy1;
-      const float w00 = __fmul_rn(wx0, wy0), w01 = __fmul_rn(wx0, t.wy1),
-                  w10 = __fmul_rn(t.wx1, wy0), w11 = __fmul_rn(t.wx1, t.wy1);
       const float cA[3] = {t.A.x, t.A.y, t.A.z}, cB[3] = {t.B.x, t.B.y, t.B.z},
                   cC[3] = {t.C.x, t.C.y, t.C.z}, cD[3] = {t.D.x, t.D.y, t.D.z};
       // E = sum_c |e_c|; J_k = sum_c sign(e_c) * corner_k[c]  (the channel sum commutes with d/dx, d/dy)
+      const float wx0 = EXACT ? t.wx0 : 1.0f - t.wx1, wy0 = EXACT ? t.wy0 : 1.0f - t.wy1;
+      const float w00 = __fmul_rn(wx0, wy0), w01 = __fmul_rn(wx0, t.wy1),
+                  w10 = __fmul_rn(t.wx1, wy0), w11 = __fmul_rn(t.wx1, t.wy1);
       float E = __uint_as_float(pad), JA = 0.f, JB = 0.f, JC = 0.f, JD = 0.f;
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
@@ -400,9 +403,9 @@ loss_fused_kernel(const LossParams P) {
         JA = fmaf(sg, cA[c], JA); JB = fmaf(sg, cB[c], JB);
         JC = fmaf(sg, cC[c], JC); JD = fmaf(sg, cD[c], JD);
       }
-      // the border zeros make the sampler's corner masks implicit: an outside corner contributes 0
       const float dx = wy0 * (JB - JA) + t.wy1 * (JD - JC);
       const float dy = wx0 * (JC - JA) + t.wx1 * (JD - JB);
+      // the border zeros make the sampler's corner masks implicit: an outside corner contributes 0
       keep[v].E = E; keep[v].u0 = dx * t.rz; keep[v].u1 = dy * t.rz;
       keep[v].u2 = -(t.qx * keep[v].u0 + t.qy * keep[v].u1);
       if (has_next)
