@@ -52,9 +52,11 @@ def test_error_codes_without_a_device(lib):
 def test_loss_descriptor_validation_and_workspace(lib):
     d = _lib.VslLossDesc(32, 128, 416, 4, 2, 0, 1, 1, 1, 0, 1.0, 0.5, 0.2, 1.0)
     n = lib.vsl_loss_ws_bytes(ctypes.byref(d))
-    # pyramid levels 1..3 of (V+1) images dominate: 3 * 32*128*416*3*4 B * (1/4+1/16+1/64)
-    pyr = 3 * 32 * 128 * 416 * 3 * 4 * (1 / 4 + 1 / 16 + 1 / 64)
-    assert pyr < n < pyr * 1.1
+    # dominated by the V source views re-laid as zero-bordered RGBA at EVERY level (16 B per pixel, 2 pixels of
+    # border) plus the RGB pyramid levels 1..3 of the target
+    rgba = 2 * sum(32 * ((128 >> s) + 4) * ((416 >> s) + 4) * 16 for s in range(4))
+    tgt = 32 * 128 * 416 * 3 * 4 * (1 / 4 + 1 / 16 + 1 / 64)
+    assert rgba + tgt < n < (rgba + tgt) * 1.02
     bad = _lib.VslLossDesc(32, 100, 416, 4, 2, 0, 1, 1, 1, 0, 1.0, 0.5, 0.2, 1.0)   # 100 % 8 != 0
     assert lib.vsl_loss_ws_bytes(ctypes.byref(bad)) == 0
     bad = _lib.VslLossDesc(32, 128, 416, 4, 5, 0, 1, 1, 1, 0, 1.0, 0.5, 0.2, 1.0)   # V > VSL_MAX_VIEWS
