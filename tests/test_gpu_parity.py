@@ -355,6 +355,9 @@ def test_no_cpu_fallback():
     (2, 16, 48, 2, 4, 'matrix', 'none'),      # four views, matrix poses, no mask
     (1, 64, 96, 5, 2, 'eular', 'const'),      # five scales (F = 16), constant validity mask
     (3, 40, 44, 3, 2, 'eular', 'exp'),        # W = 44: ragged tiles, odd coarse widths (11)
+    (2, 48, 64, 1, 2, 'eular', 'exp'),        # a single scale: no pyramid, the prep launch only re-lays the sources
+    (1, 192, 256, 4, 1, 'angleaxis', 'none'), # BASELINE cfg4 frame size (DeMoN pairs), one view per direction
+    (1, 480, 640, 4, 2, 'eular', 'exp'),      # BASELINE cfg5 frame size: 15 column strips x 30 row bands at scale 0
 ])
 def test_fused_shape_sweep_against_oracle(B, H, W, S, V, fmt, mode):
     """Views 1..4, scales 2..5, widths that are not multiples of 32 / 4, every pose format and mask mode."""
