@@ -534,78 +534,109 @@ loss_fused_kernel(const LossParams P) {
   }
 }
 
-// grid = B + 1 blocks of 1024 threads.  Block b < B: pose gradients of batch element b (all views); one WARP per
-// (scale, view, component) sums that image's partial slots (lane-strided, then a fixed shuffle tree).
+// grid = B + 1 blocks of kFinThreads.  Block b < B: pose gradients of batch element b (all views).  The tile partials
+// of (image, scale) are contiguous rows of N floats: warp w adds rows w, w + 8, ... with lane = column (one
+// coalesced request per row, every request independent), the 8 warp sums are combined in warp order.
 // Block B: the three loss scalars.  Every sum runs in a fixed order in double => deterministic.
+// Launched programmatically dependent on the fused kernel: what does not depend on it (K_s^-1 from the caller's
+// intrinsics) is done before griddepcontrol.wait, under the fused kernel's tail.
+constexpr int kFinThreads = 256;
 template <int V>
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(kFinThreads)
 loss_finalize_kernel(const LossParams P, const float* __restrict__ poses, const float* __restrict__ K_pyr,
                      int pose_format, float inv_loss_scale, float* __restrict__ losses, float* __restrict__ g_poses) {
-  constexpr int N = NT<V>::value;
-  asm volatile("griddepcontrol.wait;" ::: "memory");   // programmatic dependent launch: the fused launch must be done
-  __shared__ double sh[32 * 3];
-  __shared__ double tsum[VSL_MAX_SCALES * V * 12];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  auto warp_dsum = [](double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-  };
+  constexpr int N = NT<V>::value, NW = kFinThreads / 32;
+  __shared__ double part[NW][VSL_MAX_SCALES][N];
+  __shared__ double tsum[VSL_MAX_SCALES][N];
+  __shared__ float sK[VSL_MAX_SCALES][9], sKinv[VSL_MAX_SCALES][9];
+  __shared__ double sgT[VSL_MAX_VIEWS][16];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n_items = P.item_begin[P.S];
-  if ((int)blockIdx.x == P.B) {
+  const int b = blockIdx.x;
+  if (b < P.B && (int)threadIdx.x < P.S) {   // same LU inverse as the transform table of the prep launch
+    const int sc = threadIdx.x;
+    float K[9], Ki[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) K[i] = K_pyr[((size_t)b * P.S + sc) * 9 + i];
+    inv3_lu(K, Ki);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { sK[sc][i] = K[i]; sKinv[sc][i] = Ki[i]; }
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // from here on: the fused launch's partials
+
+  if (b == P.B) {
+    // losses: columns 0..2 of every tile row, thread-strided, then a fixed tree
     double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-    for (int i = threadIdx.x; i < n_items; i += blockDim.x) {
-      const float* p = P.partials + (size_t)i * N;
-      a0 += (double)p[0]; a1 += (double)p[1]; a2 += (double)p[2];
+    constexpr int U = 8;                       // rows in flight per thread: the loads of a batch are independent
+    for (int i0 = threadIdx.x; i0 < n_items; i0 += kFinThreads * U) {
+      float q[U][3];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + u * kFinThreads;
+        const float* p = P.partials + (size_t)(i < n_items ? i : 0) * N;
+        q[u][0] = i < n_items ? p[0] : 0.f; q[u][1] = i < n_items ? p[1] : 0.f; q[u][2] = i < n_items ? p[2] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) { a0 += (double)q[u][0]; a1 += (double)q[u][1]; a2 += (double)q[u][2]; }
     }
-    a0 = warp_dsum(a0); a1 = warp_dsum(a1); a2 = warp_dsum(a2);
-    if (lane == 0) { sh[warp * 3] = a0; sh[warp * 3 + 1] = a1; sh[warp * 3 + 2] = a2; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+      a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    }
+    if (lane == 0) { part[warp][0][0] = a0; part[warp][0][1] = a1; part[warp][0][2] = a2; }
     __syncthreads();
     if (threadIdx.x < 3) {
       double t = 0.0;
-      for (int w = 0; w < nwarp; ++w) t += sh[w * 3 + threadIdx.x];
+      for (int w = 0; w < NW; ++w) t += part[w][0][threadIdx.x];
       losses[threadIdx.x] = (float)(t * (double)inv_loss_scale);
     }
     return;
   }
-  const int b = blockIdx.x;
-  // loads of every round first (independent, all in flight), shuffle trees afterwards
-  constexpr int kRounds = (VSL_MAX_SCALES * V * 12 + 31) / 32;
-  double acc[kRounds];
+
+  for (int sc = 0; sc < P.S; ++sc) {
+    const int per_b = P.bands[sc] * P.strips[sc];
+    const float* p = P.partials + (size_t)(P.item_begin[sc] + b * per_b) * N;
+    for (int c = lane; c < N; c += 32) {
+      double acc = 0.0;
+      constexpr int U = 8;                     // rows in flight per lane
+      for (int i0 = warp; i0 < per_b; i0 += NW * U) {
+        float q[U];
 #pragma unroll
-  for (int r = 0; r < kRounds; ++r) {
-    const int e = warp + r * nwarp;
-    acc[r] = 0.0;
-    if (e < P.S * V * 12) {
-      const int k = e % 12, v = (e / 12) % V, s = e / (12 * V);
-      const int per_b = P.bands[s] * P.strips[s];
-      const float* p = P.partials + (size_t)(P.item_begin[s] + b * per_b) * N + 3 + v * 12 + k;
-      for (int i = lane; i < per_b; i += 32) acc[r] += (double)p[(size_t)i * N];
+        for (int u = 0; u < U; ++u) {
+          const int i = i0 + u * NW;
+          q[u] = i < per_b ? p[(size_t)i * N + c] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) acc += (double)q[u];
+      }
+      part[warp][sc][c] = acc;
     }
   }
+  __syncthreads();
+  for (int e = threadIdx.x; e < P.S * N; e += kFinThreads) {
+    const int sc = e / N, c = e - sc * N;
+    double t = 0.0;
 #pragma unroll
-  for (int r = 0; r < kRounds; ++r) {
-    const int e = warp + r * nwarp;
-    const double a = warp_dsum(acc[r]);
-    if (lane == 0 && e < P.S * V * 12) tsum[e] = a;
+    for (int w = 0; w < NW; ++w) t += part[w][sc][c];
+    tsum[sc][c] = t;
   }
   __syncthreads();
-  // dT[v][k][j] = sum_s sum_i K_s[i][k] * dP_s[i][j]: one thread per matrix element, short chains
-  __shared__ double sgT[VSL_MAX_VIEWS][16];
+  // dT[v][k][j] = sum_s sum_i K_s[i][k] * dP_s[i][j]: one thread per matrix element
   if ((int)threadIdx.x < V * 16) {
     const int v = threadIdx.x >> 4, k = (threadIdx.x >> 2) & 3, j = threadIdx.x & 3;
     double acc = 0.0;
     if (k < 3) {
-      for (int s = 0; s < P.S; ++s) {
-        const double* t = tsum + (s * V + v) * 12;
-        const Xform& xf = P.xf[((size_t)s * V + v) * P.B + b];
-        const float* Ks = K_pyr + ((size_t)b * P.S + s) * 9;
+      for (int sc = 0; sc < P.S; ++sc) {
+        const double* t = &tsum[sc][3 + v * 12];
+        const float* ki = sKinv[sc];
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-          const double dPij = (j < 3) ? (double)xf.kinv[j * 3] * t[i] + (double)xf.kinv[j * 3 + 1] * t[3 + i] +
-                                            (double)xf.kinv[j * 3 + 2] * t[6 + i]
+          const double dPij = (j < 3) ? (double)ki[j * 3] * t[i] + (double)ki[j * 3 + 1] * t[3 + i] +
+                                            (double)ki[j * 3 + 2] * t[6 + i]
                                       : t[9 + i];
-          acc += (double)Ks[i * 3 + k] * dPij;
+          acc += (double)sK[sc][i * 3 + k] * dPij;
         }
       }
     }
@@ -772,6 +803,9 @@ loss_prep_kernel(const PrepImgJob job, const PrepJob prep) {
   __shared__ float4 tile4[kPrepPx * 3 / 4];
   float* tile = reinterpret_cast<float*>(tile4);
   const int B = job.B, H = job.H, W = job.W;
+  // launched programmatically dependent on whatever kernel precedes it in the stream (usually the previous step's
+  // finalize, or the network that produced the inputs): only the launch latency overlaps, nothing is read before
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   // grid = (tiles_x, tiles_y, extra_z + (V + 1) * B): no integer division on the way to a tile
   if ((int)blockIdx.z < job.extra_z) {
     // ---- border zeros of the RGBA levels and the transform table: scheduled first, so their serial
@@ -956,7 +990,7 @@ int run_loss(const VslLossDesc* d, LossParams& P, const float* poses, const floa
   {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(d->B + 1);
-    cfg.blockDim = dim3(1024);
+    cfg.blockDim = dim3(kFinThreads);
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -971,15 +1005,25 @@ int run_loss(const VslLossDesc* d, LossParams& P, const float* poses, const floa
 }
 
 int launch_prep(const PrepImgJob& job, const PrepJob& prep, cudaStream_t st) {
-  const dim3 grid(job.tiles_x, job.tiles_y, job.extra_z + (job.V + 1) * job.B);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(job.tiles_x, job.tiles_y, job.extra_z + (job.V + 1) * job.B);
+  cfg.blockDim = dim3(kPrepThreads);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaSuccess;
   switch (job.S) {
-    case 1: loss_prep_kernel<0><<<grid, kPrepThreads, 0, st>>>(job, prep); break;
-    case 2: loss_prep_kernel<1><<<grid, kPrepThreads, 0, st>>>(job, prep); break;
-    case 3: loss_prep_kernel<2><<<grid, kPrepThreads, 0, st>>>(job, prep); break;
-    case 4: loss_prep_kernel<3><<<grid, kPrepThreads, 0, st>>>(job, prep); break;
-    case 5: loss_prep_kernel<4><<<grid, kPrepThreads, 0, st>>>(job, prep); break;
-    default: loss_prep_kernel<5><<<grid, kPrepThreads, 0, st>>>(job, prep); break;
+    case 1: e = cudaLaunchKernelEx(&cfg, loss_prep_kernel<0>, job, prep); break;
+    case 2: e = cudaLaunchKernelEx(&cfg, loss_prep_kernel<1>, job, prep); break;
+    case 3: e = cudaLaunchKernelEx(&cfg, loss_prep_kernel<2>, job, prep); break;
+    case 4: e = cudaLaunchKernelEx(&cfg, loss_prep_kernel<3>, job, prep); break;
+    case 5: e = cudaLaunchKernelEx(&cfg, loss_prep_kernel<4>, job, prep); break;
+    default: e = cudaLaunchKernelEx(&cfg, loss_prep_kernel<5>, job, prep); break;
   }
+  if (e != cudaSuccess) return (int)e;
   return launch_status();
 }
 
