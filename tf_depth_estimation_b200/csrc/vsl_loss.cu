@@ -684,7 +684,7 @@ struct PrepImgJob {
   float4* src_lvl[VSL_MAX_VIEWS][VSL_MAX_SCALES];   // zero-bordered RGBA levels
   int V, B, H, W, S;
   int tiles_x, tiles_y, n_tiles;                    // per image; n_tiles = (V + 1) * B * tiles_y * tiles_x
-  int n_extra_blocks, extra_z;                      // border / transform blocks: the first extra_z grid slices
+  int n_blocks;                                     // persistent blocks of the launch
   int border_begin[VSL_MAX_SCALES + 1];             // prefix sums of border float4 per image over the scales
 };
 
@@ -796,24 +796,34 @@ VSL_DEV void prep_rgba0(const float* tile, int rows, int cols, float4* __restric
   }
 }
 
+// q = n / d for 0 <= n < 2^31, d >= 1 without the generic 20-instruction sequence: float estimate + one correction
+VSL_DEV int fast_div(int n, int d, float inv_d) {
+  int q = __float2int_rz(((float)n + 0.5f) * inv_d);
+  const int r = n - q * d;
+  q += (r >= d) - (r < 0);
+  return q;
+}
+
+// Persistent blocks, two tile buffers: the cp.async of tile i+1 is in flight while tile i is turned into its
+// output levels, so a block never sits idle waiting for its load.
 template <int LOG2F>
-__global__ void __launch_bounds__(kPrepThreads)
+__global__ void __launch_bounds__(kPrepThreads, 4)
 loss_prep_kernel(const PrepImgJob job, const PrepJob prep) {
   constexpr int F = 1 << LOG2F, RB = F > 8 ? F : 8, TW = kPrepPx / RB;
-  __shared__ float4 tile4[kPrepPx * 3 / 4];
-  float* tile = reinterpret_cast<float*>(tile4);
+  __shared__ float4 tile4[2][kPrepPx * 3 / 4];
   const int B = job.B, H = job.H, W = job.W;
   // launched programmatically dependent on whatever kernel precedes it in the stream (usually the previous step's
   // finalize, or the network that produced the inputs): only the launch latency overlaps, nothing is read before
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  // grid = (tiles_x, tiles_y, extra_z + (V + 1) * B): no integer division on the way to a tile
-  if ((int)blockIdx.z < job.extra_z) {
-    // ---- border zeros of the RGBA levels and the transform table: scheduled first, so their serial
-    // chains (sin / cos, LU inverse) run under the tiles instead of as a tail
-    int k = (((int)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * kPrepThreads + threadIdx.x;
+
+  // ---- border zeros of the RGBA levels and the transform table, spread over all blocks and done first, so their
+  // serial chains (sin / cos, LU inverse) run under the tiles instead of as a tail
+  {
     const int per_img = job.border_begin[job.S];
     const int n_border = job.V * B * per_img;
-    if (k < n_border) {
+    for (int k0 = blockIdx.x * kPrepThreads + threadIdx.x; k0 < n_border + prep.n; k0 += gridDim.x * kPrepThreads) {
+      int k = k0;
+      if (k >= n_border) { prep_one(prep, k - n_border); continue; }
       const int vb = k / per_img;
       k -= vb * per_img;
       int s = 0;
@@ -832,74 +842,99 @@ loss_prep_kernel(const PrepImgJob job, const PrepJob prep) {
         col = c < kPad ? c : Ws + c;
       }
       job.src_lvl[v][s][((size_t)b * (Hs + 2 * kPad) + row) * st + col] = make_float4(0.f, 0.f, 0.f, 0.f);
-      return;
     }
-    k -= n_border;
-    if (k < prep.n) prep_one(prep, k);
-    return;
   }
-  // ---- which tile
-  const int tyi = blockIdx.y, txi = blockIdx.x;
-  const int ib = (int)blockIdx.z - job.extra_z;           // image * B + b
-  const int im = ib / B, b = ib - im * B;
-  const int y0 = tyi * RB, x0 = txi * TW;
-  const int rows = min(RB, H - y0), cols = min(TW, W - x0);   // multiples of F
-  const float* __restrict__ img = im == 0 ? job.tgt : job.src[im > 0 ? im - 1 : 0];
-  const float* __restrict__ g0 = img + (((size_t)b * H + y0) * W + x0) * 3;
 
-  // ---- stage: row r of the tile = cols * 3 contiguous floats
-  if ((W % 4 == 0) && (cols % 4 == 0) && ((reinterpret_cast<uintptr_t>(img) & 15) == 0)) {
-    const int q_row = cols * 3 / 4;                 // float4 per row
-    const unsigned ts = (unsigned)__cvta_generic_to_shared(tile);
-    // the level-0 images are read exactly once: evict-first in L2, so that what this launch WRITES (the RGBA
-    // levels the fused launch gathers from next) is what stays resident
-    unsigned long long pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    if (rows == RB && cols == TW) {                 // full tile: compile-time trip counts
-      constexpr int QR = TW * 3 / 4;
+  // the level-0 images are read exactly once: evict-first in L2, so that what this launch WRITES (the RGBA
+  // levels the fused launch gathers from next) is what stays resident
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  const int per_img = job.tiles_x * job.tiles_y;
+  const float inv_per_img = 1.0f / (float)per_img, inv_tx = 1.0f / (float)job.tiles_x, inv_B = 1.0f / (float)B;
+
+  struct Tile { int im, b, y0, x0, rows, cols; };
+  auto decode = [&](int t) {
+    Tile q;
+    const int ib = fast_div(t, per_img, inv_per_img), rem = t - ib * per_img;   // ib = image * B + b
+    const int tyi = fast_div(rem, job.tiles_x, inv_tx), txi = rem - tyi * job.tiles_x;
+    q.im = fast_div(ib, B, inv_B); q.b = ib - q.im * B;
+    q.y0 = tyi * RB; q.x0 = txi * TW;
+    q.rows = min(RB, H - q.y0); q.cols = min(TW, W - q.x0);   // multiples of F
+    return q;
+  };
+  // stage: row r of the tile = cols * 3 contiguous floats
+  auto stage = [&](const Tile& q, float* tile) {
+    const float* __restrict__ img = q.im == 0 ? job.tgt : job.src[q.im > 0 ? q.im - 1 : 0];
+    const float* __restrict__ g0 = img + (((size_t)q.b * H + q.y0) * W + q.x0) * 3;
+    if ((W % 4 == 0) && (q.cols % 4 == 0) && ((reinterpret_cast<uintptr_t>(img) & 15) == 0)) {
+      const unsigned ts = (unsigned)__cvta_generic_to_shared(tile);
+      if (q.rows == RB && q.cols == TW) {                 // full tile: compile-time trip counts
+        constexpr int QR = TW * 3 / 4;
 #pragma unroll
-      for (int i = 0; i < (RB * QR) / kPrepThreads; ++i) {
-        const int e = threadIdx.x + i * kPrepThreads;
-        const int r = e / QR, q = e - r * QR;
-        asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(ts + (unsigned)(r * TW * 3 + q * 4) * 4u),
-                     "l"(g0 + (size_t)r * W * 3 + q * 4), "l"(pol)
-                     : "memory");
+        for (int i = 0; i < (RB * QR) / kPrepThreads; ++i) {
+          const int e = threadIdx.x + i * kPrepThreads;
+          const int r = e / QR, c = e - r * QR;
+          asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(ts + (unsigned)(r * TW * 3 + c * 4) * 4u),
+                       "l"(g0 + (size_t)r * W * 3 + c * 4), "l"(pol)
+                       : "memory");
+        }
+      } else {
+        const int q_row = q.cols * 3 / 4;                 // float4 per row
+        for (int r = threadIdx.x >> 5; r < q.rows; r += kPrepThreads / 32)
+          for (int c = threadIdx.x & 31; c < q_row; c += 32)
+            asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(ts + (unsigned)(r * TW * 3 + c * 4) * 4u),
+                         "l"(g0 + (size_t)r * W * 3 + c * 4), "l"(pol)
+                         : "memory");
       }
     } else {
-      for (int r = threadIdx.x >> 5; r < rows; r += kPrepThreads / 32)
-        for (int q = threadIdx.x & 31; q < q_row; q += 32)
-          asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(ts + (unsigned)(r * TW * 3 + q * 4) * 4u),
-                       "l"(g0 + (size_t)r * W * 3 + q * 4), "l"(pol)
-                       : "memory");
+      const int n_row = q.cols * 3;
+      for (int i = threadIdx.x; i < q.rows * n_row; i += kPrepThreads) {
+        const int r = i / n_row, c = i - r * n_row;
+        tile[r * TW * 3 + c] = __ldg(g0 + (size_t)r * W * 3 + c);
+      }
     }
-    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-  } else {
-    const int n_row = cols * 3;
-    for (int i = threadIdx.x; i < rows * n_row; i += kPrepThreads) {
-      const int r = i / n_row, q = i - r * n_row;
-      tile[r * TW * 3 + q] = __ldg(g0 + (size_t)r * W * 3 + q);
-    }
-  }
-  __syncthreads();
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
 
-  if (im == 0) {
-    prep_levels<LOG2F, TW, RB, false>(tile, rows, cols, [&](int sh, int& stride) {
-      const int Hs = H >> sh, Ws = W >> sh;
-      stride = Ws * 3;
-      return job.tgt_lvl[sh] + (((size_t)b * Hs + (y0 >> sh)) * Ws + (x0 >> sh)) * 3;
-    });
-  } else {
-    const int v = im - 1;
-    auto dst_of = [&](int sh, int& stride) {
-      const int Hs = H >> sh, Ws = W >> sh, st = Ws + 2 * kPad;
-      stride = st * 4;
-      return reinterpret_cast<float*>(job.src_lvl[v][sh] + ((size_t)b * (Hs + 2 * kPad) + (y0 >> sh) + kPad) * st +
-                                      (x0 >> sh) + kPad);
-    };
-    int st0;
-    float* d0 = dst_of(0, st0);
-    prep_rgba0<TW, RB>(tile, rows, cols, reinterpret_cast<float4*>(d0), st0 / 4);
-    prep_levels<LOG2F, TW, RB, true>(tile, rows, cols, dst_of);
+  int t = blockIdx.x;
+  if (t >= job.n_tiles) return;
+  Tile cur = decode(t);
+  stage(cur, reinterpret_cast<float*>(tile4[0]));
+  for (int it = 0; t < job.n_tiles; ++it, t += gridDim.x) {
+    const float* tile = reinterpret_cast<const float*>(tile4[it & 1]);
+    const int tn = t + gridDim.x;
+    Tile nxt = cur;
+    if (tn < job.n_tiles) {
+      nxt = decode(tn);
+      stage(nxt, reinterpret_cast<float*>(tile4[(it + 1) & 1]));
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int b = cur.b, y0 = cur.y0, x0 = cur.x0, rows = cur.rows, cols = cur.cols;
+    if (cur.im == 0) {
+      prep_levels<LOG2F, TW, RB, false>(tile, rows, cols, [&](int sh, int& stride) {
+        const int Hs = H >> sh, Ws = W >> sh;
+        stride = Ws * 3;
+        return job.tgt_lvl[sh] + (size_t)(((b * Hs + (y0 >> sh)) * Ws + (x0 >> sh)) * 3);
+      });
+    } else {
+      const int v = cur.im - 1;
+      auto dst_of = [&](int sh, int& stride) {
+        const int Hs = H >> sh, Ws = W >> sh, st = Ws + 2 * kPad;
+        stride = st * 4;
+        return reinterpret_cast<float*>(job.src_lvl[v][sh] +
+                                        (size_t)((b * (Hs + 2 * kPad) + (y0 >> sh) + kPad) * st + (x0 >> sh) + kPad));
+      };
+      int st0;
+      float* d0 = dst_of(0, st0);
+      prep_rgba0<TW, RB>(tile, rows, cols, reinterpret_cast<float4*>(d0), st0 / 4);
+      prep_levels<LOG2F, TW, RB, true>(tile, rows, cols, dst_of);
+    }
+    __syncthreads();   // this buffer is the target of the stage after next
+    cur = nxt;
   }
 }
 
@@ -1006,7 +1041,7 @@ int run_loss(const VslLossDesc* d, LossParams& P, const float* poses, const floa
 
 int launch_prep(const PrepImgJob& job, const PrepJob& prep, cudaStream_t st) {
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(job.tiles_x, job.tiles_y, job.extra_z + (job.V + 1) * job.B);
+  cfg.gridDim = dim3(job.n_blocks);
   cfg.blockDim = dim3(kPrepThreads);
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -1127,8 +1162,13 @@ int vsl_loss_fwd_bwd(const VslLossDesc* d, const float* tgt, const float* const*
       job.border_begin[s + 1] = job.border_begin[s];
     }
   }
-  job.n_extra_blocks = (int)(((long long)job.V * job.B * job.border_begin[job.S] + prep.n + kPrepThreads - 1) / kPrepThreads);
-  job.extra_z = (job.n_extra_blocks + job.tiles_x * job.tiles_y - 1) / (job.tiles_x * job.tiles_y);
+  {
+    // persistent blocks: as many as can be resident (2 x 12 KB of shared memory and <= 64 registers x 256 threads
+    // each: 4 per SM), never more than there are tiles
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    job.n_blocks = std::min(job.n_tiles, sms * 4);
+  }
   rc = launch_prep(job, prep, st);
   if (rc != VSL_OK) return rc;
   // 2 + 3. fused loss and finalize
