@@ -40,11 +40,13 @@ namespace vsl {
 #ifndef VSL_RH
 #define VSL_RH 16
 #endif
+// 4 independent warps per block, 4 blocks per SM (128 registers x 512 threads fill the register file): measured
+// best of {1x16, 2x8, 4x4, 8x2, 16x1}; block granularity only matters for how evenly the tail drains
 #ifndef VSL_FUSED_WARPS
-#define VSL_FUSED_WARPS 8
+#define VSL_FUSED_WARPS 4
 #endif
 #ifndef VSL_FUSED_MIN_BLOCKS
-#define VSL_FUSED_MIN_BLOCKS 2
+#define VSL_FUSED_MIN_BLOCKS 4
 #endif
 
 constexpr int kRH = VSL_RH;                     // tile rows per warp
@@ -156,7 +158,7 @@ VSL_DEV void tap_issue(Tap& t, const float (&p)[12], float c0, float c1, float c
 // EXACT = false: the same algebra with FMA contraction, MUFU reciprocal / exp / log and the closed form
 //                d(depth) = -<du, t> / depth; differs from EXACT by a few ulp per quantity.
 template <int V, bool EXACT>
-__global__ void __launch_bounds__(kThreads, (V <= 2 ? VSL_FUSED_MIN_BLOCKS : 1))
+__global__ void __launch_bounds__(kThreads, (V <= 2 ? VSL_FUSED_MIN_BLOCKS : VSL_FUSED_MIN_BLOCKS / 2))
 loss_fused_kernel(const LossParams P) {
   constexpr int N = NT<V>::value;
   using L = WarpSmem<V>;
