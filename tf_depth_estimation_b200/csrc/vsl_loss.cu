@@ -87,10 +87,9 @@ template <int V> struct NT { static constexpr int value = 3 + 12 * V; };
 // one warp's slice of dynamic shared memory (floats)
 template <int V> struct WarpSmem {
   static constexpr int qt = 0;                          // [kQH][kQS]  x or 1/x with a 2-pixel halo
-  static constexpr int sA = qt + kQH * kQS;             // [kOH][kOW]  cxx * sign(dx2) per owner
-  static constexpr int sB = sA + kOH * kOW;             //             cyy * sign(dy2)
-  static constexpr int sC = sB + kOH * kOW;             //             cxy*sign(dxdy) + cyx*sign(dydx)
-  static constexpr int xc = sC + kOH * kOW;             // [kRH][32]  x itself where the tile holds 1/x
+  static constexpr int ha = qt + kQH * kQS;             // [kOH][2]    cxx * sign(dx2) of the 2 columns left of the tile
+  static constexpr int hc = ha + kOH * 2;               // [kOH][2]    cxy*sign(dxdy) + cyx*sign(dydx), same columns
+  static constexpr int xc = hc + kOH * 2;               // [kRH][32]   x itself where the tile holds 1/x
   static constexpr int total = (xc + kRH * 32 + 3) / 4 * 4;
   static constexpr size_t block_bytes = sizeof(float) * total * kWarps;
 };
@@ -153,6 +152,39 @@ VSL_DEV void tap_issue(Tap& t, const float (&p)[12], float c0, float c1, float c
   t.C = __ldg(g + stride4); t.D = __ldg(g + stride4 + 1);
 }
 
+// The four second differences owned by the element at q (their top-left corner), my_losses.py:27-36:
+// weighted signs for the gradient (a: xx, b: yy, c: xy + yx) and the weighted |.| sum for the loss.
+// gx, gy: image coordinates of the element as unsigned (a difference exists iff its support is inside).
+template <bool EXACT>
+VSL_DEV void owner_signs(const float* q, unsigned gx, unsigned gy, int H, int W, float cxx, float cxy, float cyx,
+                         float cyy, float& a, float& b, float& c, float& sm) {
+  const float q00 = q[0], q01 = q[1], q02 = q[2], q10 = q[kQS], q11 = q[kQS + 1], q20 = q[2 * kQS];
+  const float dx0 = __fsub_rn(q01, q00), dy0 = __fsub_rn(q10, q00);
+  float dxx = __fsub_rn(__fsub_rn(q02, q01), dx0);
+  float dyy = __fsub_rn(__fsub_rn(q20, q10), dy0);
+  float dxy = __fsub_rn(__fsub_rn(q11, q10), dx0);  // d/dy of dx
+  // unsigned compares fold the >= 0 tests; H, W >= 3 is guaranteed by check_desc
+  if (!(gy < (unsigned)H && gx < (unsigned)(W - 2))) dxx = 0.f;
+  if (!(gx < (unsigned)W && gy < (unsigned)(H - 2))) dyy = 0.f;
+  const bool mixed = gx < (unsigned)(W - 1) && gy < (unsigned)(H - 1);
+  if (!mixed) dxy = 0.f;
+  if (EXACT) {
+    float dyx = __fsub_rn(__fsub_rn(q11, q01), dy0);  // d/dx of dy
+    if (!mixed) dyx = 0.f;
+    a = signed_by(cxx, dxx);
+    b = signed_by(cyy, dyy);
+    c = signed_by(cxy, dxy) + signed_by(cyx, dyx);
+    sm = cxx * fabsf(dxx) + cyy * fabsf(dyy) + cxy * fabsf(dxy) + cyx * fabsf(dyx);
+  } else {
+    // d/dy of dx and d/dx of dy are the same number up to rounding: the fast path evaluates it once
+    const float cm = cxy + cyx;
+    a = cxx * sign_fast(dxx);
+    b = cyy * sign_fast(dyy);
+    c = cm * sign_fast(dxy);
+    sm = cxx * fabsf(dxx) + cyy * fabsf(dyy) + cm * fabsf(dxy);
+  }
+}
+
 // EXACT = true : coordinates, softmax and the warped value follow the reference's rounding sequence
 //                (bit-identical sample positions to the oracle for matrix poses).
 // EXACT = false: the same algebra with FMA contraction, MUFU reciprocal / exp / log and the closed form
@@ -170,9 +202,8 @@ loss_fused_kernel(const LossParams P) {
   if (tile >= P.item_begin[P.S]) return;   // warps are independent: no block barrier anywhere below
   float* wsm = reinterpret_cast<float*>(smem4) + warp * L::total;
   float* qt = wsm + L::qt;
-  float* sA = wsm + L::sA;
-  float* sB = wsm + L::sB;
-  float* sC = wsm + L::sC;
+  float* sha = wsm + L::ha;
+  float* shc = wsm + L::hc;
   float* sxc = wsm + L::xc;
 
   // ---- which tile
@@ -223,43 +254,17 @@ loss_fused_kernel(const LossParams P) {
 
   float pix_sum = 0.f, exp_sum = 0.f, sm_sum = 0.f;
 
-  // ---- 2. smoothness, pass 1: every element of (tile + 2 rows above + 2 columns left) evaluates the four
-  // second differences it owns (it is their top-left corner) ONCE and publishes their weighted signs.
-  {
-    const float cxx = P.csm[s][0], cxy = P.csm[s][1], cyx = P.csm[s][2], cyy = P.csm[s][3];
-    int oy = 0, ox = lane;
-#pragma unroll 2
-    for (int i = lane; i < kOH * kOW; i += 32) {
-      const float* q = qt + oy * kQS + ox;
-      const float q00 = q[0], q01 = q[1], q02 = q[2], q10 = q[kQS], q11 = q[kQS + 1], q20 = q[2 * kQS];
-      const unsigned gx = (unsigned)(x_base - kHalo + ox), gy = (unsigned)(y_base - kHalo + oy);
-      const float dx0 = __fsub_rn(q01, q00), dy0 = __fsub_rn(q10, q00);
-      float dxx = __fsub_rn(__fsub_rn(q02, q01), dx0);
-      float dyy = __fsub_rn(__fsub_rn(q20, q10), dy0);
-      float dxy = __fsub_rn(__fsub_rn(q11, q10), dx0);  // d/dy of dx
-      float dyx = EXACT ? __fsub_rn(__fsub_rn(q11, q01), dy0) : 0.f;  // d/dx of dy
-      // a difference exists iff its whole support lies inside the image (unsigned compares fold the >= 0 tests;
-      // H, W >= 3 is guaranteed by check_desc)
-      if (!(gy < (unsigned)H && gx < (unsigned)(W - 2))) dxx = 0.f;
-      if (!(gx < (unsigned)W && gy < (unsigned)(H - 2))) dyy = 0.f;
-      if (!(gx < (unsigned)(W - 1) && gy < (unsigned)(H - 1))) { dxy = 0.f; dyx = 0.f; }
-      if (EXACT) {
-        sA[i] = signed_by(cxx, dxx);
-        sB[i] = signed_by(cyy, dyy);
-        sC[i] = signed_by(cxy, dxy) + signed_by(cyx, dyx);
-        if (oy >= kHalo && ox >= kHalo)
-          sm_sum += cxx * fabsf(dxx) + cyy * fabsf(dyy) + cxy * fabsf(dxy) + cyx * fabsf(dyx);
-      } else {
-        // d/dy of dx and d/dx of dy are the same number up to rounding: the fast path evaluates it once
-        const float cm = cxy + cyx;
-        sA[i] = cxx * sign_fast(dxx);
-        sB[i] = cyy * sign_fast(dyy);
-        sC[i] = cm * sign_fast(dxy);
-        if (oy >= kHalo && ox >= kHalo) sm_sum += cxx * fabsf(dxx) + cyy * fabsf(dyy) + cm * fabsf(dxy);
-      }
-      ox += 32;
-      if (ox >= kOW) { ox -= kOW; ++oy; }
-    }
+  // ---- 2. smoothness of the two columns LEFT of the tile: the weighted signs of their xx and xy/yx second
+  // differences, which the gradient of columns 0 and 1 needs.  Everything else of the smoothness term is
+  // evaluated in the row loop, lane = column: own column in registers, the two to the left by shuffle.
+  const float cxx = P.csm[s][0], cxy = P.csm[s][1], cyx = P.csm[s][2], cyy = P.csm[s][3];
+  for (int i = lane; i < kOH * 2; i += 32) {
+    const int oy = i >> 1, ox = i & 1;
+    float a, bb, c, sm;
+    owner_signs<EXACT>(qt + oy * kQS + ox, (unsigned)(x_base - kHalo + ox), (unsigned)(y_base - kHalo + oy), H, W, cxx,
+                       cxy, cyx, cyy, a, bb, c, sm);
+    sha[i] = a;
+    shc[i] = c;
   }
   __syncwarp();
 
@@ -313,10 +318,20 @@ loss_fused_kernel(const LossParams P) {
 #pragma unroll
     for (int i = 0; i < 3; ++i) { S2[v][i] = 0.f; S3[v][i] = 0.f; S4[v][i] = 0.f; }
 
-  // vertical neighbours of the smoothness gradient travel down in registers
-  const int o0 = kHalo * kOW + lane + kHalo;          // owner slot of (row 0, this column)
-  float b2 = sB[o0 - 2 * kOW], b1 = sB[o0 - kOW];
-  float c10 = sC[o0 - kOW], c11 = sC[o0 - kOW - 1];
+  // vertical neighbours of the smoothness gradient travel down in registers: the owners of the two rows above
+  // the tile come first
+  float b1, b2, c10, c11;
+  {
+    float a, bb, c, sm;
+    owner_signs<EXACT>(qt + lane + kHalo, (unsigned)x, (unsigned)(y_base - 2), H, W, cxx, cxy, cyx, cyy, a, bb, c, sm);
+    b2 = bb;
+    owner_signs<EXACT>(qt + kQS + lane + kHalo, (unsigned)x, (unsigned)(y_base - 1), H, W, cxx, cxy, cyx, cyy, a, bb, c,
+                       sm);
+    b1 = bb;
+    c10 = c;
+    c11 = __shfl_up_sync(0xffffffffu, c, 1);
+    if (lane == 0) c11 = shc[1 * 2 + 1];
+  }
 
   const float* __restrict__ tgt_img = P.tgt[s] + img_off * 3;
   const float* __restrict__ lg_img = use_lg ? P.logits[s] + img_off * (2 * V) : nullptr;
@@ -416,12 +431,24 @@ loss_fused_kernel(const LossParams P) {
     if (has_next) load_stream(nxt, pofs + W);
 
     // ---- phase 2
-    // smoothness, pass 2: gradient = the published signs of the 10 stencils this element is part of
-    const int o = o0 + r * kOW;
-    const float a0 = sA[o], a1 = sA[o - 1], a2 = sA[o - 2];
-    const float b0 = sB[o], c00 = sC[o], c01 = sC[o - 1];
-    const float g_q = (a0 - 2.f * a1 + a2) + (b0 - 2.f * b1 + b2) + (c00 - c01 - c10 + c11);
-    b2 = b1; b1 = b0; c10 = c00; c11 = c01;
+    // smoothness: the four differences this element owns, then the gradient = the weighted signs of the 10
+    // stencils it is part of (own column from registers, the two columns to the left by shuffle)
+    float g_q;
+    {
+      float a0, b0, c00, sm;
+      owner_signs<EXACT>(qt + (r + kHalo) * kQS + lane + kHalo, (unsigned)x, (unsigned)(y_base + r), H, W, cxx, cxy, cyx,
+                         cyy, a0, b0, c00, sm);
+      sm_sum += sm;
+      float a1 = __shfl_up_sync(0xffffffffu, a0, 1), a2 = __shfl_up_sync(0xffffffffu, a0, 2);
+      float c01 = __shfl_up_sync(0xffffffffu, c00, 1);
+      if (lane < 2) {
+        const int o = (r + kHalo) * 2;
+        if (lane == 0) { a1 = sha[o + 1]; a2 = sha[o]; c01 = shc[o + 1]; }
+        else a2 = sha[o + 1];
+      }
+      g_q = (a0 - 2.f * a1 + a2) + (b0 - 2.f * b1 + b2) + (c00 - c01 - c10 + c11);
+      b2 = b1; b1 = b0; c10 = c00; c11 = c01;
+    }
 
     float g_d = 0.f;
 #pragma unroll
