@@ -38,7 +38,7 @@
 namespace vsl {
 
 #ifndef VSL_RH
-#define VSL_RH 16
+#define VSL_RH 32
 #endif
 // 4 independent warps per block, 4 blocks per SM (128 registers x 512 threads fill the register file): measured
 // best of {1x16, 2x8, 4x4, 8x2, 16x1}; block granularity only matters for how evenly the tail drains
