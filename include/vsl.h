@@ -152,7 +152,8 @@ typedef struct {
   float loss_scale;      /* upstream gradient of the summed loss, folded into every gradient */
   int exact_coords;      /* 1: reference rounding sequence for coordinates / softmax / blend (bit-identical
                             sample positions to the oracle for matrix poses); 0: FMA + MUFU fast path */
-  int reserved_;
+  int want_src_grad;     /* 1: also produce d/d(source images) into g_srcs (atomic scatter: the one output whose
+                            summation order is not deterministic); needs exact_coords == 0 */
   void* ev_main_begin;   /* optional cudaEvent_t pair recorded on `stream` immediately around the fused  */
   void* ev_main_end;     /* loss kernel (launch 3 of the step) so a caller can time it in situ; NULL = off */
 } VslLossDesc;
@@ -166,6 +167,7 @@ int vsl_loss_fwd_bwd(const VslLossDesc* d,
                      const float* const* mask_pyr /*S x [B,Hs,Ws,1], MASK_CONST*/,
                      float* losses /*device [3]*/, float* const* g_x_pyr /*S x [B,Hs,Ws,1]*/,
                      float* g_poses /*same shape as poses*/, float* const* g_logits_pyr /*S, MASK_EXP*/,
+                     float* const* g_srcs /*host array V x [B,H,W,3]; NULL unless want_src_grad*/,
                      void* ws, vsl_stream_t stream);
 
 #ifdef __cplusplus

@@ -406,3 +406,38 @@ def test_pyramid_shapes_bit_exact():
         lv = ops.image_pyramid(cu(img), S)
         for s in range(1, S):
             assert torch.equal(lv[s].cpu(), O.resize_area(img, H >> s, W >> s)), (C, S, s)
+
+
+def test_fused_source_image_gradient_against_oracle():
+    """d/d(source images) of the fused step (atomic 16-byte scatter into gradient levels + fold-back through the
+    resize_area pyramid) against float64 autograd of the oracle.  A target pixel whose photometric error is within
+    rounding of 0 has an undetermined sign(e) ("Discontinuities") and moves up to four source pixels, so
+    the comparison is over the entries that agree to 1e-4 of the largest gradient, which must be >= 99.5 %."""
+    B, H, W, S, V = 2, 32, 104, 4, 2
+    d = synth.make_snippets(B, H, W, S=S, V=V, seed=41, motion=1.5)
+    flags = ops.LossFlags(num_scales=S)
+    srcs = [cu(s, True) for s in d['srcs']]
+    xs = [cu(x, True) for x in d['disp_pyr']]
+    ps = cu(d['poses'], True)
+    lgs = [cu(l, True) for l in d['logits_pyr']]
+    total, losses = ops.view_synthesis_loss(cu(d['tgt']), srcs, xs, ps, cu(d['K_pyr']), logits_pyr=lgs, flags=flags)
+    total.backward()
+    osrc = [s.double().requires_grad_() for s in d['srcs']]
+    oxs = [x.double().requires_grad_() for x in d['disp_pyr']]
+    op_ = d['poses'].double().requires_grad_()
+    ol = [l.double().requires_grad_() for l in d['logits_pyr']]
+    ref = O.view_synthesis_loss(d['tgt'].double(), osrc, oxs, op_, d['K_pyr'].double(), ol, None, O.LossFlags(num_scales=S))
+    sum(ref).backward()
+    for got, want in zip(losses.tolist(), ref):
+        assert abs(got - float(want)) <= 1e-5 * abs(float(want)) + 1e-9
+    assert rel_err(ps.grad, op_.grad) <= 1e-4          # the other gradients are those of the plain step
+    for v in range(V):
+        g, w = srcs[v].grad.cpu().double(), osrc[v].grad
+        assert float(w.abs().max()) > 0
+        ok = (g - w).abs() <= 1e-4 * float(w.abs().max())
+        assert float(ok.double().mean()) >= 0.995, (v, float(ok.double().mean()))
+        assert abs(float(g.sum()) - float(w.sum())) <= 2e-3 * float(w.abs().sum())
+    # the request is refused, not ignored, where it is not implemented
+    with pytest.raises(Exception):
+        ops.view_synthesis_loss(cu(d['tgt']), srcs, xs, ps, cu(d['K_pyr']), logits_pyr=lgs,
+                                flags=ops.LossFlags(num_scales=S, exact_coords=True))

@@ -25,7 +25,7 @@ class VslLossDesc(ctypes.Structure):
                 ('smooth_on_inverse', ctypes.c_int),
                 ('data_weight', ctypes.c_float), ('smooth_weight', ctypes.c_float),
                 ('explain_reg_weight', ctypes.c_float), ('loss_scale', ctypes.c_float),
-                ('exact_coords', ctypes.c_int), ('reserved_', ctypes.c_int),
+                ('exact_coords', ctypes.c_int), ('want_src_grad', ctypes.c_int),
                 ('ev_main_begin', ctypes.c_void_p), ('ev_main_end', ctypes.c_void_p)]
 
 
@@ -60,7 +60,8 @@ SIGNATURES = {
                                         ctypes.POINTER(ctypes.c_void_p), _c_float_p, _c_float_p,
                                         ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p),
                                         _c_float_p, ctypes.POINTER(ctypes.c_void_p), _c_float_p,
-                                        ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p, _c_stream]),
+                                        ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p),
+                                        ctypes.c_void_p, _c_stream]),
 }
 
 _lib = None

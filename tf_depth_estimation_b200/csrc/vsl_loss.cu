@@ -66,6 +66,7 @@ struct LossParams {
   int mask_mode, depth_is_inverse, smooth_on_inverse;
   const float* tgt[VSL_MAX_SCALES];                    // RGB
   const float4* src[VSL_MAX_VIEWS][VSL_MAX_SCALES];    // zero-bordered RGBA [B][Hs+4][Ws+4]
+  float4* gsrc[VSL_MAX_VIEWS][VSL_MAX_SCALES];         // d/d(those levels), same layout (only with DSRC)
   const float* x[VSL_MAX_SCALES];
   const float* logits[VSL_MAX_SCALES];
   const float* mask[VSL_MAX_SCALES];
@@ -122,6 +123,7 @@ struct Tap {
   float4 A, B, C, D;             // corners (x0,y0) (x1,y0) (x0,y1) (x1,y1)
   float wx0, wx1, wy0, wy1;      // (x1 - x), (x - x0), (y1 - y), (y - y0)
   float qx, qy, rz;              // projected coordinates (unclamped) and 1 / (z + eps)
+  int off;                       // float4 offset of corner A inside the level (kept for the d/d(source) scatter)
 };
 
 // Projection, footprint and the four 16-byte gathers of one view.  p: the 12 floats of P (warp-uniform).
@@ -147,6 +149,7 @@ VSL_DEV void tap_issue(Tap& t, const float (&p)[12], float c0, float c1, float c
     t.wx0 = __fsub_rn(__fadd_rn(fx, 1.0f), xc); t.wy0 = __fsub_rn(__fadd_rn(fy, 1.0f), yc);
   }
   const int off = (int)(__float_as_uint(ty) * (unsigned)stride4 + __float_as_uint(tx) + (unsigned)coff);  // wraps to the true offset
+  t.off = off;
   const float4* __restrict__ g = src + off;
   t.A = __ldg(g); t.B = __ldg(g + 1);
   t.C = __ldg(g + stride4); t.D = __ldg(g + stride4 + 1);
@@ -189,7 +192,9 @@ VSL_DEV void owner_signs(const float* q, unsigned gx, unsigned gy, int H, int W,
 //                (bit-identical sample positions to the oracle for matrix poses).
 // EXACT = false: the same algebra with FMA contraction, MUFU reciprocal / exp / log and the closed form
 //                d(depth) = -<du, t> / depth; differs from EXACT by a few ulp per quantity.
-template <int V, bool EXACT>
+// DSRC = true additionally scatters d/d(source levels) with 16-byte reductions (red.global.add.v4.f32) into
+// gradient levels of the same zero-bordered RGBA layout; loss_fold_src_grad_kernel folds them back to level 0.
+template <int V, bool EXACT, bool DSRC>
 __global__ void __launch_bounds__(kThreads, (V <= 2 ? VSL_FUSED_MIN_BLOCKS : VSL_FUSED_MIN_BLOCKS / 2))
 loss_fused_kernel(const LossParams P) {
   constexpr int N = NT<V>::value;
@@ -410,6 +415,7 @@ loss_fused_kernel(const LossParams P) {
       const float w00 = __fmul_rn(wx0, wy0), w01 = __fmul_rn(wx0, t.wy1),
                   w10 = __fmul_rn(t.wx1, wy0), w11 = __fmul_rn(t.wx1, t.wy1);
       float E = __uint_as_float(pad), JA = 0.f, JB = 0.f, JC = 0.f, JD = 0.f;
+      float sgc[3] = {0.f, 0.f, 0.f};
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         const float wv = EXACT ? blend(w00, w01, w10, w11, cA[c], cC[c], cB[c], cD[c])
@@ -419,6 +425,35 @@ loss_fused_kernel(const LossParams P) {
         const float sg = EXACT ? signed_by(1.f, e) : sign_fast(e);
         JA = fmaf(sg, cA[c], JA); JB = fmaf(sg, cB[c], JB);
         JC = fmaf(sg, cC[c], JC); JD = fmaf(sg, cD[c], JD);
+        if (DSRC) sgc[c] = sg;
+      }
+      if (DSRC) {
+        // d/d(corner_k[c]) = cpix * m * sign(e_c) * w_k; a corner in the border lands in the border of the
+        // gradient level, which nobody reads
+        float m = cur.mc;
+        if (use_lg) {
+          const float l0 = cur.lg[2 * v], l1 = cur.lg[2 * v + 1];
+          if (EXACT) {
+            const float mx = fmaxf(l0, l1);
+            const float e0 = expf(l0 - mx), e1 = expf(l1 - mx);
+            m = e1 / (e0 + e1);
+          } else {
+            m = rcp_fast(1.f + ex2_fast(1.4426950408889634f * (l0 - l1)));   // softmax(l)[1]
+          }
+        }
+        if (act) {
+          float4* g = P.gsrc[v][s] + src_off + t.off;
+          const float km = cpix * m;
+          const float k00 = km * w00, k10 = km * w10, k01 = km * w01, k11 = km * w11;
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(g), "f"(k00 * sgc[0]), "f"(k00 * sgc[1]),
+                       "f"(k00 * sgc[2]), "f"(0.f) : "memory");
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(g + 1), "f"(k10 * sgc[0]), "f"(k10 * sgc[1]),
+                       "f"(k10 * sgc[2]), "f"(0.f) : "memory");
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(g + stride4), "f"(k01 * sgc[0]),
+                       "f"(k01 * sgc[1]), "f"(k01 * sgc[2]), "f"(0.f) : "memory");
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(g + stride4 + 1), "f"(k11 * sgc[0]),
+                       "f"(k11 * sgc[1]), "f"(k11 * sgc[2]), "f"(0.f) : "memory");
+        }
       }
       const float dx = wy0 * (JB - JA) + t.wy1 * (JD - JC);
       const float dy = wx0 * (JC - JA) + t.wx1 * (JD - JB);
@@ -967,6 +1002,31 @@ loss_prep_kernel(const PrepImgJob job, const PrepJob prep) {
   }
 }
 
+// d/d(source image) of the fused step: the gradient levels (zero-bordered RGBA, scattered into by
+// loss_fused_kernel<.., DSRC>) folded back onto the caller's [B,H,W,3] layout.  Level s is the 2^s x 2^s block
+// mean of level 0 (resize_area), so every level-0 pixel receives 1/4^s of its level-s pixel's gradient.
+// One thread per level-0 pixel.
+struct FoldJob {
+  const float4* glvl[VSL_MAX_SCALES];   // one view's gradient levels
+  float* g_src;                         // [B,H,W,3]
+  int B, H, W, S;
+};
+__global__ void __launch_bounds__(256)
+loss_fold_src_grad_kernel(const FoldJob j) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
+  if (x >= j.W) return;
+  float g0 = 0.f, g1 = 0.f, g2 = 0.f, w = 1.0f;
+  for (int s = 0; s < j.S; ++s) {
+    const int Hs = j.H >> s, Ws = j.W >> s, st = Ws + 2 * kPad;
+    const float4 q = __ldg(j.glvl[s] + ((size_t)b * (Hs + 2 * kPad) + (y >> s) + kPad) * st + (x >> s) + kPad);
+    g0 = fmaf(w, q.x, g0); g1 = fmaf(w, q.y, g1); g2 = fmaf(w, q.z, g2);
+    w *= 0.25f;
+  }
+  float* o = j.g_src + (((size_t)b * j.H + y) * j.W + x) * 3;
+  o[0] = g0; o[1] = g1; o[2] = g2;
+}
+
 }  // namespace vsl
 
 using namespace vsl;
@@ -974,7 +1034,7 @@ using namespace vsl;
 namespace {
 
 struct WsLayout {
-  size_t xf, partials, tgt_pyr, src_pyr, total;      // byte offsets
+  size_t xf, partials, tgt_pyr, src_pyr, gsrc_pyr, total;      // byte offsets (gsrc_pyr only with want_src_grad)
   size_t tgt_off[VSL_MAX_SCALES];                    // floats, level s of the target pyramid (s >= 1)
   size_t src_off[VSL_MAX_SCALES];                    // float4, level s inside one view's RGBA block
   size_t src_view;                                   // float4 per view
@@ -992,6 +1052,7 @@ int check_desc(const VslLossDesc* d) {
   VSL_REQUIRE((long long)(d->V + 1) * d->B * (d->H + 4) * (d->W + 4) < (1ll << 31), VSL_E_SHAPE);
   VSL_REQUIRE(d->pose_format >= VSL_POSE_EULER && d->pose_format <= VSL_POSE_MATRIX, VSL_E_FORMAT);
   VSL_REQUIRE(d->mask_mode >= VSL_MASK_NONE && d->mask_mode <= VSL_MASK_CONST, VSL_E_FORMAT);
+  VSL_REQUIRE(!(d->want_src_grad && d->exact_coords), VSL_E_UNSUPPORTED);
   return VSL_OK;
 }
 
@@ -1017,13 +1078,14 @@ void layout(const VslLossDesc* d, WsLayout* L) {
   L->partials = round_up(sizeof(Xform) * (size_t)d->S * d->V * d->B, 256);
   L->tgt_pyr = L->partials + round_up(sizeof(float) * (size_t)n * nt, 256);
   L->src_pyr = L->tgt_pyr + round_up(sizeof(float) * tl, 256);
-  L->total = L->src_pyr + sizeof(float4) * sl * (size_t)d->V;
+  L->gsrc_pyr = L->src_pyr + sizeof(float4) * sl * (size_t)d->V;
+  L->total = L->gsrc_pyr + (d->want_src_grad ? sizeof(float4) * sl * (size_t)d->V : 0);
 }
 
-template <int V, bool EXACT>
+template <int V, bool EXACT, bool DSRC>
 int launch_fused(const LossParams& P, cudaStream_t st) {
   // > 48 KB of dynamic shared memory needs the opt-in; idempotent and cheap, so set on every call (no state)
-  cudaError_t e = cudaFuncSetAttribute(loss_fused_kernel<V, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaError_t e = cudaFuncSetAttribute(loss_fused_kernel<V, EXACT, DSRC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)WarpSmem<V>::block_bytes);
   if (e != cudaSuccess) return (int)e;
   const int n = P.item_begin[P.S];
@@ -1039,7 +1101,7 @@ int launch_fused(const LossParams& P, cudaStream_t st) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  e = cudaLaunchKernelEx(&cfg, loss_fused_kernel<V, EXACT>, P);
+  e = cudaLaunchKernelEx(&cfg, loss_fused_kernel<V, EXACT, DSRC>, P);
   if (e != cudaSuccess) return (int)e;
   return VSL_OK;
 }
@@ -1048,7 +1110,9 @@ template <int V>
 int run_loss(const VslLossDesc* d, LossParams& P, const float* poses, const float* K_pyr, float* losses,
              float* g_poses, cudaStream_t st) {
   if (d->ev_main_begin != nullptr) cudaEventRecord((cudaEvent_t)d->ev_main_begin, st);
-  const int rc = d->exact_coords ? launch_fused<V, true>(P, st) : launch_fused<V, false>(P, st);
+  // d/d(source) rides on the fast arithmetic only (check_desc refuses exact_coords + want_src_grad)
+  const int rc = d->want_src_grad ? launch_fused<V, false, true>(P, st)
+                                  : (d->exact_coords ? launch_fused<V, true, false>(P, st) : launch_fused<V, false, false>(P, st));
   if (rc != VSL_OK) return rc;
   if (d->ev_main_end != nullptr) cudaEventRecord((cudaEvent_t)d->ev_main_end, st);
   {
@@ -1105,13 +1169,14 @@ size_t vsl_loss_ws_bytes(const VslLossDesc* d) {
 int vsl_loss_fwd_bwd(const VslLossDesc* d, const float* tgt, const float* const* srcs, const float* const* x_pyr,
                      const float* poses, const float* K_pyr, const float* const* logits_pyr,
                      const float* const* mask_pyr, float* losses, float* const* g_x_pyr, float* g_poses,
-                     float* const* g_logits_pyr, void* ws, vsl_stream_t stream) {
+                     float* const* g_logits_pyr, float* const* g_srcs, void* ws, vsl_stream_t stream) {
   int rc = check_desc(d);
   if (rc != VSL_OK) return rc;
   VSL_REQUIRE(tgt && srcs && x_pyr && poses && K_pyr && losses && g_x_pyr && g_poses && ws, VSL_E_NULL);
   VSL_REQUIRE(d->mask_mode != VSL_MASK_EXP || (logits_pyr && g_logits_pyr), VSL_E_NULL);
   VSL_REQUIRE(d->mask_mode != VSL_MASK_CONST || mask_pyr, VSL_E_NULL);
   VSL_REQUIRE(d->loss_scale != 0.f, VSL_E_UNSUPPORTED);
+  VSL_REQUIRE(!d->want_src_grad || g_srcs, VSL_E_NULL);
   VSL_REQUIRE(aligned(ws, 256), VSL_E_ALIGN);
   cudaStream_t st = (cudaStream_t)stream;
   WsLayout L;
@@ -1120,6 +1185,7 @@ int vsl_loss_fwd_bwd(const VslLossDesc* d, const float* tgt, const float* const*
   Xform* xf = reinterpret_cast<Xform*>(base + L.xf);
   float* tgt_pyr = reinterpret_cast<float*>(base + L.tgt_pyr);
   float4* src_pyr = reinterpret_cast<float4*>(base + L.src_pyr);
+  float4* gsrc_pyr = reinterpret_cast<float4*>(base + L.gsrc_pyr);
 
   LossParams P;
   P.B = d->B; P.H = d->H; P.W = d->W; P.S = d->S; P.V = d->V;
@@ -1131,7 +1197,7 @@ int vsl_loss_fwd_bwd(const VslLossDesc* d, const float* tgt, const float* const*
   for (int s = 0; s < VSL_MAX_SCALES; ++s) {
     P.tgt[s] = nullptr; P.x[s] = nullptr; P.logits[s] = nullptr; P.mask[s] = nullptr;
     P.g_x[s] = nullptr; P.g_logits[s] = nullptr; P.lg_vec4[s] = 0; P.strips[s] = 0; P.bands[s] = 0;
-    for (int v = 0; v < VSL_MAX_VIEWS; ++v) P.src[v][s] = nullptr;
+    for (int v = 0; v < VSL_MAX_VIEWS; ++v) { P.src[v][s] = nullptr; P.gsrc[v][s] = nullptr; }
   }
   for (int s = 0; s < d->S; ++s) {
     const int H = d->H >> s, W = d->W >> s;
@@ -1150,7 +1216,10 @@ int vsl_loss_fwd_bwd(const VslLossDesc* d, const float* tgt, const float* const*
       P.mask[s] = mask_pyr[s];
     }
     P.tgt[s] = (s == 0) ? tgt : tgt_pyr + L.tgt_off[s];
-    for (int v = 0; v < d->V; ++v) P.src[v][s] = src_pyr + L.src_view * (size_t)v + L.src_off[s];
+    for (int v = 0; v < d->V; ++v) {
+      P.src[v][s] = src_pyr + L.src_view * (size_t)v + L.src_off[s];
+      P.gsrc[v][s] = d->want_src_grad ? gsrc_pyr + L.src_view * (size_t)v + L.src_off[s] : nullptr;
+    }
     P.strips[s] = L.strips[s]; P.bands[s] = L.bands[s];
     P.wstep[s] = 2.0f / (float)(W - 1);  // fp32 division, as grid_step() does on the device
     P.hstep[s] = 2.0f / (float)(H - 1);
@@ -1165,6 +1234,12 @@ int vsl_loss_fwd_bwd(const VslLossDesc* d, const float* tgt, const float* const*
     P.csm[s][3] = (float)(sw / ((double)d->B * (H - 2) * W));
   }
 
+  // 0. (only with want_src_grad) the gradient levels start from zero
+  if (d->want_src_grad) {
+    for (int v = 0; v < d->V; ++v) VSL_REQUIRE(g_srcs[v], VSL_E_NULL);
+    const cudaError_t e = cudaMemsetAsync(gsrc_pyr, 0, sizeof(float4) * L.src_view * (size_t)d->V, st);
+    if (e != cudaSuccess) return (int)e;
+  }
   // 1. pyramids, RGBA source levels, transforms
   const PrepJob prep = make_prep(poses, K_pyr, d->B, d->S, d->V, d->pose_format, xf, nullptr);
   PrepImgJob job;
@@ -1202,11 +1277,21 @@ int vsl_loss_fwd_bwd(const VslLossDesc* d, const float* tgt, const float* const*
   if (rc != VSL_OK) return rc;
   // 2 + 3. fused loss and finalize
   switch (d->V) {
-    case 1: return run_loss<1>(d, P, poses, K_pyr, losses, g_poses, st);
-    case 2: return run_loss<2>(d, P, poses, K_pyr, losses, g_poses, st);
-    case 3: return run_loss<3>(d, P, poses, K_pyr, losses, g_poses, st);
-    default: return run_loss<4>(d, P, poses, K_pyr, losses, g_poses, st);
+    case 1: rc = run_loss<1>(d, P, poses, K_pyr, losses, g_poses, st); break;
+    case 2: rc = run_loss<2>(d, P, poses, K_pyr, losses, g_poses, st); break;
+    case 3: rc = run_loss<3>(d, P, poses, K_pyr, losses, g_poses, st); break;
+    default: rc = run_loss<4>(d, P, poses, K_pyr, losses, g_poses, st); break;
   }
+  if (rc != VSL_OK || !d->want_src_grad) return rc;
+  // 4. d/d(source image): fold the gradient levels back to [B,H,W,3]
+  for (int v = 0; v < d->V; ++v) {
+    FoldJob fj;
+    for (int s = 0; s < VSL_MAX_SCALES; ++s) fj.glvl[s] = s < d->S ? P.gsrc[v][s] : nullptr;
+    fj.g_src = g_srcs[v];
+    fj.B = d->B; fj.H = d->H; fj.W = d->W; fj.S = d->S;
+    loss_fold_src_grad_kernel<<<dim3((d->W + 255) / 256, d->H, d->B), 256, 0, st>>>(fj);
+  }
+  return launch_status();
 }
 
 }  // extern "C"

@@ -392,9 +392,10 @@ class ViewSynthesisPlan(object):
     """Pre-allocated state for repeated fused-loss steps at one shape: workspace, gradient buffers and the
     pointer tables of the C call.  One instance per (shape, flags); not thread-safe."""
 
-    def __init__(self, B, H, W, V, flags, mask_mode, device, loss_scale=1.0):
+    def __init__(self, B, H, W, V, flags, mask_mode, device, loss_scale=1.0, want_src_grad=False):
         lib = _lib.load()
         S = flags.num_scales
+        self.want_src_grad = bool(want_src_grad)
         self.B, self.H, self.W, self.S, self.V = B, H, W, S, V
         self.mask_mode = mask_mode
         self.fmt = _fmt(flags.pose_format)
@@ -402,7 +403,7 @@ class ViewSynthesisPlan(object):
                                 int(flags.depth_is_inverse), int(flags.smooth_on_inverse),
                                 float(flags.data_weight), float(flags.smooth_weight),
                                 float(flags.explain_reg_weight), float(loss_scale),
-                                int(getattr(flags, 'exact_coords', False)), 0, None, None)
+                                int(getattr(flags, 'exact_coords', False)), int(self.want_src_grad), None, None)
         nbytes = lib.vsl_loss_ws_bytes(self.desc)
         if nbytes == 0:
             raise ValueError('unsupported loss shape B=%d H=%d W=%d S=%d V=%d' % (B, H, W, S, V))
@@ -412,6 +413,9 @@ class ViewSynthesisPlan(object):
         self.g_poses = torch.empty((B, V, 4, 4) if self.fmt == 2 else (B, V, 6), device=device)
         self.g_logits = ([torch.empty(B, H >> s, W >> s, 2 * V, device=device) for s in range(S)]
                          if mask_mode == _lib.MASK_EXP else None)
+        # d/d(source images): produced only on request (an extra atomic scatter + fold-back pass)
+        self.g_srcs = [torch.empty(B, H, W, 3, device=device) for _ in range(V)] if self.want_src_grad else None
+        self._gs_ptrs = ptr_array([t.data_ptr() for t in self.g_srcs]) if self.g_srcs else None
         self.version = 0  # bumped by every run(); lets autograd detect a stale backward
         self._gx_ptrs = ptr_array([t.data_ptr() for t in self.g_x])
         self._gl_ptrs = ptr_array([t.data_ptr() for t in self.g_logits]) if self.g_logits else None
@@ -423,7 +427,7 @@ class ViewSynthesisPlan(object):
                 ptr_array([x.data_ptr() for x in x_pyr]), poses.data_ptr(), K_pyr.data_ptr(),
                 ptr_array([l.data_ptr() for l in logits_pyr]) if logits_pyr is not None else None,
                 ptr_array([m.data_ptr() for m in mask_pyr]) if mask_pyr is not None else None,
-                self.losses.data_ptr(), self._gx_ptrs, self.g_poses.data_ptr(), self._gl_ptrs,
+                self.losses.data_ptr(), self._gx_ptrs, self.g_poses.data_ptr(), self._gl_ptrs, self._gs_ptrs,
                 self.ws.data_ptr())
 
     def run_bound(self, args, stream=None):
@@ -443,15 +447,16 @@ class ViewSynthesisPlan(object):
 
 class _ViewSynthesisLoss(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, plan, tgt, srcs, K_pyr, poses, n_x, *pyr):
-        x_pyr = [_f32(t, 'x_pyr') for t in pyr[:n_x]]
-        rest = [_f32(t, 'pyr') for t in pyr[n_x:]]
+    def forward(ctx, plan, tgt, K_pyr, poses, n_src, n_x, *rest_all):
+        srcs = [_f32(t, 'src') for t in rest_all[:n_src]]
+        x_pyr = [_f32(t, 'x_pyr') for t in rest_all[n_src:n_src + n_x]]
+        rest = [_f32(t, 'pyr') for t in rest_all[n_src + n_x:]]
         logits = rest if plan.mask_mode == _lib.MASK_EXP else None
         mask = rest if plan.mask_mode == _lib.MASK_CONST else None
-        plan.run(_f32(tgt, 'tgt'), [_f32(s, 'src') for s in srcs], x_pyr, _f32(poses, 'poses'), _f32(K_pyr, 'K_pyr'),
-                 logits, mask)
+        plan.run(_f32(tgt, 'tgt'), srcs, x_pyr, _f32(poses, 'poses'), _f32(K_pyr, 'K_pyr'), logits, mask)
         ctx.plan = plan
         ctx.version = plan.version
+        ctx.n_src = n_src
         ctx.n_x = n_x
         ctx.n_rest = len(rest)
         losses = plan.losses.clone()
@@ -465,10 +470,11 @@ class _ViewSynthesisLoss(torch.autograd.Function):
         if plan.version != ctx.version:
             raise RuntimeError('view_synthesis_loss: the plan ran again before this backward; the gradients of '
                                'the earlier forward were overwritten (call backward before the next forward)')
+        g_src = ([g * g_total for g in plan.g_srcs] if plan.g_srcs is not None else [None] * ctx.n_src)
         g_x = [g * g_total for g in plan.g_x]
         g_rest = ([g * g_total for g in plan.g_logits] if plan.mask_mode == _lib.MASK_EXP
                   else [None] * ctx.n_rest)
-        return (None, None, None, None, plan.g_poses * g_total, None) + tuple(g_x) + tuple(g_rest)
+        return (None, None, None, plan.g_poses * g_total, None, None) + tuple(g_src) + tuple(g_x) + tuple(g_rest)
 
 
 _PLANS = {}
@@ -491,12 +497,13 @@ def view_synthesis_loss(tgt, srcs, x_pyr, poses, K_pyr, logits_pyr=None, mask_py
     if C != 3 or len(x_pyr) != S:
         raise ValueError('tgt must be [B,H,W,3] and x_pyr must hold num_scales=%d levels' % S)
     mode = _lib.MASK_EXP if logits_pyr is not None else (_lib.MASK_CONST if mask_pyr is not None else _lib.MASK_NONE)
-    key = (B, H, W, V, mode, tgt.device, tuple(sorted(flags.__dict__.items())))
+    want_src = any(getattr(t, 'requires_grad', False) for t in srcs)
+    key = (B, H, W, V, mode, tgt.device, want_src, tuple(sorted(flags.__dict__.items())))
     plan = _PLANS.get(key)
     if plan is None:
-        plan = _PLANS[key] = ViewSynthesisPlan(B, H, W, V, flags, mode, tgt.device)
+        plan = _PLANS[key] = ViewSynthesisPlan(B, H, W, V, flags, mode, tgt.device, want_src_grad=want_src)
     rest = list(logits_pyr if logits_pyr is not None else (mask_pyr or []))
-    return _ViewSynthesisLoss.apply(plan, tgt, list(srcs), K_pyr, poses, S, *x_pyr, *rest)
+    return _ViewSynthesisLoss.apply(plan, tgt, K_pyr, poses, V, S, *srcs, *x_pyr, *rest)
 
 
 class HostPipeline(object):
