@@ -868,13 +868,13 @@ VSL_DEV int fast_div(int n, int d, float inv_d) {
   return q;
 }
 
-// Persistent blocks, two tile buffers: the cp.async of tile i+1 is in flight while tile i is turned into its
-// output levels, so a block never sits idle waiting for its load.
+// Persistent blocks, three tile buffers: the cp.async of tile i+1 is in flight while tile i is turned into its
+// output levels, so a block never sits idle waiting for its load, and one barrier per tile is enough.
 template <int LOG2F>
 __global__ void __launch_bounds__(kPrepThreads, 4)
 loss_prep_kernel(const PrepImgJob job, const PrepJob prep) {
   constexpr int F = 1 << LOG2F, RB = F > 8 ? F : 8, TW = kPrepPx / RB;
-  __shared__ float4 tile4[2][kPrepPx * 3 / 4];
+  __shared__ float4 tile4[3][kPrepPx * 3 / 4];
   const int B = job.B, H = job.H, W = job.W;
   // launched programmatically dependent on whatever kernel precedes it in the stream (usually the previous step's
   // finalize, or the network that produced the inputs): only the launch latency overlaps, nothing is read before
@@ -965,12 +965,12 @@ loss_prep_kernel(const PrepImgJob job, const PrepJob prep) {
   Tile cur = decode(t);
   stage(cur, reinterpret_cast<float*>(tile4[0]));
   for (int it = 0; t < job.n_tiles; ++it, t += gridDim.x) {
-    const float* tile = reinterpret_cast<const float*>(tile4[it & 1]);
+    const float* tile = reinterpret_cast<const float*>(tile4[it % 3]);
     const int tn = t + gridDim.x;
     Tile nxt = cur;
     if (tn < job.n_tiles) {
       nxt = decode(tn);
-      stage(nxt, reinterpret_cast<float*>(tile4[(it + 1) & 1]));
+      stage(nxt, reinterpret_cast<float*>(tile4[(it + 1) % 3]));
       asm volatile("cp.async.wait_group 1;" ::: "memory");
     } else {
       asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -997,7 +997,7 @@ loss_prep_kernel(const PrepImgJob job, const PrepJob prep) {
       prep_rgba0<TW, RB>(tile, rows, cols, reinterpret_cast<float4*>(d0), st0 / 4);
       prep_levels<LOG2F, TW, RB, true>(tile, rows, cols, dst_of);
     }
-    __syncthreads();   // this buffer is the target of the stage after next
+    // three buffers: the one staged next was last read two tiles ago, before the barrier above -- no second barrier
     cur = nxt;
   }
 }
@@ -1050,6 +1050,7 @@ int check_desc(const VslLossDesc* d) {
   // 32-bit pixel offsets inside one image and thread indices of the prep launch
   VSL_REQUIRE((long long)(d->H + 4) * (d->W + 4) < (1ll << 26), VSL_E_SHAPE);
   VSL_REQUIRE((long long)(d->V + 1) * d->B * (d->H + 4) * (d->W + 4) < (1ll << 31), VSL_E_SHAPE);
+  VSL_REQUIRE((long long)d->B * (d->H + 4) * (d->W + 4) * 2 * (d->V > 2 ? d->V : 2) < (1ll << 31), VSL_E_SHAPE);  // float offsets
   VSL_REQUIRE(d->pose_format >= VSL_POSE_EULER && d->pose_format <= VSL_POSE_MATRIX, VSL_E_FORMAT);
   VSL_REQUIRE(d->mask_mode >= VSL_MASK_NONE && d->mask_mode <= VSL_MASK_CONST, VSL_E_FORMAT);
   VSL_REQUIRE(!(d->want_src_grad && d->exact_coords), VSL_E_UNSUPPORTED);
