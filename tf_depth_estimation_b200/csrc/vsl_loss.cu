@@ -81,6 +81,13 @@ struct LossParams {
   int strips[VSL_MAX_SCALES], bands[VSL_MAX_SCALES];
   int lg_vec4[VSL_MAX_SCALES];     // logits / g_logits of this scale are 16-byte aligned (and V is even)
   float wstep[VSL_MAX_SCALES], hstep[VSL_MAX_SCALES];  // meshgrid linspace steps 2/(W-1), 2/(H-1) in fp32
+  // per-scale constants precomputed on the host: under register pressure the compiler re-derives loop invariants
+  // inside the row loop, and re-loading one word from the constant bank is all that should cost
+  int Hs[VSL_MAX_SCALES], Ws[VSL_MAX_SCALES];
+  int stride4[VSL_MAX_SCALES];     // float4 per row of a zero-bordered RGBA level
+  int plane4[VSL_MAX_SCALES];      // float4 per image of it
+  int coff[VSL_MAX_SCALES];        // (kPad * stride4 + kPad) - magic bias * (stride4 + 1), wrapping: see tap_issue
+  float Wf[VSL_MAX_SCALES], Hf[VSL_MAX_SCALES];
 };
 
 template <int V> struct NT { static constexpr int value = 3 + 12 * V; };
@@ -218,16 +225,16 @@ loss_fused_kernel(const LossParams P) {
   const int rem = tile - P.item_begin[s];
   const int b = rem / per_b, r2 = rem - b * per_b;
   const int band = r2 / strips, strip = r2 - band * strips;
-  const int H = P.H >> s, W = P.W >> s;
+  const int H = P.Hs[s], W = P.Ws[s];
   const int y_base = band * kRH, x_base = strip * 32;
   const int rows = min(kRH, H - y_base);
   const int x = x_base + lane;
   const bool act = x < W;
-  const size_t img_off = (size_t)b * H * W;
+  const int pix0 = b * H * W;                  // first pixel of this image inside the level (32-bit: check_desc)
   const bool use_lg = P.mask_mode == VSL_MASK_EXP;
 
   // ---- 1. the x tile (+halo), zero outside the image, and this image's transforms
-  const float* __restrict__ xs = P.x[s] + img_off;
+  const float* __restrict__ xs = P.x[s] + pix0;
   {
     // 4-byte cp.async with a zero source size outside the image: every element of the tile is in flight at
     // once and no register holds it on the way
@@ -281,11 +288,11 @@ loss_fused_kernel(const LossParams P) {
   const int xl = min(x, W - 1);
   const float gx = grid_coord(xl, W, P.wstep[s]);
   const float hstep = P.hstep[s];
-  const float Wf = (float)W, Hf = (float)H;
-  const int stride4 = W + 2 * kPad;
-  // corner offset = (iy + kPad) * stride4 + (ix + kPad) with iy, ix still carrying the magic bias
-  const int coff = (int)((unsigned)(kPad * stride4 + kPad) - kMagicBits * (unsigned)(stride4 + 1));
-  const size_t src_off = (size_t)b * (H + 2 * kPad) * stride4;
+  const float Wf = P.Wf[s], Hf = P.Hf[s];
+  const int stride4 = P.stride4[s];
+  // corner offset inside the level = b * plane + (iy + kPad) * stride4 + (ix + kPad), with iy, ix still carrying
+  // the magic bias (P.coff removes it, wrapping)
+  const int coff = P.coff[s] + b * P.plane4[s];
   const float cpix = P.cpix[s], cexp = P.cexp[s];
 
   // Everything above read only the caller's inputs.  The launch is programmatically dependent on the prep launch
@@ -338,11 +345,12 @@ loss_fused_kernel(const LossParams P) {
     if (lane == 0) c11 = shc[1 * 2 + 1];
   }
 
-  const float* __restrict__ tgt_img = P.tgt[s] + img_off * 3;
-  const float* __restrict__ lg_img = use_lg ? P.logits[s] + img_off * (2 * V) : nullptr;
-  float* __restrict__ glg_img = use_lg ? P.g_logits[s] + img_off * (2 * V) : nullptr;
-  const float* __restrict__ mk_img = P.mask_mode == VSL_MASK_CONST ? P.mask[s] + img_off : nullptr;
-  float* __restrict__ gx_img = P.g_x[s] + img_off;
+  // level base pointers (whole level, not this image: the image offset rides in the 32-bit pixel index)
+  const float* __restrict__ tgt_img = P.tgt[s];
+  const float* __restrict__ lg_img = use_lg ? P.logits[s] : nullptr;
+  float* __restrict__ glg_img = use_lg ? P.g_logits[s] : nullptr;
+  const float* __restrict__ mk_img = P.mask_mode == VSL_MASK_CONST ? P.mask[s] : nullptr;
+  float* __restrict__ gx_img = P.g_x[s];
   const bool lg4 = (V % 2 == 0) && P.lg_vec4[s] != 0;
   const int smooth_inv = P.smooth_on_inverse, depth_inv = P.depth_is_inverse;
 
@@ -393,7 +401,7 @@ loss_fused_kernel(const LossParams P) {
   // these load groups share, no wait ever lands on a load that was only just issued.
   struct Keep { float E, u0, u1, u2; };         // what phase 2 needs of a view: sum|e| and dL/du up to the factor cpix * m
   Tap tap[V];
-  int pofs = y_base * W + xl;                   // pixel offset inside this image
+  int pofs = pix0 + y_base * W + xl;            // pixel index inside the level
 
   auto row = [&](Stream& cur, Stream& nxt, Geo& gc, Geo& gn, int r) {
     const bool has_next = r + 1 < rows;
@@ -442,7 +450,7 @@ loss_fused_kernel(const LossParams P) {
           }
         }
         if (act) {
-          float4* g = P.gsrc[v][s] + src_off + t.off;
+          float4* g = P.gsrc[v][s] + t.off;
           const float km = cpix * m;
           const float k00 = km * w00, k10 = km * w10, k01 = km * w01, k11 = km * w11;
           asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(g), "f"(k00 * sgc[0]), "f"(k00 * sgc[1]),
@@ -461,7 +469,7 @@ loss_fused_kernel(const LossParams P) {
       keep[v].E = E; keep[v].u0 = dx * t.rz; keep[v].u1 = dy * t.rz;
       keep[v].u2 = -(t.qx * keep[v].u0 + t.qy * keep[v].u1);
       if (has_next)
-        tap_issue<EXACT>(t, Pm[v], gn.c0, gn.c1, gn.c2, P.src[v][s] + src_off, stride4, coff, Wf, Hf);
+        tap_issue<EXACT>(t, Pm[v], gn.c0, gn.c1, gn.c2, P.src[v][s], stride4, coff, Wf, Hf);
     }
     if (has_next) load_stream(nxt, pofs + W);
 
@@ -563,7 +571,7 @@ loss_fused_kernel(const LossParams P) {
     make_geo(g0, 0);
 #pragma unroll
     for (int v = 0; v < V; ++v)
-      tap_issue<EXACT>(tap[v], Pm[v], g0.c0, g0.c1, g0.c2, P.src[v][s] + src_off, stride4, coff, Wf, Hf);
+      tap_issue<EXACT>(tap[v], Pm[v], g0.c0, g0.c1, g0.c2, P.src[v][s], stride4, coff, Wf, Hf);
     for (int r = 0; r < rows; r += 2) {
       row(st0, st1, g0, g1, r);
       if (r + 1 < rows) row(st1, st0, g1, g0, r + 1);
@@ -1222,6 +1230,11 @@ int vsl_loss_fwd_bwd(const VslLossDesc* d, const float* tgt, const float* const*
       P.gsrc[v][s] = d->want_src_grad ? gsrc_pyr + L.src_view * (size_t)v + L.src_off[s] : nullptr;
     }
     P.strips[s] = L.strips[s]; P.bands[s] = L.bands[s];
+    P.Hs[s] = H; P.Ws[s] = W;
+    P.stride4[s] = W + 2 * kPad;
+    P.plane4[s] = (H + 2 * kPad) * (W + 2 * kPad);
+    P.coff[s] = (int)((unsigned)(kPad * P.stride4[s] + kPad) - kMagicBits * (unsigned)(P.stride4[s] + 1));
+    P.Wf[s] = (float)W; P.Hf[s] = (float)H;
     P.wstep[s] = 2.0f / (float)(W - 1);  // fp32 division, as grid_step() does on the device
     P.hstep[s] = 2.0f / (float)(H - 1);
     const double npx = (double)d->B * H * W;
