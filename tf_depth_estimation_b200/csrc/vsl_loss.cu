@@ -76,7 +76,9 @@ struct LossParams {
   float* partials;                 // [n_items][NT]
   float cpix[VSL_MAX_SCALES];      // loss_scale * data_weight_s / (B Hs Ws 3)
   float cexp[VSL_MAX_SCALES];      // loss_scale * explain_reg_weight / (B Hs Ws)
-  float csm[VSL_MAX_SCALES][4];    // loss_scale * smooth_weight / 2^s / count_k   (xx, xy, yx, yy)
+  // loss_scale * smooth_weight / 2^s / count_k, one flat array per second difference (a per-scale constant the
+  // compiler re-loads inside the row loop should be ONE indexed constant-bank load)
+  float cxx[VSL_MAX_SCALES], cxy[VSL_MAX_SCALES], cyx[VSL_MAX_SCALES], cyy[VSL_MAX_SCALES];
   int item_begin[VSL_MAX_SCALES + 1];
   int strips[VSL_MAX_SCALES], bands[VSL_MAX_SCALES];
   int lg_vec4[VSL_MAX_SCALES];     // logits / g_logits of this scale are 16-byte aligned (and V is even)
@@ -269,7 +271,7 @@ loss_fused_kernel(const LossParams P) {
   // ---- 2. smoothness of the two columns LEFT of the tile: the weighted signs of their xx and xy/yx second
   // differences, which the gradient of columns 0 and 1 needs.  Everything else of the smoothness term is
   // evaluated in the row loop, lane = column: own column in registers, the two to the left by shuffle.
-  const float cxx = P.csm[s][0], cxy = P.csm[s][1], cyx = P.csm[s][2], cyy = P.csm[s][3];
+  const float cxx = P.cxx[s], cxy = P.cxy[s], cyx = P.cyx[s], cyy = P.cyy[s];
   for (int i = lane; i < kOH * 2; i += 32) {
     const int oy = i >> 1, ox = i & 1;
     float a, bb, c, sm;
@@ -1242,10 +1244,10 @@ int vsl_loss_fwd_bwd(const VslLossDesc* d, const float* tgt, const float* const*
     P.cpix[s] = (float)((double)d->loss_scale * dw / (npx * 3.0));
     P.cexp[s] = (float)((double)d->loss_scale * (double)d->explain_reg_weight / npx);
     const double sw = (double)d->loss_scale * (double)d->smooth_weight / (double)(1 << s);
-    P.csm[s][0] = (float)(sw / ((double)d->B * H * (W - 2)));
-    P.csm[s][1] = (float)(sw / ((double)d->B * (H - 1) * (W - 1)));
-    P.csm[s][2] = P.csm[s][1];
-    P.csm[s][3] = (float)(sw / ((double)d->B * (H - 2) * W));
+    P.cxx[s] = (float)(sw / ((double)d->B * H * (W - 2)));
+    P.cxy[s] = (float)(sw / ((double)d->B * (H - 1) * (W - 1)));
+    P.cyx[s] = P.cxy[s];
+    P.cyy[s] = (float)(sw / ((double)d->B * (H - 2) * W));
   }
 
   // 0. (only with want_src_grad) the gradient levels start from zero
