@@ -1,5 +1,5 @@
 import sys, torch
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 from tf_depth_estimation_b200 import ops, synth, _lib
 dev = torch.device('cuda:0')
 cu = lambda t: t.to(dev).contiguous()
