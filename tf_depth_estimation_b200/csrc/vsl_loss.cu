@@ -495,13 +495,14 @@ loss_fused_kernel(const LossParams P) {
       b2 = b1; b1 = b0; c10 = c00; c11 = c01;
     }
 
-    float g_d = 0.f;
+    // mask values m (explainability softmax or constant), the regulariser and d/dlogits -- all views inside ONE
+    // uniform branch, so their dependent MUFU chains interleave instead of running one after the other
+    float mv[V];
+    if (use_lg) {
 #pragma unroll
-    for (int v = 0; v < V; ++v) {
-      // mask value m (explainability softmax or constant) and the regulariser
-      float m = cur.mc, p0 = 0.f, p1 = 0.f;
-      if (use_lg) {
+      for (int v = 0; v < V; ++v) {
         const float l0 = cur.lg[2 * v], l1 = cur.lg[2 * v + 1];
+        float p0, p1;
         if (EXACT) {
           const float mx = fmaxf(l0, l1);
           const float e0 = expf(l0 - mx), e1 = expf(l1 - mx), se = e0 + e1;
@@ -514,14 +515,19 @@ loss_fused_kernel(const LossParams P) {
           p1 = z >= 0.f ? small : big;
           exp_sum += fmaf(lg2_fast(se), 0.6931471805599453f, fmaxf(z, 0.f));
         }
-        m = p1;
-      }
-      const float E = keep[v].E;
-      pix_sum = fmaf(m, E, pix_sum);
-      if (use_lg) {
-        const float g0 = p0 * (cexp - cpix * E * p1);
+        mv[v] = p1;
+        const float g0 = p0 * (cexp - cpix * keep[v].E * p1);
         cur.lg[2 * v] = g0; cur.lg[2 * v + 1] = -g0;
       }
+    } else {
+#pragma unroll
+      for (int v = 0; v < V; ++v) mv[v] = cur.mc;
+    }
+    float g_d = 0.f;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const float m = mv[v];
+      pix_sum = fmaf(m, keep[v].E, pix_sum);
       const float k = cpix * m;
       const float du0 = keep[v].u0 * k, du1 = keep[v].u1 * k, du2 = keep[v].u2 * k;
       const float* pp = Pm[v];
