@@ -42,3 +42,23 @@ def test_pipeline_matches_plan_over_many_steps():
         assert all(torch.equal(a, b.cpu()) for a, b in zip(gl, plan.g_logits)), i
     h2d, d2h = pipe.bytes_per_step()
     assert h2d == 4 * sum(t.numel() for t in pipe._flat(hosts[0])) and d2h > 0
+
+
+def test_pipeline_single_copy_arena_matches_per_tensor_copies():
+    """host_inputs(): the same step fed from one pinned arena (one H2D copy) and from separate pinned tensors."""
+    B, H, W, S, V = 2, 32, 64, 3, 2
+    flags = ops.LossFlags(num_scales=S)
+    pipe = ops.HostPipeline(B, H, W, V, flags, _lib.MASK_EXP, DEV)
+    d = synth.make_snippets(B, H, W, S=S, V=V, seed=321)
+    sep = _host_inputs(d)
+    arena = pipe.host_inputs()
+    arena['tgt'].copy_(d['tgt']); arena['poses'].copy_(d['poses']); arena['Kp'].copy_(d['K_pyr'])
+    for dst, src in zip(arena['srcs'] + arena['xs'] + arena['lgs'], d['srcs'] + d['disp_pyr'] + d['logits_pyr']):
+        dst.copy_(src)
+    outs = []
+    for h in (sep, arena):
+        l, gx, gp, gl = pipe.result(pipe.submit(h))
+        outs.append((l.clone(), [g.clone() for g in gx], gp.clone(), [g.clone() for g in gl]))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][2], outs[1][2])
+    assert all(torch.equal(a, b) for a, b in zip(outs[0][1] + outs[0][3], outs[1][1] + outs[1][3]))
+    assert float(outs[0][0].abs().sum()) > 0

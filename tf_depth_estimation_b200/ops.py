@@ -388,6 +388,27 @@ class LossFlags(object):
         self.__dict__.update(kw)
 
 
+def _arena(shapes, device=None, pinned=False):
+    """One float32 buffer carved into 256-byte aligned views of the given shapes -> (buffer, [views]).  Lets a whole
+    set of tensors cross PCIe as ONE copy."""
+    offs, n = [], 0
+    for shp in shapes:
+        offs.append(n)
+        cnt = 1
+        for d in shp:
+            cnt *= d
+        n += (cnt + 63) // 64 * 64
+    buf = torch.empty(max(n, 64), dtype=torch.float32).pin_memory() if pinned else \
+        torch.empty(max(n, 64), dtype=torch.float32, device=device)
+    views = []
+    for shp, o in zip(shapes, offs):
+        cnt = 1
+        for d in shp:
+            cnt *= d
+        views.append(buf[o:o + cnt].view(*shp))
+    return buf, views
+
+
 class ViewSynthesisPlan(object):
     """Pre-allocated state for repeated fused-loss steps at one shape: workspace, gradient buffers and the
     pointer tables of the C call.  One instance per (shape, flags); not thread-safe."""
@@ -408,11 +429,18 @@ class ViewSynthesisPlan(object):
         if nbytes == 0:
             raise ValueError('unsupported loss shape B=%d H=%d W=%d S=%d V=%d' % (B, H, W, S, V))
         self.ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
-        self.losses = torch.zeros(3, device=device)
-        self.g_x = [torch.empty(B, H >> s, W >> s, 1, device=device) for s in range(S)]
-        self.g_poses = torch.empty((B, V, 4, 4) if self.fmt == 2 else (B, V, 6), device=device)
-        self.g_logits = ([torch.empty(B, H >> s, W >> s, 2 * V, device=device) for s in range(S)]
-                         if mask_mode == _lib.MASK_EXP else None)
+        # every output of a step lives in one arena, so a host pipeline can fetch them with a single copy
+        pose_shape = (B, V, 4, 4) if self.fmt == 2 else (B, V, 6)
+        shapes = [(3,)] + [(B, H >> s, W >> s, 1) for s in range(S)] + [pose_shape]
+        if mask_mode == _lib.MASK_EXP:
+            shapes += [(B, H >> s, W >> s, 2 * V) for s in range(S)]
+        self.out_arena, views = _arena(shapes, device=device)
+        self.out_shapes = shapes
+        self.losses = views[0]
+        self.losses.zero_()
+        self.g_x = views[1:1 + S]
+        self.g_poses = views[1 + S]
+        self.g_logits = views[2 + S:2 + 2 * S] if mask_mode == _lib.MASK_EXP else None
         # d/d(source images): produced only on request (an extra atomic scatter + fold-back pass)
         self.g_srcs = [torch.empty(B, H, W, 3, device=device) for _ in range(V)] if self.want_src_grad else None
         self._gs_ptrs = ptr_array([t.data_ptr() for t in self.g_srcs]) if self.g_srcs else None
@@ -522,16 +550,29 @@ class HostPipeline(object):
         self.plans = [ViewSynthesisPlan(B, H, W, V, flags, mask_mode, device, loss_scale) for _ in range(self.DEPTH)]
         S = flags.num_scales
         pose_shape = (B, V, 4, 4) if self.plans[0].fmt == 2 else (B, V, 6)
-        mk = lambda *shape: torch.empty(*shape, device=device)
-        self.dev_in = [dict(tgt=mk(B, H, W, 3), srcs=[mk(B, H, W, 3) for _ in range(V)],
-                            xs=[mk(B, H >> s, W >> s, 1) for s in range(S)], poses=mk(*pose_shape), Kp=mk(B, S, 3, 3),
-                            lgs=([mk(B, H >> s, W >> s, 2 * V) for s in range(S)] if mask_mode == _lib.MASK_EXP else None))
-                       for _ in range(self.DEPTH)]
+        in_shapes = ([(B, H, W, 3)] + [(B, H, W, 3)] * V + [(B, H >> s, W >> s, 1) for s in range(S)] +
+                     [pose_shape, (B, S, 3, 3)] +
+                     ([(B, H >> s, W >> s, 2 * V) for s in range(S)] if mask_mode == _lib.MASK_EXP else []))
+
+        def carve(views):
+            return dict(tgt=views[0], srcs=views[1:1 + V], xs=views[1 + V:1 + V + S], poses=views[1 + V + S],
+                        Kp=views[2 + V + S], lgs=(views[3 + V + S:3 + V + 2 * S] if mask_mode == _lib.MASK_EXP else None))
+        self._in_shapes, self._carve = in_shapes, carve
+        # device inputs of a slot = one arena; host inputs allocated by host_inputs() mirror it, so a step's
+        # inputs cross PCIe as ONE copy (and its outputs likewise, from the plan's output arena)
+        self.dev_in_arena, self.dev_in = [], []
+        for _ in range(self.DEPTH):
+            buf, views = _arena(in_shapes, device=device)
+            self.dev_in_arena.append(buf)
+            self.dev_in.append(carve(views))
         self.bound = [p.bind(d['tgt'], d['srcs'], d['xs'], d['poses'], d['Kp'], d['lgs'])
                       for p, d in zip(self.plans, self.dev_in)]
-        pin = lambda t: torch.empty(t.shape, dtype=t.dtype).pin_memory()
-        self.host_out = [dict(losses=pin(p.losses), g_x=[pin(g) for g in p.g_x], g_poses=pin(p.g_poses),
-                              g_lgs=[pin(g) for g in (p.g_logits or [])]) for p in self.plans]
+        self.host_out_arena, self.host_out = [], []
+        for p in self.plans:
+            buf, views = _arena(p.out_shapes, pinned=True)
+            self.host_out_arena.append(buf)
+            self.host_out.append(dict(losses=views[0], g_x=views[1:1 + S], g_poses=views[1 + S],
+                                      g_lgs=(views[2 + S:2 + 2 * S] if mask_mode == _lib.MASK_EXP else [])))
         self.s_in, self.s_comp, self.s_out = (torch.cuda.Stream(device=device) for _ in range(3))
         ev = lambda: [torch.cuda.Event() for _ in range(self.DEPTH)]
         self.ev_in, self.ev_comp, self.ev_out = ev(), ev(), ev()
@@ -547,6 +588,14 @@ class HostPipeline(object):
             out.extend(v if isinstance(v, (list, tuple)) else [v])
         return out
 
+    def host_inputs(self):
+        """A dict of pinned host tensors (tgt, srcs, xs, poses, Kp, lgs) that are views into ONE pinned arena laid out
+        like the device-side inputs: submit() then moves a step's inputs with a single copy.  Fill them in place."""
+        buf, views = _arena(self._in_shapes, pinned=True)
+        d = self._carve(views)
+        d['_arena'] = buf
+        return d
+
     def bytes_per_step(self):
         h2d = sum(t.numel() * 4 for t in self._flat(self.dev_in[0]))
         o = self.host_out[0]
@@ -560,8 +609,11 @@ class HostPipeline(object):
         with torch.cuda.stream(self.s_in):
             if not first_use:
                 self.s_in.wait_event(self.ev_comp[k])          # step-2's kernels have consumed these inputs
-            for src, dst in zip(self._flat(host_inputs), self._flat(dev)):
-                dst.copy_(src, non_blocking=True)
+            if host_inputs.get('_arena') is not None:
+                self.dev_in_arena[k].copy_(host_inputs['_arena'], non_blocking=True)
+            else:
+                for src, dst in zip(self._flat(host_inputs), self._flat(dev)):
+                    dst.copy_(src, non_blocking=True)
             self.ev_in[k].record(self.s_in)
         with torch.cuda.stream(self.s_comp):
             self.s_comp.wait_event(self.ev_in[k])
@@ -571,10 +623,7 @@ class HostPipeline(object):
             self.ev_comp[k].record(self.s_comp)
         with torch.cuda.stream(self.s_out):
             self.s_out.wait_event(self.ev_comp[k])
-            out['losses'].copy_(plan.losses, non_blocking=True)
-            for src, dst in zip(plan.g_x + [plan.g_poses] + (plan.g_logits or []),
-                                out['g_x'] + [out['g_poses']] + out['g_lgs']):
-                dst.copy_(src, non_blocking=True)
+            self.host_out_arena[k].copy_(plan.out_arena, non_blocking=True)
             self.ev_out[k].record(self.s_out)
         self.step += 1
         return k
