@@ -154,6 +154,11 @@ typedef struct {
                             sample positions to the oracle for matrix poses); 0: FMA + MUFU fast path */
   int want_src_grad;     /* 1: also produce d/d(source images) into g_srcs (atomic scatter: the one output whose
                             summation order is not deterministic); needs exact_coords == 0 */
+  int x_is_logit;        /* 1: x_pyr holds the disparity head's PRE-activation output; the kernel applies
+                            disp = disp_scale * sigmoid(x) + disp_min (nets_optflow_depth.py:8-9,143-144) on load and
+                            its derivative on store, so the head's elementwise ops and their backward disappear */
+  float disp_scale, disp_min;
+  int reserved_;
   void* ev_main_begin;   /* optional cudaEvent_t pair recorded on `stream` immediately around the fused  */
   void* ev_main_end;     /* loss kernel (launch 3 of the step) so a caller can time it in situ; NULL = off */
 } VslLossDesc;

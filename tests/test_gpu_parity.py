@@ -441,3 +441,39 @@ def test_fused_source_image_gradient_against_oracle():
     with pytest.raises(Exception):
         ops.view_synthesis_loss(cu(d['tgt']), srcs, xs, ps, cu(d['K_pyr']), logits_pyr=lgs,
                                 flags=ops.LossFlags(num_scales=S, exact_coords=True))
+
+
+@pytest.mark.parametrize('smooth_inv,depth_inv', [(False, True), (True, False), (True, True)])
+def test_fused_disparity_head_on_load(smooth_inv, depth_inv):
+    """x_is_logit: the kernel consumes the disparity head's pre-activation output and applies
+    DISP_SCALING * sigmoid + MIN_DISP (nets_optflow_depth.py:8-9,143-144) on load and its derivative on store;
+    against the oracle fed with the activated disparity, gradient taken through the sigmoid by float64 autograd."""
+    B, H, W, S, V = 2, 32, 104, 3, 2
+    d = synth.make_snippets(B, H, W, S=S, V=V, seed=55)
+    g = torch.Generator().manual_seed(5)
+    raw = [0.8 * torch.randn(B, H >> s, W >> s, 1, generator=g) for s in range(S)]
+    scale, mn = 4.0, 0.01
+    kw = dict(num_scales=S, smooth_on_inverse=smooth_inv, depth_is_inverse=depth_inv)
+    for exact in (False, True):
+        flags = ops.LossFlags(x_is_logit=True, disp_scaling=scale, min_disp=mn, exact_coords=exact, **kw)
+        xs = [cu(x, True) for x in raw]
+        ps = cu(d['poses'], True)
+        lgs = [cu(l, True) for l in d['logits_pyr']]
+        total, losses = ops.view_synthesis_loss(cu(d['tgt']), [cu(s) for s in d['srcs']], xs, ps, cu(d['K_pyr']),
+                                                logits_pyr=lgs, flags=flags)
+        total.backward()
+        oraw = [x.double().requires_grad_() for x in raw]
+        odisp = [scale * torch.sigmoid(x) + mn for x in oraw]
+        op_ = d['poses'].double().requires_grad_()
+        ol = [l.double().requires_grad_() for l in d['logits_pyr']]
+        ref = O.view_synthesis_loss(d['tgt'].double(), [s.double() for s in d['srcs']], odisp, op_, d['K_pyr'].double(),
+                                    ol, None, O.LossFlags(**kw))
+        sum(ref).backward()
+        for got, want in zip(losses.tolist(), ref):
+            assert abs(got - float(want)) <= 1e-5 * abs(float(want)) + 1e-9, (exact, got, float(want))
+        assert rel_err(ps.grad, op_.grad) <= 1e-4
+        disp32 = [(scale * torch.sigmoid(x) + mn) for x in raw]
+        ok = smooth_pixels(d['tgt'], d['srcs'], disp32, d['poses'], d['K_pyr'], ops.LossFlags(**kw))
+        for s in range(S):
+            all_views = torch.stack(ok[s]).all(0)
+            assert masked_rel_err(xs[s].grad, oraw[s].grad, all_views.unsqueeze(3)) <= 1e-4, (exact, s)

@@ -64,6 +64,8 @@ constexpr unsigned kMagicBits = 0x4B400000u;
 struct LossParams {
   int B, H, W, S, V;
   int mask_mode, depth_is_inverse, smooth_on_inverse;
+  int x_is_logit;                  // x = pre-activation of the disparity head: disp = disp_scale * sigmoid(x) + disp_min
+  float disp_scale, disp_min;
   const float* tgt[VSL_MAX_SCALES];                    // RGB
   const float4* src[VSL_MAX_VIEWS][VSL_MAX_SCALES];    // zero-bordered RGBA [B][Hs+4][Ws+4]
   float4* gsrc[VSL_MAX_VIEWS][VSL_MAX_SCALES];         // d/d(those levels), same layout (only with DSRC)
@@ -254,6 +256,20 @@ loss_fused_kernel(const LossParams P) {
     }
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
     __syncwarp();
+    if (P.x_is_logit != 0) {          // disparity head on load (nets_optflow_depth.py:143-144); outside stays 0
+      int ty = 0, tc = lane;
+      for (int i = lane; i < kQH * kQS; i += 32) {
+        const int gy = y_base - kHalo + ty, gx = x_base - kHalo + tc;
+        if ((unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W) {
+          const float v = qt[i];
+          const float sg = EXACT ? 1.0f / (1.0f + expf(-v)) : rcp_fast(1.0f + ex2_fast(-1.4426950408889634f * v));
+          qt[i] = fmaf(P.disp_scale, sg, P.disp_min);
+        }
+        tc += 32;
+        if (tc >= kQS) { tc -= kQS; ++ty; }
+      }
+      __syncwarp();
+    }
     if (P.smooth_on_inverse != 0) {   // the smoothness term lives on 1/x (train_depth_then_cam_lr.py:217)
       if (!P.depth_is_inverse) {      // ... while the warp wants x itself: keep the tile's centre rows
         for (int r = 0; r < kRH; ++r) sxc[r * 32 + lane] = qt[(r + kHalo) * kQS + lane + kHalo];
@@ -554,7 +570,15 @@ loss_fused_kernel(const LossParams P) {
       } else if (depth_inv) {
         dd_dx = -gc.d * gc.d;
       }
-      __stcs(gx_img + pofs, g_d * dd_dx + g_q * dq_dx);
+      float g_out = g_d * dd_dx + g_q * dq_dx;
+      if (P.x_is_logit != 0) {          // d(disp)/dx = scale * s (1 - s), s recovered from disp itself
+        float disp;
+        if (smooth_inv) disp = depth_inv ? rcp_fast(qt[(r + kHalo) * kQS + (xl - x_base) + kHalo]) : gc.d;
+        else disp = qt[(r + kHalo) * kQS + (xl - x_base) + kHalo];
+        const float u = disp - P.disp_min;
+        g_out *= u * (P.disp_scale - u) * rcp_fast(P.disp_scale);
+      }
+      __stcs(gx_img + pofs, g_out);
       if (use_lg) {
         if (lg4) {
 #pragma unroll
@@ -1070,6 +1094,7 @@ int check_desc(const VslLossDesc* d) {
   VSL_REQUIRE(d->pose_format >= VSL_POSE_EULER && d->pose_format <= VSL_POSE_MATRIX, VSL_E_FORMAT);
   VSL_REQUIRE(d->mask_mode >= VSL_MASK_NONE && d->mask_mode <= VSL_MASK_CONST, VSL_E_FORMAT);
   VSL_REQUIRE(!(d->want_src_grad && d->exact_coords), VSL_E_UNSUPPORTED);
+  VSL_REQUIRE(!d->x_is_logit || d->disp_scale > 0.f, VSL_E_UNSUPPORTED);
   return VSL_OK;
 }
 
@@ -1207,6 +1232,7 @@ int vsl_loss_fwd_bwd(const VslLossDesc* d, const float* tgt, const float* const*
   LossParams P;
   P.B = d->B; P.H = d->H; P.W = d->W; P.S = d->S; P.V = d->V;
   P.mask_mode = d->mask_mode; P.depth_is_inverse = d->depth_is_inverse; P.smooth_on_inverse = d->smooth_on_inverse;
+  P.x_is_logit = d->x_is_logit; P.disp_scale = d->disp_scale; P.disp_min = d->disp_min;
   P.xf = xf;
   P.partials = reinterpret_cast<float*>(base + L.partials);
   for (int s = 0; s <= d->S; ++s) P.item_begin[s] = L.item_begin[s];

@@ -385,6 +385,11 @@ class LossFlags(object):
         self.depth_is_inverse = True     # warp depth = 1/x (train.py:128)
         self.smooth_on_inverse = False   # smooth(1/x) (train_depth_then_cam_lr.py:217)
         self.exact_coords = False        # True: reference rounding sequence in the fused kernel (slower)
+        # x_pyr = pre-activation output of the disparity head; the kernel applies disp_scaling * sigmoid + min_disp
+        # (nets_optflow_depth.py:8-9,143-144) and its derivative itself
+        self.x_is_logit = False
+        self.disp_scaling = 4.0
+        self.min_disp = 0.0
         self.__dict__.update(kw)
 
 
@@ -424,7 +429,9 @@ class ViewSynthesisPlan(object):
                                 int(flags.depth_is_inverse), int(flags.smooth_on_inverse),
                                 float(flags.data_weight), float(flags.smooth_weight),
                                 float(flags.explain_reg_weight), float(loss_scale),
-                                int(getattr(flags, 'exact_coords', False)), int(self.want_src_grad), None, None)
+                                int(getattr(flags, 'exact_coords', False)), int(self.want_src_grad),
+                                int(getattr(flags, 'x_is_logit', False)), float(getattr(flags, 'disp_scaling', 4.0)),
+                                float(getattr(flags, 'min_disp', 0.0)), 0, None, None)
         nbytes = lib.vsl_loss_ws_bytes(self.desc)
         if nbytes == 0:
             raise ValueError('unsupported loss shape B=%d H=%d W=%d S=%d V=%d' % (B, H, W, S, V))
