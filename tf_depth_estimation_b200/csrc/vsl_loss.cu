@@ -9,20 +9,21 @@
 //                           zeros all round); K_s^-1 and P = K4_s . T_v per (scale, view, batch) ride along.
 //   2. loss_fused_kernel    every scale and view in ONE grid.  A WARP owns a tile of 32 columns x kRH rows
 //                           of one image at one scale and never talks to another warp (no block barrier):
-//        smoothness: the warp stages x (+2 halo) in its slice of shared memory, evaluates the four second
-//        differences each element owns ONCE and publishes their weighted signs; then it walks down the
-//        rows, lane = column: smoothness gradient gathered from the published signs (vertical neighbours
-//        carried in registers), back-projection, and per view projection, bilinear gather, L1 against the
-//        target, explainability / validity mask, softmax cross-entropy regulariser -- and, because the loss
-//        is a weighted sum of means whose upstream gradient is known (loss_scale), d/dx and d/dlogits are
-//        written in the same pass and dP = sum du (x) [cam;1] is accumulated in registers and reduced once
-//        per tile with a shuffle butterfly.  No full-resolution intermediate is ever written.
+//        it stages x (+2 halo) in its slice of shared memory, then walks down the rows, lane = column.  Per
+//        pixel: the four second differences the element owns (smoothness loss) and the gradient of the 10
+//        stencils it is part of (own column carried in registers, left neighbours by shuffle);
+//        back-projection; per view projection, bilinear gather, L1 against the target, explainability /
+//        validity mask, softmax cross-entropy regulariser -- and, because the loss is a weighted sum of means
+//        whose upstream gradient is known (loss_scale), d/dx and d/dlogits are written in the same pass and
+//        dP = sum du (x) [cam;1] is accumulated in registers and reduced once per tile with a shuffle
+//        butterfly.  No full-resolution intermediate is ever written.  The row loop is software-pipelined:
+//        the gathers and streamed operands of row r+1 are in flight while row r is computed.
 //   3. loss_finalize_kernel fixed-order reduction of the tile partials (deterministic), dT = K4^T dP summed
 //                           over scales, pose chain rule, the three loss scalars.
 //
-// Why the zero-bordered RGBA copy of the sources: the gather is the L1-throughput hot spot.  With packed
-// RGB a corner is three scalar loads whose 32 lanes straddle four cache lines each (12 loads, ~54 L1
-// wavefronts per pixel-view); with one pixel = one aligned float4 it is 4 loads / ~18 wavefronts.  The
+// Why the zero-bordered RGBA copy of the sources: the kernel is instruction-bound and the gather is its
+// most expensive part.  With packed RGB a corner is three scalar loads at a 12-byte stride (12 loads per
+// pixel-view) plus the sampler's mask logic; with one pixel = one aligned float4 it is 4 loads.  The
 // border implements the sampler's zero padding (utils.py:266-270) in the DATA: a corner outside the image
 // reads zeros, so neither the value nor d/dx, d/dy needs the four "corner == clipped corner" masks, and
 // coordinates are simply clamped to [-2, size] (where everything in reach is zero) before the floor.
@@ -33,7 +34,7 @@
 #include <type_traits>
 
 #include "vsl_common.cuh"
-// Part of the single translation unit vsl_lib.cu (prep_one / PrepJob / row_sums / PyrLevel come from vsl_ops.cu).
+// Part of the single translation unit vsl_lib.cu (prep_one / PrepJob come from vsl_ops.cu).
 
 namespace vsl {
 
@@ -56,7 +57,6 @@ constexpr int kHalo = 2;
 constexpr int kQH = kRH + 2 * kHalo;            // rows of x held per tile
 constexpr int kQS = 32 + 2 * kHalo;             // 36 columns of x
 constexpr int kOH = kRH + kHalo;                // owner rows: tile + 2 above
-constexpr int kOW = 32 + kHalo;                 // owner columns: tile + 2 to the left
 constexpr int kPad = 2;                         // zero border (pixels) of the RGBA source levels
 constexpr float kMagic = 12582912.0f;           // 1.5 * 2^23
 constexpr unsigned kMagicBits = 0x4B400000u;
