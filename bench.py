@@ -267,11 +267,16 @@ def run_ours(args):
     # neighbouring steps overlap on three streams
     pipe = ops.HostPipeline(B, H, W, V, flags, _lib.MASK_EXP, dev, loss_scale=vdist.local_loss_scale(B, B * world))
     h_in = pipe.host_inputs()          # pinned host tensors carved from one arena: a step's inputs move as ONE copy
-    h_in['tgt'].copy_(host['tgt']); h_in['poses'].copy_(host['poses']); h_in['Kp'].copy_(host['K_pyr'])
-    for dst, src in zip(h_in['srcs'] + h_in['xs'] + h_in['lgs'], host['srcs'] + host['disp_pyr'] + host['logits_pyr']):
-        dst.copy_(src)
+    if os.environ.get('VSL_E2E_SEPARATE'):   # experiment switch: one pinned tensor and one copy per input
+        h_in = dict(tgt=host['tgt'].pin_memory(), srcs=[t.pin_memory() for t in host['srcs']],
+                    xs=[t.pin_memory() for t in host['disp_pyr']], poses=host['poses'].pin_memory(),
+                    Kp=host['K_pyr'].pin_memory(), lgs=[t.pin_memory() for t in host['logits_pyr']])
+    if h_in.get('_arena') is not None:
+        h_in['tgt'].copy_(host['tgt']); h_in['poses'].copy_(host['poses']); h_in['Kp'].copy_(host['K_pyr'])
+        for dst, src in zip(h_in['srcs'] + h_in['xs'] + h_in['lgs'], host['srcs'] + host['disp_pyr'] + host['logits_pyr']):
+            dst.copy_(src)
     h2d, d2h = pipe.bytes_per_step()
-    Ke = max(6, min(K, 40))
+    Ke = max(6, min(K, 150))
     for _ in range(4):
         slot = pipe.submit(h_in)
     e2e_losses = pipe.result(slot)[0].tolist()
