@@ -502,10 +502,12 @@ loss_fused_kernel(const LossParams P) {
       sm_sum += sm;
       float a1 = __shfl_up_sync(0xffffffffu, a0, 1), a2 = __shfl_up_sync(0xffffffffu, a0, 2);
       float c01 = __shfl_up_sync(0xffffffffu, c00, 1);
-      if (lane < 2) {
+      {  // lanes 0 and 1 take what lies left of the tile from the halo columns: broadcast loads + selects, no branch
         const int o = (r + kHalo) * 2;
-        if (lane == 0) { a1 = sha[o + 1]; a2 = sha[o]; c01 = shc[o + 1]; }
-        else a2 = sha[o + 1];
+        const float h0 = sha[o], h1 = sha[o + 1], hc1 = shc[o + 1];
+        a1 = lane == 0 ? h1 : a1;
+        a2 = lane == 0 ? h0 : (lane == 1 ? h1 : a2);
+        c01 = lane == 0 ? hc1 : c01;
       }
       g_q = (a0 - 2.f * a1 + a2) + (b0 - 2.f * b1 + b2) + (c00 - c01 - c10 + c11);
       b2 = b1; b1 = b0; c10 = c00; c11 = c01;
