@@ -173,7 +173,7 @@ def run_reference(args):
         step()
     dt = (time.time() - t0) / args.steps
     val = pixel_views(Bs) / dt / 1e6
-    print(json.dumps({
+    args.out.emit(json.dumps({
         'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
@@ -322,9 +322,25 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             out['cpu_baseline'] = cpu_baseline(B_sample=8, reps=12)
-        print(json.dumps(out))
+        args.out.emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+class _QuietStdout(object):
+    """stdout of the process (C level too: NCCL prints its version banner there) goes to stderr until emit(), so
+    that the ONE JSON line is all the driver reads on stdout."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, line):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        print(line)
+        sys.stdout.flush()
 
 
 def main():
@@ -336,6 +352,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    args.out = _QuietStdout()
     if args.impl == 'reference':
         run_reference(args)
     else:
