@@ -1049,24 +1049,26 @@ loss_prep_kernel(const PrepImgJob job, const PrepJob prep) {
 // mean of level 0 (resize_area), so every level-0 pixel receives 1/4^s of its level-s pixel's gradient.
 // One thread per level-0 pixel.
 struct FoldJob {
-  const float4* glvl[VSL_MAX_SCALES];   // one view's gradient levels
-  float* g_src;                         // [B,H,W,3]
+  const float4* glvl[VSL_MAX_VIEWS][VSL_MAX_SCALES];   // gradient levels per view
+  float* g_src[VSL_MAX_VIEWS];                         // [B,H,W,3] per view
   int B, H, W, S;
 };
+// grid = (ceil(W / 256), H, V * B): one launch for every view
 __global__ void __launch_bounds__(256)
 loss_fold_src_grad_kernel(const FoldJob j) {
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  const int v = blockIdx.z / j.B, b = blockIdx.z - v * j.B;
   if (x >= j.W) return;
   float g0 = 0.f, g1 = 0.f, g2 = 0.f, w = 1.0f;
   for (int s = 0; s < j.S; ++s) {
     const int Hs = j.H >> s, Ws = j.W >> s, st = Ws + 2 * kPad;
-    const float4 q = __ldg(j.glvl[s] + ((size_t)b * (Hs + 2 * kPad) + (y >> s) + kPad) * st + (x >> s) + kPad);
+    const float4 q = __ldg(j.glvl[v][s] + ((size_t)b * (Hs + 2 * kPad) + (y >> s) + kPad) * st + (x >> s) + kPad);
     g0 = fmaf(w, q.x, g0); g1 = fmaf(w, q.y, g1); g2 = fmaf(w, q.z, g2);
     w *= 0.25f;
   }
-  float* o = j.g_src + (((size_t)b * j.H + y) * j.W + x) * 3;
-  o[0] = g0; o[1] = g1; o[2] = g2;
+  float* o = j.g_src[v] + (((size_t)b * j.H + y) * j.W + x) * 3;
+  __stcs(o, g0); __stcs(o + 1, g1); __stcs(o + 2, g2);
 }
 
 }  // namespace vsl
@@ -1333,13 +1335,15 @@ int vsl_loss_fwd_bwd(const VslLossDesc* d, const float* tgt, const float* const*
     default: rc = run_loss<4>(d, P, poses, K_pyr, losses, g_poses, st); break;
   }
   if (rc != VSL_OK || !d->want_src_grad) return rc;
-  // 4. d/d(source image): fold the gradient levels back to [B,H,W,3]
-  for (int v = 0; v < d->V; ++v) {
+  // 4. d/d(source image): fold the gradient levels back to [B,H,W,3], all views in one launch
+  {
     FoldJob fj;
-    for (int s = 0; s < VSL_MAX_SCALES; ++s) fj.glvl[s] = s < d->S ? P.gsrc[v][s] : nullptr;
-    fj.g_src = g_srcs[v];
+    for (int v = 0; v < VSL_MAX_VIEWS; ++v) {
+      fj.g_src[v] = v < d->V ? g_srcs[v] : nullptr;
+      for (int s = 0; s < VSL_MAX_SCALES; ++s) fj.glvl[v][s] = (v < d->V && s < d->S) ? P.gsrc[v][s] : nullptr;
+    }
     fj.B = d->B; fj.H = d->H; fj.W = d->W; fj.S = d->S;
-    loss_fold_src_grad_kernel<<<dim3((d->W + 255) / 256, d->H, d->B), 256, 0, st>>>(fj);
+    loss_fold_src_grad_kernel<<<dim3((d->W + 255) / 256, d->H, d->V * d->B), 256, 0, st>>>(fj);
   }
   return launch_status();
 }
