@@ -62,3 +62,38 @@ def test_pipeline_single_copy_arena_matches_per_tensor_copies():
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][2], outs[1][2])
     assert all(torch.equal(a, b) for a, b in zip(outs[0][1] + outs[0][3], outs[1][1] + outs[1][3]))
     assert float(outs[0][0].abs().sum()) > 0
+
+
+def test_fused_step_is_cuda_graph_capturable():
+    """The three launches of a step (programmatic dependent launches included) capture into a CUDA graph; replaying
+    the graph on new input values reproduces the directly launched step bit for bit."""
+    B, H, W, S, V = 2, 32, 64, 3, 2
+    flags = ops.LossFlags(num_scales=S)
+    plan = ops.ViewSynthesisPlan(B, H, W, V, flags, _lib.MASK_EXP, DEV)
+    d0 = synth.make_snippets(B, H, W, S=S, V=V, seed=11)
+    d1 = synth.make_snippets(B, H, W, S=S, V=V, seed=12)
+    cu = lambda t: t.to(DEV).contiguous()
+    buf = dict(tgt=cu(d0['tgt']), srcs=[cu(s) for s in d0['srcs']], xs=[cu(x) for x in d0['disp_pyr']],
+               poses=cu(d0['poses']), Kp=cu(d0['K_pyr']), lgs=[cu(l) for l in d0['logits_pyr']])
+    bound = plan.bind(buf['tgt'], buf['srcs'], buf['xs'], buf['poses'], buf['Kp'], buf['lgs'])
+    side = torch.cuda.Stream(device=DEV)
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        plan.run_bound(bound, side.cuda_stream)          # warm-up outside capture (attribute opt-ins, lazy loads)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        plan.run_bound(bound, torch.cuda.current_stream().cuda_stream)
+    # new values in the same buffers, then replay
+    buf['tgt'].copy_(d1['tgt']); buf['poses'].copy_(d1['poses']); buf['Kp'].copy_(d1['K_pyr'])
+    for dst, src in zip(buf['srcs'] + buf['xs'] + buf['lgs'], d1['srcs'] + d1['disp_pyr'] + d1['logits_pyr']):
+        dst.copy_(src)
+    graph.replay()
+    torch.cuda.synchronize()
+    got = (plan.losses.clone(), [g.clone() for g in plan.g_x], plan.g_poses.clone(), [g.clone() for g in plan.g_logits])
+    plan.run_bound(bound)
+    torch.cuda.synchronize()
+    assert torch.equal(got[0], plan.losses) and torch.equal(got[2], plan.g_poses)
+    assert all(torch.equal(a, b) for a, b in zip(got[1] + got[3], plan.g_x + plan.g_logits))
+    assert float(got[0].abs().sum()) > 0
