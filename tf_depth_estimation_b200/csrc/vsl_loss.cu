@@ -206,7 +206,10 @@ VSL_DEV void owner_signs(const float* q, unsigned gx, unsigned gy, int H, int W,
 // DSRC = true additionally scatters d/d(source levels) with 16-byte reductions (red.global.add.v4.f32) into
 // gradient levels of the same zero-bordered RGBA layout; loss_fold_src_grad_kernel folds them back to level 0.
 template <int V, bool EXACT, bool DSRC>
-__global__ void __launch_bounds__(kThreads, (V <= 2 ? VSL_FUSED_MIN_BLOCKS : VSL_FUSED_MIN_BLOCKS / 2))
+// the exact mode (IEEE divisions, expf / logf, unfused sequences) needs ~170 registers: one block less per SM
+// beats spilling
+__global__ void __launch_bounds__(kThreads, (V <= 2 ? (EXACT ? VSL_FUSED_MIN_BLOCKS - 1 : VSL_FUSED_MIN_BLOCKS)
+                                                      : VSL_FUSED_MIN_BLOCKS / 2))
 loss_fused_kernel(const LossParams P) {
   constexpr int N = NT<V>::value;
   using L = WarpSmem<V>;
