@@ -86,6 +86,17 @@ int vsl_bilinear_bwd(const float* imgs, const float* coords, const float* flowx,
                      float* g_imgs /*nullable, atomics*/, float* g_coords /*[B,Ht,Wt,2] nullable*/,
                      vsl_stream_t stream);
 
+/* ---- consistent_depth_loss(src_depth, pred_src_depth, coords)  utils_lr.py:369-458 in one pass:
+ *      err = |pred_src_depth - bilinear(src_depth, coords)|, [B,Ht,Wt,1], no reduction (as the reference).
+ *      Backward for an upstream g_err: g_pred and g_coords deterministic, g_src_depth by atomics (zeroed here);
+ *      each nullable. */
+int vsl_consist_fwd(const float* src_depth /*[B,Hs,Ws,1]*/, const float* pred /*[B,Ht,Wt,1]*/,
+                    const float* coords /*[B,Ht,Wt,2]*/, int B, int Hs, int Ws, int Ht, int Wt, float* err,
+                    vsl_stream_t stream);
+int vsl_consist_bwd(const float* src_depth, const float* pred, const float* coords, int B, int Hs, int Ws, int Ht,
+                    int Wt, const float* g_err, float* g_src_depth, float* g_pred, float* g_coords,
+                    vsl_stream_t stream);
+
 /* ---- depth_optflow(coords)  utils.py:321-338: flow = coords - meshgrid. */
 int vsl_depth_optflow(const float* coords /*[B,H,W,2]*/, int B, int H, int W, float* flowx, float* flowy,
                       vsl_stream_t stream);
@@ -174,6 +185,34 @@ int vsl_loss_fwd_bwd(const VslLossDesc* d,
                      float* g_poses /*same shape as poses*/, float* const* g_logits_pyr /*S, MASK_EXP*/,
                      float* const* g_srcs /*host array V x [B,H,W,3]; NULL unless want_src_grad*/,
                      void* ws, vsl_stream_t stream);
+
+/* ---- EXTENSIONS, not in the reference (BASELINE.json's north_star names them): off unless a
+ *      caller asks.  Oracle: oracle/vsl_oracle.py ssim_dissimilarity / edge_aware_smooth_loss; parity unpinned.
+ *
+ *      SSIM dissimilarity clip((1 - SSIM(x, y)) / 2, 0, 1) with 3x3 VALID average pools, C1 = 0.01^2,
+ *      C2 = 0.03^2.  x, y: [B,H,W,C], C <= 4.  map: [B,H-2,W-2,C] (nullable); loss: device float = mean(map)
+ *      (nullable; needs ws).  Backward: upstream = g_map (per element, nullable) plus, when mean_path != 0,
+ *      g_loss[0] / count (g_loss NULL means 1).  Deterministic (gather form). */
+size_t vsl_ssim_ws_bytes(int B, int H, int W, int C);
+int vsl_ssim_fwd(const float* x, const float* y, int B, int H, int W, int C, float* map, float* loss, void* ws,
+                 vsl_stream_t stream);
+int vsl_ssim_bwd(const float* x, const float* y, int B, int H, int W, int C, const float* g_map,
+                 const float* g_loss, int mean_path, float* g_x /*nullable*/, float* g_y /*nullable*/,
+                 vsl_stream_t stream);
+/*      Edge-aware first-order smoothness mean(|d_x disp| exp(-mean_c |d_x img|)) + the same along y.
+ *      disp: [B,H,W,1], img: [B,H,W,C], C <= 4.  g_img nullable. */
+size_t vsl_edge_smooth_ws_bytes(int B, int H, int W);
+int vsl_edge_smooth_fwd(const float* disp, const float* img, int B, int H, int W, int C, float* loss, void* ws,
+                        vsl_stream_t stream);
+int vsl_edge_smooth_bwd(const float* disp, const float* img, int B, int H, int W, int C, const float* g_loss,
+                        float* g_disp, float* g_img, vsl_stream_t stream);
+
+/* ---- the step after the path: tf.train.AdamOptimizer(lr, beta1) as the training scripts apply it
+ *      (train_depth_then_cam_lr.py:413, train.py:148), TensorFlow's ApplyAdam arithmetic, over one flat range of
+ *      n parameters (param, grad, m, v cut at the same offset out of 16-byte aligned arenas).  step = t >= 1;
+ *      grad is multiplied by grad_scale first (1, or 1/world to average summed rank gradients). */
+int vsl_adam_step(float* param, const float* grad, float* m, float* v, long long n, float lr, float beta1,
+                  float beta2, float eps, int step, float grad_scale, vsl_stream_t stream);
 
 #ifdef __cplusplus
 }

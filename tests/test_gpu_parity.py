@@ -122,6 +122,30 @@ def test_optflow_warp_gradients():
         assert rel_err(y.grad, x.grad) <= 1e-4
 
 
+def test_consistent_depth_loss_gradients():
+    """utils_lr.py:369-458 as one kernel each way: d/d(src_depth) (atomics), d/d(pred), d/d(coords)."""
+    g = torch.Generator().manual_seed(9)
+    B, Hs, Ws, Ht, Wt = 2, 20, 28, 24, 32
+    src = 1.0 + 4.0 * torch.rand(B, Hs, Ws, 1, generator=g)
+    pred = 1.0 + 4.0 * torch.rand(B, Ht, Wt, 1, generator=g)
+    # coordinates over and beyond the source frame (zero padding on every side)
+    coords = torch.stack([torch.rand(B, Ht, Wt, generator=g) * (Ws + 3) - 2,
+                          torch.rand(B, Ht, Wt, generator=g) * (Hs + 3) - 2], dim=3)
+    R = torch.randn(B, Ht, Wt, 1, generator=g)
+    a = [src.double().requires_grad_(), pred.double().requires_grad_(), coords.double().requires_grad_()]
+    (O.consistent_depth_loss(*a) * R.double()).sum().backward()
+    b = [cu(src, True), cu(pred, True), cu(coords, True)]
+    err = ops.consistent_depth_loss(*b)
+    assert float((err.detach().cpu().double() - O.consistent_depth_loss(*[t.detach() for t in a])).abs().max()) <= 1e-5
+    (err * cu(R)).sum().backward()
+    for x, y in zip(a, b):
+        assert rel_err(y.grad, x.grad) <= 1e-4
+    # only the prediction asks for a gradient: the other two buffers are not produced
+    p2 = cu(pred, True)
+    (ops.consistent_depth_loss(cu(src), p2, cu(coords)) * cu(R)).sum().backward()
+    assert torch.equal(p2.grad, b[1].grad)
+
+
 def test_loss_terms_golden(golden):
     c = golden['terms']
     for inverse, key in ((False, 'smooth'), (True, 'smooth_inv')):

@@ -42,6 +42,8 @@ SIGNATURES = {
     'vsl_warp_bwd': (ctypes.c_int, [_c_float_p] * 4 + [ctypes.c_int] * 5 + [_c_float_p] * 8 + [ctypes.c_void_p, _c_stream]),
     'vsl_bilinear_fwd': (ctypes.c_int, [_c_float_p] * 4 + [ctypes.c_int] * 6 + [_c_float_p] * 3 + [_c_stream]),
     'vsl_bilinear_bwd': (ctypes.c_int, [_c_float_p] * 4 + [ctypes.c_int] * 6 + [_c_float_p] * 4 + [_c_stream]),
+    'vsl_consist_fwd': (ctypes.c_int, [_c_float_p] * 3 + [ctypes.c_int] * 5 + [_c_float_p, _c_stream]),
+    'vsl_consist_bwd': (ctypes.c_int, [_c_float_p] * 3 + [ctypes.c_int] * 5 + [_c_float_p] * 4 + [_c_stream]),
     'vsl_depth_optflow': (ctypes.c_int, [_c_float_p] + [ctypes.c_int] * 3 + [_c_float_p] * 2 + [_c_stream]),
     'vsl_meshgrid': (ctypes.c_int, [ctypes.c_int] * 4 + [_c_float_p, _c_stream]),
     'vsl_pixel2cam_fwd': (ctypes.c_int, [_c_float_p] * 3 + [ctypes.c_int] * 4 + [_c_float_p, _c_stream]),
@@ -64,6 +66,14 @@ SIGNATURES = {
                                         _c_float_p, ctypes.POINTER(ctypes.c_void_p), _c_float_p,
                                         ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p),
                                         ctypes.c_void_p, _c_stream]),
+    'vsl_adam_step': (ctypes.c_int, [_c_float_p] * 4 + [ctypes.c_longlong] + [ctypes.c_float] * 4 + [ctypes.c_int, ctypes.c_float, _c_stream]),
+    'vsl_ssim_ws_bytes': (ctypes.c_size_t, [ctypes.c_int] * 4),
+    'vsl_ssim_fwd': (ctypes.c_int, [_c_float_p] * 2 + [ctypes.c_int] * 4 + [_c_float_p] * 2 + [ctypes.c_void_p, _c_stream]),
+    'vsl_ssim_bwd': (ctypes.c_int, [_c_float_p] * 2 + [ctypes.c_int] * 4 + [_c_float_p] * 2 + [ctypes.c_int] +
+                     [_c_float_p] * 2 + [_c_stream]),
+    'vsl_edge_smooth_ws_bytes': (ctypes.c_size_t, [ctypes.c_int] * 3),
+    'vsl_edge_smooth_fwd': (ctypes.c_int, [_c_float_p] * 2 + [ctypes.c_int] * 4 + [_c_float_p, ctypes.c_void_p, _c_stream]),
+    'vsl_edge_smooth_bwd': (ctypes.c_int, [_c_float_p] * 2 + [ctypes.c_int] * 4 + [_c_float_p] * 3 + [_c_stream]),
 }
 
 _lib = None

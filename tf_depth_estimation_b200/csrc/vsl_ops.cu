@@ -286,6 +286,57 @@ bilinear_bwd_kernel(const float* __restrict__ imgs, const float* __restrict__ co
   if (g_coords != nullptr) reinterpret_cast<float2*>(g_coords)[gp] = make_float2(dx, dy);
 }
 
+// consistent_depth_loss (utils_lr.py:369-458) in one pass: the 1-channel bilinear fetch of src_depth at `coords`
+// and |pred_src_depth - sampled|, without the sampled map, the difference and their backward intermediates.
+__global__ void __launch_bounds__(256)
+consist_fwd_kernel(const float* __restrict__ src_depth, const float* __restrict__ pred,
+                   const float* __restrict__ coords, int Hs, int Ws, int Ht, int Wt, float* __restrict__ err) {
+  const int b = blockIdx.y, pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= Ht * Wt) return;
+  const size_t gp = (size_t)b * Ht * Wt + pix;
+  const float2 xy = reinterpret_cast<const float2*>(coords)[gp];
+  Foot f = footprint(xy.x, xy.y, Ws, Hs);
+  const float* base = src_depth + (size_t)b * Hs * Ws;
+  const float v = blend(__fmul_rn(f.wx0, f.wy0), __fmul_rn(f.wx0, f.wy1), __fmul_rn(f.wx1, f.wy0),
+                        __fmul_rn(f.wx1, f.wy1), __ldg(base + (size_t)f.y0 * Ws + f.x0),
+                        __ldg(base + (size_t)f.y1 * Ws + f.x0), __ldg(base + (size_t)f.y0 * Ws + f.x1),
+                        __ldg(base + (size_t)f.y1 * Ws + f.x1));
+  err[gp] = fabsf(__fsub_rn(pred[gp], v));
+}
+
+__global__ void __launch_bounds__(256)
+consist_bwd_kernel(const float* __restrict__ src_depth, const float* __restrict__ pred,
+                   const float* __restrict__ coords, int Hs, int Ws, int Ht, int Wt,
+                   const float* __restrict__ g_err, float* __restrict__ g_src_depth, float* __restrict__ g_pred,
+                   float* __restrict__ g_coords) {
+  const int b = blockIdx.y, pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= Ht * Wt) return;
+  const size_t gp = (size_t)b * Ht * Wt + pix;
+  const float2 xy = reinterpret_cast<const float2*>(coords)[gp];
+  Foot f = footprint(xy.x, xy.y, Ws, Hs);
+  const size_t ib = (size_t)b * Hs * Ws;
+  const size_t o00 = ib + (size_t)f.y0 * Ws + f.x0, o01 = ib + (size_t)f.y1 * Ws + f.x0;
+  const size_t o10 = ib + (size_t)f.y0 * Ws + f.x1, o11 = ib + (size_t)f.y1 * Ws + f.x1;
+  const float i00 = __ldg(src_depth + o00), i01 = __ldg(src_depth + o01), i10 = __ldg(src_depth + o10),
+              i11 = __ldg(src_depth + o11);
+  const float w00 = __fmul_rn(f.wx0, f.wy0), w01 = __fmul_rn(f.wx0, f.wy1), w10 = __fmul_rn(f.wx1, f.wy0),
+              w11 = __fmul_rn(f.wx1, f.wy1);
+  const float v = blend(w00, w01, w10, w11, i00, i01, i10, i11);
+  const float gs = sgn(__fsub_rn(pred[gp], v)) * g_err[gp];   // d|e|/d(pred); the sampled value receives -gs
+  if (g_pred != nullptr) g_pred[gp] = gs;
+  if (g_coords != nullptr) {
+    const float dx = -gs * (f.wy0 * (f.mx1 * i10 - f.mx0 * i00) + f.wy1 * (f.mx1 * i11 - f.mx0 * i01));
+    const float dy = -gs * (f.wx0 * (f.my1 * i01 - f.my0 * i00) + f.wx1 * (f.my1 * i11 - f.my0 * i10));
+    reinterpret_cast<float2*>(g_coords)[gp] = make_float2(dx, dy);
+  }
+  if (g_src_depth != nullptr && gs != 0.f) {
+    if (w00 != 0.f) atomicAdd(g_src_depth + o00, -w00 * gs);
+    if (w01 != 0.f) atomicAdd(g_src_depth + o01, -w01 * gs);
+    if (w10 != 0.f) atomicAdd(g_src_depth + o10, -w10 * gs);
+    if (w11 != 0.f) atomicAdd(g_src_depth + o11, -w11 * gs);
+  }
+}
+
 __global__ void depth_optflow_kernel(const float* __restrict__ coords, int H, int W, size_t n,
                                      float* __restrict__ flowx, float* __restrict__ flowy) {
   size_t gp = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -868,6 +919,33 @@ int vsl_bilinear_bwd(const float* imgs, const float* coords, const float* flowx,
     case 3: bilinear_bwd_kernel<3><<<grid, 256, 0, st>>>(imgs, coords, flowx, flowy, Hs, Ws, Ht, Wt, g_out, g_wmask, g_imgs, g_coords); break;
     default: bilinear_bwd_kernel<4><<<grid, 256, 0, st>>>(imgs, coords, flowx, flowy, Hs, Ws, Ht, Wt, g_out, g_wmask, g_imgs, g_coords); break;
   }
+  return launch_status();
+}
+
+int vsl_consist_fwd(const float* src_depth, const float* pred, const float* coords, int B, int Hs, int Ws, int Ht,
+                    int Wt, float* err, vsl_stream_t stream) {
+  VSL_REQUIRE(src_depth && pred && coords && err, VSL_E_NULL);
+  VSL_REQUIRE(B > 0 && B <= 65535 && Hs > 0 && Ws > 0 && Ht > 0 && Wt > 0, VSL_E_SHAPE);
+  VSL_REQUIRE(aligned(coords, 8), VSL_E_ALIGN);
+  dim3 grid((Ht * Wt + 255) / 256, B);
+  consist_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src_depth, pred, coords, Hs, Ws, Ht, Wt, err);
+  return launch_status();
+}
+
+int vsl_consist_bwd(const float* src_depth, const float* pred, const float* coords, int B, int Hs, int Ws, int Ht,
+                    int Wt, const float* g_err, float* g_src_depth, float* g_pred, float* g_coords,
+                    vsl_stream_t stream) {
+  VSL_REQUIRE(src_depth && pred && coords && g_err, VSL_E_NULL);
+  VSL_REQUIRE(B > 0 && B <= 65535 && Hs > 0 && Ws > 0 && Ht > 0 && Wt > 0, VSL_E_SHAPE);
+  VSL_REQUIRE(aligned(coords, 8) && (g_coords == nullptr || aligned(g_coords, 8)), VSL_E_ALIGN);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (g_src_depth != nullptr) {
+    cudaError_t e = cudaMemsetAsync(g_src_depth, 0, sizeof(float) * (size_t)B * Hs * Ws, st);
+    if (e != cudaSuccess) return (int)e;
+  }
+  dim3 grid((Ht * Wt + 255) / 256, B);
+  consist_bwd_kernel<<<grid, 256, 0, st>>>(src_depth, pred, coords, Hs, Ws, Ht, Wt, g_err, g_src_depth, g_pred,
+                                           g_coords);
   return launch_status();
 }
 

@@ -195,10 +195,38 @@ def depth_optflow(src_pixel_coords):
     return _DepthOptflow.apply(src_pixel_coords)
 
 
+class _ConsistentDepth(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, src_depth, pred, coords):
+        src_depth, pred, coords = _f32(src_depth, 'src_depth'), _f32(pred, 'pred_src_depth'), _f32(coords, 'coords')
+        B, Hs, Ws, _ = src_depth.shape
+        Ht, Wt = coords.shape[1], coords.shape[2]
+        err = torch.empty(B, Ht, Wt, 1, device=src_depth.device)
+        check(_lib.load().vsl_consist_fwd(src_depth.data_ptr(), pred.data_ptr(), coords.data_ptr(), B, Hs, Ws, Ht, Wt,
+                                          err.data_ptr(), _stream()))
+        ctx.save_for_backward(src_depth, pred, coords)
+        return err
+
+    @staticmethod
+    def backward(ctx, g_err):
+        src_depth, pred, coords = ctx.saved_tensors
+        B, Hs, Ws, _ = src_depth.shape
+        Ht, Wt = coords.shape[1], coords.shape[2]
+        g_s = torch.empty_like(src_depth) if ctx.needs_input_grad[0] else None
+        g_p = torch.empty_like(pred) if ctx.needs_input_grad[1] else None
+        g_c = torch.empty_like(coords) if ctx.needs_input_grad[2] else None
+        check(_lib.load().vsl_consist_bwd(src_depth.data_ptr(), pred.data_ptr(), coords.data_ptr(), B, Hs, Ws, Ht, Wt,
+                                          _f32(g_err, 'g_err').data_ptr(), _p(g_s), _p(g_p), _p(g_c), _stream()))
+        return g_s, g_p, g_c
+
+
 def consistent_depth_loss(src_depth, pred_src_depth, coords):
-    """utils_lr.py:369-458: |pred_src_depth - bilinear(src_depth, coords)| (no reduction)."""
-    sampled, _ = _Bilinear.apply(src_depth, coords, None, None)
-    return torch.abs(pred_src_depth - sampled)
+    """utils_lr.py:369-458: |pred_src_depth - bilinear(src_depth, coords)| (no reduction), one kernel each way."""
+    if src_depth.dim() != 4 or src_depth.shape[3] != 1 or coords.dim() != 4 or coords.shape[3] != 2:
+        raise ValueError('src_depth [B,Hs,Ws,1] / coords [B,Ht,Wt,2] expected')
+    if tuple(pred_src_depth.shape) != (coords.shape[0], coords.shape[1], coords.shape[2], 1):
+        raise ValueError('pred_src_depth must be [B,Ht,Wt,1]')
+    return _ConsistentDepth.apply(src_depth, pred_src_depth, coords)
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -359,6 +387,84 @@ def compute_exp_reg_loss(pred, ref=None):
     if pred.shape[-1] != 2:
         raise ValueError('pred must have 2 channels')
     return _ExpReg.apply(pred)
+
+
+# ----------------------------------------------------------------------------------------------------
+# Extensions that the reference does NOT contain (named by BASELINE.json's north_star):
+# off unless a caller asks for them; oracle = oracle/vsl_oracle.py, parity unpinned.
+class _Ssim(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, y, reduce_mean):
+        lib = _lib.load()
+        x, y = _f32(x, 'x'), _f32(y, 'y')
+        if x.shape != y.shape or x.dim() != 4:
+            raise ValueError('x and y must be [B,H,W,C] of the same shape')
+        B, H, W, C = x.shape
+        ctx.save_for_backward(x, y)
+        ctx.reduce_mean = bool(reduce_mean)
+        if reduce_mean:
+            out = torch.empty((), device=x.device)
+            ws = _ws(lib.vsl_ssim_ws_bytes(B, H, W, C), x.device)
+            check(lib.vsl_ssim_fwd(x.data_ptr(), y.data_ptr(), B, H, W, C, None, out.data_ptr(), ws.data_ptr(), _stream()))
+        else:
+            out = torch.empty(B, H - 2, W - 2, C, device=x.device)
+            check(lib.vsl_ssim_fwd(x.data_ptr(), y.data_ptr(), B, H, W, C, out.data_ptr(), None, None, _stream()))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, y = ctx.saved_tensors
+        B, H, W, C = x.shape
+        g = _f32(g, 'g')
+        g_x = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        g_y = torch.empty_like(y) if ctx.needs_input_grad[1] else None
+        if g_x is None and g_y is None:
+            return None, None, None
+        if ctx.reduce_mean:
+            check(_lib.load().vsl_ssim_bwd(x.data_ptr(), y.data_ptr(), B, H, W, C, None, g.data_ptr(), 1, _p(g_x), _p(g_y), _stream()))
+        else:
+            check(_lib.load().vsl_ssim_bwd(x.data_ptr(), y.data_ptr(), B, H, W, C, g.data_ptr(), None, 0, _p(g_x), _p(g_y), _stream()))
+        return g_x, g_y, None
+
+
+def ssim_dissimilarity(x, y):
+    """EXTENSION (not in the reference): clip((1 - SSIM(x, y)) / 2, 0, 1), 3x3 VALID pools -> [B,H-2,W-2,C]."""
+    return _Ssim.apply(x, y, False)
+
+
+def ssim_loss(x, y):
+    """EXTENSION: mean of ssim_dissimilarity(x, y), reduced inside the kernel (no map is written)."""
+    return _Ssim.apply(x, y, True)
+
+
+class _EdgeSmooth(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, disp, img):
+        lib = _lib.load()
+        disp, img = _f32(disp, 'disp'), _f32(img, 'img')
+        if disp.dim() != 4 or disp.shape[3] != 1 or img.dim() != 4 or img.shape[:3] != disp.shape[:3]:
+            raise ValueError('disp must be [B,H,W,1] and img [B,H,W,C] of the same size')
+        B, H, W, C = img.shape
+        loss = torch.empty((), device=disp.device)
+        ws = _ws(lib.vsl_edge_smooth_ws_bytes(B, H, W), disp.device)
+        check(lib.vsl_edge_smooth_fwd(disp.data_ptr(), img.data_ptr(), B, H, W, C, loss.data_ptr(), ws.data_ptr(), _stream()))
+        ctx.save_for_backward(disp, img)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        disp, img = ctx.saved_tensors
+        B, H, W, C = img.shape
+        g_d = torch.empty_like(disp)
+        g_i = torch.empty_like(img) if ctx.needs_input_grad[1] else None
+        check(_lib.load().vsl_edge_smooth_bwd(disp.data_ptr(), img.data_ptr(), B, H, W, C, _f32(g, 'g').data_ptr(),
+                                              g_d.data_ptr(), _p(g_i), _stream()))
+        return g_d, g_i
+
+
+def edge_aware_smooth_loss(disp, img):
+    """EXTENSION (not in the reference): mean(|d_x disp| exp(-mean_c |d_x img|)) + the same along y."""
+    return _EdgeSmooth.apply(disp, img)
 
 
 def image_pyramid(img, num_scales):
