@@ -214,6 +214,29 @@ int vsl_edge_smooth_bwd(const float* disp, const float* img, int B, int H, int W
 int vsl_adam_step(float* param, const float* grad, float* m, float* v, long long n, float lr, float beta1,
                   float beta2, float eps, int step, float grad_scale, vsl_stream_t stream);
 
+/*      The same step data-parallel, as ONE kernel over NVLink peer memory (reduce-scatter + Adam + all-gather):
+ *      peer_grads[r] / peer_params[r] (host arrays of `world` device pointers, 16-byte aligned) are rank r's flat
+ *      gradient / parameter arenas as mapped into this process (this rank's own at index `rank`).  This rank sums
+ *      the gradients of all ranks over its shard [lo, hi) (multiples of 4 floats) in rank order, updates the shard
+ *      with moments m_shard / v_shard (hi - lo floats each) and stores the new parameters into every rank's arena.
+ *      Bracket it with vsl_peer_barrier (before: all gradients written; after: all parameters landed).
+ *      vsl_peer_barrier: peer_flags[r] = rank r's flag array (>= 16 unsigned, zero-initialised) as mapped here;
+ *      epoch must grow by 1 per call; *timed_out (device int, nullable) is set if a peer does not arrive in ~3 s. */
+/*      Peer arenas -- the one place the library allocates: memory other processes map must come straight from
+ *      cudaMalloc (an IPC handle names a whole allocation).  vsl_peer_alloc zero-fills; the owner frees with
+ *      vsl_peer_free after every peer has closed its mapping.  vsl_ipc_open maps a peer's arena for kernels of the
+ *      CURRENT device (cudaIpcMemLazyEnablePeerAccess); handle64 is the 64-byte cudaIpcMemHandle_t. */
+int vsl_peer_alloc(size_t bytes, void** ptr);
+int vsl_peer_free(void* ptr);
+int vsl_ipc_get_handle(void* ptr, unsigned char* handle64);
+int vsl_ipc_open(const unsigned char* handle64, void** ptr);
+int vsl_ipc_close(void* ptr);
+int vsl_peer_barrier(unsigned* const* peer_flags, int rank, int world, unsigned epoch, int* timed_out,
+                     vsl_stream_t stream);
+int vsl_dp_adam_step(const float* const* peer_grads, float* const* peer_params, int rank, int world, float* m_shard,
+                     float* v_shard, long long lo, long long hi, float lr, float beta1, float beta2, float eps,
+                     int step, float grad_scale, vsl_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

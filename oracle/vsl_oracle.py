@@ -383,3 +383,21 @@ def edge_aware_smooth_loss(disp, img):
     wx = torch.exp(-(img[:, :, 1:] - img[:, :, :-1]).abs().mean(3, keepdim=True))
     wy = torch.exp(-(img[:, 1:] - img[:, :-1]).abs().mean(3, keepdim=True))
     return (ddx.abs() * wx).mean() + (ddy.abs() * wy).mean()
+
+
+# ----------------------------------------------------------------------------
+# the step after the path: tf.train.AdamOptimizer(lr, beta1), train_depth_then_cam_lr.py:413.
+# TensorFlow is not vendored by the reference and unpinned; this restates the algorithm TF 1.x documents for
+# AdamOptimizer / ApplyAdam (training/adam.py docstring).  Parity unpinned (no reference fixture exists).
+# ----------------------------------------------------------------------------
+def adam_step_tf(param, grad, m, v, t, lr, beta1=0.9, beta2=0.999, eps=1e-8):
+    """-> (param, m, v) after step t >= 1:  lr_t = lr sqrt(1 - b2^t) / (1 - b1^t);
+    m = b1 m + (1 - b1) g;  v = b2 v + (1 - b2) g^2;  param -= lr_t m / (sqrt(v) + eps)."""
+    # TF casts the hyper-parameters to the variable dtype (float32) before use: 1 - float32(0.999) is
+    # 9.99987e-4, not 1e-3 -- a 1.3e-5 relative difference in v that belongs to the reference's behaviour
+    import numpy as _np
+    lr, beta1, beta2, eps = (float(_np.float32(h)) for h in (lr, beta1, beta2, eps))
+    lr_t = lr * (1.0 - beta2 ** t) ** 0.5 / (1.0 - beta1 ** t)
+    m = beta1 * m + (1.0 - beta1) * grad
+    v = beta2 * v + (1.0 - beta2) * grad * grad
+    return param - lr_t * m / (v.sqrt() + eps), m, v

@@ -76,3 +76,71 @@ def test_two_rank_gloo_matches_global_batch(tmp_path):
     lo, hi = got['lo_hi']
     # per-sample gradients of a rank are exactly that rank's rows of the global gradient
     assert torch.allclose(got['ps'], ps.grad[lo:hi], rtol=1e-10, atol=1e-14)
+
+
+# ---- the data-parallel optimiser step (dist.DataParallelAdam): bucketing + reduction logic over gloo, with the
+# oracle's Adam restatement injected as the update (the CUDA kernel needs a GPU; tests/test_gpu_optim.py covers it)
+SHAPES = [(7, 3), (5,), (2, 3, 4), (1,), (33,)]
+
+
+def _oracle_adam(hyper):
+    def fn(p, g, m, v, step):
+        np_, nm, nv = O.adam_step_tf(p.double(), g.double() * hyper.get('grad_scale', 1.0), m.double(), v.double(), step,
+                                     hyper['lr'], hyper['beta1'], hyper['beta2'], hyper['eps'])
+        p.copy_(np_); m.copy_(nm); v.copy_(nv)
+    return fn
+
+
+def _rank_grads(rank, step):
+    g = torch.Generator().manual_seed(1000 * step + rank)
+    return [torch.randn(s, generator=g) for s in SHAPES]
+
+
+def _dp_worker(rank, world, port, out):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    hyper = dict(lr=0.01, beta1=0.9, beta2=0.999, eps=1e-8)
+    dp = vdist.DataParallelAdam(SHAPES, 'cpu', bucket_bytes=64, adam_fn=_oracle_adam(hyper), **hyper)  # 16-float buckets
+    assert len(dp.buckets) > 3
+    for p in dp.params:
+        p.fill_(0.5)
+    for step in (1, 2, 3):
+        for gv, g in zip(dp.grads, _rank_grads(rank, step)):
+            gv.copy_(g)
+        assert dp.step() == step
+    if rank == 0:
+        torch.save([p.clone() for p in dp.params], out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_data_parallel_adam_two_ranks(tmp_path):
+    out = str(tmp_path / 'params.pt')
+    mp.spawn(_dp_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = torch.load(out)
+    # single process: Adam on the summed gradients, tensor by tensor
+    hyper = dict(lr=0.01, beta1=0.9, beta2=0.999, eps=1e-8)
+    ps = [torch.full(s, 0.5, dtype=torch.float64) for s in SHAPES]
+    ms = [torch.zeros(s, dtype=torch.float64) for s in SHAPES]
+    vs = [torch.zeros(s, dtype=torch.float64) for s in SHAPES]
+    for step in (1, 2, 3):
+        gs = [(a + b).double() for a, b in zip(_rank_grads(0, step), _rank_grads(1, step))]
+        for i in range(len(SHAPES)):
+            ps[i], ms[i], vs[i] = O.adam_step_tf(ps[i], gs[i], ms[i], vs[i], step, **hyper)
+    for a, b in zip(got, ps):
+        assert a.shape == b.shape
+        assert torch.allclose(a.double(), b, rtol=1e-5, atol=1e-7)
+
+
+def test_data_parallel_adam_layout():
+    dp = vdist.DataParallelAdam(SHAPES, 'cpu', lr=0.1, adam_fn=lambda *a: None)
+    assert all(o % 4 == 0 for o in dp.offsets)                      # 16-byte aligned tensors
+    assert dp.buckets[0][0] == 0 and dp.buckets[-1][1] == dp.numel
+    assert all(a[1] == b[0] for a, b in zip(dp.buckets, dp.buckets[1:]))
+    assert [tuple(p.shape) for p in dp.params] == SHAPES
+    dp.grads[2].fill_(3.0)
+    assert float(dp.grad_flat.sum()) == 3.0 * 24                    # views alias the arena
+    with pytest.raises(TypeError):
+        vdist.DataParallelAdam(SHAPES, 'cpu', lr=0.1).step()        # default update = the CUDA kernel: no CPU fallback

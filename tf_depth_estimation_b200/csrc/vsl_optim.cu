@@ -8,6 +8,8 @@
 // (epsilon outside the bias correction, unlike torch.optim.Adam).  HBM-bound: 16 B read + 12 B written per
 // parameter; 16-byte accesses, gradient read evict-first (single use), grid = a multiple of the SM count.
 #pragma once
+#include <string.h>
+
 #include "vsl_common.cuh"
 
 namespace vsl {
@@ -45,6 +47,80 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
   }
 }
 
+
+// =====================================================================================================
+// Data-parallel step as ONE kernel over NVLink peer memory (instead of NCCL all-reduce -> Adam):
+// rank r owns the contiguous shard [lo, hi) of the flat arena.  For its shard it
+//   1. loads the gradient of EVERY rank (its own from HBM, the others' by peer-to-peer 16-byte loads over
+//      NVLink / NVSwitch) and sums them in rank order            -- the reduce-scatter;
+//   2. applies Adam with moments that exist for the shard only   -- 8 B/param of optimiser state / world;
+//   3. stores the new parameters into every rank's arena (peer-to-peer 16-byte stores) -- the all-gather.
+// Only the owner ever computes an element, so all replicas hold bit-identical parameters, and the sum order is
+// fixed => deterministic.  Per rank and step the links carry (world-1)/world of the arena in and out -- what a
+// ring all-reduce moves, in one pass and with no intermediate buffer -- and HBM sees 1/world of Adam's traffic.
+// Two flag barriers (peer_barrier_kernel) order it against the ranks' gradient producers and parameter readers.
+// =====================================================================================================
+constexpr int kMaxPeers = 16;
+struct PeerPtrs {
+  const float* grad[kMaxPeers];
+  float* param[kMaxPeers];
+};
+
+template <int WORLD>   // 0 = run-time world
+__global__ void __launch_bounds__(256)
+dp_adam_kernel(PeerPtrs pp, int world_rt, int rank, float* __restrict__ m, float* __restrict__ v, long long lo,
+               long long n4, AdamConsts c) {
+  const int world = WORLD ? WORLD : world_rt;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+  float4* m4 = reinterpret_cast<float4*>(m);
+  float4* v4 = reinterpret_cast<float4*>(v);
+  const long long lo4 = lo / 4;
+  for (long long i = tid; i < n4; i += nth) {
+    const long long gi = lo4 + i;
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < (WORLD ? WORLD : kMaxPeers); ++r) {
+      if (r < world) {
+        const float4 t = __ldcs(reinterpret_cast<const float4*>(pp.grad[r]) + gi);
+        g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+      }
+    }
+    float4 p = reinterpret_cast<const float4*>(pp.param[rank])[gi], mm = m4[i], vv = v4[i];
+    adam_one(p.x, g.x, mm.x, vv.x, c); adam_one(p.y, g.y, mm.y, vv.y, c);
+    adam_one(p.z, g.z, mm.z, vv.z, c); adam_one(p.w, g.w, mm.w, vv.w, c);
+    m4[i] = mm; v4[i] = vv;
+#pragma unroll
+    for (int r = 0; r < (WORLD ? WORLD : kMaxPeers); ++r)
+      if (r < world) reinterpret_cast<float4*>(pp.param[r])[gi] = p;
+  }
+}
+
+// Barrier across the GPUs of a node through peer-mapped flag words.  flags of rank q: unsigned[kMaxPeers], word r is
+// written by rank r only.  One block of `world` threads: thread r publishes `epoch` into rank r's word [rank], then
+// waits until this GPU's word [r] has reached `epoch`.  Everything this GPU wrote before (peer stores of the
+// previous kernel included) is fenced system-wide first.  A bounded spin: if a peer never arrives the kernel sets
+// *timed_out instead of hanging the GPU.
+struct PeerFlags { unsigned* f[kMaxPeers]; };
+
+__global__ void peer_barrier_kernel(PeerFlags pf, int rank, int world, unsigned epoch, int* timed_out) {
+  const int r = threadIdx.x;
+  if (r >= world) return;
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pf.f[r] + rank), "r"(epoch) : "memory");
+  const unsigned* mine = pf.f[rank] + r;
+  const long long t0 = clock64();
+  unsigned seen;
+  do {
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
+    if ((int)(seen - epoch) >= 0) break;
+    if (clock64() - t0 > 6000000000LL) {   // ~3 s at 2 GHz
+      if (timed_out != nullptr) *timed_out = 1;
+      break;
+    }
+  } while (true);
+  __threadfence_system();
+}
+
 }  // namespace vsl
 
 using namespace vsl;
@@ -69,6 +145,88 @@ int vsl_adam_step(float* param, const float* grad, float* m, float* v, long long
   const long long want = ((n - head) / 4 + 255) / 256 + 1;
   const int blocks = (int)(want < 148 * 8 ? want : 148 * 8);
   adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, m, v, n, head, c);
+  return launch_status();
+}
+
+// ---- peer arenas: the one place this library allocates, because memory that other processes map has to come
+// straight from cudaMalloc (an IPC handle names a whole allocation) and must outlive every mapping of it.
+int vsl_peer_alloc(size_t bytes, void** ptr) {
+  VSL_REQUIRE(ptr, VSL_E_NULL);
+  VSL_REQUIRE(bytes > 0, VSL_E_SHAPE);
+  cudaError_t e = cudaMalloc(ptr, bytes);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaMemset(*ptr, 0, bytes);
+  return e == cudaSuccess ? VSL_OK : (int)e;
+}
+int vsl_peer_free(void* ptr) {
+  cudaError_t e = cudaFree(ptr);
+  return e == cudaSuccess ? VSL_OK : (int)e;
+}
+int vsl_ipc_get_handle(void* ptr, unsigned char* handle64) {
+  VSL_REQUIRE(ptr && handle64, VSL_E_NULL);
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, ptr);
+  if (e != cudaSuccess) return (int)e;
+  memcpy(handle64, &h, 64);
+  return VSL_OK;
+}
+// Opened with the CURRENT device as the accessor: the peer's allocation is mapped for kernels of this GPU
+// (cudaIpcMemLazyEnablePeerAccess), which a mapping made under the owner's device would not be.
+int vsl_ipc_open(const unsigned char* handle64, void** ptr) {
+  VSL_REQUIRE(handle64 && ptr, VSL_E_NULL);
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  cudaError_t e = cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess);
+  return e == cudaSuccess ? VSL_OK : (int)e;
+}
+int vsl_ipc_close(void* ptr) {
+  cudaError_t e = cudaIpcCloseMemHandle(ptr);
+  return e == cudaSuccess ? VSL_OK : (int)e;
+}
+
+int vsl_peer_barrier(unsigned* const* peer_flags, int rank, int world, unsigned epoch, int* timed_out,
+                     vsl_stream_t stream) {
+  VSL_REQUIRE(peer_flags, VSL_E_NULL);
+  VSL_REQUIRE(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, VSL_E_SHAPE);
+  PeerFlags pf;
+  for (int r = 0; r < kMaxPeers; ++r) pf.f[r] = r < world ? peer_flags[r] : nullptr;
+  for (int r = 0; r < world; ++r) VSL_REQUIRE(pf.f[r] != nullptr, VSL_E_NULL);
+  peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(pf, rank, world, epoch, timed_out);
+  return launch_status();
+}
+
+int vsl_dp_adam_step(const float* const* peer_grads, float* const* peer_params, int rank, int world, float* m_shard,
+                     float* v_shard, long long lo, long long hi, float lr, float beta1, float beta2, float eps,
+                     int step, float grad_scale, vsl_stream_t stream) {
+  VSL_REQUIRE(peer_grads && peer_params && m_shard && v_shard, VSL_E_NULL);
+  VSL_REQUIRE(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world && step >= 1, VSL_E_SHAPE);
+  VSL_REQUIRE(lo >= 0 && hi >= lo && lo % 4 == 0 && hi % 4 == 0, VSL_E_SHAPE);
+  PeerPtrs pp;
+  for (int r = 0; r < kMaxPeers; ++r) {
+    pp.grad[r] = r < world ? peer_grads[r] : nullptr;
+    pp.param[r] = r < world ? peer_params[r] : nullptr;
+    if (r < world) {
+      VSL_REQUIRE(pp.grad[r] && pp.param[r], VSL_E_NULL);
+      VSL_REQUIRE(aligned(pp.grad[r], 16) && aligned(pp.param[r], 16), VSL_E_ALIGN);
+    }
+  }
+  VSL_REQUIRE(aligned(m_shard, 16) && aligned(v_shard, 16), VSL_E_ALIGN);
+  if (hi == lo) return VSL_OK;
+  AdamConsts c;
+  c.lr_t = (float)((double)lr * sqrt(1.0 - pow((double)beta2, (double)step)) / (1.0 - pow((double)beta1, (double)step)));
+  c.omb1 = 1.0f - beta1; c.omb2 = 1.0f - beta2; c.eps = eps; c.gscale = grad_scale;
+  const long long n4 = (hi - lo) / 4;
+  const long long want = (n4 + 255) / 256;
+  const int blocks = (int)(want < 148 * 8 ? want : 148 * 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (world) {
+    case 1: dp_adam_kernel<1><<<blocks, 256, 0, st>>>(pp, world, rank, m_shard, v_shard, lo, n4, c); break;
+    case 2: dp_adam_kernel<2><<<blocks, 256, 0, st>>>(pp, world, rank, m_shard, v_shard, lo, n4, c); break;
+    case 4: dp_adam_kernel<4><<<blocks, 256, 0, st>>>(pp, world, rank, m_shard, v_shard, lo, n4, c); break;
+    case 8: dp_adam_kernel<8><<<blocks, 256, 0, st>>>(pp, world, rank, m_shard, v_shard, lo, n4, c); break;
+    default: dp_adam_kernel<0><<<blocks, 256, 0, st>>>(pp, world, rank, m_shard, v_shard, lo, n4, c); break;
+  }
   return launch_status();
 }
 

@@ -56,3 +56,208 @@ def reduce_sum_(tensors, group=None):
         t.copy_(flat[off:off + t.numel()].reshape(t.shape))
         off += t.numel()
     return tensors
+
+
+class DataParallelAdam(object):
+    """The data-parallel optimiser step of SURVEY.md 8e / 8f.3: every parameter, gradient and Adam moment lives in
+    one flat float32 arena; step() all-reduces the gradient arena bucket by bucket (asynchronously: NCCL's stream)
+    and applies tf.train.AdamOptimizer (train_depth_then_cam_lr.py:413) to a bucket as soon as its sum has landed,
+    so the update of bucket k runs under the all-reduce of bucket k+1.  No concatenation, no copy-back.
+
+    `params[i]` / `grads[i]` are views shaped like shapes[i]: a network writes its gradients straight into
+    `grads[i]` (e.g. `p.grad = dp.grads[i]`).  Rank gradients are expected to be this rank's SHARE of the
+    global-batch gradient (local_loss_scale), hence a SUM and grad_scale = 1.
+
+    adam_fn(param, grad, m, v, step) applies one update in place to flat views; the default is the CUDA kernel
+    (ops.adam_step).  The CPU gloo tests inject a restatement to exercise the bucketing logic.
+    """
+
+    def __init__(self, shapes, device, lr, beta1=0.9, beta2=0.999, eps=1e-8, bucket_bytes=32 << 20, group=None,
+                 adam_fn=None, grad_scale=1.0):
+        self.shapes = [tuple(int(d) for d in s) for s in shapes]
+        sizes = []
+        for s in self.shapes:
+            n = 1
+            for d in s:
+                n *= d
+            sizes.append(n)
+        # every tensor starts on a 16-byte boundary (vector accesses in the kernels that consume the views)
+        self.offsets, off = [], 0
+        for n in sizes:
+            self.offsets.append(off)
+            off += (n + 3) // 4 * 4
+        self.numel = max(off, 4)
+        mk = lambda: torch.zeros(self.numel, dtype=torch.float32, device=device)
+        self.param_flat, self.grad_flat, self.m_flat, self.v_flat = mk(), mk(), mk(), mk()
+        cut = lambda flat: [flat[o:o + n].view(s) for o, n, s in zip(self.offsets, sizes, self.shapes)]
+        self.params, self.grads = cut(self.param_flat), cut(self.grad_flat)
+        per = max(int(bucket_bytes) // 4 // 4 * 4, 4)
+        self.buckets = [(lo, min(lo + per, self.numel)) for lo in range(0, self.numel, per)]
+        self.group, self.t = group, 0
+        self.hyper = dict(lr=lr, beta1=beta1, beta2=beta2, eps=eps, grad_scale=grad_scale)
+        if adam_fn is None:
+            from . import ops
+
+            def adam_fn(p, g, m, v, step):
+                ops.adam_step(p, g, m, v, step, **self.hyper)
+        self.adam_fn = adam_fn
+
+    def step(self):
+        """All-reduce (SUM) + Adam over every bucket; returns the step count t."""
+        self.t += 1
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+        works = []
+        if multi:
+            for lo, hi in self.buckets:
+                works.append(dist.all_reduce(self.grad_flat[lo:hi], op=dist.ReduceOp.SUM, group=self.group,
+                                             async_op=True))
+        for k, (lo, hi) in enumerate(self.buckets):
+            if multi:
+                works[k].wait()     # NCCL: the current stream waits for bucket k, the host does not
+            self.adam_fn(self.param_flat[lo:hi], self.grad_flat[lo:hi], self.m_flat[lo:hi], self.v_flat[lo:hi], self.t)
+        return self.t
+
+
+class _DevMem(object):
+    """A raw device range exposed to torch through __cuda_array_interface__ (zero copy)."""
+
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {'shape': (n,), 'typestr': typestr, 'data': (ptr, False), 'version': 2}
+
+
+class PeerArena(object):
+    """One cudaMalloc'ed, zero-filled block per rank, mapped into every rank of the node over CUDA IPC with this
+    rank's GPU as the accessor (csrc/vsl_optim.cu vsl_peer_alloc / vsl_ipc_*).  base[r] is rank r's block as a raw
+    device address valid in THIS process (base[rank] is the local block).  One node only."""
+
+    def __init__(self, nbytes, device, group=None):
+        import ctypes
+        from . import _lib
+        self._lib, self.lib = _lib, _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != 'cuda':
+            raise TypeError('PeerArena needs a CUDA device (this path has no CPU fallback)')
+        multi = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size(group) if multi else 1
+        self.rank = dist.get_rank(group) if multi else 0
+        self.nbytes = (int(nbytes) + 255) // 256 * 256
+        self._opened = []
+        with torch.cuda.device(self.device):
+            p = ctypes.c_void_p()
+            _lib.check(self.lib.vsl_peer_alloc(self.nbytes, ctypes.byref(p)))
+            self.local = p.value
+            self.base = [self.local]
+            if self.world > 1:
+                h = ctypes.create_string_buffer(64)
+                _lib.check(self.lib.vsl_ipc_get_handle(self.local, h))
+                handles = [None] * self.world
+                dist.all_gather_object(handles, h.raw, group=group)
+                self.base = []
+                for r in range(self.world):
+                    if r == self.rank:
+                        self.base.append(self.local)
+                        continue
+                    q = ctypes.c_void_p()
+                    _lib.check(self.lib.vsl_ipc_open(handles[r], ctypes.byref(q)))
+                    self._opened.append(q.value)
+                    self.base.append(q.value)
+                dist.barrier(group=group)       # every rank has opened every handle before anyone moves on
+        self._group = group
+
+    def view(self, byte_offset, n, dtype=torch.float32):
+        """torch view of n elements of the LOCAL block."""
+        typestr = {torch.float32: '<f4', torch.int32: '<i4'}[dtype]
+        return torch.as_tensor(_DevMem(self.local + byte_offset, n, typestr), device=self.device)
+
+    def close(self):
+        """Unmap the peers' blocks, wait for every rank to have done so, free the local block."""
+        if self.local is None:
+            return
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize()
+            for q in self._opened:
+                self.lib.vsl_ipc_close(q)
+            self._opened = []
+            if self.world > 1 and dist.is_initialized():
+                dist.barrier(group=self._group)
+            self.lib.vsl_peer_free(self.local)
+        self.local = None
+
+
+class PeerDataParallelAdam(object):
+    """dist.DataParallelAdam's step as ONE kernel over NVLink peer memory (csrc/vsl_optim.cu dp_adam_kernel):
+    rank r sums every rank's gradient over its shard of the flat arena with peer-to-peer loads (reduce-scatter),
+    applies tf.train.AdamOptimizer to the shard (the moments exist for the shard only) and stores the new
+    parameters into every rank's arena (all-gather).  Two flag barriers in peer memory bracket it; nothing goes
+    through NCCL after construction.  Replicas stay bit-identical (one owner per element, fixed sum order).
+
+    Same `params` / `grads` views as DataParallelAdam.  One node, world <= 16, CUDA only.  Call close() before
+    the process group is destroyed.
+    """
+
+    def __init__(self, shapes, device, lr, beta1=0.9, beta2=0.999, eps=1e-8, group=None, grad_scale=1.0):
+        from . import _lib
+        self._lib = _lib
+        self.lib = _lib.load()
+        device = torch.device(device)
+        self.shapes = [tuple(int(d) for d in s) for s in shapes]
+        sizes = []
+        for s in self.shapes:
+            n = 1
+            for d in s:
+                n *= d
+            sizes.append(n)
+        self.offsets, off = [], 0
+        for n in sizes:
+            self.offsets.append(off)
+            off += (n + 3) // 4 * 4
+        self.numel = max(off, 4)
+        # local block: [flags 256 B][timed-out word, padded to 256 B][parameters][gradients]
+        arena_bytes = 512 + 8 * self.numel
+        self.arena = PeerArena(arena_bytes, device, group)
+        self.world, self.rank = self.arena.world, self.arena.rank
+        if self.world > 16:
+            raise ValueError('PeerDataParallelAdam supports up to 16 ranks of one node')
+        per = (self.numel // 4 + self.world - 1) // self.world * 4          # shard length, a multiple of 4 floats
+        self.lo = min(self.rank * per, self.numel)
+        self.hi = min(self.lo + per, self.numel)
+        self.param_flat = self.arena.view(512, self.numel)
+        self.grad_flat = self.arena.view(512 + 4 * self.numel, self.numel)
+        self.timed_out = self.arena.view(256, 1, torch.int32)
+        mk = lambda n: torch.zeros(max(n, 4), dtype=torch.float32, device=device)
+        self.m_shard, self.v_shard = mk(self.hi - self.lo), mk(self.hi - self.lo)
+        cut = lambda flat: [flat[o:o + n].view(s) for o, n, s in zip(self.offsets, sizes, self.shapes)]
+        self.params, self.grads = cut(self.param_flat), cut(self.grad_flat)
+        self._pf = _lib.ptr_array(list(self.arena.base))
+        self._pp = _lib.ptr_array([b + 512 for b in self.arena.base])
+        self._pg = _lib.ptr_array([b + 512 + 4 * self.numel for b in self.arena.base])
+        self.hyper = (float(lr), float(beta1), float(beta2), float(eps))
+        self.grad_scale = float(grad_scale)
+        self.t, self.epoch = 0, 0
+
+    def _barrier(self, stream):
+        self.epoch += 1
+        self._lib.check(self.lib.vsl_peer_barrier(self._pf, self.rank, self.world, self.epoch, self.timed_out.data_ptr(),
+                                                  stream))
+
+    def step(self, stream=None):
+        """barrier (all gradients written) -> fused reduce-scatter + Adam + all-gather -> barrier (all parameters
+        landed).  Enqueued on the current stream; the host does not wait."""
+        self.t += 1
+        st = torch.cuda.current_stream().cuda_stream if stream is None else stream
+        if self.world > 1:
+            self._barrier(st)
+        self._lib.check(self.lib.vsl_dp_adam_step(self._pg, self._pp, self.rank, self.world, self.m_shard.data_ptr(),
+                                                  self.v_shard.data_ptr(), self.lo, self.hi, *self.hyper, self.t,
+                                                  self.grad_scale, st))
+        if self.world > 1:
+            self._barrier(st)
+        return self.t
+
+    def check_peers(self):
+        """Host-side check (synchronises): raises if a barrier ever gave up waiting for a peer."""
+        if int(self.timed_out.item()) != 0:
+            raise RuntimeError('a peer did not reach the barrier (rank %d of %d)' % (self.rank, self.world))
+
+    def close(self):
+        self.arena.close()

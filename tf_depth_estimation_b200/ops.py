@@ -467,6 +467,20 @@ def edge_aware_smooth_loss(disp, img):
     return _EdgeSmooth.apply(disp, img)
 
 
+def adam_step(param, grad, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0, stream=None):
+    """tf.train.AdamOptimizer(lr, beta1) applied in place to one flat float32 range (train_depth_then_cam_lr.py:413;
+    TensorFlow's ApplyAdam arithmetic).  param / grad / m / v: 1-D CUDA views cut at the same offset of their arenas."""
+    ts = (param, grad, m, v)
+    for t, name in zip(ts, ('param', 'grad', 'm', 'v')):
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            raise TypeError('%s must be a contiguous CUDA float32 tensor (this path has no CPU fallback)' % name)
+        if t.numel() != param.numel():
+            raise ValueError('param, grad, m, v must have the same number of elements')
+    check(_lib.load().vsl_adam_step(param.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), param.numel(),
+                                    float(lr), float(beta1), float(beta2), float(eps), int(step), float(grad_scale),
+                                    _stream() if stream is None else stream))
+
+
 def image_pyramid(img, num_scales):
     """tf.image.resize_area(img, [H/2^s, W/2^s]) for s = 0..S-1 (level 0 is `img` itself). No gradient."""
     lib = _lib.load()
