@@ -9,7 +9,8 @@
  *   - every pointer is a DEVICE pointer to contiguous float32, layouts as in the reference (NHWC images,
  *     [B,H,W] depth, [B,H,W,2] coords with x first, row-major 3x3 / 4x4 matrices);
  *   - the caller owns every buffer, including the workspace (`ws`, size from the matching *_ws_bytes());
- *     the library allocates nothing, frees nothing and keeps no global state;
+ *     the library allocates nothing, frees nothing and keeps no global state (one explicit exception: the peer
+ *     arenas of the data-parallel optimiser step, vsl_peer_alloc / vsl_peer_free at the end of this file);
  *   - all work is enqueued on `stream` (a cudaStream_t); no call synchronises;
  *   - return value: 0 = OK, < 0 = VSL_E_* argument error (nothing enqueued), > 0 = a raw cudaError_t;
  *     no C++ exception crosses the boundary;

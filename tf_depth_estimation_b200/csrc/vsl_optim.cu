@@ -8,6 +8,7 @@
 // (epsilon outside the bias correction, unlike torch.optim.Adam).  HBM-bound: 16 B read + 12 B written per
 // parameter; 16-byte accesses, gradient read evict-first (single use), grid = a multiple of the SM count.
 #pragma once
+#include <stdlib.h>
 #include <string.h>
 
 #include "vsl_common.cuh"
@@ -69,29 +70,51 @@ struct PeerPtrs {
 template <int WORLD>   // 0 = run-time world
 __global__ void __launch_bounds__(256)
 dp_adam_kernel(PeerPtrs pp, int world_rt, int rank, float* __restrict__ m, float* __restrict__ v, long long lo,
-               long long n4, AdamConsts c) {
+               long long n4, AdamConsts c, int dbg) {
+  constexpr int U = 4;    // float4s per thread and trip: U * world peer loads in flight before the first use
   const int world = WORLD ? WORLD : world_rt;
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
   float4* m4 = reinterpret_cast<float4*>(m);
   float4* v4 = reinterpret_cast<float4*>(v);
+  const float4* own_p = reinterpret_cast<const float4*>(pp.param[rank]);
   const long long lo4 = lo / 4;
-  for (long long i = tid; i < n4; i += nth) {
-    const long long gi = lo4 + i;
-    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long i0 = tid; i0 < n4; i0 += nth * U) {
+    float4 g[U], p[U], mm[U], vv[U];
+    // the far loads first (peers in rank order, this rank's own gradient among them) ...
+#pragma unroll
+    for (int u = 0; u < U; ++u) g[u] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int r = 0; r < (WORLD ? WORLD : kMaxPeers); ++r) {
       if (r < world) {
-        const float4 t = __ldcs(reinterpret_cast<const float4*>(pp.grad[r]) + gi);
-        g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+        const float4* src = reinterpret_cast<const float4*>(pp.grad[(dbg & 2) ? rank : r]) + lo4;
+        float4 t[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const long long i = i0 + u * nth;
+          t[u] = i < n4 ? __ldcs(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) { g[u].x += t[u].x; g[u].y += t[u].y; g[u].z += t[u].z; g[u].w += t[u].w; }
       }
     }
-    float4 p = reinterpret_cast<const float4*>(pp.param[rank])[gi], mm = m4[i], vv = v4[i];
-    adam_one(p.x, g.x, mm.x, vv.x, c); adam_one(p.y, g.y, mm.y, vv.y, c);
-    adam_one(p.z, g.z, mm.z, vv.z, c); adam_one(p.w, g.w, mm.w, vv.w, c);
-    m4[i] = mm; v4[i] = vv;
+    // ... then this rank's parameters and moments
 #pragma unroll
-    for (int r = 0; r < (WORLD ? WORLD : kMaxPeers); ++r)
-      if (r < world) reinterpret_cast<float4*>(pp.param[r])[gi] = p;
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * nth;
+      if (i < n4) { p[u] = own_p[lo4 + i]; mm[u] = m4[i]; vv[u] = v4[i]; }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * nth;
+      if (i < n4) {
+        adam_one(p[u].x, g[u].x, mm[u].x, vv[u].x, c); adam_one(p[u].y, g[u].y, mm[u].y, vv[u].y, c);
+        adam_one(p[u].z, g[u].z, mm[u].z, vv[u].z, c); adam_one(p[u].w, g[u].w, mm[u].w, vv[u].w, c);
+        m4[i] = mm[u]; v4[i] = vv[u];
+#pragma unroll
+        for (int r = 0; r < (WORLD ? WORLD : kMaxPeers); ++r)
+          if (r < world && (!(dbg & 1) || r == rank)) reinterpret_cast<float4*>(pp.param[r])[lo4 + i] = p[u];
+      }
+    }
   }
 }
 
@@ -217,15 +240,17 @@ int vsl_dp_adam_step(const float* const* peer_grads, float* const* peer_params, 
   c.lr_t = (float)((double)lr * sqrt(1.0 - pow((double)beta2, (double)step)) / (1.0 - pow((double)beta1, (double)step)));
   c.omb1 = 1.0f - beta1; c.omb2 = 1.0f - beta2; c.eps = eps; c.gscale = grad_scale;
   const long long n4 = (hi - lo) / 4;
-  const long long want = (n4 + 255) / 256;
+  const long long want = (n4 + 4 * 256 - 1) / (4 * 256);
   const int blocks = (int)(want < 148 * 8 ? want : 148 * 8);
   cudaStream_t st = (cudaStream_t)stream;
+  const char* de = getenv("VSL_DP_DEBUG");   // timing experiments only: 1 = no remote stores, 2 = no remote loads
+  const int dbg = de ? atoi(de) : 0;
   switch (world) {
-    case 1: dp_adam_kernel<1><<<blocks, 256, 0, st>>>(pp, world, rank, m_shard, v_shard, lo, n4, c); break;
-    case 2: dp_adam_kernel<2><<<blocks, 256, 0, st>>>(pp, world, rank, m_shard, v_shard, lo, n4, c); break;
-    case 4: dp_adam_kernel<4><<<blocks, 256, 0, st>>>(pp, world, rank, m_shard, v_shard, lo, n4, c); break;
-    case 8: dp_adam_kernel<8><<<blocks, 256, 0, st>>>(pp, world, rank, m_shard, v_shard, lo, n4, c); break;
-    default: dp_adam_kernel<0><<<blocks, 256, 0, st>>>(pp, world, rank, m_shard, v_shard, lo, n4, c); break;
+    case 1: dp_adam_kernel<1><<<blocks, 256, 0, st>>>(pp, world, rank, m_shard, v_shard, lo, n4, c, dbg); break;
+    case 2: dp_adam_kernel<2><<<blocks, 256, 0, st>>>(pp, world, rank, m_shard, v_shard, lo, n4, c, dbg); break;
+    case 4: dp_adam_kernel<4><<<blocks, 256, 0, st>>>(pp, world, rank, m_shard, v_shard, lo, n4, c, dbg); break;
+    case 8: dp_adam_kernel<8><<<blocks, 256, 0, st>>>(pp, world, rank, m_shard, v_shard, lo, n4, c, dbg); break;
+    default: dp_adam_kernel<0><<<blocks, 256, 0, st>>>(pp, world, rank, m_shard, v_shard, lo, n4, c, dbg); break;
   }
   return launch_status();
 }
