@@ -31,3 +31,32 @@ timeit('projective_inverse_warp fwd+bwd (d depth, d pose)', fb, npx * (12 + 4 + 
 timeit('compute_smooth_loss fwd', lambda: ops.compute_smooth_loss(disp), npx * 4)
 timeit('compute_exp_reg_loss fwd', lambda: ops.compute_exp_reg_loss(lg), npx * 8)
 timeit('image_pyramid (3 levels)', lambda: ops.image_pyramid(img, 4), npx * 12 * 1.328)
+
+# ---- consistent_depth_loss as one kernel each way; the extension ops; the flat Adam kernel
+tgt = cu(d['tgt'])
+coords = ops.projective_inverse_warp(img, depth, pose, K, 'eular')[1].detach()
+sd, pd = cu(1.0 / d['disp_pyr'][0]), cu(1.0 / d['disp_pyr'][0]) * 1.01
+timeit('consistent_depth_loss fwd', lambda: ops.consistent_depth_loss(sd, pd, coords), npx * (4 + 4 + 8 + 4))
+pdr = pd.clone().requires_grad_()
+def cfb():
+    e = ops.consistent_depth_loss(sd, pdr, coords)
+    e.backward(e)
+timeit('consistent_depth_loss fwd+bwd (d pred)', cfb, npx * (2 * (4 + 4 + 8) + 4 + 4 + 4))
+timeit('ssim_loss fwd (mean, no map)', lambda: ops.ssim_loss(img, tgt), npx * 24)
+ir = img.clone().requires_grad_()
+def sfb():
+    ops.ssim_loss(ir, tgt).backward()
+timeit('ssim_loss fwd+bwd (d x)', sfb, npx * (24 + 24 + 12))
+timeit('edge_aware_smooth_loss fwd', lambda: ops.edge_aware_smooth_loss(disp, tgt), npx * 16)
+dpr = disp.clone().requires_grad_()
+def efb():
+    ops.edge_aware_smooth_loss(dpr, tgt).backward()
+timeit('edge_aware_smooth_loss fwd+bwd (d disp)', efb, npx * (16 + 16 + 4))
+NP = 33_200_000
+p_, g_, m_, v_ = (torch.zeros(NP, device=dev) for _ in range(4))
+g_.normal_()
+step = [0]
+def adam():
+    step[0] += 1
+    ops.adam_step(p_, g_, m_, v_, step[0], lr=2e-4)
+timeit('adam_step, 33.2 M parameters', adam, NP * 28)

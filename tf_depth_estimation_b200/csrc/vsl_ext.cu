@@ -30,28 +30,24 @@ struct SsimDims {
 };
 
 // rows [row0, row0+nrows) x flat columns [col0, col0+ncols) of image b into dst (row stride `ld`), zero outside
-VSL_DEV void ssim_load_tile(float* dst, int ld, const float* __restrict__ img, int row0, int col0, int nrows,
-                            int ncols, int H, int WC) {
-  for (int i = threadIdx.x; i < nrows * ncols; i += kSsThreads) {
-    const int r = i / ncols, c = i - r * ncols;
+template <int LD, int NROWS>   // LD: row pitch of the tile (a constant, so the index split is a multiply-shift)
+VSL_DEV void ssim_load_tile(float* dst, const float* __restrict__ img, int row0, int col0, int ncols, int H, int WC) {
+  for (int i = threadIdx.x; i < NROWS * LD; i += kSsThreads) {
+    const int r = i / LD, c = i - r * LD;
+    if (c >= ncols) continue;
     const int gr = row0 + r, gc = col0 + c;
     float v = 0.f;
     if ((unsigned)gr < (unsigned)H && (unsigned)gc < (unsigned)WC) v = __ldg(img + (size_t)gr * WC + gc);
-    dst[r * ld + c] = v;
+    dst[i] = v;
   }
 }
 
 struct SsimWin { float S, ax, ay, beta, gamma; };
 
-// Window whose top-left element is at x[0] / y[0]; row stride ld, column stride C.
+// The 9 + 9 values of one window -> SSIM (and, with GRAD, the coefficients of its derivative).
 template <bool GRAD>
-VSL_DEV SsimWin ssim_window(const float* x, const float* y, int ld, int C) {
+VSL_DEV SsimWin ssim_stats(const float (&xv)[9], const float (&yv)[9]) {
   const float C1 = 1e-4f, C2 = 9e-4f, ninth = 1.0f / 9.0f;
-  float xv[9], yv[9];
-#pragma unroll
-  for (int i = 0; i < 3; ++i)
-#pragma unroll
-    for (int j = 0; j < 3; ++j) { xv[i * 3 + j] = x[i * ld + j * C]; yv[i * 3 + j] = y[i * ld + j * C]; }
   float sx = 0.f, sy = 0.f;
 #pragma unroll
   for (int k = 0; k < 9; ++k) { sx += xv[k]; sy += yv[k]; }
@@ -79,6 +75,17 @@ VSL_DEV SsimWin ssim_window(const float* x, const float* y, int ld, int C) {
   return w;
 }
 
+// Window whose top-left element is at x[0] / y[0]; row stride ld, column stride C.
+template <bool GRAD>
+VSL_DEV SsimWin ssim_window(const float* x, const float* y, int ld, int C) {
+  float xv[9], yv[9];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { xv[i * 3 + j] = x[i * ld + j * C]; yv[i * 3 + j] = y[i * ld + j * C]; }
+  return ssim_stats<GRAD>(xv, yv);
+}
+
 __global__ void __launch_bounds__(kSsThreads)
 ssim_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y, SsimDims d, float* __restrict__ map,
                 float* __restrict__ partial) {
@@ -87,18 +94,36 @@ ssim_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y, SsimDi
   const int b = blockIdx.z, i0 = blockIdx.y * kSsTY, f0 = blockIdx.x * kSsTX;
   const size_t img = (size_t)b * d.H * d.WC;
   const int ncols = kSsTX + 2 * d.C;
-  ssim_load_tile(tx, kSsCfW, x + img, i0, f0, kSsTY + 2, ncols, d.H, d.WC);
-  ssim_load_tile(ty, kSsCfW, y + img, i0, f0, kSsTY + 2, ncols, d.H, d.WC);
+  ssim_load_tile<kSsCfW, kSsTY + 2>(tx, x + img, i0, f0, ncols, d.H, d.WC);
+  ssim_load_tile<kSsCfW, kSsTY + 2>(ty, y + img, i0, f0, ncols, d.H, d.WC);
   __syncthreads();
   float acc[1] = {0.f};
-  for (int e = threadIdx.x; e < kSsTY * kSsTX; e += kSsThreads) {
-    const int r = e / kSsTX, c = e - r * kSsTX;
-    const int wi = i0 + r, wf = f0 + c;
-    if (wi < d.H - 2 && wf < d.OWC) {
-      const SsimWin w = ssim_window<false>(tx + r * kSsCfW + c, ty + r * kSsCfW + c, kSsCfW, d.C);
-      const float v = fminf(fmaxf(0.5f * (1.0f - w.S), 0.f), 1.f);
-      if (map != nullptr) map[((size_t)b * (d.H - 2) + wi) * d.OWC + wf] = v;
-      acc[0] += v;
+  {
+    // a thread owns one flat column and walks down half of the tile's rows with the window in registers: each
+    // step loads only the new bottom row (6 shared-memory reads per window instead of 18)
+    constexpr int kRowsPer = kSsTY / (kSsThreads / kSsTX);
+    const int c = threadIdx.x % kSsTX, r0 = (threadIdx.x / kSsTX) * kRowsPer;
+    const int wf = f0 + c, C = d.C;
+    float xv[9], yv[9];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      xv[3 + j] = tx[r0 * kSsCfW + c + j * C];       yv[3 + j] = ty[r0 * kSsCfW + c + j * C];
+      xv[6 + j] = tx[(r0 + 1) * kSsCfW + c + j * C]; yv[6 + j] = ty[(r0 + 1) * kSsCfW + c + j * C];
+    }
+#pragma unroll
+    for (int k = 0; k < kRowsPer; ++k) {
+      const int r = r0 + k, wi = i0 + r;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        xv[j] = xv[3 + j]; xv[3 + j] = xv[6 + j]; xv[6 + j] = tx[(r + 2) * kSsCfW + c + j * C];
+        yv[j] = yv[3 + j]; yv[3 + j] = yv[6 + j]; yv[6 + j] = ty[(r + 2) * kSsCfW + c + j * C];
+      }
+      if (wi < d.H - 2 && wf < d.OWC) {
+        const SsimWin w = ssim_stats<false>(xv, yv);
+        const float v = fminf(fmaxf(0.5f * (1.0f - w.S), 0.f), 1.f);
+        if (map != nullptr) map[((size_t)b * (d.H - 2) + wi) * d.OWC + wf] = v;
+        acc[0] += v;
+      }
     }
   }
   acc[0] *= d.inv_n;
@@ -117,13 +142,14 @@ ssim_bwd_kernel(const float* __restrict__ x, const float* __restrict__ y, SsimDi
   const size_t img = (size_t)b * d.H * d.WC;
   // pixels of rows [i0, i0+8), flat columns [f0, f0+128): windows of rows [i0-2, i0+8), columns [f0-2C, f0+128),
   // inputs of rows [i0-2, i0+10), columns [f0-2C, f0+128+2C)
-  ssim_load_tile(tx, kSsInW, x + img, i0 - 2, f0 - 2 * C, kSsInH, kSsTX + 4 * C, d.H, d.WC);
-  ssim_load_tile(ty, kSsInW, y + img, i0 - 2, f0 - 2 * C, kSsInH, kSsTX + 4 * C, d.H, d.WC);
+  ssim_load_tile<kSsInW, kSsInH>(tx, x + img, i0 - 2, f0 - 2 * C, kSsTX + 4 * C, d.H, d.WC);
+  ssim_load_tile<kSsInW, kSsInH>(ty, y + img, i0 - 2, f0 - 2 * C, kSsTX + 4 * C, d.H, d.WC);
   __syncthreads();
   const float g_mean = mean_path ? (g_loss != nullptr ? g_loss[0] : 1.0f) * d.inv_n : 0.f;
   const int wcols = kSsTX + 2 * C;
-  for (int e = threadIdx.x; e < kSsCfH * wcols; e += kSsThreads) {
-    const int r = e / wcols, c = e - r * wcols;
+  for (int e = threadIdx.x; e < kSsCfH * kSsCfW; e += kSsThreads) {
+    const int r = e / kSsCfW, c = e - r * kSsCfW;
+    if (c >= wcols) continue;
     const int wi = i0 - 2 + r, wf = f0 - 2 * C + c;
     float ax = 0.f, ay = 0.f, be = 0.f, ga = 0.f;
     if ((unsigned)wi < (unsigned)(d.H - 2) && (unsigned)wf < (unsigned)d.OWC) {
