@@ -101,3 +101,59 @@ def test_geometry_building_blocks(mods):
     Re = L.euler2mat(cu(e[:, 2:3]), cu(e[:, 1:2]), cu(e[:, 0:1]))
     assert tuple(Re.shape) == (4, 1, 3, 3)
     assert (Re.cpu() - O.euler2mat(e[:, 2:3], e[:, 1:2], e[:, 0:1])).abs().max() <= 1e-6
+
+
+def _depth_golden():
+    import ast
+    import numpy as np
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'depth_losses_golden.npz'))
+    cases = {'single': {}, 'pair': {}}
+    for k in z.files:
+        if '/' in k:
+            c, n = k.split('/', 1)
+            cases[c][n] = torch.from_numpy(np.array(z[k]))
+    flags = ast.literal_eval(str(z['flags']))
+    return cases, type('FLAGS', (object,), flags)
+
+
+def test_composite_depth_losses_golden(mods):
+    """my_losses.py:46 / :101 executed from the reference's own source over the TF1 shim (tests/golden/
+    make_golden_depth_losses.py; DeMoN's un-vendored ops restated) against the drop-in on the GPU."""
+    _, _, my_losses = mods
+    cases, FLAGS = _depth_golden()
+    S = FLAGS.num_scales
+    c = cases['single']
+    preds = [cu(c['pred%d' % s], True) for s in range(S)]
+    depth_loss, smooth_loss, sig = my_losses.compute_loss_single_depth(preds, cu(c['label']), int(c['step']), FLAGS)
+    assert smooth_loss == 0
+    assert rel_err(depth_loss, c['depth_loss']) <= 1e-5 and rel_err(sig, c['sig_loss']) <= 1e-5
+    (depth_loss + sig).backward()
+    for s in range(S):
+        assert rel_err(preds[s].grad, c['g_pred%d_f64' % s]) <= 1e-4
+
+    c = cases['pair']
+    n = S - 2
+    pdl = [cu(c['pred_depth_left%d' % i], True) for i in range(n)]
+    pdr = [cu(c['pred_depth_right%d' % i], True) for i in range(n)]
+    p_r, p_l = cu(c['pred_poses_right'], True), cu(c['pred_poses_left'], True)
+    out = my_losses.compute_loss_pairwise_depth(cu(c['image_left']), cu(c['image_right']), pdl, p_r, None, pdr, p_l, None,
+                                                cu(c['gt_right_cam']), cu(c['intrinsics']), cu(c['label']), FLAGS,
+                                                int(c['step']))
+    assert len(out) == 11 and out[2] == 0 and out[3] == 0 and out[5] == 0
+    assert rel_err(out[0], c['depth_loss']) <= 1e-5
+    assert rel_err(out[1], c['cam_loss']) <= 1e-5
+    assert rel_err(out[4], c['sig_loss']) <= 1e-5
+    for name, lst in zip(('left_image', 'right_image', 'proj_image_left', 'proj_image_right', 'proj_error'), out[6:]):
+        assert len(lst) == n
+        for i, t in enumerate(lst):
+            assert float((t.detach().cpu() - c['%s%d' % (name, i)]).abs().max()) <= 1e-5
+    Rr = torch.Generator().manual_seed(7)
+    extra = sum((w * torch.randn(w.shape, generator=Rr).to(DEV)).sum() for w in out[9]) * 1e-3
+    (out[0] + out[1] + out[4] + extra).backward()
+    for i in range(n):
+        assert rel_err(pdl[i].grad, c['g_pdl%d_f64' % i]) <= 1e-4
+        # through the warp: per-pixel gradients away from the bilinear kinks
+        diff = (pdr[i].grad.cpu().double() - c['g_pdr%d_f64' % i]).abs()
+        assert float((diff > 1e-4 * c['g_pdr%d_f64' % i].abs().max()).double().mean()) < 0.03
+    assert rel_err(p_r.grad, c['g_poses_r_f64']) <= 1e-4
+    assert rel_err(p_l.grad, c['g_poses_l_f64']) <= 1e-4

@@ -141,3 +141,26 @@ def test_composite_loss(golden):
                 if fl['mask']:
                     assert rel_err(grads[S + 1 + s], c['g_logits%d_%s' % (s, tag)]) <= tol
             assert rel_err(grads[S], c['g_poses_' + tag]) <= tol
+
+
+def test_depth_loss_golden_file_is_consistent():
+    """tests/golden/depth_losses_golden.npz (the reference's compute_loss_single_depth body executed over the shim)
+    against a direct restatement from the oracle's building blocks: pins the fixture and oracle/demon_ops.py."""
+    import ast
+    import os
+    import numpy as np
+    from oracle import demon_ops as D
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'depth_losses_golden.npz'))
+    F = ast.literal_eval(str(z['flags']))
+    label = torch.from_numpy(z['single/label'])
+    w = float(D.ease_out_quad(float(z['single/step']), 0, F['depth_sig_weight'], float(F['max_steps'] // 3)))
+    depth, sig = 0.0, 0.0
+    for s in range(F['num_scales']):
+        pred = torch.from_numpy(z['single/pred%d' % s])
+        lab = O.resize_area(label, F['resizedheight'] >> s, F['resizedwidth'] >> s)
+        sig = sig + w * D.pointwise_l2_loss(D.scale_invariant_gradient(pred.permute(0, 3, 1, 2), [2], [1]),
+                                           D.scale_invariant_gradient(lab.permute(0, 3, 1, 2), [2], [1]), 1e-6)
+        depth = depth + D.replace_nonfinite(lab - pred).abs().mean() * F['depth_weight'] / 2 ** s
+    assert abs(float(depth) - float(z['single/depth_loss'])) <= 1e-6 * float(z['single/depth_loss'])
+    assert abs(float(sig) - float(z['single/sig_loss'])) <= 1e-6 * float(z['single/sig_loss'])
+    assert z['pair/zeros'].tolist() == [0.0, 0.0, 0.0]

@@ -176,7 +176,7 @@ warp_bwd_kernel(const float* __restrict__ img, const float* __restrict__ depth, 
     acc[4] = du1 * c0; acc[5] = du1 * c1; acc[6] = du1 * c2; acc[7] = du1;
     acc[8] = du2 * c0; acc[9] = du2 * c1; acc[10] = du2 * c2; acc[11] = du2;
   }
-  if (partial != nullptr) block_sum<12>(acc, scratch, partial + ((size_t)b * gridDim.x + blockIdx.x) * 12);
+  if (partial != nullptr) block_sum_bfly<12>(acc, scratch, partial + ((size_t)b * gridDim.x + blockIdx.x) * 12);
 }
 
 // One warp per batch element: fixed-order sum of the block partials, dT = K4^T dP (+ upstream dT), then the
