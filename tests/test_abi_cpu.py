@@ -83,3 +83,31 @@ def test_missing_library_fails_loudly(monkeypatch, lib):
     monkeypatch.setattr(_lib, 'LIB_PATH', '/nonexistent/libvsl.so')
     with pytest.raises(ImportError, match='no CPU or eager fallback'):
         _lib.load()
+
+
+def test_error_codes_of_the_extension_and_optimiser_entries(lib):
+    """Argument checks return before anything touches a device (fake non-NULL pointers are never dereferenced)."""
+    assert lib.vsl_consist_fwd(None, 16, 16, 2, 8, 8, 8, 8, 16, None) == -1
+    assert lib.vsl_consist_fwd(16, 16, 20, 2, 8, 8, 8, 8, 16, None) == -4             # coords not 8-byte aligned
+    assert lib.vsl_consist_bwd(16, 16, 16, 0, 8, 8, 8, 8, 16, None, 16, None, None) == -2
+    assert lib.vsl_ssim_fwd(16, 16, 2, 2, 8, 3, 16, None, None, None) == -2            # H < 3: no 3x3 window
+    assert lib.vsl_ssim_fwd(16, 16, 2, 8, 8, 5, 16, None, None, None) == -2            # C > 4
+    assert lib.vsl_ssim_fwd(16, 16, 2, 8, 8, 3, None, None, None, None) == -1          # neither map nor loss
+    assert lib.vsl_ssim_fwd(16, 16, 2, 8, 8, 3, None, 16, None, None) == -1            # loss without workspace
+    assert lib.vsl_ssim_bwd(16, 16, 2, 8, 8, 3, None, None, 0, 16, None, None) == -1   # no upstream gradient
+    assert lib.vsl_ssim_ws_bytes(2, 8, 8, 3) == 4 * 1 * 1 * 2 and lib.vsl_ssim_ws_bytes(2, 2, 8, 3) == 0
+    assert lib.vsl_edge_smooth_fwd(16, 16, 2, 1, 8, 3, 16, 16, None) == -2             # H < 2
+    assert lib.vsl_edge_smooth_bwd(16, 16, 2, 8, 8, 3, None, None, None, None) == -1
+    assert lib.vsl_adam_step(None, 16, 16, 16, 10, 1e-3, 0.9, 0.999, 1e-8, 1, 1.0, None) == -1
+    assert lib.vsl_adam_step(16, 16, 16, 16, 10, 1e-3, 0.9, 0.999, 1e-8, 0, 1.0, None) == -2     # t >= 1
+    assert lib.vsl_adam_step(16, 20, 16, 16, 10, 1e-3, 0.9, 0.999, 1e-8, 1, 1.0, None) == -4     # ranges out of phase
+    ptrs = _lib.ptr_array([16, 32])
+    assert lib.vsl_dp_adam_step(ptrs, ptrs, 2, 2, 16, 16, 0, 8, 1e-3, 0.9, 0.999, 1e-8, 1, 1.0, None) == -2   # rank
+    assert lib.vsl_dp_adam_step(ptrs, ptrs, 0, 2, 16, 16, 0, 6, 1e-3, 0.9, 0.999, 1e-8, 1, 1.0, None) == -2   # hi % 4
+    assert lib.vsl_dp_adam_step(ptrs, ptrs, 0, 2, 16, 16, 8, 8, 1e-3, 0.9, 0.999, 1e-8, 1, 1.0, None) == 0    # empty shard
+    assert lib.vsl_dp_adam_step(_lib.ptr_array([16, 36]), ptrs, 0, 2, 16, 16, 0, 8, 1e-3, 0.9, 0.999, 1e-8, 1, 1.0,
+                                None) == -4
+    assert lib.vsl_peer_barrier(ptrs, 0, 17, 1, None, None) == -2                      # world > 16
+    assert lib.vsl_peer_barrier(None, 0, 2, 1, None, None) == -1
+    assert lib.vsl_ipc_get_handle(None, None) == -1 and lib.vsl_ipc_open(None, None) == -1
+    assert lib.vsl_peer_alloc(0, ctypes.byref(ctypes.c_void_p())) == -2
