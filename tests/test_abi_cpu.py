@@ -111,3 +111,51 @@ def test_error_codes_of_the_extension_and_optimiser_entries(lib):
     assert lib.vsl_peer_barrier(None, 0, 2, 1, None, None) == -1
     assert lib.vsl_ipc_get_handle(None, None) == -1 and lib.vsl_ipc_open(None, None) == -1
     assert lib.vsl_peer_alloc(0, ctypes.byref(ctypes.c_void_p())) == -2
+
+
+def test_drop_in_modules_export_the_reference_names():
+    """what `from utils import *` / `from utils_lr import *` / `from my_losses import *` must provide
+    (names and leading argument names as in the reference; import only, nothing is computed without a GPU)."""
+    import importlib
+    import inspect
+    import sys
+    compat = os.path.join(ROOT, 'tf_depth_estimation_b200', 'compat')
+    sys.path.insert(0, compat)
+    saved = {n: sys.modules.pop(n, None) for n in ('utils', 'utils_lr', 'my_losses')}
+    try:
+        utils, utils_lr, my_losses = (importlib.import_module(n) for n in ('utils', 'utils_lr', 'my_losses'))
+        for m in (utils, utils_lr, my_losses):
+            assert os.path.dirname(os.path.abspath(m.__file__)) == compat
+        want = {
+            utils: {'euler2mat': ['z', 'y', 'x'], 'pose_vec2mat': ['vec'], 'pixel2cam': ['depth', 'pixel_coords', 'intrinsics'],
+                    'cam2pixel': ['cam_coords', 'proj'], 'meshgrid': ['batch', 'height', 'width'],
+                    'projective_inverse_warp': ['img', 'depth', 'pose', 'intrinsics'],
+                    'optflow_warp': ['img', 'flowx', 'flowy'], 'bilinear_sampler': ['imgs', 'coords'],
+                    'depth_optflow': ['src_pixel_coords']},
+            utils_lr: {'euler2mat': ['z', 'y', 'x'], 'axis_angle_to_rotation_matrix': ['axis', 'angle'],
+                       'pose_vec2mat': ['vec', 'format'], 'pixel2cam': ['depth', 'pixel_coords', 'intrinsics'],
+                       'cam2pixel': ['cam_coords', 'proj'], 'meshgrid': ['batch', 'height', 'width'],
+                       'projective_inverse_warp': ['img', 'depth', 'pose', 'intrinsics', 'format'],
+                       'bilinear_sampler': ['imgs', 'coords'],
+                       'consistent_depth_loss': ['src_depth', 'pred_src_depth', 'coords']},
+            my_losses: {'get_reference_explain_mask': ['downscaling', 'FLAGS'], 'compute_smooth_loss': ['pred_disp'],
+                        'compute_exp_reg_loss': ['pred', 'ref'],
+                        'compute_loss_single_depth': ['pred_depth', 'label', 'global_step', 'FLAGS'],
+                        'compute_loss_pairwise_depth': ['image_left', 'image_right', 'pred_depth_left', 'pred_poses_right',
+                                                        'pred_exp_logits_left', 'pred_depth_right', 'pred_poses_left',
+                                                        'pred_exp_logits_right', 'gt_right_cam', 'intrinsics', 'label',
+                                                        'FLAGS', 'global_step'],
+                        'view_synthesis_loss': ['tgt', 'srcs']},
+        }
+        for mod, names in want.items():
+            for name, args in names.items():
+                fn = getattr(mod, name)
+                got = list(inspect.signature(fn).parameters)[:len(args)]
+                assert got == args, (mod.__name__, name, got)
+                assert name in mod.__all__, (mod.__name__, name)
+    finally:
+        sys.path.remove(compat)
+        for n, m in saved.items():
+            sys.modules.pop(n, None)
+            if m is not None:
+                sys.modules[n] = m
