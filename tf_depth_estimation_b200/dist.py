@@ -58,6 +58,21 @@ def reduce_sum_(tensors, group=None):
     return tensors
 
 
+def _flat_layout(shapes):
+    """Layout of a list of tensors inside one flat float32 arena: every tensor starts on a 16-byte boundary (the
+    kernels that consume the views use vector accesses).  -> (shapes, sizes, offsets, numel)."""
+    shapes = [tuple(int(d) for d in s) for s in shapes]
+    sizes, offsets, off = [], [], 0
+    for s in shapes:
+        n = 1
+        for d in s:
+            n *= d
+        sizes.append(n)
+        offsets.append(off)
+        off += (n + 3) // 4 * 4
+    return shapes, sizes, offsets, max(off, 4)
+
+
 class DataParallelAdam(object):
     """The data-parallel optimiser step of SURVEY.md 8e / 8f.3: every parameter, gradient and Adam moment lives in
     one flat float32 arena; step() all-reduces the gradient arena bucket by bucket (asynchronously: NCCL's stream)
@@ -74,19 +89,7 @@ class DataParallelAdam(object):
 
     def __init__(self, shapes, device, lr, beta1=0.9, beta2=0.999, eps=1e-8, bucket_bytes=32 << 20, group=None,
                  adam_fn=None, grad_scale=1.0):
-        self.shapes = [tuple(int(d) for d in s) for s in shapes]
-        sizes = []
-        for s in self.shapes:
-            n = 1
-            for d in s:
-                n *= d
-            sizes.append(n)
-        # every tensor starts on a 16-byte boundary (vector accesses in the kernels that consume the views)
-        self.offsets, off = [], 0
-        for n in sizes:
-            self.offsets.append(off)
-            off += (n + 3) // 4 * 4
-        self.numel = max(off, 4)
+        self.shapes, sizes, self.offsets, self.numel = _flat_layout(shapes)
         mk = lambda: torch.zeros(self.numel, dtype=torch.float32, device=device)
         self.param_flat, self.grad_flat, self.m_flat, self.v_flat = mk(), mk(), mk(), mk()
         cut = lambda flat: [flat[o:o + n].view(s) for o, n, s in zip(self.offsets, sizes, self.shapes)]
@@ -200,18 +203,7 @@ class PeerDataParallelAdam(object):
         self._lib = _lib
         self.lib = _lib.load()
         device = torch.device(device)
-        self.shapes = [tuple(int(d) for d in s) for s in shapes]
-        sizes = []
-        for s in self.shapes:
-            n = 1
-            for d in s:
-                n *= d
-            sizes.append(n)
-        self.offsets, off = [], 0
-        for n in sizes:
-            self.offsets.append(off)
-            off += (n + 3) // 4 * 4
-        self.numel = max(off, 4)
+        self.shapes, sizes, self.offsets, self.numel = _flat_layout(shapes)
         # local block: [flags 256 B][timed-out word, padded to 256 B][parameters][gradients]
         arena_bytes = 512 + 8 * self.numel
         self.arena = PeerArena(arena_bytes, device, group)
