@@ -153,7 +153,7 @@ def test_depth_loss_golden_file_is_consistent():
     z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'depth_losses_golden.npz'))
     F = ast.literal_eval(str(z['flags']))
     label = torch.from_numpy(z['single/label'])
-    w = float(D.ease_out_quad(float(z['single/step']), 0, F['depth_sig_weight'], float(F['max_steps'] // 3)))
+    w = float(D.ease_out_quad(float(z['single/step'].reshape(-1)[0]), 0, F['depth_sig_weight'], float(F['max_steps'] // 3)))
     depth, sig = 0.0, 0.0
     for s in range(F['num_scales']):
         pred = torch.from_numpy(z['single/pred%d' % s])
@@ -161,6 +161,51 @@ def test_depth_loss_golden_file_is_consistent():
         sig = sig + w * D.pointwise_l2_loss(D.scale_invariant_gradient(pred.permute(0, 3, 1, 2), [2], [1]),
                                            D.scale_invariant_gradient(lab.permute(0, 3, 1, 2), [2], [1]), 1e-6)
         depth = depth + D.replace_nonfinite(lab - pred).abs().mean() * F['depth_weight'] / 2 ** s
-    assert abs(float(depth) - float(z['single/depth_loss'])) <= 1e-6 * float(z['single/depth_loss'])
-    assert abs(float(sig) - float(z['single/sig_loss'])) <= 1e-6 * float(z['single/sig_loss'])
+    assert abs(float(depth) - float(z['single/depth_loss'].reshape(-1)[0])) <= 1e-6 * float(z['single/depth_loss'].reshape(-1)[0])
+    assert abs(float(sig) - float(z['single/sig_loss'].reshape(-1)[0])) <= 1e-6 * float(z['single/sig_loss'].reshape(-1)[0])
     assert z['pair/zeros'].tolist() == [0.0, 0.0, 0.0]
+
+
+def test_extension_and_optimiser_oracles_known_answers():
+    """The oracle pieces that have NO reference implementation behind them (SSIM, edge-aware smoothness: absent from
+    the reference; Adam and DeMoN's ops: un-vendored third parties) at least reproduce hand-derived values."""
+    from oracle import demon_ops as D
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(1, 6, 7, 2, generator=g, dtype=torch.float64)
+    assert float(O.ssim_dissimilarity(x, x).abs().max()) <= 1e-12                       # SSIM(x, x) = 1
+    one, zero = torch.ones(1, 4, 4, 1, dtype=torch.float64), torch.zeros(1, 4, 4, 1, dtype=torch.float64)
+    want = 0.5 * (1 - 1e-4 / (1 + 1e-4))                                                # means 1 / 0, no variance
+    assert float((O.ssim_dissimilarity(one, zero) - want).abs().max()) <= 1e-12
+    # one window by hand
+    a, b = x[:, :3, :3, :1], torch.rand(1, 3, 3, 1, generator=g, dtype=torch.float64)
+    ma, mb = a.mean(), b.mean()
+    va, vb, cab = ((a - ma) ** 2).mean(), ((b - mb) ** 2).mean(), ((a - ma) * (b - mb)).mean()
+    s = (2 * ma * mb + 1e-4) * (2 * cab + 9e-4) / ((ma * ma + mb * mb + 1e-4) * (va + vb + 9e-4))
+    assert abs(float(O.ssim_dissimilarity(a, b)) - float(torch.clamp((1 - s) / 2, 0, 1))) <= 1e-12
+    # edge-aware smoothness: a unit disparity step across a flat image costs 1 / (B H (W - 1)) per crossing row
+    disp = torch.zeros(1, 4, 6, 1, dtype=torch.float64)
+    disp[:, :, 3:] = 1.0
+    img = torch.full((1, 4, 6, 3), 0.5, dtype=torch.float64)
+    assert abs(float(O.edge_aware_smooth_loss(disp, img)) - 4.0 / (4 * 5)) <= 1e-12
+    img[:, :, 3:] += 0.2                                                                 # an image edge at the same place
+    assert abs(float(O.edge_aware_smooth_loss(disp, img)) - 4.0 / (4 * 5) * float(torch.exp(torch.tensor(-0.2)))) <= 1e-7
+    # Adam, first step: update = lr g / (|g| + eps / sqrt(1 - beta2)) with the float32-rounded hyper-parameters
+    import numpy as np
+    gg = torch.tensor([2.0, -0.5, 1e-9], dtype=torch.float64)
+    p, m, v = O.adam_step_tf(torch.zeros(3, dtype=torch.float64), gg, torch.zeros(3, dtype=torch.float64),
+                             torch.zeros(3, dtype=torch.float64), 1, 0.1)
+    lr, b2, eps = float(np.float32(0.1)), float(np.float32(0.999)), float(np.float32(1e-8))
+    assert torch.allclose(p, -lr * gg / (gg.abs() + eps / (1 - b2) ** 0.5), rtol=1e-12, atol=0)
+    assert torch.allclose(m, (1 - float(np.float32(0.9))) * gg, rtol=1e-12, atol=0)
+    # DeMoN ops: scale-invariant gradient of a horizontal ramp, hole handling, easing
+    ramp = torch.arange(6, dtype=torch.float64).reshape(1, 1, 1, 6).repeat(1, 1, 5, 1)
+    sig = D.scale_invariant_gradient(ramp, [2], [1], 0.001)
+    assert tuple(sig.shape) == (1, 2, 5, 6)
+    xs = torch.arange(4, dtype=torch.float64)
+    assert torch.allclose(sig[0, 0, 0, :4], 2 / (xs + 2 + xs + 0.001)) and float(sig[0, 0, :, 4:].abs().max()) == 0
+    assert float(sig[0, 1].abs().max()) == 0                                            # constant along y
+    hole = torch.tensor([1.0, float('inf'), float('nan'), -2.0])
+    assert D.replace_nonfinite(hole).tolist() == [1.0, 0.0, 0.0, -2.0]
+    assert abs(float(D.pointwise_l2_loss(torch.full((1, 2, 1, 1), 3.0), torch.zeros(1, 2, 1, 1), 0.0)) - 18 ** 0.5) <= 1e-6
+    assert float(D.ease_out_quad(0.0, 0, 2.0, 100.0)) == 0.0 and float(D.ease_out_quad(100.0, 0, 2.0, 100.0)) == 2.0
+    assert abs(float(D.ease_out_quad(50.0, 0, 2.0, 100.0)) - 1.5) <= 1e-12 and float(D.ease_out_quad(1e9, 0, 2.0, 100.0)) == 2.0
