@@ -110,7 +110,15 @@ def _peer_worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs of one node (NVLink peer memory)')
+def _two_peer_gpus():
+    try:
+        return torch.cuda.device_count() >= 2 and torch.cuda.can_device_access_peer(0, 1) and \
+            torch.cuda.can_device_access_peer(1, 0)
+    except Exception:
+        return False
+
+
+@pytest.mark.skipif(not _two_peer_gpus(), reason='needs 2 GPUs of one node with peer access (NVLink peer memory)')
 def test_peer_data_parallel_adam_two_ranks(tmp_path):
     import socket
     import torch.multiprocessing as mp
