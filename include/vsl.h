@@ -151,7 +151,7 @@ int vsl_pyramid(const float* img /*[B,H,W,C]*/, int B, int H, int W, int C, int 
  *      explainability mask of train_depth_then_cam_lr.py:297-328 (or a constant validity mask,
  *      train_optflow_combine.py:176,187-188), forward AND backward in one pass over the data.
  *
- *      losses[3] = (pixel, smooth, exp); gradients are those of (pixel + smooth + exp) * loss_scale.  */
+ *      losses[4] = (pixel, smooth, exp, pixel + smooth + exp); gradients are those of losses[3] * loss_scale.  */
 typedef struct {
   int B, H, W;           /* level-0 size; level s is (H>>s) x (W>>s) */
   int S, V;              /* scales (<= VSL_MAX_SCALES), source views (<= VSL_MAX_VIEWS) */
@@ -182,10 +182,17 @@ int vsl_loss_fwd_bwd(const VslLossDesc* d,
                      const float* poses, const float* K_pyr /*[B,S,3,3]*/,
                      const float* const* logits_pyr /*S x [B,Hs,Ws,2V], MASK_EXP*/,
                      const float* const* mask_pyr /*S x [B,Hs,Ws,1], MASK_CONST*/,
-                     float* losses /*device [3]*/, float* const* g_x_pyr /*S x [B,Hs,Ws,1]*/,
+                     float* losses /*device [4]*/, float* const* g_x_pyr /*S x [B,Hs,Ws,1]*/,
                      float* g_poses /*same shape as poses*/, float* const* g_logits_pyr /*S, MASK_EXP*/,
                      float* const* g_srcs /*host array V x [B,H,W,3]; NULL unless want_src_grad*/,
                      void* ws, vsl_stream_t stream);
+
+/* ---- upstream gradient of the summed loss: dst[0..n) = src[0..n) * (*num / *den) (num, den: device floats; den
+ *      NULL means 1).  What TF autodiff does with the incoming gradient of `total_loss` in the reference
+ *      (slim.learning.create_train_op, train_depth_then_cam_lr.py:417), applied to the whole gradient arena of a
+ *      fused step in one launch; in place with a factor of exactly 1 the kernel returns without touching memory.
+ *      dst, src 16-byte aligned. */
+int vsl_scale(float* dst, const float* src, long long n, const float* num, const float* den, vsl_stream_t stream);
 
 /* ---- EXTENSIONS, not in the reference (BASELINE.json's north_star names them): off unless a
  *      caller asks.  Oracle: oracle/vsl_oracle.py ssim_dissimilarity / edge_aware_smooth_loss; parity unpinned.
@@ -222,7 +229,14 @@ int vsl_adam_step(float* param, const float* grad, float* m, float* v, long long
  *      with moments m_shard / v_shard (hi - lo floats each) and stores the new parameters into every rank's arena.
  *      Bracket it with vsl_peer_barrier (before: all gradients written; after: all parameters landed).
  *      vsl_peer_barrier: peer_flags[r] = rank r's flag array (>= 16 unsigned, zero-initialised) as mapped here;
- *      epoch must grow by 1 per call; *timed_out (device int, nullable) is set if a peer does not arrive in ~3 s. */
+ *      epoch must grow by 1 per call.  The wait is bounded in wall-clock time: timeout_ms (0 = the default of 2
+ *      minutes).  If a peer does not arrive, *timed_out (int, nullable; device memory or PINNED HOST memory, so the
+ *      host can poll it without synchronising) is set to 1 -- and a set *timed_out turns every later
+ *      vsl_dp_adam_step / vsl_dp_step given the same pointer into a no-op (no update, no peer store): a step is never
+ *      computed from a late peer's half-written gradients; the caller must treat the flag as a fatal error.
+ *      vsl_dp_step: barrier -> fused step -> barrier as ONE call with the barrier epoch and Adam's step count t held in
+ *      `state` (device int[4] = epoch, t, timed-out mirror, -; zero-initialised, owned by the caller; the kernels advance it), so the sequence takes no
+ *      per-step host argument and can be captured into / replayed from a CUDA graph. */
 /*      Peer arenas -- the one place the library allocates: memory other processes map must come straight from
  *      cudaMalloc (an IPC handle names a whole allocation).  vsl_peer_alloc zero-fills; the owner frees with
  *      vsl_peer_free after every peer has closed its mapping.  vsl_ipc_open maps a peer's arena for kernels of the
@@ -233,10 +247,14 @@ int vsl_ipc_get_handle(void* ptr, unsigned char* handle64);
 int vsl_ipc_open(const unsigned char* handle64, void** ptr);
 int vsl_ipc_close(void* ptr);
 int vsl_peer_barrier(unsigned* const* peer_flags, int rank, int world, unsigned epoch, int* timed_out,
-                     vsl_stream_t stream);
+                     long long timeout_ms, vsl_stream_t stream);
 int vsl_dp_adam_step(const float* const* peer_grads, float* const* peer_params, int rank, int world, float* m_shard,
                      float* v_shard, long long lo, long long hi, float lr, float beta1, float beta2, float eps,
-                     int step, float grad_scale, vsl_stream_t stream);
+                     int step, float grad_scale, const int* timed_out /*nullable*/, vsl_stream_t stream);
+int vsl_dp_step(unsigned* const* peer_flags, const float* const* peer_grads, float* const* peer_params, int rank,
+                int world, float* m_shard, float* v_shard, long long lo, long long hi, float lr, float beta1, float beta2,
+                float eps, float grad_scale, int* state, int* timed_out /*nullable*/, long long timeout_ms,
+                vsl_stream_t stream);
 
 #ifdef __cplusplus
 }

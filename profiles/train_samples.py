@@ -143,8 +143,8 @@ def main():
         x_pyr = [nhwc(x) for x in disp_net(nchw(tgt))]
         pose, masks = pose_net(nchw(torch.cat([tgt] + srcs, dim=3)))
         total, losses = ops.view_synthesis_loss(tgt, srcs, x_pyr, pose.contiguous(), K_pyr,
-                                                logits_pyr=[nhwc(m) for m in masks], flags=flags)
-        (total * scale).backward()
+                                                logits_pyr=[nhwc(m) for m in masks], flags=flags, loss_scale=scale)
+        total.backward()        # the rank's B_local / B_global share is folded into the kernel's gradients
         return losses
 
     def step():

@@ -102,13 +102,18 @@ def test_error_codes_of_the_extension_and_optimiser_entries(lib):
     assert lib.vsl_adam_step(16, 16, 16, 16, 10, 1e-3, 0.9, 0.999, 1e-8, 0, 1.0, None) == -2     # t >= 1
     assert lib.vsl_adam_step(16, 20, 16, 16, 10, 1e-3, 0.9, 0.999, 1e-8, 1, 1.0, None) == -4     # ranges out of phase
     ptrs = _lib.ptr_array([16, 32])
-    assert lib.vsl_dp_adam_step(ptrs, ptrs, 2, 2, 16, 16, 0, 8, 1e-3, 0.9, 0.999, 1e-8, 1, 1.0, None) == -2   # rank
-    assert lib.vsl_dp_adam_step(ptrs, ptrs, 0, 2, 16, 16, 0, 6, 1e-3, 0.9, 0.999, 1e-8, 1, 1.0, None) == -2   # hi % 4
-    assert lib.vsl_dp_adam_step(ptrs, ptrs, 0, 2, 16, 16, 8, 8, 1e-3, 0.9, 0.999, 1e-8, 1, 1.0, None) == 0    # empty shard
+    assert lib.vsl_dp_adam_step(ptrs, ptrs, 2, 2, 16, 16, 0, 8, 1e-3, 0.9, 0.999, 1e-8, 1, 1.0, None, None) == -2   # rank
+    assert lib.vsl_dp_adam_step(ptrs, ptrs, 0, 2, 16, 16, 0, 6, 1e-3, 0.9, 0.999, 1e-8, 1, 1.0, None, None) == -2   # hi % 4
+    assert lib.vsl_dp_adam_step(ptrs, ptrs, 0, 2, 16, 16, 8, 8, 1e-3, 0.9, 0.999, 1e-8, 1, 1.0, None, None) == 0    # empty shard
     assert lib.vsl_dp_adam_step(_lib.ptr_array([16, 36]), ptrs, 0, 2, 16, 16, 0, 8, 1e-3, 0.9, 0.999, 1e-8, 1, 1.0,
-                                None) == -4
-    assert lib.vsl_peer_barrier(ptrs, 0, 17, 1, None, None) == -2                      # world > 16
-    assert lib.vsl_peer_barrier(None, 0, 2, 1, None, None) == -1
+                                None, None) == -4
+    assert lib.vsl_peer_barrier(ptrs, 0, 17, 1, None, 0, None) == -2                   # world > 16
+    assert lib.vsl_peer_barrier(None, 0, 2, 1, None, 0, None) == -1
+    assert lib.vsl_peer_barrier(ptrs, 0, 2, 1, None, -5, None) == -2                   # negative timeout
+    # the graph-capturable whole step needs its device-resident state block
+    assert lib.vsl_dp_step(ptrs, ptrs, ptrs, 0, 2, 16, 16, 0, 8, 1e-3, 0.9, 0.999, 1e-8, 1.0, None, None, 0, None) == -1
+    assert lib.vsl_scale(None, 16, 4, 16, None, None) == -1 and lib.vsl_scale(16, 16, 0, 16, None, None) == -2
+    assert lib.vsl_scale(20, 16, 4, 16, None, None) == -4
     assert lib.vsl_ipc_get_handle(None, None) == -1 and lib.vsl_ipc_open(None, None) == -1
     assert lib.vsl_peer_alloc(0, ctypes.byref(ctypes.c_void_p())) == -2
 

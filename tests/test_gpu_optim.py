@@ -140,3 +140,98 @@ def test_peer_data_parallel_adam_two_ranks(tmp_path):
     for i in range(len(shapes)):
         assert torch.equal(a[i], b[i])                           # replicas bit-identical
         assert float((a[i].double() - ref[i][0]).abs().max()) <= 2e-6 * float(ref[i][0].abs().max()) + 1e-9
+
+
+# ------------------------------------------------------------------ the fused peer step on ONE GPU: ranks = streams
+def _adam_reference_on_gpu(shapes, grads_per_step, lr):
+    """'gather, add in rank order, vsl_adam_step' on one flat arena -> (param_flat, m_flat, v_flat)."""
+    _, _, _, numel = vdist._flat_layout(shapes)
+    p, g, m, v = (torch.zeros(numel, device=DEV) for _ in range(4))
+    for t, per_rank in enumerate(grads_per_step, start=1):
+        g.zero_()
+        for gr in per_rank:                 # rank order, float32 adds: what dp_adam_kernel does element by element
+            g += gr
+        ops.adam_step(p, g, m, v, t, lr=lr)
+    return p, m, v
+
+
+@pytest.mark.parametrize('world', [2, 4])
+def test_peer_step_ranks_in_one_process_single_gpu(world):
+    """dp_adam_kernel<2>/<4> + peer_barrier_kernel proven on a ONE-GPU box: `world` ranks live in this process, each
+    with its own arena (InProcessArena) and its own stream; their barrier kernels run concurrently and meet through
+    the flag words exactly as ranks on different GPUs do.  Result: every replica bit-identical to 'sum the gradients
+    in rank order, then vsl_adam_step', moments included."""
+    shapes = [(301, 7), (64,), (5,), (4099,), (33, 1031)]
+    ranks = vdist.PeerDataParallelAdam.in_process(shapes, [DEV] * world, lr=1e-2, timeout_s=20.0)
+    streams = [torch.cuda.Stream() for _ in ranks]
+    numel = ranks[0].numel
+    gen = torch.Generator().manual_seed(5)
+    history = []
+    for t in (1, 2, 3, 4):
+        per_rank = [torch.randn(numel, generator=gen).to(DEV) * (0.1 if r else 1.0) for r in range(world)]
+        history.append(per_rank)
+        for dp, gr in zip(ranks, per_rank):
+            dp.grad_flat.copy_(gr)
+        torch.cuda.synchronize()
+        for dp, st in zip(ranks, streams):                      # rank r's whole step is queued before rank r+1's:
+            dp.step(stream=st.cuda_stream)                      # its first barrier spins until the others arrive
+        torch.cuda.synchronize()                                # (the next gradients are written on another stream)
+    for dp in ranks:
+        dp.check_peers()
+    p_ref, m_ref, v_ref = _adam_reference_on_gpu(shapes, history, 1e-2)
+    for dp in ranks:
+        assert torch.equal(dp.param_flat, p_ref), 'rank %d parameters differ from the reference order' % dp.rank
+        assert torch.equal(dp.m_shard[:dp.hi - dp.lo], m_ref[dp.lo:dp.hi])
+        assert torch.equal(dp.v_shard[:dp.hi - dp.lo], v_ref[dp.lo:dp.hi])
+        assert dp.state[:2].tolist() == [8, 4]                  # 2 barriers per step; Adam's t lives on the device
+    for dp in ranks:
+        dp.close()
+
+
+def test_peer_step_timeout_fails_the_step_instead_of_corrupting():
+    """A rank whose peer never arrives: the barrier gives up after timeout_s, the update is NOT applied (no
+    half-written gradients are ever summed), and the host-side step raises."""
+    shapes = [(1000,)]
+    ranks = vdist.PeerDataParallelAdam.in_process(shapes, [DEV, DEV], lr=1e-2, timeout_s=0.3)
+    a = ranks[0]
+    a.param_flat.fill_(1.0)
+    a.grad_flat.fill_(3.0)
+    st = torch.cuda.Stream()
+    a.step(stream=st.cuda_stream)                                # rank 1 never steps
+    with pytest.raises(vdist.PeerTimeout):
+        a.check_peers()
+    assert float((a.param_flat - 1.0).abs().max()) == 0.0        # untouched
+    assert float(a.m_shard.abs().max()) == 0.0
+    with pytest.raises(vdist.PeerTimeout):
+        a.step(stream=st.cuda_stream)
+    torch.cuda.synchronize()
+    for dp in ranks:
+        dp.close()
+
+
+def test_peer_step_replays_from_a_cuda_graph():
+    """The barrier epoch and Adam's step count live in device memory, so the step takes no per-step host argument:
+    captured once, replayed three times == three eager steps of the oracle's Adam."""
+    shapes = [(257, 3), (1000,)]
+    dp = vdist.PeerDataParallelAdam(shapes, DEV, lr=1e-3)
+    gen = torch.Generator().manual_seed(1)
+    gs = [torch.randn(dp.numel, generator=gen).to(DEV) for _ in range(3)]
+    static_g = torch.zeros(dp.numel, device=DEV)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            dp.grad_flat.copy_(static_g)
+            dp.step()
+    torch.cuda.current_stream().wait_stream(side)
+    rp = torch.zeros(dp.numel, dtype=torch.float64)
+    rm, rv = torch.zeros_like(rp), torch.zeros_like(rp)
+    for t, g in enumerate(gs, start=1):
+        static_g.copy_(g)
+        graph.replay()
+        rp, rm, rv = O.adam_step_tf(rp, g.cpu().double(), rm, rv, t, 1e-3)
+    dp.check_peers()
+    assert dp.state[:2].tolist() == [3, 3]
+    assert float((dp.param_flat.cpu().double() - rp).abs().max()) <= 1e-6 * float(rp.abs().max()) + 1e-9
+    dp.close()

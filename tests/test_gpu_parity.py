@@ -501,3 +501,88 @@ def test_fused_disparity_head_on_load(smooth_inv, depth_inv):
         for s in range(S):
             all_views = torch.stack(ok[s]).all(0)
             assert masked_rel_err(xs[s].grad, oraw[s].grad, all_views.unsqueeze(3)) <= 1e-4, (exact, s)
+
+
+# ---------------------------------------------------------------------------------------- full BASELINE sizes vs the oracle
+def _oracle_per_sample(d, flags_kw, samples, S, V, mode='exp'):
+    """float64 oracle, one sample at a time (the batch mean of per-sample means IS the batch mean: every sample has
+    the same pixel count): -> (losses[3] averaged over ALL samples, {b: (g_x list, g_poses, g_logits list)})."""
+    B = d['tgt'].shape[0]
+    of = O.LossFlags(**flags_kw)
+    tot = torch.zeros(3, dtype=torch.float64)
+    grads = {}
+    for b in range(B):
+        sl = slice(b, b + 1)
+        need = b in samples
+        xs = [x[sl].double().requires_grad_(need) for x in d['disp_pyr']]
+        ps = d['poses'][sl].double().requires_grad_(need)
+        lg = [l[sl].double().requires_grad_(need) for l in d['logits_pyr']] if mode == 'exp' else None
+        with torch.set_grad_enabled(need):
+            r = O.view_synthesis_loss(d['tgt'][sl].double(), [s[sl].double() for s in d['srcs']], xs, ps,
+                                      d['K_pyr'][sl].double(), lg, None, of)
+        tot += torch.stack([t.detach() for t in r])
+        if need:
+            sum(r).backward()
+            grads[b] = ([x.grad for x in xs], ps.grad, [l.grad for l in lg] if lg else None)
+    return tot / B, grads
+
+
+def _full_size_vs_oracle(d, B, H, W, S, V, samples, mode='exp', flags_kw=None):
+    flags_kw = dict(flags_kw or {}, num_scales=S)
+    flags = ops.LossFlags(**flags_kw)
+    xs = [cu(x, True) for x in d['disp_pyr']]
+    ps = cu(d['poses'], True)
+    lgs = [cu(l, True) for l in d['logits_pyr']] if mode == 'exp' else None
+    total, losses = ops.view_synthesis_loss(cu(d['tgt']), [cu(s) for s in d['srcs']], xs, ps, cu(d['K_pyr']),
+                                            logits_pyr=lgs, flags=flags)
+    total.backward()
+    want, grads = _oracle_per_sample(d, flags_kw, samples, S, V, mode)
+    for i, key in enumerate(('pixel', 'smooth', 'exp')):
+        assert abs(float(losses[i]) - float(want[i])) <= 1e-5 * abs(float(want[i])) + 1e-9, (key, float(losses[i]), float(want[i]))
+    assert abs(float(total) - float(want.sum())) <= 1e-5 * float(want.sum())
+    for b, (ogx, ogp, ogl) in grads.items():
+        sl = slice(b, b + 1)
+        one = dict(tgt=d['tgt'][sl], srcs=[s[sl] for s in d['srcs']], disp=[x[sl] for x in d['disp_pyr']],
+                   poses=d['poses'][sl], K=d['K_pyr'][sl])
+        # the kernel's gradients are those of the B-sample mean: 1/B of the single-sample oracle's
+        assert rel_err(ps.grad[sl] * B, ogp) <= 1e-4, ('g_poses', b, rel_err(ps.grad[sl] * B, ogp))
+        ok = smooth_pixels(one['tgt'], one['srcs'], one['disp'], one['poses'], one['K'], flags)
+        for s in range(S):
+            all_views = torch.stack(ok[s]).all(0)
+            assert all_views.float().mean() > 0.97, (b, s, float(all_views.float().mean()))
+            e = masked_rel_err(xs[s].grad[sl] * B, ogx[s], all_views.unsqueeze(3))
+            assert e <= 1e-4, ('g_x', b, s, e)
+            if mode == 'exp':
+                m = torch.stack([o for o in ok[s] for _ in (0, 1)], dim=3)
+                e = masked_rel_err(lgs[s].grad[sl] * B, ogl[s], m)
+                assert e <= 1e-4, ('g_logits', b, s, e)
+
+
+def test_full_size_cfg2_against_oracle():
+    """BASELINE.json configs[1] at FULL size (B=32, 128x416, 4 scales, 2 views, explainability mask): the three
+    losses over the whole batch to 1e-5, pose and per-pixel gradients of samples 0, 13 and 31 to 1e-4 against the
+    float64 oracle."""
+    d = synth.make_snippets(32, 128, 416, S=4, V=2, seed=1234)
+    _full_size_vs_oracle(d, 32, 128, 416, 4, 2, samples=(0, 13, 31))
+
+
+def test_full_size_cfg5_beyond_2_pow_24_against_oracle():
+    """BASELINE.json configs[4] at FULL size (B=64, 480x640: 19.66 M pixels at level 0, beyond the 2^24 elements where
+    the reference's own float32 gather indices break, utils.py:273-294).  Samples 0, 31 and 63 -- the last
+    one lives wholly above 2^24 -- pin the kernel's 32-bit wrapped offset arithmetic against the exact-index oracle."""
+    d = synth.make_snippets(64, 480, 640, S=4, V=2, seed=1239)
+    assert 63 * 480 * 640 > 2 ** 24
+    _full_size_vs_oracle(d, 64, 480, 640, 4, 2, samples=(0, 31, 63))
+
+
+@pytest.mark.parametrize('direction', ['left_to_right', 'right_to_left'])
+def test_full_size_cfg4_both_directions_against_oracle(direction):
+    """BASELINE.json configs[3] at FULL size (DeMoN pairs, B=64, 192x256, one source view per direction, angle-axis
+    poses, smoothness on 1/depth and unnormalised data weight as train_depth_then_cam_lr.py:217,310 use them)."""
+    d = synth.make_snippets(64, 192, 256, S=4, V=1, seed=1238)
+    if direction == 'right_to_left':       # the other image of the pair is the target, the motion is reversed
+        d['tgt'], d['srcs'] = d['srcs'][0], [d['tgt']]
+        d['poses'] = -d['poses']
+    kw = dict(pose_format='angleaxis', smooth_on_inverse=True, depth_is_inverse=True, pixel_scale_norm=False,
+              smooth_weight=0.3, data_weight=2.0, explain_reg_weight=0.4)
+    _full_size_vs_oracle(d, 64, 192, 256, 4, 1, samples=(0, 40, 63), flags_kw=kw)

@@ -66,6 +66,7 @@ SIGNATURES = {
                                         _c_float_p, ctypes.POINTER(ctypes.c_void_p), _c_float_p,
                                         ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p),
                                         ctypes.c_void_p, _c_stream]),
+    'vsl_scale': (ctypes.c_int, [_c_float_p] * 2 + [ctypes.c_longlong] + [_c_float_p] * 2 + [_c_stream]),
     'vsl_adam_step': (ctypes.c_int, [_c_float_p] * 4 + [ctypes.c_longlong] + [ctypes.c_float] * 4 + [ctypes.c_int, ctypes.c_float, _c_stream]),
     'vsl_peer_alloc': (ctypes.c_int, [ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]),
     'vsl_peer_free': (ctypes.c_int, [ctypes.c_void_p]),
@@ -73,9 +74,13 @@ SIGNATURES = {
     'vsl_ipc_open': (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]),
     'vsl_ipc_close': (ctypes.c_int, [ctypes.c_void_p]),
     'vsl_peer_barrier': (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int, ctypes.c_uint,
-                                        ctypes.c_void_p, _c_stream]),
+                                        ctypes.c_void_p, ctypes.c_longlong, _c_stream]),
     'vsl_dp_adam_step': (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p)] * 2 + [ctypes.c_int] * 2 + [_c_float_p] * 2 +
-                         [ctypes.c_longlong] * 2 + [ctypes.c_float] * 4 + [ctypes.c_int, ctypes.c_float, _c_stream]),
+                         [ctypes.c_longlong] * 2 + [ctypes.c_float] * 4 + [ctypes.c_int, ctypes.c_float, ctypes.c_void_p,
+                                                                          _c_stream]),
+    'vsl_dp_step': (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p)] * 3 + [ctypes.c_int] * 2 + [_c_float_p] * 2 +
+                    [ctypes.c_longlong] * 2 + [ctypes.c_float] * 5 + [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong,
+                                                                     _c_stream]),
     'vsl_ssim_ws_bytes': (ctypes.c_size_t, [ctypes.c_int] * 4),
     'vsl_ssim_fwd': (ctypes.c_int, [_c_float_p] * 2 + [ctypes.c_int] * 4 + [_c_float_p] * 2 + [ctypes.c_void_p, _c_stream]),
     'vsl_ssim_bwd': (ctypes.c_int, [_c_float_p] * 2 + [ctypes.c_int] * 4 + [_c_float_p] * 2 + [ctypes.c_int] +

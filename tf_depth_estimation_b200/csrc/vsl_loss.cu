@@ -700,7 +700,10 @@ loss_finalize_kernel(const LossParams P, const float* __restrict__ poses, const 
       double t = 0.0;
       for (int w = 0; w < NW; ++w) t += part[w][0][threadIdx.x];
       losses[threadIdx.x] = (float)(t * (double)inv_loss_scale);
+      tsum[0][threadIdx.x] = t;
     }
+    __syncthreads();
+    if (threadIdx.x == 0) losses[3] = (float)((tsum[0][0] + tsum[0][1] + tsum[0][2]) * (double)inv_loss_scale);
     return;
   }
 

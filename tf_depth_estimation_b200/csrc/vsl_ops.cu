@@ -769,6 +769,27 @@ static int launch_pyramid(const PyrJob& job, const PrepJob& prep, int B, int H, 
   }
 }
 
+// dst = src * (*num / *den): the upstream gradient of the summed loss applied to a whole gradient arena in ONE
+// launch.  In place (dst == src) with a factor of exactly 1 -- total.backward() -- every block returns after one
+// scalar load: the gradients were already produced by the fused step.
+__global__ void __launch_bounds__(256)
+scale_kernel(float* __restrict__ dst, const float* __restrict__ src, long long n, const float* __restrict__ num,
+             const float* __restrict__ den) {
+  float f = __ldg(num);
+  if (den != nullptr) f = f / __ldg(den);
+  if (dst == src && f == 1.0f) return;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+  const long long n4 = n / 4;
+  float4* d4 = reinterpret_cast<float4*>(dst);
+  const float4* s4 = reinterpret_cast<const float4*>(src);
+  for (long long i = tid; i < n4; i += nth) {
+    float4 q = s4[i];
+    q.x *= f; q.y *= f; q.z *= f; q.w *= f;
+    d4[i] = q;
+  }
+  for (long long i = 4 * n4 + tid; i < n; i += nth) dst[i] = src[i] * f;
+}
+
 }  // namespace vsl
 
 // =====================================================================================================
@@ -1096,6 +1117,16 @@ int vsl_pyramid(const float* img, int B, int H, int W, int C, int S, float* cons
   PrepJob none;
   none.n = 0;
   return launch_pyramid(job, none, B, H, W, C, S, (cudaStream_t)stream);
+}
+
+int vsl_scale(float* dst, const float* src, long long n, const float* num, const float* den, vsl_stream_t stream) {
+  VSL_REQUIRE(dst && src && num, VSL_E_NULL);
+  VSL_REQUIRE(n > 0, VSL_E_SHAPE);
+  VSL_REQUIRE(aligned(dst, 16) && aligned(src, 16), VSL_E_ALIGN);
+  const long long want = (n / 4 + 255) / 256 + 1;
+  const int blocks = (int)(want < 148 * 8 ? want : 148 * 8);
+  scale_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dst, src, n, num, den);
+  return launch_status();
 }
 
 }  // extern "C"

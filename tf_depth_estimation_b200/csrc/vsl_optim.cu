@@ -67,12 +67,41 @@ struct PeerPtrs {
   float* param[kMaxPeers];
 };
 
+// Hyper-parameters as the host passes them; lr_t is formed on the device when the step count lives there.
+struct AdamHyper { float lr, beta1, beta2, eps, gscale; int step; };
+
+VSL_DEV AdamConsts adam_consts(const AdamHyper& h, int t) {
+  AdamConsts c;
+  c.lr_t = (float)((double)h.lr * sqrt(1.0 - pow((double)h.beta2, (double)t)) / (1.0 - pow((double)h.beta1, (double)t)));
+  c.omb1 = 1.0f - h.beta1; c.omb2 = 1.0f - h.beta2; c.eps = h.eps; c.gscale = h.gscale;
+  return c;
+}
+
+// state (nullable): device int[4] = {barrier epoch, Adam step count t, timed-out mirror, -}, advanced by peer_barrier_kernel, so
+// that the whole barrier -> step -> barrier sequence takes no per-step host argument and replays from a CUDA graph.
+// timed_out (nullable; may be pinned host memory): set by a barrier that gave up -- then this kernel does NOTHING
+// (no update, no peer store): a late peer must never be summed half-written (the step fails instead, see dist.py).
+#ifdef VSL_DP_TIMING_EXPERIMENTS
+#define VSL_DP_DBG(x) (x)
+#else
+#define VSL_DP_DBG(x) 0
+#endif
 template <int WORLD>   // 0 = run-time world
 __global__ void __launch_bounds__(256)
 dp_adam_kernel(PeerPtrs pp, int world_rt, int rank, float* __restrict__ m, float* __restrict__ v, long long lo,
-               long long n4, AdamConsts c, int dbg) {
+               long long n4, AdamHyper hy, const int* __restrict__ state, const volatile int* timed_out, int dbg) {
   constexpr int U = 4;    // float4s per thread and trip: U * world peer loads in flight before the first use
   const int world = WORLD ? WORLD : world_rt;
+  __shared__ AdamConsts sc;
+  __shared__ int s_dead;
+  if (threadIdx.x == 0) {
+    // with a state block the failure flag is mirrored in device memory (state[2]): no PCIe read on this kernel's path
+    s_dead = state != nullptr ? (state[2] != 0) : ((timed_out != nullptr && *timed_out != 0) ? 1 : 0);
+    sc = adam_consts(hy, state != nullptr ? state[1] + 1 : hy.step);
+  }
+  __syncthreads();
+  if (s_dead) return;
+  const AdamConsts c = sc;
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
   float4* m4 = reinterpret_cast<float4*>(m);
   float4* v4 = reinterpret_cast<float4*>(v);
@@ -86,7 +115,7 @@ dp_adam_kernel(PeerPtrs pp, int world_rt, int rank, float* __restrict__ m, float
 #pragma unroll
     for (int r = 0; r < (WORLD ? WORLD : kMaxPeers); ++r) {
       if (r < world) {
-        const float4* src = reinterpret_cast<const float4*>(pp.grad[(dbg & 2) ? rank : r]) + lo4;
+        const float4* src = reinterpret_cast<const float4*>(pp.grad[VSL_DP_DBG(dbg & 2) ? rank : r]) + lo4;
         float4 t[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -112,7 +141,7 @@ dp_adam_kernel(PeerPtrs pp, int world_rt, int rank, float* __restrict__ m, float
         m4[i] = mm[u]; v4[i] = vv[u];
 #pragma unroll
         for (int r = 0; r < (WORLD ? WORLD : kMaxPeers); ++r)
-          if (r < world && (!(dbg & 1) || r == rank)) reinterpret_cast<float4*>(pp.param[r])[lo4 + i] = p[u];
+          if (r < world && (!VSL_DP_DBG(dbg & 1) || r == rank)) reinterpret_cast<float4*>(pp.param[r])[lo4 + i] = p[u];
       }
     }
   }
@@ -121,27 +150,51 @@ dp_adam_kernel(PeerPtrs pp, int world_rt, int rank, float* __restrict__ m, float
 // Barrier across the GPUs of a node through peer-mapped flag words.  flags of rank q: unsigned[kMaxPeers], word r is
 // written by rank r only.  One block of `world` threads: thread r publishes `epoch` into rank r's word [rank], then
 // waits until this GPU's word [r] has reached `epoch`.  Everything this GPU wrote before (peer stores of the
-// previous kernel included) is fenced system-wide first.  A bounded spin: if a peer never arrives the kernel sets
-// *timed_out instead of hanging the GPU.
+// previous kernel included) is fenced system-wide first.  The spin is bounded in wall-clock time (%globaltimer):
+// if a peer does not arrive within timeout_ns the kernel sets *timed_out -- which makes every later dp_adam_kernel
+// a no-op and the host-side step raise -- instead of hanging the GPU or letting the step run on half-written data.
+// With `state` the epoch is state[0] + 1 (and is stored back; bump_step also advances the Adam step count
+// state[1]), so the launch takes no per-step host argument.
 struct PeerFlags { unsigned* f[kMaxPeers]; };
 
-__global__ void peer_barrier_kernel(PeerFlags pf, int rank, int world, unsigned epoch, int* timed_out) {
+VSL_DEV unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+__global__ void peer_barrier_kernel(PeerFlags pf, int rank, int world, unsigned epoch_arg, int* state, int bump_step,
+                                    volatile int* timed_out, unsigned long long timeout_ns) {
   const int r = threadIdx.x;
-  if (r >= world) return;
-  __threadfence_system();
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pf.f[r] + rank), "r"(epoch) : "memory");
-  const unsigned* mine = pf.f[rank] + r;
-  const long long t0 = clock64();
-  unsigned seen;
-  do {
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
-    if ((int)(seen - epoch) >= 0) break;
-    if (clock64() - t0 > 6000000000LL) {   // ~3 s at 2 GHz
-      if (timed_out != nullptr) *timed_out = 1;
-      break;
-    }
-  } while (true);
-  __threadfence_system();
+  const unsigned epoch = state != nullptr ? (unsigned)state[0] + 1u : epoch_arg;
+  __syncthreads();
+  if (r < world) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pf.f[r] + rank), "r"(epoch) : "memory");
+    const unsigned* mine = pf.f[rank] + r;
+    const unsigned long long t0 = global_ns();
+    unsigned seen;
+    unsigned spins = 0;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
+      if ((int)(seen - epoch) >= 0) break;
+      if ((++spins & 1023u) == 0u) {
+        if (state != nullptr ? (*(volatile int*)(state + 2) != 0) : (timed_out != nullptr && *timed_out != 0))
+          break;                                                     // a barrier of this rank already failed
+        if (global_ns() - t0 > timeout_ns) {
+          if (timed_out != nullptr) *timed_out = 1;
+          if (state != nullptr) atomicExch(state + 2, 1);
+          break;
+        }
+      }
+    } while (true);
+    __threadfence_system();
+  }
+  __syncthreads();
+  if (r == 0 && state != nullptr) {
+    state[0] = (int)epoch;
+    if (bump_step) state[1] += 1;
+  }
 }
 
 }  // namespace vsl
@@ -208,22 +261,28 @@ int vsl_ipc_close(void* ptr) {
   return e == cudaSuccess ? VSL_OK : (int)e;
 }
 
-int vsl_peer_barrier(unsigned* const* peer_flags, int rank, int world, unsigned epoch, int* timed_out,
-                     vsl_stream_t stream) {
+namespace {
+
+constexpr long long kDefaultBarrierTimeoutMs = 120000;   // 2 minutes: rank skew (checkpoint, loader stall) is not a fault
+
+int launch_barrier(unsigned* const* peer_flags, int rank, int world, unsigned epoch, int* state, int bump_step,
+                   int* timed_out, long long timeout_ms, cudaStream_t st) {
   VSL_REQUIRE(peer_flags, VSL_E_NULL);
-  VSL_REQUIRE(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, VSL_E_SHAPE);
+  VSL_REQUIRE(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world && timeout_ms >= 0, VSL_E_SHAPE);
   PeerFlags pf;
   for (int r = 0; r < kMaxPeers; ++r) pf.f[r] = r < world ? peer_flags[r] : nullptr;
   for (int r = 0; r < world; ++r) VSL_REQUIRE(pf.f[r] != nullptr, VSL_E_NULL);
-  peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(pf, rank, world, epoch, timed_out);
+  const unsigned long long ns = (unsigned long long)(timeout_ms > 0 ? timeout_ms : kDefaultBarrierTimeoutMs) * 1000000ull;
+  peer_barrier_kernel<<<1, 32, 0, st>>>(pf, rank, world, epoch, state, bump_step, timed_out, ns);
   return launch_status();
 }
 
-int vsl_dp_adam_step(const float* const* peer_grads, float* const* peer_params, int rank, int world, float* m_shard,
-                     float* v_shard, long long lo, long long hi, float lr, float beta1, float beta2, float eps,
-                     int step, float grad_scale, vsl_stream_t stream) {
+int launch_dp_adam(const float* const* peer_grads, float* const* peer_params, int rank, int world, float* m_shard,
+                   float* v_shard, long long lo, long long hi, const AdamHyper& hy, const int* state,
+                   const int* timed_out, cudaStream_t st) {
   VSL_REQUIRE(peer_grads && peer_params && m_shard && v_shard, VSL_E_NULL);
-  VSL_REQUIRE(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world && step >= 1, VSL_E_SHAPE);
+  VSL_REQUIRE(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world && (state != nullptr || hy.step >= 1),
+              VSL_E_SHAPE);
   VSL_REQUIRE(lo >= 0 && hi >= lo && lo % 4 == 0 && hi % 4 == 0, VSL_E_SHAPE);
   PeerPtrs pp;
   for (int r = 0; r < kMaxPeers; ++r) {
@@ -236,23 +295,54 @@ int vsl_dp_adam_step(const float* const* peer_grads, float* const* peer_params, 
   }
   VSL_REQUIRE(aligned(m_shard, 16) && aligned(v_shard, 16), VSL_E_ALIGN);
   if (hi == lo) return VSL_OK;
-  AdamConsts c;
-  c.lr_t = (float)((double)lr * sqrt(1.0 - pow((double)beta2, (double)step)) / (1.0 - pow((double)beta1, (double)step)));
-  c.omb1 = 1.0f - beta1; c.omb2 = 1.0f - beta2; c.eps = eps; c.gscale = grad_scale;
   const long long n4 = (hi - lo) / 4;
   const long long want = (n4 + 4 * 256 - 1) / (4 * 256);
   const int blocks = (int)(want < 148 * 8 ? want : 148 * 8);
-  cudaStream_t st = (cudaStream_t)stream;
-  const char* de = getenv("VSL_DP_DEBUG");   // timing experiments only: 1 = no remote stores, 2 = no remote loads
-  const int dbg = de ? atoi(de) : 0;
+  int dbg = 0;
+#ifdef VSL_DP_TIMING_EXPERIMENTS   // never defined for the shipped library: 1 = no remote stores, 2 = no remote loads
+  const char* de = getenv("VSL_DP_DEBUG");
+  dbg = de ? atoi(de) : 0;
+#endif
   switch (world) {
-    case 1: dp_adam_kernel<1><<<blocks, 256, 0, st>>>(pp, world, rank, m_shard, v_shard, lo, n4, c, dbg); break;
-    case 2: dp_adam_kernel<2><<<blocks, 256, 0, st>>>(pp, world, rank, m_shard, v_shard, lo, n4, c, dbg); break;
-    case 4: dp_adam_kernel<4><<<blocks, 256, 0, st>>>(pp, world, rank, m_shard, v_shard, lo, n4, c, dbg); break;
-    case 8: dp_adam_kernel<8><<<blocks, 256, 0, st>>>(pp, world, rank, m_shard, v_shard, lo, n4, c, dbg); break;
-    default: dp_adam_kernel<0><<<blocks, 256, 0, st>>>(pp, world, rank, m_shard, v_shard, lo, n4, c, dbg); break;
+    case 1: dp_adam_kernel<1><<<blocks, 256, 0, st>>>(pp, world, rank, m_shard, v_shard, lo, n4, hy, state, timed_out, dbg); break;
+    case 2: dp_adam_kernel<2><<<blocks, 256, 0, st>>>(pp, world, rank, m_shard, v_shard, lo, n4, hy, state, timed_out, dbg); break;
+    case 4: dp_adam_kernel<4><<<blocks, 256, 0, st>>>(pp, world, rank, m_shard, v_shard, lo, n4, hy, state, timed_out, dbg); break;
+    case 8: dp_adam_kernel<8><<<blocks, 256, 0, st>>>(pp, world, rank, m_shard, v_shard, lo, n4, hy, state, timed_out, dbg); break;
+    default: dp_adam_kernel<0><<<blocks, 256, 0, st>>>(pp, world, rank, m_shard, v_shard, lo, n4, hy, state, timed_out, dbg); break;
   }
   return launch_status();
+}
+
+}  // namespace
+
+int vsl_peer_barrier(unsigned* const* peer_flags, int rank, int world, unsigned epoch, int* timed_out,
+                     long long timeout_ms, vsl_stream_t stream) {
+  return launch_barrier(peer_flags, rank, world, epoch, nullptr, 0, timed_out, timeout_ms, (cudaStream_t)stream);
+}
+
+int vsl_dp_adam_step(const float* const* peer_grads, float* const* peer_params, int rank, int world, float* m_shard,
+                     float* v_shard, long long lo, long long hi, float lr, float beta1, float beta2, float eps,
+                     int step, float grad_scale, const int* timed_out, vsl_stream_t stream) {
+  const AdamHyper hy = {lr, beta1, beta2, eps, grad_scale, step};
+  return launch_dp_adam(peer_grads, peer_params, rank, world, m_shard, v_shard, lo, hi, hy, nullptr, timed_out,
+                        (cudaStream_t)stream);
+}
+
+int vsl_dp_step(unsigned* const* peer_flags, const float* const* peer_grads, float* const* peer_params, int rank,
+                int world, float* m_shard, float* v_shard, long long lo, long long hi, float lr, float beta1, float beta2,
+                float eps, float grad_scale, int* state, int* timed_out, long long timeout_ms, vsl_stream_t stream) {
+  VSL_REQUIRE(state, VSL_E_NULL);
+  cudaStream_t st = (cudaStream_t)stream;
+  const AdamHyper hy = {lr, beta1, beta2, eps, grad_scale, 0};
+  int rc = VSL_OK;
+  if (world > 1) {
+    rc = launch_barrier(peer_flags, rank, world, 0u, state, 0, timed_out, timeout_ms, st);
+    if (rc != VSL_OK) return rc;
+  }
+  rc = launch_dp_adam(peer_grads, peer_params, rank, world, m_shard, v_shard, lo, hi, hy, state, timed_out, st);
+  if (rc != VSL_OK) return rc;
+  // the trailing barrier also advances the Adam step count (after every block of the update has read it)
+  return launch_barrier(peer_flags, rank, world, 0u, state, 1, timed_out, timeout_ms, st);
 }
 
 }  // extern "C"

@@ -187,6 +187,50 @@ class PeerArena(object):
         self.local = None
 
 
+class InProcessArena(object):
+    """PeerArena's interface for `world` ranks that live in ONE process (one block per rank, on the given devices --
+    which may all be the same GPU): the blocks are plain cudaMalloc allocations, so base[r] is valid for every rank
+    and no IPC is involved.  Lets one host thread drive several ranks on separate streams -- a single-process
+    multi-GPU trainer, and the way the peer kernels are exercised on a one-GPU box."""
+
+    def __init__(self, rank, world, bases, nbytes, device):
+        from . import _lib
+        self.lib = _lib.load()
+        self.rank, self.world, self.base, self.nbytes = rank, world, list(bases), nbytes
+        self.local, self.device = bases[rank], torch.device(device)
+
+    @classmethod
+    def make(cls, nbytes, devices):
+        import ctypes
+        from . import _lib
+        lib = _lib.load()
+        nbytes = (int(nbytes) + 255) // 256 * 256
+        devices = [torch.device(d) for d in devices]
+        bases = []
+        for d in devices:
+            if d.type != 'cuda':
+                raise TypeError('InProcessArena needs CUDA devices (this path has no CPU fallback)')
+            with torch.cuda.device(d):
+                p = ctypes.c_void_p()
+                _lib.check(lib.vsl_peer_alloc(nbytes, ctypes.byref(p)))
+                bases.append(p.value)
+        return [cls(r, len(devices), bases, nbytes, devices[r]) for r in range(len(devices))]
+
+    view = PeerArena.view
+
+    def close(self):
+        if self.local is None:
+            return
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize()
+            self.lib.vsl_peer_free(self.local)
+        self.local = None
+
+
+class PeerTimeout(RuntimeError):
+    """A peer did not reach a barrier of the fused optimiser step in time; the step was NOT applied."""
+
+
 class PeerDataParallelAdam(object):
     """dist.DataParallelAdam's step as ONE kernel over NVLink peer memory (csrc/vsl_optim.cu dp_adam_kernel):
     rank r sums every rank's gradient over its shard of the flat arena with peer-to-peer loads (reduce-scatter),
@@ -194,19 +238,30 @@ class PeerDataParallelAdam(object):
     parameters into every rank's arena (all-gather).  Two flag barriers in peer memory bracket it; nothing goes
     through NCCL after construction.  Replicas stay bit-identical (one owner per element, fixed sum order).
 
+    The barrier epoch and Adam's step count live in device memory (`state`) and are advanced by the kernels, so
+    step() passes no per-step argument: the whole step can be captured into a CUDA graph together with the networks.
+
+    Failure behaviour: a barrier waits `timeout_s` (default 120 s) of wall-clock time for its peers.  If one does not
+    arrive, the kernel raises a flag in PINNED HOST memory, every later launch of the step becomes a no-op (nothing is
+    ever computed from a late peer's half-written gradients) and the next step() / check_peers() raises PeerTimeout.
+    step() polls the flag without synchronising; it therefore reports a timeout one call late at the latest.
+
     Same `params` / `grads` views as DataParallelAdam.  One node, world <= 16, CUDA only.  Call close() before
     the process group is destroyed.
     """
 
-    def __init__(self, shapes, device, lr, beta1=0.9, beta2=0.999, eps=1e-8, group=None, grad_scale=1.0):
+    def __init__(self, shapes, device, lr, beta1=0.9, beta2=0.999, eps=1e-8, group=None, grad_scale=1.0,
+                 timeout_s=120.0, arena=None):
         from . import _lib
         self._lib = _lib
         self.lib = _lib.load()
         device = torch.device(device)
         self.shapes, sizes, self.offsets, self.numel = _flat_layout(shapes)
-        # local block: [flags 256 B][timed-out word, padded to 256 B][parameters][gradients]
+        # local block: [flags 256 B][state: epoch, t (device ints), padded to 256 B][parameters][gradients]
         arena_bytes = 512 + 8 * self.numel
-        self.arena = PeerArena(arena_bytes, device, group)
+        self.arena = arena if arena is not None else PeerArena(arena_bytes, device, group)
+        if self.arena.nbytes < arena_bytes:
+            raise ValueError('arena too small: %d < %d bytes' % (self.arena.nbytes, arena_bytes))
         self.world, self.rank = self.arena.world, self.arena.rank
         if self.world > 16:
             raise ValueError('PeerDataParallelAdam supports up to 16 ranks of one node')
@@ -215,9 +270,14 @@ class PeerDataParallelAdam(object):
         self.hi = min(self.lo + per, self.numel)
         self.param_flat = self.arena.view(512, self.numel)
         self.grad_flat = self.arena.view(512 + 4 * self.numel, self.numel)
-        self.timed_out = self.arena.view(256, 1, torch.int32)
-        mk = lambda n: torch.zeros(max(n, 4), dtype=torch.float32, device=device)
-        self.m_shard, self.v_shard = mk(self.hi - self.lo), mk(self.hi - self.lo)
+        self.state = self.arena.view(256, 4, torch.int32)                  # [epoch, t, -, -], advanced on the device
+        # the failure flag lives in pinned host memory: the barrier kernel writes it over PCIe, the host polls it
+        # without a synchronisation
+        self.timed_out = torch.zeros(4, dtype=torch.int32).pin_memory()
+        self.timeout_ms = max(int(float(timeout_s) * 1000.0), 1)
+        with torch.cuda.device(device):
+            mk = lambda n: torch.zeros(max(n, 4), dtype=torch.float32, device=device)
+            self.m_shard, self.v_shard = mk(self.hi - self.lo), mk(self.hi - self.lo)
         cut = lambda flat: [flat[o:o + n].view(s) for o, n, s in zip(self.offsets, sizes, self.shapes)]
         self.params, self.grads = cut(self.param_flat), cut(self.grad_flat)
         self._pf = _lib.ptr_array(list(self.arena.base))
@@ -225,31 +285,40 @@ class PeerDataParallelAdam(object):
         self._pg = _lib.ptr_array([b + 512 + 4 * self.numel for b in self.arena.base])
         self.hyper = (float(lr), float(beta1), float(beta2), float(eps))
         self.grad_scale = float(grad_scale)
-        self.t, self.epoch = 0, 0
+        self.t = 0
+        self.device = device
 
-    def _barrier(self, stream):
-        self.epoch += 1
-        self._lib.check(self.lib.vsl_peer_barrier(self._pf, self.rank, self.world, self.epoch, self.timed_out.data_ptr(),
-                                                  stream))
+    @classmethod
+    def in_process(cls, shapes, devices, lr, **kw):
+        """`len(devices)` ranks inside this process (see InProcessArena) -> list of instances, rank order."""
+        _, _, _, numel = _flat_layout(shapes)
+        arenas = InProcessArena.make(512 + 8 * numel, devices)
+        return [cls(shapes, a.device, lr, arena=a, **kw) for a in arenas]
+
+    def _raise_if_timed_out(self):
+        if int(self.timed_out[0]) != 0:
+            raise PeerTimeout('rank %d of %d: a peer did not reach the optimiser-step barrier within %.0f s; the step '
+                              'was not applied and the replicas must be considered out of sync'
+                              % (self.rank, self.world, self.timeout_ms / 1000.0))
 
     def step(self, stream=None):
         """barrier (all gradients written) -> fused reduce-scatter + Adam + all-gather -> barrier (all parameters
-        landed).  Enqueued on the current stream; the host does not wait."""
+        landed), one C call.  Enqueued on the current stream; the host does not wait.  Raises PeerTimeout if an
+        earlier step's barrier gave up."""
+        self._raise_if_timed_out()
         self.t += 1
-        st = torch.cuda.current_stream().cuda_stream if stream is None else stream
-        if self.world > 1:
-            self._barrier(st)
-        self._lib.check(self.lib.vsl_dp_adam_step(self._pg, self._pp, self.rank, self.world, self.m_shard.data_ptr(),
-                                                  self.v_shard.data_ptr(), self.lo, self.hi, *self.hyper, self.t,
-                                                  self.grad_scale, st))
-        if self.world > 1:
-            self._barrier(st)
+        st = torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
+        self._lib.check(self.lib.vsl_dp_step(self._pf, self._pg, self._pp, self.rank, self.world,
+                                             self.m_shard.data_ptr(), self.v_shard.data_ptr(), self.lo, self.hi,
+                                             *self.hyper, self.grad_scale, self.state.data_ptr(),
+                                             self.timed_out.data_ptr(), self.timeout_ms, st))
         return self.t
 
     def check_peers(self):
-        """Host-side check (synchronises): raises if a barrier ever gave up waiting for a peer."""
-        if int(self.timed_out.item()) != 0:
-            raise RuntimeError('a peer did not reach the barrier (rank %d of %d)' % (self.rank, self.world))
+        """Synchronises this rank's device, then raises PeerTimeout if any barrier gave up.  Call it wherever the
+        parameters are about to be trusted (before a checkpoint, at the end of training)."""
+        torch.cuda.synchronize(self.device)
+        self._raise_if_timed_out()
 
     def close(self):
         self.arena.close()

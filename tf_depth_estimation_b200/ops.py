@@ -3,6 +3,10 @@
 torch is used for device memory, streams and autograd bookkeeping only; every number is produced by the
 hand-written sm_100a kernels in csrc/.  All tensors must be CUDA float32; anything else raises.
 """
+import collections
+import threading
+import warnings
+
 import torch
 
 from . import _lib
@@ -13,11 +17,84 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+class VslLayoutWarning(UserWarning):
+    """A non-contiguous input was copied into a packed buffer before the C call."""
+
+
+_LAYOUT_POLICY = ['copy']
+
+
+def set_layout_policy(policy):
+    """What to do with a non-contiguous input (the C ABI takes packed buffers, as TF hands its kernels):
+    'copy'   -- pack it into a fresh buffer and emit a VslLayoutWarning naming the argument (default: the reference's
+                call sites pass channel slices such as src_image_stack[:, :, :, 3*i:3*(i+1)], train.py:127, which
+                TF materialises too);
+    'strict' -- raise ValueError (for callers that want to be sure no hidden copy sits on their hot path).
+    Returns the previous policy."""
+    if policy not in ('copy', 'strict'):
+        raise ValueError("policy must be 'copy' or 'strict'")
+    prev, _LAYOUT_POLICY[0] = _LAYOUT_POLICY[0], policy
+    return prev
+
+
+def from_external(t, name='tensor'):
+    """Ingress for device memory owned by another framework: anything that speaks DLPack (`__dlpack__`, or a raw
+    DLPack capsule such as tf.experimental.dlpack.to_dlpack(x) returns) or `__cuda_array_interface__` (CuPy, Numba)
+    becomes a zero-copy torch view.  torch here is the memory / stream plumbing under the C ABI, not a compute path."""
+    if isinstance(t, torch.Tensor):
+        return t
+    if type(t).__name__ == 'PyCapsule':
+        return torch.utils.dlpack.from_dlpack(t)
+    if hasattr(t, '__dlpack__'):
+        return torch.from_dlpack(t)
+    if hasattr(t, '__cuda_array_interface__'):
+        return torch.as_tensor(t, device='cuda')
+    raise TypeError('%s must be a CUDA tensor, a DLPack producer or a __cuda_array_interface__ object, got %s'
+                    % (name, type(t).__name__))
+
+
+def _is_foreign(t):
+    return (not isinstance(t, torch.Tensor)) and (type(t).__name__ == 'PyCapsule' or hasattr(t, '__dlpack__') or
+                                                    hasattr(t, '__cuda_array_interface__'))
+
+
+def _ingress(fn):
+    """Public entry points accept foreign device tensors for every tensor argument (see from_external)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*args, **kw):
+        args = [from_external(a) if _is_foreign(a) else a for a in args]
+        kw = {k: (from_external(v) if _is_foreign(v) else v) for k, v in kw.items()}
+        return fn(*args, **kw)
+    return wrapped
+
+
+def to_dlpack(t):
+    """Egress: a DLPack capsule of a result (zero copy), e.g. for tf.experimental.dlpack.from_dlpack."""
+    return torch.utils.dlpack.to_dlpack(t)
+
+
 def _f32(t, name):
-    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+    t = from_external(t, name)
+    if not t.is_cuda:
         raise TypeError('%s must be a CUDA tensor (this path has no CPU fallback)' % name)
     if t.dtype != torch.float32:
         raise TypeError('%s must be float32, got %s' % (name, t.dtype))
+    if not t.is_contiguous():
+        if _LAYOUT_POLICY[0] == 'strict':
+            raise ValueError('%s is not contiguous (shape %s, strides %s) and the layout policy is strict'
+                             % (name, tuple(t.shape), tuple(t.stride())))
+        warnings.warn('%s is not contiguous (shape %s, strides %s): packed into a copy before the C call'
+                      % (name, tuple(t.shape), tuple(t.stride())), VslLayoutWarning, stacklevel=3)
+        t = t.contiguous()
+    return t
+
+
+def _g32(t, name='grad'):
+    """An upstream gradient handed over by autograd (never a caller's input): packed without a warning."""
+    if t.dtype != torch.float32 or not t.is_cuda:
+        raise TypeError('%s must be CUDA float32' % name)
     return t.contiguous()
 
 
@@ -53,11 +130,12 @@ class _PoseVec2Mat(torch.autograd.Function):
     def backward(ctx, g_mat):
         vec, = ctx.saved_tensors
         g_vec = torch.empty_like(vec)
-        check(_lib.load().vsl_pose_vec2mat_bwd(vec.data_ptr(), _f32(g_mat, 'g_mat').data_ptr(), vec.shape[0],
+        check(_lib.load().vsl_pose_vec2mat_bwd(vec.data_ptr(), _g32(g_mat, 'g_mat').data_ptr(), vec.shape[0],
                                                ctx.fmt, g_vec.data_ptr(), _stream()))
         return g_vec, None
 
 
+@_ingress
 def pose_vec2mat(vec, format='eular'):
     if vec.dim() != 2 or vec.shape[1] != 6:
         raise ValueError('vec must be [B, 6], got %s' % (tuple(vec.shape),))
@@ -94,7 +172,7 @@ class _ProjectiveInverseWarp(torch.autograd.Function):
         img, depth, pose, K = ctx.saved_tensors
         B, H, W, C = img.shape
         need_img, need_depth, need_pose = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
-        gs = [None if g is None else _f32(g, 'grad') for g in (g_out, g_coords, g_wmask, g_z, g_pose_mat)]
+        gs = [None if g is None else _g32(g, 'grad') for g in (g_out, g_coords, g_wmask, g_z, g_pose_mat)]
         g_img = torch.empty_like(img) if need_img else None
         g_depth = torch.empty_like(depth) if need_depth else None
         g_pose = torch.empty_like(pose) if need_pose else None
@@ -105,6 +183,7 @@ class _ProjectiveInverseWarp(torch.autograd.Function):
         return g_img, g_depth, g_pose, None, None
 
 
+@_ingress
 def projective_inverse_warp(img, depth, pose, intrinsics, format='eular'):
     """utils_lr.py:222-256 -> (out_img, src_pixel_coords, wmask, src_depth, pose_mat)."""
     fmt = _fmt(format)
@@ -146,8 +225,8 @@ class _Bilinear(torch.autograd.Function):
         B, Hs, Ws, C = imgs.shape
         ref = coords if coords is not None else flowx
         Ht, Wt = ref.shape[1], ref.shape[2]
-        g_out = None if g_out is None else _f32(g_out, 'g_out')
-        g_wmask = None if g_wmask is None else _f32(g_wmask, 'g_wmask')
+        g_out = None if g_out is None else _g32(g_out, 'g_out')
+        g_wmask = None if g_wmask is None else _g32(g_wmask, 'g_wmask')
         need_c = any(ctx.needs_input_grad[1:])
         g_imgs = torch.empty_like(imgs) if ctx.needs_input_grad[0] else None
         g_coords = torch.empty(B, Ht, Wt, 2, device=imgs.device) if need_c else None
@@ -160,6 +239,7 @@ class _Bilinear(torch.autograd.Function):
         return g_imgs, None, gfx, gfy
 
 
+@_ingress
 def bilinear_sampler(imgs, coords):
     """utils.py:219-308 -> (output, wmask)."""
     if imgs.dim() != 4 or coords.dim() != 4 or coords.shape[3] != 2 or coords.shape[0] != imgs.shape[0]:
@@ -167,6 +247,7 @@ def bilinear_sampler(imgs, coords):
     return _Bilinear.apply(imgs, coords, None, None)
 
 
+@_ingress
 def optflow_warp(img, flowx, flowy):
     """utils.py:201-217 -> output_img."""
     B, H, W, _ = img.shape
@@ -190,6 +271,7 @@ class _DepthOptflow(torch.autograd.Function):
         return torch.cat([gfx, gfy], dim=3)
 
 
+@_ingress
 def depth_optflow(src_pixel_coords):
     """utils.py:321-338 -> (flowx, flowy)."""
     return _DepthOptflow.apply(src_pixel_coords)
@@ -216,10 +298,11 @@ class _ConsistentDepth(torch.autograd.Function):
         g_p = torch.empty_like(pred) if ctx.needs_input_grad[1] else None
         g_c = torch.empty_like(coords) if ctx.needs_input_grad[2] else None
         check(_lib.load().vsl_consist_bwd(src_depth.data_ptr(), pred.data_ptr(), coords.data_ptr(), B, Hs, Ws, Ht, Wt,
-                                          _f32(g_err, 'g_err').data_ptr(), _p(g_s), _p(g_p), _p(g_c), _stream()))
+                                          _g32(g_err, 'g_err').data_ptr(), _p(g_s), _p(g_p), _p(g_c), _stream()))
         return g_s, g_p, g_c
 
 
+@_ingress
 def consistent_depth_loss(src_depth, pred_src_depth, coords):
     """utils_lr.py:369-458: |pred_src_depth - bilinear(src_depth, coords)| (no reduction), one kernel each way."""
     if src_depth.dim() != 4 or src_depth.shape[3] != 1 or coords.dim() != 4 or coords.shape[3] != 2:
@@ -254,11 +337,12 @@ class _Pixel2Cam(torch.autograd.Function):
         pc, K = ctx.saved_tensors
         B, _, H, W = pc.shape
         g_depth = torch.empty(B, H, W, device=pc.device)
-        check(_lib.load().vsl_pixel2cam_bwd(pc.data_ptr(), K.data_ptr(), _f32(g_cam, 'g_cam').data_ptr(), B, H, W,
+        check(_lib.load().vsl_pixel2cam_bwd(pc.data_ptr(), K.data_ptr(), _g32(g_cam, 'g_cam').data_ptr(), B, H, W,
                                             int(ctx.homog), g_depth.data_ptr(), _stream()))
         return g_depth, None, None, None
 
 
+@_ingress
 def pixel2cam(depth, pixel_coords, intrinsics, is_homogeneous=True):
     """utils.py:100-119 -> [B, 4|3, H, W].  Differentiable wrt depth."""
     if depth.dim() != 3 or pixel_coords.dim() != 4 or pixel_coords.shape[1] != 3:
@@ -284,13 +368,14 @@ class _Cam2Pixel(torch.autograd.Function):
         B, _, H, W = cam.shape
         g_cam = torch.empty_like(cam) if ctx.needs_input_grad[0] else None
         g_proj = torch.empty_like(proj) if ctx.needs_input_grad[1] else None
-        gc = None if g_coords is None else _f32(g_coords, 'g_coords')
-        gz = None if g_z is None else _f32(g_z, 'g_z')
+        gc = None if g_coords is None else _g32(g_coords, 'g_coords')
+        gz = None if g_z is None else _g32(g_z, 'g_z')
         check(_lib.load().vsl_cam2pixel_bwd(cam.data_ptr(), proj.data_ptr(), _p(gc), _p(gz), B, H, W, _p(g_cam),
                                             _p(g_proj), _stream()))
         return g_cam, g_proj
 
 
+@_ingress
 def cam2pixel(cam_coords, proj):
     """utils_lr.py:172-194 -> (pixel_coords [B,H,W,2], z_u [B,H,W,1])."""
     if cam_coords.dim() != 4 or cam_coords.shape[1] != 4 or tuple(proj.shape) != (cam_coords.shape[0], 4, 4):
@@ -312,11 +397,12 @@ class _AxisAngle(torch.autograd.Function):
     def backward(ctx, g_R):
         axis, angle = ctx.saved_tensors
         g_axis, g_angle = torch.empty_like(axis), torch.empty_like(angle)
-        check(_lib.load().vsl_axis_angle_bwd(axis.data_ptr(), angle.data_ptr(), _f32(g_R, 'g_R').data_ptr(),
+        check(_lib.load().vsl_axis_angle_bwd(axis.data_ptr(), angle.data_ptr(), _g32(g_R, 'g_R').data_ptr(),
                                              axis.shape[0], g_axis.data_ptr(), g_angle.data_ptr(), _stream()))
         return g_axis, g_angle
 
 
+@_ingress
 def axis_angle_to_rotation_matrix(axis, angle):
     """utils_lr.py:77-103: axis [B,3], angle [B,1,1] -> I + sin(angle) [axis]x + (1-cos(angle)) [axis]x^2."""
     if axis.dim() != 2 or axis.shape[1] != 3 or angle.numel() != axis.shape[0]:
@@ -324,6 +410,7 @@ def axis_angle_to_rotation_matrix(axis, angle):
     return _AxisAngle.apply(axis, angle.reshape(-1)).reshape(-1, 3, 3)
 
 
+@_ingress
 def euler2mat(z, y, x):
     """utils.py:26-75: z, y, x [B,1] -> R = Rx.Ry.Rz [B,1,3,3] (angles clipped to +-pi)."""
     vec = torch.cat([torch.zeros(z.shape[0], 3, device=z.device), x.reshape(-1, 1), y.reshape(-1, 1), z.reshape(-1, 1)], 1)
@@ -349,11 +436,12 @@ class _SmoothLoss(torch.autograd.Function):
         x, = ctx.saved_tensors
         B, H, W, C = x.shape
         g_x = torch.empty_like(x)
-        check(_lib.load().vsl_smooth_bwd(x.data_ptr(), B, H, W, C, ctx.inverse, _f32(g, 'g').data_ptr(),
+        check(_lib.load().vsl_smooth_bwd(x.data_ptr(), B, H, W, C, ctx.inverse, _g32(g, 'g').data_ptr(),
                                          g_x.data_ptr(), _stream()))
         return g_x, None
 
 
+@_ingress
 def compute_smooth_loss(pred_disp, inverse=False):
     """my_losses.py:27-36.  inverse=True evaluates the loss on 1/pred_disp inside the kernel."""
     if pred_disp.dim() != 4:
@@ -377,11 +465,12 @@ class _ExpReg(torch.autograd.Function):
     def backward(ctx, g):
         logits, = ctx.saved_tensors
         g_l = torch.empty_like(logits)
-        check(_lib.load().vsl_expreg_bwd(logits.data_ptr(), logits.numel() // 2, _f32(g, 'g').data_ptr(),
+        check(_lib.load().vsl_expreg_bwd(logits.data_ptr(), logits.numel() // 2, _g32(g, 'g').data_ptr(),
                                          g_l.data_ptr(), _stream()))
         return g_l
 
 
+@_ingress
 def compute_exp_reg_loss(pred, ref=None):
     """my_losses.py:39-43 with ref = the constant [0,1] mask of my_losses.py:14-23 (the only one used)."""
     if pred.shape[-1] != 2:
@@ -415,7 +504,7 @@ class _Ssim(torch.autograd.Function):
     def backward(ctx, g):
         x, y = ctx.saved_tensors
         B, H, W, C = x.shape
-        g = _f32(g, 'g')
+        g = _g32(g, 'g')
         g_x = torch.empty_like(x) if ctx.needs_input_grad[0] else None
         g_y = torch.empty_like(y) if ctx.needs_input_grad[1] else None
         if g_x is None and g_y is None:
@@ -427,11 +516,13 @@ class _Ssim(torch.autograd.Function):
         return g_x, g_y, None
 
 
+@_ingress
 def ssim_dissimilarity(x, y):
     """EXTENSION (not in the reference): clip((1 - SSIM(x, y)) / 2, 0, 1), 3x3 VALID pools -> [B,H-2,W-2,C]."""
     return _Ssim.apply(x, y, False)
 
 
+@_ingress
 def ssim_loss(x, y):
     """EXTENSION: mean of ssim_dissimilarity(x, y), reduced inside the kernel (no map is written)."""
     return _Ssim.apply(x, y, True)
@@ -457,11 +548,12 @@ class _EdgeSmooth(torch.autograd.Function):
         B, H, W, C = img.shape
         g_d = torch.empty_like(disp)
         g_i = torch.empty_like(img) if ctx.needs_input_grad[1] else None
-        check(_lib.load().vsl_edge_smooth_bwd(disp.data_ptr(), img.data_ptr(), B, H, W, C, _f32(g, 'g').data_ptr(),
+        check(_lib.load().vsl_edge_smooth_bwd(disp.data_ptr(), img.data_ptr(), B, H, W, C, _g32(g, 'g').data_ptr(),
                                               g_d.data_ptr(), _p(g_i), _stream()))
         return g_d, g_i
 
 
+@_ingress
 def edge_aware_smooth_loss(disp, img):
     """EXTENSION (not in the reference): mean(|d_x disp| exp(-mean_c |d_x img|)) + the same along y."""
     return _EdgeSmooth.apply(disp, img)
@@ -481,6 +573,7 @@ def adam_step(param, grad, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1e-8, gra
                                     _stream() if stream is None else stream))
 
 
+@_ingress
 def image_pyramid(img, num_scales):
     """tf.image.resize_area(img, [H/2^s, W/2^s]) for s = 0..S-1 (level 0 is `img` itself). No gradient."""
     lib = _lib.load()
@@ -534,9 +627,70 @@ def _arena(shapes, device=None, pinned=False):
     return buf, views
 
 
+def _loss_out_shapes(B, H, W, S, V, fmt, mask_mode):
+    pose_shape = (B, V, 4, 4) if fmt == 2 else (B, V, 6)
+    shapes = [(4,)] + [(B, H >> s, W >> s, 1) for s in range(S)] + [pose_shape]
+    if mask_mode == _lib.MASK_EXP:
+        shapes += [(B, H >> s, W >> s, 2 * V) for s in range(S)]
+    return shapes
+
+
+class LossOutputs(object):
+    """Everything one fused step produces -- losses[3], d/dx per scale, d/dposes, d/dlogits per scale -- as views of
+    ONE float32 arena (a host pipeline fetches them with a single copy; the upstream gradient is applied to them
+    with a single launch)."""
+
+    def __init__(self, B, H, W, S, V, fmt, mask_mode, device):
+        self.shapes = _loss_out_shapes(B, H, W, S, V, fmt, mask_mode)
+        self.arena, views = _arena(self.shapes, device=device)
+        self.losses = views[0][:3]           # (pixel, smooth, exp)
+        self.total = views[0][3]             # their sum, written by the same kernel
+        self.g_x = views[1:1 + S]
+        self.g_poses = views[1 + S]
+        self.g_logits = views[2 + S:2 + 2 * S] if mask_mode == _lib.MASK_EXP else None
+        self.grad_offset = 64              # floats: the gradients start at the arena's second 256-byte slot
+        self._gx_ptrs = ptr_array([t.data_ptr() for t in self.g_x])
+        self._gl_ptrs = ptr_array([t.data_ptr() for t in self.g_logits]) if self.g_logits else None
+
+
+def _want(shape, t, name):
+    if tuple(t.shape) != tuple(shape):
+        raise ValueError('%s must have shape %s, got %s' % (name, tuple(shape), tuple(t.shape)))
+
+
+def check_loss_shapes(B, H, W, S, V, fmt, mask_mode, tgt, srcs, x_pyr, poses, K_pyr, logits_pyr=None, mask_pyr=None):
+    """ValueError unless every tensor has the shape the fused step indexes it by."""
+    _want((B, H, W, 3), tgt, 'tgt')
+    if len(srcs) != V:
+        raise ValueError('srcs must hold %d source views, got %d' % (V, len(srcs)))
+    for v, t in enumerate(srcs):
+        _want((B, H, W, 3), t, 'srcs[%d]' % v)
+    if len(x_pyr) != S:
+        raise ValueError('x_pyr must hold num_scales=%d levels (finest first), got %d' % (S, len(x_pyr)))
+    for s_, t in enumerate(x_pyr):
+        _want((B, H >> s_, W >> s_, 1), t, 'x_pyr[%d]' % s_)
+    _want((B, V, 4, 4) if fmt == 2 else (B, V, 6), poses, 'poses')
+    _want((B, S, 3, 3), K_pyr, 'K_pyr')
+    if mask_mode == _lib.MASK_EXP:
+        if logits_pyr is None or len(logits_pyr) != S:
+            raise ValueError('logits_pyr must hold %d levels' % S)
+        for s_, t in enumerate(logits_pyr):
+            _want((B, H >> s_, W >> s_, 2 * V), t, 'logits_pyr[%d]' % s_)
+    elif logits_pyr is not None:
+        raise ValueError('logits_pyr given but the step runs without the explainability mask')
+    if mask_mode == _lib.MASK_CONST:
+        if mask_pyr is None or len(mask_pyr) != S:
+            raise ValueError('mask_pyr must hold %d levels' % S)
+        for s_, t in enumerate(mask_pyr):
+            _want((B, H >> s_, W >> s_, 1), t, 'mask_pyr[%d]' % s_)
+    elif mask_pyr is not None:
+        raise ValueError('mask_pyr given but the step runs without a constant mask')
+
+
 class ViewSynthesisPlan(object):
-    """Pre-allocated state for repeated fused-loss steps at one shape: workspace, gradient buffers and the
-    pointer tables of the C call.  One instance per (shape, flags); not thread-safe."""
+    """Pre-allocated state for repeated fused-loss steps at one shape: the descriptor, the workspace and (for the
+    plan's own run()/run_bound()) one set of output buffers.  One instance per (shape, flags); the workspace is
+    reused by every call, so calls of one plan must be ordered on one stream."""
 
     def __init__(self, B, H, W, V, flags, mask_mode, device, loss_scale=1.0, want_src_grad=False):
         lib = _lib.load()
@@ -544,6 +698,7 @@ class ViewSynthesisPlan(object):
         self.want_src_grad = bool(want_src_grad)
         self.B, self.H, self.W, self.S, self.V = B, H, W, S, V
         self.mask_mode = mask_mode
+        self.device = device
         self.fmt = _fmt(flags.pose_format)
         self.desc = VslLossDesc(B, H, W, S, V, self.fmt, mask_mode, int(flags.pixel_scale_norm),
                                 int(flags.depth_is_inverse), int(flags.smooth_on_inverse),
@@ -556,34 +711,42 @@ class ViewSynthesisPlan(object):
         if nbytes == 0:
             raise ValueError('unsupported loss shape B=%d H=%d W=%d S=%d V=%d' % (B, H, W, S, V))
         self.ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
-        # every output of a step lives in one arena, so a host pipeline can fetch them with a single copy
-        pose_shape = (B, V, 4, 4) if self.fmt == 2 else (B, V, 6)
-        shapes = [(3,)] + [(B, H >> s, W >> s, 1) for s in range(S)] + [pose_shape]
-        if mask_mode == _lib.MASK_EXP:
-            shapes += [(B, H >> s, W >> s, 2 * V) for s in range(S)]
-        self.out_arena, views = _arena(shapes, device=device)
-        self.out_shapes = shapes
-        self.losses = views[0]
-        self.losses.zero_()
-        self.g_x = views[1:1 + S]
-        self.g_poses = views[1 + S]
-        self.g_logits = views[2 + S:2 + 2 * S] if mask_mode == _lib.MASK_EXP else None
+        self.out = self.new_outputs()
+        self.out_arena, self.out_shapes = self.out.arena, self.out.shapes
+        self.losses = self.out.losses
+        self.out.arena[:4].zero_()
+        self.g_x, self.g_poses, self.g_logits = self.out.g_x, self.out.g_poses, self.out.g_logits
         # d/d(source images): produced only on request (an extra atomic scatter + fold-back pass)
-        self.g_srcs = [torch.empty(B, H, W, 3, device=device) for _ in range(V)] if self.want_src_grad else None
-        self._gs_ptrs = ptr_array([t.data_ptr() for t in self.g_srcs]) if self.g_srcs else None
-        self.version = 0  # bumped by every run(); lets autograd detect a stale backward
-        self._gx_ptrs = ptr_array([t.data_ptr() for t in self.g_x])
-        self._gl_ptrs = ptr_array([t.data_ptr() for t in self.g_logits]) if self.g_logits else None
+        self.g_srcs = self.new_src_grads() if self.want_src_grad else None
+        self.version = 0  # bumped by every run()
 
-    def bind(self, tgt, srcs, x_pyr, poses, K_pyr, logits_pyr=None, mask_pyr=None):
-        """Pre-marshal the C arguments for one set of input buffers; run_bound(args) then costs one ctypes
-        call.  The caller keeps the tensors alive."""
+    def new_outputs(self):
+        return LossOutputs(self.B, self.H, self.W, self.S, self.V, self.fmt, self.mask_mode, self.device)
+
+    def new_src_grads(self):
+        return [torch.empty(self.B, self.H, self.W, 3, device=self.device) for _ in range(self.V)]
+
+    def check_inputs(self, tgt, srcs, x_pyr, poses, K_pyr, logits_pyr=None, mask_pyr=None):
+        """Every tensor's shape against the plan's (B, H, W, S, V, pose format, mask mode): the C call indexes raw
+        pointers by the plan's sizes, so a mismatch must be an error here, never an out-of-bounds read there."""
+        check_loss_shapes(self.B, self.H, self.W, self.S, self.V, self.fmt, self.mask_mode, tgt, srcs, x_pyr, poses,
+                          K_pyr, logits_pyr, mask_pyr)
+        for t in [tgt, poses, K_pyr] + list(srcs) + list(x_pyr) + list(logits_pyr or []) + list(mask_pyr or []):
+            if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+                raise TypeError('the fused step takes contiguous CUDA float32 tensors (no CPU fallback)')
+
+    def bind(self, tgt, srcs, x_pyr, poses, K_pyr, logits_pyr=None, mask_pyr=None, out=None, g_srcs=None):
+        """Validate and pre-marshal the C arguments for one set of input (and output) buffers; run_bound(args) then
+        costs one ctypes call.  The caller keeps the tensors alive."""
+        self.check_inputs(tgt, srcs, x_pyr, poses, K_pyr, logits_pyr, mask_pyr)
+        out = self.out if out is None else out
+        g_srcs = self.g_srcs if g_srcs is None else g_srcs
         return (self.desc, tgt.data_ptr(), ptr_array([s.data_ptr() for s in srcs]),
                 ptr_array([x.data_ptr() for x in x_pyr]), poses.data_ptr(), K_pyr.data_ptr(),
                 ptr_array([l.data_ptr() for l in logits_pyr]) if logits_pyr is not None else None,
                 ptr_array([m.data_ptr() for m in mask_pyr]) if mask_pyr is not None else None,
-                self.losses.data_ptr(), self._gx_ptrs, self.g_poses.data_ptr(), self._gl_ptrs, self._gs_ptrs,
-                self.ws.data_ptr())
+                out.losses.data_ptr(), out._gx_ptrs, out.g_poses.data_ptr(), out._gl_ptrs,
+                ptr_array([t.data_ptr() for t in g_srcs]) if g_srcs else None, self.ws.data_ptr())
 
     def run_bound(self, args, stream=None):
         self.version += 1
@@ -601,6 +764,11 @@ class ViewSynthesisPlan(object):
 
 
 class _ViewSynthesisLoss(torch.autograd.Function):
+    """Forward runs the fused step: the gradients of (pixel + smooth + exp) * loss_scale come out of the same kernel
+    pass, into an output arena that belongs to THIS call (so any number of forwards may precede their backwards).
+    Backward applies the upstream gradient of `total` to that arena with one launch (vsl_scale; a no-op kernel when
+    it is exactly 1, i.e. total.backward()) and hands out views of it."""
+
     @staticmethod
     def forward(ctx, plan, tgt, K_pyr, poses, n_src, n_x, *rest_all):
         srcs = [_f32(t, 'src') for t in rest_all[:n_src]]
@@ -608,56 +776,114 @@ class _ViewSynthesisLoss(torch.autograd.Function):
         rest = [_f32(t, 'pyr') for t in rest_all[n_src + n_x:]]
         logits = rest if plan.mask_mode == _lib.MASK_EXP else None
         mask = rest if plan.mask_mode == _lib.MASK_CONST else None
-        plan.run(_f32(tgt, 'tgt'), srcs, x_pyr, _f32(poses, 'poses'), _f32(K_pyr, 'K_pyr'), logits, mask)
-        ctx.plan = plan
-        ctx.version = plan.version
-        ctx.n_src = n_src
-        ctx.n_x = n_x
-        ctx.n_rest = len(rest)
-        losses = plan.losses.clone()
-        total = losses.sum()
+        out = plan.new_outputs()
+        g_srcs = plan.new_src_grads() if plan.want_src_grad else None
+        plan.run_bound(plan.bind(_f32(tgt, 'tgt'), srcs, x_pyr, _f32(poses, 'poses'), _f32(K_pyr, 'K_pyr'), logits,
+                                 mask, out=out, g_srcs=g_srcs))
+        ctx.out, ctx.g_srcs, ctx.mask_mode = out, g_srcs, plan.mask_mode
+        ctx.n_src, ctx.n_x, ctx.n_rest = n_src, n_x, len(rest)
+        ctx.applied = None                    # device scalar: the upstream factor the arena currently carries
+        # views of this call's own arena: no copy, no reduction launch (the finalize kernel wrote the total too)
+        total, losses = out.total.view(()), out.losses.view(3)
         ctx.mark_non_differentiable(losses)
         return total, losses
 
     @staticmethod
     def backward(ctx, g_total, _g_losses):
-        plan = ctx.plan
-        if plan.version != ctx.version:
-            raise RuntimeError('view_synthesis_loss: the plan ran again before this backward; the gradients of '
-                               'the earlier forward were overwritten (call backward before the next forward)')
-        g_src = ([g * g_total for g in plan.g_srcs] if plan.g_srcs is not None else [None] * ctx.n_src)
-        g_x = [g * g_total for g in plan.g_x]
-        g_rest = ([g * g_total for g in plan.g_logits] if plan.mask_mode == _lib.MASK_EXP
-                  else [None] * ctx.n_rest)
-        return (None, None, None, plan.g_poses * g_total, None, None) + tuple(g_src) + tuple(g_x) + tuple(g_rest)
+        lib, out = _lib.load(), ctx.out
+        g = g_total.detach().to(torch.float32).reshape(1).contiguous()
+        n = out.arena.numel() - out.grad_offset
+        src_ptr = out.arena.data_ptr() + 4 * out.grad_offset
+        if ctx.applied is None:               # the usual single backward: in place
+            check(lib.vsl_scale(src_ptr, src_ptr, n, g.data_ptr(), None, _stream()))
+            ctx.applied = g
+            g_x, g_poses, g_logits = out.g_x, out.g_poses, out.g_logits
+            g_srcs = ctx.g_srcs
+            if g_srcs is not None:
+                for t in g_srcs:
+                    check(lib.vsl_scale(t.data_ptr(), t.data_ptr(), t.numel(), g.data_ptr(), None, _stream()))
+        else:                                 # backward again (retain_graph): fresh buffers, factor g / applied
+            fresh = LossOutputs.__new__(LossOutputs)
+            fresh.arena = torch.empty_like(out.arena)
+            check(lib.vsl_scale(fresh.arena.data_ptr() + 4 * out.grad_offset, src_ptr, n, g.data_ptr(),
+                                ctx.applied.data_ptr(), _stream()))
+            views, o = [], 0
+            for shp in out.shapes:
+                cnt = 1
+                for d in shp:
+                    cnt *= d
+                views.append(fresh.arena[o:o + cnt].view(*shp))
+                o += (cnt + 63) // 64 * 64
+            S = len(out.g_x)
+            g_x, g_poses = views[1:1 + S], views[1 + S]
+            g_logits = views[2 + S:2 + 2 * S] if out.g_logits is not None else None
+            g_srcs = None
+            if ctx.g_srcs is not None:
+                g_srcs = [torch.empty_like(t) for t in ctx.g_srcs]
+                for d, t in zip(g_srcs, ctx.g_srcs):
+                    check(lib.vsl_scale(d.data_ptr(), t.data_ptr(), t.numel(), g.data_ptr(), ctx.applied.data_ptr(),
+                                        _stream()))
+        gs = tuple(g_srcs) if g_srcs is not None else (None,) * ctx.n_src
+        gr = tuple(g_logits) if ctx.mask_mode == _lib.MASK_EXP else (None,) * ctx.n_rest
+        return (None, None, None, g_poses, None, None) + gs + tuple(g_x) + gr
 
 
-_PLANS = {}
+_PLANS = collections.OrderedDict()
+_PLANS_LOCK = threading.Lock()
+_PLANS_MAX = 8
 
 
-def view_synthesis_loss(tgt, srcs, x_pyr, poses, K_pyr, logits_pyr=None, mask_pyr=None, flags=None):
+def _plan_for(key, make):
+    """Bounded (LRU, _PLANS_MAX entries) and thread-safe cache of plans: a plan owns a workspace as large as the
+    re-laid source pyramids, so shapes that are no longer used must not pin device memory for ever."""
+    with _PLANS_LOCK:
+        plan = _PLANS.get(key)
+        if plan is not None:
+            _PLANS.move_to_end(key)
+            return plan
+        plan = _PLANS[key] = make()
+        while len(_PLANS) > _PLANS_MAX:
+            _PLANS.popitem(last=False)
+        return plan
+
+
+def view_synthesis_loss(tgt, srcs, x_pyr, poses, K_pyr, logits_pyr=None, mask_pyr=None, flags=None, loss_scale=1.0):
     """The reference's per-scale loss loop (train.py:107-135 + train_depth_then_cam_lr.py:297-328) as ONE fused
     forward+backward call.
 
-    tgt [B,H,W,3]; srcs: list of V [B,H,W,3]; x_pyr: list of S network outputs [B,Hs,Ws,1]; poses [B,V,6] or
-    [B,V,4,4]; K_pyr [B,S,3,3]; logits_pyr: list of S [B,Hs,Ws,2V] (explainability) or mask_pyr: list of S
-    constant weights [B,Hs,Ws,1].  -> (total, losses[3] = pixel, smooth, exp).  `total` is differentiable wrt
-    x_pyr, poses and logits_pyr; the gradients were produced in the same kernel pass as the loss.
+    tgt [B,H,W,3]; srcs: list of V [B,H,W,3]; x_pyr: list of S network outputs [B,Hs,Ws,1] (finest first); poses
+    [B,V,6] or [B,V,4,4]; K_pyr [B,S,3,3]; logits_pyr: list of S [B,Hs,Ws,2V] (explainability) or mask_pyr: list of S
+    constant weights [B,Hs,Ws,1].  Every shape is checked (ValueError) before anything reaches the C call.
+    -> (total, losses[3] = pixel, smooth, exp).  `total` is differentiable wrt x_pyr, poses and logits_pyr (and the
+    source images if they require grad); the gradients were produced in the same kernel pass as the loss.
+    loss_scale: a constant factor of the objective known up front (a data-parallel rank's B_local / B_global share,
+    dist.local_loss_scale) -- folded into the kernel's gradients for free; `total` and `losses` stay unscaled means.
     """
     flags = flags or LossFlags()
     if logits_pyr is not None and mask_pyr is not None:
         raise ValueError('give logits_pyr or mask_pyr, not both')
+    tgt = from_external(tgt, 'tgt')
+    if not tgt.is_cuda:
+        raise TypeError('view_synthesis_loss takes CUDA tensors (this path has no CPU fallback)')
+    srcs = [from_external(t, 'srcs') for t in srcs]
+    x_pyr = [from_external(t, 'x_pyr') for t in x_pyr]
+    poses, K_pyr = from_external(poses, 'poses'), from_external(K_pyr, 'K_pyr')
+    if tgt.dim() != 4 or tgt.shape[3] != 3:
+        raise ValueError('tgt must be [B,H,W,3], got %s' % (tuple(tgt.shape),))
     B, H, W, C = tgt.shape
     V, S = len(srcs), flags.num_scales
-    if C != 3 or len(x_pyr) != S:
-        raise ValueError('tgt must be [B,H,W,3] and x_pyr must hold num_scales=%d levels' % S)
+    if len(x_pyr) != S:
+        raise ValueError('x_pyr must hold num_scales=%d levels' % S)
     mode = _lib.MASK_EXP if logits_pyr is not None else (_lib.MASK_CONST if mask_pyr is not None else _lib.MASK_NONE)
     want_src = any(getattr(t, 'requires_grad', False) for t in srcs)
-    key = (B, H, W, V, mode, tgt.device, want_src, tuple(sorted(flags.__dict__.items())))
-    plan = _PLANS.get(key)
-    if plan is None:
-        plan = _PLANS[key] = ViewSynthesisPlan(B, H, W, V, flags, mode, tgt.device, want_src_grad=want_src)
-    rest = list(logits_pyr if logits_pyr is not None else (mask_pyr or []))
+    rest = [from_external(t, 'pyr') for t in (logits_pyr if logits_pyr is not None else (mask_pyr or []))]
+    # shapes first: a wrong layout is a ValueError here, before any pointer reaches the library
+    check_loss_shapes(B, H, W, S, V, _fmt(flags.pose_format), mode, tgt, srcs, x_pyr, poses, K_pyr,
+                      rest if mode == _lib.MASK_EXP else None, rest if mode == _lib.MASK_CONST else None)
+    key = (B, H, W, V, mode, tgt.device, torch.cuda.current_stream(tgt.device).cuda_stream, want_src, float(loss_scale),
+           tuple(sorted(flags.__dict__.items())))
+    plan = _plan_for(key, lambda: ViewSynthesisPlan(B, H, W, V, flags, mode, tgt.device, loss_scale=loss_scale,
+                                                    want_src_grad=want_src))
     return _ViewSynthesisLoss.apply(plan, tgt, K_pyr, poses, V, S, *srcs, *x_pyr, *rest)
 
 
@@ -698,9 +924,13 @@ class HostPipeline(object):
         for p in self.plans:
             buf, views = _arena(p.out_shapes, pinned=True)
             self.host_out_arena.append(buf)
-            self.host_out.append(dict(losses=views[0], g_x=views[1:1 + S], g_poses=views[1 + S],
+            self.host_out.append(dict(losses=views[0][:3], total=views[0][3], g_x=views[1:1 + S], g_poses=views[1 + S],
                                       g_lgs=(views[2 + S:2 + 2 * S] if mask_mode == _lib.MASK_EXP else [])))
         self.s_in, self.s_comp, self.s_out = (torch.cuda.Stream(device=device) for _ in range(3))
+        # the plans' buffers were initialised on the current stream: nothing on the side streams may overtake that
+        cur = torch.cuda.current_stream(device)
+        for st in (self.s_in, self.s_comp, self.s_out):
+            st.wait_stream(cur)
         ev = lambda: [torch.cuda.Event() for _ in range(self.DEPTH)]
         self.ev_in, self.ev_comp, self.ev_out = ev(), ev(), ev()
         self.step = 0

@@ -28,20 +28,23 @@ def _warp_grad(op, g_out, g_coords, g_wmask, g_z, g_pose_mat):
 
 def view_synthesis_loss(tgt, srcs, x_pyr, poses, k_pyr, logits_pyr, FLAGS, pose_format='eular'):
     """The per-scale loop of train.py:107-135 / train_depth_then_cam_lr.py:297-328 as one op.
-    -> (pixel_loss, smooth_loss, exp_loss); differentiable wrt x_pyr, poses, logits_pyr."""
+    -> (total, pixel_loss, smooth_loss, exp_loss).  Only `total` (= pixel + smooth + exp, the sum every train script
+    forms, term weights already inside FLAGS) is differentiable, wrt x_pyr, poses, logits_pyr: the op produces ONE set
+    of gradients, those of the sum.  The three terms are returned under stop_gradient for summaries; re-weighting
+    them after the fact would silently use the wrong gradients, so it is made impossible instead."""
     out = _mod.vsl_view_synthesis_loss(tgt, srcs, x_pyr, poses, k_pyr, logits_pyr, pose_format=_FORMAT[pose_format],
                                        data_weight=FLAGS.data_weight, smooth_weight=FLAGS.smooth_weight,
                                        explain_reg_weight=FLAGS.explain_reg_weight)
-    return out.losses[0], out.losses[1], out.losses[2]
+    terms = tf.stop_gradient(out.losses[:3])
+    return out.losses[3], terms[0], terms[1], terms[2]
 
 
 @_ops.RegisterGradient('VslViewSynthesisLoss')
 def _loss_grad(op, g_losses, *_unused):
-    # the three losses share one set of gradients (those of their sum), scaled by the upstream of the sum
+    # losses = [pixel, smooth, exp, total]; the op's precomputed gradients are those of `total`, so only the upstream
+    # entry of `total` may be non-zero (the wrapper above hands the other three out under stop_gradient)
     S, V = op.get_attr('S'), op.get_attr('V')
-    # the op's gradients are those of pixel + smooth + exp (the sum every train script forms, with the term weights
-    # already inside FLAGS), so the three upstream entries are one and the same scalar
-    g = g_losses[0]
+    g = g_losses[3]
     g_x = [g * t for t in op.outputs[1:1 + S]]
     g_poses = g * op.outputs[1 + S]
     g_lg = [g * t for t in op.outputs[2 + S:2 + 2 * S]]
