@@ -504,58 +504,79 @@ def test_fused_disparity_head_on_load(smooth_inv, depth_inv):
 
 
 # ---------------------------------------------------------------------------------------- full BASELINE sizes vs the oracle
+def _oracle_one(d, b, of, dtype, mode, need_grad):
+    sl = slice(b, b + 1)
+    c = (lambda t: t.double()) if dtype == torch.float64 else (lambda t: t.float())
+    xs = [c(x[sl]).clone().requires_grad_(need_grad) for x in d['disp_pyr']]
+    ps = c(d['poses'][sl]).clone().requires_grad_(need_grad)
+    lg = [c(l[sl]).clone().requires_grad_(need_grad) for l in d['logits_pyr']] if mode == 'exp' else None
+    with torch.set_grad_enabled(need_grad):
+        r = O.view_synthesis_loss(c(d['tgt'][sl]), [c(s[sl]) for s in d['srcs']], xs, ps, c(d['K_pyr'][sl]), lg, None, of)
+    if need_grad:
+        sum(r).backward()
+        return r, ([x.grad for x in xs], ps.grad, [l.grad for l in lg] if lg else None)
+    return r, None
+
+
 def _oracle_per_sample(d, flags_kw, samples, S, V, mode='exp'):
-    """float64 oracle, one sample at a time (the batch mean of per-sample means IS the batch mean: every sample has
-    the same pixel count): -> (losses[3] averaged over ALL samples, {b: (g_x list, g_poses, g_logits list)})."""
+    """One sample at a time (the batch mean of per-sample means IS the batch mean: every sample has the same pixel
+    count): -> (float64 losses[3] averaged over ALL samples, {b: (float64 grads, float32 grads)}), grads = (g_x list,
+    g_poses, g_logits list).  The float32 oracle is the reference's own arithmetic (bit-identical to the goldens
+    produced by executing the reference's source, tests/test_oracle_golden.py); float64 is the mathematical truth."""
     B = d['tgt'].shape[0]
     of = O.LossFlags(**flags_kw)
     tot = torch.zeros(3, dtype=torch.float64)
     grads = {}
     for b in range(B):
-        sl = slice(b, b + 1)
-        need = b in samples
-        xs = [x[sl].double().requires_grad_(need) for x in d['disp_pyr']]
-        ps = d['poses'][sl].double().requires_grad_(need)
-        lg = [l[sl].double().requires_grad_(need) for l in d['logits_pyr']] if mode == 'exp' else None
-        with torch.set_grad_enabled(need):
-            r = O.view_synthesis_loss(d['tgt'][sl].double(), [s[sl].double() for s in d['srcs']], xs, ps,
-                                      d['K_pyr'][sl].double(), lg, None, of)
+        r, g64 = _oracle_one(d, b, of, torch.float64, mode, b in samples)
         tot += torch.stack([t.detach() for t in r])
-        if need:
-            sum(r).backward()
-            grads[b] = ([x.grad for x in xs], ps.grad, [l.grad for l in lg] if lg else None)
+        if b in samples:
+            grads[b] = (g64, _oracle_one(d, b, of, torch.float32, mode, True)[1])
     return tot / B, grads
 
 
-def _full_size_vs_oracle(d, B, H, W, S, V, samples, mode='exp', flags_kw=None):
+def _full_size_vs_oracle(d, B, H, W, S, V, samples, mode='exp', flags_kw=None, exact_too=False):
+    """Losses of the whole batch against the float64 oracle (1e-5).  Gradients of the given samples (1e-4, max-norm):
+    the bar is parity with the REFERENCE, whose arithmetic is float32 -- at 480x640 its own pose gradient is 3e-4
+    away from float64 (coordinates near 640 px carry 4e-5 px of float32 rounding, and a sample within that of an
+    integer coordinate lands in another bilinear cell; profiles/diag_fullsize.py prints the three-way comparison).
+    A gradient therefore passes if it is within 1e-4 of the float32 oracle OR of the float64 one (the fast arithmetic
+    contracts FMAs and may round a coordinate the way float64 does); the exact mode must follow float32 to 1e-5."""
     flags_kw = dict(flags_kw or {}, num_scales=S)
-    flags = ops.LossFlags(**flags_kw)
-    xs = [cu(x, True) for x in d['disp_pyr']]
-    ps = cu(d['poses'], True)
-    lgs = [cu(l, True) for l in d['logits_pyr']] if mode == 'exp' else None
-    total, losses = ops.view_synthesis_loss(cu(d['tgt']), [cu(s) for s in d['srcs']], xs, ps, cu(d['K_pyr']),
-                                            logits_pyr=lgs, flags=flags)
-    total.backward()
     want, grads = _oracle_per_sample(d, flags_kw, samples, S, V, mode)
-    for i, key in enumerate(('pixel', 'smooth', 'exp')):
-        assert abs(float(losses[i]) - float(want[i])) <= 1e-5 * abs(float(want[i])) + 1e-9, (key, float(losses[i]), float(want[i]))
-    assert abs(float(total) - float(want.sum())) <= 1e-5 * float(want.sum())
-    for b, (ogx, ogp, ogl) in grads.items():
-        sl = slice(b, b + 1)
-        one = dict(tgt=d['tgt'][sl], srcs=[s[sl] for s in d['srcs']], disp=[x[sl] for x in d['disp_pyr']],
-                   poses=d['poses'][sl], K=d['K_pyr'][sl])
-        # the kernel's gradients are those of the B-sample mean: 1/B of the single-sample oracle's
-        assert rel_err(ps.grad[sl] * B, ogp) <= 1e-4, ('g_poses', b, rel_err(ps.grad[sl] * B, ogp))
-        ok = smooth_pixels(one['tgt'], one['srcs'], one['disp'], one['poses'], one['K'], flags)
-        for s in range(S):
-            all_views = torch.stack(ok[s]).all(0)
-            assert all_views.float().mean() > 0.97, (b, s, float(all_views.float().mean()))
-            e = masked_rel_err(xs[s].grad[sl] * B, ogx[s], all_views.unsqueeze(3))
-            assert e <= 1e-4, ('g_x', b, s, e)
-            if mode == 'exp':
-                m = torch.stack([o for o in ok[s] for _ in (0, 1)], dim=3)
-                e = masked_rel_err(lgs[s].grad[sl] * B, ogl[s], m)
-                assert e <= 1e-4, ('g_logits', b, s, e)
+    for exact in ((False, True) if exact_too else (False,)):
+        flags = ops.LossFlags(exact_coords=exact, **flags_kw)
+        xs = [cu(x, True) for x in d['disp_pyr']]
+        ps = cu(d['poses'], True)
+        lgs = [cu(l, True) for l in d['logits_pyr']] if mode == 'exp' else None
+        total, losses = ops.view_synthesis_loss(cu(d['tgt']), [cu(s) for s in d['srcs']], xs, ps, cu(d['K_pyr']),
+                                                logits_pyr=lgs, flags=flags)
+        total.backward()
+        for i, key in enumerate(('pixel', 'smooth', 'exp')):
+            assert abs(float(losses[i]) - float(want[i])) <= 1e-5 * abs(float(want[i])) + 1e-9, (key, float(losses[i]), float(want[i]))
+        assert abs(float(total) - float(want.sum())) <= 1e-5 * float(want.sum())
+        for b, ((gx64, gp64, gl64), (gx32, gp32, gl32)) in grads.items():
+            sl = slice(b, b + 1)
+            one = dict(tgt=d['tgt'][sl], srcs=[s[sl] for s in d['srcs']], disp=[x[sl] for x in d['disp_pyr']],
+                       poses=d['poses'][sl], K=d['K_pyr'][sl])
+            # the kernel's gradients are those of the B-sample mean: 1/B of the single-sample oracle's
+            e32, e64 = rel_err(ps.grad[sl] * B, gp32), rel_err(ps.grad[sl] * B, gp64)
+            assert min(e32, e64) <= 1e-4, ('g_poses', exact, b, e32, e64)
+            if exact:
+                assert e32 <= 1e-5, ('g_poses exact vs float32 reference arithmetic', b, e32)
+            ok = smooth_pixels(one['tgt'], one['srcs'], one['disp'], one['poses'], one['K'], flags)
+            for s in range(S):
+                all_views = torch.stack(ok[s]).all(0)
+                assert all_views.float().mean() > 0.97, (b, s, float(all_views.float().mean()))
+                m = all_views.unsqueeze(3)
+                e32 = masked_rel_err(xs[s].grad[sl] * B, gx32[s], m)
+                e64 = masked_rel_err(xs[s].grad[sl] * B, gx64[s], m)
+                assert min(e32, e64) <= 1e-4, ('g_x', exact, b, s, e32, e64)
+                if mode == 'exp':
+                    m = torch.stack([o for o in ok[s] for _ in (0, 1)], dim=3)
+                    e32 = masked_rel_err(lgs[s].grad[sl] * B, gl32[s], m)
+                    e64 = masked_rel_err(lgs[s].grad[sl] * B, gl64[s], m)
+                    assert min(e32, e64) <= 1e-4, ('g_logits', exact, b, s, e32, e64)
 
 
 def test_full_size_cfg2_against_oracle():
@@ -572,7 +593,7 @@ def test_full_size_cfg5_beyond_2_pow_24_against_oracle():
     one lives wholly above 2^24 -- pin the kernel's 32-bit wrapped offset arithmetic against the exact-index oracle."""
     d = synth.make_snippets(64, 480, 640, S=4, V=2, seed=1239)
     assert 63 * 480 * 640 > 2 ** 24
-    _full_size_vs_oracle(d, 64, 480, 640, 4, 2, samples=(0, 31, 63))
+    _full_size_vs_oracle(d, 64, 480, 640, 4, 2, samples=(0, 31, 63), exact_too=True)
 
 
 @pytest.mark.parametrize('direction', ['left_to_right', 'right_to_left'])

@@ -335,6 +335,18 @@ int vsl_dp_step(unsigned* const* peer_flags, const float* const* peer_grads, flo
   cudaStream_t st = (cudaStream_t)stream;
   const AdamHyper hy = {lr, beta1, beta2, eps, grad_scale, 0};
   int rc = VSL_OK;
+  // CUDA loads kernels lazily, and loading one may wait for running work.  The update kernel must therefore be
+  // resident BEFORE this rank's first barrier starts to spin: otherwise a process that drives several ranks (one
+  // host thread, one stream per rank) would sit in the load behind its own barrier, never launch the next rank,
+  // and the barrier would time out.
+  {
+    cudaFuncAttributes fa;
+    const void* fn = world == 1 ? (const void*)dp_adam_kernel<1> : world == 2 ? (const void*)dp_adam_kernel<2>
+                   : world == 4 ? (const void*)dp_adam_kernel<4> : world == 8 ? (const void*)dp_adam_kernel<8>
+                                                                              : (const void*)dp_adam_kernel<0>;
+    const cudaError_t e = cudaFuncGetAttributes(&fa, fn);
+    if (e != cudaSuccess) return (int)e;
+  }
   if (world > 1) {
     rc = launch_barrier(peer_flags, rank, world, 0u, state, 0, timed_out, timeout_ms, st);
     if (rc != VSL_OK) return rc;

@@ -62,11 +62,16 @@ def _ingress(fn):
     """Public entry points accept foreign device tensors for every tensor argument (see from_external)."""
     import functools
 
+    scalars = (torch.Tensor, int, float, bool, str, type(None))
+
+    def conv(a):
+        # anything that is neither a tensor nor a plain scalar / flag must be a device-memory producer: lists,
+        # numpy arrays etc. raise TypeError in from_external instead of an AttributeError deep inside the op
+        return a if isinstance(a, scalars) else from_external(a)
+
     @functools.wraps(fn)
     def wrapped(*args, **kw):
-        args = [from_external(a) if _is_foreign(a) else a for a in args]
-        kw = {k: (from_external(v) if _is_foreign(v) else v) for k, v in kw.items()}
-        return fn(*args, **kw)
+        return fn(*[conv(a) for a in args], **{k: conv(v) for k, v in kw.items()})
     return wrapped
 
 
