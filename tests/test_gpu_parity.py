@@ -607,3 +607,50 @@ def test_full_size_cfg4_both_directions_against_oracle(direction):
     kw = dict(pose_format='angleaxis', smooth_on_inverse=True, depth_is_inverse=True, pixel_scale_norm=False,
               smooth_weight=0.3, data_weight=2.0, explain_reg_weight=0.4)
     _full_size_vs_oracle(d, 64, 192, 256, 4, 1, samples=(0, 40, 63), flags_kw=kw)
+
+
+# ---------------------------------------------------------------------------------------- view-paired kernel
+@pytest.mark.parametrize('V,mode,kw', [
+    (2, 'exp', {}),
+    (2, 'const', dict(smooth_on_inverse=True, depth_is_inverse=False)),
+    (2, 'none', dict(smooth_on_inverse=True, depth_is_inverse=True, pixel_scale_norm=False)),
+    (4, 'exp', dict(pose_format='angleaxis')),
+    (2, 'exp', dict(x_is_logit=True, disp_scaling=4.0, min_disp=0.01)),
+])
+def test_paired_kernel_matches_scalar_fast_path(V, mode, kw):
+    """An even number of views runs loss_fused_pair_kernel (packed fp32x2, folded projection); exact_coords = 2 asks
+    for the scalar fast kernel on the same inputs.  The two differ by rounding only: losses to 2e-6, pose gradients
+    to 2e-5, per-pixel gradients to 2e-5 of the largest one away from the kinks.  Ragged sizes: 44 -> 22 -> 11
+    columns (partial strips), 40 rows (a 32-row band plus a partial one: the last image rows of the smoothness term
+    fall inside a tile)."""
+    B, H, W, S = 3, 40, 44, 3
+    d = synth.make_snippets(B, H, W, S=S, V=V, seed=300 + V, motion=1.5)
+    g = torch.Generator().manual_seed(3)
+    masks = [torch.rand(B, H >> s, W >> s, 1, generator=g) for s in range(S)]
+    raw = [0.8 * torch.randn(B, H >> s, W >> s, 1, generator=g) for s in range(S)] if kw.get('x_is_logit') else d['disp_pyr']
+    res = {}
+    for which in (0, 2):
+        flags = ops.LossFlags(num_scales=S, exact_coords=which, **kw)
+        xs = [cu(x, True) for x in raw]
+        ps = cu(d['poses'], True)
+        lgs = [cu(l, True) for l in d['logits_pyr']] if mode == 'exp' else None
+        total, losses = ops.view_synthesis_loss(cu(d['tgt']), [cu(s) for s in d['srcs']], xs, ps, cu(d['K_pyr']),
+                                                logits_pyr=lgs, mask_pyr=[cu(m) for m in masks] if mode == 'const' else None,
+                                                flags=flags)
+        total.backward()
+        res[which] = (losses.clone(), ps.grad.clone(), [x.grad.clone() for x in xs],
+                      [l.grad.clone() for l in lgs] if lgs else [])
+    a, b = res[0], res[2]
+    assert rel_err(a[0], b[0]) <= 2e-6, (a[0], b[0])
+    assert rel_err(a[1], b[1]) <= 2e-5
+    disp = [4.0 * torch.sigmoid(x) + 0.01 for x in raw] if kw.get('x_is_logit') else raw
+    fl = ops.LossFlags(num_scales=S, **{k: v for k, v in kw.items() if k not in ('x_is_logit', 'disp_scaling', 'min_disp')})
+    ok = smooth_pixels(d['tgt'], d['srcs'], disp, d['poses'], d['K_pyr'], fl)
+    for s in range(S):
+        m = torch.stack(ok[s]).all(0).unsqueeze(3)
+        # the smoothness term has kinks of its own (a second difference within rounding of 0): allow a stencil's worth
+        diff = ((a[2][s] - b[2][s]).abs().cpu() * m) / b[2][s].abs().max().cpu()
+        assert int((diff > 2e-5).sum()) <= 8, (s, int((diff > 2e-5).sum()), float(diff.max()))
+        if mode == 'exp':
+            ml = torch.stack([o for o in ok[s] for _ in (0, 1)], dim=3)
+            assert masked_rel_err(a[3][s], b[3][s], ml) <= 2e-5, s

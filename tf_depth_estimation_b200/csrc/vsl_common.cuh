@@ -100,6 +100,20 @@ VSL_DEV void block_sum_bfly(float (&v)[N], float* scratch, float* out) {
   }
 }
 
+// Sums `n` partials in double in a fixed order; out[0] = result.  One block.
+static __global__ void sum_partials_kernel(const float* __restrict__ partial, int n, float* __restrict__ out) {
+  __shared__ double sh[256];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += (double)partial[i];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = (float)sh[0];
+}
+
 VSL_DEV float sgn(float v) { return (v > 0.f) ? 1.f : ((v < 0.f) ? -1.f : 0.f); }  // tf.abs' gradient
 
 }  // namespace vsl

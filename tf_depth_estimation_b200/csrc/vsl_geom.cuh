@@ -29,6 +29,13 @@ struct Xform {
   float p[12];
 };
 
+// The same transform folded for the view-paired fused kernel: u = depth * (Q [gx, gy, 1]) + t with
+// Q = P[:, :3] . K^-1 (formed in double from the float32 P and K^-1, rounded once) and t = P[:, 3].
+struct XformQ {
+  float q[9];
+  float t[3];
+};
+
 struct Ray { float r0, r1, r2; };     // K^-1 [gx, gy, 1]
 struct Proj { float x, y, z, zp; };   // sampled coords, u2, u2 + eps
 

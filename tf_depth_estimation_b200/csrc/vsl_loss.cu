@@ -34,100 +34,10 @@
 #include <type_traits>
 
 #include "vsl_common.cuh"
-// Part of the single translation unit vsl_lib.cu (prep_one / PrepJob come from vsl_ops.cu).
+#include "vsl_prep.cuh"
+#include "vsl_loss_common.cuh"
 
 namespace vsl {
-
-#ifndef VSL_RH
-#define VSL_RH 32
-#endif
-// 4 independent warps per block, 4 blocks per SM (128 registers x 512 threads fill the register file): measured
-// best of {1x16, 2x8, 4x4, 8x2, 16x1}; block granularity only matters for how evenly the tail drains
-#ifndef VSL_FUSED_WARPS
-#define VSL_FUSED_WARPS 4
-#endif
-#ifndef VSL_FUSED_MIN_BLOCKS
-#define VSL_FUSED_MIN_BLOCKS 4
-#endif
-
-constexpr int kRH = VSL_RH;                     // tile rows per warp
-constexpr int kWarps = VSL_FUSED_WARPS;         // independent warps per block
-constexpr int kThreads = 32 * kWarps;
-constexpr int kHalo = 2;
-constexpr int kQH = kRH + 2 * kHalo;            // rows of x held per tile
-constexpr int kQS = 32 + 2 * kHalo;             // 36 columns of x
-constexpr int kOH = kRH + kHalo;                // owner rows: tile + 2 above
-constexpr int kPad = 2;                         // zero border (pixels) of the RGBA source levels
-constexpr float kMagic = 12582912.0f;           // 1.5 * 2^23
-constexpr unsigned kMagicBits = 0x4B400000u;
-
-struct LossParams {
-  int B, H, W, S, V;
-  int mask_mode, depth_is_inverse, smooth_on_inverse;
-  int x_is_logit;                  // x = pre-activation of the disparity head: disp = disp_scale * sigmoid(x) + disp_min
-  float disp_scale, disp_min;
-  const float* tgt[VSL_MAX_SCALES];                    // RGB
-  const float4* src[VSL_MAX_VIEWS][VSL_MAX_SCALES];    // zero-bordered RGBA [B][Hs+4][Ws+4]
-  float4* gsrc[VSL_MAX_VIEWS][VSL_MAX_SCALES];         // d/d(those levels), same layout (only with DSRC)
-  const float* x[VSL_MAX_SCALES];
-  const float* logits[VSL_MAX_SCALES];
-  const float* mask[VSL_MAX_SCALES];
-  float* g_x[VSL_MAX_SCALES];
-  float* g_logits[VSL_MAX_SCALES];
-  const Xform* xf;                 // [S][V][B]
-  float* partials;                 // [n_items][NT]
-  float cpix[VSL_MAX_SCALES];      // loss_scale * data_weight_s / (B Hs Ws 3)
-  float cexp[VSL_MAX_SCALES];      // loss_scale * explain_reg_weight / (B Hs Ws)
-  // loss_scale * smooth_weight / 2^s / count_k, one flat array per second difference (a per-scale constant the
-  // compiler re-loads inside the row loop should be ONE indexed constant-bank load)
-  float cxx[VSL_MAX_SCALES], cxy[VSL_MAX_SCALES], cyx[VSL_MAX_SCALES], cyy[VSL_MAX_SCALES];
-  int item_begin[VSL_MAX_SCALES + 1];
-  int strips[VSL_MAX_SCALES], bands[VSL_MAX_SCALES];
-  int lg_vec4[VSL_MAX_SCALES];     // logits / g_logits of this scale are 16-byte aligned (and V is even)
-  float wstep[VSL_MAX_SCALES], hstep[VSL_MAX_SCALES];  // meshgrid linspace steps 2/(W-1), 2/(H-1) in fp32
-  // per-scale constants precomputed on the host: under register pressure the compiler re-derives loop invariants
-  // inside the row loop, and re-loading one word from the constant bank is all that should cost
-  int Hs[VSL_MAX_SCALES], Ws[VSL_MAX_SCALES];
-  int stride4[VSL_MAX_SCALES];     // float4 per row of a zero-bordered RGBA level
-  int plane4[VSL_MAX_SCALES];      // float4 per image of it
-  int coff[VSL_MAX_SCALES];        // (kPad * stride4 + kPad) - magic bias * (stride4 + 1), wrapping: see tap_issue
-  float Wf[VSL_MAX_SCALES], Hf[VSL_MAX_SCALES];
-};
-
-template <int V> struct NT { static constexpr int value = 3 + 12 * V; };
-
-// one warp's slice of dynamic shared memory (floats)
-template <int V> struct WarpSmem {
-  static constexpr int qt = 0;                          // [kQH][kQS]  x or 1/x with a 2-pixel halo
-  static constexpr int ha = qt + kQH * kQS;             // [kOH][2]    cxx * sign(dx2) of the 2 columns left of the tile
-  static constexpr int hc = ha + kOH * 2;               // [kOH][2]    cxy*sign(dxdy) + cyx*sign(dydx), same columns
-  static constexpr int xc = hc + kOH * 2;               // [kRH][32]   x itself where the tile holds 1/x
-  static constexpr int total = (xc + kRH * 32 + 3) / 4 * 4;
-  static constexpr size_t block_bytes = sizeof(float) * total * kWarps;
-};
-
-VSL_DEV float signed_by(float c, float v) {  // c * sign(v), sign(0) = 0
-  return (v == 0.f) ? 0.f : copysignf(c, v);
-}
-VSL_DEV float rcp_fast(float a) {
-  float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
-  return r;
-}
-VSL_DEV float ex2_fast(float a) {
-  float r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
-  return r;
-}
-VSL_DEV float lg2_fast(float a) {
-  float r;
-  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
-  return r;
-}
-// sign(e) in {-1, 0, 1} with two FMA-pipe instructions: sat(e * 2^100 + 0.5) is 0, 0.5 or 1
-VSL_DEV float sign_fast(float e) {
-  return fmaf(__saturatef(fmaf(e, 1.2676506e30f, 0.5f)), 2.0f, -1.0f);
-}
 
 // What one (pixel, view) has in flight between issuing its gathers and consuming them.
 struct Tap {
@@ -161,42 +71,13 @@ VSL_DEV void tap_issue(Tap& t, const float (&p)[12], float c0, float c1, float c
   }
   const int off = (int)(__float_as_uint(ty) * (unsigned)stride4 + __float_as_uint(tx) + (unsigned)coff);  // wraps to the true offset
   t.off = off;
+#ifdef VSL_EXP_L1GATHER   // timing experiment (wrong results): every gather hits the same line
+  const float4* __restrict__ g = src + (off & 1);
+#else
   const float4* __restrict__ g = src + off;
+#endif
   t.A = __ldg(g); t.B = __ldg(g + 1);
   t.C = __ldg(g + stride4); t.D = __ldg(g + stride4 + 1);
-}
-
-// The four second differences owned by the element at q (their top-left corner), my_losses.py:27-36:
-// weighted signs for the gradient (a: xx, b: yy, c: xy + yx) and the weighted |.| sum for the loss.
-// gx, gy: image coordinates of the element as unsigned (a difference exists iff its support is inside).
-template <bool EXACT>
-VSL_DEV void owner_signs(const float* q, unsigned gx, unsigned gy, int H, int W, float cxx, float cxy, float cyx,
-                         float cyy, float& a, float& b, float& c, float& sm) {
-  const float q00 = q[0], q01 = q[1], q02 = q[2], q10 = q[kQS], q11 = q[kQS + 1], q20 = q[2 * kQS];
-  const float dx0 = __fsub_rn(q01, q00), dy0 = __fsub_rn(q10, q00);
-  float dxx = __fsub_rn(__fsub_rn(q02, q01), dx0);
-  float dyy = __fsub_rn(__fsub_rn(q20, q10), dy0);
-  float dxy = __fsub_rn(__fsub_rn(q11, q10), dx0);  // d/dy of dx
-  // unsigned compares fold the >= 0 tests; H, W >= 3 is guaranteed by check_desc
-  if (!(gy < (unsigned)H && gx < (unsigned)(W - 2))) dxx = 0.f;
-  if (!(gx < (unsigned)W && gy < (unsigned)(H - 2))) dyy = 0.f;
-  const bool mixed = gx < (unsigned)(W - 1) && gy < (unsigned)(H - 1);
-  if (!mixed) dxy = 0.f;
-  if (EXACT) {
-    float dyx = __fsub_rn(__fsub_rn(q11, q01), dy0);  // d/dx of dy
-    if (!mixed) dyx = 0.f;
-    a = signed_by(cxx, dxx);
-    b = signed_by(cyy, dyy);
-    c = signed_by(cxy, dxy) + signed_by(cyx, dyx);
-    sm = cxx * fabsf(dxx) + cyy * fabsf(dyy) + cxy * fabsf(dxy) + cyx * fabsf(dyx);
-  } else {
-    // d/dy of dx and d/dx of dy are the same number up to rounding: the fast path evaluates it once
-    const float cm = cxy + cyx;
-    a = cxx * sign_fast(dxx);
-    b = cyy * sign_fast(dyy);
-    c = cm * sign_fast(dxy);
-    sm = cxx * fabsf(dxx) + cyy * fabsf(dyy) + cm * fabsf(dxy);
-  }
 }
 
 // EXACT = true : coordinates, softmax and the warped value follow the reference's rounding sequence
@@ -492,7 +373,19 @@ loss_fused_kernel(const LossParams P) {
       if (has_next)
         tap_issue<EXACT>(t, Pm[v], gn.c0, gn.c1, gn.c2, P.src[v][s], stride4, coff, Wf, Hf);
     }
+#ifdef VSL_EXP_NOSTREAM   // timing experiment (wrong results): what do the streamed loads cost?
+    nxt = cur;
+#else
     if (has_next) load_stream(nxt, pofs + W);
+#endif
+#ifdef VSL_EXP_PREFETCH
+    {
+      const float* ta = tgt_img + (pofs + 3 * W) * 3;
+      const float* la = use_lg ? lg_img + (size_t)(pofs + 3 * W) * (2 * V) : ta;
+      asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.s32 p, %2, %3;\n\t@p prefetch.global.L2 [%0];\n\t@p prefetch.global.L2 [%1];\n\t}" ::"l"(ta),
+                   "l"(la), "r"(r + 3), "r"(rows));
+    }
+#endif
 
     // ---- phase 2
     // smoothness: the four differences this element owns, then the gradient = the weighted signs of the 10
@@ -1084,7 +977,7 @@ using namespace vsl;
 namespace {
 
 struct WsLayout {
-  size_t xf, partials, tgt_pyr, src_pyr, gsrc_pyr, total;      // byte offsets (gsrc_pyr only with want_src_grad)
+  size_t xf, xq, partials, tgt_pyr, src_pyr, gsrc_pyr, total;  // byte offsets (gsrc_pyr only with want_src_grad)
   size_t tgt_off[VSL_MAX_SCALES];                    // floats, level s of the target pyramid (s >= 1)
   size_t src_off[VSL_MAX_SCALES];                    // float4, level s inside one view's RGBA block
   size_t src_view;                                   // float4 per view
@@ -1103,7 +996,8 @@ int check_desc(const VslLossDesc* d) {
   VSL_REQUIRE((long long)d->B * (d->H + 4) * (d->W + 4) * 2 * (d->V > 2 ? d->V : 2) < (1ll << 31), VSL_E_SHAPE);  // float offsets
   VSL_REQUIRE(d->pose_format >= VSL_POSE_EULER && d->pose_format <= VSL_POSE_MATRIX, VSL_E_FORMAT);
   VSL_REQUIRE(d->mask_mode >= VSL_MASK_NONE && d->mask_mode <= VSL_MASK_CONST, VSL_E_FORMAT);
-  VSL_REQUIRE(!(d->want_src_grad && d->exact_coords), VSL_E_UNSUPPORTED);
+  VSL_REQUIRE(d->exact_coords >= 0 && d->exact_coords <= 2, VSL_E_FORMAT);
+  VSL_REQUIRE(!(d->want_src_grad && d->exact_coords == 1), VSL_E_UNSUPPORTED);
   VSL_REQUIRE(!d->x_is_logit || d->disp_scale > 0.f, VSL_E_UNSUPPORTED);
   return VSL_OK;
 }
@@ -1127,18 +1021,18 @@ void layout(const VslLossDesc* d, WsLayout* L) {
   L->n_items = n;
   L->src_view = sl;
   L->xf = 0;
-  L->partials = round_up(sizeof(Xform) * (size_t)d->S * d->V * d->B, 256);
+  L->xq = round_up(sizeof(Xform) * (size_t)d->S * d->V * d->B, 256);
+  L->partials = L->xq + round_up(sizeof(XformQ) * (size_t)d->S * d->V * d->B, 256);
   L->tgt_pyr = L->partials + round_up(sizeof(float) * (size_t)n * nt, 256);
   L->src_pyr = L->tgt_pyr + round_up(sizeof(float) * tl, 256);
   L->gsrc_pyr = L->src_pyr + sizeof(float4) * sl * (size_t)d->V;
   L->total = L->gsrc_pyr + (d->want_src_grad ? sizeof(float4) * sl * (size_t)d->V : 0);
 }
 
-template <int V, bool EXACT, bool DSRC>
-int launch_fused(const LossParams& P, cudaStream_t st) {
+template <typename Kern>
+int launch_fused_as(Kern kern, size_t smem_bytes, const LossParams& P, cudaStream_t st) {
   // > 48 KB of dynamic shared memory needs the opt-in; idempotent and cheap, so set on every call (no state)
-  cudaError_t e = cudaFuncSetAttribute(loss_fused_kernel<V, EXACT, DSRC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)WarpSmem<V>::block_bytes);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
   if (e != cudaSuccess) return (int)e;
   const int n = P.item_begin[P.S];
   // programmatic dependent launch: blocks may be scheduled while the prep launch drains; the kernel itself
@@ -1146,16 +1040,30 @@ int launch_fused(const LossParams& P, cudaStream_t st) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((n + kWarps - 1) / kWarps);
   cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = WarpSmem<V>::block_bytes;
+  cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  e = cudaLaunchKernelEx(&cfg, loss_fused_kernel<V, EXACT, DSRC>, P);
+  e = cudaLaunchKernelEx(&cfg, kern, P);
   if (e != cudaSuccess) return (int)e;
   return VSL_OK;
+}
+
+template <int V, bool EXACT, bool DSRC>
+int launch_fused(const LossParams& P, cudaStream_t st) {
+  return launch_fused_as(loss_fused_kernel<V, EXACT, DSRC>, WarpSmem<V>::block_bytes, P, st);
+}
+// fast arithmetic: an even number of views runs the view-paired kernel (packed fp32x2), unless the caller asks for
+// the scalar one (exact_coords == 2: kept selectable so that the two can be compared on the same inputs)
+template <int V>
+int launch_fused_fast(const LossParams& P, int scalar_only, cudaStream_t st) {
+  if constexpr (V % 2 == 0) {
+    if (!scalar_only) return launch_fused_pair(V, P, st);
+  }
+  return launch_fused<V, false, false>(P, st);
 }
 
 template <int V>
@@ -1163,8 +1071,13 @@ int run_loss(const VslLossDesc* d, LossParams& P, const float* poses, const floa
              float* g_poses, cudaStream_t st) {
   if (d->ev_main_begin != nullptr) cudaEventRecord((cudaEvent_t)d->ev_main_begin, st);
   // d/d(source) rides on the fast arithmetic only (check_desc refuses exact_coords + want_src_grad)
+#ifdef VSL_DEV_V2_ONLY
+  const int rc = launch_fused_fast<V>(P, d->exact_coords == 2, st);
+#else
   const int rc = d->want_src_grad ? launch_fused<V, false, true>(P, st)
-                                  : (d->exact_coords ? launch_fused<V, true, false>(P, st) : launch_fused<V, false, false>(P, st));
+                                  : (d->exact_coords == 1 ? launch_fused<V, true, false>(P, st)
+                                                          : launch_fused_fast<V>(P, d->exact_coords == 2, st));
+#endif
   if (rc != VSL_OK) return rc;
   if (d->ev_main_end != nullptr) cudaEventRecord((cudaEvent_t)d->ev_main_end, st);
   {
@@ -1244,6 +1157,7 @@ int vsl_loss_fwd_bwd(const VslLossDesc* d, const float* tgt, const float* const*
   P.mask_mode = d->mask_mode; P.depth_is_inverse = d->depth_is_inverse; P.smooth_on_inverse = d->smooth_on_inverse;
   P.x_is_logit = d->x_is_logit; P.disp_scale = d->disp_scale; P.disp_min = d->disp_min;
   P.xf = xf;
+  P.xq = reinterpret_cast<const XformQ*>(base + L.xq);
   P.partials = reinterpret_cast<float*>(base + L.partials);
   for (int s = 0; s <= d->S; ++s) P.item_begin[s] = L.item_begin[s];
   for (int v = 0; v < d->V; ++v) VSL_REQUIRE(srcs[v], VSL_E_NULL);
@@ -1299,7 +1213,8 @@ int vsl_loss_fwd_bwd(const VslLossDesc* d, const float* tgt, const float* const*
     if (e != cudaSuccess) return (int)e;
   }
   // 1. pyramids, RGBA source levels, transforms
-  const PrepJob prep = make_prep(poses, K_pyr, d->B, d->S, d->V, d->pose_format, xf, nullptr);
+  PrepJob prep = make_prep(poses, K_pyr, d->B, d->S, d->V, d->pose_format, xf, nullptr);
+  prep.xq = reinterpret_cast<XformQ*>(base + L.xq);
   PrepImgJob job;
   job.tgt = tgt;
   job.V = d->V; job.B = d->B; job.H = d->H; job.W = d->W; job.S = d->S;
@@ -1334,12 +1249,16 @@ int vsl_loss_fwd_bwd(const VslLossDesc* d, const float* tgt, const float* const*
   rc = launch_prep(job, prep, st);
   if (rc != VSL_OK) return rc;
   // 2 + 3. fused loss and finalize
+#ifdef VSL_DEV_V2_ONLY   // development builds only (never the shipped library): one instantiation, quick to compile
+  rc = d->V == 2 ? run_loss<2>(d, P, poses, K_pyr, losses, g_poses, st) : VSL_E_UNSUPPORTED;
+#else
   switch (d->V) {
     case 1: rc = run_loss<1>(d, P, poses, K_pyr, losses, g_poses, st); break;
     case 2: rc = run_loss<2>(d, P, poses, K_pyr, losses, g_poses, st); break;
     case 3: rc = run_loss<3>(d, P, poses, K_pyr, losses, g_poses, st); break;
     default: rc = run_loss<4>(d, P, poses, K_pyr, losses, g_poses, st); break;
   }
+#endif
   if (rc != VSL_OK || !d->want_src_grad) return rc;
   // 4. d/d(source image): fold the gradient levels back to [B,H,W,3], all views in one launch
   {

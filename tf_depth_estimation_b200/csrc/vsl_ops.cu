@@ -3,6 +3,7 @@
 #include <algorithm>
 
 #include "vsl_common.cuh"
+#include "vsl_prep.cuh"
 
 namespace vsl {
 
@@ -29,42 +30,9 @@ __global__ void pose_bwd_kernel(const float* __restrict__ vec, const float* __re
   for (int i = 0; i < 6; ++i) g_vec[b * 6 + i] = g[i];
 }
 
-// Per (scale, view, batch) transform table: K_s^-1 and rows 0..2 of K4_s . T_v.
-// xf[(s*V + v)*B + b];  K_pyr is [B,S,3,3];  poses is [B,V,6] or [B,V,4,4].
-struct PrepJob {
-  const float* poses;
-  const float* K_pyr;
-  Xform* xf;
-  float* pose_mat;  // [B,V,4,4], nullable
-  int B, S, V, format, n;
-};
-
-VSL_DEV void prep_one(const PrepJob& j, int idx) {
-  const int b = idx % j.B, v = (idx / j.B) % j.V, s = idx / (j.B * j.V);
-  const int psz = (j.format == VSL_POSE_MATRIX) ? 16 : 6;
-  float T[16], K[9];
-  pose_to_mat(j.poses + (size_t)(b * j.V + v) * psz, j.format, T);
-#pragma unroll
-  for (int i = 0; i < 9; ++i) K[i] = j.K_pyr[(size_t)(b * j.S + s) * 9 + i];
-  Xform o;
-  inv3_lu(K, o.kinv);
-  proj_rows(K, T, o.p);
-  j.xf[idx] = o;
-  if (j.pose_mat != nullptr && s == 0)
-    for (int i = 0; i < 16; ++i) j.pose_mat[(size_t)(b * j.V + v) * 16 + i] = T[i];
-}
-
 __global__ void prep_xforms_kernel(const PrepJob j) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx < j.n) prep_one(j, idx);
-}
-
-static inline PrepJob make_prep(const float* poses, const float* K_pyr, int B, int S, int V, int format, Xform* xf,
-                                float* pose_mat) {
-  PrepJob j;
-  j.poses = poses; j.K_pyr = K_pyr; j.xf = xf; j.pose_mat = pose_mat;
-  j.B = B; j.S = S; j.V = V; j.format = format; j.n = B * S * V;
-  return j;
 }
 
 // =====================================================================================================
@@ -542,20 +510,6 @@ smooth_fwd_kernel(const float* __restrict__ x, SmoothDims d, float* __restrict__
     acc[0] += s;
   }
   block_sum<1>(acc, scratch, partial + blockIdx.x);
-}
-
-// Sums `n` partials in double in a fixed order; out[0] = result.  One block.
-__global__ void sum_partials_kernel(const float* __restrict__ partial, int n, float* __restrict__ out) {
-  __shared__ double sh[256];
-  double s = 0.0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) s += (double)partial[i];
-  sh[threadIdx.x] = s;
-  __syncthreads();
-  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
-    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) out[0] = (float)sh[0];
 }
 
 // Gradient as a gather stencil (deterministic): every element collects the signs of the second
