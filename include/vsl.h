@@ -163,7 +163,9 @@ typedef struct {
   float data_weight, smooth_weight, explain_reg_weight;
   float loss_scale;      /* upstream gradient of the summed loss, folded into every gradient */
   int exact_coords;      /* 1: reference rounding sequence for coordinates / softmax / blend (bit-identical
-                            sample positions to the oracle for matrix poses); 0: FMA + MUFU fast path */
+                            sample positions to the oracle for matrix poses); 0: FMA + MUFU fast path (an even
+                            number of views runs the view-paired packed-fp32x2 kernel); 2: fast path, scalar
+                            kernel for any number of views (A/B comparisons) */
   int want_src_grad;     /* 1: also produce d/d(source images) into g_srcs (atomic scatter: the one output whose
                             summation order is not deterministic); needs exact_coords == 0 */
   int x_is_logit;        /* 1: x_pyr holds the disparity head's PRE-activation output; the kernel applies

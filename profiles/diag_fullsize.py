@@ -93,6 +93,46 @@ def main(name):
                 masked_rel_err(got[False][2][s][sl] * B, gl64[s], ml), masked_rel_err(got[True][2][s][sl] * B, gl64[s], ml)))
 
 
+
+
+def worst_logit_pixels(name='cfg5', b=0, s=0, arith=0):
+    """Where does d/dlogits differ most from the float64 oracle (sample b, scale s), and what does the pixel look like?"""
+    B, H, W, S, V, seed, samples, kw = CFG[name]
+    kw = dict(kw, num_scales=S)
+    d = synth.make_snippets(B, H, W, S=S, V=V, seed=seed)
+    sl = slice(b, b + 1)
+    one = {k: ([t[sl] for t in v] if isinstance(v, list) else v[sl]) for k, v in d.items() if k in ('tgt', 'srcs', 'disp_pyr', 'poses', 'K_pyr', 'logits_pyr')}
+    flags = ops.LossFlags(exact_coords=arith, **kw)
+    lgs = [cu(l, True) for l in one['logits_pyr']]
+    total, _ = ops.view_synthesis_loss(cu(one['tgt']), [cu(t) for t in one['srcs']], [cu(x, True) for x in one['disp_pyr']], cu(one['poses'], True),
+                                       cu(one['K_pyr']), logits_pyr=lgs, flags=flags)
+    total.backward()
+    gx64, gp64, gl64 = oracle_one(d, b, kw, torch.float64)
+    ok = smooth_pixels(one['tgt'], one['srcs'], one['disp_pyr'], one['poses'], one['K_pyr'], ops.LossFlags(**kw))
+    m = torch.stack([o for o in ok[s] for _ in (0, 1)], dim=3)
+    got = lgs[s].grad.cpu().double()
+    diff = ((got - gl64[s]).abs() * m) / gl64[s].abs().max()
+    print('%s b=%d s=%d arith=%d: d/dlogits off by > 1e-4: %d px, > 5e-5: %d px, worst %.2e' % (name, b, s, arith, int((diff > 1e-4).sum()), int((diff > 5e-5).sum()), float(diff.max())))
+    hs, ws = H >> s, W >> s
+    tgt_s = O.resize_area(one['tgt'].double(), hs, ws)
+    for idx in torch.nonzero(diff > 0.8 * diff.max())[:6]:
+        _, y, x, c = [int(i) for i in idx]
+        v = c // 2
+        src_s = O.resize_area(one['srcs'][v].double(), hs, ws)
+        depth = (1.0 / one['disp_pyr'][s].double()).squeeze(3)
+        warped, coords, _, z, _ = O.projective_inverse_warp(src_s, depth, one['poses'][:, v].double(), one['K_pyr'][:, s].double(), 'eular')
+        w32, c32, _, _, _ = O.projective_inverse_warp(src_s.float(), depth.float(), one['poses'][:, v], one['K_pyr'][:, s], 'eular')
+        e = (warped - tgt_s)[0, y, x]
+        print('  (y=%d x=%d ch=%d) got %.6e want %.6e | coords64 (%.5f, %.5f) coords32-64 (%.1e, %.1e) z %.3f | e = %s' % (
+            y, x, c, float(got[0, y, x, c]), float(gl64[s][0, y, x, c]), float(coords[0, y, x, 0]), float(coords[0, y, x, 1]),
+            float(c32[0, y, x, 0]) - float(coords[0, y, x, 0]), float(c32[0, y, x, 1]) - float(coords[0, y, x, 1]), float(z[0, y, x, 0]),
+            ['%.2e' % float(t) for t in e]))
+
+
 if __name__ == '__main__':
-    for n in sys.argv[1:] or ['cfg5', 'cfg4']:
-        main(n)
+    if len(sys.argv) > 1 and sys.argv[1] == 'logits':
+        for arith in (0, 1, 2):
+            worst_logit_pixels('cfg5', 0, 0, arith)
+    else:
+        for n in sys.argv[1:] or ['cfg5', 'cfg4']:
+            main(n)

@@ -39,6 +39,32 @@
 
 namespace vsl {
 
+// switches of the fast arithmetic's shortcuts (timing experiments: -DVSL_T_FOLD=0 ...)
+#ifndef VSL_T_FOLD
+#define VSL_T_FOLD 1
+#endif
+#ifndef VSL_T_SMOOTH
+#define VSL_T_SMOOTH 1
+#endif
+#ifndef VSL_T_LERP
+#define VSL_T_LERP 1
+#endif
+#ifndef VSL_T_LOGPROD
+#define VSL_T_LOGPROD 1
+#endif
+#ifndef VSL_T_INVD
+#define VSL_T_INVD 1
+#endif
+constexpr bool kTFold = VSL_T_FOLD, kTSmooth = VSL_T_SMOOTH, kTLerp = VSL_T_LERP, kTLogProd = VSL_T_LOGPROD, kTInvD = VSL_T_INVD;
+
+// timing experiment (wrong results): VSL_EXP_TIMELINE makes every warp record %globaltimer at the stages of its
+// tile; the stamps replace the tile's partial sums (profiles/run_fused.py reads them back from the workspace)
+#ifdef VSL_EXP_TIMELINE
+#define VSL_STAMP(k) do { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); stamps[k] = t_; } while (0)
+#else
+#define VSL_STAMP(k) do { } while (0)
+#endif
+
 // What one (pixel, view) has in flight between issuing its gathers and consuming them.
 struct Tap {
   float4 A, B, C, D;             // corners (x0,y0) (x1,y0) (x0,y1) (x1,y1)
@@ -48,12 +74,22 @@ struct Tap {
 };
 
 // Projection, footprint and the four 16-byte gathers of one view.  p: the 12 floats of P (warp-uniform).
+// EXACT: u = P [c; 1] in the reference's rounding sequence (c = ray * depth).  Fast: the projection folded per image,
+// u_i = d * (a_i + gy * qy_i) + p[4 i + 3] with Q = P[:, :3] K^-1 (XformQ): a_i = Q[i][0] gx + Q[i][2] is a lane
+// constant (the column is fixed), qy_i = Q[i][1] warp-uniform -- 6 FMAs instead of 3 + 9.
 template <bool EXACT>
-VSL_DEV void tap_issue(Tap& t, const float (&p)[12], float c0, float c1, float c2, const float4* __restrict__ src,
-                       int stride4, int coff, float Wf, float Hf) {
+VSL_DEV void tap_issue(Tap& t, const float (&p)[12], float c0, float c1, float c2, const float (&a)[3],
+                       const float (&qy)[3], float d, float gy, const float4* __restrict__ src, int stride4, int coff,
+                       float Wf, float Hf) {
   if (EXACT) {
     const Proj q = project(p, c0, c1, c2);
     t.qx = q.x; t.qy = q.y; t.rz = 1.0f / q.zp;
+  } else if (kTFold) {
+    const float u0 = fmaf(d, fmaf(gy, qy[0], a[0]), p[3]);
+    const float u1 = fmaf(d, fmaf(gy, qy[1], a[1]), p[7]);
+    const float u2 = fmaf(d, fmaf(gy, qy[2], a[2]), p[11]);
+    t.rz = rcp_fast(u2 + kEpsZ);
+    t.qx = u0 * t.rz; t.qy = u1 * t.rz;
   } else {
     const float u0 = fmaf(p[0], c0, fmaf(p[1], c1, fmaf(p[2], c2, p[3])));
     const float u1 = fmaf(p[4], c0, fmaf(p[5], c1, fmaf(p[6], c2, p[7])));
@@ -93,18 +129,25 @@ __global__ void __launch_bounds__(kThreads, (V <= 2 ? (EXACT ? VSL_FUSED_MIN_BLO
                                                       : VSL_FUSED_MIN_BLOCKS / 2))
 loss_fused_kernel(const LossParams P) {
   constexpr int N = NT<V>::value;
-  using L = WarpSmem<V>;
+  using L = WarpSmem<V, EXACT>;
   extern __shared__ float4 smem4[];
   // the shuffle tells the compiler `warp` (and everything derived from it: tile, scale, sizes, base pointers) is
   // warp-uniform, so those values live in uniform registers instead of 128-per-thread vector registers
   const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int tile = blockIdx.x * kWarps + warp;
   if (tile >= P.item_begin[P.S]) return;   // warps are independent: no block barrier anywhere below
+#ifdef VSL_EXP_TIMELINE
+  unsigned long long stamps[8];
+#endif
+  VSL_STAMP(0);
   float* wsm = reinterpret_cast<float*>(smem4) + warp * L::total;
   float* qt = wsm + L::qt;
   float* sha = wsm + L::ha;
   float* shc = wsm + L::hc;
   float* sxc = wsm + L::xc;
+  // the row table through a per-thread address: a load the compiler believes to be warp-uniform is followed by a
+  // register -> uniform-register move that waits for it; as an ordinary per-lane value the row constants are operands
+  const float* rtv = reinterpret_cast<const float*>(smem4) + (threadIdx.x >> 5) * L::total + L::rt;
 
   // ---- which tile
   int s = 0;
@@ -138,7 +181,15 @@ loss_fused_kernel(const LossParams P) {
       tc += 32;
       if (tc >= kQS) { tc -= kQS; ++ty; }
     }
-    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (!EXACT)   // the tile's row table (fp32 linspace row coordinate of utils.py:153-159, smoothness row weights)
+    {
+      float* rt = wsm + L::rt + 3 * lane;
+      rt[0] = grid_coord(y_base + lane, H, P.hstep[s]);
+      rt[1] = y_base + lane < H - 2 ? P.cyy[s] : 0.f;
+      rt[2] = y_base + lane < H - 1 ? 1.f : 0.f;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();
     if (P.x_is_logit != 0) {          // disparity head on load (nets_optflow_depth.py:143-144); outside stays 0
       int ty = 0, tc = lane;
@@ -155,7 +206,7 @@ loss_fused_kernel(const LossParams P) {
       __syncwarp();
     }
     if (P.smooth_on_inverse != 0) {   // the smoothness term lives on 1/x (train_depth_then_cam_lr.py:217)
-      if (!P.depth_is_inverse) {      // ... while the warp wants x itself: keep the tile's centre rows
+      if (EXACT && !P.depth_is_inverse) {   // ... while the warp wants x itself: keep the tile's centre rows
         for (int r = 0; r < kRH; ++r) sxc[r * 32 + lane] = qt[(r + kHalo) * kQS + lane + kHalo];
       }
       for (int i = lane; i < kQH * kQS; i += 32) {
@@ -167,7 +218,11 @@ loss_fused_kernel(const LossParams P) {
   __syncwarp();
 
   float pix_sum = 0.f, exp_sum = 0.f, sm_sum = 0.f;
+  float se_prod[V];                 // fast arithmetic: running product of the softmax denominators, per view
+#pragma unroll
+  for (int v = 0; v < V; ++v) se_prod[v] = 1.f;
 
+  VSL_STAMP(1);
   // ---- 2. smoothness of the two columns LEFT of the tile: the weighted signs of their xx and xy/yx second
   // differences, which the gradient of columns 0 and 1 needs.  Everything else of the smoothness term is
   // evaluated in the row loop, lane = column: own column in registers, the two to the left by shuffle.
@@ -196,10 +251,16 @@ loss_fused_kernel(const LossParams P) {
   // the magic bias (P.coff removes it, wrapping)
   const int coff = P.coff[s] + b * P.plane4[s];
   const float cpix = P.cpix[s], cexp = P.cexp[s];
+  // fast arithmetic: image-border conditions of the smoothness term are data, not predicates -- a lane's weights are
+  // zero where the second difference its column owns does not exist (the row conditions come from the row table)
+  const float kxx_l = x < W - 2 ? cxx : 0.f;
+  const float kxy_l = x < W - 1 ? cxy + cyx : 0.f;
 
   // Everything above read only the caller's inputs.  The launch is programmatically dependent on the prep launch
   // (it may start while that one drains): wait here, before the first read of what prep wrote.
+  VSL_STAMP(2);
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  VSL_STAMP(3);
 
   // This image's transforms.  Every lane reads the same words; the shuffle marks them warp-uniform, so K^-1 and
   // the V projection matrices sit in uniform registers and enter the FMAs as operands -- no shared memory, no
@@ -219,11 +280,29 @@ loss_fused_kernel(const LossParams P) {
   // K^-1: the column that multiplies gx is folded per thread
   const float3 k0 = make_float3(kinv[0], kinv[1], kinv[2]), k1 = make_float3(kinv[3], kinv[4], kinv[5]),
                k2 = make_float3(kinv[6], kinv[7], kinv[8]);
-  float kx0, kx1, kx2;
+  float kx0 = 0.f, kx1 = 0.f, kx2 = 0.f;
   if (EXACT) {
     kx0 = __fmul_rn(k0.x, gx); kx1 = __fmul_rn(k1.x, gx); kx2 = __fmul_rn(k2.x, gx);
-  } else {
+  } else if (!kTFold) {
     kx0 = fmaf(k0.x, gx, k0.z); kx1 = fmaf(k1.x, gx, k1.z); kx2 = fmaf(k2.x, gx, k2.z);
+  }
+  // fast arithmetic: the folded projection of tap_issue -- per view Q[i][1] (uniform) and Q[i][0] gx + Q[i][2] (lane)
+  float Qy[V][3], Al[V][3];
+#pragma unroll
+  for (int v = 0; v < V; ++v)
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { Qy[v][i] = 0.f; Al[v][i] = 0.f; }
+  if (!EXACT && kTFold) {
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const float* xq = reinterpret_cast<const float*>(P.xq + ((size_t)s * V + v) * P.B + b);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const float q0 = __shfl_sync(0xffffffffu, __ldg(xq + 3 * i), 0), q2 = __shfl_sync(0xffffffffu, __ldg(xq + 3 * i + 2), 0);
+        Qy[v][i] = __shfl_sync(0xffffffffu, __ldg(xq + 3 * i + 1), 0);
+        Al[v][i] = fmaf(q0, gx, q2);
+      }
+    }
   }
 
   float S2[V][3], S3[V][3], S4[V][3];  // sum du*d*gy, du*d, du   (sum du*d*gx = gx * S3: the column is fixed)
@@ -257,7 +336,7 @@ loss_fused_kernel(const LossParams P) {
   const int smooth_inv = P.smooth_on_inverse, depth_inv = P.depth_is_inverse;
 
   struct Stream { float tt[3]; float lg[2 * V]; float mc; };               // streamed operands of one row
-  struct Geo { float d, dgy, r0, r1, r2, c0, c1, c2; };                     // per-pixel geometry of one row
+  struct Geo { float d, gy, dgy, r0, r1, r2, c0, c1, c2; };                 // per-pixel geometry of one row
 
   auto load_stream = [&](Stream& st, int pofs) {
 #pragma unroll
@@ -282,18 +361,24 @@ loss_fused_kernel(const LossParams P) {
   };
   auto make_geo = [&](Geo& g, int r) {
     const float qc = qt[(r + kHalo) * kQS + (xl - x_base) + kHalo];
-    if (smooth_inv) g.d = depth_inv ? qc : sxc[r * 32 + (xl - x_base)];
+    if (smooth_inv) g.d = depth_inv ? qc : (EXACT ? sxc[r * 32 + (xl - x_base)] : rcp_fast(qc));
     else g.d = !depth_inv ? qc : (EXACT ? __fdiv_rn(1.0f, qc) : rcp_fast(qc));
-    const float gy = grid_coord(y_base + r, H, hstep);
     if (EXACT) {  // pixel2cam's matmul (utils.py:114): sequential k, no contraction
+      const float gy = grid_coord(y_base + r, H, hstep);
       g.r0 = __fadd_rn(__fadd_rn(kx0, __fmul_rn(k0.y, gy)), k0.z);
       g.r1 = __fadd_rn(__fadd_rn(kx1, __fmul_rn(k1.y, gy)), k1.z);
       g.r2 = __fadd_rn(__fadd_rn(kx2, __fmul_rn(k2.y, gy)), k2.z);
+      g.c0 = __fmul_rn(g.r0, g.d); g.c1 = __fmul_rn(g.r1, g.d); g.c2 = __fmul_rn(g.r2, g.d);
+      g.dgy = g.d * gy;
+    } else if (kTFold) {   // the ray is folded into the per-view projection (tap_issue); the row coordinate comes from the table
+      g.gy = rtv[3 * r];
+      g.dgy = g.d * g.gy;
     } else {
+      const float gy = grid_coord(y_base + r, H, hstep);
       g.r0 = fmaf(k0.y, gy, kx0); g.r1 = fmaf(k1.y, gy, kx1); g.r2 = fmaf(k2.y, gy, kx2);
+      g.c0 = __fmul_rn(g.r0, g.d); g.c1 = __fmul_rn(g.r1, g.d); g.c2 = __fmul_rn(g.r2, g.d);
+      g.dgy = g.d * gy;
     }
-    g.c0 = __fmul_rn(g.r0, g.d); g.c1 = __fmul_rn(g.r1, g.d); g.c2 = __fmul_rn(g.r2, g.d);
-    g.dgy = g.d * gy;
   };
 
   // One row = two phases.  Phase 1 holds every long-latency wait and issue: blend view v from its landed
@@ -321,9 +406,13 @@ loss_fused_kernel(const LossParams P) {
       const float cA[3] = {t.A.x, t.A.y, t.A.z}, cB[3] = {t.B.x, t.B.y, t.B.z},
                   cC[3] = {t.C.x, t.C.y, t.C.z}, cD[3] = {t.D.x, t.D.y, t.D.z};
       // E = sum_c |e_c|; J_k = sum_c sign(e_c) * corner_k[c]  (the channel sum commutes with d/dx, d/dy)
-      const float wx0 = EXACT ? t.wx0 : 1.0f - t.wx1, wy0 = EXACT ? t.wy0 : 1.0f - t.wy1;
-      const float w00 = __fmul_rn(wx0, wy0), w01 = __fmul_rn(wx0, t.wy1),
-                  w10 = __fmul_rn(t.wx1, wy0), w11 = __fmul_rn(t.wx1, t.wy1);
+      // EXACT: the reference's four products.  Fast: one product, w11 = wx1 wy1, then w10 = wx1 - w11,
+      // w01 = wy1 - w11, w00 = (1 - wx1) - w01
+      constexpr bool kProd = EXACT || !kTLerp;
+      const float wx0 = EXACT ? t.wx0 : 1.0f - t.wx1, wy0 = EXACT ? t.wy0 : (kProd ? 1.0f - t.wy1 : 0.f);
+      const float w11 = __fmul_rn(t.wx1, t.wy1);
+      const float w10 = kProd ? __fmul_rn(t.wx1, wy0) : t.wx1 - w11, w01 = kProd ? __fmul_rn(wx0, t.wy1) : t.wy1 - w11;
+      const float w00 = kProd ? __fmul_rn(wx0, wy0) : wx0 - w01;
       float E = __uint_as_float(pad), JA = 0.f, JB = 0.f, JC = 0.f, JD = 0.f;
       float sgc[3] = {0.f, 0.f, 0.f};
 #pragma unroll
@@ -365,13 +454,21 @@ loss_fused_kernel(const LossParams P) {
                        "f"(k11 * sgc[1]), "f"(k11 * sgc[2]), "f"(0.f) : "memory");
         }
       }
-      const float dx = wy0 * (JB - JA) + t.wy1 * (JD - JC);
-      const float dy = wx0 * (JC - JA) + t.wx1 * (JD - JB);
+      // d/dx = wy0 (JB - JA) + wy1 (JD - JC), d/dy = wx0 (JC - JA) + wx1 (JD - JB); the fast path in lerp form
+      float dx, dy;
+      if (kProd) {
+        dx = wy0 * (JB - JA) + t.wy1 * (JD - JC);
+        dy = wx0 * (JC - JA) + t.wx1 * (JD - JB);
+      } else {
+        const float ax = JB - JA, ay = JC - JA;
+        dx = fmaf(t.wy1, (JD - JC) - ax, ax);
+        dy = fmaf(t.wx1, (JD - JB) - ay, ay);
+      }
       // the border zeros make the sampler's corner masks implicit: an outside corner contributes 0
       keep[v].E = E; keep[v].u0 = dx * t.rz; keep[v].u1 = dy * t.rz;
       keep[v].u2 = -(t.qx * keep[v].u0 + t.qy * keep[v].u1);
       if (has_next)
-        tap_issue<EXACT>(t, Pm[v], gn.c0, gn.c1, gn.c2, P.src[v][s], stride4, coff, Wf, Hf);
+        tap_issue<EXACT>(t, Pm[v], gn.c0, gn.c1, gn.c2, Al[v], Qy[v], gn.d, gn.gy, P.src[v][s], stride4, coff, Wf, Hf);
     }
 #ifdef VSL_EXP_NOSTREAM   // timing experiment (wrong results): what do the streamed loads cost?
     nxt = cur;
@@ -392,10 +489,23 @@ loss_fused_kernel(const LossParams P) {
     // stencils it is part of (own column from registers, the two columns to the left by shuffle)
     float g_q;
     {
-      float a0, b0, c00, sm;
-      owner_signs<EXACT>(qt + (r + kHalo) * kQS + lane + kHalo, (unsigned)x, (unsigned)(y_base + r), H, W, cxx, cxy, cyx,
-                         cyy, a0, b0, c00, sm);
-      sm_sum += sm;
+      float a0, b0, c00;
+      if (EXACT || !kTSmooth) {
+        float sm;
+        owner_signs<EXACT>(qt + (r + kHalo) * kQS + lane + kHalo, (unsigned)x, (unsigned)(y_base + r), H, W, cxx, cxy, cyx,
+                           cyy, a0, b0, c00, sm);
+        sm_sum += sm;
+      } else {
+        // the same differences with the border conditions as weights (lane: kxx_l, kxy_l; row: table entries y, z):
+        // no compares, no selects; lanes past the image edge are dropped from the sum at the end
+        const float* q = qt + (r + kHalo) * kQS + lane + kHalo;
+        const float q00 = q[0], q01 = q[1], q02 = q[2], q10 = q[kQS], q11 = q[kQS + 1], q20 = q[2 * kQS];
+        const float dx0 = q01 - q00, dy0 = q10 - q00;
+        const float dxx = (q02 - q01) - dx0, dyy = (q20 - q10) - dy0, dxy = (q11 - q10) - dx0;
+        const float kyy_r = rtv[3 * r + 1], kxy_r = kxy_l * rtv[3 * r + 2];
+        a0 = kxx_l * sign_fast(dxx); b0 = kyy_r * sign_fast(dyy); c00 = kxy_r * sign_fast(dxy);
+        sm_sum = fmaf(kxx_l, fabsf(dxx), fmaf(kyy_r, fabsf(dyy), fmaf(kxy_r, fabsf(dxy), sm_sum)));
+      }
       float a1 = __shfl_up_sync(0xffffffffu, a0, 1), a2 = __shfl_up_sync(0xffffffffu, a0, 2);
       float c01 = __shfl_up_sync(0xffffffffu, c00, 1);
       {  // lanes 0 and 1 take what lies left of the tile from the halo columns: broadcast loads + selects, no branch
@@ -427,7 +537,14 @@ loss_fused_kernel(const LossParams P) {
           const float e = ex2_fast(-1.4426950408889634f * fabsf(z)), se = 1.f + e, big = rcp_fast(se), small = e * big;
           p0 = z >= 0.f ? big : small;
           p1 = z >= 0.f ? small : big;
-          exp_sum += fmaf(lg2_fast(se), 0.6931471805599453f, fmaxf(z, 0.f));
+          // log(1 + e^-|z|) + max(z, 0); the logarithms of a tile are taken once, of the product of its 1 + e^-|z|
+          // (at most 2^kRH per view: no overflow; 1e-7 relative on the sum)
+          if (kTLogProd) {
+            se_prod[v] *= se;
+            exp_sum += fmaxf(z, 0.f);
+          } else {
+            exp_sum += fmaf(lg2_fast(se), 0.6931471805599453f, fmaxf(z, 0.f));
+          }
         }
         mv[v] = p1;
         const float g0 = p0 * (cexp - cpix * keep[v].E * p1);
@@ -457,7 +574,11 @@ loss_fused_kernel(const LossParams P) {
       S3[v][0] = fmaf(du0, gc.d, S3[v][0]);   S3[v][1] = fmaf(du1, gc.d, S3[v][1]);   S3[v][2] = fmaf(du2, gc.d, S3[v][2]);
       S4[v][0] += du0;                        S4[v][1] += du1;                        S4[v][2] += du2;
     }
-    if (!EXACT) g_d *= rcp_fast(gc.d);
+    if (!EXACT) {
+      // d = 1 / x (and the tile holds x): 1 / d is the tile value itself, no reciprocal
+      const float inv_d = (kTInvD && depth_inv && !smooth_inv) ? qt[(r + kHalo) * kQS + (xl - x_base) + kHalo] : rcp_fast(gc.d);
+      g_d *= inv_d;
+    }
     if (act) {
       // chain rules of depth = x or 1/x and of the smoothed quantity q = x or 1/x
       float dd_dx = 1.f, dq_dx = 1.f;
@@ -497,21 +618,33 @@ loss_fused_kernel(const LossParams P) {
   {
     Stream st0, st1;                            // ping-pong: no register copies between rows
     Geo g0, g1;
+    VSL_STAMP(4);
     load_stream(st0, pofs);
     make_geo(g0, 0);
 #pragma unroll
     for (int v = 0; v < V; ++v)
-      tap_issue<EXACT>(tap[v], Pm[v], g0.c0, g0.c1, g0.c2, P.src[v][s], stride4, coff, Wf, Hf);
-    for (int r = 0; r < rows; r += 2) {
+      tap_issue<EXACT>(tap[v], Pm[v], g0.c0, g0.c1, g0.c2, Al[v], Qy[v], g0.d, g0.gy, P.src[v][s], stride4, coff, Wf, Hf);
+    VSL_STAMP(5);
+#ifdef VSL_EXP_ROWS   // timing experiment (wrong results): only the first VSL_EXP_ROWS rows of every tile
+    const int rows_run = min(rows, VSL_EXP_ROWS);
+#else
+    const int rows_run = rows;
+#endif
+    for (int r = 0; r < rows_run; r += 2) {
       row(st0, st1, g0, g1, r);
       if (r + 1 < rows) row(st1, st0, g1, g0, r + 1);
     }
   }
 
+  VSL_STAMP(6);
   // ---- 4. one warp reduction per tile: 3 loss sums + per view (gx sum du d, sum du d gy, sum du d, sum du)
   float vals[N];
+  if (!EXACT && kTLogProd) {
+#pragma unroll
+    for (int v = 0; v < V; ++v) exp_sum = fmaf(lg2_fast(se_prod[v]), 0.6931471805599453f, exp_sum);
+  }
   vals[0] = pix_sum * cpix; vals[1] = sm_sum; vals[2] = exp_sum * cexp;
-  if (!act) { vals[0] = 0.f; vals[2] = 0.f; }   // lanes past the image edge recomputed the last column
+  if (!act) { vals[0] = 0.f; vals[1] = 0.f; vals[2] = 0.f; }   // lanes past the image edge recomputed the last column
 #pragma unroll
   for (int v = 0; v < V; ++v)
 #pragma unroll
@@ -534,6 +667,20 @@ loss_fused_kernel(const LossParams P) {
     const int idx = bfly_index<N>(lane, j);
     if (idx >= 0) out[idx] = vals[j];
   }
+#ifdef VSL_EXP_TIMELINE
+  VSL_STAMP(7);
+  __syncwarp();
+  if (lane == 0) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    for (int k = 0; k < 8; ++k) {
+      out[2 * k] = __uint_as_float((unsigned)(stamps[k] & 0xffffffffull));
+      out[2 * k + 1] = __uint_as_float((unsigned)(stamps[k] >> 32));
+    }
+    out[16] = __uint_as_float(smid);
+    out[17] = __uint_as_float((unsigned)s);
+  }
+#endif
 }
 
 // grid = B + 1 blocks of kFinThreads.  Block b < B: pose gradients of batch element b (all views).  The tile partials
@@ -1054,10 +1201,11 @@ int launch_fused_as(Kern kern, size_t smem_bytes, const LossParams& P, cudaStrea
 
 template <int V, bool EXACT, bool DSRC>
 int launch_fused(const LossParams& P, cudaStream_t st) {
-  return launch_fused_as(loss_fused_kernel<V, EXACT, DSRC>, WarpSmem<V>::block_bytes, P, st);
+  return launch_fused_as(loss_fused_kernel<V, EXACT, DSRC>, WarpSmem<V, EXACT>::block_bytes, P, st);
 }
-// fast arithmetic: an even number of views runs the view-paired kernel (packed fp32x2), unless the caller asks for
-// the scalar one (exact_coords == 2: kept selectable so that the two can be compared on the same inputs)
+// fast arithmetic: an even number of views runs the view-paired kernel (packed fp32x2, vsl_loss_pair.cu: 23 % fewer
+// instructions, same time at 128x416, 2 % faster at 480x640); exact_coords == 2 asks for the scalar kernel instead,
+// so that the two can be compared on the same inputs
 template <int V>
 int launch_fused_fast(const LossParams& P, int scalar_only, cudaStream_t st) {
   if constexpr (V % 2 == 0) {

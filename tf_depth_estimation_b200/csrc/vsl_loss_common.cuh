@@ -63,14 +63,25 @@ struct LossParams {
 
 template <int V> struct NT { static constexpr int value = 3 + 12 * V; };
 
-// one warp's slice of dynamic shared memory (floats)
-template <int V> struct WarpSmem {
+// One warp's slice of dynamic shared memory (floats).  What the unified L1 does not give to shared memory is the
+// cache the gathers run in, and the carve-out moves in steps (..., 100, 132, 164, 196 KB): the fast-arithmetic
+// kernels keep 4 blocks x (4 warps x total x 4 B + 1 KB) just inside the 100 KB step (156 KB of L1; at 164 KB the
+// kernel is 1.5 us slower, at 196 KB 4 us slower).
+template <int V, bool EXACT> struct WarpSmem {
   static constexpr int qt = 0;                          // [kQH][kQS]  x or 1/x with a 2-pixel halo
   static constexpr int ha = qt + kQH * kQS;             // [kOH][2]    cxx * sign(dx2) of the 2 columns left of the tile
   static constexpr int hc = ha + kOH * 2;               // [kOH][2]    cxy*sign(dxdy) + cyx*sign(dydx), same columns
-  static constexpr int xc = hc + kOH * 2;               // [kRH][32]   x itself where the tile holds 1/x
-  static constexpr int total = (xc + kRH * 32 + 3) / 4 * 4;
+  // [kRH][3] per tile row (fast arithmetic): grid row coordinate; weight of the yy second difference (0 in the last
+  // two image rows, where it does not exist); 1 / 0 = the mixed difference exists / does not (last image row)
+  static constexpr int rt = hc + kOH * 2;
+  // [kRH][32] x itself where the tile holds 1/x (smoothness on 1/x, warp on x): the exact mode only -- the fast
+  // arithmetic takes the reciprocal of the tile value again (2 ulp)
+  static constexpr int xc = rt + (EXACT ? 0 : 3 * kRH);
+  static constexpr int total = (xc + (EXACT ? kRH * 32 : 0) + 3) / 4 * 4;
   static constexpr size_t block_bytes = sizeof(float) * total * kWarps;
+  static_assert(EXACT || VSL_FUSED_WARPS != 4 || VSL_FUSED_MIN_BLOCKS != 4 || VSL_RH != 32 ||
+                    (sizeof(float) * total * 4 + 1024) * 4 <= 100 * 1024,
+                "shared memory of the fast fused kernels crosses the 100 KB carve-out");
 };
 
 VSL_DEV float signed_by(float c, float v) {  // c * sign(v), sign(0) = 0

@@ -65,12 +65,10 @@ struct TapPair {
 
 constexpr int kPF = 3;   // rows ahead of their load that the streamed operands are prefetched into L2
 
-template <int V> struct PairSmem {
-  // [kRH][4] per tile row: grid coordinate, weight of the yy difference (0 in the last two image rows), 1 / 0 =
-  // the mixed difference exists / does not (last image row), unused
-  static constexpr int gy = WarpSmem<V>::total;
-  static constexpr int total = (gy + 4 * kRH + 3) / 4 * 4;
-  static constexpr size_t block_bytes = sizeof(float) * total * kWarps;
+template <int V> struct PairSmem {   // the general kernel's layout: the row table is WarpSmem<V, false>::rt
+  static constexpr int gy = WarpSmem<V, false>::rt;
+  static constexpr int total = WarpSmem<V, false>::total;
+  static constexpr size_t block_bytes = WarpSmem<V, false>::block_bytes;
 };
 
 template <int V>
@@ -78,7 +76,7 @@ __global__ void __launch_bounds__(kThreads, (V <= 2 ? VSL_FUSED_MIN_BLOCKS : VSL
 loss_fused_pair_kernel(const LossParams P) {
   static_assert(V % 2 == 0, "views are processed in pairs");
   constexpr int NP = V / 2, N = NT<V>::value;
-  using L = WarpSmem<V>;
+  using L = WarpSmem<V, false>;
   extern __shared__ float4 smem4[];
   const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int tile = blockIdx.x * kWarps + warp;
@@ -87,7 +85,6 @@ loss_fused_pair_kernel(const LossParams P) {
   float* qt = wsm + L::qt;
   float* sha = wsm + L::ha;
   float* shc = wsm + L::hc;
-  float* sxc = wsm + L::xc;
   float* gyt = wsm + PairSmem<V>::gy;
   // the same table through a per-thread address: a load the compiler believes to be warp-uniform is followed by a
   // register -> uniform-register move that waits for it; as an ordinary per-lane value the row constants just feed
@@ -126,9 +123,9 @@ loss_fused_pair_kernel(const LossParams P) {
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     // the grid row coordinates of the tile (fp32 linspace formula of utils.py:153-159), one per lane
-    reinterpret_cast<float4*>(gyt)[lane] = make_float4(grid_coord(y_base + lane, H, P.hstep[s]),
-                                                       y_base + lane < H - 2 ? P.cyy[s] : 0.f,
-                                                       y_base + lane < H - 1 ? 1.f : 0.f, 0.f);
+    gyt[3 * lane] = grid_coord(y_base + lane, H, P.hstep[s]);
+    gyt[3 * lane + 1] = y_base + lane < H - 2 ? P.cyy[s] : 0.f;
+    gyt[3 * lane + 2] = y_base + lane < H - 1 ? 1.f : 0.f;
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();
     if (P.x_is_logit != 0) {
@@ -146,9 +143,6 @@ loss_fused_pair_kernel(const LossParams P) {
       __syncwarp();
     }
     if (P.smooth_on_inverse != 0) {
-      if (!P.depth_is_inverse) {
-        for (int r = 0; r < kRH; ++r) sxc[r * 32 + lane] = qt[(r + kHalo) * kQS + lane + kHalo];
-      }
       for (int i = lane; i < kQH * kQS; i += 32) {
         const float v = qt[i];
         qt[i] = v != 0.f ? __fdiv_rn(1.0f, v) : 0.f;
@@ -265,9 +259,9 @@ loss_fused_pair_kernel(const LossParams P) {
   };
   auto make_geo = [&](Geo& g, int r) {
     const float qc = qt[(r + kHalo) * kQS + (xl - x_base) + kHalo];
-    if (smooth_inv) g.d = depth_inv ? qc : sxc[r * 32 + (xl - x_base)];
+    if (smooth_inv) g.d = depth_inv ? qc : rcp_fast(qc);   // the tile holds 1/x, the warp wants x
     else g.d = !depth_inv ? qc : rcp_fast(qc);
-    g.gy = gyv[4 * r];
+    g.gy = gyv[3 * r];
     g.dgy = g.d * g.gy;
   };
 
@@ -385,8 +379,7 @@ loss_fused_pair_kernel(const LossParams P) {
       const float dx0 = q01 - q00, dy0 = q10 - q00;
       const float dxx = (q02 - q01) - dx0, dyy = (q20 - q10) - dy0, dxy = (q11 - q10) - dx0;
       // row conditions come as weights from the row table: yy needs y < H-2, the mixed difference y < H-1
-      const float4 rt = reinterpret_cast<const float4*>(gyv)[r];
-      const float kyy_r = rt.y, kxy_r = kxy_l * rt.z;
+      const float kyy_r = gyv[3 * r + 1], kxy_r = kxy_l * gyv[3 * r + 2];
       const float a0 = kxx_l * sign_fast(dxx), b0 = kyy_r * sign_fast(dyy), c00 = kxy_r * sign_fast(dxy);
       sm_sum = fmaf(kxx_l, fabsf(dxx), fmaf(kyy_r, fabsf(dyy), fmaf(kxy_r, fabsf(dxy), sm_sum)));
       a1 = __shfl_up_sync(0xffffffffu, a0, 1); a2 = __shfl_up_sync(0xffffffffu, a0, 2);
