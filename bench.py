@@ -1,27 +1,35 @@
 #!/usr/bin/env python
 """bench.py -- view-synthesis loss forward+backward throughput on B200 (BASELINE.json metric).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfg2|cfg3|cfg4|cfg5]
 
 A *step* is one pass of the hot path over one batch of synthetic frame snippets: K_s^-1 / P tables, the
 resize_area pyramids of target + source images, and the fused multi-scale loss forward+backward (3 launches).
-Workload at every N: BASELINE.json configs[1] per GPU -- B=32, 128x416, 4 scales, 2 source views, fp32,
-explainability mask on (weak scaling: the path shards over the batch, no data-path collective).
+Default workload (the BENCH / SCALE line): BASELINE.json configs[1] per GPU -- B=32, 128x416, 4 scales, 2 source
+views, fp32, explainability mask on (weak scaling: the path shards over the batch, no data-path collective).
+--config selects the other BASELINE shapes: cfg3 (global batch 256 split over the ranks, strong scaling), cfg4
+(DeMoN pairs 192x256, B=64, one view per direction, angle-axis poses), cfg5 (480x640, B=64, the HBM-stress shape).
 
 Unit: Mpix/s, where one "pix" is one PIXEL-VIEW (one target pixel x one scale x one source view;
-SURVEY.md 8d): a step processes B*H*W*1.328125*V of them.
+SURVEY.md 8d): a step processes B*H*W*(sum_s 4^-s)*V of them.
 
 JSON keys beyond the base contract:
   roofline      the fused loss kernel, timed in situ with CUDA events recorded by the library immediately
-                around its launch in every timed step; achieved = algorithmic bytes / mean duration, against
+                around its launch in every 4th timed step; achieved = algorithmic bytes / mean duration, against
                 MEASURED_PEAKS.json hbm_gbs (fallback 6650 GB/s, B200_PROFILING.md).
   cpu_baseline  the CPU oracle (op-for-op torch-CPU restatement of the reference, autograd backward) on this
                 box's host cores, on a bounded sample of the same workload.
-  e2e           the same step through the public API with HOST buffers (ops.HostPipeline): pinned H2D of every
-                input, the step, D2H of the losses and every gradient, all inside the timed region; copies and
-                kernels of neighbouring steps overlap (3 streams, 2 buffer sets).
+  e2e           the same step through the public API with HOST buffers (ops.HostPipeline): the frames as the
+                reference's loader holds them (uint8, converted on load exactly as imageselect_Dataloader.py:93 does),
+                network outputs as float32; pinned H2D of every input, the step, D2H of the losses and every gradient,
+                all inside the timed region; copies and kernels of neighbouring steps overlap (3 streams, 2 slots).
+  train         (default config only) BASELINE's second metric, end-to-end training samples/s at N GPUs:
+                configs[2] (DispNet + PoseExpNet, global batch 256 split over the ranks) with this repository's
+                fused loss and its fused reduce-scatter + Adam + all-gather optimiser step over NVLink peer memory
+                (profiles/train_samples.py; the networks are torch/cuDNN, outside the hot path).
 """
 import argparse
+import importlib.util
 import json
 import os
 import statistics
@@ -35,19 +43,35 @@ sys.path.insert(0, ROOT)
 
 METRIC = 'view-synthesis loss fwd+bwd throughput (pixel-views/s)'
 UNIT = 'Mpix/s'
-WORKLOAD = dict(B=32, H=128, W=416, S=4, V=2)
-PYR = sum(0.25 ** s for s in range(WORKLOAD['S']))  # 1.328125
+DEMON = dict(pose_format='angleaxis', smooth_on_inverse=True, depth_is_inverse=True, pixel_scale_norm=False)
+CONFIGS = {
+    'cfg2': dict(B=32, H=128, W=416, S=4, V=2, flags={}, sets=6, cpu_B=8, scaling='weak',
+                 text='cfg2: view-synthesis loss fwd+bwd (pyramids + fused multi-scale loss), per GPU B=32 128x416 4 '
+                      'scales 2 source views, explainability mask, euler poses'),
+    'cfg3': dict(B=256, H=128, W=416, S=4, V=2, flags={}, sets=3, cpu_B=8, scaling='strong',
+                 text='cfg3: the loss step of train.py at global batch 256 (split over the ranks), 128x416 4 scales 2 '
+                      'source views, explainability mask, euler poses'),
+    'cfg4': dict(B=64, H=192, W=256, S=4, V=1, flags=DEMON, sets=4, cpu_B=8, scaling='weak',
+                 text='cfg4: DeMoN pairs 192x256, per GPU B=64, one source view per direction, angle-axis poses, '
+                      'smoothness on 1/depth, explainability mask'),
+    'cfg5': dict(B=64, H=480, W=640, S=4, V=2, flags={}, sets=2, cpu_B=1, scaling='weak',
+                 text='cfg5: 480x640 multi-scale refinement shape, per GPU B=64, 4 scales 2 source views, '
+                      'explainability mask (HBM stress: 2.9 GB workspace)'),
+}
 
 
-def pixel_views(B):
-    return B * WORKLOAD['H'] * WORKLOAD['W'] * PYR * WORKLOAD['V']
+def pyr(S):
+    return sum(0.25 ** s for s in range(S))
 
 
-def fused_kernel_bytes(B):
-    """Algorithmic (compulsory) HBM bytes of ONE launch of loss_fused_kernel ('bytes'): per target
+def pixel_views(c, B):
+    return B * c['H'] * c['W'] * pyr(c['S']) * c['V']
+
+
+def fused_kernel_bytes(c, B):
+    """Algorithmic (compulsory) HBM bytes of ONE launch of the fused loss kernel: per target
     pixel read x 4 + target 12, write g_x 4; per view read gathered source 12 + logits 8, write g_logits 8."""
-    V = WORKLOAD['V']
-    return B * WORKLOAD['H'] * WORKLOAD['W'] * PYR * (20 + 28 * V)
+    return B * c['H'] * c['W'] * pyr(c['S']) * (20 + 28 * c['V'])
 
 
 def measured_peak():
@@ -58,12 +82,12 @@ def measured_peak():
         return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
-def recorded_traffic():
-    """dram bytes per launch of the fused kernel from the committed ncu --set full capture, if any."""
+def recorded_traffic(name):
+    """dram bytes per launch of the fused kernel from the committed ncu --set full capture of this config, if any."""
     try:
         with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as fh:
             t = json.load(fh)
-        return t.get('loss_fused_kernel_cfg2_dram_bytes_per_launch')
+        return t.get('loss_fused_kernel_%s_dram_bytes_per_launch' % name)
     except Exception:
         return None
 
@@ -116,12 +140,12 @@ class ClockSampler(object):
 
 
 # ------------------------------------------------------------------------------------------ CPU legs
-def oracle_step_fn(B, seed=4321):
+def oracle_step_fn(c, B, seed=4321):
     import torch
     from oracle import vsl_oracle as O
     from tf_depth_estimation_b200 import synth
-    d = synth.make_snippets(B, WORKLOAD['H'], WORKLOAD['W'], S=WORKLOAD['S'], V=WORKLOAD['V'], seed=seed)
-    flags = O.LossFlags()
+    d = synth.make_snippets(B, c['H'], c['W'], S=c['S'], V=c['V'], seed=seed)
+    flags = O.LossFlags(num_scales=c['S'], **c['flags'])
 
     def step():
         xs = [x.clone().requires_grad_() for x in d['disp_pyr']]
@@ -133,13 +157,14 @@ def oracle_step_fn(B, seed=4321):
     return step
 
 
-def cpu_baseline(B_sample, reps, budget_s=25.0):
-    """Times the CPU oracle (kind 'port': TF is not installable) on B_sample snippets of the
-    workload with every host core."""
+def cpu_baseline(c, reps, budget_s=25.0):
+    """Times the CPU oracle (kind 'port': TF is not installable) on cpu_B snippets of the workload
+    with every host core."""
     import torch
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    step = oracle_step_fn(B_sample)
+    Bs = c['cpu_B']
+    step = oracle_step_fn(c, Bs)
     step()
     times, t_begin = [], time.time()
     for _ in range(reps):
@@ -149,43 +174,60 @@ def cpu_baseline(B_sample, reps, budget_s=25.0):
         if time.time() - t_begin > budget_s:
             break
     dt = statistics.median(times)
-    return {'value': pixel_views(B_sample) / dt / 1e6, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-            'sample': 'B=%d of the %d snippets per step (128x416, 4 scales, 2 views, fwd+autograd bwd), median of %d '
-                      'runs, %.3f s each' % (B_sample, WORKLOAD['B'], len(times), dt)}
+    return {'value': pixel_views(c, Bs) / dt / 1e6, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+            'sample': 'B=%d snippets of the step (%dx%d, %d scales, %d views, fwd+autograd bwd), median of %d '
+                      'runs, %.3f s each' % (Bs, c['H'], c['W'], c['S'], c['V'], len(times), dt)}
 
 
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path.  TensorFlow 1.x cannot run here, so
     this is the oracle port (an op-for-op restatement validated against the reference's own source, see
-    oracle/); each step is a bounded sample (B=8 of the 32 snippets)."""
+    oracle/); each step is a bounded sample (cpu_B snippets of the batch)."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     import torch
+    c = CONFIGS[args.config]
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    Bs = 8
-    step = oracle_step_fn(Bs)
+    Bs = c['cpu_B']
+    step = oracle_step_fn(c, Bs)
     for _ in range(args.warmup):
         step()
     t0 = time.time()
     for _ in range(args.steps):
         step()
     dt = (time.time() - t0) / args.steps
-    val = pixel_views(Bs) / dt / 1e6
+    val = pixel_views(c, Bs) / dt / 1e6
     args.out.emit(json.dumps({
         'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
-        'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+        'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': c['scaling'],
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': dict(workload='cfg2: view-synthesis loss fwd+bwd, B=32 128x416 4 scales 2 views, exp mask '
-                                '(each reference step = B=8 sample of it)', **WORKLOAD),
+        'config': dict(workload=c['text'] + ' (each reference step = B=%d sample of it)' % Bs,
+                       B=c['B'], H=c['H'], W=c['W'], S=c['S'], V=c['V']),
         'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                         'sample': 'B=8 of 32 snippets per step, torch-CPU oracle, all host threads'},
+                         'sample': 'B=%d snippets per step, torch-CPU oracle, all host threads' % Bs},
         'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0}))
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
+def train_leg(rank, world, dev):
+    """BASELINE's second metric through profiles/train_samples.py; never lets a failure take the bench line down."""
+    try:
+        spec = importlib.util.spec_from_file_location('train_samples', os.path.join(ROOT, 'profiles', 'train_samples.py'))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        r = mod.measure(rank, world, dev, global_batch=256, steps=6, warmup=3, optim='peer', graph=1, timeout_s=30.0)
+        return {'samples_per_s': r['value'], 'ms_per_step': r['ms_per_step'], 'optim_us': r['optim_us'], 'loss_us': r['loss_us'],
+                'global_batch': r['global_batch'], 'per_gpu_batch': r['per_gpu_batch'], 'scaling': 'strong',
+                'optimiser': 'fused reduce-scatter + Adam + all-gather over NVLink peer memory (dp_adam_kernel)',
+                'cuda_graph': r['cuda_graph'], 'params': r['params'], 'losses_finite': r['losses_finite'],
+                'workload': 'configs[2]: DispNet + PoseExpNet (torch/cuDNN fp32, TF32 allowed), explainability mask, 128x416'}
+    except Exception as e:   # noqa: BLE001
+        return {'error': '%s: %s' % (type(e).__name__, e)}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -202,15 +244,25 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     _lib.load()
+    to_u8 = lambda t: (t * 255.0).round().clamp(0, 255).to(dtype=torch.uint8)   # what a decoded frame is
 
-    B, H, W, S, V = (WORKLOAD[k] for k in 'BHWSV')
-    flags = ops.LossFlags()
-    # weak scaling: every rank holds B snippets of a global batch of B * world
-    plan = ops.ViewSynthesisPlan(B, H, W, V, flags, _lib.MASK_EXP, dev, loss_scale=vdist.local_loss_scale(B, B * world))
+    c = CONFIGS[args.config]
+    H, W, S, V = (c[k] for k in 'HWSV')
+    if c['scaling'] == 'strong':            # a fixed global batch, split over the ranks
+        lo, hi = vdist.shard_range(c['B'], rank, world)
+        B, B_global = hi - lo, c['B']
+    else:                                    # every rank holds B snippets of a global batch of B * world
+        B, B_global = c['B'], c['B'] * world
+    flags = ops.LossFlags(num_scales=S, **c['flags'])
+    scale = vdist.local_loss_scale(B, B_global)
+    plan = ops.ViewSynthesisPlan(B, H, W, V, flags, _lib.MASK_EXP, dev, loss_scale=scale)
 
     # rotating input sets so that consecutive steps never find their inputs in the 126 MB L2
-    NSETS = 6
-    host = synth.make_snippets(B, H, W, S=S, V=V, seed=1234 + rank)
+    NSETS = c['sets']
+    host = synth.make_snippets(min(B, 32), H, W, S=S, V=V, seed=1234 + rank)
+    if B > 32:
+        host = {k: ([t.repeat(B // 32, *([1] * (t.dim() - 1))) for t in v] if isinstance(v, list) else
+                    (v.repeat(B // 32, *([1] * (v.dim() - 1))) if hasattr(v, 'repeat') else v)) for k, v in host.items()}
 
     def to_dev(d, roll):
         r = lambda t: torch.roll(t, roll, dims=0).to(dev).contiguous()
@@ -260,26 +312,43 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
-    losses = vdist.reduce_losses(plan.losses, B, B * world).cpu().tolist()  # 12-byte all-reduce, outside the timed region
+    losses = vdist.reduce_losses(plan.losses, B, B_global).cpu().tolist()  # 12-byte all-reduce, outside the timed region
+
+    # ---- the same device-resident step fed with the loader's uint8 frames (converted on load)
+    flags8 = ops.LossFlags(num_scales=S, img_format='u8_255', **c['flags'])
+    plan8 = ops.ViewSynthesisPlan(B, H, W, V, flags8, _lib.MASK_EXP, dev, loss_scale=scale)
+    sets8 = [dict(s, tgt=to_u8(s['tgt']), srcs=[to_u8(x) for x in s['srcs']]) for s in sets]
+    bound8 = [plan8.bind(s['tgt'], s['srcs'], s['xs'], s['poses'], s['Kp'], s['lgs']) for s in sets8]
+    for i in range(Wm):
+        plan8.run_bound(bound8[i % NSETS], stream)
+    barrier()
+    u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    u0.record()
+    for i in range(K):
+        plan8.run_bound(bound8[(Wm + i) % NSETS], stream)
+    u1.record()
+    barrier()
+    t8 = torch.tensor([u0.elapsed_time(u1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t8, op=dist.ReduceOp.MAX)
+    ms8 = float(t8.item())
+    del sets8, bound8, plan8
 
     # ---- e2e: host buffers in, host results out, through the public API (ops.HostPipeline): every step copies
     # all its inputs from pinned host memory and all its losses + gradients back; H2D / kernels / D2H of
-    # neighbouring steps overlap on three streams
-    pipe = ops.HostPipeline(B, H, W, V, flags, _lib.MASK_EXP, dev, loss_scale=vdist.local_loss_scale(B, B * world))
+    # neighbouring steps overlap on three streams.  Frames travel as the loader's uint8.
+    pipe = ops.HostPipeline(B, H, W, V, flags8, _lib.MASK_EXP, dev, loss_scale=scale)
     h_in = pipe.host_inputs()          # pinned host tensors carved from one arena: a step's inputs move as ONE copy
-    if os.environ.get('VSL_E2E_SEPARATE'):   # experiment switch: one pinned tensor and one copy per input
-        h_in = dict(tgt=host['tgt'].pin_memory(), srcs=[t.pin_memory() for t in host['srcs']],
-                    xs=[t.pin_memory() for t in host['disp_pyr']], poses=host['poses'].pin_memory(),
-                    Kp=host['K_pyr'].pin_memory(), lgs=[t.pin_memory() for t in host['logits_pyr']])
-    if h_in.get('_arena') is not None:
-        h_in['tgt'].copy_(host['tgt']); h_in['poses'].copy_(host['poses']); h_in['Kp'].copy_(host['K_pyr'])
-        for dst, src in zip(h_in['srcs'] + h_in['xs'] + h_in['lgs'], host['srcs'] + host['disp_pyr'] + host['logits_pyr']):
-            dst.copy_(src)
+    h_in['tgt'].copy_(to_u8(host['tgt'])); h_in['poses'].copy_(host['poses']); h_in['Kp'].copy_(host['K_pyr'])
+    for dst, src in zip(h_in['srcs'], host['srcs']):
+        dst.copy_(to_u8(src))
+    for dst, src in zip(h_in['xs'] + h_in['lgs'], host['disp_pyr'] + host['logits_pyr']):
+        dst.copy_(src)
     h2d, d2h = pipe.bytes_per_step()
     Ke = max(6, min(K, 150))
     for _ in range(4):
         slot = pipe.submit(h_in)
-    e2e_losses = pipe.result(slot)[0].tolist()
+    pipe.result(slot)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(pipe.s_in)
@@ -294,34 +363,47 @@ def run_ours(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_ms = float(te.item()) / Ke
     clocks = sampler.stop(t_wall0, t_wall1)
+    del pipe, h_in, sets, bound
+    torch.cuda.empty_cache()
+
+    train = None
+    if args.config == 'cfg2' and not args.no_train:
+        train = train_leg(rank, world, dev)
 
     if rank == 0:
         peak, peak_src = measured_peak()
         kmean = statistics.mean(kern_ms)
-        achieved = fused_kernel_bytes(B) / (kmean * 1e-3) / 1e9
+        algo = fused_kernel_bytes(c, B)
+        achieved = algo / (kmean * 1e-3) / 1e9
+        total_pv = pixel_views(c, B_global if c['scaling'] == 'strong' else B) * (1 if c['scaling'] == 'strong' else world)
+        kname = 'loss_fused_pair_kernel<%d>' % V if V % 2 == 0 else 'loss_fused_kernel<%d, false, false>' % V
         out = {
-            'metric': METRIC, 'value': pixel_views(B) * world * K / (ms_max * 1e-3) / 1e6, 'unit': UNIT,
+            'metric': METRIC, 'value': total_pv * K / (ms_max * 1e-3) / 1e6, 'unit': UNIT,
             'n_gpus': world, 'steps': K, 'warmup': Wm, 'ms_per_step': ms_max / K, 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': dict(workload='cfg2: view-synthesis loss fwd+bwd (pyramids + fused multi-scale loss), per GPU '
-                                    'B=32 128x416 4 scales 2 source views, explainability mask, euler poses',
+            'scaling': c['scaling'], 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': dict(workload=c['text'], name=args.config,
                            l2='%d rotating input sets of %.0f MB each (> 126 MB L2 between reuses)' % (NSETS, set_bytes / 1e6),
-                           pix='1 pix = 1 pixel-view = target pixel x scale x view; %.0f per step per GPU' % pixel_views(B),
-                           parallelism='dp%d (batch shards, no data-path collective)' % world, **WORKLOAD),
-            'roofline': {'bound': 'hbm', 'kernel': 'loss_fused_kernel<2>', 'achieved': achieved, 'peak': peak,
-                         'unit': 'GB/s', 'frac': achieved / peak, 'traffic': recorded_traffic(),
-                         'algorithmic_bytes_per_launch': fused_kernel_bytes(B), 'kernel_ms_mean': kmean,
+                           pix='1 pix = 1 pixel-view = target pixel x scale x view; %.0f per step per GPU' % pixel_views(c, B),
+                           parallelism='dp%d (batch shards, no data-path collective)' % world,
+                           B=B, H=H, W=W, S=S, V=V),
+            'roofline': {'bound': 'hbm', 'kernel': kname, 'achieved': achieved, 'peak': peak,
+                         'unit': 'GB/s', 'frac': achieved / peak, 'traffic': recorded_traffic(args.config),
+                         'algorithmic_bytes_per_launch': algo, 'kernel_ms_mean': kmean,
                          'kernel_ms_min': min(kern_ms), 'kernel_share_of_step': kmean / (ms_max / K), 'kernel_timed_steps': len(kern_ms),
                          'peak_source': peak_src},
-            'e2e': {'value': pixel_views(B) * world / (e2e_ms * 1e-3) / 1e6, 'unit': UNIT, 'ms_per_step': e2e_ms,
+            'value_u8_frames': {'value': total_pv * K / (ms8 * 1e-3) / 1e6, 'unit': UNIT, 'ms_per_step': ms8 / K,
+                                'how': 'the same device-resident step with the frames as uint8 (converted on load, results bit-identical)'},
+            'e2e': {'value': total_pv / (e2e_ms * 1e-3) / 1e6, 'unit': UNIT, 'ms_per_step': e2e_ms,
                     'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'steps': Ke,
-                    'how': 'ops.HostPipeline: pinned host inputs -> H2D (one copy) -> 3 launches -> D2H of losses and all '
-                           'gradients (one copy), double-buffered over 3 streams'},
+                    'how': 'ops.HostPipeline: pinned host inputs (frames uint8 as the loader holds them, network outputs float32) '
+                           '-> H2D (one copy) -> 3 launches -> D2H of losses and all gradients (one copy), double-buffered over 3 streams'},
             'gpu_launches': 3 * K, 'launches_per_step': 3, 'clocks': clocks,
             'losses': {'pixel': losses[0], 'smooth': losses[1], 'exp': losses[2]},
         }
+        if train is not None:
+            out['train'] = train
         if world == 1 and not args.no_cpu_baseline:
-            out['cpu_baseline'] = cpu_baseline(B_sample=8, reps=12)
+            out['cpu_baseline'] = cpu_baseline(c, reps=12)
         args.out.emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -349,7 +431,9 @@ def main():
     ap.add_argument('--steps', type=int, default=600)
     ap.add_argument('--warmup', type=int, default=20)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--config', default='cfg2', choices=sorted(CONFIGS))
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-train', action='store_true')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     args.out = _QuietStdout()

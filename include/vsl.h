@@ -43,6 +43,7 @@ enum {
 };
 
 enum { VSL_MASK_NONE = 0, VSL_MASK_EXP = 1, VSL_MASK_CONST = 2 };
+enum { VSL_IMG_F32 = 0, VSL_IMG_U8_255 = 1, VSL_IMG_U8_255_CENTRED = 2, VSL_IMG_U8_RAW = 3 };
 
 #define VSL_MAX_SCALES 6
 #define VSL_MAX_VIEWS 4
@@ -172,7 +173,11 @@ typedef struct {
                             disp = disp_scale * sigmoid(x) + disp_min (nets_optflow_depth.py:8-9,143-144) on load and
                             its derivative on store, so the head's elementwise ops and their backward disappear */
   float disp_scale, disp_min;
-  int reserved_;
+  int img_format;        /* VSL_IMG_*: what tgt / srcs hold.  F32: float32 (vsl_loss_fwd_bwd).  U8_*: the loader's uint8
+                            (vsl_loss_fwd_bwd_u8), converted on load exactly as the reference's loaders do:
+                            U8_255 (float)u8 / 255.0 (imageselect_Dataloader.py:86-93), U8_255_CENTRED ... - 0.5
+                            (imageselect_Dataloader_optflow_dim11.py:128), U8_RAW the value itself
+                            (imageselect_Dataloader_optflow.py:129) */
   void* ev_main_begin;   /* optional cudaEvent_t pair recorded on `stream` immediately around the fused  */
   void* ev_main_end;     /* loss kernel (launch 3 of the step) so a caller can time it in situ; NULL = off */
 } VslLossDesc;
@@ -188,6 +193,16 @@ int vsl_loss_fwd_bwd(const VslLossDesc* d,
                      float* g_poses /*same shape as poses*/, float* const* g_logits_pyr /*S, MASK_EXP*/,
                      float* const* g_srcs /*host array V x [B,H,W,3]; NULL unless want_src_grad*/,
                      void* ws, vsl_stream_t stream);
+/* The same step fed with the images as the reference's input pipeline holds them before its conversion to float
+ * (uint8 [B,H,W,3], imageselect_Dataloader.py:86-93): a quarter of the bytes to move and to read, results
+ * bit-identical to vsl_loss_fwd_bwd on the converted images.  d->img_format selects the conversion (VSL_IMG_U8_*);
+ * no gradient w.r.t. the images. */
+int vsl_loss_fwd_bwd_u8(const VslLossDesc* d,
+                        const unsigned char* tgt /*[B,H,W,3]*/, const unsigned char* const* srcs /*host array V*/,
+                        const float* const* x_pyr, const float* poses, const float* K_pyr,
+                        const float* const* logits_pyr, const float* const* mask_pyr,
+                        float* losses, float* const* g_x_pyr, float* g_poses, float* const* g_logits_pyr,
+                        void* ws, vsl_stream_t stream);
 
 /* ---- upstream gradient of the summed loss: dst[0..n) = src[0..n) * (*num / *den) (num, den: device floats; den
  *      NULL means 1).  What TF autodiff does with the incoming gradient of `total_loss` in the reference

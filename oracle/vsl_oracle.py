@@ -290,6 +290,19 @@ def get_reference_explain_mask(downscaling, batch, height, width, dtype=torch.fl
     return m
 
 
+def images_from_uint8(u8, img_format='u8_255'):
+    """The loaders' conversion of decoded uint8 frames to the float32 images the graph sees:
+    'u8_255'          tf.to_float(image) / 255.0          imageselect_Dataloader.py:86-93
+    'u8_255_centred'  image_seq / 255.0 - 0.5             imageselect_Dataloader_optflow_dim11.py:128
+    'u8_raw'          tf.to_float only (normalisation commented out)   imageselect_Dataloader_optflow.py:129
+    float32 IEEE division and subtraction, as TF's RealDiv / Sub kernels."""
+    x = u8.to(torch.float32)
+    if img_format == 'u8_raw':
+        return x
+    x = x / torch.tensor(255.0, dtype=torch.float32)
+    return x - torch.tensor(0.5, dtype=torch.float32) if img_format == 'u8_255_centred' else x
+
+
 def resize_area(x, oh, ow):
     """tf.image.resize_area for integer shrink factors (e.g. train_depth_then_cam_lr.py:227-232).
 

@@ -102,30 +102,20 @@ class PoseExpNet(nn.Module):    # nets.py:16-84
         return pose, [self.m1(u1), self.m2(u2), self.m3(u3), self.m4(u4)]
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument('--global-batch', type=int, default=256)
-    ap.add_argument('--steps', type=int, default=10)
-    ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--optim', default='peer', choices=['peer', 'nccl'])
-    ap.add_argument('--graph', type=int, default=1, help='replay networks + loss (forward and backward) as one CUDA graph')
-    a = ap.parse_args()
-    rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
-    local = int(os.environ.get('LOCAL_RANK', 0))
-    torch.cuda.set_device(local)
-    dev = torch.device('cuda', local)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
+def measure(rank, world, dev, global_batch=256, steps=10, warmup=3, optim='peer', graph=1, timeout_s=120.0):
+    """One measurement on an initialised process group (or a single process) -> dict (identical on every rank except
+    that only rank 0's is meant to be printed).  The caller owns the process group."""
     H, W, S, V = 128, 416, 4, 2
-    lo, hi = vdist.shard_range(a.global_batch, rank, world)
+    lo, hi = vdist.shard_range(global_batch, rank, world)
     B = hi - lo
     torch.manual_seed(0)        # identical initial weights on every rank
     disp_net, pose_net = DispNet().to(dev).to(memory_format=torch.channels_last), \
         PoseExpNet(V).to(dev).to(memory_format=torch.channels_last)
     params = [p for p in list(disp_net.parameters()) + list(pose_net.parameters())]
-    Opt = vdist.PeerDataParallelAdam if a.optim == 'peer' else vdist.DataParallelAdam
-    kw = {} if a.optim == 'peer' else {'bucket_bytes': 1 << 30}
-    dp = Opt([p.shape for p in params], dev, lr=2e-4, beta1=0.9, **kw)
+    if optim == 'peer':
+        dp = vdist.PeerDataParallelAdam([p.shape for p in params], dev, lr=2e-4, beta1=0.9, timeout_s=timeout_s)
+    else:
+        dp = vdist.DataParallelAdam([p.shape for p in params], dev, lr=2e-4, beta1=0.9, bucket_bytes=1 << 30)
     for p, pv, gv in zip(params, dp.params, dp.grads):
         pv.copy_(p.data)
         p.data = pv             # the networks compute on / into the flat arenas: no copies around the optimiser
@@ -136,14 +126,20 @@ def main():
     flags = ops.LossFlags(num_scales=S, x_is_logit=True, disp_scaling=10.0, min_disp=0.01)
     nchw = lambda t: t.permute(0, 3, 1, 2)      # NHWC storage seen as NCHW / channels_last: no copy
     nhwc = lambda t: t.permute(0, 2, 3, 1).contiguous()
-    scale = vdist.local_loss_scale(B, a.global_batch)
+    scale = vdist.local_loss_scale(B, global_batch)
+    loss_ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
 
-    def fwd_bwd():
+    def fwd_bwd(time_loss=False):
         dp.grad_flat.zero_()
         x_pyr = [nhwc(x) for x in disp_net(nchw(tgt))]
         pose, masks = pose_net(nchw(torch.cat([tgt] + srcs, dim=3)))
-        total, losses = ops.view_synthesis_loss(tgt, srcs, x_pyr, pose.contiguous(), K_pyr,
-                                                logits_pyr=[nhwc(m) for m in masks], flags=flags, loss_scale=scale)
+        lg = [nhwc(m) for m in masks]
+        pose = pose.contiguous()
+        if time_loss:
+            loss_ev[0].record()
+        total, losses = ops.view_synthesis_loss(tgt, srcs, x_pyr, pose, K_pyr, logits_pyr=lg, flags=flags, loss_scale=scale)
+        if time_loss:
+            loss_ev[1].record()
         total.backward()        # the rank's B_local / B_global share is folded into the kernel's gradients
         return losses
 
@@ -152,12 +148,24 @@ def main():
         dp.step()
         return losses
 
-    for _ in range(a.warmup):
+    for _ in range(warmup):
         losses = step()
+    # this repository's share of the step, timed on their own (eager, before any graph capture)
+    fwd_bwd(time_loss=True)
+    oe = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    oe[0].record()
+    for _ in range(5):
+        dp.step()
+    oe[1].record()
+    torch.cuda.synchronize()
+    loss_us, optim_us = loss_ev[0].elapsed_time(loss_ev[1]) * 1e3, oe[0].elapsed_time(oe[1]) * 1e3 / 5
     graphed = False
-    if a.graph:
+    if graph:
         # networks + loss, forward and backward, as ONE CUDA graph (the step is launch-bound at 32 samples per GPU);
-        # the optimiser step stays outside: its barrier epochs are host-side arguments
+        # the optimiser step is launched right behind every replay (its epoch / step count live on the device)
         try:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
@@ -186,24 +194,44 @@ def main():
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(a.steps):
+    for _ in range(steps):
         losses = step()
     e1.record()
     torch.cuda.synchronize()
-    t = torch.tensor([e0.elapsed_time(e1) / a.steps], device=dev)
+    t = torch.tensor([e0.elapsed_time(e1) / steps, optim_us, loss_us], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if hasattr(dp, 'check_peers'):
         dp.check_peers()
     ok = bool(torch.isfinite(losses).all())
-    if rank == 0:
-        print(json.dumps({'metric': 'train samples/s (DispNet + PoseExpNet torch/cuDNN fp32-TF32, fused loss, %s optimiser step)' % a.optim,
-                          'value': a.global_batch / (float(t) * 1e-3), 'unit': 'samples/s', 'n_gpus': world,
-                          'global_batch': a.global_batch, 'per_gpu_batch': B, 'ms_per_step': float(t), 'steps': a.steps,
-                          'params': int(sum(p.numel() for p in params)), 'scaling': 'strong', 'cuda_graph': graphed, 'losses_finite': ok,
-                          'losses': [float(v) for v in losses]}))
+    out = {'metric': 'train samples/s (DispNet + PoseExpNet torch/cuDNN fp32-TF32, fused loss, %s optimiser step)' % optim,
+           'value': global_batch / (float(t[0]) * 1e-3), 'unit': 'samples/s', 'n_gpus': world,
+           'global_batch': global_batch, 'per_gpu_batch': B, 'ms_per_step': float(t[0]), 'steps': steps,
+           'optim_us': float(t[1]), 'loss_us': float(t[2]), 'optimiser': optim,
+           'params': int(sum(p.numel() for p in params)), 'scaling': 'strong', 'cuda_graph': graphed, 'losses_finite': ok,
+           'losses': [float(v) for v in losses]}
     if hasattr(dp, 'close'):
         dp.close()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--global-batch', type=int, default=256)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--optim', default='peer', choices=['peer', 'nccl'])
+    ap.add_argument('--graph', type=int, default=1, help='replay networks + loss (forward and backward) as one CUDA graph')
+    a = ap.parse_args()
+    rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    out = measure(rank, world, dev, a.global_batch, a.steps, a.warmup, a.optim, a.graph)
+    if rank == 0:
+        print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 

@@ -180,3 +180,69 @@ def test_fused_loss_launches_no_eager_torch_kernels():
     bad = [n for n in kernels if 'at::native' in n or 'elementwise' in n]
     # autograd materialises the upstream gradient of `total` (one fill of a single float) -- nothing else may be eager
     assert all('fill' in n.lower() or 'FillFunctor' in n for n in bad), bad
+
+
+# ---------------------------------------------------------------------------------------- uint8 images
+@pytest.mark.parametrize('B,H,W,S,V,fmt', [
+    (2, 32, 64, 3, 2, 'u8_255'),            # rows of 64 x 3 bytes: the 16-byte staged path
+    (2, 24, 36, 3, 1, 'u8_255_centred'),    # W % 16 != 0: byte loads; one view (scalar kernel)
+    (1, 40, 44, 3, 2, 'u8_raw'),            # ragged tiles, raw [0, 255] values
+    (4, 128, 416, 4, 2, 'u8_255'),          # BASELINE frame size
+])
+def test_uint8_images_bit_identical_to_converted_float32(B, H, W, S, V, fmt):
+    """vsl_loss_fwd_bwd_u8 (the loader's uint8 frames, converted on load) == vsl_loss_fwd_bwd on the images the
+    reference's loader would have produced from them (imageselect_Dataloader.py:93 and siblings, restated in
+    oracle.images_from_uint8): losses and every gradient bit for bit."""
+    from oracle import vsl_oracle as O
+    d = synth.make_snippets(B, H, W, S=S, V=V, seed=17)
+    g = torch.Generator().manual_seed(9)
+    u8 = [torch.randint(0, 256, (B, H, W, 3), generator=g, dtype=torch.uint8) for _ in range(V + 1)]
+    f32 = [O.images_from_uint8(t, fmt) for t in u8]
+    scale = 1.0 / 255.0 if fmt == 'u8_raw' else 1.0          # keep the raw-valued loss in a sane range
+    res = []
+    for imgs, kind in ((f32, 'f32'), (u8, fmt)):
+        flags = ops.LossFlags(num_scales=S, img_format=kind, data_weight=scale)
+        xs = [cu(x).requires_grad_() for x in d['disp_pyr']]
+        ps = cu(d['poses']).requires_grad_()
+        lgs = [cu(l).requires_grad_() for l in d['logits_pyr']]
+        dev_imgs = [t.to(DEV) for t in imgs]
+        total, losses = ops.view_synthesis_loss(dev_imgs[0], dev_imgs[1:], xs, ps, cu(d['K_pyr']), logits_pyr=lgs, flags=flags)
+        total.backward()
+        res.append([losses.clone(), ps.grad.clone()] + [x.grad.clone() for x in xs] + [l.grad.clone() for l in lgs])
+    assert float(res[0][0].abs().sum()) > 0
+    for a, b in zip(*res):
+        assert torch.equal(a, b)
+    # dtype / format mismatches are refused before anything reaches the library
+    with pytest.raises(TypeError):
+        ops.view_synthesis_loss(u8[0].to(DEV), [t.to(DEV) for t in u8[1:]], xs, ps, cu(d['K_pyr']), logits_pyr=lgs,
+                                flags=ops.LossFlags(num_scales=S))
+    with pytest.raises(TypeError):
+        ops.view_synthesis_loss(f32[0].to(DEV), [t.to(DEV) for t in f32[1:]], xs, ps, cu(d['K_pyr']), logits_pyr=lgs,
+                                flags=ops.LossFlags(num_scales=S, img_format=fmt))
+
+
+def test_host_pipeline_uint8_frames():
+    """HostPipeline fed with uint8 frames (a quarter of the image bytes over PCIe) returns what the float32 pipeline
+    returns for the converted images."""
+    from oracle import vsl_oracle as O
+    from tf_depth_estimation_b200 import _lib
+    B, H, W, S, V = 2, 32, 64, 3, 2
+    d = synth.make_snippets(B, H, W, S=S, V=V, seed=23)
+    g = torch.Generator().manual_seed(4)
+    u8 = [torch.randint(0, 256, (B, H, W, 3), generator=g, dtype=torch.uint8) for _ in range(V + 1)]
+    outs = []
+    for kind in ('f32', 'u8_255'):
+        pipe = ops.HostPipeline(B, H, W, V, ops.LossFlags(num_scales=S, img_format=kind), _lib.MASK_EXP, torch.device(DEV))
+        h = pipe.host_inputs()
+        imgs = u8 if kind != 'f32' else [O.images_from_uint8(t) for t in u8]
+        h['tgt'].copy_(imgs[0]); h['poses'].copy_(d['poses']); h['Kp'].copy_(d['K_pyr'])
+        for dst, src in zip(h['srcs'] + h['xs'] + h['lgs'], imgs[1:] + d['disp_pyr'] + d['logits_pyr']):
+            dst.copy_(src)
+        l, gx, gp, gl = pipe.result(pipe.submit(h))
+        outs.append([l.clone(), gp.clone()] + [t.clone() for t in gx] + [t.clone() for t in gl])
+        if kind != 'f32':
+            assert pipe.bytes_per_step()[0] < 0.6 * h2d_f32
+        else:
+            h2d_f32 = pipe.bytes_per_step()[0]
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)

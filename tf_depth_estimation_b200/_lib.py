@@ -11,6 +11,8 @@ LIB_PATH = os.environ.get('VSL_LIB_PATH') or os.path.join(_HERE, 'libvsl.so')  #
 
 POSE_FORMATS = {'eular': 0, 'euler': 0, 'angleaxis': 1, 'matrix': 2}
 MASK_NONE, MASK_EXP, MASK_CONST = 0, 1, 2
+IMG_F32, IMG_U8_255, IMG_U8_255_CENTRED, IMG_U8_RAW = 0, 1, 2, 3
+IMG_FORMATS = {'f32': 0, 'u8_255': 1, 'u8_255_centred': 2, 'u8_raw': 3}
 MAX_SCALES, MAX_VIEWS = 6, 4
 
 _c_float_p = ctypes.c_void_p
@@ -27,7 +29,7 @@ class VslLossDesc(ctypes.Structure):
                 ('explain_reg_weight', ctypes.c_float), ('loss_scale', ctypes.c_float),
                 ('exact_coords', ctypes.c_int), ('want_src_grad', ctypes.c_int),
                 ('x_is_logit', ctypes.c_int), ('disp_scale', ctypes.c_float), ('disp_min', ctypes.c_float),
-                ('reserved_', ctypes.c_int),
+                ('img_format', ctypes.c_int),
                 ('ev_main_begin', ctypes.c_void_p), ('ev_main_end', ctypes.c_void_p)]
 
 
@@ -66,6 +68,11 @@ SIGNATURES = {
                                         _c_float_p, ctypes.POINTER(ctypes.c_void_p), _c_float_p,
                                         ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p),
                                         ctypes.c_void_p, _c_stream]),
+    'vsl_loss_fwd_bwd_u8': (ctypes.c_int, [ctypes.POINTER(VslLossDesc), ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p),
+                                           ctypes.POINTER(ctypes.c_void_p), _c_float_p, _c_float_p,
+                                           ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p),
+                                           _c_float_p, ctypes.POINTER(ctypes.c_void_p), _c_float_p,
+                                           ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p, _c_stream]),
     'vsl_scale': (ctypes.c_int, [_c_float_p] * 2 + [ctypes.c_longlong] + [_c_float_p] * 2 + [_c_stream]),
     'vsl_adam_step': (ctypes.c_int, [_c_float_p] * 4 + [ctypes.c_longlong] + [ctypes.c_float] * 4 + [ctypes.c_int, ctypes.c_float, _c_stream]),
     'vsl_peer_alloc': (ctypes.c_int, [ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]),

@@ -830,9 +830,10 @@ constexpr int kPrepPx = 1024;       // level-0 pixels per tile
 constexpr int kPrepThreads = 256;
 
 struct PrepImgJob {
-  const float* tgt;
-  const float* src[VSL_MAX_VIEWS];
-  float* tgt_lvl[VSL_MAX_SCALES];                   // RGB levels, [0] unused
+  const void* tgt;                                  // [B,H,W,3] float32, or uint8 (img_format != VSL_IMG_F32)
+  const void* src[VSL_MAX_VIEWS];
+  float* tgt_lvl[VSL_MAX_SCALES];                   // RGB levels; [0] = the float32 target, written only for uint8 images
+  float img_div, img_sub;                           // uint8 images: value = (float)u8 / img_div - img_sub
   float4* src_lvl[VSL_MAX_VIEWS][VSL_MAX_SCALES];   // zero-bordered RGBA levels
   int V, B, H, W, S;
   int tiles_x, tiles_y, n_tiles;                    // per image; n_tiles = (V + 1) * B * tiles_y * tiles_x
@@ -958,11 +959,19 @@ VSL_DEV int fast_div(int n, int d, float inv_d) {
 
 // Persistent blocks, three tile buffers: the cp.async of tile i+1 is in flight while tile i is turned into its
 // output levels, so a block never sits idle waiting for its load, and one barrier per tile is enough.
-template <int LOG2F>
+// U8: the images arrive as the loader's uint8 (imageselect_Dataloader.py:86-93: decode_jpeg -> to_float -> / 255.0).
+// A tile's bytes are staged the same way (a quarter of the traffic), then turned into the float tile through a
+// 256-entry table of (float)u8 / img_div - img_sub -- IEEE division and subtraction, i.e. the reference's own
+// conversion, bit for bit -- and the float32 level 0 of the target is written out for the fused kernel.
+template <int LOG2F, bool U8>
 __global__ void __launch_bounds__(kPrepThreads, 4)
 loss_prep_kernel(const PrepImgJob job, const PrepJob prep) {
   constexpr int F = 1 << LOG2F, RB = F > 8 ? F : 8, TW = kPrepPx / RB;
-  __shared__ float4 tile4[3][kPrepPx * 3 / 4];
+  constexpr int NBUF = U8 ? 2 : 3;                  // float tiles (uint8: the in-flight buffers are the byte tiles)
+  __shared__ float4 tile4[NBUF][kPrepPx * 3 / 4];
+  __shared__ uint4 raw4[U8 ? 3 : 1][U8 ? kPrepPx * 3 / 16 : 1];
+  __shared__ float lut[U8 ? 256 : 1];
+  if (U8) lut[threadIdx.x] = __fsub_rn(__fdiv_rn((float)threadIdx.x, job.img_div), job.img_sub);   // kPrepThreads == 256
   const int B = job.B, H = job.H, W = job.W;
   // launched programmatically dependent on whatever kernel precedes it in the stream (usually the previous step's
   // finalize, or the network that produced the inputs): only the launch latency overlaps, nothing is read before
@@ -1015,8 +1024,30 @@ loss_prep_kernel(const PrepImgJob job, const PrepJob prep) {
     return q;
   };
   // stage: row r of the tile = cols * 3 contiguous floats
+  // uint8: row r of the tile = cols * 3 contiguous bytes at raw + r * TW * 3
+  auto stage_u8 = [&](const Tile& q, unsigned char* raw) {
+    const unsigned char* __restrict__ img = reinterpret_cast<const unsigned char*>(q.im == 0 ? job.tgt : job.src[q.im > 0 ? q.im - 1 : 0]);
+    const unsigned char* __restrict__ g0 = img + (((size_t)q.b * H + q.y0) * W + q.x0) * 3;
+    if ((W % 16 == 0) && (q.cols % 16 == 0) && ((reinterpret_cast<uintptr_t>(img) & 15) == 0)) {
+      const unsigned ts = (unsigned)__cvta_generic_to_shared(raw);
+      const int q_row = q.cols * 3 / 16;                  // 16-byte pieces per row
+      for (int e = threadIdx.x; e < q.rows * q_row; e += kPrepThreads) {
+        const int r = e / q_row, c = e - r * q_row;
+        asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(ts + (unsigned)(r * TW * 3 + c * 16)),
+                     "l"(g0 + (size_t)r * W * 3 + c * 16), "l"(pol)
+                     : "memory");
+      }
+    } else {
+      const int n_row = q.cols * 3;
+      for (int i = threadIdx.x; i < q.rows * n_row; i += kPrepThreads) {
+        const int r = i / n_row, c = i - r * n_row;
+        raw[r * TW * 3 + c] = __ldg(g0 + (size_t)r * W * 3 + c);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
   auto stage = [&](const Tile& q, float* tile) {
-    const float* __restrict__ img = q.im == 0 ? job.tgt : job.src[q.im > 0 ? q.im - 1 : 0];
+    const float* __restrict__ img = reinterpret_cast<const float*>(q.im == 0 ? job.tgt : job.src[q.im > 0 ? q.im - 1 : 0]);
     const float* __restrict__ g0 = img + (((size_t)q.b * H + q.y0) * W + q.x0) * 3;
     if ((W % 4 == 0) && (q.cols % 4 == 0) && ((reinterpret_cast<uintptr_t>(img) & 15) == 0)) {
       const unsigned ts = (unsigned)__cvta_generic_to_shared(tile);
@@ -1051,22 +1082,45 @@ loss_prep_kernel(const PrepImgJob job, const PrepJob prep) {
   int t = blockIdx.x;
   if (t >= job.n_tiles) return;
   Tile cur = decode(t);
-  stage(cur, reinterpret_cast<float*>(tile4[0]));
+  if (U8) stage_u8(cur, reinterpret_cast<unsigned char*>(raw4[0]));
+  else stage(cur, reinterpret_cast<float*>(tile4[0]));
   for (int it = 0; t < job.n_tiles; ++it, t += gridDim.x) {
-    const float* tile = reinterpret_cast<const float*>(tile4[it % 3]);
+    const float* tile = reinterpret_cast<const float*>(tile4[it % NBUF]);
     const int tn = t + gridDim.x;
     Tile nxt = cur;
     if (tn < job.n_tiles) {
       nxt = decode(tn);
-      stage(nxt, reinterpret_cast<float*>(tile4[(it + 1) % 3]));
+      if (U8) stage_u8(nxt, reinterpret_cast<unsigned char*>(raw4[(it + 1) % 3]));
+      else stage(nxt, reinterpret_cast<float*>(tile4[(it + 1) % 3]));
       asm volatile("cp.async.wait_group 1;" ::: "memory");
     } else {
       asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
+    if (U8) {
+      // bytes -> floats through the table, four at a time (every row of the byte tile is a multiple of 4 bytes long:
+      // cols is a multiple of F >= 1 ... the tail of a ragged row converts stale bytes nobody reads)
+      const unsigned* rw = reinterpret_cast<const unsigned*>(raw4[it % 3]);
+      float4* tw = tile4[it % NBUF];
+#pragma unroll
+      for (int j = 0; j < (kPrepPx * 3 / 4) / kPrepThreads; ++j) {
+        const int e = threadIdx.x + j * kPrepThreads;
+        const unsigned w = rw[e];
+        tw[e] = make_float4(lut[w & 255u], lut[(w >> 8) & 255u], lut[(w >> 16) & 255u], lut[w >> 24]);
+      }
+      __syncthreads();
+    }
 
     const int b = cur.b, y0 = cur.y0, x0 = cur.x0, rows = cur.rows, cols = cur.cols;
     if (cur.im == 0) {
+      if (U8) {   // the float32 target at level 0 (the fused kernel streams it): rows of cols * 3 contiguous floats
+        float* __restrict__ d0 = job.tgt_lvl[0] + (((size_t)b * H + y0) * W + x0) * 3;
+        const int n_row = cols * 3;
+        for (int i = threadIdx.x; i < rows * n_row; i += kPrepThreads) {
+          const int r = i / n_row, c = i - r * n_row;
+          d0[(size_t)r * W * 3 + c] = tile[r * TW * 3 + c];
+        }
+      }
       prep_levels<LOG2F, TW, RB, false>(tile, rows, cols, [&](int sh, int& stride) {
         const int Hs = H >> sh, Ws = W >> sh;
         stride = Ws * 3;
@@ -1124,7 +1178,7 @@ using namespace vsl;
 namespace {
 
 struct WsLayout {
-  size_t xf, xq, partials, tgt_pyr, src_pyr, gsrc_pyr, total;  // byte offsets (gsrc_pyr only with want_src_grad)
+  size_t xf, xq, partials, tgt_pyr, src_pyr, gsrc_pyr, tgt0, total;  // byte offsets (gsrc_pyr only with want_src_grad, tgt0 only for uint8 images)
   size_t tgt_off[VSL_MAX_SCALES];                    // floats, level s of the target pyramid (s >= 1)
   size_t src_off[VSL_MAX_SCALES];                    // float4, level s inside one view's RGBA block
   size_t src_view;                                   // float4 per view
@@ -1144,6 +1198,8 @@ int check_desc(const VslLossDesc* d) {
   VSL_REQUIRE(d->pose_format >= VSL_POSE_EULER && d->pose_format <= VSL_POSE_MATRIX, VSL_E_FORMAT);
   VSL_REQUIRE(d->mask_mode >= VSL_MASK_NONE && d->mask_mode <= VSL_MASK_CONST, VSL_E_FORMAT);
   VSL_REQUIRE(d->exact_coords >= 0 && d->exact_coords <= 2, VSL_E_FORMAT);
+  VSL_REQUIRE(d->img_format >= VSL_IMG_F32 && d->img_format <= VSL_IMG_U8_RAW, VSL_E_FORMAT);
+  VSL_REQUIRE(!(d->want_src_grad && d->img_format != VSL_IMG_F32), VSL_E_UNSUPPORTED);   // no gradient w.r.t. bytes
   VSL_REQUIRE(!(d->want_src_grad && d->exact_coords == 1), VSL_E_UNSUPPORTED);
   VSL_REQUIRE(!d->x_is_logit || d->disp_scale > 0.f, VSL_E_UNSUPPORTED);
   return VSL_OK;
@@ -1173,7 +1229,8 @@ void layout(const VslLossDesc* d, WsLayout* L) {
   L->tgt_pyr = L->partials + round_up(sizeof(float) * (size_t)n * nt, 256);
   L->src_pyr = L->tgt_pyr + round_up(sizeof(float) * tl, 256);
   L->gsrc_pyr = L->src_pyr + sizeof(float4) * sl * (size_t)d->V;
-  L->total = L->gsrc_pyr + (d->want_src_grad ? sizeof(float4) * sl * (size_t)d->V : 0);
+  L->tgt0 = L->gsrc_pyr + (d->want_src_grad ? sizeof(float4) * sl * (size_t)d->V : 0);
+  L->total = L->tgt0 + (d->img_format != VSL_IMG_F32 ? round_up(sizeof(float) * (size_t)d->B * d->H * d->W * 3, 256) : 0);
 }
 
 template <typename Kern>
@@ -1245,7 +1302,7 @@ int run_loss(const VslLossDesc* d, LossParams& P, const float* poses, const floa
   return launch_status();
 }
 
-int launch_prep(const PrepImgJob& job, const PrepJob& prep, cudaStream_t st) {
+int launch_prep(const PrepImgJob& job, const PrepJob& prep, bool u8, cudaStream_t st) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(job.n_blocks);
   cfg.blockDim = dim3(kPrepThreads);
@@ -1256,13 +1313,24 @@ int launch_prep(const PrepImgJob& job, const PrepJob& prep, cudaStream_t st) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   cudaError_t e = cudaSuccess;
-  switch (job.S) {
-    case 1: e = cudaLaunchKernelEx(&cfg, loss_prep_kernel<0>, job, prep); break;
-    case 2: e = cudaLaunchKernelEx(&cfg, loss_prep_kernel<1>, job, prep); break;
-    case 3: e = cudaLaunchKernelEx(&cfg, loss_prep_kernel<2>, job, prep); break;
-    case 4: e = cudaLaunchKernelEx(&cfg, loss_prep_kernel<3>, job, prep); break;
-    case 5: e = cudaLaunchKernelEx(&cfg, loss_prep_kernel<4>, job, prep); break;
-    default: e = cudaLaunchKernelEx(&cfg, loss_prep_kernel<5>, job, prep); break;
+  if (u8) {
+    switch (job.S) {
+      case 1: e = cudaLaunchKernelEx(&cfg, loss_prep_kernel<0, true>, job, prep); break;
+      case 2: e = cudaLaunchKernelEx(&cfg, loss_prep_kernel<1, true>, job, prep); break;
+      case 3: e = cudaLaunchKernelEx(&cfg, loss_prep_kernel<2, true>, job, prep); break;
+      case 4: e = cudaLaunchKernelEx(&cfg, loss_prep_kernel<3, true>, job, prep); break;
+      case 5: e = cudaLaunchKernelEx(&cfg, loss_prep_kernel<4, true>, job, prep); break;
+      default: e = cudaLaunchKernelEx(&cfg, loss_prep_kernel<5, true>, job, prep); break;
+    }
+  } else {
+    switch (job.S) {
+      case 1: e = cudaLaunchKernelEx(&cfg, loss_prep_kernel<0, false>, job, prep); break;
+      case 2: e = cudaLaunchKernelEx(&cfg, loss_prep_kernel<1, false>, job, prep); break;
+      case 3: e = cudaLaunchKernelEx(&cfg, loss_prep_kernel<2, false>, job, prep); break;
+      case 4: e = cudaLaunchKernelEx(&cfg, loss_prep_kernel<3, false>, job, prep); break;
+      case 5: e = cudaLaunchKernelEx(&cfg, loss_prep_kernel<4, false>, job, prep); break;
+      default: e = cudaLaunchKernelEx(&cfg, loss_prep_kernel<5, false>, job, prep); break;
+    }
   }
   if (e != cudaSuccess) return (int)e;
   return launch_status();
@@ -1279,12 +1347,15 @@ size_t vsl_loss_ws_bytes(const VslLossDesc* d) {
   return L.total;
 }
 
-int vsl_loss_fwd_bwd(const VslLossDesc* d, const float* tgt, const float* const* srcs, const float* const* x_pyr,
-                     const float* poses, const float* K_pyr, const float* const* logits_pyr,
-                     const float* const* mask_pyr, float* losses, float* const* g_x_pyr, float* g_poses,
-                     float* const* g_logits_pyr, float* const* g_srcs, void* ws, vsl_stream_t stream) {
-  int rc = check_desc(d);
-  if (rc != VSL_OK) return rc;
+}  // extern "C"
+
+namespace {
+// tgt / srcs: float32 or uint8 images, as d->img_format says
+int loss_fwd_bwd(const VslLossDesc* d, const void* tgt, const void* const* srcs, const float* const* x_pyr,
+                 const float* poses, const float* K_pyr, const float* const* logits_pyr,
+                 const float* const* mask_pyr, float* losses, float* const* g_x_pyr, float* g_poses,
+                 float* const* g_logits_pyr, float* const* g_srcs, void* ws, vsl_stream_t stream) {
+  int rc = VSL_OK;
   VSL_REQUIRE(tgt && srcs && x_pyr && poses && K_pyr && losses && g_x_pyr && g_poses && ws, VSL_E_NULL);
   VSL_REQUIRE(d->mask_mode != VSL_MASK_EXP || (logits_pyr && g_logits_pyr), VSL_E_NULL);
   VSL_REQUIRE(d->mask_mode != VSL_MASK_CONST || mask_pyr, VSL_E_NULL);
@@ -1299,6 +1370,7 @@ int vsl_loss_fwd_bwd(const VslLossDesc* d, const float* tgt, const float* const*
   float* tgt_pyr = reinterpret_cast<float*>(base + L.tgt_pyr);
   float4* src_pyr = reinterpret_cast<float4*>(base + L.src_pyr);
   float4* gsrc_pyr = reinterpret_cast<float4*>(base + L.gsrc_pyr);
+  const bool u8 = d->img_format != VSL_IMG_F32;
 
   LossParams P;
   P.B = d->B; P.H = d->H; P.W = d->W; P.S = d->S; P.V = d->V;
@@ -1330,7 +1402,8 @@ int vsl_loss_fwd_bwd(const VslLossDesc* d, const float* tgt, const float* const*
       VSL_REQUIRE(mask_pyr[s], VSL_E_NULL);
       P.mask[s] = mask_pyr[s];
     }
-    P.tgt[s] = (s == 0) ? tgt : tgt_pyr + L.tgt_off[s];
+    P.tgt[s] = (s == 0) ? (u8 ? reinterpret_cast<const float*>(base + L.tgt0) : reinterpret_cast<const float*>(tgt))
+                        : tgt_pyr + L.tgt_off[s];
     for (int v = 0; v < d->V; ++v) {
       P.src[v][s] = src_pyr + L.src_view * (size_t)v + L.src_off[s];
       P.gsrc[v][s] = d->want_src_grad ? gsrc_pyr + L.src_view * (size_t)v + L.src_off[s] : nullptr;
@@ -1365,6 +1438,10 @@ int vsl_loss_fwd_bwd(const VslLossDesc* d, const float* tgt, const float* const*
   prep.xq = reinterpret_cast<XformQ*>(base + L.xq);
   PrepImgJob job;
   job.tgt = tgt;
+  // uint8 images: (float)u8 / 255 (imageselect_Dataloader.py:93), / 255 - 0.5 (imageselect_Dataloader_optflow_dim11.py:128)
+  // or the raw value (imageselect_Dataloader_optflow.py:129, normalisation commented out)
+  job.img_div = d->img_format == VSL_IMG_U8_RAW ? 1.0f : 255.0f;
+  job.img_sub = d->img_format == VSL_IMG_U8_255_CENTRED ? 0.5f : 0.0f;
   job.V = d->V; job.B = d->B; job.H = d->H; job.W = d->W; job.S = d->S;
   const int F = 1 << (d->S - 1);
   {
@@ -1376,6 +1453,7 @@ int vsl_loss_fwd_bwd(const VslLossDesc* d, const float* tgt, const float* const*
   job.border_begin[0] = 0;
   for (int s = 0; s < VSL_MAX_SCALES; ++s) {
     job.tgt_lvl[s] = (s >= 1 && s < d->S) ? tgt_pyr + L.tgt_off[s] : nullptr;
+    if (s == 0 && u8) job.tgt_lvl[0] = reinterpret_cast<float*>(base + L.tgt0);
     for (int v = 0; v < VSL_MAX_VIEWS; ++v) {
       job.src[v] = v < d->V ? srcs[v] : nullptr;
       job.src_lvl[v][s] = (v < d->V && s < d->S) ? src_pyr + L.src_view * (size_t)v + L.src_off[s] : nullptr;
@@ -1394,7 +1472,7 @@ int vsl_loss_fwd_bwd(const VslLossDesc* d, const float* tgt, const float* const*
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     job.n_blocks = std::min(job.n_tiles, sms * 4);
   }
-  rc = launch_prep(job, prep, st);
+  rc = launch_prep(job, prep, u8, st);
   if (rc != VSL_OK) return rc;
   // 2 + 3. fused loss and finalize
 #ifdef VSL_DEV_V2_ONLY   // development builds only (never the shipped library): one instantiation, quick to compile
@@ -1419,6 +1497,32 @@ int vsl_loss_fwd_bwd(const VslLossDesc* d, const float* tgt, const float* const*
     loss_fold_src_grad_kernel<<<dim3((d->W + 255) / 256, d->H, d->V * d->B), 256, 0, st>>>(fj);
   }
   return launch_status();
+}
+}  // namespace
+
+extern "C" {
+
+int vsl_loss_fwd_bwd(const VslLossDesc* d, const float* tgt, const float* const* srcs, const float* const* x_pyr,
+                     const float* poses, const float* K_pyr, const float* const* logits_pyr,
+                     const float* const* mask_pyr, float* losses, float* const* g_x_pyr, float* g_poses,
+                     float* const* g_logits_pyr, float* const* g_srcs, void* ws, vsl_stream_t stream) {
+  const int rc = check_desc(d);
+  if (rc != VSL_OK) return rc;
+  VSL_REQUIRE(d->img_format == VSL_IMG_F32, VSL_E_FORMAT);
+  return loss_fwd_bwd(d, tgt, reinterpret_cast<const void* const*>(srcs), x_pyr, poses, K_pyr, logits_pyr, mask_pyr, losses,
+                      g_x_pyr, g_poses, g_logits_pyr, g_srcs, ws, stream);
+}
+
+int vsl_loss_fwd_bwd_u8(const VslLossDesc* d, const unsigned char* tgt, const unsigned char* const* srcs,
+                        const float* const* x_pyr, const float* poses, const float* K_pyr,
+                        const float* const* logits_pyr, const float* const* mask_pyr, float* losses,
+                        float* const* g_x_pyr, float* g_poses, float* const* g_logits_pyr, void* ws,
+                        vsl_stream_t stream) {
+  const int rc = check_desc(d);
+  if (rc != VSL_OK) return rc;
+  VSL_REQUIRE(d->img_format != VSL_IMG_F32, VSL_E_FORMAT);
+  return loss_fwd_bwd(d, tgt, reinterpret_cast<const void* const*>(srcs), x_pyr, poses, K_pyr, logits_pyr, mask_pyr, losses,
+                      g_x_pyr, g_poses, g_logits_pyr, nullptr, ws, stream);
 }
 
 }  // extern "C"

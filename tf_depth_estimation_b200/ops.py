@@ -96,6 +96,18 @@ def _f32(t, name):
     return t
 
 
+def _img(t, name, dtype):
+    """An image argument of the fused step: float32, or the loader's uint8 when the flags say so."""
+    if dtype == torch.float32:
+        return _f32(t, name)
+    t = from_external(t, name)
+    if not t.is_cuda:
+        raise TypeError('%s must be a CUDA tensor (this path has no CPU fallback)' % name)
+    if t.dtype != torch.uint8:
+        raise TypeError('%s must be uint8 for this img_format, got %s' % (name, t.dtype))
+    return t if t.is_contiguous() else t.contiguous()
+
+
 def _g32(t, name='grad'):
     """An upstream gradient handed over by autograd (never a caller's input): packed without a warning."""
     if t.dtype != torch.float32 or not t.is_cuda:
@@ -608,27 +620,38 @@ class LossFlags(object):
         self.x_is_logit = False
         self.disp_scaling = 4.0
         self.min_disp = 0.0
+        # what the image tensors hold: 'f32' (float32, as the reference's graph sees them) or the loader's uint8
+        # before its conversion -- 'u8_255': x / 255.0 (imageselect_Dataloader.py:93), 'u8_255_centred': x / 255.0 - 0.5
+        # (imageselect_Dataloader_optflow_dim11.py:128), 'u8_raw': x (imageselect_Dataloader_optflow.py:129).  The
+        # kernel converts on load; results are bit-identical to feeding the converted float32 images.
+        self.img_format = 'f32'
         self.__dict__.update(kw)
 
 
-def _arena(shapes, device=None, pinned=False):
-    """One float32 buffer carved into 256-byte aligned views of the given shapes -> (buffer, [views]).  Lets a whole
-    set of tensors cross PCIe as ONE copy."""
+def _arena(shapes, device=None, pinned=False, dtypes=None):
+    """One buffer carved into 256-byte aligned views of the given shapes (float32 unless `dtypes` says otherwise)
+    -> (buffer, [views]).  Lets a whole set of tensors cross PCIe as ONE copy."""
+    dtypes = dtypes or [torch.float32] * len(shapes)
     offs, n = [], 0
-    for shp in shapes:
+    for shp, dt in zip(shapes, dtypes):
         offs.append(n)
         cnt = 1
         for d in shp:
             cnt *= d
-        n += (cnt + 63) // 64 * 64
-    buf = torch.empty(max(n, 64), dtype=torch.float32).pin_memory() if pinned else \
-        torch.empty(max(n, 64), dtype=torch.float32, device=device)
+        n += (cnt * torch.empty(0, dtype=dt).element_size() + 255) // 256 * 256
+    if all(dt == torch.float32 for dt in dtypes):
+        buf = torch.empty(max(n, 256) // 4, dtype=torch.float32).pin_memory() if pinned else \
+            torch.empty(max(n, 256) // 4, dtype=torch.float32, device=device)
+        raw = buf.view(torch.uint8)
+    else:
+        buf = raw = torch.empty(max(n, 256), dtype=torch.uint8).pin_memory() if pinned else \
+            torch.empty(max(n, 256), dtype=torch.uint8, device=device)
     views = []
-    for shp, o in zip(shapes, offs):
+    for shp, dt, o in zip(shapes, dtypes, offs):
         cnt = 1
         for d in shp:
             cnt *= d
-        views.append(buf[o:o + cnt].view(*shp))
+        views.append(raw[o:o + cnt * torch.empty(0, dtype=dt).element_size()].view(dt).view(*shp))
     return buf, views
 
 
@@ -705,13 +728,20 @@ class ViewSynthesisPlan(object):
         self.mask_mode = mask_mode
         self.device = device
         self.fmt = _fmt(flags.pose_format)
+        try:
+            self.img_format = _lib.IMG_FORMATS[getattr(flags, 'img_format', 'f32')]
+        except KeyError:
+            raise ValueError("img_format must be one of %s" % sorted(_lib.IMG_FORMATS))
+        self.img_dtype = torch.float32 if self.img_format == _lib.IMG_F32 else torch.uint8
+        if self.img_format != _lib.IMG_F32 and want_src_grad:
+            raise ValueError('no gradient with respect to uint8 images')
         self.desc = VslLossDesc(B, H, W, S, V, self.fmt, mask_mode, int(flags.pixel_scale_norm),
                                 int(flags.depth_is_inverse), int(flags.smooth_on_inverse),
                                 float(flags.data_weight), float(flags.smooth_weight),
                                 float(flags.explain_reg_weight), float(loss_scale),
                                 int(getattr(flags, 'exact_coords', False)), int(self.want_src_grad),
                                 int(getattr(flags, 'x_is_logit', False)), float(getattr(flags, 'disp_scaling', 4.0)),
-                                float(getattr(flags, 'min_disp', 0.0)), 0, None, None)
+                                float(getattr(flags, 'min_disp', 0.0)), self.img_format, None, None)
         nbytes = lib.vsl_loss_ws_bytes(self.desc)
         if nbytes == 0:
             raise ValueError('unsupported loss shape B=%d H=%d W=%d S=%d V=%d' % (B, H, W, S, V))
@@ -736,9 +766,13 @@ class ViewSynthesisPlan(object):
         pointers by the plan's sizes, so a mismatch must be an error here, never an out-of-bounds read there."""
         check_loss_shapes(self.B, self.H, self.W, self.S, self.V, self.fmt, self.mask_mode, tgt, srcs, x_pyr, poses,
                           K_pyr, logits_pyr, mask_pyr)
-        for t in [tgt, poses, K_pyr] + list(srcs) + list(x_pyr) + list(logits_pyr or []) + list(mask_pyr or []):
+        for t in [poses, K_pyr] + list(x_pyr) + list(logits_pyr or []) + list(mask_pyr or []):
             if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
                 raise TypeError('the fused step takes contiguous CUDA float32 tensors (no CPU fallback)')
+        for t in [tgt] + list(srcs):
+            if not (t.is_cuda and t.dtype == self.img_dtype and t.is_contiguous()):
+                raise TypeError('images must be contiguous CUDA %s tensors for img_format=%r (no CPU fallback)'
+                                % (self.img_dtype, self.img_format))
 
     def bind(self, tgt, srcs, x_pyr, poses, K_pyr, logits_pyr=None, mask_pyr=None, out=None, g_srcs=None):
         """Validate and pre-marshal the C arguments for one set of input (and output) buffers; run_bound(args) then
@@ -746,16 +780,20 @@ class ViewSynthesisPlan(object):
         self.check_inputs(tgt, srcs, x_pyr, poses, K_pyr, logits_pyr, mask_pyr)
         out = self.out if out is None else out
         g_srcs = self.g_srcs if g_srcs is None else g_srcs
-        return (self.desc, tgt.data_ptr(), ptr_array([s.data_ptr() for s in srcs]),
+        head = (self.desc, tgt.data_ptr(), ptr_array([s.data_ptr() for s in srcs]),
                 ptr_array([x.data_ptr() for x in x_pyr]), poses.data_ptr(), K_pyr.data_ptr(),
                 ptr_array([l.data_ptr() for l in logits_pyr]) if logits_pyr is not None else None,
                 ptr_array([m.data_ptr() for m in mask_pyr]) if mask_pyr is not None else None,
-                out.losses.data_ptr(), out._gx_ptrs, out.g_poses.data_ptr(), out._gl_ptrs,
-                ptr_array([t.data_ptr() for t in g_srcs]) if g_srcs else None, self.ws.data_ptr())
+                out.losses.data_ptr(), out._gx_ptrs, out.g_poses.data_ptr(), out._gl_ptrs)
+        if self.img_format != _lib.IMG_F32:          # vsl_loss_fwd_bwd_u8: no d/d(source images)
+            return head + (self.ws.data_ptr(),)
+        return head + (ptr_array([t.data_ptr() for t in g_srcs]) if g_srcs else None, self.ws.data_ptr())
 
     def run_bound(self, args, stream=None):
         self.version += 1
-        check(_lib.load().vsl_loss_fwd_bwd(*args, _stream() if stream is None else stream))
+        lib = _lib.load()
+        fn = lib.vsl_loss_fwd_bwd if self.img_format == _lib.IMG_F32 else lib.vsl_loss_fwd_bwd_u8
+        check(fn(*args, _stream() if stream is None else stream))
         return self.losses
 
     def set_profile_events(self, begin=None, end=None):
@@ -776,14 +814,14 @@ class _ViewSynthesisLoss(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, plan, tgt, K_pyr, poses, n_src, n_x, *rest_all):
-        srcs = [_f32(t, 'src') for t in rest_all[:n_src]]
+        srcs = [_img(t, 'src', plan.img_dtype) for t in rest_all[:n_src]]
         x_pyr = [_f32(t, 'x_pyr') for t in rest_all[n_src:n_src + n_x]]
         rest = [_f32(t, 'pyr') for t in rest_all[n_src + n_x:]]
         logits = rest if plan.mask_mode == _lib.MASK_EXP else None
         mask = rest if plan.mask_mode == _lib.MASK_CONST else None
         out = plan.new_outputs()
         g_srcs = plan.new_src_grads() if plan.want_src_grad else None
-        plan.run_bound(plan.bind(_f32(tgt, 'tgt'), srcs, x_pyr, _f32(poses, 'poses'), _f32(K_pyr, 'K_pyr'), logits,
+        plan.run_bound(plan.bind(_img(tgt, 'tgt', plan.img_dtype), srcs, x_pyr, _f32(poses, 'poses'), _f32(K_pyr, 'K_pyr'), logits,
                                  mask, out=out, g_srcs=g_srcs))
         ctx.out, ctx.g_srcs, ctx.mask_mode = out, g_srcs, plan.mask_mode
         ctx.n_src, ctx.n_x, ctx.n_rest = n_src, n_x, len(rest)
@@ -911,16 +949,19 @@ class HostPipeline(object):
         in_shapes = ([(B, H, W, 3)] + [(B, H, W, 3)] * V + [(B, H >> s, W >> s, 1) for s in range(S)] +
                      [pose_shape, (B, S, 3, 3)] +
                      ([(B, H >> s, W >> s, 2 * V) for s in range(S)] if mask_mode == _lib.MASK_EXP else []))
+        # images in the dtype the flags name (uint8 = what the reference's loader holds before `/ 255.0`: a quarter of
+        # the bytes over PCIe), everything else float32
+        in_dtypes = [self.plans[0].img_dtype] * (1 + V) + [torch.float32] * (len(in_shapes) - 1 - V)
 
         def carve(views):
             return dict(tgt=views[0], srcs=views[1:1 + V], xs=views[1 + V:1 + V + S], poses=views[1 + V + S],
                         Kp=views[2 + V + S], lgs=(views[3 + V + S:3 + V + 2 * S] if mask_mode == _lib.MASK_EXP else None))
-        self._in_shapes, self._carve = in_shapes, carve
+        self._in_shapes, self._in_dtypes, self._carve = in_shapes, in_dtypes, carve
         # device inputs of a slot = one arena; host inputs allocated by host_inputs() mirror it, so a step's
         # inputs cross PCIe as ONE copy (and its outputs likewise, from the plan's output arena)
         self.dev_in_arena, self.dev_in = [], []
         for _ in range(self.DEPTH):
-            buf, views = _arena(in_shapes, device=device)
+            buf, views = _arena(in_shapes, device=device, dtypes=in_dtypes)
             self.dev_in_arena.append(buf)
             self.dev_in.append(carve(views))
         self.bound = [p.bind(d['tgt'], d['srcs'], d['xs'], d['poses'], d['Kp'], d['lgs'])
@@ -953,13 +994,13 @@ class HostPipeline(object):
     def host_inputs(self):
         """A dict of pinned host tensors (tgt, srcs, xs, poses, Kp, lgs) that are views into ONE pinned arena laid out
         like the device-side inputs: submit() then moves a step's inputs with a single copy.  Fill them in place."""
-        buf, views = _arena(self._in_shapes, pinned=True)
+        buf, views = _arena(self._in_shapes, pinned=True, dtypes=self._in_dtypes)
         d = self._carve(views)
         d['_arena'] = buf
         return d
 
     def bytes_per_step(self):
-        h2d = sum(t.numel() * 4 for t in self._flat(self.dev_in[0]))
+        h2d = sum(t.numel() * t.element_size() for t in self._flat(self.dev_in[0]))
         o = self.host_out[0]
         d2h = sum(t.numel() * 4 for t in [o['losses'], o['g_poses']] + o['g_x'] + o['g_lgs'])
         return h2d, d2h
