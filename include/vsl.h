@@ -189,7 +189,7 @@ int vsl_loss_fwd_bwd(const VslLossDesc* d,
                      const float* poses, const float* K_pyr /*[B,S,3,3]*/,
                      const float* const* logits_pyr /*S x [B,Hs,Ws,2V], MASK_EXP*/,
                      const float* const* mask_pyr /*S x [B,Hs,Ws,1], MASK_CONST*/,
-                     float* losses /*device [4]*/, float* const* g_x_pyr /*S x [B,Hs,Ws,1]*/,
+                     float* losses /*device [5]: pixel, smooth, exp, consist, their sum*/, float* const* g_x_pyr /*S x [B,Hs,Ws,1]*/,
                      float* g_poses /*same shape as poses*/, float* const* g_logits_pyr /*S, MASK_EXP*/,
                      float* const* g_srcs /*host array V x [B,H,W,3]; NULL unless want_src_grad*/,
                      void* ws, vsl_stream_t stream);

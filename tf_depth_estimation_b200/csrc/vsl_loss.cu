@@ -644,16 +644,17 @@ loss_fused_kernel(const LossParams P) {
     for (int v = 0; v < V; ++v) exp_sum = fmaf(lg2_fast(se_prod[v]), 0.6931471805599453f, exp_sum);
   }
   vals[0] = pix_sum * cpix; vals[1] = sm_sum; vals[2] = exp_sum * cexp;
+  vals[3] = 0.f;                    // consistency term (slot reserved)
   if (!act) { vals[0] = 0.f; vals[1] = 0.f; vals[2] = 0.f; }   // lanes past the image edge recomputed the last column
 #pragma unroll
   for (int v = 0; v < V; ++v)
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-      vals[3 + v * 12 + i] = gx * S3[v][i];
-      vals[3 + v * 12 + 3 + i] = S2[v][i];
-      vals[3 + v * 12 + 6 + i] = S3[v][i];
-      vals[3 + v * 12 + 9 + i] = S4[v][i];
-      if (!act) { vals[3 + v * 12 + i] = 0.f; vals[3 + v * 12 + 3 + i] = 0.f; vals[3 + v * 12 + 6 + i] = 0.f; vals[3 + v * 12 + 9 + i] = 0.f; }
+      vals[kLossSlots + v * 12 + i] = gx * S3[v][i];
+      vals[kLossSlots + v * 12 + 3 + i] = S2[v][i];
+      vals[kLossSlots + v * 12 + 6 + i] = S3[v][i];
+      vals[kLossSlots + v * 12 + 9 + i] = S4[v][i];
+      if (!act) { vals[kLossSlots + v * 12 + i] = 0.f; vals[kLossSlots + v * 12 + 3 + i] = 0.f; vals[kLossSlots + v * 12 + 6 + i] = 0.f; vals[kLossSlots + v * 12 + 9 + i] = 0.f; }
     }
   using Z = BflySizes<N>;
   bfly_step<N, 16>(vals, lane);
@@ -714,36 +715,40 @@ loss_finalize_kernel(const LossParams P, const float* __restrict__ poses, const 
   asm volatile("griddepcontrol.wait;" ::: "memory");   // from here on: the fused launch's partials
 
   if (b == P.B) {
-    // losses: columns 0..2 of every tile row, thread-strided, then a fixed tree
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-    constexpr int U = 8;                       // rows in flight per thread: the loads of a batch are independent
+    // losses: columns 0..3 of every tile row (pixel, smooth, exp, consist), thread-strided, then a fixed tree
+    double acc[kLossSlots] = {0.0, 0.0, 0.0, 0.0};
+    constexpr int U = 10;                      // rows in flight per thread: the loads of a batch are independent
     for (int i0 = threadIdx.x; i0 < n_items; i0 += kFinThreads * U) {
-      float q[U][3];
+      float q[U][kLossSlots];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int i = i0 + u * kFinThreads;
         const float* p = P.partials + (size_t)(i < n_items ? i : 0) * N;
-        q[u][0] = i < n_items ? p[0] : 0.f; q[u][1] = i < n_items ? p[1] : 0.f; q[u][2] = i < n_items ? p[2] : 0.f;
+#pragma unroll
+        for (int k = 0; k < kLossSlots; ++k) q[u][k] = i < n_items ? p[k] : 0.f;
       }
 #pragma unroll
-      for (int u = 0; u < U; ++u) { a0 += (double)q[u][0]; a1 += (double)q[u][1]; a2 += (double)q[u][2]; }
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int k = 0; k < kLossSlots; ++k) acc[k] += (double)q[u][k];
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-      a2 += __shfl_xor_sync(0xffffffffu, a2, o);
-    }
-    if (lane == 0) { part[warp][0][0] = a0; part[warp][0][1] = a1; part[warp][0][2] = a2; }
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int k = 0; k < kLossSlots; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+    if (lane == 0)
+#pragma unroll
+      for (int k = 0; k < kLossSlots; ++k) part[warp][0][k] = acc[k];
     __syncthreads();
-    if (threadIdx.x < 3) {
+    if (threadIdx.x < kLossSlots) {
       double t = 0.0;
       for (int w = 0; w < NW; ++w) t += part[w][0][threadIdx.x];
-      losses[threadIdx.x] = (float)(t * (double)inv_loss_scale);
+      losses[threadIdx.x] = (float)(t * (double)inv_loss_scale);   // [0..3] = pixel, smooth, exp, consist
       tsum[0][threadIdx.x] = t;
     }
     __syncthreads();
-    if (threadIdx.x == 0) losses[3] = (float)((tsum[0][0] + tsum[0][1] + tsum[0][2]) * (double)inv_loss_scale);
+    if (threadIdx.x == 0)                                           // [4] = their sum
+      losses[4] = (float)((tsum[0][0] + tsum[0][1] + tsum[0][2] + tsum[0][3]) * (double)inv_loss_scale);
     return;
   }
 
@@ -781,7 +786,7 @@ loss_finalize_kernel(const LossParams P, const float* __restrict__ poses, const 
     double acc = 0.0;
     if (k < 3) {
       for (int sc = 0; sc < P.S; ++sc) {
-        const double* t = &tsum[sc][3 + v * 12];
+        const double* t = &tsum[sc][kLossSlots + v * 12];
         const float* ki = sKinv[sc];
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
@@ -1206,7 +1211,7 @@ int check_desc(const VslLossDesc* d) {
 }
 
 void layout(const VslLossDesc* d, WsLayout* L) {
-  const int nt = 3 + 12 * d->V;
+  const int nt = kLossSlots + 12 * d->V;
   int n = 0;
   size_t tl = 0, sl = 0;
   for (int s = 0; s < d->S; ++s) {

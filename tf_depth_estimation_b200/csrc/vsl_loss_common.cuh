@@ -61,7 +61,9 @@ struct LossParams {
   float Wf[VSL_MAX_SCALES], Hf[VSL_MAX_SCALES];
 };
 
-template <int V> struct NT { static constexpr int value = 3 + 12 * V; };
+// partial sums per tile: kLossSlots loss sums (pixel, smooth, exp, consist) + per view 12 dP entries
+constexpr int kLossSlots = 4;
+template <int V> struct NT { static constexpr int value = kLossSlots + 12 * V; };
 
 // One warp's slice of dynamic shared memory (floats).  What the unified L1 does not give to shared memory is the
 // cache the gathers run in, and the carve-out moves in steps (..., 100, 132, 164, 196 KB): the fast-arithmetic

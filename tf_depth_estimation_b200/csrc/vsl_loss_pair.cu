@@ -495,6 +495,7 @@ loss_fused_pair_kernel(const LossParams P) {
   pix_sum = lo(pix2) + hi(pix2);
   exp_sum = lo(exp2) + hi(exp2);
   vals[0] = pix_sum * cpix; vals[1] = sm_sum; vals[2] = exp_sum * cexp;
+  vals[3] = 0.f;                                                // consistency term: the scalar kernel only
   if (!act) { vals[0] = 0.f; vals[1] = 0.f; vals[2] = 0.f; }   // lanes past the image edge recomputed the last column
 #pragma unroll
   for (int v = 0; v < V; ++v)
@@ -505,10 +506,10 @@ loss_fused_pair_kernel(const LossParams P) {
       const float s2 = sgn_i * ((v & 1) ? hi(S2[p][i]) : lo(S2[p][i]));
       const float s3 = sgn_i * ((v & 1) ? hi(S3[p][i]) : lo(S3[p][i]));
       const float s4 = sgn_i * ((v & 1) ? hi(S4[p][i]) : lo(S4[p][i]));
-      vals[3 + v * 12 + i] = act ? gx_end * s3 : 0.f;
-      vals[3 + v * 12 + 3 + i] = act ? s2 : 0.f;
-      vals[3 + v * 12 + 6 + i] = act ? s3 : 0.f;
-      vals[3 + v * 12 + 9 + i] = act ? s4 : 0.f;
+      vals[kLossSlots + v * 12 + i] = act ? gx_end * s3 : 0.f;
+      vals[kLossSlots + v * 12 + 3 + i] = act ? s2 : 0.f;
+      vals[kLossSlots + v * 12 + 6 + i] = act ? s3 : 0.f;
+      vals[kLossSlots + v * 12 + 9 + i] = act ? s4 : 0.f;
     }
   using Z = BflySizes<N>;
   bfly_step<N, 16>(vals, lane);

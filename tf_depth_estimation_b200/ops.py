@@ -657,7 +657,7 @@ def _arena(shapes, device=None, pinned=False, dtypes=None):
 
 def _loss_out_shapes(B, H, W, S, V, fmt, mask_mode):
     pose_shape = (B, V, 4, 4) if fmt == 2 else (B, V, 6)
-    shapes = [(4,)] + [(B, H >> s, W >> s, 1) for s in range(S)] + [pose_shape]
+    shapes = [(8,)] + [(B, H >> s, W >> s, 1) for s in range(S)] + [pose_shape]
     if mask_mode == _lib.MASK_EXP:
         shapes += [(B, H >> s, W >> s, 2 * V) for s in range(S)]
     return shapes
@@ -672,7 +672,8 @@ class LossOutputs(object):
         self.shapes = _loss_out_shapes(B, H, W, S, V, fmt, mask_mode)
         self.arena, views = _arena(self.shapes, device=device)
         self.losses = views[0][:3]           # (pixel, smooth, exp)
-        self.total = views[0][3]             # their sum, written by the same kernel
+        self.consist = views[0][3]           # the depth-consistency term (0 unless the step carries one)
+        self.total = views[0][4]             # their sum, written by the same kernel
         self.g_x = views[1:1 + S]
         self.g_poses = views[1 + S]
         self.g_logits = views[2 + S:2 + 2 * S] if mask_mode == _lib.MASK_EXP else None
@@ -749,7 +750,7 @@ class ViewSynthesisPlan(object):
         self.out = self.new_outputs()
         self.out_arena, self.out_shapes = self.out.arena, self.out.shapes
         self.losses = self.out.losses
-        self.out.arena[:4].zero_()
+        self.out.arena[:8].zero_()
         self.g_x, self.g_poses, self.g_logits = self.out.g_x, self.out.g_poses, self.out.g_logits
         # d/d(source images): produced only on request (an extra atomic scatter + fold-back pass)
         self.g_srcs = self.new_src_grads() if self.want_src_grad else None
@@ -970,7 +971,7 @@ class HostPipeline(object):
         for p in self.plans:
             buf, views = _arena(p.out_shapes, pinned=True)
             self.host_out_arena.append(buf)
-            self.host_out.append(dict(losses=views[0][:3], total=views[0][3], g_x=views[1:1 + S], g_poses=views[1 + S],
+            self.host_out.append(dict(losses=views[0][:3], total=views[0][4], g_x=views[1:1 + S], g_poses=views[1 + S],
                                       g_lgs=(views[2 + S:2 + 2 * S] if mask_mode == _lib.MASK_EXP else [])))
         self.s_in, self.s_comp, self.s_out = (torch.cuda.Stream(device=device) for _ in range(3))
         # the plans' buffers were initialised on the current stream: nothing on the side streams may overtake that

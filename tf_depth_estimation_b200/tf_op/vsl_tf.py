@@ -36,7 +36,7 @@ def view_synthesis_loss(tgt, srcs, x_pyr, poses, k_pyr, logits_pyr, FLAGS, pose_
                                        data_weight=FLAGS.data_weight, smooth_weight=FLAGS.smooth_weight,
                                        explain_reg_weight=FLAGS.explain_reg_weight)
     terms = tf.stop_gradient(out.losses[:3])
-    return out.losses[3], terms[0], terms[1], terms[2]
+    return out.losses[4], terms[0], terms[1], terms[2]
 
 
 @_ops.RegisterGradient('VslViewSynthesisLoss')
@@ -44,7 +44,7 @@ def _loss_grad(op, g_losses, *_unused):
     # losses = [pixel, smooth, exp, total]; the op's precomputed gradients are those of `total`, so only the upstream
     # entry of `total` may be non-zero (the wrapper above hands the other three out under stop_gradient)
     S, V = op.get_attr('S'), op.get_attr('V')
-    g = g_losses[3]
+    g = g_losses[4]
     g_x = [g * t for t in op.outputs[1:1 + S]]
     g_poses = g * op.outputs[1 + S]
     g_lg = [g * t for t in op.outputs[2 + S:2 + 2 * S]]

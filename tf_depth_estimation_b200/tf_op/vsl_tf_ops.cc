@@ -138,7 +138,7 @@ REGISTER_OP("VslViewSynthesisLoss")
     .Attr("pose_format: int = 0").Attr("pixel_scale_norm: int = 1").Attr("depth_is_inverse: int = 1")
     .Attr("smooth_on_inverse: int = 0").Attr("data_weight: float = 1.0").Attr("smooth_weight: float = 0.5")
     .Attr("explain_reg_weight: float = 0.2")
-    .Output("losses: float")              // [4] = pixel, smooth, exp, total
+    .Output("losses: float")              // [5] = pixel, smooth, exp, consist, total
     .Output("g_x_pyr: S * float")
     .Output("g_poses: float")
     .Output("g_logits_pyr: S * float")
@@ -180,7 +180,7 @@ class VslViewSynthesisLossOp : public tf::OpKernel {
     float *g_x[VSL_MAX_SCALES], *g_lg[VSL_MAX_SCALES];
     for (int v = 0; v < V; ++v) srcs[v] = In(ctx, 1 + v);
     tf::Tensor *losses, *g_poses, *t, ws;
-    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, tf::TensorShape({4}), &losses));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, tf::TensorShape({5}), &losses));
     for (int s = 0; s < S; ++s) {
       xs[s] = In(ctx, 1 + V + s);
       lgs[s] = In(ctx, 3 + V + S + s);
