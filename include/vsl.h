@@ -152,7 +152,7 @@ int vsl_pyramid(const float* img /*[B,H,W,C]*/, int B, int H, int W, int C, int 
  *      explainability mask of train_depth_then_cam_lr.py:297-328 (or a constant validity mask,
  *      train_optflow_combine.py:176,187-188), forward AND backward in one pass over the data.
  *
- *      losses[4] = (pixel, smooth, exp, pixel + smooth + exp); gradients are those of losses[3] * loss_scale.  */
+ *      losses[5] = (pixel, smooth, exp, consist, their sum); gradients are those of losses[4] * loss_scale.  */
 typedef struct {
   int B, H, W;           /* level-0 size; level s is (H>>s) x (W>>s) */
   int S, V;              /* scales (<= VSL_MAX_SCALES), source views (<= VSL_MAX_VIEWS) */
@@ -178,6 +178,12 @@ typedef struct {
                             U8_255 (float)u8 / 255.0 (imageselect_Dataloader.py:86-93), U8_255_CENTRED ... - 0.5
                             (imageselect_Dataloader_optflow_dim11.py:128), U8_RAW the value itself
                             (imageselect_Dataloader_optflow.py:129) */
+  float consist_weight;  /* > 0 (vsl_loss_consist_fwd_bwd only): the left-right depth-consistency term of
+                            train_depth_then_cam_lr.py:336-340 rides on the same gather --
+                            sum_s consist_weight * mean(|z_v - bilinear(source depth_v_s, coords_v)| * mask_v), z_v the
+                            projected depth of the warp (utils_lr.py:172-194), the source depth map fetched by
+                            consistent_depth_loss (utils_lr.py:369-458).  Needs exact_coords != 1, no want_src_grad,
+                            no x_is_logit */
   void* ev_main_begin;   /* optional cudaEvent_t pair recorded on `stream` immediately around the fused  */
   void* ev_main_end;     /* loss kernel (launch 3 of the step) so a caller can time it in situ; NULL = off */
 } VslLossDesc;
@@ -203,6 +209,18 @@ int vsl_loss_fwd_bwd_u8(const VslLossDesc* d,
                         const float* const* logits_pyr, const float* const* mask_pyr,
                         float* losses, float* const* g_x_pyr, float* g_poses, float* const* g_logits_pyr,
                         void* ws, vsl_stream_t stream);
+
+/* The step with the depth-consistency term (d->consist_weight > 0): src_x_pyr[v * S + s] is source view v's own
+ * network output at scale s, [B,Hs,Ws,1] (its depth map is x or 1/x as d->depth_is_inverse says, like the
+ * target's); the prep launch lays it into the fourth channel of that view's RGBA level, so the consistency fetch
+ * is part of the 16-byte gathers the photometric term issues anyway.  g_src_x_pyr (nullable, same layout): the
+ * gradient w.r.t. src_x_pyr (atomic scatter, like g_srcs).  losses[3] = the consistency term. */
+int vsl_loss_consist_fwd_bwd(const VslLossDesc* d, const float* tgt, const float* const* srcs,
+                             const float* const* x_pyr, const float* const* src_x_pyr /*host array V*S*/,
+                             const float* poses, const float* K_pyr, const float* const* logits_pyr,
+                             const float* const* mask_pyr, float* losses, float* const* g_x_pyr,
+                             float* const* g_src_x_pyr /*host array V*S, nullable*/, float* g_poses,
+                             float* const* g_logits_pyr, void* ws, vsl_stream_t stream);
 
 /* ---- upstream gradient of the summed loss: dst[0..n) = src[0..n) * (*num / *den) (num, den: device floats; den
  *      NULL means 1).  What TF autodiff does with the incoming gradient of `total_loss` in the reference

@@ -336,18 +336,23 @@ class LossFlags(object):
         self.pixel_scale_norm = True        # data_weight/2^s (train.py:135) vs not (train_depth_then_cam_lr.py:310)
         self.depth_is_inverse = True        # warp depth = 1/x (train.py:128) vs x
         self.smooth_on_inverse = False      # smooth(1/x) (train_depth_then_cam_lr.py:217) vs smooth(x) (train.py:108)
+        self.consist_weight = 0.0           # FLAGS.depth_weight on the consistency term (train_depth_then_cam_lr.py:339-340)
         self.__dict__.update(kw)
 
 
-def view_synthesis_loss(tgt, srcs, x_pyr, poses, K_pyr, logits_pyr=None, mask_pyr=None, flags=None):
+def view_synthesis_loss(tgt, srcs, x_pyr, poses, K_pyr, logits_pyr=None, mask_pyr=None, flags=None, src_x_pyr=None):
     """Per-scale loop of train.py:107-135 with the exp-mask of train_depth_then_cam_lr.py:297-328.
 
     tgt [B,H,W,3]; srcs: list of V [B,H,W,3]; x_pyr: list of S network outputs [B,Hs,Ws,1];
     poses [B,V,6] or [B,V,4,4]; K_pyr [B,S,3,3]; logits_pyr: list of S [B,Hs,Ws,2V] or None;
     mask_pyr: list of S constant weights [B,Hs,Ws,1] or None (train_optflow_combine.py:176,187).
-    -> (pixel_loss, smooth_loss, exp_loss)
+    src_x_pyr (with flags.consist_weight > 0): per source view its own S network outputs; adds the left-right
+    depth-consistency term of train_depth_then_cam_lr.py:336-340 (consistent_depth_loss on the warp's projected depth
+    and coordinates, weighted by the same mask as the photometric error).
+    -> (pixel_loss, smooth_loss, exp_loss) [+ (consist_loss,) with src_x_pyr]
     """
     f = flags or LossFlags()
+    consist = None
     B, H, W, _ = tgt.shape
     zero = torch.zeros((), dtype=tgt.dtype)
     pixel, smooth, exp = zero, zero, zero
@@ -360,17 +365,29 @@ def view_synthesis_loss(tgt, srcs, x_pyr, poses, K_pyr, logits_pyr=None, mask_py
         dw = f.data_weight / (2 ** s) if f.pixel_scale_norm else f.data_weight
         for v, src in enumerate(srcs):
             src_s = resize_area(src, hs, ws)
-            warped = projective_inverse_warp(src_s, depth, poses[:, v], K_pyr[:, s], f.pose_format)[0]
+            warped, coords, _, z_u, _ = projective_inverse_warp(src_s, depth, poses[:, v], K_pyr[:, s], f.pose_format)
             err = torch.abs(warped - tgt_s)
+            cerr = None
+            if src_x_pyr is not None:
+                sx = src_x_pyr[v][s]
+                cerr = consistent_depth_loss(1.0 / sx if f.depth_is_inverse else sx, z_u, coords)
             if logits_pyr is not None:
                 lg = logits_pyr[s][..., 2 * v:2 * v + 2]
                 if f.explain_reg_weight > 0:
                     ref = get_reference_explain_mask(s, B, H, W, tgt.dtype)
                     exp = exp + f.explain_reg_weight * compute_exp_reg_loss(lg, ref)
                 err = err * torch.softmax(lg, dim=-1)[..., 1:2]
+                if cerr is not None:
+                    cerr = cerr * torch.softmax(lg, dim=-1)[..., 1:2]
             elif mask_pyr is not None:
                 err = err * mask_pyr[s]
+                if cerr is not None:
+                    cerr = cerr * mask_pyr[s]
             pixel = pixel + err.mean() * dw
+            if cerr is not None:
+                consist = cerr.mean() * f.consist_weight + (consist if consist is not None else 0.0)
+    if src_x_pyr is not None:
+        return pixel, smooth, exp, consist
     return pixel, smooth, exp
 
 

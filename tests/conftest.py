@@ -27,9 +27,8 @@ class Case(dict):
             raise AttributeError(k)
 
 
-@pytest.fixture(scope='session')
-def golden():
-    z = np.load(GOLDEN, allow_pickle=False)
+def _load_cases(path):
+    z = np.load(path, allow_pickle=False)
     cases = {}
     for key in z.files:
         case, name = key.split('/', 1)
@@ -42,6 +41,18 @@ def golden():
             v = torch.from_numpy(np.array(a))
         cases.setdefault(case, Case())[name] = v
     return cases
+
+
+@pytest.fixture(scope='session')
+def golden():
+    return _load_cases(GOLDEN)
+
+
+@pytest.fixture(scope='session')
+def golden_consist():
+    """tests/golden/consist_golden.npz: the left-right loss of train_depth_then_cam_lr.py:211-340 incl. the depth
+    consistency term, from the reference's own functions (tests/golden/make_golden_consist.py)."""
+    return _load_cases(os.path.join(ROOT, 'tests', 'golden', 'consist_golden.npz'))['lr_consist']
 
 
 def rel_err(a, b):

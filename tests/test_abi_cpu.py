@@ -61,7 +61,7 @@ def test_loss_descriptor_validation_and_workspace(lib):
     assert lib.vsl_loss_ws_bytes(ctypes.byref(bad)) == 0
     bad = _lib.VslLossDesc(32, 128, 416, 4, 5, 0, 1, 1, 1, 0, 1.0, 0.5, 0.2, 1.0)   # V > VSL_MAX_VIEWS
     assert lib.vsl_loss_ws_bytes(ctypes.byref(bad)) == 0
-    assert ctypes.sizeof(_lib.VslLossDesc) == 20 * 4 + 2 * 8
+    assert ctypes.sizeof(_lib.VslLossDesc) == 21 * 4 + 4 + 2 * 8   # 21 scalars, padding, 2 event handles
 
 
 def test_host_side_rejects_cpu_tensors_and_bad_shapes(lib):

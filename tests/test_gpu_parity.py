@@ -209,6 +209,122 @@ def test_fused_loss_golden(golden, exact):
         assert e <= 1e-4, (name, 'g_poses', e)
 
 
+def _consist_fn(tgt, srcs, xs, ps, K, lgs, sx, f):
+    total, losses = ops.view_synthesis_loss(tgt, srcs, xs, ps, K, logits_pyr=lgs, flags=f, src_x_pyr=sx)
+    assert losses.shape == (4,)
+    return [total, losses]
+
+
+def test_fused_consistency_term_golden(golden_consist):
+    """The left-right loss of train_depth_then_cam_lr.py:211-340 -- photometric + smoothness + mask regulariser + the
+    left-right depth-consistency term (:336-340) -- as TWO fused steps (one per warp direction, each one's source-depth
+    pyramid being the other one's prediction), against the reference-executed golden: loss terms 1e-5, pose
+    gradients 1e-4, per-pixel gradients 1e-4 away from the kinks.  d/d(pred) sums the direct path of one direction
+    and the scattered d/d(source depth) of the other."""
+    from tests.parity_util import lr_flags, lr_two_directions
+    c = golden_consist
+    flags = lr_flags(ops.LossFlags, c.flags)
+    S = flags.num_scales
+    (total, losses), L = lr_two_directions(_consist_fn, c, cu, flags)
+    total.backward()
+    for i, key in enumerate(('pixel', 'smooth', 'exp', 'consist')):
+        want = float(c[key + '_f64'])
+        assert abs(float(losses[i]) - want) <= 1e-5 * abs(want), (key, float(losses[i]), want)
+    assert abs(float(total.detach()) - sum(float(c[k + '_f64']) for k in ('pixel', 'smooth', 'exp', 'consist'))) <= 1e-4
+    assert rel_err(L['po_r'].grad, c.g_pose_right_f64) <= 1e-4, rel_err(L['po_r'].grad, c.g_pose_right_f64)
+    assert rel_err(L['po_l'].grad, c.g_pose_left_f64) <= 1e-4
+    preds = {'left': [c['pred_left%d' % s] for s in range(S)], 'right': [c['pred_right%d' % s] for s in range(S)]}
+    ok_l = smooth_pixels(c.image_left, [c.image_right], preds['left'], c.pose_right.unsqueeze(1), c.K_pyr, flags,
+                         src_x_pyr=[preds['right']])
+    ok_r = smooth_pixels(c.image_right, [c.image_left], preds['right'], c.pose_left.unsqueeze(1), c.K_pyr, flags,
+                         src_x_pyr=[preds['left']])
+    for s in range(S):
+        for side, ok, xs, lgs in (('left', ok_l, L['pl'], L['ll']), ('right', ok_r, L['pr'], L['lr'])):
+            m = ok[s][0]
+            assert m.float().mean() > 0.95, (side, s, float(m.float().mean()))
+            e = masked_rel_err(xs[s].grad, c['g_pred_%s%d_f64' % (side, s)], m.unsqueeze(3))
+            assert e <= 1e-4, ('g_pred', side, s, e)
+            e = masked_rel_err(lgs[s].grad, c['g_lg_%s%d_f64' % (side, s)], m.unsqueeze(3))
+            assert e <= 1e-4, ('g_lg', side, s, e)
+
+
+def test_fused_consistency_term_matches_unfused_ops_and_oracle():
+    """The consistency term inside the fused step == the reference-signature ops composed by hand
+    (projective_inverse_warp -> consistent_depth_loss -> mask -> mean) and == the float64 oracle, for two source views
+    at a ragged shape, with the explainability mask, a constant mask and no mask; depth = x and depth = 1/x."""
+    B, H, W, S, V = 2, 40, 104, 3, 2
+    d = synth.make_snippets(B, H, W, S=S, V=V, seed=41, motion=2.0)
+    g = torch.Generator().manual_seed(5)
+    src_x = [[(x + 0.1 * torch.rand(x.shape, generator=g)) for x in d['disp_pyr']] for _ in range(V)]
+    masks = [torch.rand(B, H >> s, W >> s, 1, generator=g) for s in range(S)]
+    for mode, inv in (('exp', True), ('const', False), ('none', True)):
+        kw = dict(num_scales=S, consist_weight=1.5, depth_is_inverse=inv, smooth_on_inverse=inv, pose_format='eular')
+        flags, of = ops.LossFlags(**kw), O.LossFlags(**kw)
+        xs = [cu(x, True) for x in d['disp_pyr']]
+        sx = [[cu(t, True) for t in p] for p in src_x]
+        ps = cu(d['poses'], True)
+        lgs = [cu(l, True) for l in d['logits_pyr']] if mode == 'exp' else None
+        mk = [cu(m) for m in masks] if mode == 'const' else None
+        tgt, srcs, Kp = cu(d['tgt']), [cu(s) for s in d['srcs']], cu(d['K_pyr'])
+        total, losses = ops.view_synthesis_loss(tgt, srcs, xs, ps, Kp, logits_pyr=lgs, mask_pyr=mk, flags=flags, src_x_pyr=sx)
+        total.backward()
+        # (a) the float64 oracle
+        oxs = [x.double().requires_grad_() for x in d['disp_pyr']]
+        osx = [[t.double().requires_grad_() for t in p] for p in src_x]
+        ops_ = d['poses'].double().requires_grad_()
+        ol = [l.double().requires_grad_() for l in d['logits_pyr']] if mode == 'exp' else None
+        ref = O.view_synthesis_loss(d['tgt'].double(), [s.double() for s in d['srcs']], oxs, ops_, d['K_pyr'].double(), ol,
+                                    [m.double() for m in masks] if mode == 'const' else None, of, src_x_pyr=osx)
+        sum(ref).backward()
+        for got, want in zip(losses.tolist(), ref):
+            assert abs(got - float(want)) <= 1e-5 * abs(float(want)) + 1e-9, (mode, got, float(want))
+        assert rel_err(ps.grad, ops_.grad) <= 1e-4, (mode, rel_err(ps.grad, ops_.grad))
+        ok = smooth_pixels(d['tgt'], d['srcs'], d['disp_pyr'], d['poses'], d['K_pyr'], flags, src_x_pyr=src_x)
+        for s in range(S):
+            m = torch.stack(ok[s]).all(0)
+            assert m.float().mean() > 0.95
+            assert masked_rel_err(xs[s].grad, oxs[s].grad, m.unsqueeze(3)) <= 1e-4, (mode, 'g_x', s)
+            for v in range(V):
+                # the scatter into the source depth has no per-pixel mask: a flipped sign lands on four source pixels
+                e = rel_err(sx[v][s].grad, osx[v][s].grad)
+                assert e <= 2e-4, (mode, 'g_src_x', v, s, e)
+        # (b) the stand-alone ops, reference call signatures
+        xs2 = [cu(x, True) for x in d['disp_pyr']]
+        sx2 = [[cu(t, True) for t in p] for p in src_x]
+        ps2 = cu(d['poses'], True)
+        sp = [ops.image_pyramid(s_, S) for s_ in srcs]
+        consist = 0
+        for s in range(S):
+            depth = (1.0 / xs2[s] if inv else xs2[s]).squeeze(3)
+            for v in range(V):
+                _, coords, _, z_u, _ = ops.projective_inverse_warp(sp[v][s], depth, ps2[:, v].contiguous(),
+                                                                   Kp[:, s].contiguous(), 'eular')
+                err = ops.consistent_depth_loss(1.0 / sx2[v][s] if inv else sx2[v][s], z_u, coords)
+                if mode == 'exp':
+                    err = err * torch.softmax(lgs[s].detach()[..., 2 * v:2 * v + 2], -1)[..., 1:2]
+                elif mode == 'const':
+                    err = err * mk[s]
+                consist = consist + err.mean() * flags.consist_weight
+        assert abs(float(losses[3]) - float(consist)) <= 1e-5 * abs(float(consist)), (mode, float(losses[3]), float(consist))
+
+
+def test_consistency_entry_argument_checks():
+    """src_x_pyr and flags.consist_weight go together; shapes are checked before the C call; the combinations the
+    kernel does not implement are refused loudly."""
+    B, H, W, S, V = 1, 16, 32, 2, 1
+    d = synth.make_snippets(B, H, W, S=S, V=V, seed=2)
+    a = (cu(d['tgt']), [cu(s) for s in d['srcs']], [cu(x) for x in d['disp_pyr']], cu(d['poses']), cu(d['K_pyr']))
+    sx = [[cu(x) for x in d['disp_pyr']]]
+    with pytest.raises(ValueError):
+        ops.view_synthesis_loss(*a, flags=ops.LossFlags(num_scales=S), src_x_pyr=sx)
+    with pytest.raises(ValueError):
+        ops.view_synthesis_loss(*a, flags=ops.LossFlags(num_scales=S, consist_weight=1.0))
+    with pytest.raises(ValueError):
+        ops.view_synthesis_loss(*a, flags=ops.LossFlags(num_scales=S, consist_weight=1.0), src_x_pyr=[sx[0][::-1]])
+    with pytest.raises(ValueError):
+        ops.view_synthesis_loss(*a, flags=ops.LossFlags(num_scales=S, consist_weight=1.0, exact_coords=True), src_x_pyr=sx)
+
+
 def test_fused_exact_mode_matches_standalone_warp_bitwise(golden):
     """exact_coords=True: the fused kernel's photometric term is built from the same rounded operations as the
     stand-alone warp, so with smoothing / regulariser off its pixel loss equals mean|warp - tgt| computed from

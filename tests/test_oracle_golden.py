@@ -143,6 +143,27 @@ def test_composite_loss(golden):
             assert rel_err(grads[S], c['g_poses_' + tag]) <= tol
 
 
+def test_lr_loss_with_consistency_term(golden_consist):
+    """The oracle's step with the depth-consistency term, called once per warp direction, reproduces the
+    reference-executed left-right loss of train_depth_then_cam_lr.py:211-340 (values and every gradient)."""
+    from tests.parity_util import lr_flags, lr_two_directions
+    c = golden_consist
+    flags = lr_flags(O.LossFlags, c.flags)
+    S = flags.num_scales
+    for dt, tag, tol in ((torch.float32, 'f32', 2e-6), (torch.float64, 'f64', 1e-12)):
+        fn = lambda tgt, srcs, xs, ps, K, lgs, sx, f: O.view_synthesis_loss(tgt, srcs, xs, ps, K, lgs, None, f, src_x_pyr=sx)
+        terms, L = lr_two_directions(fn, c, lambda t, g: t.to(dt).requires_grad_(g), flags)
+        for t, key in zip(terms, ('pixel', 'smooth', 'exp', 'consist')):
+            assert rel_err(t, c['%s_%s' % (key, tag)]) <= tol, (key, tag)
+        wrt = L['pl'] + L['pr'] + [L['po_r'], L['po_l']] + L['ll'] + L['lr']
+        grads = torch.autograd.grad(sum(terms), wrt)
+        names = (['g_pred_left%d' % s for s in range(S)] + ['g_pred_right%d' % s for s in range(S)] +
+                 ['g_pose_right', 'g_pose_left'] + ['g_lg_left%d' % s for s in range(S)] +
+                 ['g_lg_right%d' % s for s in range(S)])
+        for g, n in zip(grads, names):
+            assert rel_err(g, c['%s_%s' % (n, tag)]) <= tol, (n, tag)
+
+
 def test_depth_loss_golden_file_is_consistent():
     """tests/golden/depth_losses_golden.npz (the reference's compute_loss_single_depth body executed over the shim)
     against a direct restatement from the oracle's building blocks: pins the fixture and oracle/demon_ops.py."""

@@ -39,24 +39,6 @@
 
 namespace vsl {
 
-// switches of the fast arithmetic's shortcuts (timing experiments: -DVSL_T_FOLD=0 ...)
-#ifndef VSL_T_FOLD
-#define VSL_T_FOLD 1
-#endif
-#ifndef VSL_T_SMOOTH
-#define VSL_T_SMOOTH 1
-#endif
-#ifndef VSL_T_LERP
-#define VSL_T_LERP 1
-#endif
-#ifndef VSL_T_LOGPROD
-#define VSL_T_LOGPROD 1
-#endif
-#ifndef VSL_T_INVD
-#define VSL_T_INVD 1
-#endif
-constexpr bool kTFold = VSL_T_FOLD, kTSmooth = VSL_T_SMOOTH, kTLerp = VSL_T_LERP, kTLogProd = VSL_T_LOGPROD, kTInvD = VSL_T_INVD;
-
 // timing experiment (wrong results): VSL_EXP_TIMELINE makes every warp record %globaltimer at the stages of its
 // tile; the stamps replace the tile's partial sums (profiles/run_fused.py reads them back from the workspace)
 #ifdef VSL_EXP_TIMELINE
@@ -70,6 +52,7 @@ struct Tap {
   float4 A, B, C, D;             // corners (x0,y0) (x1,y0) (x0,y1) (x1,y1)
   float wx0, wx1, wy0, wy1;      // (x1 - x), (x - x0), (y1 - y), (y - y0)
   float qx, qy, rz;              // projected coordinates (unclamped) and 1 / (z + eps)
+  float zu;                      // z itself: the source-frame depth the consistency term compares (fast arithmetic)
   int off;                       // float4 offset of corner A inside the level (kept for the d/d(source) scatter)
 };
 
@@ -84,18 +67,13 @@ VSL_DEV void tap_issue(Tap& t, const float (&p)[12], float c0, float c1, float c
   if (EXACT) {
     const Proj q = project(p, c0, c1, c2);
     t.qx = q.x; t.qy = q.y; t.rz = 1.0f / q.zp;
-  } else if (kTFold) {
+  } else {
     const float u0 = fmaf(d, fmaf(gy, qy[0], a[0]), p[3]);
     const float u1 = fmaf(d, fmaf(gy, qy[1], a[1]), p[7]);
     const float u2 = fmaf(d, fmaf(gy, qy[2], a[2]), p[11]);
     t.rz = rcp_fast(u2 + kEpsZ);
     t.qx = u0 * t.rz; t.qy = u1 * t.rz;
-  } else {
-    const float u0 = fmaf(p[0], c0, fmaf(p[1], c1, fmaf(p[2], c2, p[3])));
-    const float u1 = fmaf(p[4], c0, fmaf(p[5], c1, fmaf(p[6], c2, p[7])));
-    const float u2 = fmaf(p[8], c0, fmaf(p[9], c1, fmaf(p[10], c2, p[11])));
-    t.rz = rcp_fast(u2 + kEpsZ);
-    t.qx = u0 * t.rz; t.qy = u1 * t.rz;
+    t.zu = u2;
   }
   // beyond [-2, size] all four corners are border zeros; clamping there changes neither value nor gradient
   const float xc = fminf(fmaxf(t.qx, -2.0f), Wf), yc = fminf(fmaxf(t.qy, -2.0f), Hf);
@@ -122,12 +100,19 @@ VSL_DEV void tap_issue(Tap& t, const float (&p)[12], float c0, float c1, float c
 //                d(depth) = -<du, t> / depth; differs from EXACT by a few ulp per quantity.
 // DSRC = true additionally scatters d/d(source levels) with 16-byte reductions (red.global.add.v4.f32) into
 // gradient levels of the same zero-bordered RGBA layout; loss_fold_src_grad_kernel folds them back to level 0.
-template <int V, bool EXACT, bool DSRC>
+// CONS = true (fast arithmetic only) adds the left-right depth-consistency term of train_depth_then_cam_lr.py:336-340
+// from the SAME gather: the source view's depth map rides in the fourth channel of its RGBA levels (written by the
+// prep launch), so consistent_depth_loss' bilinear fetch (utils_lr.py:369-458) is one more blend of values that are
+// already in registers: |z - sampled| * mask, its gradient w.r.t. the coordinates (through the sampler) and w.r.t. z
+// join d/du, the mask's share joins d/dlogits, and d/d(source depth) is scattered with 4 float reductions into a
+// zero-bordered plane of the same geometry (loss_crop_src_depth_grad_kernel returns its interior).
+template <int V, bool EXACT, bool DSRC, bool CONS = false>
 // the exact mode (IEEE divisions, expf / logf, unfused sequences) needs ~170 registers: one block less per SM
 // beats spilling
-__global__ void __launch_bounds__(kThreads, (V <= 2 ? (EXACT ? VSL_FUSED_MIN_BLOCKS - 1 : VSL_FUSED_MIN_BLOCKS)
+__global__ void __launch_bounds__(kThreads, (V <= 2 ? (EXACT || CONS ? VSL_FUSED_MIN_BLOCKS - 1 : VSL_FUSED_MIN_BLOCKS)
                                                       : VSL_FUSED_MIN_BLOCKS / 2))
 loss_fused_kernel(const LossParams P) {
+  static_assert(!CONS || (!EXACT && !DSRC), "the consistency term rides on the fast arithmetic");
   constexpr int N = NT<V>::value;
   using L = WarpSmem<V, EXACT>;
   extern __shared__ float4 smem4[];
@@ -217,7 +202,8 @@ loss_fused_kernel(const LossParams P) {
   }
   __syncwarp();
 
-  float pix_sum = 0.f, exp_sum = 0.f, sm_sum = 0.f;
+  float pix_sum = 0.f, exp_sum = 0.f, sm_sum = 0.f, con_sum = 0.f;
+  const float ccon = CONS ? P.ccon[s] : 0.f;
   float se_prod[V];                 // fast arithmetic: running product of the softmax denominators, per view
 #pragma unroll
   for (int v = 0; v < V; ++v) se_prod[v] = 1.f;
@@ -283,8 +269,6 @@ loss_fused_kernel(const LossParams P) {
   float kx0 = 0.f, kx1 = 0.f, kx2 = 0.f;
   if (EXACT) {
     kx0 = __fmul_rn(k0.x, gx); kx1 = __fmul_rn(k1.x, gx); kx2 = __fmul_rn(k2.x, gx);
-  } else if (!kTFold) {
-    kx0 = fmaf(k0.x, gx, k0.z); kx1 = fmaf(k1.x, gx, k1.z); kx2 = fmaf(k2.x, gx, k2.z);
   }
   // fast arithmetic: the folded projection of tap_issue -- per view Q[i][1] (uniform) and Q[i][0] gx + Q[i][2] (lane)
   float Qy[V][3], Al[V][3];
@@ -292,7 +276,7 @@ loss_fused_kernel(const LossParams P) {
   for (int v = 0; v < V; ++v)
 #pragma unroll
     for (int i = 0; i < 3; ++i) { Qy[v][i] = 0.f; Al[v][i] = 0.f; }
-  if (!EXACT && kTFold) {
+  if (!EXACT) {
 #pragma unroll
     for (int v = 0; v < V; ++v) {
       const float* xq = reinterpret_cast<const float*>(P.xq + ((size_t)s * V + v) * P.B + b);
@@ -370,14 +354,9 @@ loss_fused_kernel(const LossParams P) {
       g.r2 = __fadd_rn(__fadd_rn(kx2, __fmul_rn(k2.y, gy)), k2.z);
       g.c0 = __fmul_rn(g.r0, g.d); g.c1 = __fmul_rn(g.r1, g.d); g.c2 = __fmul_rn(g.r2, g.d);
       g.dgy = g.d * gy;
-    } else if (kTFold) {   // the ray is folded into the per-view projection (tap_issue); the row coordinate comes from the table
+    } else {      // the ray is folded into the per-view projection (tap_issue); the row coordinate comes from the table
       g.gy = rtv[3 * r];
       g.dgy = g.d * g.gy;
-    } else {
-      const float gy = grid_coord(y_base + r, H, hstep);
-      g.r0 = fmaf(k0.y, gy, kx0); g.r1 = fmaf(k1.y, gy, kx1); g.r2 = fmaf(k2.y, gy, kx2);
-      g.c0 = __fmul_rn(g.r0, g.d); g.c1 = __fmul_rn(g.r1, g.d); g.c2 = __fmul_rn(g.r2, g.d);
-      g.dgy = g.d * gy;
     }
   };
 
@@ -386,7 +365,9 @@ loss_fused_kernel(const LossParams P) {
   // request the next row's streamed operands.  Phase 2 (softmax, gradients, accumulation, stores: over half
   // of the row's arithmetic) touches nothing in flight -- so whichever hardware scoreboards the compiler lets
   // these load groups share, no wait ever lands on a load that was only just issued.
-  struct Keep { float E, u0, u1, u2; };         // what phase 2 needs of a view: sum|e| and dL/du up to the factor cpix * m
+  // what phase 2 needs of a view: sum|e| and dL/du up to the factor cpix * m (CONS: up to the factor m; Cz = |z - sampled
+  // source depth|, gz = ccon * sign(z - sampled) * z, the <du, u> the closed form of d/d(depth) otherwise lacks)
+  struct Keep { float E, u0, u1, u2, Cz, gz; };
   Tap tap[V];
   int pofs = pix0 + y_base * W + xl;            // pixel index inside the level
 
@@ -401,14 +382,14 @@ loss_fused_kernel(const LossParams P) {
       // allocator hands those registers to the very next instructions after the loads are issued, and the
       // write-after-write hazard then stalls the warp for the full memory latency.  OR-ing them into the
       // running |e| sum (a no-op on the value) keeps them reserved until the data is consumed: 2 LOP3 per view.
-      const unsigned pad = __float_as_uint(t.A.w) | __float_as_uint(t.B.w) | __float_as_uint(t.C.w) |
-                           __float_as_uint(t.D.w);
+      const unsigned pad = CONS ? 0u : (__float_as_uint(t.A.w) | __float_as_uint(t.B.w) | __float_as_uint(t.C.w) |
+                                        __float_as_uint(t.D.w));   // CONS: the fourth channel is data and is consumed
       const float cA[3] = {t.A.x, t.A.y, t.A.z}, cB[3] = {t.B.x, t.B.y, t.B.z},
                   cC[3] = {t.C.x, t.C.y, t.C.z}, cD[3] = {t.D.x, t.D.y, t.D.z};
       // E = sum_c |e_c|; J_k = sum_c sign(e_c) * corner_k[c]  (the channel sum commutes with d/dx, d/dy)
       // EXACT: the reference's four products.  Fast: one product, w11 = wx1 wy1, then w10 = wx1 - w11,
       // w01 = wy1 - w11, w00 = (1 - wx1) - w01
-      constexpr bool kProd = EXACT || !kTLerp;
+      constexpr bool kProd = EXACT;
       const float wx0 = EXACT ? t.wx0 : 1.0f - t.wx1, wy0 = EXACT ? t.wy0 : (kProd ? 1.0f - t.wy1 : 0.f);
       const float w11 = __fmul_rn(t.wx1, t.wy1);
       const float w10 = kProd ? __fmul_rn(t.wx1, wy0) : t.wx1 - w11, w01 = kProd ? __fmul_rn(wx0, t.wy1) : t.wy1 - w11;
@@ -464,9 +445,35 @@ loss_fused_kernel(const LossParams P) {
         dx = fmaf(t.wy1, (JD - JC) - ax, ax);
         dy = fmaf(t.wx1, (JD - JB) - ay, ay);
       }
-      // the border zeros make the sampler's corner masks implicit: an outside corner contributes 0
-      keep[v].E = E; keep[v].u0 = dx * t.rz; keep[v].u1 = dy * t.rz;
-      keep[v].u2 = -(t.qx * keep[v].u0 + t.qy * keep[v].u1);
+      if (CONS) {
+        // consistent_depth_loss: sampled = bilinear(source depth) at the same corners, err = |z - sampled|
+        const float sw = fmaf(w11, t.D.w, fmaf(w10, t.B.w, fmaf(w01, t.C.w, w00 * t.A.w)));
+        const float ec = t.zu - sw;
+        const float sc = sign_fast(ec) * ccon;                       // ccon * sign(z - sampled)
+        const float axw = t.B.w - t.A.w, ayw = t.C.w - t.A.w;
+        const float dxw = fmaf(t.wy1, (t.D.w - t.C.w) - axw, axw), dyw = fmaf(t.wx1, (t.D.w - t.B.w) - ayw, ayw);
+        dx = fmaf(cpix, dx, -sc * dxw);                              // d/dx of (cpix E + ccon err) / m
+        dy = fmaf(cpix, dy, -sc * dyw);
+        keep[v].Cz = fabsf(ec);
+        keep[v].gz = sc * t.zu;
+        if (P.gsd[v][s] != nullptr && act) {
+          // d/d(source depth corner k) = -ccon m sign w_k; the mask value is needed here already
+          float m = cur.mc;
+          if (use_lg) m = rcp_fast(1.f + ex2_fast(1.4426950408889634f * (cur.lg[2 * v] - cur.lg[2 * v + 1])));
+          const float km = -sc * m;
+          float* g = P.gsd[v][s] + t.off;
+          asm volatile("red.global.add.f32 [%0], %1;" ::"l"(g), "f"(km * w00) : "memory");
+          asm volatile("red.global.add.f32 [%0], %1;" ::"l"(g + 1), "f"(km * w10) : "memory");
+          asm volatile("red.global.add.f32 [%0], %1;" ::"l"(g + stride4), "f"(km * w01) : "memory");
+          asm volatile("red.global.add.f32 [%0], %1;" ::"l"(g + stride4 + 1), "f"(km * w11) : "memory");
+        }
+        keep[v].E = E; keep[v].u0 = dx * t.rz; keep[v].u1 = dy * t.rz;
+        keep[v].u2 = sc - (t.qx * keep[v].u0 + t.qy * keep[v].u1);    // + d/dz of the consistency term
+      } else {
+        // the border zeros make the sampler's corner masks implicit: an outside corner contributes 0
+        keep[v].E = E; keep[v].u0 = dx * t.rz; keep[v].u1 = dy * t.rz;
+        keep[v].u2 = -(t.qx * keep[v].u0 + t.qy * keep[v].u1);
+      }
       if (has_next)
         tap_issue<EXACT>(t, Pm[v], gn.c0, gn.c1, gn.c2, Al[v], Qy[v], gn.d, gn.gy, P.src[v][s], stride4, coff, Wf, Hf);
     }
@@ -490,7 +497,7 @@ loss_fused_kernel(const LossParams P) {
     float g_q;
     {
       float a0, b0, c00;
-      if (EXACT || !kTSmooth) {
+      if (EXACT) {
         float sm;
         owner_signs<EXACT>(qt + (r + kHalo) * kQS + lane + kHalo, (unsigned)x, (unsigned)(y_base + r), H, W, cxx, cxy, cyx,
                            cyy, a0, b0, c00, sm);
@@ -539,15 +546,12 @@ loss_fused_kernel(const LossParams P) {
           p1 = z >= 0.f ? small : big;
           // log(1 + e^-|z|) + max(z, 0); the logarithms of a tile are taken once, of the product of its 1 + e^-|z|
           // (at most 2^kRH per view: no overflow; 1e-7 relative on the sum)
-          if (kTLogProd) {
-            se_prod[v] *= se;
-            exp_sum += fmaxf(z, 0.f);
-          } else {
-            exp_sum += fmaf(lg2_fast(se), 0.6931471805599453f, fmaxf(z, 0.f));
-          }
+          se_prod[v] *= se;
+          exp_sum += fmaxf(z, 0.f);
         }
         mv[v] = p1;
-        const float g0 = p0 * (cexp - cpix * keep[v].E * p1);
+        // d/dm of the mask-weighted terms: cpix E (+ ccon |z - sampled|)
+        const float g0 = p0 * (cexp - (CONS ? fmaf(ccon, keep[v].Cz, cpix * keep[v].E) : cpix * keep[v].E) * p1);
         cur.lg[2 * v] = g0; cur.lg[2 * v + 1] = -g0;
       }
     } else {
@@ -559,7 +563,8 @@ loss_fused_kernel(const LossParams P) {
     for (int v = 0; v < V; ++v) {
       const float m = mv[v];
       pix_sum = fmaf(m, keep[v].E, pix_sum);
-      const float k = cpix * m;
+      if (CONS) con_sum = fmaf(m, keep[v].Cz, con_sum);
+      const float k = CONS ? m : cpix * m;         // CONS: cpix / ccon already sit in u0..u2
       const float du0 = keep[v].u0 * k, du1 = keep[v].u1 * k, du2 = keep[v].u2 * k;
       const float* pp = Pm[v];
       if (EXACT) {
@@ -568,7 +573,8 @@ loss_fused_kernel(const LossParams P) {
         const float gc2 = du0 * pp[2] + du1 * pp[6] + du2 * pp[10];
         g_d += gc0 * gc.r0 + gc1 * gc.r1 + gc2 * gc.r2;
       } else {
-        g_d -= du0 * pp[3] + du1 * pp[7] + du2 * pp[11];  // <du, M ray> = <du, u - t> / d and <du, u> = 0
+        g_d -= du0 * pp[3] + du1 * pp[7] + du2 * pp[11];  // <du, M ray> = <du, u - t> / d and <du, u> = 0 ...
+        if (CONS) g_d = fmaf(m, keep[v].gz, g_d);         // ... but for d/dz of the consistency term: <du, u> = g_z z
       }
       S2[v][0] = fmaf(du0, gc.dgy, S2[v][0]); S2[v][1] = fmaf(du1, gc.dgy, S2[v][1]); S2[v][2] = fmaf(du2, gc.dgy, S2[v][2]);
       S3[v][0] = fmaf(du0, gc.d, S3[v][0]);   S3[v][1] = fmaf(du1, gc.d, S3[v][1]);   S3[v][2] = fmaf(du2, gc.d, S3[v][2]);
@@ -576,7 +582,7 @@ loss_fused_kernel(const LossParams P) {
     }
     if (!EXACT) {
       // d = 1 / x (and the tile holds x): 1 / d is the tile value itself, no reciprocal
-      const float inv_d = (kTInvD && depth_inv && !smooth_inv) ? qt[(r + kHalo) * kQS + (xl - x_base) + kHalo] : rcp_fast(gc.d);
+      const float inv_d = (depth_inv && !smooth_inv) ? qt[(r + kHalo) * kQS + (xl - x_base) + kHalo] : rcp_fast(gc.d);
       g_d *= inv_d;
     }
     if (act) {
@@ -639,13 +645,13 @@ loss_fused_kernel(const LossParams P) {
   VSL_STAMP(6);
   // ---- 4. one warp reduction per tile: 3 loss sums + per view (gx sum du d, sum du d gy, sum du d, sum du)
   float vals[N];
-  if (!EXACT && kTLogProd) {
+  if (!EXACT) {
 #pragma unroll
     for (int v = 0; v < V; ++v) exp_sum = fmaf(lg2_fast(se_prod[v]), 0.6931471805599453f, exp_sum);
   }
   vals[0] = pix_sum * cpix; vals[1] = sm_sum; vals[2] = exp_sum * cexp;
-  vals[3] = 0.f;                    // consistency term (slot reserved)
-  if (!act) { vals[0] = 0.f; vals[1] = 0.f; vals[2] = 0.f; }   // lanes past the image edge recomputed the last column
+  vals[3] = CONS ? con_sum * ccon : 0.f;
+  if (!act) { vals[0] = 0.f; vals[1] = 0.f; vals[2] = 0.f; vals[3] = 0.f; }   // lanes past the image edge recomputed the last column
 #pragma unroll
   for (int v = 0; v < V; ++v)
 #pragma unroll
@@ -840,6 +846,10 @@ struct PrepImgJob {
   float* tgt_lvl[VSL_MAX_SCALES];                   // RGB levels; [0] = the float32 target, written only for uint8 images
   float img_div, img_sub;                           // uint8 images: value = (float)u8 / img_div - img_sub
   float4* src_lvl[VSL_MAX_VIEWS][VSL_MAX_SCALES];   // zero-bordered RGBA levels
+  // consistency term: source view v's own network output at scale s ([B,Hs,Ws,1], nullable); its depth map (x, or 1/x
+  // with src_x_inverse) becomes the fourth channel of src_lvl[v][s]
+  const float* src_x[VSL_MAX_VIEWS][VSL_MAX_SCALES];
+  int src_x_inverse;
   int V, B, H, W, S;
   int tiles_x, tiles_y, n_tiles;                    // per image; n_tiles = (V + 1) * B * tiles_y * tiles_x
   int n_blocks;                                     // persistent blocks of the launch
@@ -848,12 +858,23 @@ struct PrepImgJob {
 
 __host__ __device__ constexpr int ilog2(int v) { return v <= 1 ? 0 : 1 + ilog2(v >> 1); }
 
+// fourth channel of a source level: zero padding, or the source view's depth map (consistency term)
+struct WChan {
+  const float* p;      // element (0, 0) of the tile inside the view's [B,Hs,Ws,1] level; nullptr = zeros
+  int stride, inverse;
+  VSL_DEV float at(int oy, int ox) const {
+    if (p == nullptr) return 0.f;
+    const float v = __ldg(p + oy * stride + ox);
+    return inverse ? __fdiv_rn(1.0f, v) : v;
+  }
+};
+
 // All elements of level SHIFT >= 3 that this tile covers: one float per (virtual) thread per step over a
 // (pixel, 4) grid whose sides are powers of two (shifts only); RGB output leaves the 4th lane of a pixel idle.
 // The caller hands this to the threads that are not busy with levels 1 and 2 (t = their index, nt = how many).
 template <int SHIFT, int TW, int RB, bool C4>
 VSL_DEV void prep_level(const float* tile, int rows, int cols, float* __restrict__ dst, int dst_row_stride, int t,
-                        int nt) {
+                        int nt, const WChan wc) {
   constexpr int f = 1 << SHIFT, C = C4 ? 4 : 3;
   constexpr int OW = TW >> SHIFT, OH = RB >> SHIFT;    // output pixels of a full tile
   constexpr int LOG2OW = ilog2(OW);
@@ -864,7 +885,9 @@ VSL_DEV void prep_level(const float* tile, int rows, int cols, float* __restrict
     const int oy = px >> LOG2OW, ox = px & (OW - 1);
     if (oy >= oh || ox >= ow || (!C4 && c == 3)) continue;
     float out = 0.f;
-    if (c < 3) {
+    if (c == 3) {
+      out = wc.at(oy, ox);
+    } else {
       const float* p = tile + (oy << SHIFT) * (TW * 3) + (ox << SHIFT) * 3 + c;
       float acc = 0.f;
 #pragma unroll
@@ -883,7 +906,8 @@ VSL_DEV void prep_level(const float* tile, int rows, int cols, float* __restrict
 // Levels 1 and 2, one output PIXEL per thread with 8- / 16-byte shared-memory loads (the 2 x 3 or 4 x 3 floats of
 // a contributing row are contiguous).  Level 1 has exactly kPrepThreads pixels per full tile, level 2 a quarter.
 template <int SHIFT, int TW, int RB, bool C4>
-VSL_DEV void prep_level12(const float* tile, int rows, int cols, float* __restrict__ dst, int dst_row_stride, int t) {
+VSL_DEV void prep_level12(const float* tile, int rows, int cols, float* __restrict__ dst, int dst_row_stride, int t,
+                          const WChan wc) {
   static_assert(SHIFT == 1 || SHIFT == 2, "vector path covers levels 1 and 2");
   constexpr int f = 1 << SHIFT, OW = TW >> SHIFT, OH = RB >> SHIFT, LOG2OW = ilog2(OW);
   if (t >= OW * OH) return;
@@ -918,29 +942,30 @@ VSL_DEV void prep_level12(const float* tile, int rows, int cols, float* __restri
   const float scale = 1.0f / (float)(f * f);
   float* d = dst + oy * dst_row_stride + ox * (C4 ? 4 : 3);
   if (C4) {
-    *reinterpret_cast<float4*>(d) = make_float4(__fmul_rn(acc[0], scale), __fmul_rn(acc[1], scale), __fmul_rn(acc[2], scale), 0.f);
+    *reinterpret_cast<float4*>(d) = make_float4(__fmul_rn(acc[0], scale), __fmul_rn(acc[1], scale), __fmul_rn(acc[2], scale),
+                                                wc.at(oy, ox));
   } else {
     d[0] = __fmul_rn(acc[0], scale); d[1] = __fmul_rn(acc[1], scale); d[2] = __fmul_rn(acc[2], scale);
   }
 }
 
 // Every level of one staged tile.  Level 1: all threads.  Level 2: the first quarter.  Levels >= 3: the rest.
-template <int LOG2F, int TW, int RB, bool C4, typename DstOf>
-VSL_DEV void prep_levels(const float* tile, int rows, int cols, DstOf dst_of) {
+template <int LOG2F, int TW, int RB, bool C4, typename DstOf, typename WOf>
+VSL_DEV void prep_levels(const float* tile, int rows, int cols, DstOf dst_of, WOf w_of) {
   const int t = threadIdx.x;
   constexpr int n2 = (TW >> 2) * (RB >> 2);
-  if constexpr (LOG2F >= 1) { int st; float* d = dst_of(1, st); prep_level12<1, TW, RB, C4>(tile, rows, cols, d, st, t); }
-  if constexpr (LOG2F >= 2) { int st; float* d = dst_of(2, st); prep_level12<2, TW, RB, C4>(tile, rows, cols, d, st, t); }
+  if constexpr (LOG2F >= 1) { int st; float* d = dst_of(1, st); prep_level12<1, TW, RB, C4>(tile, rows, cols, d, st, t, w_of(1)); }
+  if constexpr (LOG2F >= 2) { int st; float* d = dst_of(2, st); prep_level12<2, TW, RB, C4>(tile, rows, cols, d, st, t, w_of(2)); }
   if (t >= n2) {
-    if constexpr (LOG2F >= 3) { int st; float* d = dst_of(3, st); prep_level<3, TW, RB, C4>(tile, rows, cols, d, st, t - n2, kPrepThreads - n2); }
-    if constexpr (LOG2F >= 4) { int st; float* d = dst_of(4, st); prep_level<4, TW, RB, C4>(tile, rows, cols, d, st, t - n2, kPrepThreads - n2); }
-    if constexpr (LOG2F >= 5) { int st; float* d = dst_of(5, st); prep_level<5, TW, RB, C4>(tile, rows, cols, d, st, t - n2, kPrepThreads - n2); }
+    if constexpr (LOG2F >= 3) { int st; float* d = dst_of(3, st); prep_level<3, TW, RB, C4>(tile, rows, cols, d, st, t - n2, kPrepThreads - n2, w_of(3)); }
+    if constexpr (LOG2F >= 4) { int st; float* d = dst_of(4, st); prep_level<4, TW, RB, C4>(tile, rows, cols, d, st, t - n2, kPrepThreads - n2, w_of(4)); }
+    if constexpr (LOG2F >= 5) { int st; float* d = dst_of(5, st); prep_level<5, TW, RB, C4>(tile, rows, cols, d, st, t - n2, kPrepThreads - n2, w_of(5)); }
   }
 }
 
 // Level 0 of a source as RGBA: one pixel per thread per step, a 16-byte store per pixel.
 template <int TW, int RB>
-VSL_DEV void prep_rgba0(const float* tile, int rows, int cols, float4* __restrict__ dst, int dst_row_stride4) {
+VSL_DEV void prep_rgba0(const float* tile, int rows, int cols, float4* __restrict__ dst, int dst_row_stride4, const WChan wc) {
   constexpr int LOG2TW = TW == 32 ? 5 : TW == 64 ? 6 : 7;
   static_assert((1 << LOG2TW) == TW, "tile width must be 32, 64 or 128");
 #pragma unroll
@@ -949,7 +974,7 @@ VSL_DEV void prep_rgba0(const float* tile, int rows, int cols, float4* __restric
     const int y = px >> LOG2TW, x = px & (TW - 1);
     if (y < rows && x < cols) {
       const float* p = tile + y * (TW * 3) + x * 3;
-      dst[(size_t)y * dst_row_stride4 + x] = make_float4(p[0], p[1], p[2], 0.f);
+      dst[(size_t)y * dst_row_stride4 + x] = make_float4(p[0], p[1], p[2], wc.at(y, x));
     }
   }
 }
@@ -1130,7 +1155,7 @@ loss_prep_kernel(const PrepImgJob job, const PrepJob prep) {
         const int Hs = H >> sh, Ws = W >> sh;
         stride = Ws * 3;
         return job.tgt_lvl[sh] + (size_t)(((b * Hs + (y0 >> sh)) * Ws + (x0 >> sh)) * 3);
-      });
+      }, [](int) { return WChan{nullptr, 0, 0}; });
     } else {
       const int v = cur.im - 1;
       auto dst_of = [&](int sh, int& stride) {
@@ -1139,10 +1164,15 @@ loss_prep_kernel(const PrepImgJob job, const PrepJob prep) {
         return reinterpret_cast<float*>(job.src_lvl[v][sh] +
                                         (size_t)((b * (Hs + 2 * kPad) + (y0 >> sh) + kPad) * st + (x0 >> sh) + kPad));
       };
+      auto w_of = [&](int sh) {
+        const float* sx = job.src_x[v][sh];
+        const int Hs = H >> sh, Ws = W >> sh;
+        return WChan{sx != nullptr ? sx + (size_t)((b * Hs + (y0 >> sh)) * Ws + (x0 >> sh)) : nullptr, Ws, job.src_x_inverse};
+      };
       int st0;
       float* d0 = dst_of(0, st0);
-      prep_rgba0<TW, RB>(tile, rows, cols, reinterpret_cast<float4*>(d0), st0 / 4);
-      prep_levels<LOG2F, TW, RB, true>(tile, rows, cols, dst_of);
+      prep_rgba0<TW, RB>(tile, rows, cols, reinterpret_cast<float4*>(d0), st0 / 4, w_of(0));
+      prep_levels<LOG2F, TW, RB, true>(tile, rows, cols, dst_of, w_of);
     }
     // three buffers: the one staged next was last read two tiles ago, before the barrier above -- no second barrier
     cur = nxt;
@@ -1176,6 +1206,34 @@ loss_fold_src_grad_kernel(const FoldJob j) {
   __stcs(o, g0); __stcs(o + 1, g1); __stcs(o + 2, g2);
 }
 
+// d/d(source view's network output) of the consistency term: the interior of the zero-bordered planes the fused
+// kernel scattered d/d(source depth) into, chained through depth = 1/x where the step says so.  One thread per
+// level-0 position; it serves the same (y, x) of every level that has it.
+struct CropJob {
+  const float* gsd[VSL_MAX_VIEWS][VSL_MAX_SCALES];
+  const float* src_x[VSL_MAX_VIEWS][VSL_MAX_SCALES];
+  float* g_src_x[VSL_MAX_VIEWS][VSL_MAX_SCALES];
+  int B, H, W, S, inverse;
+};
+// grid = (ceil(W / 256), H, V * B)
+__global__ void __launch_bounds__(256)
+loss_crop_src_depth_grad_kernel(const CropJob j) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  const int v = blockIdx.z / j.B, b = blockIdx.z - v * j.B;
+  for (int s = 0; s < j.S; ++s) {
+    const int Hs = j.H >> s, Ws = j.W >> s;
+    if (x >= Ws || y >= Hs) return;
+    float g = __ldg(j.gsd[v][s] + ((size_t)b * (Hs + 2 * kPad) + y + kPad) * (Ws + 2 * kPad) + x + kPad);
+    const size_t o = ((size_t)b * Hs + y) * Ws + x;
+    if (j.inverse) {
+      const float q = __fdiv_rn(1.0f, __ldg(j.src_x[v][s] + o));   // depth = 1/x: d(depth)/dx = -depth^2
+      g *= -q * q;
+    }
+    __stcs(j.g_src_x[v][s] + o, g);
+  }
+}
+
 }  // namespace vsl
 
 using namespace vsl;
@@ -1183,7 +1241,7 @@ using namespace vsl;
 namespace {
 
 struct WsLayout {
-  size_t xf, xq, partials, tgt_pyr, src_pyr, gsrc_pyr, tgt0, total;  // byte offsets (gsrc_pyr only with want_src_grad, tgt0 only for uint8 images)
+  size_t xf, xq, partials, tgt_pyr, src_pyr, gsrc_pyr, tgt0, gsd, total;  // byte offsets (gsrc_pyr only with want_src_grad, tgt0 only for uint8 images, gsd only with the consistency term)
   size_t tgt_off[VSL_MAX_SCALES];                    // floats, level s of the target pyramid (s >= 1)
   size_t src_off[VSL_MAX_SCALES];                    // float4, level s inside one view's RGBA block
   size_t src_view;                                   // float4 per view
@@ -1207,6 +1265,10 @@ int check_desc(const VslLossDesc* d) {
   VSL_REQUIRE(!(d->want_src_grad && d->img_format != VSL_IMG_F32), VSL_E_UNSUPPORTED);   // no gradient w.r.t. bytes
   VSL_REQUIRE(!(d->want_src_grad && d->exact_coords == 1), VSL_E_UNSUPPORTED);
   VSL_REQUIRE(!d->x_is_logit || d->disp_scale > 0.f, VSL_E_UNSUPPORTED);
+  VSL_REQUIRE(d->consist_weight >= 0.f, VSL_E_UNSUPPORTED);
+  // the consistency term rides on the fast arithmetic of the float32 entry
+  VSL_REQUIRE(!(d->consist_weight > 0.f) || (d->exact_coords != 1 && !d->want_src_grad && !d->x_is_logit &&
+                                             d->img_format == VSL_IMG_F32), VSL_E_UNSUPPORTED);
   return VSL_OK;
 }
 
@@ -1235,7 +1297,8 @@ void layout(const VslLossDesc* d, WsLayout* L) {
   L->src_pyr = L->tgt_pyr + round_up(sizeof(float) * tl, 256);
   L->gsrc_pyr = L->src_pyr + sizeof(float4) * sl * (size_t)d->V;
   L->tgt0 = L->gsrc_pyr + (d->want_src_grad ? sizeof(float4) * sl * (size_t)d->V : 0);
-  L->total = L->tgt0 + (d->img_format != VSL_IMG_F32 ? round_up(sizeof(float) * (size_t)d->B * d->H * d->W * 3, 256) : 0);
+  L->gsd = L->tgt0 + (d->img_format != VSL_IMG_F32 ? round_up(sizeof(float) * (size_t)d->B * d->H * d->W * 3, 256) : 0);
+  L->total = L->gsd + (d->consist_weight > 0.f ? round_up(sizeof(float) * sl * (size_t)d->V, 256) : 0);
 }
 
 template <typename Kern>
@@ -1261,9 +1324,9 @@ int launch_fused_as(Kern kern, size_t smem_bytes, const LossParams& P, cudaStrea
   return VSL_OK;
 }
 
-template <int V, bool EXACT, bool DSRC>
+template <int V, bool EXACT, bool DSRC, bool CONS = false>
 int launch_fused(const LossParams& P, cudaStream_t st) {
-  return launch_fused_as(loss_fused_kernel<V, EXACT, DSRC>, WarpSmem<V, EXACT>::block_bytes, P, st);
+  return launch_fused_as(loss_fused_kernel<V, EXACT, DSRC, CONS>, WarpSmem<V, EXACT>::block_bytes, P, st);
 }
 // fast arithmetic: an even number of views runs the view-paired kernel (packed fp32x2, vsl_loss_pair.cu: 23 % fewer
 // instructions, same time at 128x416, 2 % faster at 480x640); exact_coords == 2 asks for the scalar kernel instead,
@@ -1284,9 +1347,10 @@ int run_loss(const VslLossDesc* d, LossParams& P, const float* poses, const floa
 #ifdef VSL_DEV_V2_ONLY
   const int rc = launch_fused_fast<V>(P, d->exact_coords == 2, st);
 #else
-  const int rc = d->want_src_grad ? launch_fused<V, false, true>(P, st)
-                                  : (d->exact_coords == 1 ? launch_fused<V, true, false>(P, st)
-                                                          : launch_fused_fast<V>(P, d->exact_coords == 2, st));
+  const int rc = d->consist_weight > 0.f ? launch_fused<V, false, false, true>(P, st)
+                 : d->want_src_grad      ? launch_fused<V, false, true>(P, st)
+                                         : (d->exact_coords == 1 ? launch_fused<V, true, false>(P, st)
+                                                                 : launch_fused_fast<V>(P, d->exact_coords == 2, st));
 #endif
   if (rc != VSL_OK) return rc;
   if (d->ev_main_end != nullptr) cudaEventRecord((cudaEvent_t)d->ev_main_end, st);
@@ -1359,8 +1423,11 @@ namespace {
 int loss_fwd_bwd(const VslLossDesc* d, const void* tgt, const void* const* srcs, const float* const* x_pyr,
                  const float* poses, const float* K_pyr, const float* const* logits_pyr,
                  const float* const* mask_pyr, float* losses, float* const* g_x_pyr, float* g_poses,
-                 float* const* g_logits_pyr, float* const* g_srcs, void* ws, vsl_stream_t stream) {
+                 float* const* g_logits_pyr, float* const* g_srcs, void* ws, vsl_stream_t stream,
+                 const float* const* src_x_pyr = nullptr, float* const* g_src_x_pyr = nullptr) {
   int rc = VSL_OK;
+  const bool cons = d->consist_weight > 0.f;
+  VSL_REQUIRE(!cons || src_x_pyr, VSL_E_NULL);
   VSL_REQUIRE(tgt && srcs && x_pyr && poses && K_pyr && losses && g_x_pyr && g_poses && ws, VSL_E_NULL);
   VSL_REQUIRE(d->mask_mode != VSL_MASK_EXP || (logits_pyr && g_logits_pyr), VSL_E_NULL);
   VSL_REQUIRE(d->mask_mode != VSL_MASK_CONST || mask_pyr, VSL_E_NULL);
@@ -1389,8 +1456,10 @@ int loss_fwd_bwd(const VslLossDesc* d, const void* tgt, const void* const* srcs,
   for (int s = 0; s < VSL_MAX_SCALES; ++s) {
     P.tgt[s] = nullptr; P.x[s] = nullptr; P.logits[s] = nullptr; P.mask[s] = nullptr;
     P.g_x[s] = nullptr; P.g_logits[s] = nullptr; P.lg_vec4[s] = 0; P.strips[s] = 0; P.bands[s] = 0;
-    for (int v = 0; v < VSL_MAX_VIEWS; ++v) { P.src[v][s] = nullptr; P.gsrc[v][s] = nullptr; }
+    for (int v = 0; v < VSL_MAX_VIEWS; ++v) { P.src[v][s] = nullptr; P.gsrc[v][s] = nullptr; P.gsd[v][s] = nullptr; }
+    P.ccon[s] = 0.f;
   }
+  float* gsd = reinterpret_cast<float*>(base + L.gsd);
   for (int s = 0; s < d->S; ++s) {
     const int H = d->H >> s, W = d->W >> s;
     VSL_REQUIRE(x_pyr[s] && g_x_pyr[s], VSL_E_NULL);
@@ -1412,6 +1481,11 @@ int loss_fwd_bwd(const VslLossDesc* d, const void* tgt, const void* const* srcs,
     for (int v = 0; v < d->V; ++v) {
       P.src[v][s] = src_pyr + L.src_view * (size_t)v + L.src_off[s];
       P.gsrc[v][s] = d->want_src_grad ? gsrc_pyr + L.src_view * (size_t)v + L.src_off[s] : nullptr;
+      if (cons) {
+        VSL_REQUIRE(src_x_pyr[v * d->S + s], VSL_E_NULL);
+        VSL_REQUIRE(!g_src_x_pyr || g_src_x_pyr[v * d->S + s], VSL_E_NULL);
+        P.gsd[v][s] = g_src_x_pyr ? gsd + L.src_view * (size_t)v + L.src_off[s] : nullptr;
+      }
     }
     P.strips[s] = L.strips[s]; P.bands[s] = L.bands[s];
     P.Hs[s] = H; P.Ws[s] = W;
@@ -1425,6 +1499,7 @@ int loss_fwd_bwd(const VslLossDesc* d, const void* tgt, const void* const* srcs,
     const double dw = d->pixel_scale_norm ? (double)d->data_weight / (double)(1 << s) : (double)d->data_weight;
     P.cpix[s] = (float)((double)d->loss_scale * dw / (npx * 3.0));
     P.cexp[s] = (float)((double)d->loss_scale * (double)d->explain_reg_weight / npx);
+    P.ccon[s] = (float)((double)d->loss_scale * (double)d->consist_weight / npx);
     const double sw = (double)d->loss_scale * (double)d->smooth_weight / (double)(1 << s);
     P.cxx[s] = (float)(sw / ((double)d->B * H * (W - 2)));
     P.cxy[s] = (float)(sw / ((double)d->B * (H - 1) * (W - 1)));
@@ -1438,6 +1513,10 @@ int loss_fwd_bwd(const VslLossDesc* d, const void* tgt, const void* const* srcs,
     const cudaError_t e = cudaMemsetAsync(gsrc_pyr, 0, sizeof(float4) * L.src_view * (size_t)d->V, st);
     if (e != cudaSuccess) return (int)e;
   }
+  if (cons && g_src_x_pyr) {
+    const cudaError_t e = cudaMemsetAsync(gsd, 0, sizeof(float) * L.src_view * (size_t)d->V, st);
+    if (e != cudaSuccess) return (int)e;
+  }
   // 1. pyramids, RGBA source levels, transforms
   PrepJob prep = make_prep(poses, K_pyr, d->B, d->S, d->V, d->pose_format, xf, nullptr);
   prep.xq = reinterpret_cast<XformQ*>(base + L.xq);
@@ -1448,6 +1527,7 @@ int loss_fwd_bwd(const VslLossDesc* d, const void* tgt, const void* const* srcs,
   job.img_div = d->img_format == VSL_IMG_U8_RAW ? 1.0f : 255.0f;
   job.img_sub = d->img_format == VSL_IMG_U8_255_CENTRED ? 0.5f : 0.0f;
   job.V = d->V; job.B = d->B; job.H = d->H; job.W = d->W; job.S = d->S;
+  job.src_x_inverse = d->depth_is_inverse;
   const int F = 1 << (d->S - 1);
   {
     const int RB = F > 8 ? F : 8, TW = kPrepPx / RB;
@@ -1462,6 +1542,7 @@ int loss_fwd_bwd(const VslLossDesc* d, const void* tgt, const void* const* srcs,
     for (int v = 0; v < VSL_MAX_VIEWS; ++v) {
       job.src[v] = v < d->V ? srcs[v] : nullptr;
       job.src_lvl[v][s] = (v < d->V && s < d->S) ? src_pyr + L.src_view * (size_t)v + L.src_off[s] : nullptr;
+      job.src_x[v][s] = (cons && v < d->V && s < d->S) ? src_x_pyr[v * d->S + s] : nullptr;
     }
     if (s < d->S) {
       const int H = d->H >> s, W = d->W >> s;
@@ -1490,6 +1571,20 @@ int loss_fwd_bwd(const VslLossDesc* d, const void* tgt, const void* const* srcs,
     default: rc = run_loss<4>(d, P, poses, K_pyr, losses, g_poses, st); break;
   }
 #endif
+  if (rc == VSL_OK && cons && g_src_x_pyr) {
+    // 4'. d/d(source views' network outputs) of the consistency term: interior of the scattered planes, chain rule
+    CropJob cj;
+    for (int v = 0; v < VSL_MAX_VIEWS; ++v)
+      for (int s = 0; s < VSL_MAX_SCALES; ++s) {
+        const bool on = v < d->V && s < d->S;
+        cj.gsd[v][s] = on ? P.gsd[v][s] : nullptr;
+        cj.src_x[v][s] = on ? src_x_pyr[v * d->S + s] : nullptr;
+        cj.g_src_x[v][s] = on ? g_src_x_pyr[v * d->S + s] : nullptr;
+      }
+    cj.B = d->B; cj.H = d->H; cj.W = d->W; cj.S = d->S; cj.inverse = d->depth_is_inverse;
+    loss_crop_src_depth_grad_kernel<<<dim3((d->W + 255) / 256, d->H, d->V * d->B), 256, 0, st>>>(cj);
+    rc = launch_status();
+  }
   if (rc != VSL_OK || !d->want_src_grad) return rc;
   // 4. d/d(source image): fold the gradient levels back to [B,H,W,3], all views in one launch
   {
@@ -1514,8 +1609,21 @@ int vsl_loss_fwd_bwd(const VslLossDesc* d, const float* tgt, const float* const*
   const int rc = check_desc(d);
   if (rc != VSL_OK) return rc;
   VSL_REQUIRE(d->img_format == VSL_IMG_F32, VSL_E_FORMAT);
+  VSL_REQUIRE(!(d->consist_weight > 0.f), VSL_E_UNSUPPORTED);   // that step is vsl_loss_consist_fwd_bwd
   return loss_fwd_bwd(d, tgt, reinterpret_cast<const void* const*>(srcs), x_pyr, poses, K_pyr, logits_pyr, mask_pyr, losses,
                       g_x_pyr, g_poses, g_logits_pyr, g_srcs, ws, stream);
+}
+
+int vsl_loss_consist_fwd_bwd(const VslLossDesc* d, const float* tgt, const float* const* srcs,
+                             const float* const* x_pyr, const float* const* src_x_pyr, const float* poses,
+                             const float* K_pyr, const float* const* logits_pyr, const float* const* mask_pyr,
+                             float* losses, float* const* g_x_pyr, float* const* g_src_x_pyr, float* g_poses,
+                             float* const* g_logits_pyr, void* ws, vsl_stream_t stream) {
+  const int rc = check_desc(d);
+  if (rc != VSL_OK) return rc;
+  VSL_REQUIRE(d->consist_weight > 0.f, VSL_E_UNSUPPORTED);
+  return loss_fwd_bwd(d, tgt, reinterpret_cast<const void* const*>(srcs), x_pyr, poses, K_pyr, logits_pyr, mask_pyr, losses,
+                      g_x_pyr, g_poses, g_logits_pyr, nullptr, ws, stream, src_x_pyr, g_src_x_pyr);
 }
 
 int vsl_loss_fwd_bwd_u8(const VslLossDesc* d, const unsigned char* tgt, const unsigned char* const* srcs,

@@ -43,6 +43,8 @@ struct LossParams {
   const Xform* xf;                 // [S][V][B]
   const XformQ* xq;                // [S][V][B], folded transforms of the view-paired kernel
   float* partials;                 // [n_items][NT]
+  float* gsd[VSL_MAX_VIEWS][VSL_MAX_SCALES];           // consistency term: d/d(source depth), zero-bordered float planes (nullable)
+  float ccon[VSL_MAX_SCALES];      // loss_scale * consist_weight / (B Hs Ws); 0 without the consistency term
   float cpix[VSL_MAX_SCALES];      // loss_scale * data_weight_s / (B Hs Ws 3)
   float cexp[VSL_MAX_SCALES];      // loss_scale * explain_reg_weight / (B Hs Ws)
   // loss_scale * smooth_weight / 2^s / count_k, one flat array per second difference (a per-scale constant the

@@ -625,6 +625,9 @@ class LossFlags(object):
         # (imageselect_Dataloader_optflow_dim11.py:128), 'u8_raw': x (imageselect_Dataloader_optflow.py:129).  The
         # kernel converts on load; results are bit-identical to feeding the converted float32 images.
         self.img_format = 'f32'
+        # > 0: the left-right depth-consistency term of train_depth_then_cam_lr.py:336-340 (its FLAGS.depth_weight)
+        # inside the fused step; view_synthesis_loss then takes the source views' own network outputs (src_x_pyr)
+        self.consist_weight = 0.0
         self.__dict__.update(kw)
 
 
@@ -655,11 +658,13 @@ def _arena(shapes, device=None, pinned=False, dtypes=None):
     return buf, views
 
 
-def _loss_out_shapes(B, H, W, S, V, fmt, mask_mode):
+def _loss_out_shapes(B, H, W, S, V, fmt, mask_mode, consist=False):
     pose_shape = (B, V, 4, 4) if fmt == 2 else (B, V, 6)
     shapes = [(8,)] + [(B, H >> s, W >> s, 1) for s in range(S)] + [pose_shape]
     if mask_mode == _lib.MASK_EXP:
         shapes += [(B, H >> s, W >> s, 2 * V) for s in range(S)]
+    if consist:                      # d/d(source views' network outputs), view-major
+        shapes += [(B, H >> s, W >> s, 1) for _ in range(V) for s in range(S)]
     return shapes
 
 
@@ -668,10 +673,10 @@ class LossOutputs(object):
     ONE float32 arena (a host pipeline fetches them with a single copy; the upstream gradient is applied to them
     with a single launch)."""
 
-    def __init__(self, B, H, W, S, V, fmt, mask_mode, device):
-        self.shapes = _loss_out_shapes(B, H, W, S, V, fmt, mask_mode)
+    def __init__(self, B, H, W, S, V, fmt, mask_mode, device, consist=False):
+        self.shapes = _loss_out_shapes(B, H, W, S, V, fmt, mask_mode, consist)
         self.arena, views = _arena(self.shapes, device=device)
-        self.losses = views[0][:3]           # (pixel, smooth, exp)
+        self.losses = views[0][:4] if consist else views[0][:3]    # (pixel, smooth, exp[, consist])
         self.consist = views[0][3]           # the depth-consistency term (0 unless the step carries one)
         self.total = views[0][4]             # their sum, written by the same kernel
         self.g_x = views[1:1 + S]
@@ -680,6 +685,8 @@ class LossOutputs(object):
         self.grad_offset = 64              # floats: the gradients start at the arena's second 256-byte slot
         self._gx_ptrs = ptr_array([t.data_ptr() for t in self.g_x])
         self._gl_ptrs = ptr_array([t.data_ptr() for t in self.g_logits]) if self.g_logits else None
+        self.g_src_x = views[len(views) - V * S:] if consist else None     # [v * S + s]
+        self._gsx_ptrs = ptr_array([t.data_ptr() for t in self.g_src_x]) if consist else None
 
 
 def _want(shape, t, name):
@@ -687,8 +694,15 @@ def _want(shape, t, name):
         raise ValueError('%s must have shape %s, got %s' % (name, tuple(shape), tuple(t.shape)))
 
 
-def check_loss_shapes(B, H, W, S, V, fmt, mask_mode, tgt, srcs, x_pyr, poses, K_pyr, logits_pyr=None, mask_pyr=None):
+def check_loss_shapes(B, H, W, S, V, fmt, mask_mode, tgt, srcs, x_pyr, poses, K_pyr, logits_pyr=None, mask_pyr=None,
+                      src_x_pyr=None):
     """ValueError unless every tensor has the shape the fused step indexes it by."""
+    if src_x_pyr is not None:
+        if len(src_x_pyr) != V or any(len(p) != S for p in src_x_pyr):
+            raise ValueError('src_x_pyr must hold %d views x %d levels' % (V, S))
+        for v, pyr in enumerate(src_x_pyr):
+            for s_, t in enumerate(pyr):
+                _want((B, H >> s_, W >> s_, 1), t, 'src_x_pyr[%d][%d]' % (v, s_))
     _want((B, H, W, 3), tgt, 'tgt')
     if len(srcs) != V:
         raise ValueError('srcs must hold %d source views, got %d' % (V, len(srcs)))
@@ -736,13 +750,19 @@ class ViewSynthesisPlan(object):
         self.img_dtype = torch.float32 if self.img_format == _lib.IMG_F32 else torch.uint8
         if self.img_format != _lib.IMG_F32 and want_src_grad:
             raise ValueError('no gradient with respect to uint8 images')
+        self.consist_weight = float(getattr(flags, 'consist_weight', 0.0))
+        self.consist = self.consist_weight > 0.0
+        if self.consist and (want_src_grad or self.img_format != _lib.IMG_F32 or getattr(flags, 'x_is_logit', False)
+                             or int(getattr(flags, 'exact_coords', False)) == 1):
+            raise ValueError('the consistency term needs float32 images, exact_coords != 1, no x_is_logit and no '
+                             'gradient w.r.t. the source images')
         self.desc = VslLossDesc(B, H, W, S, V, self.fmt, mask_mode, int(flags.pixel_scale_norm),
                                 int(flags.depth_is_inverse), int(flags.smooth_on_inverse),
                                 float(flags.data_weight), float(flags.smooth_weight),
                                 float(flags.explain_reg_weight), float(loss_scale),
                                 int(getattr(flags, 'exact_coords', False)), int(self.want_src_grad),
                                 int(getattr(flags, 'x_is_logit', False)), float(getattr(flags, 'disp_scaling', 4.0)),
-                                float(getattr(flags, 'min_disp', 0.0)), self.img_format, None, None)
+                                float(getattr(flags, 'min_disp', 0.0)), self.img_format, self.consist_weight, None, None)
         nbytes = lib.vsl_loss_ws_bytes(self.desc)
         if nbytes == 0:
             raise ValueError('unsupported loss shape B=%d H=%d W=%d S=%d V=%d' % (B, H, W, S, V))
@@ -757,17 +777,20 @@ class ViewSynthesisPlan(object):
         self.version = 0  # bumped by every run()
 
     def new_outputs(self):
-        return LossOutputs(self.B, self.H, self.W, self.S, self.V, self.fmt, self.mask_mode, self.device)
+        return LossOutputs(self.B, self.H, self.W, self.S, self.V, self.fmt, self.mask_mode, self.device, self.consist)
 
     def new_src_grads(self):
         return [torch.empty(self.B, self.H, self.W, 3, device=self.device) for _ in range(self.V)]
 
-    def check_inputs(self, tgt, srcs, x_pyr, poses, K_pyr, logits_pyr=None, mask_pyr=None):
+    def check_inputs(self, tgt, srcs, x_pyr, poses, K_pyr, logits_pyr=None, mask_pyr=None, src_x_pyr=None):
         """Every tensor's shape against the plan's (B, H, W, S, V, pose format, mask mode): the C call indexes raw
         pointers by the plan's sizes, so a mismatch must be an error here, never an out-of-bounds read there."""
+        if self.consist != (src_x_pyr is not None):
+            raise ValueError('src_x_pyr goes with flags.consist_weight > 0 (and only with it)')
         check_loss_shapes(self.B, self.H, self.W, self.S, self.V, self.fmt, self.mask_mode, tgt, srcs, x_pyr, poses,
-                          K_pyr, logits_pyr, mask_pyr)
-        for t in [poses, K_pyr] + list(x_pyr) + list(logits_pyr or []) + list(mask_pyr or []):
+                          K_pyr, logits_pyr, mask_pyr, src_x_pyr)
+        for t in [poses, K_pyr] + list(x_pyr) + list(logits_pyr or []) + list(mask_pyr or []) + \
+                [t for p in (src_x_pyr or []) for t in p]:
             if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
                 raise TypeError('the fused step takes contiguous CUDA float32 tensors (no CPU fallback)')
         for t in [tgt] + list(srcs):
@@ -775,12 +798,21 @@ class ViewSynthesisPlan(object):
                 raise TypeError('images must be contiguous CUDA %s tensors for img_format=%r (no CPU fallback)'
                                 % (self.img_dtype, self.img_format))
 
-    def bind(self, tgt, srcs, x_pyr, poses, K_pyr, logits_pyr=None, mask_pyr=None, out=None, g_srcs=None):
+    def bind(self, tgt, srcs, x_pyr, poses, K_pyr, logits_pyr=None, mask_pyr=None, out=None, g_srcs=None,
+             src_x_pyr=None):
         """Validate and pre-marshal the C arguments for one set of input (and output) buffers; run_bound(args) then
         costs one ctypes call.  The caller keeps the tensors alive."""
-        self.check_inputs(tgt, srcs, x_pyr, poses, K_pyr, logits_pyr, mask_pyr)
+        self.check_inputs(tgt, srcs, x_pyr, poses, K_pyr, logits_pyr, mask_pyr, src_x_pyr)
         out = self.out if out is None else out
         g_srcs = self.g_srcs if g_srcs is None else g_srcs
+        if self.consist:                             # vsl_loss_consist_fwd_bwd
+            return (self.desc, tgt.data_ptr(), ptr_array([s.data_ptr() for s in srcs]),
+                    ptr_array([x.data_ptr() for x in x_pyr]),
+                    ptr_array([t.data_ptr() for p in src_x_pyr for t in p]), poses.data_ptr(), K_pyr.data_ptr(),
+                    ptr_array([l.data_ptr() for l in logits_pyr]) if logits_pyr is not None else None,
+                    ptr_array([m.data_ptr() for m in mask_pyr]) if mask_pyr is not None else None,
+                    out.losses.data_ptr(), out._gx_ptrs, out._gsx_ptrs, out.g_poses.data_ptr(), out._gl_ptrs,
+                    self.ws.data_ptr())
         head = (self.desc, tgt.data_ptr(), ptr_array([s.data_ptr() for s in srcs]),
                 ptr_array([x.data_ptr() for x in x_pyr]), poses.data_ptr(), K_pyr.data_ptr(),
                 ptr_array([l.data_ptr() for l in logits_pyr]) if logits_pyr is not None else None,
@@ -793,7 +825,8 @@ class ViewSynthesisPlan(object):
     def run_bound(self, args, stream=None):
         self.version += 1
         lib = _lib.load()
-        fn = lib.vsl_loss_fwd_bwd if self.img_format == _lib.IMG_F32 else lib.vsl_loss_fwd_bwd_u8
+        fn = lib.vsl_loss_consist_fwd_bwd if self.consist else (
+            lib.vsl_loss_fwd_bwd if self.img_format == _lib.IMG_F32 else lib.vsl_loss_fwd_bwd_u8)
         check(fn(*args, _stream() if stream is None else stream))
         return self.losses
 
@@ -801,10 +834,10 @@ class ViewSynthesisPlan(object):
         """cudaEvent_t handles (ints) recorded immediately around the fused loss kernel; None switches off."""
         self.desc.ev_main_begin, self.desc.ev_main_end = begin, end
 
-    def run(self, tgt, srcs, x_pyr, poses, K_pyr, logits_pyr=None, mask_pyr=None):
+    def run(self, tgt, srcs, x_pyr, poses, K_pyr, logits_pyr=None, mask_pyr=None, src_x_pyr=None):
         """Enqueue one fused forward+backward.  Inputs must already be contiguous CUDA float32 of the plan's
-        shapes.  Results land in self.losses / self.g_x / self.g_poses / self.g_logits."""
-        return self.run_bound(self.bind(tgt, srcs, x_pyr, poses, K_pyr, logits_pyr, mask_pyr))
+        shapes.  Results land in self.losses / self.g_x / self.g_poses / self.g_logits (/ self.out.g_src_x)."""
+        return self.run_bound(self.bind(tgt, srcs, x_pyr, poses, K_pyr, logits_pyr, mask_pyr, src_x_pyr=src_x_pyr))
 
 
 class _ViewSynthesisLoss(torch.autograd.Function):
@@ -814,21 +847,23 @@ class _ViewSynthesisLoss(torch.autograd.Function):
     it is exactly 1, i.e. total.backward()) and hands out views of it."""
 
     @staticmethod
-    def forward(ctx, plan, tgt, K_pyr, poses, n_src, n_x, *rest_all):
+    def forward(ctx, plan, tgt, K_pyr, poses, n_src, n_x, n_rest, *rest_all):
         srcs = [_img(t, 'src', plan.img_dtype) for t in rest_all[:n_src]]
         x_pyr = [_f32(t, 'x_pyr') for t in rest_all[n_src:n_src + n_x]]
-        rest = [_f32(t, 'pyr') for t in rest_all[n_src + n_x:]]
+        rest = [_f32(t, 'pyr') for t in rest_all[n_src + n_x:n_src + n_x + n_rest]]
+        src_x = [_f32(t, 'src_x_pyr') for t in rest_all[n_src + n_x + n_rest:]]       # view-major, V * S or none
         logits = rest if plan.mask_mode == _lib.MASK_EXP else None
         mask = rest if plan.mask_mode == _lib.MASK_CONST else None
         out = plan.new_outputs()
         g_srcs = plan.new_src_grads() if plan.want_src_grad else None
+        src_x_pyr = [src_x[v * n_x:(v + 1) * n_x] for v in range(n_src)] if src_x else None
         plan.run_bound(plan.bind(_img(tgt, 'tgt', plan.img_dtype), srcs, x_pyr, _f32(poses, 'poses'), _f32(K_pyr, 'K_pyr'), logits,
-                                 mask, out=out, g_srcs=g_srcs))
+                                 mask, out=out, g_srcs=g_srcs, src_x_pyr=src_x_pyr))
         ctx.out, ctx.g_srcs, ctx.mask_mode = out, g_srcs, plan.mask_mode
-        ctx.n_src, ctx.n_x, ctx.n_rest = n_src, n_x, len(rest)
+        ctx.n_src, ctx.n_x, ctx.n_rest, ctx.n_sx = n_src, n_x, len(rest), len(src_x)
         ctx.applied = None                    # device scalar: the upstream factor the arena currently carries
         # views of this call's own arena: no copy, no reduction launch (the finalize kernel wrote the total too)
-        total, losses = out.total.view(()), out.losses.view(3)
+        total, losses = out.total.view(()), out.losses.view(-1)
         ctx.mark_non_differentiable(losses)
         return total, losses
 
@@ -842,6 +877,7 @@ class _ViewSynthesisLoss(torch.autograd.Function):
             check(lib.vsl_scale(src_ptr, src_ptr, n, g.data_ptr(), None, _stream()))
             ctx.applied = g
             g_x, g_poses, g_logits = out.g_x, out.g_poses, out.g_logits
+            g_src_x = out.g_src_x
             g_srcs = ctx.g_srcs
             if g_srcs is not None:
                 for t in g_srcs:
@@ -861,6 +897,7 @@ class _ViewSynthesisLoss(torch.autograd.Function):
             S = len(out.g_x)
             g_x, g_poses = views[1:1 + S], views[1 + S]
             g_logits = views[2 + S:2 + 2 * S] if out.g_logits is not None else None
+            g_src_x = views[len(views) - ctx.n_sx:] if ctx.n_sx else None
             g_srcs = None
             if ctx.g_srcs is not None:
                 g_srcs = [torch.empty_like(t) for t in ctx.g_srcs]
@@ -869,7 +906,7 @@ class _ViewSynthesisLoss(torch.autograd.Function):
                                         _stream()))
         gs = tuple(g_srcs) if g_srcs is not None else (None,) * ctx.n_src
         gr = tuple(g_logits) if ctx.mask_mode == _lib.MASK_EXP else (None,) * ctx.n_rest
-        return (None, None, None, g_poses, None, None) + gs + tuple(g_x) + gr
+        return (None, None, None, g_poses, None, None, None) + gs + tuple(g_x) + gr + tuple(g_src_x or ())
 
 
 _PLANS = collections.OrderedDict()
@@ -891,7 +928,8 @@ def _plan_for(key, make):
         return plan
 
 
-def view_synthesis_loss(tgt, srcs, x_pyr, poses, K_pyr, logits_pyr=None, mask_pyr=None, flags=None, loss_scale=1.0):
+def view_synthesis_loss(tgt, srcs, x_pyr, poses, K_pyr, logits_pyr=None, mask_pyr=None, flags=None, loss_scale=1.0,
+                        src_x_pyr=None):
     """The reference's per-scale loss loop (train.py:107-135 + train_depth_then_cam_lr.py:297-328) as ONE fused
     forward+backward call.
 
@@ -900,6 +938,10 @@ def view_synthesis_loss(tgt, srcs, x_pyr, poses, K_pyr, logits_pyr=None, mask_py
     constant weights [B,Hs,Ws,1].  Every shape is checked (ValueError) before anything reaches the C call.
     -> (total, losses[3] = pixel, smooth, exp).  `total` is differentiable wrt x_pyr, poses and logits_pyr (and the
     source images if they require grad); the gradients were produced in the same kernel pass as the loss.
+    With flags.consist_weight > 0 the step also carries the left-right depth-consistency term
+    (train_depth_then_cam_lr.py:336-340): src_x_pyr = per source view the list of ITS S network outputs
+    [B,Hs,Ws,1] (depth = x or 1/x like the target's); losses becomes [4] = pixel, smooth, exp, consist and `total`
+    is differentiable wrt src_x_pyr too.
     loss_scale: a constant factor of the objective known up front (a data-parallel rank's B_local / B_global share,
     dist.local_loss_scale) -- folded into the kernel's gradients for free; `total` and `losses` stay unscaled means.
     """
@@ -921,14 +963,20 @@ def view_synthesis_loss(tgt, srcs, x_pyr, poses, K_pyr, logits_pyr=None, mask_py
     mode = _lib.MASK_EXP if logits_pyr is not None else (_lib.MASK_CONST if mask_pyr is not None else _lib.MASK_NONE)
     want_src = any(getattr(t, 'requires_grad', False) for t in srcs)
     rest = [from_external(t, 'pyr') for t in (logits_pyr if logits_pyr is not None else (mask_pyr or []))]
+    consist = float(getattr(flags, 'consist_weight', 0.0)) > 0.0
+    if consist != (src_x_pyr is not None):
+        raise ValueError('src_x_pyr goes with flags.consist_weight > 0 (and only with it)')
+    if consist:
+        src_x_pyr = [[from_external(t, 'src_x_pyr') for t in p] for p in src_x_pyr]
     # shapes first: a wrong layout is a ValueError here, before any pointer reaches the library
     check_loss_shapes(B, H, W, S, V, _fmt(flags.pose_format), mode, tgt, srcs, x_pyr, poses, K_pyr,
-                      rest if mode == _lib.MASK_EXP else None, rest if mode == _lib.MASK_CONST else None)
+                      rest if mode == _lib.MASK_EXP else None, rest if mode == _lib.MASK_CONST else None, src_x_pyr)
     key = (B, H, W, V, mode, tgt.device, torch.cuda.current_stream(tgt.device).cuda_stream, want_src, float(loss_scale),
            tuple(sorted(flags.__dict__.items())))
     plan = _plan_for(key, lambda: ViewSynthesisPlan(B, H, W, V, flags, mode, tgt.device, loss_scale=loss_scale,
                                                     want_src_grad=want_src))
-    return _ViewSynthesisLoss.apply(plan, tgt, K_pyr, poses, V, S, *srcs, *x_pyr, *rest)
+    return _ViewSynthesisLoss.apply(plan, tgt, K_pyr, poses, V, S, len(rest), *srcs, *x_pyr, *rest,
+                                    *[t for p in (src_x_pyr or []) for t in p])
 
 
 class HostPipeline(object):
