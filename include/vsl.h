@@ -189,6 +189,10 @@ typedef struct {
 } VslLossDesc;
 
 size_t vsl_loss_ws_bytes(const VslLossDesc* d);
+/* Where the prep launch leaves its products inside the workspace (tests and tools): byte offsets, out[s] = RGB level
+ * s of the target [B,Hs,Ws,3] (level 0: -1 unless the images are uint8 -- the float32 target is read in place),
+ * out[S + v * S + s] = level s of source view v as zero-bordered RGBA [B,Hs+4,Ws+4,4].  out: S + V * S entries. */
+int vsl_loss_ws_layout(const VslLossDesc* d, long long* out);
 int vsl_loss_fwd_bwd(const VslLossDesc* d,
                      const float* tgt /*[B,H,W,3]*/, const float* const* srcs /*host array V x [B,H,W,3]*/,
                      const float* const* x_pyr /*host array S x [B,Hs,Ws,1]*/,

@@ -325,6 +325,52 @@ def test_consistency_entry_argument_checks():
         ops.view_synthesis_loss(*a, flags=ops.LossFlags(num_scales=S, consist_weight=1.0, exact_coords=True), src_x_pyr=sx)
 
 
+@pytest.mark.parametrize('shape', [(2, 32, 64, 4, 2), (1, 48, 104, 4, 1), (3, 16, 416, 1, 2), (2, 20, 36, 3, 2),
+                                   (1, 64, 96, 5, 3), (2, 18, 30, 2, 1), (1, 96, 96, 6, 1), (2, 128, 416, 4, 2)])
+def test_prep_launch_products_bit_exact(shape):
+    """What launch 1 leaves in the workspace -- resize_area levels of the target (RGB) and of every source view
+    (zero-bordered RGBA; the fourth channel zero, or the source view's depth map with the consistency term) -- is
+    BIT-identical to the oracle's resize_area (TF's ComputePatchSum order), for the register form of the launch
+    (W % 4 == 0, at most 5 scales), the staged form (the rest) and the uint8 ingest."""
+    B, H, W, S, V = shape
+    d = synth.make_snippets(B, H, W, S=S, V=V, seed=11)
+    for variant in ('f32', 'u8', 'consist'):
+        if variant == 'consist' and S > 5:
+            continue
+        kw = dict(num_scales=S)
+        imgs = [d['tgt']] + list(d['srcs'])
+        if variant == 'u8':
+            kw['img_format'] = 'u8_255'
+            u8 = [(t * 255).round().clamp(0, 255).to(torch.uint8) for t in imgs]
+            imgs = [O.images_from_uint8(t, 'u8_255') for t in u8]
+            dev_imgs = [t.to(DEV) for t in u8]
+        else:
+            dev_imgs = [cu(t) for t in imgs]
+        if variant == 'consist':
+            kw.update(consist_weight=1.0)
+        flags = ops.LossFlags(**kw)
+        plan = ops.ViewSynthesisPlan(B, H, W, V, flags, 1, torch.device(DEV))
+        sx = [[cu(x + 0.25 * (v + 1)) for x in d['disp_pyr']] for v in range(V)] if variant == 'consist' else None
+        plan.run(dev_imgs[0], dev_imgs[1:], [cu(x) for x in d['disp_pyr']], cu(d['poses']), cu(d['K_pyr']),
+                 logits_pyr=[cu(l) for l in d['logits_pyr']], src_x_pyr=sx)
+        torch.cuda.synchronize()
+        tgt_lv, src_lv = plan.prep_levels()
+        for s in range(S):
+            hs, ws = H >> s, W >> s
+            if tgt_lv[s] is not None:
+                assert torch.equal(tgt_lv[s].cpu(), O.resize_area(imgs[0], hs, ws)), (variant, 'tgt', s)
+            else:
+                assert s == 0 and variant != 'u8'
+            for v in range(V):
+                got = src_lv[v][s].cpu()
+                assert torch.equal(got[:, 2:-2, 2:-2, :3], O.resize_area(imgs[1 + v], hs, ws)), (variant, 'src', v, s)
+                border = got.clone()
+                border[:, 2:-2, 2:-2] = 0
+                assert float(border.abs().max()) == 0.0, (variant, 'border', v, s)
+                want_w = (1.0 / (d['disp_pyr'][s] + 0.25 * (v + 1)))[..., 0] if variant == 'consist' else torch.zeros(B, hs, ws)
+                assert torch.equal(got[:, 2:-2, 2:-2, 3], want_w), (variant, 'w', v, s)
+
+
 def test_fused_exact_mode_matches_standalone_warp_bitwise(golden):
     """exact_coords=True: the fused kernel's photometric term is built from the same rounded operations as the
     stand-alone warp, so with smoothing / regulariser off its pixel loss equals mean|warp - tgt| computed from

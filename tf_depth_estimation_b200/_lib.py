@@ -62,6 +62,7 @@ SIGNATURES = {
     'vsl_expreg_bwd': (ctypes.c_int, [_c_float_p, ctypes.c_longlong, _c_float_p, _c_float_p, _c_stream]),
     'vsl_pyramid': (ctypes.c_int, [_c_float_p] + [ctypes.c_int] * 5 + [ctypes.POINTER(ctypes.c_void_p), _c_stream]),
     'vsl_loss_ws_bytes': (ctypes.c_size_t, [ctypes.POINTER(VslLossDesc)]),
+    'vsl_loss_ws_layout': (ctypes.c_int, [ctypes.POINTER(VslLossDesc), ctypes.POINTER(ctypes.c_longlong)]),
     'vsl_loss_fwd_bwd': (ctypes.c_int, [ctypes.POINTER(VslLossDesc), _c_float_p, ctypes.POINTER(ctypes.c_void_p),
                                         ctypes.POINTER(ctypes.c_void_p), _c_float_p, _c_float_p,
                                         ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p),

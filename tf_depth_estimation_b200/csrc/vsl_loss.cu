@@ -987,6 +987,36 @@ VSL_DEV int fast_div(int n, int d, float inv_d) {
   return q;
 }
 
+// Border zeros of the RGBA levels and the transform table, spread over all blocks of a prep launch and done first, so
+// their serial chains (sin / cos, LU inverse) run under the image work instead of as a tail.
+VSL_DEV void prep_borders_and_table(const PrepImgJob& job, const PrepJob& prep) {
+  const int B = job.B, H = job.H, W = job.W;
+  const int per_img = job.border_begin[job.S];
+  const int n_border = job.V * B * per_img;
+  for (int k0 = blockIdx.x * blockDim.x + threadIdx.x; k0 < n_border + prep.n; k0 += gridDim.x * blockDim.x) {
+    int k = k0;
+    if (k >= n_border) { prep_one(prep, k - n_border); continue; }
+    const int vb = k / per_img;
+    k -= vb * per_img;
+    int s = 0;
+    while (s + 1 < job.S && k >= job.border_begin[s + 1]) ++s;
+    k -= job.border_begin[s];
+    const int v = vb / B, b = vb - v * B;
+    const int Hs = H >> s, Ws = W >> s, st = Ws + 2 * kPad;
+    int row, col;
+    if (k < 2 * kPad * st) {             // kPad full rows on top, kPad at the bottom
+      row = k / st; col = k - row * st;
+      if (row >= kPad) row += Hs;
+    } else {                             // 2 * kPad columns beside each image row
+      k -= 2 * kPad * st;
+      row = kPad + k / (2 * kPad);
+      const int c = k % (2 * kPad);
+      col = c < kPad ? c : Ws + c;
+    }
+    job.src_lvl[v][s][((size_t)b * (Hs + 2 * kPad) + row) * st + col] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
 // Persistent blocks, three tile buffers: the cp.async of tile i+1 is in flight while tile i is turned into its
 // output levels, so a block never sits idle waiting for its load, and one barrier per tile is enough.
 // U8: the images arrive as the loader's uint8 (imageselect_Dataloader.py:86-93: decode_jpeg -> to_float -> / 255.0).
@@ -1007,34 +1037,7 @@ loss_prep_kernel(const PrepImgJob job, const PrepJob prep) {
   // finalize, or the network that produced the inputs): only the launch latency overlaps, nothing is read before
   asm volatile("griddepcontrol.wait;" ::: "memory");
 
-  // ---- border zeros of the RGBA levels and the transform table, spread over all blocks and done first, so their
-  // serial chains (sin / cos, LU inverse) run under the tiles instead of as a tail
-  {
-    const int per_img = job.border_begin[job.S];
-    const int n_border = job.V * B * per_img;
-    for (int k0 = blockIdx.x * kPrepThreads + threadIdx.x; k0 < n_border + prep.n; k0 += gridDim.x * kPrepThreads) {
-      int k = k0;
-      if (k >= n_border) { prep_one(prep, k - n_border); continue; }
-      const int vb = k / per_img;
-      k -= vb * per_img;
-      int s = 0;
-      while (s + 1 < job.S && k >= job.border_begin[s + 1]) ++s;
-      k -= job.border_begin[s];
-      const int v = vb / B, b = vb - v * B;
-      const int Hs = H >> s, Ws = W >> s, st = Ws + 2 * kPad;
-      int row, col;
-      if (k < 2 * kPad * st) {             // kPad full rows on top, kPad at the bottom
-        row = k / st; col = k - row * st;
-        if (row >= kPad) row += Hs;
-      } else {                             // 2 * kPad columns beside each image row
-        k -= 2 * kPad * st;
-        row = kPad + k / (2 * kPad);
-        const int c = k % (2 * kPad);
-        col = c < kPad ? c : Ws + c;
-      }
-      job.src_lvl[v][s][((size_t)b * (Hs + 2 * kPad) + row) * st + col] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-  }
+  prep_borders_and_table(job, prep);
 
   // the level-0 images are read exactly once: evict-first in L2, so that what this launch WRITES (the RGBA
   // levels the fused launch gathers from next) is what stays resident
@@ -1175,6 +1178,315 @@ loss_prep_kernel(const PrepImgJob job, const PrepJob prep) {
       prep_levels<LOG2F, TW, RB, true>(tile, rows, cols, dst_of, w_of);
     }
     // three buffers: the one staged next was last read two tiles ago, before the barrier above -- no second barrier
+    cur = nxt;
+  }
+}
+
+// =====================================================================================================
+// Launch 1, register form (float32 images, W % 4 == 0, at most 5 scales): no shared memory, no barrier.
+// A WARP owns a patch of 32 columns x 16 rows of one image: lane = (ly, lx) = (lane / 8, lane % 8), a thread holds
+// the 4 x 4 pixels at (4 ly, 4 lx) of the patch -- 12 aligned 16-byte loads, everything in flight at once -- and
+// produces from its registers
+//   level 0 as RGBA (sources): 16 stores of 16 bytes, 64 contiguous bytes per row and lane;
+//   level 1: its 2 x 2 outputs, level 2: its one output -- thread-local;
+//   level k >= 3: the ResizeArea order (a row's 2^k values left to right, the row sums top to bottom) is a CHAIN,
+//   so the running row sum walks across the 2^(k-2) lanes of a row group by shuffles (lane j continues where lane
+//   j - 1 stopped), then the running column sum down the lane rows: bit-identical to the serial order.
+// 16 warp-instructions per 32 pixels instead of the staged kernel's 109: the launch goes from issue-bound to
+// memory-bound.  Warps stride over the patches (persistent, no tail beyond one patch).
+// =====================================================================================================
+constexpr int kPrepRegThreads = 128, kPrepRegBlocks = 4;
+constexpr int kPatchF4 = 16 * 24;                 // float4 per staged patch: 16 rows x 32 pixels x 3 floats
+constexpr size_t kPrepRegSmem = sizeof(float4) * 2 * kPatchF4 * (kPrepRegThreads / 32);
+
+VSL_DEV float4 ldg_stream4(const float* p, unsigned long long pol) {
+  float4 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+  return v;
+}
+
+// the chain over n lanes at lane distance `dist` (1: along a row group, 8: down the lane rows): lane j of a group
+// continues the left-to-right sum where lane j - 1 stopped.  v[i]: this lane's own 4 addends of sum i, in order.
+template <int n, int dist, int M>
+VSL_DEV void chain_across(float (&run)[M], const float (&v)[M][4], int pos) {
+#pragma unroll
+  for (int j = 1; j < n; ++j) {
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+      const float t = __shfl_up_sync(0xffffffffu, run[i], dist);
+      const float cand = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(t, v[i][0]), v[i][1]), v[i][2]), v[i][3]);
+      run[i] = pos == j ? cand : run[i];
+    }
+  }
+}
+
+VSL_DEV void stg256(float* p, float a0, float a1, float a2, float a3, float a4, float a5, float a6, float a7) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(a0), "f"(a1), "f"(a2), "f"(a3),
+               "f"(a4), "f"(a5), "f"(a6), "f"(a7) : "memory");
+}
+
+// Where the products of one patch go.  Source view v: straight to its zero-bordered RGBA levels, 32 bytes (two pixels)
+// per store where the level allows -- a whole sector per lane; two 16-byte stores are two partial-sector requests on
+// the SM's path to L2, which is what bounds this launch.  WCH: the fourth channel carries the view's depth map
+// (consistency term) instead of zeros.  TGT: the target's RGB levels are 12 bytes per pixel -- written lane by lane
+// they would be quarter-filled sectors, so they are assembled in the warp's spent stage buffer and leave as
+// contiguous rows (prep_flush_tgt).
+__host__ __device__ constexpr int prep_scr_off(int sh) { return sh <= 1 ? 0 : prep_scr_off(sh - 1) + (16 >> (sh - 1)) * (32 >> (sh - 1)) * 3; }
+
+template <bool TGT, bool WCH>
+struct PrepSink {
+  const PrepImgJob& job;
+  int v, b, H, W;
+  float* scr;
+  struct Lvl { float* d; const float* w; int st, wst; };
+  // level sh: where this thread's first output pixel (y >> sh, x >> sh) goes, and the row strides (floats)
+  VSL_DEV Lvl lvl(int sh, int y, int x) const {
+    Lvl L;
+    const int Hs = H >> sh, Ws = W >> sh;
+    if (TGT) {
+      L.st = (32 >> sh) * 3;
+      L.d = scr + prep_scr_off(sh) + ((y & 15) >> sh) * L.st + ((x & 31) >> sh) * 3;
+      L.w = nullptr; L.wst = 0;
+    } else {
+      const int st = Ws + 2 * kPad;
+      L.st = st * 4;
+      L.d = reinterpret_cast<float*>(job.src_lvl[v][sh] + ((size_t)b * (Hs + 2 * kPad) + (y >> sh) + kPad) * st + (x >> sh) + kPad);
+      L.wst = Ws;
+      L.w = WCH ? job.src_x[v][sh] + ((size_t)b * Hs + (y >> sh)) * Ws + (x >> sh) : nullptr;
+    }
+    return L;
+  }
+  VSL_DEV float w_at(const Lvl& L, int r, int j) const {
+    if (!WCH) return 0.f;
+    const float q = __ldg(L.w + r * L.wst + j);
+    return job.src_x_inverse ? __fdiv_rn(1.0f, q) : q;
+  }
+  // pixel (row r, column j) relative to the thread's first one
+  VSL_DEV void px(const Lvl& L, int r, int j, float c0, float c1, float c2) const {
+    if (TGT) {
+      float* d = L.d + r * L.st + j * 3;
+      d[0] = c0; d[1] = c1; d[2] = c2;
+    } else {
+      *reinterpret_cast<float4*>(L.d + r * L.st + j * 4) = make_float4(c0, c1, c2, w_at(L, r, j));
+    }
+  }
+  // two horizontally adjacent pixels starting at an even column
+  VSL_DEV void px2(const Lvl& L, int r, int j, const float (&c)[6]) const {
+    if (TGT) {
+      float2* d = reinterpret_cast<float2*>(L.d + r * L.st + j * 3);
+      d[0] = make_float2(c[0], c[1]); d[1] = make_float2(c[2], c[3]); d[2] = make_float2(c[4], c[5]);
+    } else {
+      stg256(L.d + r * L.st + j * 4, c[0], c[1], c[2], w_at(L, r, j), c[3], c[4], c[5], w_at(L, r, j + 1));
+    }
+  }
+};
+
+// The target levels of one patch, scratch -> global: consecutive lanes write consecutive words of a level row.
+template <int LOG2F>
+VSL_DEV void prep_flush_tgt(const PrepImgJob& job, const float* scr, int b, int x0, int y0, int lane) {
+  const int H = job.H, W = job.W;
+  const int rows = min(16, H - y0), cols = min(32, W - x0);
+#pragma unroll
+  for (int sh = 1; sh <= LOG2F; ++sh) {
+    const int Ws = W >> sh, nr = rows >> sh, nf = (cols >> sh) * 3;             // valid rows, valid floats per row
+    float* __restrict__ d = job.tgt_lvl[sh] + (((size_t)b * (H >> sh) + (y0 >> sh)) * Ws + (x0 >> sh)) * 3;
+    const float* t = scr + prep_scr_off(sh);
+    const int ts = (32 >> sh) * 3;
+    if (((nf | Ws) & 1) == 0) {                   // 8-byte words where the level's rows (Ws * 12 bytes) keep them aligned
+      const int per = nf >> 1;
+      const float inv = 1.0f / (float)per;
+      for (int i = lane; i < nr * per; i += 32) {
+        const int r = fast_div(i, per, inv), c = i - r * per;
+        *reinterpret_cast<float2*>(d + (size_t)r * Ws * 3 + 2 * c) = *reinterpret_cast<const float2*>(t + r * ts + 2 * c);
+      }
+    } else {
+      const float inv = 1.0f / (float)nf;
+      for (int i = lane; i < nr * nf; i += 32) {
+        const int r = fast_div(i, nf, inv), c = i - r * nf;
+        d[(size_t)r * Ws * 3 + c] = t[r * ts + c];
+      }
+    }
+  }
+}
+
+// Every level of the 4 x 4 pixels a thread holds (a[row][pixel * 3 + channel]) at (y, x) of image b.
+template <int LOG2F, bool TGT, bool WCH>
+VSL_DEV void prep_patch(const PrepSink<TGT, WCH> out, const float (&a)[4][12], int x, int y, int lx, int ly, bool in_x) {
+  const int H = out.H;
+  using Lvl = typename PrepSink<TGT, WCH>::Lvl;
+  // ---- level 0 as RGBA
+  if (!TGT && in_x) {
+    const Lvl L = out.lvl(0, y, x);
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      if (y + r < H) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const float c[6] = {a[r][6 * j], a[r][6 * j + 1], a[r][6 * j + 2], a[r][6 * j + 3], a[r][6 * j + 4], a[r][6 * j + 5]};
+          out.px2(L, r, 2 * j, c);
+        }
+      }
+  }
+  if constexpr (LOG2F >= 1) {
+    // pair sums of every row: (a0 + a1), (a2 + a3) -- level 1's row sums, and the head of every longer chain
+    float s2[4][2][3];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) s2[r][j][c] = __fadd_rn(a[r][6 * j + c], a[r][6 * j + 3 + c]);
+    if (in_x) {
+      const Lvl L = out.lvl(1, y, x);
+#pragma unroll
+      for (int ry = 0; ry < 2; ++ry)
+        if (y + 2 * ry + 1 < H) {
+          float c[6];
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) c[3 * j + ch] = __fmul_rn(__fadd_rn(s2[2 * ry][j][ch], s2[2 * ry + 1][j][ch]), 0.25f);
+          out.px2(L, ry, 0, c);
+        }
+    }
+    if constexpr (LOG2F >= 2) {
+      // row sums of the thread's 4 pixels: ((a0 + a1) + a2) + a3
+      float s4[12];                             // [row * 3 + channel]
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) s4[r * 3 + c] = __fadd_rn(__fadd_rn(s2[r][0][c], a[r][6 + c]), a[r][9 + c]);
+      float t4[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) t4[c] = __fadd_rn(__fadd_rn(__fadd_rn(s4[c], s4[3 + c]), s4[6 + c]), s4[9 + c]);
+      if (in_x && y + 3 < H)
+        out.px(out.lvl(2, y, x), 0, 0, __fmul_rn(t4[0], 0.0625f), __fmul_rn(t4[1], 0.0625f), __fmul_rn(t4[2], 0.0625f));
+      if constexpr (LOG2F >= 3) {
+        // own addends of the row chains, [row * 3 + channel][pixel]
+        float own[12][4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) own[r * 3 + c][j] = a[r][3 * j + c];
+        auto level = [&](auto kc) {
+          constexpr int k = decltype(kc)::value, n = 1 << (k - 2);
+          float run[12];
+#pragma unroll
+          for (int i = 0; i < 12; ++i) run[i] = s4[i];
+          chain_across<n, 1, 12>(run, own, lx & (n - 1));           // lanes at the end of a row group: full row sums
+          float col[3], rows4[3][4];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) rows4[c][r] = run[r * 3 + c];
+            col[c] = __fadd_rn(__fadd_rn(__fadd_rn(rows4[c][0], rows4[c][1]), rows4[c][2]), rows4[c][3]);
+          }
+          chain_across<n, 8, 3>(col, rows4, ly & (n - 1));
+          if ((lx & (n - 1)) == n - 1 && (ly & (n - 1)) == n - 1 && in_x && y + 3 < H) {
+            constexpr float sc = 1.0f / (float)(1 << (2 * k));
+            out.px(out.lvl(k, y, x), 0, 0, __fmul_rn(col[0], sc), __fmul_rn(col[1], sc), __fmul_rn(col[2], sc));
+          }
+        };
+        level(std::integral_constant<int, 3>{});
+        if constexpr (LOG2F >= 4) level(std::integral_constant<int, 4>{});
+      }
+    }
+  }
+}
+
+// Warps stride over the patches.  A patch's 6 KB travel global -> shared memory as 16-byte cp.async, lane = chunk
+// (fully coalesced, nothing held in registers on the way), into a two-stage buffer the warp owns: the next patch is in
+// flight while this one is turned into its levels, so a warp's loads never wait for its arithmetic and stores.
+template <int LOG2F>
+__global__ void __launch_bounds__(kPrepRegThreads, kPrepRegBlocks)
+loss_prep_reg_kernel(const PrepImgJob job, const PrepJob prep) {
+  static_assert(LOG2F <= 4, "levels above 4 chain across more lane rows than a warp has");
+  extern __shared__ float4 smem4[];               // [warps][2 stages][16 rows][24 float4]
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  prep_borders_and_table(job, prep);
+
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  const int B = job.B, H = job.H, W = job.W;
+  const int lane = threadIdx.x & 31, lx = lane & 7, ly = lane >> 3;
+  constexpr int wpb = kPrepRegThreads / 32;
+  const int warp = threadIdx.x >> 5;
+  const int warp0 = blockIdx.x * wpb + warp, n_warps = gridDim.x * wpb;
+  const int px = (W + 31) >> 5, py = (H + 15) >> 4, per_img = px * py;
+  const int n_patches = (job.V + 1) * B * per_img;
+  const float inv_per_img = 1.0f / (float)per_img, inv_px = 1.0f / (float)px, inv_B = 1.0f / (float)B;
+  float4* const stage0 = smem4 + warp * (2 * kPatchF4);
+  const unsigned stage0_s = (unsigned)__cvta_generic_to_shared(stage0);
+
+  struct Patch { int im, b, x0, y0; };
+  auto decode = [&](int p) {
+    Patch q;
+    const int ib = fast_div(p, per_img, inv_per_img), rem = p - ib * per_img;     // ib = image * B + b
+    const int pyi = fast_div(rem, px, inv_px), pxi = rem - pyi * px;
+    q.im = fast_div(ib, B, inv_B); q.b = ib - q.im * B;
+    q.x0 = pxi * 32; q.y0 = pyi * 16;
+    return q;
+  };
+  auto issue = [&](const Patch& q, int stage) {
+    const float* __restrict__ img = reinterpret_cast<const float*>(q.im == 0 ? job.tgt : job.src[q.im > 0 ? q.im - 1 : 0]);
+    const float* __restrict__ g = img + (((size_t)q.b * H + q.y0) * W + q.x0) * 3;
+    const int rows = min(16, H - q.y0), row_f4 = min(32, W - q.x0) * 3 / 4;       // 16-byte chunks per row
+    const unsigned dst = stage0_s + (unsigned)(stage * kPatchF4 * 16);
+#pragma unroll
+    for (int k = 0; k < kPatchF4 / 32; ++k) {
+      const int c = lane + 32 * k, r = c / 24, cc = c - r * 24;
+      if (r < rows && cc < row_f4)
+        asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst + (unsigned)c * 16u),
+                     "l"(g + (size_t)r * W * 3 + cc * 4), "l"(pol) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  int p = warp0;
+  if (p >= n_patches) return;
+  Patch cur = decode(p);
+  issue(cur, 0);
+  for (int it = 0; p < n_patches; ++it, p += n_warps) {
+    const int pn = p + n_warps;
+    Patch nxt = cur;
+    if (pn < n_patches) {
+      nxt = decode(pn);
+      issue(nxt, (it + 1) & 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncwarp();
+    const int x = cur.x0 + lx * 4, y = cur.y0 + ly * 4;
+    const bool in_x = x < W;                      // a thread's 4 columns are inside or outside together (W % 4 == 0)
+    float a[4][12];                               // [row][pixel * 3 + channel]
+    {
+      const float4* t = stage0 + (it & 1) * kPatchF4 + (ly * 4) * 24 + lx * 3;
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const float4 q = t[r * 24 + k];
+          a[r][4 * k] = q.x; a[r][4 * k + 1] = q.y; a[r][4 * k + 2] = q.z; a[r][4 * k + 3] = q.w;
+        }
+    }
+    // the image kind is warp-uniform: one specialised body each (no per-store branches)
+    const int im = cur.im, b = cur.b;
+    if (im == 0) {
+      float* scr = reinterpret_cast<float*>(stage0 + (it & 1) * kPatchF4);   // this stage is spent once every lane has read it
+      __syncwarp();
+      prep_patch<LOG2F, true, false>(PrepSink<true, false>{job, 0, b, H, W, scr}, a, x, y, lx, ly, in_x);
+      __syncwarp();
+      prep_flush_tgt<LOG2F>(job, scr, b, cur.x0, cur.y0, lane);
+    } else if (job.src_x[im - 1][0] == nullptr) {
+      prep_patch<LOG2F, false, false>(PrepSink<false, false>{job, im - 1, b, H, W, nullptr}, a, x, y, lx, ly, in_x);
+    } else {
+      prep_patch<LOG2F, false, true>(PrepSink<false, true>{job, im - 1, b, H, W, nullptr}, a, x, y, lx, ly, in_x);
+    }
+    __syncwarp();                                 // every lane has read this stage before the next issue refills it
     cur = nxt;
   }
 }
@@ -1382,7 +1694,31 @@ int launch_prep(const PrepImgJob& job, const PrepJob& prep, bool u8, cudaStream_
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   cudaError_t e = cudaSuccess;
-  if (u8) {
+  // float32 images whose rows are 16-byte aligned take the register form (no shared memory, a warp per 32 x 16 patch)
+  bool reg_form = !u8 && job.W % 4 == 0 && job.S <= 5 && aligned(job.tgt, 16);
+  for (int v = 0; v < job.V; ++v) reg_form = reg_form && aligned(job.src[v], 16);
+#ifdef VSL_PREP_STAGED
+  reg_form = false;
+#endif
+  if (reg_form) {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int n_patches = (job.V + 1) * job.B * ((job.W + 31) / 32) * ((job.H + 15) / 16);
+    cfg.gridDim = dim3(std::min((n_patches + kPrepRegThreads / 32 - 1) / (kPrepRegThreads / 32), sms * kPrepRegBlocks));
+    cfg.blockDim = dim3(kPrepRegThreads);
+    cfg.dynamicSmemBytes = kPrepRegSmem;
+    auto go = [&](auto kern) {
+      cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPrepRegSmem);
+      return e2 != cudaSuccess ? e2 : cudaLaunchKernelEx(&cfg, kern, job, prep);
+    };
+    switch (job.S) {
+      case 1: e = go(loss_prep_reg_kernel<0>); break;
+      case 2: e = go(loss_prep_reg_kernel<1>); break;
+      case 3: e = go(loss_prep_reg_kernel<2>); break;
+      case 4: e = go(loss_prep_reg_kernel<3>); break;
+      default: e = go(loss_prep_reg_kernel<4>); break;
+    }
+  } else if (u8) {
     switch (job.S) {
       case 1: e = cudaLaunchKernelEx(&cfg, loss_prep_kernel<0, true>, job, prep); break;
       case 2: e = cudaLaunchKernelEx(&cfg, loss_prep_kernel<1, true>, job, prep); break;
@@ -1414,6 +1750,21 @@ size_t vsl_loss_ws_bytes(const VslLossDesc* d) {
   WsLayout L;
   layout(d, &L);
   return L.total;
+}
+
+int vsl_loss_ws_layout(const VslLossDesc* d, long long* out) {
+  const int rc = check_desc(d);
+  if (rc != VSL_OK) return rc;
+  VSL_REQUIRE(out, VSL_E_NULL);
+  WsLayout L;
+  layout(d, &L);
+  for (int s = 0; s < d->S; ++s) {
+    out[s] = s == 0 ? (d->img_format != VSL_IMG_F32 ? (long long)L.tgt0 : -1ll)
+                    : (long long)(L.tgt_pyr + sizeof(float) * L.tgt_off[s]);
+    for (int v = 0; v < d->V; ++v)
+      out[d->S + v * d->S + s] = (long long)(L.src_pyr + sizeof(float4) * (L.src_view * (size_t)v + L.src_off[s]));
+  }
+  return VSL_OK;
 }
 
 }  // extern "C"

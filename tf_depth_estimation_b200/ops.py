@@ -830,6 +830,25 @@ class ViewSynthesisPlan(object):
         check(fn(*args, _stream() if stream is None else stream))
         return self.losses
 
+    def prep_levels(self):
+        """Views of what the prep launch of the last step left in the workspace: (target RGB levels [B,Hs,Ws,3] -- level
+        0 is None unless the images are uint8 --, per source view its zero-bordered RGBA levels [B,Hs+4,Ws+4,4]).
+        For tests and tools."""
+        import ctypes
+        n = self.S + self.V * self.S
+        offs = (ctypes.c_longlong * n)()
+        check(_lib.load().vsl_loss_ws_layout(self.desc, offs))
+
+        def view(o, shape):
+            cnt = 1
+            for d in shape:
+                cnt *= d
+            return self.ws[o:o + 4 * cnt].view(torch.float32).view(*shape)
+        B, H, W, S, V = self.B, self.H, self.W, self.S, self.V
+        tgt = [view(offs[s], (B, H >> s, W >> s, 3)) if offs[s] >= 0 else None for s in range(S)]
+        srcs = [[view(offs[S + v * S + s], (B, (H >> s) + 4, (W >> s) + 4, 4)) for s in range(S)] for v in range(V)]
+        return tgt, srcs
+
     def set_profile_events(self, begin=None, end=None):
         """cudaEvent_t handles (ints) recorded immediately around the fused loss kernel; None switches off."""
         self.desc.ev_main_begin, self.desc.ev_main_end = begin, end
