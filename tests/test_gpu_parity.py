@@ -326,7 +326,7 @@ def test_consistency_entry_argument_checks():
 
 
 @pytest.mark.parametrize('shape', [(2, 32, 64, 4, 2), (1, 48, 104, 4, 1), (3, 16, 416, 1, 2), (2, 20, 36, 3, 2),
-                                   (1, 64, 96, 5, 3), (2, 18, 30, 2, 1), (1, 96, 96, 6, 1), (2, 128, 416, 4, 2)])
+                                   (1, 64, 96, 5, 3), (2, 18, 30, 2, 1), (1, 96, 96, 6, 1), (1, 40, 104, 4, 2), (2, 128, 416, 4, 2)])
 def test_prep_launch_products_bit_exact(shape):
     """What launch 1 leaves in the workspace -- resize_area levels of the target (RGB) and of every source view
     (zero-bordered RGBA; the fourth channel zero, or the source view's depth map with the consistency term) -- is

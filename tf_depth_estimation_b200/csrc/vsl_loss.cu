@@ -758,23 +758,42 @@ loss_finalize_kernel(const LossParams P, const float* __restrict__ poses, const 
     return;
   }
 
-  for (int sc = 0; sc < P.S; ++sc) {
-    const int per_b = P.bands[sc] * P.strips[sc];
-    const float* p = P.partials + (size_t)(P.item_begin[sc] + b * per_b) * N;
-    for (int c = lane; c < N; c += 32) {
-      double acc = 0.0;
-      constexpr int U = 8;                     // rows in flight per lane
-      for (int i0 = warp; i0 < per_b; i0 += NW * U) {
+  // the tile rows of this image at every scale as ONE list (row k of scale sc sits at item_begin[sc] + b * per_b + k):
+  // warp w takes rows w, w + NW, ... of the list, lane = column, and has all of its rows in flight at once -- one
+  // round trip to L2 for the whole image instead of one per scale
+  {
+    int first[VSL_MAX_SCALES + 1];
+    first[0] = 0;
+#pragma unroll
+    for (int sc = 0; sc < VSL_MAX_SCALES; ++sc) first[sc + 1] = first[sc] + (sc < P.S ? P.bands[sc] * P.strips[sc] : 0);
+    const int total = first[VSL_MAX_SCALES];
+    constexpr int U = 12;                       // rows in flight per lane
+    for (int col = lane; col < N; col += 32) {  // N = 4 + 12 V columns: a second pass for three and four views
+      double acc[VSL_MAX_SCALES];
+#pragma unroll
+      for (int sc = 0; sc < VSL_MAX_SCALES; ++sc) acc[sc] = 0.0;
+      for (int k0 = warp; k0 < total; k0 += NW * U) {
         float q[U];
+        int qs[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const int i = i0 + u * NW;
-          q[u] = i < per_b ? p[(size_t)i * N + c] : 0.f;
+          const int k = k0 + u * NW;
+          int sc = 0, f0 = 0, pb = first[1];
+#pragma unroll
+          for (int t = 1; t < VSL_MAX_SCALES; ++t)
+            if (t < P.S && k >= first[t]) { sc = t; f0 = first[t]; pb = first[t + 1] - first[t]; }
+          qs[u] = k < total ? sc : -1;
+          const int item = P.item_begin[sc] + b * pb + (k - f0);
+          q[u] = k < total ? P.partials[(size_t)item * N + col] : 0.f;
         }
 #pragma unroll
-        for (int u = 0; u < U; ++u) acc += (double)q[u];
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+          for (int sc = 0; sc < VSL_MAX_SCALES; ++sc) acc[sc] += qs[u] == sc ? (double)q[u] : 0.0;
       }
-      part[warp][sc][c] = acc;
+#pragma unroll
+      for (int sc = 0; sc < VSL_MAX_SCALES; ++sc)
+        if (sc < P.S) part[warp][sc][col] = acc[sc];
     }
   }
   __syncthreads();
@@ -1601,6 +1620,7 @@ void layout(const VslLossDesc* d, WsLayout* L) {
   }
   L->item_begin[d->S] = n;
   L->n_items = n;
+  sl = round_up(sl, 2);        // every view's block starts 32-byte aligned (the prep launch stores pixel pairs)
   L->src_view = sl;
   L->xf = 0;
   L->xq = round_up(sizeof(Xform) * (size_t)d->S * d->V * d->B, 256);
