@@ -295,6 +295,17 @@ int vsl_dp_step(unsigned* const* peer_flags, const float* const* peer_grads, flo
                 float eps, float grad_scale, int* state, int* timed_out /*nullable*/, long long timeout_ms,
                 vsl_stream_t stream);
 
+/*      vsl_dp_step through the NVSwitch's multicast engine (NVLS): mc_grads / mc_params are the MULTICAST addresses of
+ *      the gradient / parameter arenas (every rank's arena bound to one multicast object at the same offset, e.g.
+ *      torch.distributed._symmetric_memory's multicast_ptr), own_params this rank's own parameter arena.  The shard's
+ *      gradient sum is ONE multimem.ld_reduce per 16 bytes (added inside the switch), the new parameters leave as ONE
+ *      multimem.st (replicated by the switch): about half the link traffic of the peer-to-peer form.  Same barriers,
+ *      state block and failure behaviour as vsl_dp_step; the in-switch sum has its own fixed association order
+ *      (deterministic, replicas bit-identical; not bit-identical to the rank-ordered sum).  world >= 2. */
+int vsl_dp_step_mc(unsigned* const* peer_flags, const float* mc_grads, float* mc_params, const float* own_params, int rank,
+                   int world, float* m_shard, float* v_shard, long long lo, long long hi, float lr, float beta1, float beta2,
+                   float eps, float grad_scale, int* state, int* timed_out, long long timeout_ms, vsl_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -113,7 +113,8 @@ def measure(rank, world, dev, global_batch=256, steps=10, warmup=3, optim='peer'
         PoseExpNet(V).to(dev).to(memory_format=torch.channels_last)
     params = [p for p in list(disp_net.parameters()) + list(pose_net.parameters())]
     if optim == 'peer':
-        dp = vdist.PeerDataParallelAdam([p.shape for p in params], dev, lr=2e-4, beta1=0.9, timeout_s=timeout_s)
+        dp = vdist.PeerDataParallelAdam([p.shape for p in params], dev, lr=2e-4, beta1=0.9, timeout_s=timeout_s,
+                                        multicast=os.environ.get('VSL_MULTICAST', 'auto') if os.environ.get('VSL_MULTICAST', 'auto') != '0' else False)
     else:
         dp = vdist.DataParallelAdam([p.shape for p in params], dev, lr=2e-4, beta1=0.9, bucket_bytes=1 << 30)
     for p, pv, gv in zip(params, dp.params, dp.grads):

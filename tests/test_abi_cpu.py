@@ -112,6 +112,12 @@ def test_error_codes_of_the_extension_and_optimiser_entries(lib):
     assert lib.vsl_peer_barrier(ptrs, 0, 2, 1, None, -5, None) == -2                   # negative timeout
     # the graph-capturable whole step needs its device-resident state block
     assert lib.vsl_dp_step(ptrs, ptrs, ptrs, 0, 2, 16, 16, 0, 8, 1e-3, 0.9, 0.999, 1e-8, 1.0, None, None, 0, None) == -1
+    # the multicast (NVLS) form: NULL addresses / state, a single rank, unaligned addresses, a shard off the 16-byte grid
+    assert lib.vsl_dp_step_mc(ptrs, 16, 16, 16, 0, 2, 16, 16, 0, 8, 1e-3, 0.9, 0.999, 1e-8, 1.0, None, None, 0, None) == -1
+    assert lib.vsl_dp_step_mc(ptrs, None, 16, 16, 0, 2, 16, 16, 0, 8, 1e-3, 0.9, 0.999, 1e-8, 1.0, 16, None, 0, None) == -1
+    assert lib.vsl_dp_step_mc(ptrs, 16, 16, 16, 0, 1, 16, 16, 0, 8, 1e-3, 0.9, 0.999, 1e-8, 1.0, 16, None, 0, None) == -2
+    assert lib.vsl_dp_step_mc(ptrs, 16, 16, 16, 0, 2, 16, 16, 2, 8, 1e-3, 0.9, 0.999, 1e-8, 1.0, 16, None, 0, None) == -2
+    assert lib.vsl_dp_step_mc(ptrs, 20, 16, 16, 0, 2, 16, 16, 0, 8, 1e-3, 0.9, 0.999, 1e-8, 1.0, 16, None, 0, None) == -4
     assert lib.vsl_scale(None, 16, 4, 16, None, None) == -1 and lib.vsl_scale(16, 16, 0, 16, None, None) == -2
     assert lib.vsl_scale(20, 16, 4, 16, None, None) == -4
     assert lib.vsl_ipc_get_handle(None, None) == -1 and lib.vsl_ipc_open(None, None) == -1

@@ -84,7 +84,7 @@ def test_peer_data_parallel_adam_single_rank():
         assert float((got[i].double() - ref[i][0]).abs().max()) <= 1e-6 * float(ref[i][0].abs().max()) + 1e-9
 
 
-def _peer_worker(rank, world, port, out):
+def _peer_worker(rank, world, port, out, multicast=False):
     import os
     import torch.distributed as dist
     os.environ['MASTER_ADDR'], os.environ['MASTER_PORT'] = '127.0.0.1', str(port)
@@ -92,7 +92,12 @@ def _peer_worker(rank, world, port, out):
     dev = torch.device('cuda', rank)
     dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
     shapes = [(301, 7), (64,), (5,), (4099,)]
-    peer = vdist.PeerDataParallelAdam(shapes, dev, lr=1e-2)
+    if multicast and not vdist.MulticastArena.available(dev):
+        torch.save('no multicast', out % rank)
+        dist.destroy_process_group()
+        return
+    peer = vdist.PeerDataParallelAdam(shapes, dev, lr=1e-2, multicast=multicast)
+    assert bool(peer.mc) == bool(multicast)
     assert peer.hi - peer.lo > 0 and (peer.lo % 4, peer.hi % 4) == (0, 0)
     for t in (1, 2, 3):
         for r in range(world):                                   # every rank can regenerate every rank's gradient
@@ -139,6 +144,35 @@ def test_peer_data_parallel_adam_two_ranks(tmp_path):
             ref[i] = O.adam_step_tf(ref[i][0], gsum[i].float().double(), ref[i][1], ref[i][2], t, 1e-2)
     for i in range(len(shapes)):
         assert torch.equal(a[i], b[i])                           # replicas bit-identical
+        assert float((a[i].double() - ref[i][0]).abs().max()) <= 2e-6 * float(ref[i][0].abs().max()) + 1e-9
+
+
+@pytest.mark.skipif(not _two_peer_gpus(), reason='needs 2 GPUs of one node behind an NVSwitch (multicast / NVLS)')
+def test_peer_data_parallel_adam_two_ranks_multicast(tmp_path):
+    """The same step through the switch's multicast engine (dp_adam_mc_kernel: multimem.ld_reduce / multimem.st on a
+    symmetric allocation): replicas bit-identical, parameters equal to the oracle's Adam on the summed gradients (two
+    addends: the in-switch sum has only one association order)."""
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(('127.0.0.1', 0)); port = s.getsockname()[1]; s.close()
+    out = str(tmp_path / 'rank%d.pt')
+    mp.spawn(_peer_worker, args=(2, port, out, True), nprocs=2, join=True)
+    a, b = torch.load(out % 0), torch.load(out % 1)
+    if isinstance(a, str):
+        pytest.skip('this node has no multicast support')
+    shapes = [(301, 7), (64,), (5,), (4099,)]
+    ref = [(torch.zeros(s, dtype=torch.float64), torch.zeros(s, dtype=torch.float64), torch.zeros(s, dtype=torch.float64))
+           for s in shapes]
+    for t in (1, 2, 3):
+        gsum = [torch.zeros(s, dtype=torch.float64) for s in shapes]
+        for r in range(2):
+            gen = torch.Generator().manual_seed(100 * t + r)
+            for acc, s in zip(gsum, shapes):
+                acc += torch.randn(s, generator=gen).double()
+        for i in range(len(shapes)):
+            ref[i] = O.adam_step_tf(ref[i][0], gsum[i].float().double(), ref[i][1], ref[i][2], t, 1e-2)
+    for i in range(len(shapes)):
+        assert torch.equal(a[i], b[i])
         assert float((a[i].double() - ref[i][0]).abs().max()) <= 2e-6 * float(ref[i][0].abs().max()) + 1e-9
 
 

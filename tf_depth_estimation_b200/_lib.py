@@ -95,6 +95,9 @@ SIGNATURES = {
     'vsl_dp_step': (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p)] * 3 + [ctypes.c_int] * 2 + [_c_float_p] * 2 +
                     [ctypes.c_longlong] * 2 + [ctypes.c_float] * 5 + [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong,
                                                                      _c_stream]),
+    'vsl_dp_step_mc': (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p)] + [ctypes.c_void_p] * 3 + [ctypes.c_int] * 2 +
+                       [_c_float_p] * 2 + [ctypes.c_longlong] * 2 + [ctypes.c_float] * 5 +
+                       [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong, _c_stream]),
     'vsl_ssim_ws_bytes': (ctypes.c_size_t, [ctypes.c_int] * 4),
     'vsl_ssim_fwd': (ctypes.c_int, [_c_float_p] * 2 + [ctypes.c_int] * 4 + [_c_float_p] * 2 + [ctypes.c_void_p, _c_stream]),
     'vsl_ssim_bwd': (ctypes.c_int, [_c_float_p] * 2 + [ctypes.c_int] * 4 + [_c_float_p] * 2 + [ctypes.c_int] +

@@ -147,6 +147,70 @@ dp_adam_kernel(PeerPtrs pp, int world_rt, int rank, float* __restrict__ m, float
   }
 }
 
+// The same step through the NVSwitch's multicast engine (NVLS): the gradient and parameter arenas of all ranks are
+// bound to one multicast object, and rank r touches its shard through the multicast address only --
+//   1. multimem.ld_reduce.add.v4.f32: ONE load returns the sum over every rank's copy, added inside the switch
+//      -- the reduce-scatter without world - 1 separate pulls;
+//   2. Adam on the shard;
+//   3. multimem.st.v4.f32: ONE store lands in every rank's parameter arena, replicated by the switch -- the all-gather.
+// Per rank the links carry about one arena in and one out instead of 2 (world - 1) / world each way.  The in-switch
+// sum has its own (fixed) association order: deterministic, replicas bit-identical (one owner per element), but
+// not bit-identical to the rank-ordered sum of dp_adam_kernel.
+// Blocks per SM of the multicast form: the reduce phase loads the links outbound (every GPU feeds the switch its copy
+// of every shard), the broadcast phase inbound -- with the whole shard in flight as ONE wave the phases run one after
+// the other on every GPU at once; fewer resident blocks looping over the shard let the stores of one trip overlap the
+// loads of the next.
+constexpr int kMcBlocksPerSm = 8;
+__global__ void __launch_bounds__(256)
+dp_adam_mc_kernel(const float* __restrict__ mc_grad, float* __restrict__ mc_param, const float* __restrict__ own_param,
+                  float* __restrict__ m, float* __restrict__ v, long long lo, long long n4, AdamHyper hy,
+                  const int* __restrict__ state, const volatile int* timed_out) {
+  constexpr int U = 4;
+  __shared__ AdamConsts sc;
+  __shared__ int s_dead;
+  if (threadIdx.x == 0) {
+    s_dead = state != nullptr ? (state[2] != 0) : ((timed_out != nullptr && *timed_out != 0) ? 1 : 0);
+    sc = adam_consts(hy, state != nullptr ? state[1] + 1 : hy.step);
+  }
+  __syncthreads();
+  if (s_dead) return;
+  const AdamConsts c = sc;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+  float4* m4 = reinterpret_cast<float4*>(m);
+  float4* v4 = reinterpret_cast<float4*>(v);
+  const long long lo4 = lo / 4;
+  const float4* own_p = reinterpret_cast<const float4*>(own_param) + lo4;
+  const float4* g_mc = reinterpret_cast<const float4*>(mc_grad) + lo4;
+  float4* p_mc = reinterpret_cast<float4*>(mc_param) + lo4;
+  for (long long i0 = tid; i0 < n4; i0 += nth * U) {
+    float4 g[U], p[U], mm[U], vv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * nth;
+      g[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < n4)
+        asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(g[u].x), "=f"(g[u].y), "=f"(g[u].z), "=f"(g[u].w) : "l"(g_mc + i) : "memory");
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * nth;
+      if (i < n4) { p[u] = own_p[i]; mm[u] = m4[i]; vv[u] = v4[i]; }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * nth;
+      if (i < n4) {
+        adam_one(p[u].x, g[u].x, mm[u].x, vv[u].x, c); adam_one(p[u].y, g[u].y, mm[u].y, vv[u].y, c);
+        adam_one(p[u].z, g[u].z, mm[u].z, vv[u].z, c); adam_one(p[u].w, g[u].w, mm[u].w, vv[u].w, c);
+        m4[i] = mm[u]; v4[i] = vv[u];
+        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p_mc + i), "f"(p[u].x),
+                     "f"(p[u].y), "f"(p[u].z), "f"(p[u].w) : "memory");
+      }
+    }
+  }
+}
+
 // Barrier across the GPUs of a node through peer-mapped flag words.  flags of rank q: unsigned[kMaxPeers], word r is
 // written by rank r only.  One block of `world` threads: thread r publishes `epoch` into rank r's word [rank], then
 // waits until this GPU's word [r] has reached `epoch`.  Everything this GPU wrote before (peer stores of the
@@ -354,6 +418,38 @@ int vsl_dp_step(unsigned* const* peer_flags, const float* const* peer_grads, flo
   rc = launch_dp_adam(peer_grads, peer_params, rank, world, m_shard, v_shard, lo, hi, hy, state, timed_out, st);
   if (rc != VSL_OK) return rc;
   // the trailing barrier also advances the Adam step count (after every block of the update has read it)
+  return launch_barrier(peer_flags, rank, world, 0u, state, 1, timed_out, timeout_ms, st);
+}
+
+int vsl_dp_step_mc(unsigned* const* peer_flags, const float* mc_grads, float* mc_params, const float* own_params, int rank,
+                   int world, float* m_shard, float* v_shard, long long lo, long long hi, float lr, float beta1, float beta2,
+                   float eps, float grad_scale, int* state, int* timed_out, long long timeout_ms, vsl_stream_t stream) {
+  VSL_REQUIRE(state && mc_grads && mc_params && own_params && m_shard && v_shard, VSL_E_NULL);
+  VSL_REQUIRE(world >= 2 && world <= kMaxPeers && rank >= 0 && rank < world, VSL_E_SHAPE);
+  VSL_REQUIRE(lo >= 0 && hi >= lo && lo % 4 == 0 && hi % 4 == 0, VSL_E_SHAPE);
+  VSL_REQUIRE(aligned(mc_grads, 16) && aligned(mc_params, 16) && aligned(own_params, 16) && aligned(m_shard, 16) &&
+                  aligned(v_shard, 16), VSL_E_ALIGN);
+  cudaStream_t st = (cudaStream_t)stream;
+  const AdamHyper hy = {lr, beta1, beta2, eps, grad_scale, 0};
+  {   // resident before the first barrier spins (see vsl_dp_step)
+    cudaFuncAttributes fa;
+    const cudaError_t e = cudaFuncGetAttributes(&fa, (const void*)dp_adam_mc_kernel);
+    if (e != cudaSuccess) return (int)e;
+  }
+  int rc = launch_barrier(peer_flags, rank, world, 0u, state, 0, timed_out, timeout_ms, st);
+  if (rc != VSL_OK) return rc;
+  if (hi > lo) {
+    const long long n4 = (hi - lo) / 4;
+    const long long want = (n4 + 4 * 256 - 1) / (4 * 256);
+    int per_sm = kMcBlocksPerSm;
+#ifdef VSL_DP_TIMING_EXPERIMENTS   // never defined for the shipped library
+    if (getenv("VSL_MC_BLOCKS_PER_SM")) per_sm = atoi(getenv("VSL_MC_BLOCKS_PER_SM"));
+#endif
+    const int blocks = (int)(want < 148 * per_sm ? want : 148 * per_sm);
+    dp_adam_mc_kernel<<<blocks, 256, 0, st>>>(mc_grads, mc_params, own_params, m_shard, v_shard, lo, n4, hy, state, timed_out);
+    rc = launch_status();
+    if (rc != VSL_OK) return rc;
+  }
   return launch_barrier(peer_flags, rank, world, 0u, state, 1, timed_out, timeout_ms, st);
 }
 

@@ -187,6 +187,64 @@ class PeerArena(object):
         self.local = None
 
 
+class MulticastArena(object):
+    """PeerArena's interface over a symmetric allocation that is ALSO bound to an NVSwitch multicast object (NVLS):
+    base[r] = rank r's block as mapped here, mc = the multicast address of the same block (a multimem.ld_reduce
+    through it sums every rank's copy inside the switch, a multimem.st lands in every rank's copy).  The
+    allocation, the fabric-handle exchange and the multicast binding are torch.distributed._symmetric_memory's
+    (CUDA VMM + cuMulticast*: plumbing); the kernels that use the addresses are csrc/vsl_optim.cu's.
+    available(device) says whether the driver / switch support it; the constructor raises if they do not."""
+
+    @staticmethod
+    def available(device):
+        try:
+            from torch._C._autograd import DeviceType
+            from torch._C._distributed_c10d import _SymmetricMemory
+            device = torch.device(device)
+            idx = device.index if device.index is not None else torch.cuda.current_device()
+            return bool(dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 and
+                        _SymmetricMemory.has_multicast_support(DeviceType.CUDA, idx))
+        except Exception:
+            return False
+
+    def __init__(self, nbytes, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.nbytes = (int(nbytes) + 255) // 256 * 256
+        with torch.cuda.device(self.device):
+            self._t = symm.empty(self.nbytes // 4, dtype=torch.float32, device=self.device)
+            self._t.zero_()
+            torch.cuda.synchronize()
+            self._hdl = symm.rendezvous(self._t, group)
+        self.base = [int(p) for p in self._hdl.buffer_ptrs]
+        self.local = self.base[self.rank]
+        self.mc = int(self._hdl.multicast_ptr or 0)
+        if self.mc == 0:
+            raise RuntimeError('the symmetric allocation has no multicast address (NVLS unavailable on this node)')
+        if self.local != self._t.data_ptr():
+            raise RuntimeError('symmetric memory: the local buffer pointer is not the tensor the arena was built from')
+        self._group = group
+        dist.barrier(group=group)
+
+    view = None   # set below (PeerArena.view)
+
+    def close(self):
+        if self.local is None:
+            return
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize()
+            if dist.is_initialized():
+                dist.barrier(group=self._group)
+        self.local, self._hdl, self._t = None, None, None
+
+
+MulticastArena.view = PeerArena.view
+
+
 class InProcessArena(object):
     """PeerArena's interface for `world` ranks that live in ONE process (one block per rank, on the given devices --
     which may all be the same GPU): the blocks are plain cudaMalloc allocations, so base[r] is valid for every rank
@@ -251,7 +309,7 @@ class PeerDataParallelAdam(object):
     """
 
     def __init__(self, shapes, device, lr, beta1=0.9, beta2=0.999, eps=1e-8, group=None, grad_scale=1.0,
-                 timeout_s=120.0, arena=None):
+                 timeout_s=120.0, arena=None, multicast=False):
         from . import _lib
         self._lib = _lib
         self.lib = _lib.load()
@@ -259,7 +317,15 @@ class PeerDataParallelAdam(object):
         self.shapes, sizes, self.offsets, self.numel = _flat_layout(shapes)
         # local block: [flags 256 B][state: epoch, t (device ints), padded to 256 B][parameters][gradients]
         arena_bytes = 512 + 8 * self.numel
+        # multicast=True: the arenas are bound to an NVSwitch multicast object and the step sums / broadcasts through
+        # it (dp_adam_mc_kernel); 'auto': that, where the node supports it, else the peer-to-peer form
+        # (per rank and direction the links carry 2 (N - 1) / N arenas peer to peer, 1 + 1 / N through the switch:
+        # 'auto' takes the multicast form from 4 ranks up)
+        if arena is None and multicast and (multicast != 'auto' or (
+                MulticastArena.available(device) and dist.get_world_size(group) >= 4)):
+            arena = MulticastArena(arena_bytes, device, group)
         self.arena = arena if arena is not None else PeerArena(arena_bytes, device, group)
+        self.mc = int(getattr(self.arena, 'mc', 0) or 0)
         if self.arena.nbytes < arena_bytes:
             raise ValueError('arena too small: %d < %d bytes' % (self.arena.nbytes, arena_bytes))
         self.world, self.rank = self.arena.world, self.arena.rank
@@ -308,6 +374,13 @@ class PeerDataParallelAdam(object):
         self._raise_if_timed_out()
         self.t += 1
         st = torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
+        if self.mc and self.world > 1:
+            self._lib.check(self.lib.vsl_dp_step_mc(self._pf, self.mc + 512 + 4 * self.numel, self.mc + 512,
+                                                    self.arena.local + 512, self.rank, self.world,
+                                                    self.m_shard.data_ptr(), self.v_shard.data_ptr(), self.lo, self.hi,
+                                                    *self.hyper, self.grad_scale, self.state.data_ptr(),
+                                                    self.timed_out.data_ptr(), self.timeout_ms, st))
+            return self.t
         self._lib.check(self.lib.vsl_dp_step(self._pf, self._pg, self._pp, self.rank, self.world,
                                              self.m_shard.data_ptr(), self.v_shard.data_ptr(), self.lo, self.hi,
                                              *self.hyper, self.grad_scale, self.state.data_ptr(),
