@@ -226,6 +226,33 @@ int vsl_loss_consist_fwd_bwd(const VslLossDesc* d, const float* tgt, const float
                              float* const* g_src_x_pyr /*host array V*S, nullable*/, float* g_poses,
                              float* const* g_logits_pyr, void* ws, vsl_stream_t stream);
 
+/* ---- the flow-and-depth loss of the DeMoN-pair family: the per-scale loop of train_optflow_combine.py:138-240
+ *      (optflow_warp utils.py:201-217 + depth_optflow utils.py:321-338 on the same sampler core),
+ *      forward AND backward in one pass.  Per scale s, every weight / 2^s:
+ *        smooth   smooth_weight * (compute_smooth_loss(pred_depth_s) + ...(flow_x_s) + ...(flow_y_s))      :142-150
+ *        depth    depth_weight * mean |label_s - pred_depth_s|                                             :163-164
+ *        pixel    data_weight * (mean(|warp(right_s; 1/pred_depth_s, proj, K_s) - left_s| * wmask3)
+ *                              + mean(|optflow_warp(right_s, flow_x_s, flow_y_s) - left_s| * wmask3))      :169-197
+ *        optflow  optflow_weight * (mean |flow_x_s - fx*| + mean |flow_y_s - fy*|),
+ *                 (fx*, fy*) = depth_optflow(coords of the warp by 1/label_s)                              :204-210
+ *      wmask3 = the validity mask of that ground-truth-depth warp on three channels (no gradient: data only);
+ *      left_s / right_s / label_s = resize_area levels.  pred_depth is INVERSE depth (the warp uses 1/x).
+ *      losses[5] = (depth, smooth, optflow, pixel, their sum = total_loss :240); gradients are those of
+ *      losses[4] * loss_scale w.r.t. the three prediction pyramids.  proj: the loader's [B,4,4] target-to-source
+ *      matrix (tgt2src_projs[:,0], :173).  H, W divisible by 2^(S-1); coarsest level at least 3 x 3. */
+typedef struct {
+  int B, H, W, S;
+  float smooth_weight, depth_weight, data_weight, optflow_weight;
+  float loss_scale;
+} VslFlowLossDesc;
+
+size_t vsl_flow_loss_ws_bytes(const VslFlowLossDesc* d);
+int vsl_flow_loss_fwd_bwd(const VslFlowLossDesc* d, const float* left /*[B,H,W,3]*/, const float* right /*[B,H,W,3]*/,
+                          const float* label /*[B,H,W,1]*/, const float* const* depth_pyr /*host array S x [B,Hs,Ws,1]*/,
+                          const float* const* flowx_pyr, const float* const* flowy_pyr, const float* proj /*[B,4,4]*/,
+                          const float* K_pyr /*[B,S,3,3]*/, float* losses /*device [5]*/, float* const* g_depth_pyr,
+                          float* const* g_flowx_pyr, float* const* g_flowy_pyr, void* ws, vsl_stream_t stream);
+
 /* ---- upstream gradient of the summed loss: dst[0..n) = src[0..n) * (*num / *den) (num, den: device floats; den
  *      NULL means 1).  What TF autodiff does with the incoming gradient of `total_loss` in the reference
  *      (slim.learning.create_train_op, train_depth_then_cam_lr.py:417), applied to the whole gradient arena of a

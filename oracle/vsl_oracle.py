@@ -391,6 +391,57 @@ def view_synthesis_loss(tgt, srcs, x_pyr, poses, K_pyr, logits_pyr=None, mask_py
     return pixel, smooth, exp
 
 
+class FlowLossFlags(object):
+    """The FLAGS train_optflow_combine.py reads in its loss loop (:138-210)."""
+
+    def __init__(self, **kw):
+        self.num_scales = 4
+        self.smooth_weight = 0.5
+        self.depth_weight = 1.0
+        self.data_weight = 1.0
+        self.optflow_weight = 1.0
+        self.__dict__.update(kw)
+
+
+def flow_depth_loss(image_left, image_right, label, pred_depth, pred_optflow_x, pred_optflow_y, proj, K_pyr,
+                    flags=None):
+    """Per-scale loop of train_optflow_combine.py:138-210 (the DeMoN-pair family, BASELINE configs[3]).
+
+    image_left / image_right [B,H,W,3]; label [B,H,W,1] ground-truth INVERSE depth (the warp uses 1/label, :171);
+    pred_depth / pred_optflow_x / pred_optflow_y: lists of S network outputs [B,Hs,Ws,1] (inverse depth, flow in
+    pixels of that scale); proj [B,4,4] the loader's target-to-source transform (tgt2src_projs[:,0], :173);
+    K_pyr [B,S,3,3].  Per scale: second-order smoothness of the three maps; |label_s - pred_depth|; the right image
+    warped by the PREDICTED depth and by the PREDICTED flow, both against the left image and both weighted by the
+    validity mask of the GROUND-TRUTH-depth warp (three channels, no gradient: the label is data); and
+    |pred_flow - depth_optflow(coords of the ground-truth warp)|.  All weights / 2^s.
+    -> (depth_loss, smooth_loss, optflow_loss, pixel_loss)   [total_loss = their sum, :240]
+    """
+    f = flags or FlowLossFlags()
+    B, H, W, _ = image_left.shape
+    zero = torch.zeros((), dtype=image_left.dtype)
+    depth_loss, smooth, smooth_x, smooth_y, optflow, pixel = zero, zero, zero, zero, zero, zero
+    for s in range(f.num_scales):
+        k = 1.0 / (2 ** s)
+        smooth = smooth + f.smooth_weight / (2 ** s) * compute_smooth_loss(pred_depth[s])
+        smooth_x = smooth_x + f.smooth_weight / (2 ** s) * compute_smooth_loss(pred_optflow_x[s])
+        smooth_y = smooth_y + f.smooth_weight / (2 ** s) * compute_smooth_loss(pred_optflow_y[s])
+        hs, ws = int(H / 2 ** s), int(W / 2 ** s)
+        lab = resize_area(label, hs, ws)
+        left = resize_area(image_left, hs, ws)
+        right = resize_area(image_right, hs, ws)
+        depth_loss = depth_loss + torch.abs(lab - pred_depth[s]).mean() * f.depth_weight * k
+        _, coords_gt, wmask = projective_inverse_warp(right, (1.0 / lab).squeeze(3), proj, K_pyr[:, s], 'matrix')[:3]
+        wmask = torch.cat([wmask, wmask, wmask], dim=3)
+        warped = projective_inverse_warp(right, (1.0 / pred_depth[s]).squeeze(3), proj, K_pyr[:, s], 'matrix')[0]
+        pixel = pixel + (torch.abs(warped - left) * wmask).mean() * f.data_weight * k
+        flowed = optflow_warp(right, pred_optflow_x[s], pred_optflow_y[s])
+        pixel = pixel + (torch.abs(flowed - left) * wmask).mean() * f.data_weight * k
+        gx, gy = depth_optflow(coords_gt)
+        optflow = optflow + torch.abs(pred_optflow_x[s] - gx).mean() * f.optflow_weight * k
+        optflow = optflow + torch.abs(pred_optflow_y[s] - gy).mean() * f.optflow_weight * k
+    return depth_loss, (smooth + smooth_x) + smooth_y, optflow, pixel      # :238: the three sums, then added
+
+
 # ----------------------------------------------------------------------------
 # flagged-off extensions named by BASELINE.json but ABSENT from the reference:
 # "parity unpinned -- no reference implementation" (SURVEY.md D1/D2)

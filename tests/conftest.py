@@ -55,6 +55,13 @@ def golden_consist():
     return _load_cases(os.path.join(ROOT, 'tests', 'golden', 'consist_golden.npz'))['lr_consist']
 
 
+@pytest.fixture(scope='session')
+def golden_flow():
+    """tests/golden/flow_golden.npz: the flow-and-depth loss of train_optflow_combine.py:138-240 from the reference's
+    own functions (tests/golden/make_golden_flow.py)."""
+    return _load_cases(os.path.join(ROOT, 'tests', 'golden', 'flow_golden.npz'))['flow']
+
+
 def rel_err(a, b):
     """max |a-b| / max |b| -- the 'relative' of BASELINE.json's gradient tolerance."""
     a, b = torch.as_tensor(a).detach().double().cpu(), torch.as_tensor(b).detach().double().cpu()

@@ -164,6 +164,29 @@ def test_lr_loss_with_consistency_term(golden_consist):
             assert rel_err(g, c['%s_%s' % (n, tag)]) <= tol, (n, tag)
 
 
+def test_flow_depth_loss(golden_flow):
+    """The oracle's flow-and-depth loss reproduces the reference-executed loop of train_optflow_combine.py:138-240:
+    the four terms bit for bit in float32, every gradient within accumulation-order rounding."""
+    c = golden_flow
+    flags = O.FlowLossFlags(**c.flags)
+    S = flags.num_scales
+    for dt, tag, tol in ((torch.float32, 'f32', 2e-6), (torch.float64, 'f64', 1e-12)):
+        pd = [c['pred_depth%d' % s].to(dt).requires_grad_() for s in range(S)]
+        fx = [c['pred_flowx%d' % s].to(dt).requires_grad_() for s in range(S)]
+        fy = [c['pred_flowy%d' % s].to(dt).requires_grad_() for s in range(S)]
+        terms = O.flow_depth_loss(c.left.to(dt), c.right.to(dt), c.label.to(dt), pd, fx, fy, c.proj.to(dt),
+                                  c.K_pyr.to(dt), flags)
+        for t, key in zip(terms, ('depth', 'smooth', 'optflow', 'pixel')):
+            if dt == torch.float32:
+                assert float(t) == float(c['%s_%s' % (key, tag)]), key
+            assert rel_err(t, c['%s_%s' % (key, tag)]) <= tol, (key, tag)
+        grads = torch.autograd.grad(sum(terms), pd + fx + fy)
+        names = ['g_pred_depth%d' % s for s in range(S)] + ['g_pred_flowx%d' % s for s in range(S)] + \
+                ['g_pred_flowy%d' % s for s in range(S)]
+        for g, n in zip(grads, names):
+            assert rel_err(g, c['%s_%s' % (n, tag)]) <= tol, (n, tag)
+
+
 def test_depth_loss_golden_file_is_consistent():
     """tests/golden/depth_losses_golden.npz (the reference's compute_loss_single_depth body executed over the shim)
     against a direct restatement from the oracle's building blocks: pins the fixture and oracle/demon_ops.py."""

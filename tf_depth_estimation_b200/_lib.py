@@ -33,6 +33,12 @@ class VslLossDesc(ctypes.Structure):
                 ('ev_main_begin', ctypes.c_void_p), ('ev_main_end', ctypes.c_void_p)]
 
 
+class VslFlowLossDesc(ctypes.Structure):
+    _fields_ = [('B', ctypes.c_int), ('H', ctypes.c_int), ('W', ctypes.c_int), ('S', ctypes.c_int),
+                ('smooth_weight', ctypes.c_float), ('depth_weight', ctypes.c_float), ('data_weight', ctypes.c_float),
+                ('optflow_weight', ctypes.c_float), ('loss_scale', ctypes.c_float)]
+
+
 # name -> (restype, argtypes); every symbol include/vsl.h declares
 SIGNATURES = {
     'vsl_version': (ctypes.c_int, []),
@@ -80,6 +86,10 @@ SIGNATURES = {
                                            ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_void_p),
                                            _c_float_p, ctypes.POINTER(ctypes.c_void_p), _c_float_p,
                                            ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p, _c_stream]),
+    'vsl_flow_loss_ws_bytes': (ctypes.c_size_t, [ctypes.POINTER(VslFlowLossDesc)]),
+    'vsl_flow_loss_fwd_bwd': (ctypes.c_int, [ctypes.POINTER(VslFlowLossDesc)] + [_c_float_p] * 3 +
+                              [ctypes.POINTER(ctypes.c_void_p)] * 3 + [_c_float_p] * 3 +
+                              [ctypes.POINTER(ctypes.c_void_p)] * 3 + [ctypes.c_void_p, _c_stream]),
     'vsl_scale': (ctypes.c_int, [_c_float_p] * 2 + [ctypes.c_longlong] + [_c_float_p] * 2 + [_c_stream]),
     'vsl_adam_step': (ctypes.c_int, [_c_float_p] * 4 + [ctypes.c_longlong] + [ctypes.c_float] * 4 + [ctypes.c_int, ctypes.c_float, _c_stream]),
     'vsl_peer_alloc': (ctypes.c_int, [ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]),

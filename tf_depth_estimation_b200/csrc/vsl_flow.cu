@@ -1,0 +1,380 @@
+// libvsl: the flow-and-depth loss of the DeMoN-pair family (train_optflow_combine.py:138-240; BASELINE configs[3];
+// SURVEY 8f.1 "same sampler core, different coordinate source"), forward AND backward in one pass.
+//
+// Per scale the reference runs three smoothness terms (compute_smooth_loss of the predicted inverse depth and of
+// both flow channels, :142-150), a supervised |label - pred_depth| (:163-164), THREE samplers -- the right image
+// warped by the ground-truth depth (only its validity mask and coordinates are used, :169-176), by the predicted
+// depth (:178-187) and by the predicted flow (optflow_warp, :190-197) -- and |pred_flow - depth_optflow(ground-truth
+// coordinates)| (:204-210): about 400 TF ops and 60 full-resolution intermediates per scale, forward alone.  Here:
+//
+//   launch 1-2  resize_area pyramids of left / right (RGB) and of the label (1 channel), bit-exact (vsl_pyramid.cuh);
+//               the transform table (K_s^-1, K4_s . T) rides on the first.
+//   launch 3    flow_loss_kernel: one block per 32 x 8 tile of one image at one scale, tiles of every scale in one
+//               grid.  The three predicted maps enter shared memory once with a 2-pixel halo: the smoothness value
+//               (each second difference owned by its top-left element) and its gradient (gather form: the signs of
+//               the ten stencils an element is part of) come from there.  Each thread then does its pixel: the
+//               ground-truth projection (mask + flow target, no gather), the two gathers with the reference's
+//               zero-padding masks, the four absolute errors and every gradient; nothing full-resolution is written
+//               but the three gradient maps.  Coordinates follow the reference's rounding sequence
+//               (vsl_geom.cuh) -- the sampled positions and the mask are bit-identical to the stand-alone warp op.
+//   launch 4    fixed-order double-precision sum of the tile partials -> losses[5].
+//
+// The pose is the loader's 4x4 matrix (tgt2src_projs[:,0], :173) and the label is data: no gradient flows to
+// either; the mask of the ground-truth warp carries none (it depends on data only).
+#include "vsl_common.cuh"
+#include "vsl_prep.cuh"
+#include "vsl_pyramid.cuh"
+
+namespace vsl {
+
+constexpr int kFlowTW = 32, kFlowTH = 8, kFlowHalo = 2;
+constexpr int kFlowSW = kFlowTW + 2 * kFlowHalo, kFlowSH = kFlowTH + 2 * kFlowHalo;   // 36 x 12 per map
+constexpr int kFlowTerms = 4;   // depth, smooth, optflow, pixel (the order the script prints them, :240)
+
+struct FlowParams {
+  int B, S;
+  int Hs[VSL_MAX_SCALES], Ws[VSL_MAX_SCALES];
+  int tiles_x[VSL_MAX_SCALES], tiles_y[VSL_MAX_SCALES];
+  int item_begin[VSL_MAX_SCALES + 1];
+  const float* left[VSL_MAX_SCALES];    // RGB levels
+  const float* right[VSL_MAX_SCALES];
+  const float* label[VSL_MAX_SCALES];   // 1 channel
+  const float* pd[VSL_MAX_SCALES];      // predicted inverse depth, flow x, flow y: [B,Hs,Ws,1]
+  const float* fx[VSL_MAX_SCALES];
+  const float* fy[VSL_MAX_SCALES];
+  float* g_pd[VSL_MAX_SCALES];
+  float* g_fx[VSL_MAX_SCALES];
+  float* g_fy[VSL_MAX_SCALES];
+  const Xform* xf;                      // [S][B]
+  float* partials;                      // [n_items][kFlowTerms]
+  float c_depth[VSL_MAX_SCALES];        // depth_weight / 2^s / (B Hs Ws)
+  float c_pixel[VSL_MAX_SCALES];        // data_weight / 2^s / (B Hs Ws 3)
+  float c_flow[VSL_MAX_SCALES];         // optflow_weight / 2^s / (B Hs Ws)
+  float c_xx[VSL_MAX_SCALES], c_xy[VSL_MAX_SCALES], c_yy[VSL_MAX_SCALES];   // smooth_weight / 2^s / count_k (xy = yx)
+  float loss_scale;
+};
+
+// One map's smoothness at element (i, j) from its shared-memory tile q (q points at the element, row pitch
+// kFlowSW): the weighted |second differences| the element owns, and the gradient it receives from the ten
+// stencils it is part of (my_losses.py:27-36; same stencil algebra as smooth_fwd_kernel / smooth_bwd_kernel).
+VSL_DEV void smooth_at(const float* q, int i, int j, int H, int W, float cxx, float cxy, float cyy, float& val,
+                       float& grad) {
+  constexpr int P = kFlowSW;
+  auto Q = [&](int di, int dj) { return q[di * P + dj]; };
+  auto dxx = [&](int di, int dj) -> float {    // second x-difference owned by (i+di, j+dj), 0 where it does not exist
+    const int jj = j + dj;
+    if (jj < 0 || jj + 2 >= W) return 0.f;
+    return __fsub_rn(__fsub_rn(Q(di, dj + 2), Q(di, dj + 1)), __fsub_rn(Q(di, dj + 1), Q(di, dj)));
+  };
+  auto dyy = [&](int di, int dj) -> float {
+    const int ii = i + di;
+    if (ii < 0 || ii + 2 >= H) return 0.f;
+    return __fsub_rn(__fsub_rn(Q(di + 2, dj), Q(di + 1, dj)), __fsub_rn(Q(di + 1, dj), Q(di, dj)));
+  };
+  auto dxy = [&](int di, int dj, int order) -> float {   // order 0: d/dy of dx, 1: d/dx of dy
+    const int ii = i + di, jj = j + dj;
+    if (ii < 0 || jj < 0 || ii + 1 >= H || jj + 1 >= W) return 0.f;
+    const float q00 = Q(di, dj), q01 = Q(di, dj + 1), q10 = Q(di + 1, dj), q11 = Q(di + 1, dj + 1);
+    return order == 0 ? __fsub_rn(__fsub_rn(q11, q10), __fsub_rn(q01, q00))
+                      : __fsub_rn(__fsub_rn(q11, q01), __fsub_rn(q10, q00));
+  };
+  const float oxx = dxx(0, 0), oyy = dyy(0, 0), oxy = dxy(0, 0, 0), oyx = dxy(0, 0, 1);
+  val = cxx * fabsf(oxx) + cyy * fabsf(oyy) + cxy * (fabsf(oxy) + fabsf(oyx));
+  float g = cxx * (sgn(oxx) - 2.f * sgn(dxx(0, -1)) + sgn(dxx(0, -2)));
+  g += cyy * (sgn(oyy) - 2.f * sgn(dyy(-1, 0)) + sgn(dyy(-2, 0)));
+  g += cxy * (sgn(oxy) - sgn(dxy(0, -1, 0)) - sgn(dxy(-1, 0, 0)) + sgn(dxy(-1, -1, 0)));
+  g += cxy * (sgn(oyx) - sgn(dxy(0, -1, 1)) - sgn(dxy(-1, 0, 1)) + sgn(dxy(-1, -1, 1)));
+  grad = g;
+}
+
+// bilinear_sampler (utils.py:219-308) of a packed RGB level at (x, y) against `tgt`, weighted by `w`:
+// returns sum_c |sample_c - tgt_c| and d(that sum)/dx, d/dy (the sampler's backward, SURVEY 8a "Backward semantics").
+VSL_DEV float sample_error(const float* __restrict__ img, int H, int W, float x, float y, const float (&tgt)[3],
+                           float& dx, float& dy) {
+  const Foot f = footprint(x, y, W, H);
+  const float w00 = __fmul_rn(f.wx0, f.wy0), w01 = __fmul_rn(f.wx0, f.wy1), w10 = __fmul_rn(f.wx1, f.wy0),
+              w11 = __fmul_rn(f.wx1, f.wy1);
+  const float* p00 = img + ((size_t)f.y0 * W + f.x0) * 3;
+  const float* p01 = img + ((size_t)f.y1 * W + f.x0) * 3;
+  const float* p10 = img + ((size_t)f.y0 * W + f.x1) * 3;
+  const float* p11 = img + ((size_t)f.y1 * W + f.x1) * 3;
+  float err = 0.f;
+  dx = 0.f; dy = 0.f;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float i00 = __ldg(p00 + c), i01 = __ldg(p01 + c), i10 = __ldg(p10 + c), i11 = __ldg(p11 + c);
+    const float e = __fsub_rn(blend(w00, w01, w10, w11, i00, i01, i10, i11), tgt[c]);
+    const float g = sgn(e);
+    err += fabsf(e);
+    dx += g * (f.wy0 * (f.mx1 * i10 - f.mx0 * i00) + f.wy1 * (f.mx1 * i11 - f.mx0 * i01));
+    dy += g * (f.wx0 * (f.my1 * i01 - f.my0 * i00) + f.wx1 * (f.my1 * i11 - f.my0 * i10));
+  }
+  return err;
+}
+
+__global__ void __launch_bounds__(kFlowTW * kFlowTH)
+flow_loss_kernel(const FlowParams P) {
+  __shared__ float tile[3][kFlowSH * kFlowSW];
+  __shared__ Xform sx;
+  __shared__ float scratch[kFlowTerms * (kFlowTW * kFlowTH / 32)];
+  const int item = blockIdx.x;
+  int s = 0;
+  while (s + 1 < P.S && item >= P.item_begin[s + 1]) ++s;
+  const int H = P.Hs[s], W = P.Ws[s];
+  const int per_b = P.tiles_x[s] * P.tiles_y[s];
+  const int rem = item - P.item_begin[s];
+  const int b = rem / per_b, r2 = rem - b * per_b;
+  const int ty = r2 / P.tiles_x[s], tx = r2 - ty * P.tiles_x[s];
+  const int y_base = ty * kFlowTH, x_base = tx * kFlowTW;
+  const size_t img0 = (size_t)b * H * W;
+
+  if (threadIdx.x < 21)
+    reinterpret_cast<float*>(&sx)[threadIdx.x] = reinterpret_cast<const float*>(P.xf + (size_t)s * P.B + b)[threadIdx.x];
+  {
+    const float* maps[3] = {P.pd[s] + img0, P.fx[s] + img0, P.fy[s] + img0};
+    for (int e = threadIdx.x; e < 3 * kFlowSH * kFlowSW; e += kFlowTW * kFlowTH) {
+      const int m = e / (kFlowSH * kFlowSW), r = e - m * (kFlowSH * kFlowSW);
+      const int ly = r / kFlowSW, lx = r - ly * kFlowSW;
+      const int gy = y_base - kFlowHalo + ly, gx = x_base - kFlowHalo + lx;
+      const bool in = (unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W;
+      tile[m][r] = in ? __ldg(maps[m] + (size_t)gy * W + gx) : 0.f;
+    }
+  }
+  __syncthreads();
+
+  const int lx = threadIdx.x & (kFlowTW - 1), ly = threadIdx.x / kFlowTW;
+  const int i = y_base + ly, j = x_base + lx;
+  float acc[kFlowTerms] = {0.f, 0.f, 0.f, 0.f};
+  if (i < H && j < W) {
+    const size_t pix = img0 + (size_t)i * W + j;
+    const int c0 = (ly + kFlowHalo) * kFlowSW + lx + kFlowHalo;
+    const float pd = tile[0][c0], fx = tile[1][c0], fy = tile[2][c0];
+    float g_pd, g_fx, g_fy;
+    {   // the three smoothness terms
+      float v0, v1, v2;
+      smooth_at(&tile[0][c0], i, j, H, W, P.c_xx[s], P.c_xy[s], P.c_yy[s], v0, g_pd);
+      smooth_at(&tile[1][c0], i, j, H, W, P.c_xx[s], P.c_xy[s], P.c_yy[s], v1, g_fx);
+      smooth_at(&tile[2][c0], i, j, H, W, P.c_xx[s], P.c_xy[s], P.c_yy[s], v2, g_fy);
+      acc[1] = v0 + v1 + v2;
+    }
+    const float gx = grid_coord(j, W, grid_step(W)), gy = grid_coord(i, H, grid_step(H));
+    const Ray ray = back_project(sx.kinv, gx, gy);
+    const float lab = __ldg(P.label[s] + pix);
+    {   // supervised inverse-depth error, :163-164
+      const float e = __fsub_rn(lab, pd);
+      acc[0] = P.c_depth[s] * fabsf(e);
+      g_pd -= P.c_depth[s] * sgn(e);
+    }
+    float wmask, tfx, tfy;
+    {   // the ground-truth warp: validity mask and flow target only, :169-176, :204
+      const float d = __fdiv_rn(1.0f, lab);
+      const Proj q = project(sx.p, __fmul_rn(ray.r0, d), __fmul_rn(ray.r1, d), __fmul_rn(ray.r2, d));
+      const Foot f = footprint(q.x, q.y, W, H);
+      wmask = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(f.wx0, f.wy0), __fmul_rn(f.wx0, f.wy1)), __fmul_rn(f.wx1, f.wy0)),
+                        __fmul_rn(f.wx1, f.wy1));
+      tfx = __fsub_rn(q.x, gx);     // depth_optflow, utils.py:321-338
+      tfy = __fsub_rn(q.y, gy);
+    }
+    float tgt[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) tgt[c] = __ldg(P.left[s] + pix * 3 + c);
+    const float* right = P.right[s] + img0 * 3;
+    const float kp = P.c_pixel[s] * wmask;
+    {   // the right image warped by the predicted depth, :178-187
+      const float d = __fdiv_rn(1.0f, pd);
+      const Proj q = project(sx.p, __fmul_rn(ray.r0, d), __fmul_rn(ray.r1, d), __fmul_rn(ray.r2, d));
+      float dx, dy;
+      const float err = sample_error(right, H, W, q.x, q.y, tgt, dx, dy);
+      acc[3] = kp * err;
+      const float du0 = dx / q.zp, du1 = dy / q.zp;
+      const float du2 = -(q.x * du0 + q.y * du1);
+      const float gc0 = du0 * sx.p[0] + du1 * sx.p[4] + du2 * sx.p[8];
+      const float gc1 = du0 * sx.p[1] + du1 * sx.p[5] + du2 * sx.p[9];
+      const float gc2 = du0 * sx.p[2] + du1 * sx.p[6] + du2 * sx.p[10];
+      const float g_d = gc0 * ray.r0 + gc1 * ray.r1 + gc2 * ray.r2;
+      g_pd -= kp * g_d * d * d;                           // depth = 1 / pred_depth
+    }
+    {   // ... and by the predicted flow (optflow_warp, utils.py:201-217), :190-197
+      float dx, dy;
+      const float err = sample_error(right, H, W, __fadd_rn(gx, fx), __fadd_rn(gy, fy), tgt, dx, dy);
+      acc[3] += kp * err;
+      g_fx += kp * dx;
+      g_fy += kp * dy;
+    }
+    {   // flow against the flow the ground-truth depth implies, :204-210
+      const float ex = __fsub_rn(fx, tfx), ey = __fsub_rn(fy, tfy);
+      acc[2] = P.c_flow[s] * (fabsf(ex) + fabsf(ey));
+      g_fx += P.c_flow[s] * sgn(ex);
+      g_fy += P.c_flow[s] * sgn(ey);
+    }
+    P.g_pd[s][pix] = g_pd * P.loss_scale;
+    P.g_fx[s][pix] = g_fx * P.loss_scale;
+    P.g_fy[s][pix] = g_fy * P.loss_scale;
+  }
+  block_sum<kFlowTerms>(acc, scratch, P.partials + (size_t)item * kFlowTerms);
+}
+
+__global__ void flow_xforms_kernel(const PrepJob j) {   // single-scale call: no pyramid launch to ride on
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < j.n) prep_one(j, idx);
+}
+
+// losses[0..3] = depth, smooth, optflow, pixel; [4] = their sum (total_loss, :240).  One block, fixed order.
+__global__ void __launch_bounds__(256)
+flow_finalize_kernel(const float* __restrict__ partials, int n_items, float* __restrict__ losses) {
+  __shared__ double sh[kFlowTerms][256];
+  double a[kFlowTerms] = {0.0, 0.0, 0.0, 0.0};
+  for (int i = threadIdx.x; i < n_items; i += 256) {
+    const float4 q = reinterpret_cast<const float4*>(partials)[i];
+    a[0] += (double)q.x; a[1] += (double)q.y; a[2] += (double)q.z; a[3] += (double)q.w;
+  }
+#pragma unroll
+  for (int k = 0; k < kFlowTerms; ++k) sh[k][threadIdx.x] = a[k];
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o)
+#pragma unroll
+      for (int k = 0; k < kFlowTerms; ++k) sh[k][threadIdx.x] += sh[k][threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x < kFlowTerms) losses[threadIdx.x] = (float)sh[threadIdx.x][0];
+  if (threadIdx.x == 0) losses[4] = (float)(((sh[0][0] + sh[1][0]) + sh[2][0]) + sh[3][0]);
+}
+
+namespace {
+
+struct FlowLayout {
+  size_t xf, partials, left[VSL_MAX_SCALES], right[VSL_MAX_SCALES], label[VSL_MAX_SCALES], total;
+  int n_items;
+};
+
+int check_flow(const VslFlowLossDesc* d) {
+  VSL_REQUIRE(d != nullptr, VSL_E_NULL);
+  VSL_REQUIRE(d->S >= 1 && d->S <= VSL_MAX_SCALES, VSL_E_SHAPE);
+  const int F = 1 << (d->S - 1);
+  VSL_REQUIRE(d->B > 0 && d->B <= 65535 / (VSL_MAX_VIEWS + 1) && d->H > 0 && d->W > 0 && d->H % F == 0 && d->W % F == 0,
+              VSL_E_SHAPE);
+  VSL_REQUIRE((d->H >> (d->S - 1)) >= 3 && (d->W >> (d->S - 1)) >= 3, VSL_E_SHAPE);   // the four means need elements
+  VSL_REQUIRE((long long)d->B * d->H * d->W * 3 < (1ll << 31), VSL_E_SHAPE);
+  return VSL_OK;
+}
+
+FlowLayout flow_layout(const VslFlowLossDesc* d) {
+  FlowLayout L;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t o = off; off += round_up(bytes, 256); return o; };
+  L.xf = take(sizeof(Xform) * (size_t)d->S * d->B);
+  L.n_items = 0;
+  for (int s = 0; s < d->S; ++s) {
+    const int Hs = d->H >> s, Ws = d->W >> s;
+    L.n_items += d->B * ((Hs + kFlowTH - 1) / kFlowTH) * ((Ws + kFlowTW - 1) / kFlowTW);
+  }
+  L.partials = take(sizeof(float) * kFlowTerms * (size_t)L.n_items);
+  for (int s = 1; s < d->S; ++s) {
+    const size_t n = (size_t)d->B * (d->H >> s) * (d->W >> s);
+    L.left[s] = take(n * 3 * sizeof(float));
+    L.right[s] = take(n * 3 * sizeof(float));
+    L.label[s] = take(n * sizeof(float));
+  }
+  L.total = off;
+  return L;
+}
+
+}  // namespace
+}  // namespace vsl
+
+using namespace vsl;
+
+extern "C" {
+
+size_t vsl_flow_loss_ws_bytes(const VslFlowLossDesc* d) {
+  if (check_flow(d) != VSL_OK) return 0;
+  return flow_layout(d).total;
+}
+
+int vsl_flow_loss_fwd_bwd(const VslFlowLossDesc* d, const float* left, const float* right, const float* label,
+                          const float* const* depth_pyr, const float* const* flowx_pyr, const float* const* flowy_pyr,
+                          const float* proj, const float* K_pyr, float* losses, float* const* g_depth_pyr,
+                          float* const* g_flowx_pyr, float* const* g_flowy_pyr, void* ws, vsl_stream_t stream) {
+  const int rc = check_flow(d);
+  if (rc != VSL_OK) return rc;
+  VSL_REQUIRE(left && right && label && depth_pyr && flowx_pyr && flowy_pyr && proj && K_pyr && losses && g_depth_pyr &&
+                  g_flowx_pyr && g_flowy_pyr && ws, VSL_E_NULL);
+  VSL_REQUIRE(aligned(ws, 256), VSL_E_ALIGN);
+  for (int s = 0; s < d->S; ++s)
+    VSL_REQUIRE(depth_pyr[s] && flowx_pyr[s] && flowy_pyr[s] && g_depth_pyr[s] && g_flowx_pyr[s] && g_flowy_pyr[s],
+                VSL_E_NULL);
+  cudaStream_t st = (cudaStream_t)stream;
+  const FlowLayout L = flow_layout(d);
+  char* base = static_cast<char*>(ws);
+
+  FlowParams P;
+  P.B = d->B; P.S = d->S;
+  P.xf = reinterpret_cast<const Xform*>(base + L.xf);
+  P.partials = reinterpret_cast<float*>(base + L.partials);
+  P.loss_scale = d->loss_scale;
+  int items = 0;
+  for (int s = 0; s < VSL_MAX_SCALES; ++s) {
+    if (s >= d->S) {
+      P.Hs[s] = P.Ws[s] = P.tiles_x[s] = P.tiles_y[s] = 0;
+      P.left[s] = P.right[s] = P.label[s] = P.pd[s] = P.fx[s] = P.fy[s] = nullptr;
+      P.g_pd[s] = P.g_fx[s] = P.g_fy[s] = nullptr;
+      P.c_depth[s] = P.c_pixel[s] = P.c_flow[s] = P.c_xx[s] = P.c_xy[s] = P.c_yy[s] = 0.f;
+      P.item_begin[s + 1] = items;
+      continue;
+    }
+    const int Hs = d->H >> s, Ws = d->W >> s;
+    P.Hs[s] = Hs; P.Ws[s] = Ws;
+    P.tiles_x[s] = (Ws + kFlowTW - 1) / kFlowTW;
+    P.tiles_y[s] = (Hs + kFlowTH - 1) / kFlowTH;
+    P.item_begin[s] = items;
+    items += d->B * P.tiles_x[s] * P.tiles_y[s];
+    P.item_begin[s + 1] = items;
+    P.left[s] = s == 0 ? left : reinterpret_cast<const float*>(base + L.left[s]);
+    P.right[s] = s == 0 ? right : reinterpret_cast<const float*>(base + L.right[s]);
+    P.label[s] = s == 0 ? label : reinterpret_cast<const float*>(base + L.label[s]);
+    P.pd[s] = depth_pyr[s]; P.fx[s] = flowx_pyr[s]; P.fy[s] = flowy_pyr[s];
+    P.g_pd[s] = g_depth_pyr[s]; P.g_fx[s] = g_flowx_pyr[s]; P.g_fy[s] = g_flowy_pyr[s];
+    const double k = 1.0 / (double)(1 << s), n = (double)d->B * Hs * Ws;
+    P.c_depth[s] = (float)(d->depth_weight * k / n);
+    P.c_pixel[s] = (float)(d->data_weight * k / (n * 3.0));
+    P.c_flow[s] = (float)(d->optflow_weight * k / n);
+    P.c_xx[s] = (float)(d->smooth_weight * k / ((double)d->B * Hs * (Ws - 2)));
+    P.c_yy[s] = (float)(d->smooth_weight * k / ((double)d->B * (Hs - 2) * Ws));
+    P.c_xy[s] = (float)(d->smooth_weight * k / ((double)d->B * (Hs - 1) * (Ws - 1)));
+  }
+
+  // launches 1-2: pyramids (+ the transform table: one matrix pose per image, every scale)
+  PrepJob prep = make_prep(proj, K_pyr, d->B, d->S, 1, VSL_POSE_MATRIX, reinterpret_cast<Xform*>(base + L.xf), nullptr);
+  if (d->S > 1) {
+    PyrJob rgb;
+    rgb.nimg = 2;
+    rgb.img[0] = left; rgb.img[1] = right;
+    for (int s = 0; s < VSL_MAX_SCALES; ++s) {
+      rgb.lvl[0][s] = (s >= 1 && s < d->S) ? reinterpret_cast<float*>(base + L.left[s]) : nullptr;
+      rgb.lvl[1][s] = (s >= 1 && s < d->S) ? reinterpret_cast<float*>(base + L.right[s]) : nullptr;
+    }
+    int e = launch_pyramid(rgb, prep, d->B, d->H, d->W, 3, d->S, st);
+    if (e != VSL_OK) return e;
+    PyrJob lab;
+    lab.nimg = 1;
+    lab.img[0] = label;
+    for (int s = 0; s < VSL_MAX_SCALES; ++s)
+      lab.lvl[0][s] = (s >= 1 && s < d->S) ? reinterpret_cast<float*>(base + L.label[s]) : nullptr;
+    PrepJob none = prep;
+    none.n = 0;
+    e = launch_pyramid(lab, none, d->B, d->H, d->W, 1, d->S, st);
+    if (e != VSL_OK) return e;
+  } else {
+    flow_xforms_kernel<<<(prep.n + 127) / 128, 128, 0, st>>>(prep);
+    const int e = launch_status();
+    if (e != VSL_OK) return e;
+  }
+  flow_loss_kernel<<<items, kFlowTW * kFlowTH, 0, st>>>(P);
+  int e = launch_status();
+  if (e != VSL_OK) return e;
+  flow_finalize_kernel<<<1, 256, 0, st>>>(P.partials, items, losses);
+  return launch_status();
+}
+
+}  // extern "C"

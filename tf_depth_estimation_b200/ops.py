@@ -4,6 +4,7 @@ torch is used for device memory, streams and autograd bookkeeping only; every nu
 hand-written sm_100a kernels in csrc/.  All tensors must be CUDA float32; anything else raises.
 """
 import collections
+import ctypes
 import threading
 import warnings
 
@@ -996,6 +997,95 @@ def view_synthesis_loss(tgt, srcs, x_pyr, poses, K_pyr, logits_pyr=None, mask_py
                                                     want_src_grad=want_src))
     return _ViewSynthesisLoss.apply(plan, tgt, K_pyr, poses, V, S, len(rest), *srcs, *x_pyr, *rest,
                                     *[t for p in (src_x_pyr or []) for t in p])
+
+
+class FlowLossFlags(object):
+    """The FLAGS the loss loop of train_optflow_combine.py:138-240 reads (reference attribute names)."""
+
+    def __init__(self, **kw):
+        self.num_scales = 4
+        self.smooth_weight = 0.5
+        self.depth_weight = 1.0
+        self.data_weight = 1.0
+        self.optflow_weight = 1.0
+        self.__dict__.update(kw)
+
+
+class _FlowDepthLoss(torch.autograd.Function):
+    """One vsl_flow_loss_fwd_bwd call: the gradients of (depth + smooth + optflow + pixel) * loss_scale w.r.t. the
+    three prediction pyramids come out of the same pass, into an arena that belongs to this call; backward applies
+    the upstream gradient of `total` to it with one launch (vsl_scale, a no-op kernel for total.backward())."""
+
+    @staticmethod
+    def forward(ctx, desc, left, right, label, proj, K_pyr, S, *pyrs):
+        lib = _lib.load()
+        left, right, label = _f32(left, 'image_left'), _f32(right, 'image_right'), _f32(label, 'label')
+        proj, K_pyr = _f32(proj, 'tgt2src_proj'), _f32(K_pyr, 'K_pyr')
+        pyrs = [_f32(t, 'pyr') for t in pyrs]
+        B, H, W = desc.B, desc.H, desc.W
+        shapes = [(8,)] + [(B, H >> s, W >> s, 1) for _ in range(3) for s in range(S)]
+        arena, views = _arena(shapes, device=left.device)
+        ws = _ws(lib.vsl_flow_loss_ws_bytes(ctypes.byref(desc)), left.device)
+        ptrs = lambda ts: ptr_array([t.data_ptr() for t in ts])
+        check(lib.vsl_flow_loss_fwd_bwd(ctypes.byref(desc), left.data_ptr(), right.data_ptr(), label.data_ptr(),
+                                        ptrs(pyrs[:S]), ptrs(pyrs[S:2 * S]), ptrs(pyrs[2 * S:]), proj.data_ptr(),
+                                        K_pyr.data_ptr(), views[0].data_ptr(), ptrs(views[1:1 + S]),
+                                        ptrs(views[1 + S:1 + 2 * S]), ptrs(views[1 + 2 * S:]), ws.data_ptr(), _stream()))
+        ctx.arena, ctx.grads, ctx.applied = arena, views[1:], None
+        total, losses = views[0][4].view(()), views[0][:4]
+        ctx.mark_non_differentiable(losses)
+        return total, losses
+
+    @staticmethod
+    def backward(ctx, g_total, _g_losses):
+        lib = _lib.load()
+        if ctx.applied is not None:
+            raise RuntimeError('flow_depth_loss: backward through the same call twice is not supported')
+        g = g_total.detach().to(torch.float32).reshape(1).contiguous()
+        n = ctx.arena.numel() - 64
+        p = ctx.arena.data_ptr() + 4 * 64
+        check(lib.vsl_scale(p, p, n, g.data_ptr(), None, _stream()))
+        ctx.applied = g
+        return (None,) * 7 + tuple(ctx.grads)
+
+
+def flow_depth_loss(image_left, image_right, label, pred_depth, pred_optflow_x, pred_optflow_y, tgt2src_proj, K_pyr,
+                    flags=None, loss_scale=1.0):
+    """The loss loop of train_optflow_combine.py:138-240 (the DeMoN-pair family) as ONE fused forward+backward call.
+
+    image_left / image_right [B,H,W,3]; label [B,H,W,1] ground-truth inverse depth; pred_depth / pred_optflow_x /
+    pred_optflow_y: lists of S network outputs [B,Hs,Ws,1] (finest first; inverse depth, flow in pixels of that
+    scale); tgt2src_proj [B,4,4] (the loader's tgt2src_projs[:,0]); K_pyr [B,S,3,3].
+    -> (total, losses[4] = depth, smooth, optflow, pixel).  `total` (= total_loss, :240) is differentiable wrt the
+    three prediction pyramids; the label, the images and the pose are data."""
+    flags = flags or FlowLossFlags()
+    image_left = from_external(image_left, 'image_left')
+    if not image_left.is_cuda:
+        raise TypeError('flow_depth_loss takes CUDA tensors (this path has no CPU fallback)')
+    if image_left.dim() != 4 or image_left.shape[3] != 3:
+        raise ValueError('image_left must be [B,H,W,3], got %s' % (tuple(image_left.shape),))
+    B, H, W, _ = image_left.shape
+    S = flags.num_scales
+    image_right, label = from_external(image_right, 'image_right'), from_external(label, 'label')
+    tgt2src_proj, K_pyr = from_external(tgt2src_proj, 'tgt2src_proj'), from_external(K_pyr, 'K_pyr')
+    _want((B, H, W, 3), image_right, 'image_right')
+    _want((B, H, W, 1), label, 'label')
+    _want((B, 4, 4), tgt2src_proj, 'tgt2src_proj')
+    _want((B, S, 3, 3), K_pyr, 'K_pyr')
+    pyrs = []
+    for name, pyr in (('pred_depth', pred_depth), ('pred_optflow_x', pred_optflow_x), ('pred_optflow_y', pred_optflow_y)):
+        if len(pyr) != S:
+            raise ValueError('%s must hold num_scales=%d levels' % (name, S))
+        for sc, t in enumerate(pyr):
+            t = from_external(t, name)
+            _want((B, H >> sc, W >> sc, 1), t, '%s[%d]' % (name, sc))
+            pyrs.append(t)
+    if H % (1 << (S - 1)) or W % (1 << (S - 1)) or (H >> (S - 1)) < 3 or (W >> (S - 1)) < 3:
+        raise ValueError('H, W must be divisible by 2^(num_scales-1) with a coarsest level of at least 3 x 3')
+    desc = _lib.VslFlowLossDesc(B=B, H=H, W=W, S=S, smooth_weight=flags.smooth_weight, depth_weight=flags.depth_weight,
+                                data_weight=flags.data_weight, optflow_weight=flags.optflow_weight,
+                                loss_scale=float(loss_scale))
+    return _FlowDepthLoss.apply(desc, image_left, image_right, label, tgt2src_proj, K_pyr, S, *pyrs)
 
 
 class HostPipeline(object):

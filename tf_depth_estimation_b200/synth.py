@@ -95,3 +95,49 @@ def make_snippets(B, H, W, S=4, V=2, seed=1234, motion=1.0, hard=False):
     logits_pyr = [torch.randn(B, H // 2 ** s, W // 2 ** s, 2 * V, generator=g) for s in range(S)]
     return dict(tgt=tgt, srcs=srcs, disp_pyr=disp_pyr, poses=poses, K=K,
                 K_pyr=intrinsics_pyramid(K, S), logits_pyr=logits_pyr)
+
+
+def _rigid(t, r):
+    """[B,3] translation + [B,3] small rotation angles -> [B,4,4] (Rz Ry Rx, what a loader's matrix holds)."""
+    B = t.shape[0]
+    cx, sx = torch.cos(r[:, 0]), torch.sin(r[:, 0])
+    cy, sy = torch.cos(r[:, 1]), torch.sin(r[:, 1])
+    cz, sz = torch.cos(r[:, 2]), torch.sin(r[:, 2])
+    one, zero = torch.ones(B), torch.zeros(B)
+    Rx = torch.stack([one, zero, zero, zero, cx, -sx, zero, sx, cx], 1).reshape(B, 3, 3)
+    Ry = torch.stack([cy, zero, sy, zero, one, zero, -sy, zero, cy], 1).reshape(B, 3, 3)
+    Rz = torch.stack([cz, -sz, zero, sz, cz, zero, zero, zero, one], 1).reshape(B, 3, 3)
+    T = torch.zeros(B, 4, 4)
+    T[:, :3, :3] = Rz @ Ry @ Rx
+    T[:, :3, 3] = t
+    T[:, 3, 3] = 1.0
+    return T.contiguous()
+
+
+def make_flow_pairs(B, H, W, S=4, seed=4321, motion=1.0):
+    """One batch of the DeMoN-pair family (train_optflow_combine.py:85-110; BASELINE configs[3]).
+
+    -> dict(left, right [B,H,W,3]; label [B,H,W,1] ground-truth inverse depth; depth_pyr / flowx_pyr / flowy_pyr
+            lists of S network outputs [B,Hs,Ws,1] (inverse depth, flow in pixels of that scale); proj [B,4,4] the
+            loader's target-to-source transform; K [B,3,3]; K_pyr [B,S,3,3])
+    """
+    g = torch.Generator().manual_seed(seed)
+    left, right = _texture(g, B, H, W, 3), _texture(g, B, H, W, 3)
+    label = torch.clamp(4.0 * torch.sigmoid(_lowpass(g, B, H, W)), 0.05, 4.0).permute(0, 2, 3, 1).contiguous()
+    disp0 = torch.clamp(label.permute(0, 3, 1, 2) * (1.0 + 0.2 * _lowpass(g, B, H, W)), 0.05, 4.0)
+    fx0, fy0 = 4.0 * motion * _lowpass(g, B, H, W), 3.0 * motion * _lowpass(g, B, H, W)
+    depth_pyr, fx_pyr, fy_pyr = [], [], []
+    for s in range(S):
+        hs, ws = H // 2 ** s, W // 2 ** s
+        pool = lambda x: torch.nn.functional.adaptive_avg_pool2d(x, (hs, ws))
+        noise = lambda a: a * torch.randn(B, 1, hs, ws, generator=g)
+        nhwc = lambda x: x.permute(0, 2, 3, 1).contiguous()
+        depth_pyr.append(nhwc(torch.clamp(pool(disp0) + noise(0.01), 0.05, 4.0)))
+        fx_pyr.append(nhwc(pool(fx0) / 2 ** s + noise(0.05)))
+        fy_pyr.append(nhwc(pool(fy0) / 2 ** s + noise(0.05)))
+    mean_depth = (1.0 / label).mean().item()
+    t = (torch.rand(B, 3, generator=g) * 2 - 1) * 0.1 * mean_depth * motion
+    r = (torch.rand(B, 3, generator=g) * 2 - 1) * 0.02 * motion
+    K = intrinsics(B, H, W)
+    return dict(left=left, right=right, label=label, depth_pyr=depth_pyr, flowx_pyr=fx_pyr, flowy_pyr=fy_pyr,
+                proj=_rigid(t, r), K=K, K_pyr=intrinsics_pyramid(K, S))
