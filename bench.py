@@ -23,6 +23,8 @@ JSON keys beyond the base contract:
                 reference's loader holds them (uint8, converted on load exactly as imageselect_Dataloader.py:93 does),
                 network outputs as float32; pinned H2D of every input, the step, D2H of the losses and every gradient,
                 all inside the timed region; copies and kernels of neighbouring steps overlap (3 streams, 2 slots).
+  flow          (--config cfg4 only) the DeMoN-pair family's own loss loop (train_optflow_combine.py:138-240) as the
+                fused flow-and-depth step vsl_flow_loss_fwd_bwd: device-resident step time, per rank.
   train         (default config only) BASELINE's second metric, end-to-end training samples/s at N GPUs:
                 configs[2] (DispNet + PoseExpNet, global batch 256 split over the ranks) with this repository's
                 fused loss and its fused reduce-scatter + Adam + all-gather optimiser step over NVLink peer memory
@@ -228,6 +230,18 @@ def train_leg(rank, world, dev):
         return {'error': '%s: %s' % (type(e).__name__, e)}
 
 
+def flow_leg(dev, steps):
+    """configs[3]'s own loss (train_optflow_combine.py:138-240) as the fused flow-and-depth step, through
+    profiles/time_flow.py; never lets a failure take the bench line down."""
+    try:
+        spec = importlib.util.spec_from_file_location('time_flow', os.path.join(ROOT, 'profiles', 'time_flow.py'))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod.measure(dev, steps=max(20, min(steps, 200)))
+    except Exception as e:   # noqa: BLE001
+        return {'error': '%s: %s' % (type(e).__name__, e)}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -370,6 +384,8 @@ def run_ours(args):
     if args.config == 'cfg2' and not args.no_train:
         train = train_leg(rank, world, dev)
 
+    flow = flow_leg(dev, K) if args.config == 'cfg4' else None
+
     if rank == 0:
         peak, peak_src = measured_peak()
         kmean = statistics.mean(kern_ms)
@@ -402,6 +418,8 @@ def run_ours(args):
         }
         if train is not None:
             out['train'] = train
+        if flow is not None:
+            out['flow'] = flow
         if world == 1 and not args.no_cpu_baseline:
             out['cpu_baseline'] = cpu_baseline(c, reps=12)
         args.out.emit(json.dumps(out))

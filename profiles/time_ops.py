@@ -28,6 +28,25 @@ def fb():
     out = ops.projective_inverse_warp(img, dr, pr, K, 'eular')[0]
     out.backward(out)
 timeit('projective_inverse_warp fwd+bwd (d depth, d pose)', fb, npx * (12 + 4 + 12 + 12 + 8 + 4 + 4 + 12 + 12 + 4 + 4))
+ig = img.clone().requires_grad_()
+def fbi():
+    out = ops.projective_inverse_warp(ig, dr, pr, K, 'eular')[0]
+    out.backward(out)
+timeit('projective_inverse_warp fwd+bwd (+ d img: aggregated vector reductions)', fbi, npx * (12 + 4 + 12 + 12 + 8 + 4 + 4 + 12 + 12 + 4 + 4 + 24))
+def graphed(fn):
+    """The same calls captured into a CUDA graph (the library never synchronises or allocates): what the GPU needs once
+    the Python / autograd dispatch of ~10 us per call is out of the way."""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3): fn()
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g): fn()
+    return g.replay
+timeit('  ... fwd (5 outputs), CUDA graph replay', graphed(lambda: ops.projective_inverse_warp(img, depth, pose, K, 'eular')), npx * (12 + 4 + 12 + 12 + 8 + 4 + 4))
+timeit('  ... fwd+bwd (d depth, d pose), CUDA graph replay', graphed(fb), npx * (12 + 4 + 12 + 12 + 8 + 4 + 4 + 12 + 12 + 4 + 4))
+timeit('  ... fwd+bwd (+ d img), CUDA graph replay', graphed(fbi), npx * (12 + 4 + 12 + 12 + 8 + 4 + 4 + 12 + 12 + 4 + 4 + 24))
 timeit('compute_smooth_loss fwd', lambda: ops.compute_smooth_loss(disp), npx * 4)
 timeit('compute_exp_reg_loss fwd', lambda: ops.compute_exp_reg_loss(lg), npx * 8)
 timeit('image_pyramid (3 levels)', lambda: ops.image_pyramid(img, 4), npx * 12 * 1.328)

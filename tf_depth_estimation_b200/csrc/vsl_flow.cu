@@ -51,39 +51,76 @@ struct FlowParams {
   float c_pixel[VSL_MAX_SCALES];        // data_weight / 2^s / (B Hs Ws 3)
   float c_flow[VSL_MAX_SCALES];         // optflow_weight / 2^s / (B Hs Ws)
   float c_xx[VSL_MAX_SCALES], c_xy[VSL_MAX_SCALES], c_yy[VSL_MAX_SCALES];   // smooth_weight / 2^s / count_k (xy = yx)
+  float wstep[VSL_MAX_SCALES], hstep[VSL_MAX_SCALES];   // meshgrid linspace steps 2/(W-1), 2/(H-1) in fp32
   float loss_scale;
 };
 
-// One map's smoothness at element (i, j) from its shared-memory tile q (q points at the element, row pitch
-// kFlowSW): the weighted |second differences| the element owns, and the gradient it receives from the ten
-// stencils it is part of (my_losses.py:27-36; same stencil algebra as smooth_fwd_kernel / smooth_bwd_kernel).
-VSL_DEV void smooth_at(const float* q, int i, int j, int H, int W, float cxx, float cxy, float cyy, float& val,
-                       float& grad) {
+// Weights of the 14 second differences an element takes part in (my_losses.py:27-36): coefficient of the mean it
+// belongs to x its place in the stencil (1, -2, 1 / 1, -1, -1, 1) x [the difference exists], shared by the three maps.
+struct SmoothW {
+  float xx[3];   // owned by (i, j), (i, j-1), (i, j-2)
+  float yy[3];   // owned by (i, j), (i-1, j), (i-2, j)
+  float xy[4];   // owned by (i, j), (i, j-1), (i-1, j), (i-1, j-1); d/dy of dx and d/dx of dy share position and weight
+  float oxx, oyy, oxy;   // the plain coefficients of the differences (i, j) owns, for the loss value
+};
+
+VSL_DEV SmoothW smooth_weights(int i, int j, int H, int W, float cxx, float cxy, float cyy) {
+  SmoothW w;
+  const float st[3] = {1.f, -2.f, 1.f};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    w.xx[k] = (j - k >= 0 && j - k + 2 < W) ? cxx * st[k] : 0.f;
+    w.yy[k] = (i - k >= 0 && i - k + 2 < H) ? cyy * st[k] : 0.f;
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int di = k >> 1, dj = k & 1;
+    const bool ok = i - di >= 0 && j - dj >= 0 && i - di + 1 < H && j - dj + 1 < W;
+    w.xy[k] = ok ? ((di ^ dj) ? -cxy : cxy) : 0.f;
+  }
+  w.oxx = fabsf(w.xx[0]); w.oyy = fabsf(w.yy[0]); w.oxy = fabsf(w.xy[0]);
+  return w;
+}
+
+// sign(e) in {-1, 0, 1} with two FMA-pipe instructions: sat(e * 2^100 + 0.5) is 0, 0.5 or 1 (exact for every float32
+// that is not denormal)
+VSL_DEV float sign2(float e) { return fmaf(__saturatef(fmaf(e, 1.2676506e30f, 0.5f)), 2.0f, -1.0f); }
+
+// One map's smoothness at an element from its shared-memory tile (q points at the element, row pitch kFlowSW; the
+// tile is zero outside the image and the weights are zero for differences that do not exist): the weighted
+// |second differences| the element owns, and the gradient it receives from the stencils it is part of.
+VSL_DEV void smooth_at(const float* q, const SmoothW& w, float& val, float& grad) {
   constexpr int P = kFlowSW;
-  auto Q = [&](int di, int dj) { return q[di * P + dj]; };
-  auto dxx = [&](int di, int dj) -> float {    // second x-difference owned by (i+di, j+dj), 0 where it does not exist
-    const int jj = j + dj;
-    if (jj < 0 || jj + 2 >= W) return 0.f;
-    return __fsub_rn(__fsub_rn(Q(di, dj + 2), Q(di, dj + 1)), __fsub_rn(Q(di, dj + 1), Q(di, dj)));
-  };
-  auto dyy = [&](int di, int dj) -> float {
-    const int ii = i + di;
-    if (ii < 0 || ii + 2 >= H) return 0.f;
-    return __fsub_rn(__fsub_rn(Q(di + 2, dj), Q(di + 1, dj)), __fsub_rn(Q(di + 1, dj), Q(di, dj)));
-  };
-  auto dxy = [&](int di, int dj, int order) -> float {   // order 0: d/dy of dx, 1: d/dx of dy
-    const int ii = i + di, jj = j + dj;
-    if (ii < 0 || jj < 0 || ii + 1 >= H || jj + 1 >= W) return 0.f;
-    const float q00 = Q(di, dj), q01 = Q(di, dj + 1), q10 = Q(di + 1, dj), q11 = Q(di + 1, dj + 1);
-    return order == 0 ? __fsub_rn(__fsub_rn(q11, q10), __fsub_rn(q01, q00))
-                      : __fsub_rn(__fsub_rn(q11, q01), __fsub_rn(q10, q00));
-  };
-  const float oxx = dxx(0, 0), oyy = dyy(0, 0), oxy = dxy(0, 0, 0), oyx = dxy(0, 0, 1);
-  val = cxx * fabsf(oxx) + cyy * fabsf(oyy) + cxy * (fabsf(oxy) + fabsf(oyx));
-  float g = cxx * (sgn(oxx) - 2.f * sgn(dxx(0, -1)) + sgn(dxx(0, -2)));
-  g += cyy * (sgn(oyy) - 2.f * sgn(dyy(-1, 0)) + sgn(dyy(-2, 0)));
-  g += cxy * (sgn(oxy) - sgn(dxy(0, -1, 0)) - sgn(dxy(-1, 0, 0)) + sgn(dxy(-1, -1, 0)));
-  g += cxy * (sgn(oyx) - sgn(dxy(0, -1, 1)) - sgn(dxy(-1, 0, 1)) + sgn(dxy(-1, -1, 1)));
+  // row i: columns j-2 .. j+2; column j: rows i-2 .. i+2; the 3 x 3 block around the element
+  const float r[5] = {q[-2], q[-1], q[0], q[1], q[2]};
+  const float c[5] = {q[-2 * P], q[-P], q[0], q[P], q[2 * P]};
+  const float nw = q[-P - 1], ne = q[-P + 1], sw = q[P - 1], se = q[P + 1];
+  float g = 0.f;
+  {
+    const float d0 = __fsub_rn(r[1], r[0]), d1 = __fsub_rn(r[2], r[1]), d2 = __fsub_rn(r[3], r[2]), d3 = __fsub_rn(r[4], r[3]);
+    const float o = __fsub_rn(d3, d2);
+    g = fmaf(w.xx[0], sign2(o), fmaf(w.xx[1], sign2(__fsub_rn(d2, d1)), w.xx[2] * sign2(__fsub_rn(d1, d0))));
+    val = w.oxx * fabsf(o);
+  }
+  {
+    const float d0 = __fsub_rn(c[1], c[0]), d1 = __fsub_rn(c[2], c[1]), d2 = __fsub_rn(c[3], c[2]), d3 = __fsub_rn(c[4], c[3]);
+    const float o = __fsub_rn(d3, d2);
+    g += fmaf(w.yy[0], sign2(o), fmaf(w.yy[1], sign2(__fsub_rn(d2, d1)), w.yy[2] * sign2(__fsub_rn(d1, d0))));
+    val = fmaf(w.oyy, fabsf(o), val);
+  }
+  {
+    // the four 2 x 2 cells around the element: (q00 q01 / q10 q11) with the owner at q00
+    auto cell = [&](float q00, float q01, float q10, float q11, float wk, bool own) {
+      const float a = __fsub_rn(__fsub_rn(q11, q10), __fsub_rn(q01, q00));   // d/dy of dx
+      const float b = __fsub_rn(__fsub_rn(q11, q01), __fsub_rn(q10, q00));   // d/dx of dy
+      g = fmaf(wk, sign2(a) + sign2(b), g);
+      if (own) val = fmaf(w.oxy, fabsf(a) + fabsf(b), val);
+    };
+    cell(r[2], r[3], c[3], se, w.xy[0], true);      // owner (i, j)
+    cell(r[1], r[2], sw, c[3], w.xy[1], false);     // owner (i, j-1)
+    cell(c[1], ne, r[2], r[3], w.xy[2], false);     // owner (i-1, j)
+    cell(nw, c[1], r[1], r[2], w.xy[3], false);     // owner (i-1, j-1)
+  }
   grad = g;
 }
 
@@ -104,7 +141,7 @@ VSL_DEV float sample_error(const float* __restrict__ img, int H, int W, float x,
   for (int c = 0; c < 3; ++c) {
     const float i00 = __ldg(p00 + c), i01 = __ldg(p01 + c), i10 = __ldg(p10 + c), i11 = __ldg(p11 + c);
     const float e = __fsub_rn(blend(w00, w01, w10, w11, i00, i01, i10, i11), tgt[c]);
-    const float g = sgn(e);
+    const float g = sign2(e);
     err += fabsf(e);
     dx += g * (f.wy0 * (f.mx1 * i10 - f.mx0 * i00) + f.wy1 * (f.mx1 * i11 - f.mx0 * i01));
     dy += g * (f.wx0 * (f.my1 * i01 - f.my0 * i00) + f.wx1 * (f.my1 * i11 - f.my0 * i10));
@@ -131,13 +168,23 @@ flow_loss_kernel(const FlowParams P) {
   if (threadIdx.x < 21)
     reinterpret_cast<float*>(&sx)[threadIdx.x] = reinterpret_cast<const float*>(P.xf + (size_t)s * P.B + b)[threadIdx.x];
   {
-    const float* maps[3] = {P.pd[s] + img0, P.fx[s] + img0, P.fy[s] + img0};
-    for (int e = threadIdx.x; e < 3 * kFlowSH * kFlowSW; e += kFlowTW * kFlowTH) {
-      const int m = e / (kFlowSH * kFlowSW), r = e - m * (kFlowSH * kFlowSW);
-      const int ly = r / kFlowSW, lx = r - ly * kFlowSW;
-      const int gy = y_base - kFlowHalo + ly, gx = x_base - kFlowHalo + lx;
-      const bool in = (unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W;
-      tile[m][r] = in ? __ldg(maps[m] + (size_t)gy * W + gx) : 0.f;
+    // 36 x 12 elements per map = 432 = 256 + 176: every thread owns one or two tile slots, shared by the three maps
+    const float* __restrict__ m0 = P.pd[s] + img0;
+    const float* __restrict__ m1 = P.fx[s] + img0;
+    const float* __restrict__ m2 = P.fy[s] + img0;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int r = threadIdx.x + k * (kFlowTW * kFlowTH);
+      if (r < kFlowSH * kFlowSW) {
+        const int ly = r / kFlowSW, lx = r - ly * kFlowSW;
+        const int gy = y_base - kFlowHalo + ly, gx = x_base - kFlowHalo + lx;
+        const bool in = (unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W;
+        const int o = in ? gy * W + gx : 0;
+        const float a = __ldg(m0 + o), bq = __ldg(m1 + o), c = __ldg(m2 + o);
+        tile[0][r] = in ? a : 0.f;
+        tile[1][r] = in ? bq : 0.f;
+        tile[2][r] = in ? c : 0.f;
+      }
     }
   }
   __syncthreads();
@@ -152,12 +199,13 @@ flow_loss_kernel(const FlowParams P) {
     float g_pd, g_fx, g_fy;
     {   // the three smoothness terms
       float v0, v1, v2;
-      smooth_at(&tile[0][c0], i, j, H, W, P.c_xx[s], P.c_xy[s], P.c_yy[s], v0, g_pd);
-      smooth_at(&tile[1][c0], i, j, H, W, P.c_xx[s], P.c_xy[s], P.c_yy[s], v1, g_fx);
-      smooth_at(&tile[2][c0], i, j, H, W, P.c_xx[s], P.c_xy[s], P.c_yy[s], v2, g_fy);
+      const SmoothW w = smooth_weights(i, j, H, W, P.c_xx[s], P.c_xy[s], P.c_yy[s]);
+      smooth_at(&tile[0][c0], w, v0, g_pd);
+      smooth_at(&tile[1][c0], w, v1, g_fx);
+      smooth_at(&tile[2][c0], w, v2, g_fy);
       acc[1] = v0 + v1 + v2;
     }
-    const float gx = grid_coord(j, W, grid_step(W)), gy = grid_coord(i, H, grid_step(H));
+    const float gx = grid_coord(j, W, P.wstep[s]), gy = grid_coord(i, H, P.hstep[s]);
     const Ray ray = back_project(sx.kinv, gx, gy);
     const float lab = __ldg(P.label[s] + pix);
     {   // supervised inverse-depth error, :163-164
@@ -186,7 +234,8 @@ flow_loss_kernel(const FlowParams P) {
       float dx, dy;
       const float err = sample_error(right, H, W, q.x, q.y, tgt, dx, dy);
       acc[3] = kp * err;
-      const float du0 = dx / q.zp, du1 = dy / q.zp;
+      const float rz = __frcp_rn(q.zp);
+      const float du0 = dx * rz, du1 = dy * rz;
       const float du2 = -(q.x * du0 + q.y * du1);
       const float gc0 = du0 * sx.p[0] + du1 * sx.p[4] + du2 * sx.p[8];
       const float gc1 = du0 * sx.p[1] + du1 * sx.p[5] + du2 * sx.p[9];
@@ -220,25 +269,39 @@ __global__ void flow_xforms_kernel(const PrepJob j) {   // single-scale call: no
 }
 
 // losses[0..3] = depth, smooth, optflow, pixel; [4] = their sum (total_loss, :240).  One block, fixed order.
-__global__ void __launch_bounds__(256)
+constexpr int kFlowFinThreads = 1024;
+__global__ void __launch_bounds__(kFlowFinThreads)
 flow_finalize_kernel(const float* __restrict__ partials, int n_items, float* __restrict__ losses) {
-  __shared__ double sh[kFlowTerms][256];
+  __shared__ double sh[kFlowFinThreads / 32][kFlowTerms];
   double a[kFlowTerms] = {0.0, 0.0, 0.0, 0.0};
-  for (int i = threadIdx.x; i < n_items; i += 256) {
-    const float4 q = reinterpret_cast<const float4*>(partials)[i];
-    a[0] += (double)q.x; a[1] += (double)q.y; a[2] += (double)q.z; a[3] += (double)q.w;
+  constexpr int U = 4;                                   // rows in flight per thread
+  for (int i0 = threadIdx.x; i0 < n_items; i0 += kFlowFinThreads * U) {
+    float4 q[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + u * kFlowFinThreads;
+      q[u] = i < n_items ? reinterpret_cast<const float4*>(partials)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) { a[0] += (double)q[u].x; a[1] += (double)q[u].y; a[2] += (double)q[u].z; a[3] += (double)q[u].w; }
   }
 #pragma unroll
-  for (int k = 0; k < kFlowTerms; ++k) sh[k][threadIdx.x] = a[k];
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int k = 0; k < kFlowTerms; ++k) a[k] += __shfl_xor_sync(0xffffffffu, a[k], o);
+  if ((threadIdx.x & 31) == 0)
+#pragma unroll
+    for (int k = 0; k < kFlowTerms; ++k) sh[threadIdx.x >> 5][k] = a[k];
   __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if ((int)threadIdx.x < o)
+  if (threadIdx.x == 0) {
+    double t[kFlowTerms] = {0.0, 0.0, 0.0, 0.0};
+    for (int w = 0; w < kFlowFinThreads / 32; ++w)
 #pragma unroll
-      for (int k = 0; k < kFlowTerms; ++k) sh[k][threadIdx.x] += sh[k][threadIdx.x + o];
-    __syncthreads();
+      for (int k = 0; k < kFlowTerms; ++k) t[k] += sh[w][k];
+#pragma unroll
+    for (int k = 0; k < kFlowTerms; ++k) losses[k] = (float)t[k];
+    losses[4] = (float)(((t[0] + t[1]) + t[2]) + t[3]);
   }
-  if (threadIdx.x < kFlowTerms) losses[threadIdx.x] = (float)sh[threadIdx.x][0];
-  if (threadIdx.x == 0) losses[4] = (float)(((sh[0][0] + sh[1][0]) + sh[2][0]) + sh[3][0]);
 }
 
 namespace {
@@ -320,6 +383,7 @@ int vsl_flow_loss_fwd_bwd(const VslFlowLossDesc* d, const float* left, const flo
       P.left[s] = P.right[s] = P.label[s] = P.pd[s] = P.fx[s] = P.fy[s] = nullptr;
       P.g_pd[s] = P.g_fx[s] = P.g_fy[s] = nullptr;
       P.c_depth[s] = P.c_pixel[s] = P.c_flow[s] = P.c_xx[s] = P.c_xy[s] = P.c_yy[s] = 0.f;
+      P.wstep[s] = P.hstep[s] = 0.f;
       P.item_begin[s + 1] = items;
       continue;
     }
@@ -342,6 +406,8 @@ int vsl_flow_loss_fwd_bwd(const VslFlowLossDesc* d, const float* left, const flo
     P.c_xx[s] = (float)(d->smooth_weight * k / ((double)d->B * Hs * (Ws - 2)));
     P.c_yy[s] = (float)(d->smooth_weight * k / ((double)d->B * (Hs - 2) * Ws));
     P.c_xy[s] = (float)(d->smooth_weight * k / ((double)d->B * (Hs - 1) * (Ws - 1)));
+    P.wstep[s] = 2.0f / (float)(Ws - 1);
+    P.hstep[s] = 2.0f / (float)(Hs - 1);
   }
 
   // launches 1-2: pyramids (+ the transform table: one matrix pose per image, every scale)
@@ -373,7 +439,7 @@ int vsl_flow_loss_fwd_bwd(const VslFlowLossDesc* d, const float* left, const flo
   flow_loss_kernel<<<items, kFlowTW * kFlowTH, 0, st>>>(P);
   int e = launch_status();
   if (e != VSL_OK) return e;
-  flow_finalize_kernel<<<1, 256, 0, st>>>(P.partials, items, losses);
+  flow_finalize_kernel<<<1, kFlowFinThreads, 0, st>>>(P.partials, items, losses);
   return launch_status();
 }
 

@@ -72,7 +72,11 @@ template <int V> struct PairSmem {   // the general kernel's layout: the row tab
 };
 
 template <int V>
+#ifdef VSL_FUSED_MAXNREG   // timing experiments: an explicit register cap instead of the one launch bounds imply
+__global__ void __maxnreg__(VSL_FUSED_MAXNREG)
+#else
 __global__ void __launch_bounds__(kThreads, (V <= 2 ? VSL_FUSED_MIN_BLOCKS : VSL_FUSED_MIN_BLOCKS / 2))
+#endif
 loss_fused_pair_kernel(const LossParams P) {
   static_assert(V % 2 == 0, "views are processed in pairs");
   constexpr int NP = V / 2, N = NT<V>::value;

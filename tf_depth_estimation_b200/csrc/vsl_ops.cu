@@ -37,13 +37,82 @@ __global__ void prep_xforms_kernel(const PrepJob j) {
 }
 
 // =====================================================================================================
+// d/d(img) of the sampler: w_k * g[c] of every target pixel added into the four corners of its footprint
+// (unsorted_segment_sum in TF's gather backward).  Warp-aggregated: consecutive lanes are consecutive target
+// pixels, and under a smooth warp lane l+1's LEFT corner column is lane l's RIGHT one -- so a lane hands the
+// contributions of its right column to its neighbour by shuffle whenever the neighbour's left column is the same
+// pair of pixels, and each lane then issues reductions for two corners instead of four.  A corner pixel of a packed
+// RGB image is 12 bytes: one 8-byte vector reduction (red.global.add.v2.f32) on its 8-byte aligned pair plus one
+// scalar, instead of three scalars.  Per target pixel: 4 reduction instructions where the plain form has 12.
+// The summation order stays unspecified (float atomics), as before.  Every lane of the warp must call this.
+// =====================================================================================================
+VSL_DEV void red_add(float* p, float v) { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
+VSL_DEV void red_add2(float* p, float a, float b) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
+template <int C>
+VSL_DEV void red_pixel(float* p, const float (&v)[C]) {
+  if (C == 3) {
+    if ((reinterpret_cast<uintptr_t>(p) & 7) == 0) { red_add2(p, v[0], v[1]); red_add(p + 2, v[2]); }
+    else { red_add(p, v[0]); red_add2(p + 1, v[1], v[2]); }
+  } else if (C == 2 || C == 4) {
+    if ((reinterpret_cast<uintptr_t>(p) & 7) == 0) {
+#pragma unroll
+      for (int c = 0; c < C; c += 2) red_add2(p + c, v[c], v[c + 1 < C ? c + 1 : c]);
+    } else {
+#pragma unroll
+      for (int c = 0; c < C; ++c) red_add(p + c, v[c]);
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < C; ++c) red_add(p + c, v[c]);
+  }
+}
+
+// gimg: this image's gradient plane [Hs,Ws,C]; f: the lane's footprint; g: upstream gradient of its output pixel
+// (ignored unless active).
+template <int C>
+VSL_DEV void scatter_corners(float* __restrict__ gimg, int Ws, const Foot& f, const float (&g)[C], bool active) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int x0 = active ? f.x0 : -1, y0 = active ? f.y0 : -1, y1 = active ? f.y1 : -1;
+  const float w00 = active ? f.wx0 * f.wy0 : 0.f, w01 = active ? f.wx0 * f.wy1 : 0.f;
+  const float w10 = active ? f.wx1 * f.wy0 : 0.f, w11 = active ? f.wx1 * f.wy1 : 0.f;
+  // does the neighbour's left column coincide with my right column?  (an inactive neighbour reports -1)
+  const int nx0 = __shfl_down_sync(full, x0, 1), ny0 = __shfl_down_sync(full, y0, 1), ny1 = __shfl_down_sync(full, y1, 1);
+  const bool give = active && lane < 31 && nx0 == f.x1 && ny0 == y0 && ny1 == y1;
+  const bool take = __shfl_up_sync(full, (int)give, 1) != 0 && lane > 0;
+  float l0[C], l1[C], r0[C], r1[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    const float gc = active ? g[c] : 0.f;
+    r0[c] = w10 * gc; r1[c] = w11 * gc;
+    const float in0 = __shfl_up_sync(full, r0[c], 1), in1 = __shfl_up_sync(full, r1[c], 1);
+    l0[c] = w00 * gc + (take ? in0 : 0.f);
+    l1[c] = w01 * gc + (take ? in1 : 0.f);
+  }
+  if (!active) return;
+  bool any_l0 = false, any_l1 = false, any_r0 = false, any_r1 = false;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    any_l0 |= l0[c] != 0.f; any_l1 |= l1[c] != 0.f; any_r0 |= r0[c] != 0.f; any_r1 |= r1[c] != 0.f;
+  }
+  if (any_l0) red_pixel<C>(gimg + ((size_t)y0 * Ws + x0) * C, l0);
+  if (any_l1) red_pixel<C>(gimg + ((size_t)y1 * Ws + x0) * C, l1);
+  if (!give) {
+    if (any_r0) red_pixel<C>(gimg + ((size_t)y0 * Ws + f.x1) * C, r0);
+    if (any_r1) red_pixel<C>(gimg + ((size_t)y1 * Ws + f.x1) * C, r1);
+  }
+}
+
+// =====================================================================================================
 // projective_inverse_warp  (utils.py:168-199, utils_lr.py:222-256)
 // grid = (ceil(H*W / 256), B); one thread per target pixel.
 // =====================================================================================================
 template <int C>
 __global__ void __launch_bounds__(256)
 warp_fwd_kernel(const float* __restrict__ img, const float* __restrict__ depth, const Xform* __restrict__ xf,
-                int H, int W, float* __restrict__ out, float* __restrict__ coords, float* __restrict__ wmask,
+                int H, int W, float wstep, float hstep, float* __restrict__ out, float* __restrict__ coords, float* __restrict__ wmask,
                 float* __restrict__ zout) {
   __shared__ Xform sx;
   const int b = blockIdx.y;
@@ -53,7 +122,7 @@ warp_fwd_kernel(const float* __restrict__ img, const float* __restrict__ depth, 
   if (pix >= H * W) return;
   const int i = pix / W, j = pix - i * W;
   const size_t gp = (size_t)b * H * W + pix;
-  const float gx = grid_coord(j, W, grid_step(W)), gy = grid_coord(i, H, grid_step(H));
+  const float gx = grid_coord(j, W, wstep), gy = grid_coord(i, H, hstep);   // steps: 2/(n-1) in fp32, from the host
   const float d = depth[gp];
   Ray r = back_project(sx.kinv, gx, gy);
   Proj q = project(sx.p, __fmul_rn(r.r0, d), __fmul_rn(r.r1, d), __fmul_rn(r.r2, d));
@@ -80,7 +149,7 @@ warp_fwd_kernel(const float* __restrict__ img, const float* __restrict__ depth, 
 template <int C>
 __global__ void __launch_bounds__(256)
 warp_bwd_kernel(const float* __restrict__ img, const float* __restrict__ depth, const Xform* __restrict__ xf,
-                int H, int W, const float* __restrict__ g_out, const float* __restrict__ g_coords,
+                int H, int W, float wstep, float hstep, const float* __restrict__ g_out, const float* __restrict__ g_coords,
                 const float* __restrict__ g_wmask, const float* __restrict__ g_z, float* __restrict__ g_img,
                 float* __restrict__ g_depth, float* __restrict__ partial) {
   __shared__ Xform sx;
@@ -92,34 +161,33 @@ warp_bwd_kernel(const float* __restrict__ img, const float* __restrict__ depth, 
   float acc[12];
 #pragma unroll
   for (int k = 0; k < 12; ++k) acc[k] = 0.f;
-  if (pix < H * W) {
+  const bool active = pix < H * W;
+  Foot f = {};
+  float gch[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) gch[c] = 0.f;
+  if (active) {
     const int i = pix / W, j = pix - i * W;
     const size_t gp = (size_t)b * H * W + pix;
-    const float gx = grid_coord(j, W, grid_step(W)), gy = grid_coord(i, H, grid_step(H));
+    const float gx = grid_coord(j, W, wstep), gy = grid_coord(i, H, hstep);   // steps: 2/(n-1) in fp32, from the host
     const float d = depth[gp];
     Ray r = back_project(sx.kinv, gx, gy);
     const float c0 = __fmul_rn(r.r0, d), c1 = __fmul_rn(r.r1, d), c2 = __fmul_rn(r.r2, d);
     Proj q = project(sx.p, c0, c1, c2);
-    Foot f = footprint(q.x, q.y, W, H);
+    f = footprint(q.x, q.y, W, H);
     float dx = 0.f, dy = 0.f;
     if (g_out != nullptr) {
       const size_t ib = (size_t)b * H * W * C;
       const size_t o00 = ib + ((size_t)f.y0 * W + f.x0) * C, o01 = ib + ((size_t)f.y1 * W + f.x0) * C;
       const size_t o10 = ib + ((size_t)f.y0 * W + f.x1) * C, o11 = ib + ((size_t)f.y1 * W + f.x1) * C;
-      const float w00 = f.wx0 * f.wy0, w01 = f.wx0 * f.wy1, w10 = f.wx1 * f.wy0, w11 = f.wx1 * f.wy1;
 #pragma unroll
       for (int c = 0; c < C; ++c) {
         const float g = g_out[gp * C + c];
+        gch[c] = g;
         const float i00 = __ldg(img + o00 + c), i01 = __ldg(img + o01 + c), i10 = __ldg(img + o10 + c),
                     i11 = __ldg(img + o11 + c);
         dx += g * (f.wy0 * (f.mx1 * i10 - f.mx0 * i00) + f.wy1 * (f.mx1 * i11 - f.mx0 * i01));
         dy += g * (f.wx0 * (f.my1 * i01 - f.my0 * i00) + f.wx1 * (f.my1 * i11 - f.my0 * i10));
-        if (g_img != nullptr) {
-          if (w00 != 0.f) atomicAdd(g_img + o00 + c, w00 * g);
-          if (w01 != 0.f) atomicAdd(g_img + o01 + c, w01 * g);
-          if (w10 != 0.f) atomicAdd(g_img + o10 + c, w10 * g);
-          if (w11 != 0.f) atomicAdd(g_img + o11 + c, w11 * g);
-        }
       }
     }
     if (g_wmask != nullptr) {
@@ -132,7 +200,8 @@ warp_bwd_kernel(const float* __restrict__ img, const float* __restrict__ depth, 
       dx += gc.x;
       dy += gc.y;
     }
-    const float du0 = dx / q.zp, du1 = dy / q.zp;
+    const float rz = __frcp_rn(q.zp);
+    const float du0 = dx * rz, du1 = dy * rz;
     float du2 = -(q.x * du0 + q.y * du1);
     if (g_z != nullptr) du2 += g_z[gp];
     if (g_depth != nullptr) {
@@ -145,6 +214,8 @@ warp_bwd_kernel(const float* __restrict__ img, const float* __restrict__ depth, 
     acc[4] = du1 * c0; acc[5] = du1 * c1; acc[6] = du1 * c2; acc[7] = du1;
     acc[8] = du2 * c0; acc[9] = du2 * c1; acc[10] = du2 * c2; acc[11] = du2;
   }
+  if (g_img != nullptr && g_out != nullptr)   // block-uniform: every lane takes part in the shuffles
+    scatter_corners<C>(g_img + (size_t)b * H * W * C, W, f, gch, active);
   if (partial != nullptr) block_sum_bfly<12>(acc, scratch, partial + ((size_t)b * gridDim.x + blockIdx.x) * 12);
 }
 
@@ -221,38 +292,40 @@ bilinear_bwd_kernel(const float* __restrict__ imgs, const float* __restrict__ co
                     int Wt, const float* __restrict__ g_out, const float* __restrict__ g_wmask,
                     float* __restrict__ g_imgs, float* __restrict__ g_coords) {
   const int b = blockIdx.y, pix = blockIdx.x * blockDim.x + threadIdx.x;
-  if (pix >= Ht * Wt) return;
-  const int i = pix / Wt, j = pix - i * Wt;
-  const size_t gp = (size_t)b * Ht * Wt + pix;
-  const float2 xy = sample_coords(coords, flowx, flowy, gp, i, j, Ht, Wt);
-  Foot f = footprint(xy.x, xy.y, Ws, Hs);
-  const size_t ib = (size_t)b * Hs * Ws * C;
-  const size_t o00 = ib + ((size_t)f.y0 * Ws + f.x0) * C, o01 = ib + ((size_t)f.y1 * Ws + f.x0) * C;
-  const size_t o10 = ib + ((size_t)f.y0 * Ws + f.x1) * C, o11 = ib + ((size_t)f.y1 * Ws + f.x1) * C;
-  const float w00 = f.wx0 * f.wy0, w01 = f.wx0 * f.wy1, w10 = f.wx1 * f.wy0, w11 = f.wx1 * f.wy1;
-  float dx = 0.f, dy = 0.f;
-  if (g_out != nullptr) {
+  const bool active = pix < Ht * Wt;
+  Foot f = {};
+  float gch[C];
 #pragma unroll
-    for (int c = 0; c < C; ++c) {
-      const float g = g_out[gp * C + c];
-      const float i00 = __ldg(imgs + o00 + c), i01 = __ldg(imgs + o01 + c), i10 = __ldg(imgs + o10 + c),
-                  i11 = __ldg(imgs + o11 + c);
-      dx += g * (f.wy0 * (f.mx1 * i10 - f.mx0 * i00) + f.wy1 * (f.mx1 * i11 - f.mx0 * i01));
-      dy += g * (f.wx0 * (f.my1 * i01 - f.my0 * i00) + f.wx1 * (f.my1 * i11 - f.my0 * i10));
-      if (g_imgs != nullptr) {
-        if (w00 != 0.f) atomicAdd(g_imgs + o00 + c, w00 * g);
-        if (w01 != 0.f) atomicAdd(g_imgs + o01 + c, w01 * g);
-        if (w10 != 0.f) atomicAdd(g_imgs + o10 + c, w10 * g);
-        if (w11 != 0.f) atomicAdd(g_imgs + o11 + c, w11 * g);
+  for (int c = 0; c < C; ++c) gch[c] = 0.f;
+  if (active) {
+    const int i = pix / Wt, j = pix - i * Wt;
+    const size_t gp = (size_t)b * Ht * Wt + pix;
+    const float2 xy = sample_coords(coords, flowx, flowy, gp, i, j, Ht, Wt);
+    f = footprint(xy.x, xy.y, Ws, Hs);
+    const size_t ib = (size_t)b * Hs * Ws * C;
+    const size_t o00 = ib + ((size_t)f.y0 * Ws + f.x0) * C, o01 = ib + ((size_t)f.y1 * Ws + f.x0) * C;
+    const size_t o10 = ib + ((size_t)f.y0 * Ws + f.x1) * C, o11 = ib + ((size_t)f.y1 * Ws + f.x1) * C;
+    float dx = 0.f, dy = 0.f;
+    if (g_out != nullptr) {
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const float g = g_out[gp * C + c];
+        gch[c] = g;
+        const float i00 = __ldg(imgs + o00 + c), i01 = __ldg(imgs + o01 + c), i10 = __ldg(imgs + o10 + c),
+                    i11 = __ldg(imgs + o11 + c);
+        dx += g * (f.wy0 * (f.mx1 * i10 - f.mx0 * i00) + f.wy1 * (f.mx1 * i11 - f.mx0 * i01));
+        dy += g * (f.wx0 * (f.my1 * i01 - f.my0 * i00) + f.wx1 * (f.my1 * i11 - f.my0 * i10));
       }
     }
+    if (g_wmask != nullptr) {
+      const float g = g_wmask[gp];
+      dx += g * (f.wy0 + f.wy1) * (f.mx1 - f.mx0);
+      dy += g * (f.wx0 + f.wx1) * (f.my1 - f.my0);
+    }
+    if (g_coords != nullptr) reinterpret_cast<float2*>(g_coords)[gp] = make_float2(dx, dy);
   }
-  if (g_wmask != nullptr) {
-    const float g = g_wmask[gp];
-    dx += g * (f.wy0 + f.wy1) * (f.mx1 - f.mx0);
-    dy += g * (f.wx0 + f.wx1) * (f.my1 - f.my0);
-  }
-  if (g_coords != nullptr) reinterpret_cast<float2*>(g_coords)[gp] = make_float2(dx, dy);
+  if (g_imgs != nullptr && g_out != nullptr)   // block-uniform: every lane takes part in the shuffles
+    scatter_corners<C>(g_imgs + (size_t)b * Hs * Ws * C, Ws, f, gch, active);
 }
 
 // consistent_depth_loss (utils_lr.py:369-458) in one pass: the 1-channel bilinear fetch of src_depth at `coords`
@@ -670,11 +743,12 @@ int vsl_warp_fwd(const float* img, const float* depth, const float* pose, const 
   Xform* xf = reinterpret_cast<Xform*>(ws);
   prep_xforms_kernel<<<(B + 63) / 64, 64, 0, st>>>(make_prep(pose, K, B, 1, 1, format, xf, pose_mat));
   dim3 grid(warp_nblk(H, W), B);
+  const float ws_ = 2.0f / (float)(W - 1), hs_ = 2.0f / (float)(H - 1);   // IEEE float division, as grid_step()
   switch (C) {
-    case 1: warp_fwd_kernel<1><<<grid, 256, 0, st>>>(img, depth, xf, H, W, out_img, coords, wmask, src_depth); break;
-    case 2: warp_fwd_kernel<2><<<grid, 256, 0, st>>>(img, depth, xf, H, W, out_img, coords, wmask, src_depth); break;
-    case 3: warp_fwd_kernel<3><<<grid, 256, 0, st>>>(img, depth, xf, H, W, out_img, coords, wmask, src_depth); break;
-    default: warp_fwd_kernel<4><<<grid, 256, 0, st>>>(img, depth, xf, H, W, out_img, coords, wmask, src_depth); break;
+    case 1: warp_fwd_kernel<1><<<grid, 256, 0, st>>>(img, depth, xf, H, W, ws_, hs_, out_img, coords, wmask, src_depth); break;
+    case 2: warp_fwd_kernel<2><<<grid, 256, 0, st>>>(img, depth, xf, H, W, ws_, hs_, out_img, coords, wmask, src_depth); break;
+    case 3: warp_fwd_kernel<3><<<grid, 256, 0, st>>>(img, depth, xf, H, W, ws_, hs_, out_img, coords, wmask, src_depth); break;
+    default: warp_fwd_kernel<4><<<grid, 256, 0, st>>>(img, depth, xf, H, W, ws_, hs_, out_img, coords, wmask, src_depth); break;
   }
   return launch_status();
 }
@@ -697,11 +771,12 @@ int vsl_warp_bwd(const float* img, const float* depth, const float* pose, const 
   const int nblk = warp_nblk(H, W);
   dim3 grid(nblk, B);
   float* part = g_pose ? partial : nullptr;
+  const float ws_ = 2.0f / (float)(W - 1), hs_ = 2.0f / (float)(H - 1);
   switch (C) {
-    case 1: warp_bwd_kernel<1><<<grid, 256, 0, st>>>(img, depth, xf, H, W, g_out_img, g_coords, g_wmask, g_src_depth, g_img, g_depth, part); break;
-    case 2: warp_bwd_kernel<2><<<grid, 256, 0, st>>>(img, depth, xf, H, W, g_out_img, g_coords, g_wmask, g_src_depth, g_img, g_depth, part); break;
-    case 3: warp_bwd_kernel<3><<<grid, 256, 0, st>>>(img, depth, xf, H, W, g_out_img, g_coords, g_wmask, g_src_depth, g_img, g_depth, part); break;
-    default: warp_bwd_kernel<4><<<grid, 256, 0, st>>>(img, depth, xf, H, W, g_out_img, g_coords, g_wmask, g_src_depth, g_img, g_depth, part); break;
+    case 1: warp_bwd_kernel<1><<<grid, 256, 0, st>>>(img, depth, xf, H, W, ws_, hs_, g_out_img, g_coords, g_wmask, g_src_depth, g_img, g_depth, part); break;
+    case 2: warp_bwd_kernel<2><<<grid, 256, 0, st>>>(img, depth, xf, H, W, ws_, hs_, g_out_img, g_coords, g_wmask, g_src_depth, g_img, g_depth, part); break;
+    case 3: warp_bwd_kernel<3><<<grid, 256, 0, st>>>(img, depth, xf, H, W, ws_, hs_, g_out_img, g_coords, g_wmask, g_src_depth, g_img, g_depth, part); break;
+    default: warp_bwd_kernel<4><<<grid, 256, 0, st>>>(img, depth, xf, H, W, ws_, hs_, g_out_img, g_coords, g_wmask, g_src_depth, g_img, g_depth, part); break;
   }
   if (g_pose != nullptr)
     warp_bwd_finalize_kernel<<<B, 32, 0, st>>>(partial, nblk, pose, K, g_pose_mat, B, format, g_pose);

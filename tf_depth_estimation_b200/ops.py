@@ -168,6 +168,7 @@ class _ProjectiveInverseWarp(torch.autograd.Function):
     @staticmethod
     def forward(ctx, img, depth, pose, K, fmt):
         lib = _lib.load()
+        ctx.set_materialize_grads(False)   # unused outputs arrive as None, not as zero-filled maps the kernel would read
         img, depth, pose, K = _f32(img, 'img'), _f32(depth, 'depth'), _f32(pose, 'pose'), _f32(K, 'intrinsics')
         B, H, W, C = img.shape
         dev = img.device
@@ -221,6 +222,7 @@ class _Bilinear(torch.autograd.Function):
     @staticmethod
     def forward(ctx, imgs, coords, flowx, flowy):
         lib = _lib.load()
+        ctx.set_materialize_grads(False)
         imgs = _f32(imgs, 'imgs')
         B, Hs, Ws, C = imgs.shape
         if coords is not None:
@@ -371,6 +373,7 @@ def pixel2cam(depth, pixel_coords, intrinsics, is_homogeneous=True):
 class _Cam2Pixel(torch.autograd.Function):
     @staticmethod
     def forward(ctx, cam, proj):
+        ctx.set_materialize_grads(False)
         cam, proj = _f32(cam, 'cam_coords'), _f32(proj, 'proj')
         B, _, H, W = cam.shape
         coords = torch.empty(B, H, W, 2, device=cam.device)
