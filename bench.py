@@ -351,6 +351,7 @@ def run_ours(args):
     # ---- e2e: host buffers in, host results out, through the public API (ops.HostPipeline): every step copies
     # all its inputs from pinned host memory and all its losses + gradients back; H2D / kernels / D2H of
     # neighbouring steps overlap on three streams.  Frames travel as the loader's uint8.
+    numa_cpus = vdist.bind_host_to_gpu(dev) if world > 1 else None   # pinned arenas on the GPU's own NUMA node
     pipe = ops.HostPipeline(B, H, W, V, flags8, _lib.MASK_EXP, dev, loss_scale=scale)
     h_in = pipe.host_inputs()          # pinned host tensors carved from one arena: a step's inputs move as ONE copy
     h_in['tgt'].copy_(to_u8(host['tgt'])); h_in['poses'].copy_(host['poses']); h_in['Kp'].copy_(host['K_pyr'])
@@ -411,6 +412,7 @@ def run_ours(args):
                                 'how': 'the same device-resident step with the frames as uint8 (converted on load, results bit-identical)'},
             'e2e': {'value': total_pv / (e2e_ms * 1e-3) / 1e6, 'unit': UNIT, 'ms_per_step': e2e_ms,
                     'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'steps': Ke,
+                    'host_numa_bound_cpus': len(numa_cpus) if numa_cpus else None,
                     'how': 'ops.HostPipeline: pinned host inputs (frames uint8 as the loader holds them, network outputs float32) '
                            '-> H2D (one copy) -> 3 launches -> D2H of losses and all gradients (one copy), double-buffered over 3 streams'},
             'gpu_launches': 3 * K, 'launches_per_step': 3, 'clocks': clocks,

@@ -253,6 +253,14 @@ int vsl_flow_loss_fwd_bwd(const VslFlowLossDesc* d, const float* left /*[B,H,W,3
                           const float* K_pyr /*[B,S,3,3]*/, float* losses /*device [5]*/, float* const* g_depth_pyr,
                           float* const* g_flowx_pyr, float* const* g_flowy_pyr, void* ws, vsl_stream_t stream);
 
+/* ---- the image path of the DeMoN-pair loader on the device (imageselect_Dataloader_optflow.py:120-133, :218-236):
+ *      strip = the decoded JPEG, uint8 [B,h,w,3], two frames side by side -> tf.image.resize_images(strip, [H, 2 W])
+ *      (bilinear, TF 1.x ResizeBilinear semantics: no align_corners, no half-pixel centres) -> tf.to_float ->
+ *      unpack_image_sequence: tgt = columns [0, W), src = columns [W, 2 W), float32 [B,H,W,3] in the 0..255 range the
+ *      script feeds (its `/ 255.0` is commented out, :129). */
+int vsl_unpack_strip(const unsigned char* strip, int B, int h, int w, int H, int W, float* tgt, float* src,
+                     vsl_stream_t stream);
+
 /* ---- upstream gradient of the summed loss: dst[0..n) = src[0..n) * (*num / *den) (num, den: device floats; den
  *      NULL means 1).  What TF autodiff does with the incoming gradient of `total_loss` in the reference
  *      (slim.learning.create_train_op, train_depth_then_cam_lr.py:417), applied to the whole gradient arena of a

@@ -442,6 +442,38 @@ def flow_depth_loss(image_left, image_right, label, pred_depth, pred_optflow_x, 
     return depth_loss, (smooth + smooth_x) + smooth_y, optflow, pixel      # :238: the three sums, then added
 
 
+def resize_bilinear_tf1(img, out_h, out_w):
+    """tf.image.resize_images(img, [out_h, out_w]) as the loaders call it (bilinear; TF 1.x ResizeBilinear, an
+    un-vendored and unpinned third party: kernels/resize_bilinear_op.cc with align_corners = False and no half-pixel
+    centres -- PARITY UNPINNED, a restatement of the published algorithm).  img: [B,h,w,C] (any real dtype) -> float32.
+    in = out_index * (in_size / float(out_size)); lower = floor(in), upper = min(ceil(in), in_size - 1),
+    lerp = in - lower; top = tl + (tr - tl) * x_lerp; bottom likewise; out = top + (bottom - top) * y_lerp."""
+    B, h, w, C = img.shape
+    f = img.to(torch.float32)
+
+    def axis(n_in, n_out):
+        scale = torch.tensor(n_in, dtype=torch.float32) / torch.tensor(n_out, dtype=torch.float32)
+        pos = torch.arange(n_out, dtype=torch.float32) * scale
+        lo = torch.floor(pos)
+        hi = torch.clamp(torch.ceil(pos), max=float(n_in - 1))
+        return lo.long(), hi.long(), pos - lo
+    y0, y1, ly = axis(h, out_h)
+    x0, x1, lx = axis(w, out_w)
+    lx = lx.reshape(1, 1, out_w, 1)
+    ly = ly.reshape(1, out_h, 1, 1)
+    rows0, rows1 = f[:, y0], f[:, y1]
+    top = rows0[:, :, x0] + (rows0[:, :, x1] - rows0[:, :, x0]) * lx
+    bot = rows1[:, :, x0] + (rows1[:, :, x1] - rows1[:, :, x0]) * lx
+    return top + (bot - top) * ly
+
+
+def unpack_strip(strip_u8, H, W):
+    """imageselect_Dataloader_optflow.py:120-133, :218-236: resize the decoded two-frame strip to [H, 2 W], to_float,
+    target = columns [0, W), source = columns [W, 2 W)."""
+    seq = resize_bilinear_tf1(strip_u8, H, 2 * W)
+    return seq[:, :, :W].contiguous(), seq[:, :, W:].contiguous()
+
+
 # ----------------------------------------------------------------------------
 # flagged-off extensions named by BASELINE.json but ABSENT from the reference:
 # "parity unpinned -- no reference implementation" (SURVEY.md D1/D2)

@@ -144,3 +144,14 @@ def test_data_parallel_adam_layout():
     assert float(dp.grad_flat.sum()) == 3.0 * 24                    # views alias the arena
     with pytest.raises(TypeError):
         vdist.DataParallelAdam(SHAPES, 'cpu', lr=0.1).step()        # default update = the CUDA kernel: no CPU fallback
+
+
+def test_numa_binding_helper(tmp_path, monkeypatch):
+    """bind_host_to_gpu: cpulist parsing, and no effect where the topology is not exposed (this CPU container)."""
+    import os
+    from tf_depth_estimation_b200 import dist as vdist
+    assert vdist._parse_cpulist('0-3,8,10-11\n') == {0, 1, 2, 3, 8, 10, 11}
+    assert vdist._parse_cpulist('') == set()
+    before = os.sched_getaffinity(0)
+    assert vdist.bind_host_to_gpu('cuda:0', sysfs=str(tmp_path)) is None
+    assert os.sched_getaffinity(0) == before

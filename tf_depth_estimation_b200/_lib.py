@@ -90,6 +90,7 @@ SIGNATURES = {
     'vsl_flow_loss_fwd_bwd': (ctypes.c_int, [ctypes.POINTER(VslFlowLossDesc)] + [_c_float_p] * 3 +
                               [ctypes.POINTER(ctypes.c_void_p)] * 3 + [_c_float_p] * 3 +
                               [ctypes.POINTER(ctypes.c_void_p)] * 3 + [ctypes.c_void_p, _c_stream]),
+    'vsl_unpack_strip': (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_int] * 5 + [_c_float_p] * 2 + [_c_stream]),
     'vsl_scale': (ctypes.c_int, [_c_float_p] * 2 + [ctypes.c_longlong] + [_c_float_p] * 2 + [_c_stream]),
     'vsl_adam_step': (ctypes.c_int, [_c_float_p] * 4 + [ctypes.c_longlong] + [ctypes.c_float] * 4 + [ctypes.c_int, ctypes.c_float, _c_stream]),
     'vsl_peer_alloc': (ctypes.c_int, [ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]),

@@ -263,6 +263,42 @@ flow_loss_kernel(const FlowParams P) {
   block_sum<kFlowTerms>(acc, scratch, P.partials + (size_t)item * kFlowTerms);
 }
 
+// =====================================================================================================
+// The loader's image path on the device (imageselect_Dataloader_optflow.py:120-133, :218-236): the decoded JPEG strip
+// (uint8, two frames side by side) -> tf.image.resize_images(strip, [H, 2 W]) (bilinear, TF1 semantics) ->
+// tf.to_float -> unpack_image_sequence (target = columns [0, W), source = columns [W, 2 W)).  One thread per output
+// pixel and frame, all channels.  TF's ResizeBilinear (un-vendored, unpinned TF 1.x: kernels/resize_bilinear_op.cc,
+// align_corners = false, no half-pixel centres): in = out_index * (in_size / (float) out_size); lower = floor(in),
+// upper = min(ceil(in), in_size - 1), lerp = in - lower; top = tl + (tr - tl) * x_lerp, bottom likewise,
+// out = top + (bottom - top) * y_lerp, all in float32.
+// =====================================================================================================
+__global__ void __launch_bounds__(256)
+unpack_strip_kernel(const unsigned char* __restrict__ strip, int B, int h, int w, int H, int W, float hscale,
+                    float wscale, float* __restrict__ tgt, float* __restrict__ src) {
+  const size_t n = (size_t)B * H * 2 * W;
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const int X = (int)(e % (size_t)(2 * W)), Y = (int)((e / (size_t)(2 * W)) % (size_t)H), b = (int)(e / ((size_t)2 * W * H));
+  const float iy = __fmul_rn((float)Y, hscale), ix = __fmul_rn((float)X, wscale);
+  const float fy0 = floorf(iy), fx0 = floorf(ix);
+  const int y0 = (int)fy0, x0 = (int)fx0;
+  const int y1 = min((int)ceilf(iy), h - 1), x1 = min((int)ceilf(ix), w - 1);
+  const float ly = __fsub_rn(iy, fy0), lx = __fsub_rn(ix, fx0);
+  const unsigned char* img = strip + (size_t)b * h * w * 3;
+  const unsigned char* tl = img + ((size_t)y0 * w + x0) * 3;
+  const unsigned char* tr = img + ((size_t)y0 * w + x1) * 3;
+  const unsigned char* bl = img + ((size_t)y1 * w + x0) * 3;
+  const unsigned char* br = img + ((size_t)y1 * w + x1) * 3;
+  float* out = (X < W ? tgt : src) + (((size_t)b * H + Y) * W + (X < W ? X : X - W)) * 3;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float a = (float)tl[c], bq = (float)tr[c], cq = (float)bl[c], d = (float)br[c];
+    const float top = __fadd_rn(a, __fmul_rn(__fsub_rn(bq, a), lx));
+    const float bot = __fadd_rn(cq, __fmul_rn(__fsub_rn(d, cq), lx));
+    out[c] = __fadd_rn(top, __fmul_rn(__fsub_rn(bot, top), ly));
+  }
+}
+
 __global__ void flow_xforms_kernel(const PrepJob j) {   // single-scale call: no pyramid launch to ride on
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx < j.n) prep_one(j, idx);
@@ -349,6 +385,18 @@ FlowLayout flow_layout(const VslFlowLossDesc* d) {
 using namespace vsl;
 
 extern "C" {
+
+int vsl_unpack_strip(const unsigned char* strip, int B, int h, int w, int H, int W, float* tgt, float* src,
+                     vsl_stream_t stream) {
+  VSL_REQUIRE(strip && tgt && src, VSL_E_NULL);
+  VSL_REQUIRE(B > 0 && h > 0 && w > 1 && H > 0 && W > 0 && (long long)B * H * W * 6 < (1ll << 40), VSL_E_SHAPE);
+  const size_t n = (size_t)B * H * 2 * W;
+  // CalculateResizeScale: in_size / static_cast<float>(out_size)
+  const float hscale = (float)h / (float)H, wscale = (float)w / (float)(2 * W);
+  unpack_strip_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(strip, B, h, w, H, W, hscale, wscale,
+                                                                                   tgt, src);
+  return launch_status();
+}
 
 size_t vsl_flow_loss_ws_bytes(const VslFlowLossDesc* d) {
   if (check_flow(d) != VSL_OK) return 0;

@@ -32,6 +32,38 @@ def shard_snippets(d, rank, world):
     return {k: cut(v) for k, v in d.items()}
 
 
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(','):
+        if not part:
+            continue
+        lo, _, hi = part.partition('-')
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_host_to_gpu(device, sysfs='/sys/bus/pci/devices'):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off (sysfs `local_cpulist` of the GPU's PCI
+    function), so that the pinned host arenas it allocates next are first-touched on that node and a rank's H2D / D2H
+    copies do not cross the socket interconnect.  One rank per GPU; call it before ops.HostPipeline / any pin_memory().
+    -> the set of CPUs bound to, or None when the topology is not exposed (containers, single-node hosts): then
+    nothing changes."""
+    import os
+    try:
+        props = torch.cuda.get_device_properties(device)
+        bdf = '%04x:%02x:%02x.0' % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+        with open(os.path.join(sysfs, bdf, 'local_cpulist')) as fh:
+            cpus = _parse_cpulist(fh.read())
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if not cpus or cpus == allowed:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:   # noqa: BLE001 -- no CUDA device, no sysfs, no affinity call on this platform: leave things alone
+        return None
+
+
 def local_loss_scale(batch_local, batch_global):
     """loss_scale for ViewSynthesisPlan so that sum-reduced rank gradients equal the global-batch gradient."""
     return float(batch_local) / float(batch_global)
