@@ -154,17 +154,36 @@ loss_fused_kernel(const LossParams P) {
   {
     // 4-byte cp.async with a zero source size outside the image: every element of the tile is in flight at
     // once and no register holds it on the way
-    int ty = 0, tc = lane;                       // (row, column) of flat element i, advanced without division
     const unsigned qt_s = (unsigned)__cvta_generic_to_shared(qt);
+    if (P.x_vec2[s] != 0) {
+      // 8-byte pieces: the tile starts 2 columns left of a multiple of 32 and the level's width is even, so a pair
+      // (2 p, 2 p + 1) of tile columns is 8-byte aligned and lies inside or outside the image as a whole
+      constexpr int kPairs = kQS / 2;
+      int ty = 0, tp = lane;
+      while (tp >= kPairs) { tp -= kPairs; ++ty; }
 #pragma unroll 4
-    for (int i = lane; i < kQH * kQS; i += 32) {
-      const int gy = y_base - kHalo + ty, gx = x_base - kHalo + tc;
-      const bool in = (unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W;
-      const float* src = xs + (in ? gy * W + gx : 0);
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(qt_s + 4u * i), "l"(src), "r"(in ? 4 : 0)
-                   : "memory");
-      tc += 32;
-      if (tc >= kQS) { tc -= kQS; ++ty; }
+      for (int i = lane; i < kQH * kPairs; i += 32) {
+        const int gy = y_base - kHalo + ty, gx = x_base - kHalo + 2 * tp;
+        const bool in = (unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W;
+        const float* src = xs + (in ? gy * W + gx : 0);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(qt_s + 8u * i), "l"(src), "r"(in ? 8 : 0)
+                     : "memory");
+        tp += 32 - kPairs;
+        ++ty;
+        if (tp >= kPairs) { tp -= kPairs; ++ty; }
+      }
+    } else {
+      int ty = 0, tc = lane;                     // (row, column) of flat element i, advanced without division
+#pragma unroll 4
+      for (int i = lane; i < kQH * kQS; i += 32) {
+        const int gy = y_base - kHalo + ty, gx = x_base - kHalo + tc;
+        const bool in = (unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W;
+        const float* src = xs + (in ? gy * W + gx : 0);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(qt_s + 4u * i), "l"(src), "r"(in ? 4 : 0)
+                     : "memory");
+        tc += 32;
+        if (tc >= kQS) { tc -= kQS; ++ty; }
+      }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     if (!EXACT)   // the tile's row table (fp32 linspace row coordinate of utils.py:153-159, smoothness row weights)
@@ -1826,7 +1845,7 @@ int loss_fwd_bwd(const VslLossDesc* d, const void* tgt, const void* const* srcs,
   for (int v = 0; v < d->V; ++v) VSL_REQUIRE(srcs[v], VSL_E_NULL);
   for (int s = 0; s < VSL_MAX_SCALES; ++s) {
     P.tgt[s] = nullptr; P.x[s] = nullptr; P.logits[s] = nullptr; P.mask[s] = nullptr;
-    P.g_x[s] = nullptr; P.g_logits[s] = nullptr; P.lg_vec4[s] = 0; P.strips[s] = 0; P.bands[s] = 0;
+    P.g_x[s] = nullptr; P.g_logits[s] = nullptr; P.lg_vec4[s] = 0; P.x_vec2[s] = 0; P.strips[s] = 0; P.bands[s] = 0;
     for (int v = 0; v < VSL_MAX_VIEWS; ++v) { P.src[v][s] = nullptr; P.gsrc[v][s] = nullptr; P.gsd[v][s] = nullptr; }
     P.ccon[s] = 0.f;
   }
@@ -1836,6 +1855,7 @@ int loss_fwd_bwd(const VslLossDesc* d, const void* tgt, const void* const* srcs,
     VSL_REQUIRE(x_pyr[s] && g_x_pyr[s], VSL_E_NULL);
     P.x[s] = x_pyr[s];
     P.g_x[s] = g_x_pyr[s];
+    P.x_vec2[s] = (W % 2 == 0) && aligned(x_pyr[s], 8);
     if (d->mask_mode == VSL_MASK_EXP) {
       VSL_REQUIRE(logits_pyr[s] && g_logits_pyr[s], VSL_E_NULL);
       VSL_REQUIRE(aligned(logits_pyr[s], 8) && aligned(g_logits_pyr[s], 8), VSL_E_ALIGN);

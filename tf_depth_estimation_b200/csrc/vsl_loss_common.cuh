@@ -53,6 +53,7 @@ struct LossParams {
   int item_begin[VSL_MAX_SCALES + 1];
   int strips[VSL_MAX_SCALES], bands[VSL_MAX_SCALES];
   int lg_vec4[VSL_MAX_SCALES];     // logits / g_logits of this scale are 16-byte aligned (and V is even)
+  int x_vec2[VSL_MAX_SCALES];      // x of this scale is 8-byte aligned and its width even: the tile fill moves pairs
   float wstep[VSL_MAX_SCALES], hstep[VSL_MAX_SCALES];  // meshgrid linspace steps 2/(W-1), 2/(H-1) in fp32
   // per-scale constants precomputed on the host: under register pressure the compiler re-derives loop invariants
   // inside the row loop, and re-loading one word from the constant bank is all that should cost

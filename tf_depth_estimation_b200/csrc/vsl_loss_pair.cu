@@ -113,17 +113,36 @@ loss_fused_pair_kernel(const LossParams P) {
   // ---- 1. the x tile (+halo), zero outside the image (identical to loss_fused_kernel)
   const float* __restrict__ xs = P.x[s] + pix0;
   {
-    int ty = 0, tc = lane;
     const unsigned qt_s = (unsigned)__cvta_generic_to_shared(qt);
+    if (P.x_vec2[s] != 0) {
+      // 8-byte pieces: the tile starts 2 columns left of a multiple of 32 and the level's width is even, so a pair
+      // (2 p, 2 p + 1) of tile columns is 8-byte aligned and lies inside or outside the image as a whole
+      constexpr int kPairs = kQS / 2;
+      int ty = 0, tp = lane;
+      while (tp >= kPairs) { tp -= kPairs; ++ty; }
 #pragma unroll 4
-    for (int i = lane; i < kQH * kQS; i += 32) {
-      const int gy = y_base - kHalo + ty, gx = x_base - kHalo + tc;
-      const bool in = (unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W;
-      const float* src = xs + (in ? gy * W + gx : 0);
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(qt_s + 4u * i), "l"(src), "r"(in ? 4 : 0)
-                   : "memory");
-      tc += 32;
-      if (tc >= kQS) { tc -= kQS; ++ty; }
+      for (int i = lane; i < kQH * kPairs; i += 32) {
+        const int gy = y_base - kHalo + ty, gx = x_base - kHalo + 2 * tp;
+        const bool in = (unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W;
+        const float* src = xs + (in ? gy * W + gx : 0);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(qt_s + 8u * i), "l"(src), "r"(in ? 8 : 0)
+                     : "memory");
+        tp += 32 - kPairs;                       // 32 pairs on: one row further (18 pairs) and 14 more
+        ++ty;
+        if (tp >= kPairs) { tp -= kPairs; ++ty; }
+      }
+    } else {
+      int ty = 0, tc = lane;
+#pragma unroll 4
+      for (int i = lane; i < kQH * kQS; i += 32) {
+        const int gy = y_base - kHalo + ty, gx = x_base - kHalo + tc;
+        const bool in = (unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W;
+        const float* src = xs + (in ? gy * W + gx : 0);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(qt_s + 4u * i), "l"(src), "r"(in ? 4 : 0)
+                     : "memory");
+        tc += 32;
+        if (tc >= kQS) { tc -= kQS; ++ty; }
+      }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     // the grid row coordinates of the tile (fp32 linspace formula of utils.py:153-159), one per lane
@@ -493,7 +512,10 @@ loss_fused_pair_kernel(const LossParams P) {
   }
 
   // ---- 4. one warp reduction per tile (same slots as loss_fused_kernel)
-  const float gx_end = grid_coord(min(x_base + lane, W - 1), W, P.wstep[s]);   // recomputed: not worth a register in the loop
+  // recomputed: not worth a register in the loop.  (The compiler keeps min(x, W - 1) on the stack across the row loop
+  // for this -- 4 bytes, reloaded here once per tile, ~3 % of the kernel in the r6 capture.  Rebuilding the column from
+  // the running pixel offset instead frees that slot and ptxas then spills a value INSIDE the loop: measured 2 us slower.)
+  const float gx_end = grid_coord(min(x_base + lane, W - 1), W, P.wstep[s]);
   float vals[N];
   float pix_sum = 0.f, exp_sum = 0.f;
   pix_sum = lo(pix2) + hi(pix2);
