@@ -47,13 +47,13 @@ METRIC = 'view-synthesis loss fwd+bwd throughput (pixel-views/s)'
 UNIT = 'Mpix/s'
 DEMON = dict(pose_format='angleaxis', smooth_on_inverse=True, depth_is_inverse=True, pixel_scale_norm=False)
 CONFIGS = {
-    'cfg2': dict(B=32, H=128, W=416, S=4, V=2, flags={}, sets=6, cpu_B=8, scaling='weak',
+    'cfg2': dict(B=32, H=128, W=416, S=4, V=2, flags={}, sets=6, cpu_B=32, scaling='weak',
                  text='cfg2: view-synthesis loss fwd+bwd (pyramids + fused multi-scale loss), per GPU B=32 128x416 4 '
                       'scales 2 source views, explainability mask, euler poses'),
-    'cfg3': dict(B=256, H=128, W=416, S=4, V=2, flags={}, sets=3, cpu_B=8, scaling='strong',
+    'cfg3': dict(B=256, H=128, W=416, S=4, V=2, flags={}, sets=3, cpu_B=32, scaling='strong',
                  text='cfg3: the loss step of train.py at global batch 256 (split over the ranks), 128x416 4 scales 2 '
                       'source views, explainability mask, euler poses'),
-    'cfg4': dict(B=64, H=192, W=256, S=4, V=1, flags=DEMON, sets=4, cpu_B=8, scaling='weak',
+    'cfg4': dict(B=64, H=192, W=256, S=4, V=1, flags=DEMON, sets=4, cpu_B=64, scaling='weak',
                  text='cfg4: DeMoN pairs 192x256, per GPU B=64, one source view per direction, angle-axis poses, '
                       'smoothness on 1/depth, explainability mask'),
     'cfg5': dict(B=64, H=480, W=640, S=4, V=2, flags={}, sets=2, cpu_B=1, scaling='weak',
@@ -184,7 +184,8 @@ def cpu_baseline(c, reps, budget_s=25.0):
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path.  TensorFlow 1.x cannot run here, so
     this is the oracle port (an op-for-op restatement validated against the reference's own source, see
-    oracle/); each step is a bounded sample (cpu_B snippets of the batch)."""
+    oracle/); each step is cpu_B snippets of the batch: the whole per-GPU batch at cfg2 / cfg4 (0.3-1 s per step on
+    the host cores), a bounded sample at cfg3 / cfg5."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
@@ -205,7 +206,8 @@ def run_reference(args):
         'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': c['scaling'],
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': dict(workload=c['text'] + ' (each reference step = B=%d sample of it)' % Bs,
+        'config': dict(workload=c['text'] + (' (each reference step = the whole per-GPU batch)' if Bs == c['B'] else
+                                             ' (each reference step = B=%d sample of it)' % Bs),
                        B=c['B'], H=c['H'], W=c['W'], S=c['S'], V=c['V']),
         'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                          'sample': 'B=%d snippets per step, torch-CPU oracle, all host threads' % Bs},
