@@ -184,6 +184,14 @@ typedef struct {
                             projected depth of the warp (utils_lr.py:172-194), the source depth map fetched by
                             consistent_depth_loss (utils_lr.py:369-458).  Needs exact_coords != 1, no want_src_grad,
                             no x_is_logit */
+  float ssim_weight;     /* EXTENSION (SSIM is absent from the reference; BASELINE.json's north_star names it): a in
+                            (0, 1] turns the photometric term of every scale and view into data_weight_s * [(1 - a) *
+                            mean(|warp - tgt| * m) + a * mean_{B,H-2,W-2,3}(D * m_centre)], D = clip((1 - SSIM_3x3(warp,
+                            tgt)) / 2, 0, 1) over VALID 3 x 3 windows (C1 = 0.01^2, C2 = 0.03^2), m the mask at the
+                            window's centre: one more launch between the fused kernel and the finalize (loss_ssim_kernel:
+                            warped + target tiles with their halo in shared memory, value and gradient, no
+                            full-resolution intermediate).  Needs exact_coords != 1, no want_src_grad, no x_is_logit,
+                            no consist_weight.  0 = off */
   void* ev_main_begin;   /* optional cudaEvent_t pair recorded on `stream` immediately around the fused  */
   void* ev_main_end;     /* loss kernel (launch 3 of the step) so a caller can time it in situ; NULL = off */
 } VslLossDesc;

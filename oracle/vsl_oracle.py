@@ -337,6 +337,9 @@ class LossFlags(object):
         self.depth_is_inverse = True        # warp depth = 1/x (train.py:128) vs x
         self.smooth_on_inverse = False      # smooth(1/x) (train_depth_then_cam_lr.py:217) vs smooth(x) (train.py:108)
         self.consist_weight = 0.0           # FLAGS.depth_weight on the consistency term (train_depth_then_cam_lr.py:339-340)
+        # EXTENSION, not in the reference ("parity unpinned -- no reference implementation"): a in (0, 1] mixes
+        # the 3x3 SSIM dissimilarity into the photometric term: dw * [(1 - a) mean(|e| m) + a mean(D m_centre)]
+        self.ssim_weight = 0.0
         self.__dict__.update(kw)
 
 
@@ -383,7 +386,16 @@ def view_synthesis_loss(tgt, srcs, x_pyr, poses, K_pyr, logits_pyr=None, mask_py
                 err = err * mask_pyr[s]
                 if cerr is not None:
                     cerr = cerr * mask_pyr[s]
-            pixel = pixel + err.mean() * dw
+            a = float(getattr(f, 'ssim_weight', 0.0))
+            if a > 0.0:
+                D = ssim_dissimilarity(warped, tgt_s)                       # [B,hs-2,ws-2,3], VALID windows
+                if logits_pyr is not None:
+                    D = D * torch.softmax(lg, dim=-1)[:, 1:-1, 1:-1, 1:2]   # the mask at the window's centre
+                elif mask_pyr is not None:
+                    D = D * mask_pyr[s][:, 1:-1, 1:-1]
+                pixel = pixel + ((1.0 - a) * err.mean() + a * D.mean()) * dw
+            else:
+                pixel = pixel + err.mean() * dw
             if cerr is not None:
                 consist = cerr.mean() * f.consist_weight + (consist if consist is not None else 0.0)
     if src_x_pyr is not None:

@@ -29,7 +29,7 @@ class VslLossDesc(ctypes.Structure):
                 ('explain_reg_weight', ctypes.c_float), ('loss_scale', ctypes.c_float),
                 ('exact_coords', ctypes.c_int), ('want_src_grad', ctypes.c_int),
                 ('x_is_logit', ctypes.c_int), ('disp_scale', ctypes.c_float), ('disp_min', ctypes.c_float),
-                ('img_format', ctypes.c_int), ('consist_weight', ctypes.c_float),
+                ('img_format', ctypes.c_int), ('consist_weight', ctypes.c_float), ('ssim_weight', ctypes.c_float),
                 ('ev_main_begin', ctypes.c_void_p), ('ev_main_end', ctypes.c_void_p)]
 
 

@@ -1619,6 +1619,9 @@ int check_desc(const VslLossDesc* d) {
   // the consistency term rides on the fast arithmetic of the float32 entry
   VSL_REQUIRE(!(d->consist_weight > 0.f) || (d->exact_coords != 1 && !d->want_src_grad && !d->x_is_logit &&
                                              d->img_format == VSL_IMG_F32), VSL_E_UNSUPPORTED);
+  VSL_REQUIRE(d->ssim_weight >= 0.f && d->ssim_weight <= 1.f, VSL_E_UNSUPPORTED);
+  VSL_REQUIRE(!(d->ssim_weight > 0.f) || (d->exact_coords != 1 && !d->want_src_grad && !d->x_is_logit &&
+                                          !(d->consist_weight > 0.f)), VSL_E_UNSUPPORTED);
   return VSL_OK;
 }
 
@@ -1705,6 +1708,10 @@ int run_loss(const VslLossDesc* d, LossParams& P, const float* poses, const floa
 #endif
   if (rc != VSL_OK) return rc;
   if (d->ev_main_end != nullptr) cudaEventRecord((cudaEvent_t)d->ev_main_end, st);
+  if (d->ssim_weight > 0.f) {   // extension: the SSIM share of the photometric term, added to the same outputs
+    const int rs = launch_ssim_term(d, P, st);
+    if (rs != VSL_OK) return rs;
+  }
   {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(d->B + 1);
@@ -1888,7 +1895,7 @@ int loss_fwd_bwd(const VslLossDesc* d, const void* tgt, const void* const* srcs,
     P.hstep[s] = 2.0f / (float)(H - 1);
     const double npx = (double)d->B * H * W;
     const double dw = d->pixel_scale_norm ? (double)d->data_weight / (double)(1 << s) : (double)d->data_weight;
-    P.cpix[s] = (float)((double)d->loss_scale * dw / (npx * 3.0));
+    P.cpix[s] = (float)((double)d->loss_scale * dw * (1.0 - (double)d->ssim_weight) / (npx * 3.0));   // the L1 share
     P.cexp[s] = (float)((double)d->loss_scale * (double)d->explain_reg_weight / npx);
     P.ccon[s] = (float)((double)d->loss_scale * (double)d->consist_weight / npx);
     const double sw = (double)d->loss_scale * (double)d->smooth_weight / (double)(1 << s);

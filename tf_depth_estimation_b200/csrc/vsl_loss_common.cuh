@@ -147,5 +147,7 @@ VSL_DEV void owner_signs(const float* q, unsigned gx, unsigned gy, int H, int W,
 
 // The view-paired kernel lives in its own translation unit (vsl_loss_pair.cu); V must be even.
 int launch_fused_pair(int V, const LossParams& P, cudaStream_t st);
+// The SSIM part of the photometric term (vsl_loss_ssim.cu): runs after the fused kernel, before the finalize.
+int launch_ssim_term(const VslLossDesc* d, const LossParams& P, cudaStream_t st);
 
 }  // namespace vsl

@@ -632,6 +632,9 @@ class LossFlags(object):
         # > 0: the left-right depth-consistency term of train_depth_then_cam_lr.py:336-340 (its FLAGS.depth_weight)
         # inside the fused step; view_synthesis_loss then takes the source views' own network outputs (src_x_pyr)
         self.consist_weight = 0.0
+        # EXTENSION (not in the reference): a in (0, 1] mixes a 3x3 SSIM dissimilarity into the photometric term of the
+        # fused step, data_weight_s * [(1 - a) * mean(|e| m) + a * mean(D m_centre)] (VslLossDesc.ssim_weight)
+        self.ssim_weight = 0.0
         self.__dict__.update(kw)
 
 
@@ -766,7 +769,8 @@ class ViewSynthesisPlan(object):
                                 float(flags.explain_reg_weight), float(loss_scale),
                                 int(getattr(flags, 'exact_coords', False)), int(self.want_src_grad),
                                 int(getattr(flags, 'x_is_logit', False)), float(getattr(flags, 'disp_scaling', 4.0)),
-                                float(getattr(flags, 'min_disp', 0.0)), self.img_format, self.consist_weight, None, None)
+                                float(getattr(flags, 'min_disp', 0.0)), self.img_format, self.consist_weight,
+                                float(getattr(flags, 'ssim_weight', 0.0)), None, None)
         nbytes = lib.vsl_loss_ws_bytes(self.desc)
         if nbytes == 0:
             raise ValueError('unsupported loss shape B=%d H=%d W=%d S=%d V=%d' % (B, H, W, S, V))
