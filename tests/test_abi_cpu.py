@@ -61,7 +61,28 @@ def test_loss_descriptor_validation_and_workspace(lib):
     assert lib.vsl_loss_ws_bytes(ctypes.byref(bad)) == 0
     bad = _lib.VslLossDesc(32, 128, 416, 4, 5, 0, 1, 1, 1, 0, 1.0, 0.5, 0.2, 1.0)   # V > VSL_MAX_VIEWS
     assert lib.vsl_loss_ws_bytes(ctypes.byref(bad)) == 0
-    assert ctypes.sizeof(_lib.VslLossDesc) == 21 * 4 + 4 + 2 * 8   # 21 scalars, padding, 2 event handles
+    assert ctypes.sizeof(_lib.VslLossDesc) == 22 * 4 + 2 * 8   # 22 scalars (ssim_weight is the last), 2 event handles
+    ssim = _lib.VslLossDesc(32, 128, 416, 4, 2, 0, 1, 1, 1, 0, 1.0, 0.5, 0.2, 1.0, exact_coords=1, ssim_weight=0.5)
+    assert lib.vsl_loss_ws_bytes(ctypes.byref(ssim)) == 0                         # the SSIM term rides on the fast arithmetic
+    ssim = _lib.VslLossDesc(32, 128, 416, 4, 2, 0, 1, 1, 1, 0, 1.0, 0.5, 0.2, 1.0, ssim_weight=1.5)
+    assert lib.vsl_loss_ws_bytes(ctypes.byref(ssim)) == 0                         # a weight outside [0, 1]
+
+
+def test_flow_step_and_loader_entries_without_a_device(lib):
+    d = _lib.VslFlowLossDesc(B=64, H=192, W=256, S=4, smooth_weight=0.5, depth_weight=1.0, data_weight=1.0,
+                             optflow_weight=1.0, loss_scale=1.0)
+    n = lib.vsl_flow_loss_ws_bytes(ctypes.byref(d))
+    levels = 64 * 192 * 256 * 7 * 4 * (1 / 4 + 1 / 16 + 1 / 64)       # left + right (RGB) + label pyramids, levels 1..3
+    assert levels < n < levels * 1.05
+    for bad in (dict(H=100), dict(S=7), dict(B=0), dict(H=16, W=16)):     # 100 % 8, too many scales, empty, 2 x 2 coarsest level
+        kw = dict(B=64, H=192, W=256, S=4, smooth_weight=0.5, depth_weight=1.0, data_weight=1.0, optflow_weight=1.0, loss_scale=1.0)
+        kw.update(bad)
+        assert lib.vsl_flow_loss_ws_bytes(ctypes.byref(_lib.VslFlowLossDesc(**kw))) == 0, bad
+    P = _lib.ptr_array([16, 16, 16, 16])
+    assert lib.vsl_flow_loss_fwd_bwd(ctypes.byref(d), None, 16, 16, P, P, P, 16, 16, 16, P, P, P, 256, None) == -1   # NULL image
+    assert lib.vsl_flow_loss_fwd_bwd(ctypes.byref(d), 16, 16, 16, P, P, P, 16, 16, 16, P, P, P, 260, None) == -4    # ws alignment
+    assert lib.vsl_unpack_strip(None, 1, 8, 16, 8, 8, 16, 16, None) == -1
+    assert lib.vsl_unpack_strip(16, 1, 8, 1, 8, 8, 16, 16, None) == -2                                             # a strip one pixel wide
 
 
 def test_host_side_rejects_cpu_tensors_and_bad_shapes(lib):
