@@ -25,6 +25,8 @@ JSON keys beyond the base contract:
                 all inside the timed region; copies and kernels of neighbouring steps overlap (3 streams, 2 slots).
   flow          (--config cfg4 only) the DeMoN-pair family's own loss loop (train_optflow_combine.py:138-240) as the
                 fused flow-and-depth step vsl_flow_loss_fwd_bwd: device-resident step time, per rank.
+  other_configs (default config, one GPU) the same device-resident step at the other BASELINE shapes -- cfg3 (B=256 on this
+                GPU), cfg4, cfg5 -- each with its step time, throughput and the fused kernel's in-situ roofline fraction.
   train         (default config only) BASELINE's second metric, end-to-end training samples/s at N GPUs:
                 configs[2] (DispNet + PoseExpNet, global batch 256 split over the ranks) with this repository's
                 fused loss and its fused reduce-scatter + Adam + all-gather optimiser step over NVLink peer memory
@@ -244,6 +246,57 @@ def flow_leg(dev, steps):
         return {'error': '%s: %s' % (type(e).__name__, e)}
 
 
+def quick_config(name, dev, rank, steps=40, warmup=5):
+    """One more BASELINE shape through the same device-resident step (rotating input sets, in-situ kernel events on
+    every 4th step): the short form of the main measurement, for the `other_configs` object of the default line."""
+    import torch
+    from tf_depth_estimation_b200 import _lib, ops, synth
+    try:
+        c = CONFIGS[name]
+        B, H, W, S, V = (c[k] for k in 'BHWSV')
+        flags = ops.LossFlags(num_scales=S, **c['flags'])
+        plan = ops.ViewSynthesisPlan(B, H, W, V, flags, _lib.MASK_EXP, dev)
+        host = synth.make_snippets(min(B, 16), H, W, S=S, V=V, seed=4321 + rank)
+        rep = lambda t, k: torch.roll(t.repeat((B + t.shape[0] - 1) // t.shape[0], *([1] * (t.dim() - 1)))[:B], k, 0).to(dev).contiguous()
+        bound = []
+        for k in range(c['sets']):
+            bound.append(plan.bind(rep(host['tgt'], k), [rep(x, k) for x in host['srcs']], [rep(x, k) for x in host['disp_pyr']],
+                                   rep(host['poses'], k), rep(host['K_pyr'], k), [rep(x, k) for x in host['logits_pyr']]))
+        stream = torch.cuda.current_stream().cuda_stream
+        timed = list(range(0, steps, 4))
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in timed]
+        for a, b in ev:
+            a.record(); b.record()
+        torch.cuda.synchronize()
+        for i in range(warmup):
+            plan.run_bound(bound[i % len(bound)], stream)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            if i % 4 == 0:
+                plan.set_profile_events(ev[i // 4][0].cuda_event, ev[i // 4][1].cuda_event)
+            else:
+                plan.set_profile_events(None, None)
+            plan.run_bound(bound[(warmup + i) % len(bound)], stream)
+        e1.record()
+        torch.cuda.synchronize()
+        plan.set_profile_events(None, None)
+        ms = e0.elapsed_time(e1) / steps
+        kms = statistics.mean(a.elapsed_time(b) for a, b in ev)
+        peak, _ = measured_peak()
+        algo = fused_kernel_bytes(c, B)
+        out = {'workload': c['text'], 'B': B, 'H': H, 'W': W, 'S': S, 'V': V, 'steps': steps, 'ms_per_step': ms,
+               'value': pixel_views(c, B) / (ms * 1e-3) / 1e6, 'unit': UNIT, 'kernel_ms_mean': kms,
+               'algorithmic_bytes_per_launch': algo, 'roofline_frac': algo / (kms * 1e-3) / 1e9 / peak,
+               'losses_finite': bool(torch.isfinite(plan.losses).all())}
+        del plan, bound
+        torch.cuda.empty_cache()
+        return out
+    except Exception as e:   # noqa: BLE001
+        return {'error': '%s: %s' % (type(e).__name__, e)}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -388,6 +441,12 @@ def run_ours(args):
         train = train_leg(rank, world, dev)
 
     flow = flow_leg(dev, K) if args.config == 'cfg4' else None
+    others = None
+    if args.config == 'cfg2' and world == 1 and not args.no_other_configs:
+        # the other BASELINE shapes on this GPU: cfg3 = configs[2]'s loss step at its global batch 256 (the same frame
+        # size in 8 waves instead of one), cfg4 = configs[3], cfg5 = configs[4] (the HBM-stress shape)
+        others = {n: quick_config(n, dev, rank) for n in ('cfg3', 'cfg4', 'cfg5')}
+        others['cfg4_flow'] = flow_leg(dev, 60)      # configs[3]'s own loss loop as the fused flow-and-depth step
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -424,6 +483,8 @@ def run_ours(args):
             out['train'] = train
         if flow is not None:
             out['flow'] = flow
+        if others is not None:
+            out['other_configs'] = others
         if world == 1 and not args.no_cpu_baseline:
             out['cpu_baseline'] = cpu_baseline(c, reps=12)
         args.out.emit(json.dumps(out))
@@ -456,6 +517,7 @@ def main():
     ap.add_argument('--config', default='cfg2', choices=sorted(CONFIGS))
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-train', action='store_true')
+    ap.add_argument('--no-other-configs', action='store_true')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     args.out = _QuietStdout()
