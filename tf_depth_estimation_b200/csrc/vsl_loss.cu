@@ -1438,11 +1438,20 @@ VSL_DEV void prep_patch(const PrepSink<TGT, WCH> out, const float (&a)[4][12], i
 // Warps stride over the patches.  A patch's 6 KB travel global -> shared memory as 16-byte cp.async, lane = chunk
 // (fully coalesced, nothing held in registers on the way), into a two-stage buffer the warp owns: the next patch is in
 // flight while this one is turned into its levels, so a warp's loads never wait for its arithmetic and stores.
-template <int LOG2F>
+// U8: the images arrive as the loader's uint8 (imageselect_Dataloader.py:86-93).  A patch is then 16 rows x 96 BYTES
+// (six 16-byte chunks per row, the first quarter of a stage), every lane turns its 4 x 4 pixels into float32 through a
+// 256-entry table of (float)u / img_div - img_sub (the reference's own IEEE division, computed once per block), and the
+// target's level 0 leaves as float32 too (the fused kernel reads it as such); everything after that is the float32 path.
+template <int LOG2F, bool U8 = false>
 __global__ void __launch_bounds__(kPrepRegThreads, kPrepRegBlocks)
 loss_prep_reg_kernel(const PrepImgJob job, const PrepJob prep) {
   static_assert(LOG2F <= 4, "levels above 4 chain across more lane rows than a warp has");
   extern __shared__ float4 smem4[];               // [warps][2 stages][16 rows][24 float4]
+  __shared__ float lut[U8 ? 256 : 1];
+  if (U8) {
+    for (int i = threadIdx.x; i < 256; i += kPrepRegThreads) lut[i] = __fsub_rn(__fdiv_rn((float)i, job.img_div), job.img_sub);
+    __syncthreads();
+  }
   asm volatile("griddepcontrol.wait;" ::: "memory");
   prep_borders_and_table(job, prep);
 
@@ -1469,10 +1478,24 @@ loss_prep_reg_kernel(const PrepImgJob job, const PrepJob prep) {
     return q;
   };
   auto issue = [&](const Patch& q, int stage) {
+    const unsigned dst = stage0_s + (unsigned)(stage * kPatchF4 * 16);
+    if (U8) {
+      const unsigned char* __restrict__ img = reinterpret_cast<const unsigned char*>(q.im == 0 ? job.tgt : job.src[q.im > 0 ? q.im - 1 : 0]);
+      const unsigned char* __restrict__ g = img + (((size_t)q.b * H + q.y0) * W + q.x0) * 3;
+      const int rows = min(16, H - q.y0), row_c = min(32, W - q.x0) * 3 / 16;     // 16-byte chunks per row (W % 16 == 0)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {                 // 16 rows x 6 chunks = 96
+        const int c = lane + 32 * k, r = c / 6, cc = c - r * 6;
+        if (r < rows && cc < row_c)
+          asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst + (unsigned)c * 16u),
+                       "l"(g + (size_t)r * W * 3 + cc * 16), "l"(pol) : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      return;
+    }
     const float* __restrict__ img = reinterpret_cast<const float*>(q.im == 0 ? job.tgt : job.src[q.im > 0 ? q.im - 1 : 0]);
     const float* __restrict__ g = img + (((size_t)q.b * H + q.y0) * W + q.x0) * 3;
     const int rows = min(16, H - q.y0), row_f4 = min(32, W - q.x0) * 3 / 4;       // 16-byte chunks per row
-    const unsigned dst = stage0_s + (unsigned)(stage * kPatchF4 * 16);
 #pragma unroll
     for (int k = 0; k < kPatchF4 / 32; ++k) {
       const int c = lane + 32 * k, r = c / 24, cc = c - r * 24;
@@ -1501,7 +1524,29 @@ loss_prep_reg_kernel(const PrepImgJob job, const PrepJob prep) {
     const int x = cur.x0 + lx * 4, y = cur.y0 + ly * 4;
     const bool in_x = x < W;                      // a thread's 4 columns are inside or outside together (W % 4 == 0)
     float a[4][12];                               // [row][pixel * 3 + channel]
-    {
+    if (U8) {
+      // a staged row is 96 bytes; this lane's 4 pixels are 12 of them = three 32-bit words
+      const unsigned* t = reinterpret_cast<const unsigned*>(stage0 + (it & 1) * kPatchF4) + (ly * 4) * 24 + lx * 3;
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const unsigned w = t[r * 24 + k];
+          a[r][4 * k] = lut[w & 255u]; a[r][4 * k + 1] = lut[(w >> 8) & 255u];
+          a[r][4 * k + 2] = lut[(w >> 16) & 255u]; a[r][4 * k + 3] = lut[w >> 24];
+        }
+      if (cur.im == 0 && in_x) {                  // the float32 target the fused kernel reads: 48 contiguous bytes per row
+        float* d0 = job.tgt_lvl[0] + (((size_t)cur.b * H + y) * W + x) * 3;
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+          if (y + r < H) {
+            float4* d = reinterpret_cast<float4*>(d0 + (size_t)r * W * 3);
+            d[0] = make_float4(a[r][0], a[r][1], a[r][2], a[r][3]);
+            d[1] = make_float4(a[r][4], a[r][5], a[r][6], a[r][7]);
+            d[2] = make_float4(a[r][8], a[r][9], a[r][10], a[r][11]);
+          }
+      }
+    } else {
       const float4* t = stage0 + (it & 1) * kPatchF4 + (ly * 4) * 24 + lx * 3;
 #pragma unroll
       for (int r = 0; r < 4; ++r)
@@ -1740,8 +1785,9 @@ int launch_prep(const PrepImgJob& job, const PrepJob& prep, bool u8, cudaStream_
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   cudaError_t e = cudaSuccess;
-  // float32 images whose rows are 16-byte aligned take the register form (no shared memory, a warp per 32 x 16 patch)
-  bool reg_form = !u8 && job.W % 4 == 0 && job.S <= 5 && aligned(job.tgt, 16);
+  // images whose rows are 16-byte aligned take the register form (a warp per 32 x 16 patch): float32 needs W % 4 == 0,
+  // the loader's uint8 W % 16 == 0 (a patch row is 96 bytes = six 16-byte chunks)
+  bool reg_form = job.W % (u8 ? 16 : 4) == 0 && job.S <= 5 && aligned(job.tgt, 16);
   for (int v = 0; v < job.V; ++v) reg_form = reg_form && aligned(job.src[v], 16);
 #ifdef VSL_PREP_STAGED
   reg_form = false;
@@ -1757,12 +1803,22 @@ int launch_prep(const PrepImgJob& job, const PrepJob& prep, bool u8, cudaStream_
       cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPrepRegSmem);
       return e2 != cudaSuccess ? e2 : cudaLaunchKernelEx(&cfg, kern, job, prep);
     };
-    switch (job.S) {
-      case 1: e = go(loss_prep_reg_kernel<0>); break;
-      case 2: e = go(loss_prep_reg_kernel<1>); break;
-      case 3: e = go(loss_prep_reg_kernel<2>); break;
-      case 4: e = go(loss_prep_reg_kernel<3>); break;
-      default: e = go(loss_prep_reg_kernel<4>); break;
+    if (u8) {
+      switch (job.S) {
+        case 1: e = go(loss_prep_reg_kernel<0, true>); break;
+        case 2: e = go(loss_prep_reg_kernel<1, true>); break;
+        case 3: e = go(loss_prep_reg_kernel<2, true>); break;
+        case 4: e = go(loss_prep_reg_kernel<3, true>); break;
+        default: e = go(loss_prep_reg_kernel<4, true>); break;
+      }
+    } else {
+      switch (job.S) {
+        case 1: e = go(loss_prep_reg_kernel<0>); break;
+        case 2: e = go(loss_prep_reg_kernel<1>); break;
+        case 3: e = go(loss_prep_reg_kernel<2>); break;
+        case 4: e = go(loss_prep_reg_kernel<3>); break;
+        default: e = go(loss_prep_reg_kernel<4>); break;
+      }
     }
   } else if (u8) {
     switch (job.S) {
