@@ -219,13 +219,21 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------ GPU arm
 def train_leg(rank, world, dev):
-    """BASELINE's second metric through profiles/train_samples.py; never lets a failure take the bench line down."""
+    """BASELINE's second metric through profiles/train_samples.py; never lets a failure take the bench line down.
+    Strong scaling as configs[2] words it (global batch 256 split over the ranks) and, beside it, the weak-scaling
+    reading (32 snippets per GPU at every N, i.e. the per-GPU work of the 8-GPU run of configs[2])."""
     try:
         spec = importlib.util.spec_from_file_location('train_samples', os.path.join(ROOT, 'profiles', 'train_samples.py'))
         mod = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(mod)
         r = mod.measure(rank, world, dev, global_batch=256, steps=6, warmup=3, optim='peer', graph=1, timeout_s=30.0)
-        return {'samples_per_s': r['value'], 'ms_per_step': r['ms_per_step'], 'optim_us': r['optim_us'], 'loss_us': r['loss_us'],
+        if 32 * world == 256:
+            w = r
+        else:
+            w = mod.measure(rank, world, dev, global_batch=32 * world, steps=10, warmup=3, optim='peer', graph=1, timeout_s=30.0)
+        weak = {'samples_per_s': w['value'], 'ms_per_step': w['ms_per_step'], 'global_batch': w['global_batch'],
+                'per_gpu_batch': w['per_gpu_batch'], 'scaling': 'weak', 'optim_us': w['optim_us'], 'loss_us': w['loss_us']}
+        return {'weak': weak, 'samples_per_s': r['value'], 'ms_per_step': r['ms_per_step'], 'optim_us': r['optim_us'], 'loss_us': r['loss_us'],
                 'global_batch': r['global_batch'], 'per_gpu_batch': r['per_gpu_batch'], 'scaling': 'strong',
                 'optimiser': 'fused reduce-scatter + Adam + all-gather over NVLink peer memory (dp_adam_kernel)',
                 'cuda_graph': r['cuda_graph'], 'params': r['params'], 'losses_finite': r['losses_finite'],
