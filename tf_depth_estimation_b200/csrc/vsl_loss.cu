@@ -109,7 +109,8 @@ VSL_DEV void tap_issue(Tap& t, const float (&p)[12], float c0, float c1, float c
 template <int V, bool EXACT, bool DSRC, bool CONS = false>
 // the exact mode (IEEE divisions, expf / logf, unfused sequences) needs ~170 registers: one block less per SM
 // beats spilling
-__global__ void __launch_bounds__(kThreads, (V <= 2 ? (EXACT || CONS ? VSL_FUSED_MIN_BLOCKS - 1 : VSL_FUSED_MIN_BLOCKS)
+__global__ void __launch_bounds__(kThreads, (V == 1 && !EXACT && !CONS && !DSRC ? VSL_V1_MIN_BLOCKS
+                                           : V <= 2 ? (EXACT || CONS ? VSL_FUSED_MIN_BLOCKS - 1 : VSL_FUSED_MIN_BLOCKS)
                                                       : VSL_FUSED_MIN_BLOCKS / 2))
 loss_fused_kernel(const LossParams P) {
   static_assert(!CONS || (!EXACT && !DSRC), "the consistency term rides on the fast arithmetic");

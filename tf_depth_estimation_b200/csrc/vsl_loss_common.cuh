@@ -16,6 +16,11 @@ namespace vsl {
 #define VSL_FUSED_MIN_BLOCKS 4
 #endif
 
+// one source view in the fast arithmetic needs 96 registers: a fifth block per SM (20 warps) without a spill
+#ifndef VSL_V1_MIN_BLOCKS
+#define VSL_V1_MIN_BLOCKS VSL_FUSED_MIN_BLOCKS
+#endif
+
 constexpr int kRH = VSL_RH;                     // tile rows per warp
 constexpr int kWarps = VSL_FUSED_WARPS;         // independent warps per block
 constexpr int kThreads = 32 * kWarps;
