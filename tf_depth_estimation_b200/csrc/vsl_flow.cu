@@ -9,10 +9,10 @@
 //
 //   launch 1-2  resize_area pyramids of left / right (RGB) and of the label (1 channel), bit-exact (vsl_pyramid.cuh);
 //               the transform table (K_s^-1, K4_s . T) rides on the first.
-//   launch 3    flow_loss_kernel: one block per 32 x 8 tile of one image at one scale, tiles of every scale in one
-//               grid.  The three predicted maps enter shared memory once with a 2-pixel halo: the smoothness value
+//   launch 3    flow_loss_kernel: one block per 32 x 32 tile of one image at one scale (a warp walks four consecutive
+//               rows), tiles of every scale in one grid.  The three predicted maps enter shared memory once with a 2-pixel halo: the smoothness value
 //               (each second difference owned by its top-left element) and its gradient (gather form: the signs of
-//               the ten stencils an element is part of) come from there.  Each thread then does its pixel: the
+//               the ten stencils an element is part of) come from there.  Each thread then does its pixels: the
 //               ground-truth projection (mask + flow target, no gather), the two gathers with the reference's
 //               zero-padding masks, the four absolute errors and every gradient; nothing full-resolution is written
 //               but the three gradient maps.  Coordinates follow the reference's rounding sequence
@@ -27,8 +27,10 @@
 
 namespace vsl {
 
-constexpr int kFlowTW = 32, kFlowTH = 8, kFlowHalo = 2;
-constexpr int kFlowSW = kFlowTW + 2 * kFlowHalo, kFlowSH = kFlowTH + 2 * kFlowHalo;   // 36 x 12 per map
+constexpr int kFlowTW = 32, kFlowTH = 32, kFlowHalo = 2;
+constexpr int kFlowWarps = 8, kFlowRows = kFlowTH / kFlowWarps;    // a warp owns kFlowRows consecutive rows of the tile
+constexpr int kFlowThreads = 32 * kFlowWarps;
+constexpr int kFlowSW = kFlowTW + 2 * kFlowHalo, kFlowSH = kFlowTH + 2 * kFlowHalo;   // 36 x 36 per map
 constexpr int kFlowTerms = 4;   // depth, smooth, optflow, pixel (the order the script prints them, :240)
 
 struct FlowParams {
@@ -64,18 +66,30 @@ struct SmoothW {
   float oxx, oyy, oxy;   // the plain coefficients of the differences (i, j) owns, for the loss value
 };
 
-VSL_DEV SmoothW smooth_weights(int i, int j, int H, int W, float cxx, float cxy, float cyy) {
+// The weights separate: an xx difference exists or not by the column alone, a yy difference by the row alone, a 2 x 2
+// cell by (row ok) x (column ok).  The column part is fixed for a thread, the row part changes with the tile row.
+struct SmoothCol { float xx[3]; bool ok[2]; };
+VSL_DEV SmoothCol smooth_cols(int j, int W, float cxx) {
+  SmoothCol c;
+  const float st[3] = {1.f, -2.f, 1.f};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) c.xx[k] = (j - k >= 0 && j - k + 2 < W) ? cxx * st[k] : 0.f;
+#pragma unroll
+  for (int dj = 0; dj < 2; ++dj) c.ok[dj] = j - dj >= 0 && j - dj + 1 < W;
+  return c;
+}
+VSL_DEV SmoothW smooth_weights(const SmoothCol& c, int i, int H, float cxy, float cyy) {
   SmoothW w;
   const float st[3] = {1.f, -2.f, 1.f};
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
-    w.xx[k] = (j - k >= 0 && j - k + 2 < W) ? cxx * st[k] : 0.f;
+    w.xx[k] = c.xx[k];
     w.yy[k] = (i - k >= 0 && i - k + 2 < H) ? cyy * st[k] : 0.f;
   }
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int di = k >> 1, dj = k & 1;
-    const bool ok = i - di >= 0 && j - dj >= 0 && i - di + 1 < H && j - dj + 1 < W;
+    const bool ok = i - di >= 0 && i - di + 1 < H && c.ok[dj];
     w.xy[k] = ok ? ((di ^ dj) ? -cxy : cxy) : 0.f;
   }
   w.oxx = fabsf(w.xx[0]); w.oyy = fabsf(w.yy[0]); w.oxy = fabsf(w.xy[0]);
@@ -149,11 +163,14 @@ VSL_DEV float sample_error(const float* __restrict__ img, int H, int W, float x,
   return err;
 }
 
-__global__ void __launch_bounds__(kFlowTW * kFlowTH)
+#ifndef VSL_FLOW_MINB
+#define VSL_FLOW_MINB 3
+#endif
+__global__ void __launch_bounds__(kFlowThreads, VSL_FLOW_MINB)
 flow_loss_kernel(const FlowParams P) {
   __shared__ float tile[3][kFlowSH * kFlowSW];
   __shared__ Xform sx;
-  __shared__ float scratch[kFlowTerms * (kFlowTW * kFlowTH / 32)];
+  __shared__ float scratch[kFlowTerms * kFlowWarps];
   const int item = blockIdx.x;
   int s = 0;
   while (s + 1 < P.S && item >= P.item_begin[s + 1]) ++s;
@@ -168,97 +185,108 @@ flow_loss_kernel(const FlowParams P) {
   if (threadIdx.x < 21)
     reinterpret_cast<float*>(&sx)[threadIdx.x] = reinterpret_cast<const float*>(P.xf + (size_t)s * P.B + b)[threadIdx.x];
   {
-    // 36 x 12 elements per map = 432 = 256 + 176: every thread owns one or two tile slots, shared by the three maps
+    // 36 x 36 elements per map, every slot shared by the three maps; rows of the tile below the image are not loaded
     const float* __restrict__ m0 = P.pd[s] + img0;
     const float* __restrict__ m1 = P.fx[s] + img0;
     const float* __restrict__ m2 = P.fy[s] + img0;
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const int r = threadIdx.x + k * (kFlowTW * kFlowTH);
-      if (r < kFlowSH * kFlowSW) {
-        const int ly = r / kFlowSW, lx = r - ly * kFlowSW;
-        const int gy = y_base - kFlowHalo + ly, gx = x_base - kFlowHalo + lx;
-        const bool in = (unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W;
-        const int o = in ? gy * W + gx : 0;
-        const float a = __ldg(m0 + o), bq = __ldg(m1 + o), c = __ldg(m2 + o);
-        tile[0][r] = in ? a : 0.f;
-        tile[1][r] = in ? bq : 0.f;
-        tile[2][r] = in ? c : 0.f;
-      }
+    const int rows = min(kFlowSH, H - y_base + 2 * kFlowHalo);
+    for (int r = threadIdx.x; r < rows * kFlowSW; r += kFlowThreads) {
+      const int ly = r / kFlowSW, lx = r - ly * kFlowSW;
+      const int gy = y_base - kFlowHalo + ly, gx = x_base - kFlowHalo + lx;
+      const bool in = (unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W;
+      const int o = in ? gy * W + gx : 0;
+      const float a = __ldg(m0 + o), bq = __ldg(m1 + o), c = __ldg(m2 + o);
+      tile[0][r] = in ? a : 0.f;
+      tile[1][r] = in ? bq : 0.f;
+      tile[2][r] = in ? c : 0.f;
     }
   }
   __syncthreads();
 
-  const int lx = threadIdx.x & (kFlowTW - 1), ly = threadIdx.x / kFlowTW;
-  const int i = y_base + ly, j = x_base + lx;
+  const int lx = threadIdx.x & 31, wy = (threadIdx.x >> 5) * kFlowRows;
+  const int j = x_base + lx;
   float acc[kFlowTerms] = {0.f, 0.f, 0.f, 0.f};
-  if (i < H && j < W) {
-    const size_t pix = img0 + (size_t)i * W + j;
-    const int c0 = (ly + kFlowHalo) * kFlowSW + lx + kFlowHalo;
-    const float pd = tile[0][c0], fx = tile[1][c0], fy = tile[2][c0];
-    float g_pd, g_fx, g_fy;
-    {   // the three smoothness terms
-      float v0, v1, v2;
-      const SmoothW w = smooth_weights(i, j, H, W, P.c_xx[s], P.c_xy[s], P.c_yy[s]);
-      smooth_at(&tile[0][c0], w, v0, g_pd);
-      smooth_at(&tile[1][c0], w, v1, g_fx);
-      smooth_at(&tile[2][c0], w, v2, g_fy);
-      acc[1] = v0 + v1 + v2;
-    }
-    const float gx = grid_coord(j, W, P.wstep[s]), gy = grid_coord(i, H, P.hstep[s]);
-    const Ray ray = back_project(sx.kinv, gx, gy);
-    const float lab = __ldg(P.label[s] + pix);
-    {   // supervised inverse-depth error, :163-164
-      const float e = __fsub_rn(lab, pd);
-      acc[0] = P.c_depth[s] * fabsf(e);
-      g_pd -= P.c_depth[s] * sgn(e);
-    }
-    float wmask, tfx, tfy;
-    {   // the ground-truth warp: validity mask and flow target only, :169-176, :204
-      const float d = __fdiv_rn(1.0f, lab);
-      const Proj q = project(sx.p, __fmul_rn(ray.r0, d), __fmul_rn(ray.r1, d), __fmul_rn(ray.r2, d));
-      const Foot f = footprint(q.x, q.y, W, H);
-      wmask = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(f.wx0, f.wy0), __fmul_rn(f.wx0, f.wy1)), __fmul_rn(f.wx1, f.wy0)),
-                        __fmul_rn(f.wx1, f.wy1));
-      tfx = __fsub_rn(q.x, gx);     // depth_optflow, utils.py:321-338
-      tfy = __fsub_rn(q.y, gy);
-    }
-    float tgt[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) tgt[c] = __ldg(P.left[s] + pix * 3 + c);
+  if (j < W) {
+    const SmoothCol wc = smooth_cols(j, W, P.c_xx[s]);
+    const float gx = grid_coord(j, W, P.wstep[s]);
     const float* right = P.right[s] + img0 * 3;
-    const float kp = P.c_pixel[s] * wmask;
-    {   // the right image warped by the predicted depth, :178-187
-      const float d = __fdiv_rn(1.0f, pd);
-      const Proj q = project(sx.p, __fmul_rn(ray.r0, d), __fmul_rn(ray.r1, d), __fmul_rn(ray.r2, d));
-      float dx, dy;
-      const float err = sample_error(right, H, W, q.x, q.y, tgt, dx, dy);
-      acc[3] = kp * err;
-      const float rz = __frcp_rn(q.zp);
-      const float du0 = dx * rz, du1 = dy * rz;
-      const float du2 = -(q.x * du0 + q.y * du1);
-      const float gc0 = du0 * sx.p[0] + du1 * sx.p[4] + du2 * sx.p[8];
-      const float gc1 = du0 * sx.p[1] + du1 * sx.p[5] + du2 * sx.p[9];
-      const float gc2 = du0 * sx.p[2] + du1 * sx.p[6] + du2 * sx.p[10];
-      const float g_d = gc0 * ray.r0 + gc1 * ray.r1 + gc2 * ray.r2;
-      g_pd -= kp * g_d * d * d;                           // depth = 1 / pred_depth
+    const float c_depth = P.c_depth[s], c_pixel = P.c_pixel[s], c_flow = P.c_flow[s], c_xy = P.c_xy[s], c_yy = P.c_yy[s];
+    const float hstep = P.hstep[s], loss_scale = P.loss_scale;
+    const float* __restrict__ labels = P.label[s];
+    const float* __restrict__ lefts = P.left[s];
+    float* __restrict__ o_pd = P.g_pd[s];
+    float* __restrict__ o_fx = P.g_fx[s];
+    float* __restrict__ o_fy = P.g_fy[s];
+#pragma unroll 1
+    for (int rr = 0; rr < kFlowRows; ++rr) {
+      const int ly = wy + rr, i = y_base + ly;
+      if (i >= H) break;
+      const size_t pix = img0 + (size_t)i * W + j;
+      const int c0 = (ly + kFlowHalo) * kFlowSW + lx + kFlowHalo;
+      const float lab = __ldg(labels + pix);
+      float tgt[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) tgt[c] = __ldg(lefts + pix * 3 + c);
+      const float pd = tile[0][c0], fx = tile[1][c0], fy = tile[2][c0];
+      float g_pd, g_fx, g_fy;
+      {   // the three smoothness terms
+        float v0, v1, v2;
+        const SmoothW w = smooth_weights(wc, i, H, c_xy, c_yy);
+        smooth_at(&tile[0][c0], w, v0, g_pd);
+        smooth_at(&tile[1][c0], w, v1, g_fx);
+        smooth_at(&tile[2][c0], w, v2, g_fy);
+        acc[1] += v0 + v1 + v2;
+      }
+      const float gy = grid_coord(i, H, hstep);
+      const Ray ray = back_project(sx.kinv, gx, gy);
+      {   // supervised inverse-depth error, :163-164
+        const float e = __fsub_rn(lab, pd);
+        acc[0] = fmaf(c_depth, fabsf(e), acc[0]);
+        g_pd -= c_depth * sgn(e);
+      }
+      float wmask, tfx, tfy;
+      {   // the ground-truth warp: validity mask and flow target only, :169-176, :204
+        const float d = __fdiv_rn(1.0f, lab);
+        const Proj q = project(sx.p, __fmul_rn(ray.r0, d), __fmul_rn(ray.r1, d), __fmul_rn(ray.r2, d));
+        const Foot f = footprint(q.x, q.y, W, H);
+        wmask = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(f.wx0, f.wy0), __fmul_rn(f.wx0, f.wy1)), __fmul_rn(f.wx1, f.wy0)),
+                          __fmul_rn(f.wx1, f.wy1));
+        tfx = __fsub_rn(q.x, gx);     // depth_optflow, utils.py:321-338
+        tfy = __fsub_rn(q.y, gy);
+      }
+      const float kp = c_pixel * wmask;
+      {   // the right image warped by the predicted depth, :178-187
+        const float d = __fdiv_rn(1.0f, pd);
+        const Proj q = project(sx.p, __fmul_rn(ray.r0, d), __fmul_rn(ray.r1, d), __fmul_rn(ray.r2, d));
+        float dx, dy;
+        const float err = sample_error(right, H, W, q.x, q.y, tgt, dx, dy);
+        acc[3] = fmaf(kp, err, acc[3]);
+        const float rz = __frcp_rn(q.zp);
+        const float du0 = dx * rz, du1 = dy * rz;
+        const float du2 = -(q.x * du0 + q.y * du1);
+        const float gc0 = du0 * sx.p[0] + du1 * sx.p[4] + du2 * sx.p[8];
+        const float gc1 = du0 * sx.p[1] + du1 * sx.p[5] + du2 * sx.p[9];
+        const float gc2 = du0 * sx.p[2] + du1 * sx.p[6] + du2 * sx.p[10];
+        const float g_d = gc0 * ray.r0 + gc1 * ray.r1 + gc2 * ray.r2;
+        g_pd -= kp * g_d * d * d;                           // depth = 1 / pred_depth
+      }
+      {   // ... and by the predicted flow (optflow_warp, utils.py:201-217), :190-197
+        float dx, dy;
+        const float err = sample_error(right, H, W, __fadd_rn(gx, fx), __fadd_rn(gy, fy), tgt, dx, dy);
+        acc[3] = fmaf(kp, err, acc[3]);
+        g_fx += kp * dx;
+        g_fy += kp * dy;
+      }
+      {   // flow against the flow the ground-truth depth implies, :204-210
+        const float ex = __fsub_rn(fx, tfx), ey = __fsub_rn(fy, tfy);
+        acc[2] = fmaf(c_flow, fabsf(ex) + fabsf(ey), acc[2]);
+        g_fx += c_flow * sgn(ex);
+        g_fy += c_flow * sgn(ey);
+      }
+      o_pd[pix] = g_pd * loss_scale;
+      o_fx[pix] = g_fx * loss_scale;
+      o_fy[pix] = g_fy * loss_scale;
     }
-    {   // ... and by the predicted flow (optflow_warp, utils.py:201-217), :190-197
-      float dx, dy;
-      const float err = sample_error(right, H, W, __fadd_rn(gx, fx), __fadd_rn(gy, fy), tgt, dx, dy);
-      acc[3] += kp * err;
-      g_fx += kp * dx;
-      g_fy += kp * dy;
-    }
-    {   // flow against the flow the ground-truth depth implies, :204-210
-      const float ex = __fsub_rn(fx, tfx), ey = __fsub_rn(fy, tfy);
-      acc[2] = P.c_flow[s] * (fabsf(ex) + fabsf(ey));
-      g_fx += P.c_flow[s] * sgn(ex);
-      g_fy += P.c_flow[s] * sgn(ey);
-    }
-    P.g_pd[s][pix] = g_pd * P.loss_scale;
-    P.g_fx[s][pix] = g_fx * P.loss_scale;
-    P.g_fy[s][pix] = g_fy * P.loss_scale;
   }
   block_sum<kFlowTerms>(acc, scratch, P.partials + (size_t)item * kFlowTerms);
 }
@@ -484,7 +512,7 @@ int vsl_flow_loss_fwd_bwd(const VslFlowLossDesc* d, const float* left, const flo
     const int e = launch_status();
     if (e != VSL_OK) return e;
   }
-  flow_loss_kernel<<<items, kFlowTW * kFlowTH, 0, st>>>(P);
+  flow_loss_kernel<<<items, kFlowThreads, 0, st>>>(P);
   int e = launch_status();
   if (e != VSL_OK) return e;
   flow_finalize_kernel<<<1, kFlowFinThreads, 0, st>>>(P.partials, items, losses);

@@ -514,7 +514,8 @@ loss_fused_pair_kernel(const LossParams P) {
   // ---- 4. one warp reduction per tile (same slots as loss_fused_kernel)
   // recomputed: not worth a register in the loop.  (The compiler keeps min(x, W - 1) on the stack across the row loop
   // for this -- 4 bytes, reloaded here once per tile, ~3 % of the kernel in the r6 capture.  Rebuilding the column from
-  // the running pixel offset instead frees that slot and ptxas then spills a value INSIDE the loop: measured 2 us slower.)
+  // the running pixel offset, or from %laneid, frees that slot and ptxas then spills a value INSIDE the loop: measured 2 us
+  // and 1 us slower.)
   const float gx_end = grid_coord(min(x_base + lane, W - 1), W, P.wstep[s]);
   float vals[N];
   float pix_sum = 0.f, exp_sum = 0.f;
