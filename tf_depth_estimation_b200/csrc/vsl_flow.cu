@@ -57,86 +57,20 @@ struct FlowParams {
   float loss_scale;
 };
 
-// Weights of the 14 second differences an element takes part in (my_losses.py:27-36): coefficient of the mean it
-// belongs to x its place in the stencil (1, -2, 1 / 1, -1, -1, 1) x [the difference exists], shared by the three maps.
-struct SmoothW {
-  float xx[3];   // owned by (i, j), (i, j-1), (i, j-2)
-  float yy[3];   // owned by (i, j), (i-1, j), (i-2, j)
-  float xy[4];   // owned by (i, j), (i, j-1), (i-1, j), (i-1, j-1); d/dy of dx and d/dx of dy share position and weight
-  float oxx, oyy, oxy;   // the plain coefficients of the differences (i, j) owns, for the loss value
-};
-
-// The weights separate: an xx difference exists or not by the column alone, a yy difference by the row alone, a 2 x 2
-// cell by (row ok) x (column ok).  The column part is fixed for a thread, the row part changes with the tile row.
-struct SmoothCol { float xx[3]; bool ok[2]; };
-VSL_DEV SmoothCol smooth_cols(int j, int W, float cxx) {
-  SmoothCol c;
-  const float st[3] = {1.f, -2.f, 1.f};
-#pragma unroll
-  for (int k = 0; k < 3; ++k) c.xx[k] = (j - k >= 0 && j - k + 2 < W) ? cxx * st[k] : 0.f;
-#pragma unroll
-  for (int dj = 0; dj < 2; ++dj) c.ok[dj] = j - dj >= 0 && j - dj + 1 < W;
-  return c;
-}
-VSL_DEV SmoothW smooth_weights(const SmoothCol& c, int i, int H, float cxy, float cyy) {
-  SmoothW w;
-  const float st[3] = {1.f, -2.f, 1.f};
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    w.xx[k] = c.xx[k];
-    w.yy[k] = (i - k >= 0 && i - k + 2 < H) ? cyy * st[k] : 0.f;
-  }
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int di = k >> 1, dj = k & 1;
-    const bool ok = i - di >= 0 && i - di + 1 < H && c.ok[dj];
-    w.xy[k] = ok ? ((di ^ dj) ? -cxy : cxy) : 0.f;
-  }
-  w.oxx = fabsf(w.xx[0]); w.oyy = fabsf(w.yy[0]); w.oxy = fabsf(w.xy[0]);
-  return w;
-}
-
 // sign(e) in {-1, 0, 1} with two FMA-pipe instructions: sat(e * 2^100 + 0.5) is 0, 0.5 or 1 (exact for every float32
 // that is not denormal)
 VSL_DEV float sign2(float e) { return fmaf(__saturatef(fmaf(e, 1.2676506e30f, 0.5f)), 2.0f, -1.0f); }
 
-// One map's smoothness at an element from its shared-memory tile (q points at the element, row pitch kFlowSW; the
-// tile is zero outside the image and the weights are zero for differences that do not exist): the weighted
-// |second differences| the element owns, and the gradient it receives from the stencils it is part of.
-VSL_DEV void smooth_at(const float* q, const SmoothW& w, float& val, float& grad) {
-  constexpr int P = kFlowSW;
-  // row i: columns j-2 .. j+2; column j: rows i-2 .. i+2; the 3 x 3 block around the element
-  const float r[5] = {q[-2], q[-1], q[0], q[1], q[2]};
-  const float c[5] = {q[-2 * P], q[-P], q[0], q[P], q[2 * P]};
-  const float nw = q[-P - 1], ne = q[-P + 1], sw = q[P - 1], se = q[P + 1];
-  float g = 0.f;
-  {
-    const float d0 = __fsub_rn(r[1], r[0]), d1 = __fsub_rn(r[2], r[1]), d2 = __fsub_rn(r[3], r[2]), d3 = __fsub_rn(r[4], r[3]);
-    const float o = __fsub_rn(d3, d2);
-    g = fmaf(w.xx[0], sign2(o), fmaf(w.xx[1], sign2(__fsub_rn(d2, d1)), w.xx[2] * sign2(__fsub_rn(d1, d0))));
-    val = w.oxx * fabsf(o);
-  }
-  {
-    const float d0 = __fsub_rn(c[1], c[0]), d1 = __fsub_rn(c[2], c[1]), d2 = __fsub_rn(c[3], c[2]), d3 = __fsub_rn(c[4], c[3]);
-    const float o = __fsub_rn(d3, d2);
-    g += fmaf(w.yy[0], sign2(o), fmaf(w.yy[1], sign2(__fsub_rn(d2, d1)), w.yy[2] * sign2(__fsub_rn(d1, d0))));
-    val = fmaf(w.oyy, fabsf(o), val);
-  }
-  {
-    // the four 2 x 2 cells around the element: (q00 q01 / q10 q11) with the owner at q00
-    auto cell = [&](float q00, float q01, float q10, float q11, float wk, bool own) {
-      const float a = __fsub_rn(__fsub_rn(q11, q10), __fsub_rn(q01, q00));   // d/dy of dx
-      const float b = __fsub_rn(__fsub_rn(q11, q01), __fsub_rn(q10, q00));   // d/dx of dy
-      g = fmaf(wk, sign2(a) + sign2(b), g);
-      if (own) val = fmaf(w.oxy, fabsf(a) + fabsf(b), val);
-    };
-    cell(r[2], r[3], c[3], se, w.xy[0], true);      // owner (i, j)
-    cell(r[1], r[2], sw, c[3], w.xy[1], false);     // owner (i, j-1)
-    cell(c[1], ne, r[2], r[3], w.xy[2], false);     // owner (i-1, j)
-    cell(nw, c[1], r[1], r[2], w.xy[3], false);     // owner (i-1, j-1)
-  }
-  grad = g;
-}
+// Owners of second differences (my_losses.py:27-36): element (oy, ox) owns dxx = q[ox+2] - 2 q[ox+1] + q[ox] of its
+// row, dyy of its column and the two mixed differences of the 2 x 2 cell to its lower right.  A tile needs the owners
+// two rows above and two columns left of it as well: (kFlowTH + 2) x (kFlowTW + 2) owners per map.
+constexpr int kFlowGW = kFlowTW + kFlowHalo, kFlowGH = kFlowTH + kFlowHalo;
+struct FlowSmem {
+  float tile[3][kFlowSH * kFlowSW];        // the three predicted maps with their halo, zero outside the image
+  float sg[3][3][kFlowGH * kFlowGW];       // per map: sign(dxx), sign(dyy), sign(dxy) + sign(dyx) of the owner, 0 if absent
+  Xform sx;
+  float scratch[kFlowTerms * kFlowWarps];
+};
 
 // bilinear_sampler (utils.py:219-308) of a packed RGB level at (x, y) against `tgt`, weighted by `w`:
 // returns sum_c |sample_c - tgt_c| and d(that sum)/dx, d/dy (the sampler's backward, SURVEY 8a "Backward semantics").
@@ -168,9 +102,11 @@ VSL_DEV float sample_error(const float* __restrict__ img, int H, int W, float x,
 #endif
 __global__ void __launch_bounds__(kFlowThreads, VSL_FLOW_MINB)
 flow_loss_kernel(const FlowParams P) {
-  __shared__ float tile[3][kFlowSH * kFlowSW];
-  __shared__ Xform sx;
-  __shared__ float scratch[kFlowTerms * kFlowWarps];
+  extern __shared__ float4 flow_smem_raw[];
+  FlowSmem& sm = *reinterpret_cast<FlowSmem*>(flow_smem_raw);
+  float (&tile)[3][kFlowSH * kFlowSW] = sm.tile;
+  Xform& sx = sm.sx;
+  float* scratch = sm.scratch;
   const int item = blockIdx.x;
   int s = 0;
   while (s + 1 < P.S && item >= P.item_begin[s + 1]) ++s;
@@ -203,14 +139,52 @@ flow_loss_kernel(const FlowParams P) {
   }
   __syncthreads();
 
+  float acc[kFlowTerms] = {0.f, 0.f, 0.f, 0.f};
+  const float c_xx = P.c_xx[s], c_xy = P.c_xy[s], c_yy = P.c_yy[s];
+  {
+    // every second difference once, at its owner: value (owners inside the tile proper) and sign (all owners).  Rows
+    // of the tile below the image were not loaded: a difference that does not exist is SELECTED away, never multiplied
+    constexpr int PT = kFlowSW;
+    float val = 0.f;
+    for (int e = threadIdx.x; e < kFlowGH * kFlowGW; e += kFlowThreads) {
+      const int ol = e / kFlowGW, oc = e - ol * kFlowGW;
+      const int oy = y_base - kFlowHalo + ol, ox = x_base - kFlowHalo + oc;
+      const bool rin = (unsigned)oy < (unsigned)H, cin = (unsigned)ox < (unsigned)W;
+      const bool exx = rin && ox >= 0 && ox + 2 < W;
+      const bool eyy = cin && oy >= 0 && oy + 2 < H;
+      const bool exy = oy >= 0 && ox >= 0 && oy + 1 < H && ox + 1 < W;
+      const bool own = ol >= kFlowHalo && oc >= kFlowHalo;
+      const int t0 = ol * PT + oc;
+#pragma unroll
+      for (int m = 0; m < 3; ++m) {
+        const float* q = &tile[m][t0];
+        const float r0 = q[0], r1 = q[1], r2 = q[2], c1 = q[PT], c2 = q[2 * PT], d = q[PT + 1];
+        const float dx0 = __fsub_rn(r1, r0), dy0 = __fsub_rn(c1, r0);
+        const float xx = __fsub_rn(__fsub_rn(r2, r1), dx0);
+        const float yy = __fsub_rn(__fsub_rn(c2, c1), dy0);
+        const float a = __fsub_rn(__fsub_rn(d, c1), dx0);      // d/dy of dx
+        const float b = __fsub_rn(__fsub_rn(d, r1), dy0);      // d/dx of dy
+        sm.sg[m][0][e] = exx ? sign2(xx) : 0.f;
+        sm.sg[m][1][e] = eyy ? sign2(yy) : 0.f;
+        sm.sg[m][2][e] = exy ? sign2(a) + sign2(b) : 0.f;
+        if (own) {
+          float v = exx ? c_xx * fabsf(xx) : 0.f;
+          v = eyy ? fmaf(c_yy, fabsf(yy), v) : v;
+          v = exy ? fmaf(c_xy, fabsf(a) + fabsf(b), v) : v;
+          val += v;
+        }
+      }
+    }
+    acc[1] = val;
+  }
+  __syncthreads();
+
   const int lx = threadIdx.x & 31, wy = (threadIdx.x >> 5) * kFlowRows;
   const int j = x_base + lx;
-  float acc[kFlowTerms] = {0.f, 0.f, 0.f, 0.f};
   if (j < W) {
-    const SmoothCol wc = smooth_cols(j, W, P.c_xx[s]);
     const float gx = grid_coord(j, W, P.wstep[s]);
     const float* right = P.right[s] + img0 * 3;
-    const float c_depth = P.c_depth[s], c_pixel = P.c_pixel[s], c_flow = P.c_flow[s], c_xy = P.c_xy[s], c_yy = P.c_yy[s];
+    const float c_depth = P.c_depth[s], c_pixel = P.c_pixel[s], c_flow = P.c_flow[s];
     const float hstep = P.hstep[s], loss_scale = P.loss_scale;
     const float* __restrict__ labels = P.label[s];
     const float* __restrict__ lefts = P.left[s];
@@ -229,13 +203,21 @@ flow_loss_kernel(const FlowParams P) {
       for (int c = 0; c < 3; ++c) tgt[c] = __ldg(lefts + pix * 3 + c);
       const float pd = tile[0][c0], fx = tile[1][c0], fy = tile[2][c0];
       float g_pd, g_fx, g_fy;
-      {   // the three smoothness terms
-        float v0, v1, v2;
-        const SmoothW w = smooth_weights(wc, i, H, c_xy, c_yy);
-        smooth_at(&tile[0][c0], w, v0, g_pd);
-        smooth_at(&tile[1][c0], w, v1, g_fx);
-        smooth_at(&tile[2][c0], w, v2, g_fy);
-        acc[1] += v0 + v1 + v2;
+      {   // gradients of the three smoothness terms: the signs of the ten differences the element is part of, times
+          // its place in the stencil (1, -2, 1 / 1, -1, -1, 1); small integers, so the bracketed sums are exact
+        const int g0 = (ly + kFlowHalo) * kFlowGW + lx + kFlowHalo;
+        auto grad = [&](int m) {
+          const float* xx = &sm.sg[m][0][g0];
+          const float* yy = &sm.sg[m][1][g0];
+          const float* xy = &sm.sg[m][2][g0];
+          const float gxx = fmaf(-2.f, xx[-1], xx[0] + xx[-2]);
+          const float gyy = fmaf(-2.f, yy[-kFlowGW], yy[0] + yy[-2 * kFlowGW]);
+          const float gxy = (xy[0] - xy[-1]) - (xy[-kFlowGW] - xy[-kFlowGW - 1]);
+          return fmaf(c_xx, gxx, fmaf(c_yy, gyy, c_xy * gxy));
+        };
+        g_pd = grad(0);
+        g_fx = grad(1);
+        g_fy = grad(2);
       }
       const float gy = grid_coord(i, H, hstep);
       const Ray ray = back_project(sx.kinv, gx, gy);
@@ -512,7 +494,13 @@ int vsl_flow_loss_fwd_bwd(const VslFlowLossDesc* d, const float* left, const flo
     const int e = launch_status();
     if (e != VSL_OK) return e;
   }
-  flow_loss_kernel<<<items, kFlowThreads, 0, st>>>(P);
+  {
+    // > 48 KB of dynamic shared memory needs the opt-in; idempotent and cheap, so set on every call (no state)
+    const cudaError_t ea = cudaFuncSetAttribute(flow_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)sizeof(FlowSmem));
+    if (ea != cudaSuccess) return (int)ea;
+  }
+  flow_loss_kernel<<<items, kFlowThreads, sizeof(FlowSmem), st>>>(P);
   int e = launch_status();
   if (e != VSL_OK) return e;
   flow_finalize_kernel<<<1, kFlowFinThreads, 0, st>>>(P.partials, items, losses);
