@@ -41,7 +41,7 @@ class Guarded(object):
             band = BAND
             self.big = _canary(band + cnt + band, dev)
         self.band, self.cnt = band, cnt
-        self.t = self.big[band:band + cnt].view(*shape)
+        self.t = self.big[band:band + cnt].view(tuple(shape))
         if like is not None:
             self.t.copy_(like)
 
@@ -261,3 +261,117 @@ def test_adam_and_strip_kernels_stay_inside_their_buffers():
     for x in bufs:
         assert x.bands_intact()
         assert bool(torch.isfinite(x.t).all())
+
+
+class _GuardedTorch(object):
+    """Stands in for the `torch` module inside tf_depth_estimation_b200.ops: everything the wrappers allocate on the
+    device (outputs, gradients, workspaces -- all through torch.empty / torch.empty_like) lands between canary bands."""
+
+    def __init__(self):
+        self.guards = []
+
+    def __getattr__(self, name):
+        return getattr(torch, name)
+
+    def _guarded(self, shape, dtype, dev):
+        g = Guarded(tuple(shape), dtype, dev)
+        self.guards.append(g)
+        return g.t
+
+    def empty(self, *size, **kw):
+        dev, dtype = kw.get('device'), kw.get('dtype', torch.float32)
+        if dev is None or torch.device(dev).type != 'cuda' or dtype not in (torch.float32, torch.uint8):
+            return torch.empty(*size, **kw)
+        shape = size[0] if len(size) == 1 and isinstance(size[0], (tuple, list, torch.Size)) else size
+        return self._guarded(shape, dtype, torch.device(dev))
+
+    def empty_like(self, t, **kw):
+        if kw or not t.is_cuda or t.dtype != torch.float32:
+            return torch.empty_like(t, **kw)
+        return self._guarded(t.shape, t.dtype, t.device)
+
+
+def test_standalone_ops_stay_inside_their_buffers(monkeypatch):
+    """What an unedited reference loop calls (`from utils_lr import *`): every op forward and backward, with the
+    inputs between NaN bands and every buffer the wrapper allocates between canary bands."""
+    dev = torch.device('cuda:0')
+    B, H, W = 2, 24, 40           # off every tile size; the coarse level (12 x 20) is smaller than a tile
+    d = synth.make_snippets(B, H, W, S=2, V=2, seed=11, motion=6.0)
+    f = synth.make_flow_pairs(B, H, W, S=2, seed=12)
+
+    def run(guarded):
+        gen = torch.Generator().manual_seed(13)
+        rnd = lambda *shape: torch.rand(*shape, generator=gen)
+        keep = []
+        gt = _GuardedTorch()
+        if guarded:
+            monkeypatch.setattr(ops, 'torch', gt)
+
+        def inp(t, grad=False):
+            if guarded:
+                g = Guarded(tuple(t.shape), torch.float32, dev, like=t.to(dev))
+                keep.append(g)
+                x = g.t
+            else:
+                x = t.to(dev).contiguous()
+            return x.requires_grad_() if grad else x
+        res = []
+
+        def done(outs, leaves):
+            outs = [o for o in (outs if isinstance(outs, (tuple, list)) else [outs]) if torch.is_tensor(o)]
+            res.extend(o.detach().clone() for o in outs)
+            diff = [o for o in outs if o.requires_grad]
+            if diff and leaves:
+                gs = torch.autograd.grad([o.sum() for o in diff], leaves, allow_unused=True)
+                res.extend(g.clone() for g in gs if g is not None)
+        try:
+            img, depth = inp(d['srcs'][0], True), inp(1.0 / d['disp_pyr'][0][..., 0], True)
+            pose, K = inp(d['poses'][:, 0], True), inp(d['K'])
+            done(ops.projective_inverse_warp(img, depth, pose, K, 'eular'), [img, depth, pose])
+            vec = inp(d['poses'][:, 1], True)
+            done(ops.pose_vec2mat(vec, 'angleaxis'), [vec])
+            coords = inp(rnd(B, H, W, 2) * torch.tensor([W + 6.0, H + 6.0]) - 3.0, True)
+            im2 = inp(d['tgt'], True)
+            done(ops.bilinear_sampler(im2, coords), [im2, coords])
+            fx, fy = inp(f['flowx_pyr'][0], True), inp(f['flowy_pyr'][0], True)
+            im3 = inp(f['right'], True)
+            done(ops.optflow_warp(im3, fx, fy), [im3, fx, fy])
+            done(ops.depth_optflow(coords.detach()), [])
+            sd, pr = inp(rnd(B, H, W, 1) + 0.5, True), inp(rnd(B, H, W, 1) + 0.5, True)
+            done(ops.consistent_depth_loss(sd, pr, coords), [sd, pr, coords])
+            grid = ops.meshgrid(B, H, W, True, device=dev)
+            done(grid, [])
+            dep2 = inp(rnd(B, H, W) + 0.5, True)
+            cam = ops.pixel2cam(dep2, grid, K, True)
+            done(cam, [dep2])
+            proj = inp(f['proj'], True)
+            cam2 = inp(cam.detach().cpu(), True)
+            done(ops.cam2pixel(cam2, proj), [cam2, proj])
+            axis, ang = inp(rnd(B, 3) - 0.5, True), inp(rnd(B, 1, 1) + 0.1, True)
+            done(ops.axis_angle_to_rotation_matrix(axis, ang), [axis, ang])
+            for inverse in (False, True):
+                x = inp(d['disp_pyr'][1], True)
+                done(ops.compute_smooth_loss(x, inverse), [x])
+            lg = inp(d['logits_pyr'][1][..., :2], True)
+            done(ops.compute_exp_reg_loss(lg), [lg])
+            a, b = inp(d['tgt'], True), inp(d['srcs'][1], True)
+            done(ops.ssim_loss(a, b), [a, b])
+            done(ops.ssim_dissimilarity(a, b), [a, b])
+            dsp, im4 = inp(d['disp_pyr'][0], True), inp(d['tgt'], True)
+            done(ops.edge_aware_smooth_loss(dsp, im4), [dsp, im4])
+            done(ops.image_pyramid(inp(d['tgt']), 3)[1:], [])
+        finally:
+            if guarded:
+                monkeypatch.undo()
+        torch.cuda.synchronize()
+        if guarded:
+            assert len(gt.guards) > 40            # the wrappers' allocations did go through the stand-in
+            for g in keep + gt.guards:
+                assert g.bands_intact(), 'a write landed outside a buffer of a stand-alone op'
+        return res
+
+    plain, guarded = run(False), run(True)
+    assert len(plain) == len(guarded) and len(plain) > 40
+    for a, b in zip(plain, guarded):
+        assert a.shape == b.shape and bool(torch.isfinite(b).all())
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-6), 'results depend on what lies around the inputs'
