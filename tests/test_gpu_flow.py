@@ -61,10 +61,11 @@ def _cuda(d, flags, loss_scale=1.0):
     return total, losses, pd, fx, fy
 
 
-@pytest.mark.parametrize('B,H,W,S,motion', [(2, 24, 40, 3, 1.0), (3, 48, 72, 4, 6.0), (1, 12, 20, 2, 1.0), (2, 16, 24, 1, 3.0)])
+@pytest.mark.parametrize('B,H,W,S,motion', [(2, 24, 40, 3, 1.0), (3, 48, 72, 4, 6.0), (1, 12, 20, 2, 1.0), (2, 16, 24, 1, 3.0),
+                                              (2, 72, 104, 3, 2.0), (1, 40, 72, 2, 1.0)])
 def test_flow_depth_loss_against_oracle(B, H, W, S, motion):
-    """Ragged tiles (widths that are no multiple of 32, heights no multiple of 8), 1-4 scales, a large-motion case
-    with a third of the samples out of view."""
+    """Ragged tiles (widths and heights that are no multiple of the 32 x 32 tile, levels that straddle one, two or three
+    tile rows, levels smaller than a tile), 1-4 scales, a large-motion case with a third of the samples out of view."""
     d = synth.make_flow_pairs(B, H, W, S=S, seed=300 + H, motion=motion)
     flags = ops.FlowLossFlags(num_scales=S, smooth_weight=0.3, depth_weight=1.5, data_weight=2.0, optflow_weight=0.4)
     terms, opd, ofx, ofy = _oracle(d, flags)
