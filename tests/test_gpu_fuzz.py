@@ -15,3 +15,13 @@ def test_randomised_parity_slice():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     assert mod.run(seed=5, n_cases=24, verbose=False) == 0
+
+
+def test_randomised_flow_parity_slice():
+    """The same for the fused flow-and-depth step (profiles/fuzz_flow.py): every pixel's gradient against the float32
+    oracle, shapes off the 32 x 32 tile."""
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'profiles', 'fuzz_flow.py')
+    spec = importlib.util.spec_from_file_location('fuzz_flow', path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.run(seed=4, n_cases=16, verbose=False) == 0
