@@ -41,7 +41,8 @@ def run(seed=0, n_cases=40, verbose=True):
         total, losses = ops.flow_depth_loss(cu(d['left']), cu(d['right']), cu(d['label']), pd, fx, fy, cu(d['proj']),
                                             cu(d['K_pyr']), flags)
         total.backward()
-        worst_l = max(abs(float(losses[i]) - float(terms[i])) / max(abs(float(terms[i])), 1e-30) for i in range(4))
+        tv = [float(t.detach()) for t in terms]
+        worst_l = max(abs(float(losses[i]) - tv[i]) / max(abs(tv[i]), 1e-30) for i in range(4))
         worst_g = max(rel_err(g[s].grad, o[s].grad) for g, o in ((pd, opd), (fx, ofx), (fy, ofy)) for s in range(S))
         ok = worst_l <= 1e-5 and worst_g <= 1e-4
         bad += 0 if ok else 1
