@@ -254,7 +254,7 @@ def flow_leg(dev, steps):
         return {'error': '%s: %s' % (type(e).__name__, e)}
 
 
-def quick_config(name, dev, rank, steps=40, warmup=5):
+def quick_config(name, dev, rank, steps=40, warmup=5, extra_flags=None, note=None):
     """One more BASELINE shape through the same device-resident step (rotating input sets, in-situ kernel events on
     every 4th step): the short form of the main measurement, for the `other_configs` object of the default line."""
     import torch
@@ -262,7 +262,7 @@ def quick_config(name, dev, rank, steps=40, warmup=5):
     try:
         c = CONFIGS[name]
         B, H, W, S, V = (c[k] for k in 'BHWSV')
-        flags = ops.LossFlags(num_scales=S, **c['flags'])
+        flags = ops.LossFlags(num_scales=S, **dict(c['flags'], **(extra_flags or {})))
         plan = ops.ViewSynthesisPlan(B, H, W, V, flags, _lib.MASK_EXP, dev)
         host = synth.make_snippets(min(B, 16), H, W, S=S, V=V, seed=4321 + rank)
         rep = lambda t, k: torch.roll(t.repeat((B + t.shape[0] - 1) // t.shape[0], *([1] * (t.dim() - 1)))[:B], k, 0).to(dev).contiguous()
@@ -298,6 +298,9 @@ def quick_config(name, dev, rank, steps=40, warmup=5):
                'value': pixel_views(c, B) / (ms * 1e-3) / 1e6, 'unit': UNIT, 'kernel_ms_mean': kms,
                'algorithmic_bytes_per_launch': algo, 'roofline_frac': algo / (kms * 1e-3) / 1e9 / peak,
                'losses_finite': bool(torch.isfinite(plan.losses).all())}
+        if note:                   # a variant of the step: the roofline model of the plain fused kernel does not describe it
+            out['workload'] = c['text'] + '; ' + note
+            del out['algorithmic_bytes_per_launch'], out['roofline_frac']
         del plan, bound
         torch.cuda.empty_cache()
         return out
@@ -455,6 +458,10 @@ def run_ours(args):
         # size in 8 waves instead of one), cfg4 = configs[3], cfg5 = configs[4] (the HBM-stress shape)
         others = {n: quick_config(n, dev, rank) for n in ('cfg3', 'cfg4', 'cfg5')}
         others['cfg4_flow'] = flow_leg(dev, 60)      # configs[3]'s own loss loop as the fused flow-and-depth step
+        # configs[1] words the photometric term as L1/SSIM; the reference itself has no SSIM, so this is the
+        # library's extension (VslLossDesc.ssim_weight: one more launch between the fused kernel and the finalize)
+        others['cfg2_l1_ssim'] = quick_config('cfg2', dev, rank, extra_flags={'ssim_weight': 0.85},
+                                              note='photometric term = 0.15 L1 + 0.85 SSIM(3x3) (extension, 4 launches per step; kernel_ms_mean is the fused L1 kernel alone)')
 
     if rank == 0:
         peak, peak_src = measured_peak()

@@ -3,7 +3,9 @@
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from tf_depth_estimation_b200 import ops, synth, _lib
-if os.environ.get('VSL_LIB_VARIANT'):   # timing experiments: profiles/build_variant.sh
+if os.environ.get('VSL_LIB_PATH'):
+    pass                                # _lib honours VSL_LIB_PATH itself
+elif os.environ.get('VSL_LIB_VARIANT'):   # timing experiments: profiles/build_variant.sh
     _lib.LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), '_exp', 'libvsl_%s.so' % os.environ['VSL_LIB_VARIANT'])
 CFG = {'cfg2': (32, 128, 416, 4, 2), 'cfg4': (64, 192, 256, 4, 1), 'cfg5': (64, 480, 640, 4, 2)}
 name = sys.argv[1] if len(sys.argv) > 1 else 'cfg2'
@@ -19,7 +21,8 @@ mk = lambda k: (cu(torch.roll(rep(d['tgt']), k, 0)), [cu(torch.roll(rep(s), k, 0
                 [cu(torch.roll(rep(x), k, 0)) for x in d['disp_pyr']], cu(torch.roll(rep(d['poses']), k, 0)),
                 cu(torch.roll(rep(d['K_pyr']), k, 0)), [cu(torch.roll(rep(l), k, 0)) for l in d['logits_pyr']])
 sets = [mk(k) for k in range(NSETS)]
-plan = ops.ViewSynthesisPlan(B, H, W, V, ops.LossFlags(exact_coords=arith), _lib.MASK_EXP, dev)
+plan = ops.ViewSynthesisPlan(B, H, W, V, ops.LossFlags(exact_coords=arith, ssim_weight=float(os.environ.get('VSL_SSIM', '0'))),
+                             _lib.MASK_EXP, dev)   # VSL_SSIM=0.85: the step with the SSIM share of the photometric term
 bounds = [plan.bind(*a) for a in sets]
 for i in range(3):
     plan.run_bound(bounds[i % NSETS])

@@ -9,11 +9,12 @@
 // m the explainability / validity mask at the window's centre.  The L1 part stays in the fused loss kernel (its weight
 // scaled by 1 - a); this kernel adds the SSIM part -- value AND gradient, no full-resolution intermediate:
 //
-//   one block = a 32 x 8 tile of one image at one scale (every scale in one grid), looping over the source views
-//   P1  the warped and target colours of the tile and a 2-pixel ring (36 x 12) -> shared memory.  Same sample
+//   one block = a 32 x 16 tile of one image at one scale (every scale in one grid; 256 threads, two rows each in P3),
+//   looping over the source views
+//   P1  the warped and target colours of the tile and a 2-pixel ring (36 x 20) -> shared memory.  Same sample
 //       positions as the fused kernel's fast arithmetic: folded projection u = d (Q [gx, gy, 1]) + t, clamp to
 //       [-2, size], four 16-byte gathers from the zero-bordered RGBA level the prep launch wrote.
-//   P2  the windows centred on the tile and a 1-pixel ring (34 x 10): SSIM per channel, and the three coefficients of
+//   P2  the windows centred on the tile and a 1-pixel ring (34 x 18): SSIM per channel, and the three coefficients of
 //       its derivative -- a window's dS/d(warp_k) is AFFINE in that pixel's (warp, tgt) values, alpha + beta warp_k +
 //       gamma tgt_k -- times the upstream weight (-a data_weight_s m / 2 count, 0 where the clip is active), to shared
 //       memory; the tile's share of the loss.
@@ -27,10 +28,25 @@
 
 namespace vsl {
 
-constexpr int kStW = 32, kStH = 8;
+#ifndef VSL_SSIM_TH
+#define VSL_SSIM_TH 16
+#endif
+constexpr int kStW = 32, kStH = VSL_SSIM_TH;      // (8-row tiles: 1.69 ring samples and 1.33 windows per pixel; 16: 1.41 / 1.20)
 constexpr int kSvW = kStW + 4, kSvH = kStH + 4;   // colour values: tile + 2-pixel ring
 constexpr int kScW = kStW + 2, kScH = kStH + 2;   // window centres: tile + 1-pixel ring
-constexpr int kStThreads = kStW * kStH;
+constexpr int kStThreads = 256;
+constexpr int kStRows = kStW * kStH / kStThreads; // tile rows a thread owns in P3 (rows ly, ly + 8, ...)
+static_assert(kStRows >= 1 && kStRows * kStThreads == kStW * kStH, "whole rows per thread");
+
+struct SsimSmem {                                  // 49.6 KB at 16-row tiles: dynamic shared memory (opt-in above 48 KB)
+  float va[3][kSvH * kSvW], vt[3][kSvH * kSvW];
+  float coef[3][3][kScH * kScW];
+  float dmap[3][kScH * kScW];   // D per channel and window
+  float msk[kScH * kScW];       // mask at the window's centre
+  float scratch[13 * (kStThreads / 32)];
+  float tot[13];
+  XformQ sxq;
+};
 
 // One target pixel's sample in source view v: everything the forward value and the backward chain need.
 struct SsimTap {
@@ -69,15 +85,21 @@ struct SsimGrid {
   int V;
 };
 
-__global__ void __launch_bounds__(kStThreads)
+#ifndef VSL_SSIM_MINB
+#define VSL_SSIM_MINB 4
+#endif
+__global__ void __launch_bounds__(kStThreads, VSL_SSIM_MINB)
 loss_ssim_kernel(const LossParams P, const SsimGrid G) {
-  __shared__ float va[3][kSvH * kSvW], vt[3][kSvH * kSvW];
-  __shared__ float coef[3][3][kScH * kScW];
-  __shared__ float dmap[3][kScH * kScW];   // D per channel and window
-  __shared__ float msk[kScH * kScW];       // mask at the window's centre
-  __shared__ float scratch[13 * (kStThreads / 32)];
-  __shared__ float tot[13];
-  __shared__ XformQ sxq;
+  extern __shared__ float4 ssim_smem_raw[];
+  SsimSmem& sm = *reinterpret_cast<SsimSmem*>(ssim_smem_raw);
+  float (&va)[3][kSvH * kSvW] = sm.va;
+  float (&vt)[3][kSvH * kSvW] = sm.vt;
+  float (&coef)[3][3][kScH * kScW] = sm.coef;
+  float (&dmap)[3][kScH * kScW] = sm.dmap;
+  float (&msk)[kScH * kScW] = sm.msk;
+  float* scratch = sm.scratch;
+  float* tot = sm.tot;
+  XformQ& sxq = sm.sxq;
   const int item = blockIdx.x;
   int s = 0;
   while (s + 1 < P.S && item >= G.item_begin[s + 1]) ++s;
@@ -90,7 +112,9 @@ loss_ssim_kernel(const LossParams P, const SsimGrid G) {
   const float css = G.css[s];
   const int nlg = 2 * G.V;
 
-  float gx_add = 0.f;     // this pixel's d/dx summed over the views in view order: one owner, one store, deterministic
+  float gx_add[kStRows];  // a pixel's d/dx summed over the views in view order: one owner, one store, deterministic
+#pragma unroll
+  for (int rr = 0; rr < kStRows; ++rr) gx_add[rr] = 0.f;
   for (int v = 0; v < G.V; ++v) {
   __syncthreads();        // the previous view's P3 has finished reading the tiles
   if (threadIdx.x < 12)
@@ -129,7 +153,7 @@ loss_ssim_kernel(const LossParams P, const SsimGrid G) {
   };
 
   // ---- P2: windows centred on the tile + 1-pixel ring.  First the mask at every centre (0 where no window exists),
-  // then one (centre, channel) pair per thread and trip: 3 x 340 pairs fill the block's 256 threads evenly
+  // then one (centre, channel) pair per thread and trip: 3 x 612 pairs over the block's 256 threads
   for (int c = threadIdx.x; c < kScH * kScW; c += kStThreads) {
     const int cy = c / kScW, cx = c - cy * kScW;
     const int y = y_base - 1 + cy, x = x_base - 1 + cx;
@@ -154,7 +178,7 @@ loss_ssim_kernel(const LossParams P, const SsimGrid G) {
           xv[i * 3 + j] = va[ch][(cy + i) * kSvW + cx + j];
           yv[i * 3 + j] = vt[ch][(cy + i) * kSvW + cx + j];
         }
-      const SsimWin w = ssim_stats<true>(xv, yv);
+      const SsimWin w = ssim_stats<true, true>(xv, yv);
       const float raw = 0.5f * (1.0f - w.S);
       dch = fminf(fmaxf(raw, 0.0f), 1.0f);
       const float up = (raw >= 0.0f && raw <= 1.0f) ? -0.5f * css * m : 0.0f;   // d(clip)/d(raw) * d(raw)/dS * weight
@@ -167,8 +191,9 @@ loss_ssim_kernel(const LossParams P, const SsimGrid G) {
   __syncthreads();
 
   // ---- P3: the tile's own pixels
-  {
-    const int lx = threadIdx.x & (kStW - 1), ly = threadIdx.x / kStW;
+#pragma unroll
+  for (int rr = 0; rr < kStRows; ++rr) {
+    const int lx = threadIdx.x & (kStW - 1), ly = threadIdx.x / kStW + rr * (kStThreads / kStW);
     const int y = y_base + ly, x = x_base + lx;
     if (y < H && x < W) {
       const int pv = (ly + 2) * kSvW + lx + 2;          // this pixel in the colour tile
@@ -200,12 +225,12 @@ loss_ssim_kernel(const LossParams P, const SsimGrid G) {
         // d/d(depth) = -<du, t> / depth (closed form: <du, u> = 0), then the chain to the network output x
         const float g_d = -(du0 * sxq.t[0] + du1 * sxq.t[1] + du2 * sxq.t[2]) * __fdividef(1.0f, t.d);
         const float chain = P.depth_is_inverse ? -t.d * t.d : 1.0f;
-        gx_add += g_d * chain;
+        gx_add[rr] += g_d * chain;
         const float dgx = t.d * t.gx, dgy = t.d * t.gy;
-        acc[1] = du0 * dgx; acc[2] = du1 * dgx; acc[3] = du2 * dgx;
-        acc[4] = du0 * dgy; acc[5] = du1 * dgy; acc[6] = du2 * dgy;
-        acc[7] = du0 * t.d; acc[8] = du1 * t.d; acc[9] = du2 * t.d;
-        acc[10] = du0; acc[11] = du1; acc[12] = du2;
+        acc[1] += du0 * dgx; acc[2] += du1 * dgx; acc[3] += du2 * dgx;
+        acc[4] += du0 * dgy; acc[5] += du1 * dgy; acc[6] += du2 * dgy;
+        acc[7] += du0 * t.d; acc[8] += du1 * t.d; acc[9] += du2 * t.d;
+        acc[10] += du0; acc[11] += du1; acc[12] += du2;
       }
       if (P.mask_mode == VSL_MASK_EXP && y >= 1 && y <= H - 2 && x >= 1 && x <= W - 2) {
         const float m = mask_at(y, x);
@@ -228,10 +253,11 @@ loss_ssim_kernel(const LossParams P, const SsimGrid G) {
     if (val != 0.f) atomicAdd(P.partials + (size_t)tile * N + col, val);
   }
   }   // views
-  {
-    const int lx = threadIdx.x & (kStW - 1), ly = threadIdx.x / kStW;
+#pragma unroll
+  for (int rr = 0; rr < kStRows; ++rr) {
+    const int lx = threadIdx.x & (kStW - 1), ly = threadIdx.x / kStW + rr * (kStThreads / kStW);
     const int y = y_base + ly, x = x_base + lx;
-    if (y < H && x < W && gx_add != 0.f) P.g_x[s][((size_t)b * H + y) * W + x] += gx_add;
+    if (y < H && x < W && gx_add[rr] != 0.f) P.g_x[s][((size_t)b * H + y) * W + x] += gx_add[rr];
   }
 }
 
@@ -256,7 +282,11 @@ int launch_ssim_term(const VslLossDesc* d, const LossParams& P, cudaStream_t st)
     G.item_begin[s + 1] = n;
   }
   static_assert(kRH % kStH == 0, "an SSIM tile lies inside one tile of the fused kernel");
-  loss_ssim_kernel<<<n, kStThreads, 0, st>>>(P, G);
+  // > 48 KB of dynamic shared memory needs the opt-in; idempotent and cheap, so set on every call (no state)
+  const cudaError_t ea = cudaFuncSetAttribute(loss_ssim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)sizeof(SsimSmem));
+  if (ea != cudaSuccess) return (int)ea;
+  loss_ssim_kernel<<<n, kStThreads, sizeof(SsimSmem), st>>>(P, G);
   return launch_status();
 }
 

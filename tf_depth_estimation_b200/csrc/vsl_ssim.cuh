@@ -8,8 +8,9 @@ namespace vsl {
 
 struct SsimWin { float S, ax, ay, beta, gamma; };
 
-// The 9 + 9 values of one window -> SSIM (and, with GRAD, the coefficients of its derivative).
-template <bool GRAD>
+// The 9 + 9 values of one window -> SSIM (and, with GRAD, the coefficients of its derivative).  FAST: one approximate
+// reciprocal (MUFU.RCP, 1 ulp) of B1 B2 instead of two IEEE divisions -- the in-step term, whose bars are 1e-5.
+template <bool GRAD, bool FAST = false>
 VSL_DEV SsimWin ssim_stats(const float (&xv)[9], const float (&yv)[9]) {
   const float C1 = 1e-4f, C2 = 9e-4f, ninth = 1.0f / 9.0f;
   float sx = 0.f, sy = 0.f;
@@ -25,7 +26,13 @@ VSL_DEV SsimWin ssim_stats(const float (&xv)[9], const float (&yv)[9]) {
   vxx *= ninth; vyy *= ninth; vxy *= ninth;
   const float A1 = 2.f * mx * my + C1, A2 = 2.f * vxy + C2;
   const float B1 = mx * mx + my * my + C1, B2 = vxx + vyy + C2;
-  const float i1 = 1.0f / B1, i2 = 1.0f / B2, inv = i1 * i2;
+  float i1, i2, inv;
+  if (FAST) {
+    inv = __fdividef(1.0f, B1 * B2);
+    i1 = inv * B2; i2 = inv * B1;
+  } else {
+    i1 = 1.0f / B1; i2 = 1.0f / B2; inv = i1 * i2;
+  }
   SsimWin w;
   w.S = A1 * A2 * inv;
   if (GRAD) {
