@@ -233,7 +233,7 @@ loss_ssim_kernel(const LossParams P, const SsimGrid G) {
         acc[10] += du0; acc[11] += du1; acc[12] += du2;
       }
       if (P.mask_mode == VSL_MASK_EXP && y >= 1 && y <= H - 2 && x >= 1 && x <= W - 2) {
-        const float m = mask_at(y, x);
+        const float m = msk[pc];                          // P2 left the mask of this very centre there
         const float g1 = css * (dmap[0][pc] + dmap[1][pc] + dmap[2][pc]) * m * (1.0f - m);      // d(m)/d(l1) = m (1 - m), d(m)/d(l0) = -m (1 - m)
         float2* gl = reinterpret_cast<float2*>(P.g_logits[s] + pix * nlg) + v;
         float2 cur = *gl;
