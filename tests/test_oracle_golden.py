@@ -118,6 +118,11 @@ def test_pyramid_and_intrinsics(golden):
     for s in (1, 2, 3):
         assert torch.equal(O.resize_area(c.img, 16 >> s, 24 >> s), c['l%d' % s])
     assert torch.equal(O.multi_scale_intrinsics(c.K, 4), c.K_pyr)
+    # the PRODUCT's own builders of the multi-scale intrinsics (what bench.py, the tests and the loader feed the kernels
+    # with) against the matrices the reference's get_multi_scale_intrinsics produced (Demon_Data_loader.py:25-39)
+    from tf_depth_estimation_b200 import data, synth
+    assert torch.equal(synth.intrinsics_pyramid(c.K, 4), c.K_pyr)
+    assert torch.equal(data.multi_scale_intrinsics(c.K, 4, 1.0, 1.0), c.K_pyr)
 
 
 def test_composite_loss(golden):
