@@ -237,7 +237,7 @@ def train_leg(rank, world, dev):
                 'global_batch': r['global_batch'], 'per_gpu_batch': r['per_gpu_batch'], 'scaling': 'strong',
                 'optimiser': 'fused reduce-scatter + Adam + all-gather over NVLink peer memory (dp_adam_kernel)',
                 'cuda_graph': r['cuda_graph'], 'params': r['params'], 'losses_finite': r['losses_finite'],
-                'workload': 'configs[2]: DispNet + PoseExpNet (torch/cuDNN fp32, TF32 allowed), explainability mask, 128x416'}
+                'workload': 'configs[2]: DispNet + PoseExpNet (torch/cuDNN fp32, TF32 allowed, cudnn.benchmark), explainability mask, 128x416'}
     except Exception as e:   # noqa: BLE001
         return {'error': '%s: %s' % (type(e).__name__, e)}
 

@@ -106,6 +106,8 @@ def measure(rank, world, dev, global_batch=256, steps=10, warmup=3, optim='peer'
     """One measurement on an initialised process group (or a single process) -> dict (identical on every rank except
     that only rank 0's is meant to be printed).  The caller owns the process group."""
     H, W, S, V = 128, 416, 4, 2
+    # the framework's own convolutions (outside the path): let cuDNN pick its algorithm per layer shape once, in the warm-up
+    torch.backends.cudnn.benchmark = os.environ.get('VSL_CUDNN_BENCHMARK', '1') != '0'
     lo, hi = vdist.shard_range(global_batch, rank, world)
     B = hi - lo
     torch.manual_seed(0)        # identical initial weights on every rank
