@@ -249,7 +249,10 @@ def flow_leg(dev, steps):
         spec = importlib.util.spec_from_file_location('time_flow', os.path.join(ROOT, 'profiles', 'time_flow.py'))
         mod = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(mod)
-        return mod.measure(dev, steps=max(20, min(steps, 200)))
+        r = mod.measure(dev, steps=max(20, min(steps, 200)))
+        peak, _ = measured_peak()     # whole step (4 launches) against the 52 compulsory bytes per pixel and scale
+        r['roofline_frac_of_step'] = r['achieved_gbs'] / peak
+        return r
     except Exception as e:   # noqa: BLE001
         return {'error': '%s: %s' % (type(e).__name__, e)}
 
