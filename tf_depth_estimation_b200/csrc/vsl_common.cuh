@@ -103,6 +103,7 @@ VSL_DEV void block_sum_bfly(float (&v)[N], float* scratch, float* out) {
 // Sums `n` partials in double in a fixed order; out[0] = result.  One block.
 static __global__ void sum_partials_kernel(const float* __restrict__ partial, int n, float* __restrict__ out) {
   __shared__ double sh[256];
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // launched programmatically dependent on the producer of `partial`
   double s = 0.0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) s += (double)partial[i];
   sh[threadIdx.x] = s;
@@ -112,6 +113,21 @@ static __global__ void sum_partials_kernel(const float* __restrict__ partial, in
     __syncthreads();
   }
   if (threadIdx.x == 0) out[0] = (float)sh[0];
+}
+
+// The partial-sum launch behind a producer kernel on the same stream: programmatic dependent launch, so its block is
+// resident (and past its launch latency) when the producer's last block retires; it waits inside (griddepcontrol.wait).
+static inline int launch_sum_partials(const float* partial, int n, float* out, cudaStream_t st) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(1);
+  cfg.blockDim = dim3(256);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return (int)cudaLaunchKernelEx(&cfg, sum_partials_kernel, partial, n, out);
 }
 
 VSL_DEV float sgn(float v) { return (v > 0.f) ? 1.f : ((v < 0.f) ? -1.f : 0.f); }  // tf.abs' gradient

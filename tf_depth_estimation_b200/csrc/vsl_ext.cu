@@ -256,7 +256,7 @@ int vsl_ssim_fwd(const float* x, const float* y, int B, int H, int W, int C, flo
   const long long nblocks = (long long)g.x * g.y * g.z;
   VSL_REQUIRE(nblocks < (1LL << 31), VSL_E_SHAPE);
   ssim_fwd_kernel<<<g, kSsThreads, 0, st>>>(x, y, ssim_dims(B, H, W, C), map, loss ? (float*)ws : nullptr);
-  if (loss) sum_partials_kernel<<<1, 256, 0, st>>>((const float*)ws, (int)nblocks, loss);
+  if (loss) { const int es = launch_sum_partials((const float*)ws, (int)nblocks, loss, st); if (es != 0) return es; }
   return launch_status();
 }
 
@@ -291,7 +291,7 @@ int vsl_edge_smooth_fwd(const float* disp, const float* img, int B, int H, int W
   const size_t n = (size_t)B * H * W;
   const int blocks = (int)((n + 255) / 256 < (size_t)kEdgeBlocks ? (n + 255) / 256 : kEdgeBlocks);
   edge_smooth_fwd_kernel<<<blocks, 256, 0, st>>>(disp, img, edge_dims(B, H, W, C), (float*)ws);
-  sum_partials_kernel<<<1, 256, 0, st>>>((const float*)ws, blocks, loss);
+  { const int es = launch_sum_partials((const float*)ws, blocks, loss, st); if (es != 0) return es; }
   return launch_status();
 }
 

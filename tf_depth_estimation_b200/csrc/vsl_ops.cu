@@ -951,7 +951,7 @@ int vsl_smooth_fwd(const float* x, int B, int H, int W, int C, int inverse, floa
   const size_t n = (size_t)B * H * W * C;
   const int blocks = (int)((n + 255) / 256 < (size_t)kReduceBlocks ? (n + 255) / 256 : kReduceBlocks);
   smooth_fwd_kernel<<<blocks, 256, 0, st>>>(x, smooth_dims(B, H, W, C, inverse), (float*)ws);
-  sum_partials_kernel<<<1, 256, 0, st>>>((const float*)ws, blocks, loss);
+  { const int es = launch_sum_partials((const float*)ws, blocks, loss, st); if (es != 0) return es; }
   return launch_status();
 }
 
@@ -975,7 +975,7 @@ int vsl_expreg_fwd(const float* logits, long long N, float* loss, void* ws, vsl_
   const long long nb = (N + 255) / 256;
   const int blocks = (int)(nb < kReduceBlocks ? nb : kReduceBlocks);
   expreg_fwd_kernel<<<blocks, 256, 0, st>>>(logits, N, (float)(1.0 / (double)N), (float*)ws);
-  sum_partials_kernel<<<1, 256, 0, st>>>((const float*)ws, blocks, loss);
+  { const int es = launch_sum_partials((const float*)ws, blocks, loss, st); if (es != 0) return es; }
   return launch_status();
 }
 
