@@ -710,14 +710,16 @@ loss_fused_kernel(const LossParams P) {
 #endif
 }
 
-// grid = B + 1 blocks of kFinThreads.  Block b < B: pose gradients of batch element b (all views).  The tile partials
+// grid = B + 1 blocks of T threads (256; 1024 -- 512 from three views up, for the shared-memory table -- when the
+// launch has more than kFinBigItems tile rows: every pass over the rows is a dependent round trip, and at B = 256 or at
+// 480 x 640 the 256-thread form makes ten of them).  Block b < B: pose gradients of batch element b (all views).  The tile partials
 // of (image, scale) are contiguous rows of N floats: warp w adds rows w, w + 8, ... with lane = column (one
 // coalesced request per row, every request independent), the 8 warp sums are combined in warp order.
 // Block B: the three loss scalars.  Every sum runs in a fixed order in double => deterministic.
 // Launched programmatically dependent on the fused kernel: what does not depend on it (K_s^-1 from the caller's
 // intrinsics) is done before griddepcontrol.wait, under the fused kernel's tail.
-constexpr int kFinThreads = 256;
-template <int V>
+constexpr int kFinBigItems = 8192;
+template <int V, int kFinThreads>
 __global__ void __launch_bounds__(kFinThreads)
 loss_finalize_kernel(const LossParams P, const float* __restrict__ poses, const float* __restrict__ K_pyr,
                      int pose_format, float inv_loss_scale, float* __restrict__ losses, float* __restrict__ g_poses) {
@@ -743,20 +745,22 @@ loss_finalize_kernel(const LossParams P, const float* __restrict__ poses, const 
   if (b == P.B) {
     // losses: columns 0..3 of every tile row (pixel, smooth, exp, consist), thread-strided, then a fixed tree
     double acc[kLossSlots] = {0.0, 0.0, 0.0, 0.0};
-    constexpr int U = 10;                      // rows in flight per thread: the loads of a batch are independent
+    // rows in flight per thread: the loads of a batch are independent; a row's four loss slots are ONE 16-byte load
+    // (a row is 16 (1 + 3 V) bytes), issued unconditionally from a clamped row -- a predicated load per row would cap
+    // the batch at the seven predicate registers -- and dropped, if past the end, when it is added
+    constexpr int U = 10;
+    static_assert(kLossSlots == 4, "one float4 per tile row");
     for (int i0 = threadIdx.x; i0 < n_items; i0 += kFinThreads * U) {
-      float q[U][kLossSlots];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int i = i0 + u * kFinThreads;
-        const float* p = P.partials + (size_t)(i < n_items ? i : 0) * N;
-#pragma unroll
-        for (int k = 0; k < kLossSlots; ++k) q[u][k] = i < n_items ? p[k] : 0.f;
-      }
+      float4 q[U];
 #pragma unroll
       for (int u = 0; u < U; ++u)
+        q[u] = *reinterpret_cast<const float4*>(P.partials + (size_t)min(i0 + u * kFinThreads, n_items - 1) * N);
 #pragma unroll
-        for (int k = 0; k < kLossSlots; ++k) acc[k] += (double)q[u][k];
+      for (int u = 0; u < U; ++u) {
+        const bool in = i0 + u * kFinThreads < n_items;
+        acc[0] += in ? (double)q[u].x : 0.0; acc[1] += in ? (double)q[u].y : 0.0;
+        acc[2] += in ? (double)q[u].z : 0.0; acc[3] += in ? (double)q[u].w : 0.0;
+      }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1)
@@ -1811,15 +1815,19 @@ int run_loss(const VslLossDesc* d, LossParams& P, const float* poses, const floa
   {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(d->B + 1);
-    cfg.blockDim = dim3(kFinThreads);
+    constexpr int kBig = V <= 2 ? 1024 : 512;
+    const bool big = P.item_begin[P.S] > kFinBigItems;
+    cfg.blockDim = dim3(big ? kBig : 256);
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    const cudaError_t e = cudaLaunchKernelEx(&cfg, loss_finalize_kernel<V>, P, poses, K_pyr, d->pose_format,
-                                             1.0f / d->loss_scale, losses, g_poses);
+    const cudaError_t e = big ? cudaLaunchKernelEx(&cfg, loss_finalize_kernel<V, kBig>, P, poses, K_pyr, d->pose_format,
+                                                   1.0f / d->loss_scale, losses, g_poses)
+                              : cudaLaunchKernelEx(&cfg, loss_finalize_kernel<V, 256>, P, poses, K_pyr, d->pose_format,
+                                                   1.0f / d->loss_scale, losses, g_poses);
     if (e != cudaSuccess) return (int)e;
   }
   return launch_status();
