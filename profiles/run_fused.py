@@ -7,7 +7,7 @@ if os.environ.get('VSL_LIB_PATH'):
     pass                                # _lib honours VSL_LIB_PATH itself
 elif os.environ.get('VSL_LIB_VARIANT'):   # timing experiments: profiles/build_variant.sh
     _lib.LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), '_exp', 'libvsl_%s.so' % os.environ['VSL_LIB_VARIANT'])
-CFG = {'cfg2': (32, 128, 416, 4, 2), 'cfg4': (64, 192, 256, 4, 1), 'cfg5': (64, 480, 640, 4, 2)}
+CFG = {'cfg2': (32, 128, 416, 4, 2), 'cfg3': (256, 128, 416, 4, 2), 'cfg4': (64, 192, 256, 4, 1), 'cfg5': (64, 480, 640, 4, 2)}
 name = sys.argv[1] if len(sys.argv) > 1 else 'cfg2'
 arith = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 steps = int(sys.argv[3]) if len(sys.argv) > 3 else 20

@@ -710,15 +710,15 @@ loss_fused_kernel(const LossParams P) {
 #endif
 }
 
-// grid = B + 1 blocks of T threads (256; 1024 -- 512 from three views up, for the shared-memory table -- when the
-// launch has more than kFinBigItems tile rows: every pass over the rows is a dependent round trip, and at B = 256 or at
-// 480 x 640 the 256-thread form makes ten of them).  Block b < B: pose gradients of batch element b (all views).  The tile partials
+// grid = B + 1 blocks of T threads (256; 1024 -- 512 from three views up, for the shared-memory table -- when an image
+// has more than kFinBigRows tile rows: every pass over the rows is a dependent round trip, and at 480 x 640 the
+// 256-thread form makes five of them per image and ten in the loss block).  Block b < B: pose gradients of batch element b (all views).  The tile partials
 // of (image, scale) are contiguous rows of N floats: warp w adds rows w, w + 8, ... with lane = column (one
 // coalesced request per row, every request independent), the 8 warp sums are combined in warp order.
 // Block B: the three loss scalars.  Every sum runs in a fixed order in double => deterministic.
 // Launched programmatically dependent on the fused kernel: what does not depend on it (K_s^-1 from the caller's
 // intrinsics) is done before griddepcontrol.wait, under the fused kernel's tail.
-constexpr int kFinBigItems = 8192;
+constexpr int kFinBigRows = 256;
 template <int V, int kFinThreads>
 __global__ void __launch_bounds__(kFinThreads)
 loss_finalize_kernel(const LossParams P, const float* __restrict__ poses, const float* __restrict__ K_pyr,
@@ -1816,7 +1816,12 @@ int run_loss(const VslLossDesc* d, LossParams& P, const float* poses, const floa
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(d->B + 1);
     constexpr int kBig = V <= 2 ? 1024 : 512;
-    const bool big = P.item_begin[P.S] > kFinBigItems;
+    // rows of ONE image over all scales: the image blocks want the wide form only when they would otherwise make
+    // several passes themselves (cfg5: 405 rows); at 72 rows per image (128 x 416) the wide block's larger
+    // reductions cost more than the loss block gains, whatever the batch (measured at B = 256: +5 us)
+    int rows_per_image = 0;
+    for (int sc = 0; sc < P.S; ++sc) rows_per_image += P.bands[sc] * P.strips[sc];
+    const bool big = rows_per_image > kFinBigRows;
     cfg.blockDim = dim3(big ? kBig : 256);
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
