@@ -263,6 +263,9 @@ def quick_config(name, dev, rank, steps=40, warmup=5, extra_flags=None, note=Non
     import torch
     from tf_depth_estimation_b200 import _lib, ops, synth
     try:
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()      # the larger shapes allocate GBs: start from the driver's pool, not from cached fragments
         c = CONFIGS[name]
         B, H, W, S, V = (c[k] for k in 'BHWSV')
         flags = ops.LossFlags(num_scales=S, **dict(c['flags'], **(extra_flags or {})))
